@@ -1,0 +1,745 @@
+/* oracle/hm_oracle.c
+ *
+ * TEST INFRASTRUCTURE ONLY.  A plain-C, CPU restatement of the data-parallel inter-search
+ * hot path of the HM-16.2 HEVC reference encoder.  It is the checker
+ * the CUDA path (libhmgpu) is compared against; nothing in the product path links, loads
+ * or calls it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may use it.
+ *
+ * Parity status: PINNED.  The reference has no golden vectors of its own, so
+ * every function below is checked against the real reference compiled from /root/reference
+ * (oracle/_ref/libhmref.so via oracle/ref_harness.cpp) by tests/test_oracle_vs_ref.py, and
+ * against the golden vectors generated from that same library (tests/golden/, made by
+ * tests/golden/make_golden.py).
+ *
+ * Written from the behaviour of the reference, not from its text: each function cites the
+ * reference file:line whose results it must reproduce bit-for-bit.
+ */
+#include "hm_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+
+static int iabs(int v) { return v < 0 ? -v : v; }
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* =====================================================================================
+ * Distortion family
+ * ===================================================================================== */
+
+/* SAD of a w x h block.
+ * Follows TComRdCost.cpp:465-964 (xGetSAD, xGetSAD4..64, xGetSAD12/24/48):
+ *  - the width-specialised functions visit rows 0, 2^s, 2*2^s, ... (s = iSubShift), then
+ *    scale the sum by << s, then >> (bitDepth-8)  (DISTORTION_PRECISION_ADJUSTMENT,
+ *    TypeDef.h:266-270);
+ *  - the generic xGetSAD (:465-491) ignores iSubShift entirely (generic != 0 here).
+ * Which one is dispatched is decided by setDistParam (TComRdCost.cpp:294-396). */
+uint32_t hmo_sad(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                 int w, int h, int sub_shift, int bit_depth, int generic)
+{
+  uint32_t sum = 0;
+  const int step = generic ? 1 : (1 << sub_shift);
+  for (int y = 0; y < h; y += step)
+    for (int x = 0; x < w; x++)
+      sum += (uint32_t)iabs((int)org[y * org_stride + x] - (int)cur[y * cur_stride + x]);
+  if (!generic) sum <<= sub_shift;
+  return sum >> (bit_depth - 8);
+}
+
+/* In-place 1-D Hadamard of length n (n = 2, 4, 8) with stride `st` over int32 data. */
+static void hadamard1d(int32_t* v, int n, int st)
+{
+  for (int len = 1; len < n; len <<= 1)
+    for (int i = 0; i < n; i += 2 * len)
+      for (int j = i; j < i + len; j++)
+      {
+        const int32_t a = v[j * st], b = v[(j + len) * st];
+        v[j * st] = a + b;
+        v[(j + len) * st] = a - b;
+      }
+}
+
+/* Sum of |H d H^T| over one n x n tile.  The reference's butterflies (TComRdCost.cpp:
+ * 1321-1534) produce the 2-D Hadamard coefficients in a permuted order with some signs
+ * flipped; the sum of absolute values is invariant to both, so a textbook Hadamard is
+ * an exact restatement.  Rounding per tile: 8x8 (s+2)>>2 (:1531), 4x4 (s+1)>>1 (:1434),
+ * 2x2 none (:1341). */
+static uint32_t had_tile(const int16_t* org, int os, const int16_t* cur, int cs, int n)
+{
+  int32_t d[64];
+  for (int y = 0; y < n; y++)
+    for (int x = 0; x < n; x++)
+      d[y * n + x] = (int32_t)org[y * os + x] - (int32_t)cur[y * cs + x];
+  for (int y = 0; y < n; y++) hadamard1d(d + y * n, n, 1);
+  for (int x = 0; x < n; x++) hadamard1d(d + x, n, n);
+  uint32_t s = 0;
+  for (int i = 0; i < n * n; i++) s += (uint32_t)iabs(d[i]);
+  if (n == 8) return (s + 2) >> 2;
+  if (n == 4) return (s + 1) >> 1;
+  return s;
+}
+
+/* SATD.  Follows xGetHADs (TComRdCost.cpp:1537-1604) / calcHAD (:398-431): 8x8 tiles iff
+ * both dimensions are multiples of 8, else 4x4 tiles, else 2x2; per-tile rounding before
+ * the sum; total >> (bitDepth-8). */
+uint32_t hmo_hads(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                  int w, int h, int bit_depth)
+{
+  int n;
+  if ((w % 8) == 0 && (h % 8) == 0) n = 8;
+  else if ((w % 4) == 0 && (h % 4) == 0) n = 4;
+  else n = 2;
+  uint32_t sum = 0;
+  for (int y = 0; y < h; y += n)
+    for (int x = 0; x < w; x += n)
+      sum += had_tile(org + y * org_stride + x, org_stride, cur + y * cur_stride + x, cur_stride, n);
+  return sum >> (bit_depth - 8);
+}
+
+/* SSE.  Follows xGetSSE* (TComRdCost.cpp:970-1315): every squared term is shifted by
+ * 2*(bitDepth-8) before accumulation into a uint32. */
+uint32_t hmo_sse(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                 int w, int h, int bit_depth)
+{
+  const int sh = (bit_depth - 8) << 1;
+  uint32_t sum = 0;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int32_t t = (int32_t)org[y * org_stride + x] - (int32_t)cur[y * cur_stride + x];
+      sum += (uint32_t)((t * t) >> sh);
+    }
+  return sum;
+}
+
+/* =====================================================================================
+ * MV rate cost
+ * ===================================================================================== */
+
+/* Exp-Golomb length of a signed MV difference.  TComRdCost::xGetComponentBits
+ * (TComRdCost.cpp:278-292): 2*floor(log2(v<=0 ? -2v+1 : 2v)) + 1. */
+uint32_t hmo_component_bits(int v)
+{
+  uint32_t t = (v <= 0) ? (uint32_t)((-v << 1) + 1) : (uint32_t)(v << 1);
+  uint32_t len = 1;
+  while (t != 1) { t >>= 1; len += 2; }
+  return len;
+}
+
+/* TComRdCost::getBits (TComRdCost.h:184-188). */
+uint32_t hmo_mv_bits(int pred_x, int pred_y, int scale, int x, int y)
+{
+  return hmo_component_bits((x << scale) - pred_x) + hmo_component_bits((y << scale) - pred_y);
+}
+
+/* TComRdCost::getCost(x,y) (TComRdCost.h:171-178): uint32 wrap-around product >> 16. */
+uint32_t hmo_mv_cost(uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y)
+{
+  return (uint32_t)(ui_cost * hmo_mv_bits(pred_x, pred_y, scale, x, y)) >> 16;
+}
+
+/* TComRdCost::getCost(bits) (TComRdCost.h:182). */
+uint32_t hmo_bits_cost(uint32_t ui_cost, uint32_t bits) { return (uint32_t)(ui_cost * bits) >> 16; }
+
+/* m_uiLambdaMotionSAD[0] = floor(65536*sqrt(lambda)) (TComRdCost.cpp:196-209), selected by
+ * getMotionCost(true,0,false) (TComRdCost.h:165). */
+uint32_t hmo_lambda_to_cost(double lambda) { return (uint32_t)floor(65536.0 * sqrt(lambda)); }
+
+/* calcRdCost(bits, dist, false, DF_SAD) in COST_STANDARD_LOSSY mode (TComRdCost.cpp:62-122):
+ * floor(dist + floor(bits*lambdaSAD + 0.5)/65536) with lambdaSAD the uint32 above. */
+double hmo_calc_rd_cost_sad(double lambda, uint32_t bits, uint32_t dist)
+{
+  const double l = (double)hmo_lambda_to_cost(lambda);
+  return floor((double)dist + floor((double)bits * l + 0.5) / 65536.0);
+}
+
+/* =====================================================================================
+ * Search-window derivation
+ * ===================================================================================== */
+
+/* Bounds of TComDataCU::clipMv (TComDataCU.cpp:2917-2929): relative to the CU origin,
+ * CTU size 64, offset 8, in quarter-pel. */
+void hmo_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int bounds[4])
+{
+  bounds[0] = (-64 - 8 - cu_x + 1) * 4;
+  bounds[1] = (pic_w + 8 - cu_x - 1) * 4;
+  bounds[2] = (-64 - 8 - cu_y + 1) * 4;
+  bounds[3] = (pic_h + 8 - cu_y - 1) * 4;
+}
+
+static void clip_with(const int bd[4], int mv[2])
+{
+  mv[0] = imin(bd[1], imax(bd[0], mv[0]));
+  mv[1] = imin(bd[3], imax(bd[2], mv[1]));
+}
+
+void hmo_clip_mv(int pic_w, int pic_h, int cu_x, int cu_y, int mv[2])
+{
+  int bd[4];
+  hmo_clip_bounds(pic_w, pic_h, cu_x, cu_y, bd);
+  clip_with(bd, mv);
+}
+
+/* int16 wrap + arithmetic shift, as TComMv stores Short (TComMv.h:53-55,112-124). */
+static int s16(int v) { return (int)(int16_t)v; }
+
+static void search_range_with(const int bd[4], int pred_x, int pred_y, int srch_rng, int ltrb[4])
+{
+  int p[2] = { pred_x, pred_y };
+  clip_with(bd, p);
+  int lt[2] = { s16(p[0] - (srch_rng << 2)), s16(p[1] - (srch_rng << 2)) };
+  int rb[2] = { s16(p[0] + (srch_rng << 2)), s16(p[1] + (srch_rng << 2)) };
+  clip_with(bd, lt);
+  clip_with(bd, rb);
+  ltrb[0] = lt[0] >> 2; ltrb[1] = lt[1] >> 2; ltrb[2] = rb[0] >> 2; ltrb[3] = rb[1] >> 2;
+}
+
+/* TEncSearch::xSetSearchRange (TEncSearch.cpp:3911-3927). */
+void hmo_set_search_range(int pic_w, int pic_h, int cu_x, int cu_y, int pred_x, int pred_y,
+                          int srch_rng, int ltrb[4])
+{
+  int bd[4];
+  hmo_clip_bounds(pic_w, pic_h, cu_x, cu_y, bd);
+  search_range_with(bd, pred_x, pred_y, srch_rng, ltrb);
+}
+
+/* =====================================================================================
+ * Interpolation
+ * ===================================================================================== */
+
+/* Tap tables: TComInterpolationFilter.cpp:57-75 (these are the H.265 8.5.3.3.3 tables). */
+static const int kLuma[4][8] = {
+  {  0, 0,   0, 64,  0,   0, 0,  0 },
+  { -1, 4, -10, 58, 17,  -5, 1,  0 },
+  { -1, 4, -11, 40, 40, -11, 4, -1 },
+  {  0, 1,  -5, 17, 58, -10, 4, -1 } };
+static const int kChroma[8][4] = {
+  {  0, 64,  0,  0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+  { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+
+#define IF_PREC 14
+#define IF_FILT 6
+#define IF_OFFS (1 << (IF_PREC - 1))
+
+/* One separable pass.  Reproduces filter<N,isVertical,isFirst,isLast> and filterCopy
+ * (TComInterpolationFilter.cpp:94-251) including the int16 store of the un-clipped value. */
+static void filter_pass(int ntaps, const int* c, int frac_is_zero, int vertical,
+                        const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                        int w, int h, int is_first, int is_last, int bit_depth)
+{
+  const int head = imax(2, IF_PREC - bit_depth);
+  const int max_val = (1 << bit_depth) - 1;
+  if (frac_is_zero)
+  {
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++)
+      {
+        const int v = src[y * src_stride + x];
+        int o;
+        if (is_first == is_last) o = v;                                   /* :98-110 */
+        else if (is_first) o = (int16_t)(v << head) - IF_OFFS;            /* :111-126 */
+        else                                                              /* :127-147 */
+        {
+          o = (int16_t)((v + IF_OFFS + (1 << (head - 1))) >> head);
+          o = imin(max_val, imax(0, o));
+        }
+        dst[y * dst_stride + x] = (int16_t)o;
+      }
+    return;
+  }
+  const int cs = vertical ? src_stride : 1;
+  int shift = IF_FILT, offset;
+  if (is_last)
+  {
+    shift += is_first ? 0 : head;
+    offset = 1 << (shift - 1);
+    offset += is_first ? 0 : (IF_OFFS << IF_FILT);
+  }
+  else
+  {
+    shift -= is_first ? head : 0;
+    offset = is_first ? -(IF_OFFS << shift) : 0;
+  }
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int16_t* p = src + y * src_stride + x - (ntaps / 2 - 1) * cs;
+      int sum = 0;
+      for (int k = 0; k < ntaps; k++) sum += p[k * cs] * c[k];
+      int16_t val = (int16_t)((sum + offset) >> shift);
+      if (is_last) { if (val < 0) val = 0; if (val > max_val) val = (int16_t)max_val; }
+      dst[y * dst_stride + x] = val;
+    }
+}
+
+/* Public filterHor (TComInterpolationFilter.cpp:331-350); chroma frac is in 1/8 units (4:2:0). */
+void hmo_filter_hor(int chroma, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                    int w, int h, int frac, int is_last, int bit_depth)
+{
+  filter_pass(chroma ? 4 : 8, chroma ? kChroma[frac] : kLuma[frac], frac == 0, 0,
+              src, src_stride, dst, dst_stride, w, h, 1, is_last, bit_depth);
+}
+
+/* Public filterVer (TComInterpolationFilter.cpp:364-381). */
+void hmo_filter_ver(int chroma, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                    int w, int h, int frac, int is_first, int is_last, int bit_depth)
+{
+  filter_pass(chroma ? 4 : 8, chroma ? kChroma[frac] : kLuma[frac], frac == 0, 1,
+              src, src_stride, dst, dst_stride, w, h, is_first, is_last, bit_depth);
+}
+
+/* Replicate padding of TComPicYuv::extendPicBorder (TComPicYuv.cpp:171-215); margin is
+ * g_uiMaxCUWidth + 16 = 80 luma samples (TComPicYuv.cpp:87-88).  dst is (w+2m) x (h+2m). */
+void hmo_extend_border(const int16_t* src, int w, int h, int margin, int16_t* dst)
+{
+  const int pw = w + 2 * margin, ph = h + 2 * margin;
+  for (int y = 0; y < ph; y++)
+  {
+    const int sy = imin(h - 1, imax(0, y - margin));
+    for (int x = 0; x < pw; x++)
+    {
+      const int sx = imin(w - 1, imax(0, x - margin));
+      dst[y * pw + x] = src[sy * w + sx];
+    }
+  }
+}
+
+/* One interpolated luma block at quarter-pel phase (fx, fy) with the ME two-pass order
+ * (horizontal first, not last -> vertical, last), which is what xExtDIFUpSamplingH/Q
+ * (TEncSearch.cpp:5565-5766) build, and which equals the uni-prediction MC output
+ * (TComPrediction.cpp:680-697). `ref` = top-left integer sample. */
+static void interp_block_luma(const int16_t* ref, int ref_stride, int fx, int fy, int w, int h,
+                              int bit_depth, int16_t* dst, int dst_stride)
+{
+  int16_t* tmp = (int16_t*)malloc(sizeof(int16_t) * (size_t)w * (size_t)(h + 8));
+  hmo_filter_hor(0, ref - 3 * ref_stride, ref_stride, tmp, w, w, h + 7, fx, 0, bit_depth);
+  hmo_filter_ver(0, tmp + 3 * w, w, dst, dst_stride, w, h, fy, 0, 1, bit_depth);
+  free(tmp);
+}
+
+void hmo_phase_planes(const int16_t* padded, int pw, int ph, int bit_depth, int16_t* planes)
+{
+  /* clamp-extended copy so that every 8-tap support is readable */
+  const int e = 4, ew = pw + 2 * e, eh = ph + 2 * e;
+  int16_t* ext = (int16_t*)malloc(sizeof(int16_t) * (size_t)ew * (size_t)eh);
+  for (int y = 0; y < eh; y++)
+    for (int x = 0; x < ew; x++)
+      ext[y * ew + x] = padded[imin(ph - 1, imax(0, y - e)) * pw + imin(pw - 1, imax(0, x - e))];
+  for (int fy = 0; fy < 4; fy++)
+    for (int fx = 0; fx < 4; fx++)
+      interp_block_luma(ext + e * ew + e, ew, fx, fy, pw, ph, bit_depth,
+                        planes + (size_t)(fy * 4 + fx) * (size_t)pw * (size_t)ph, pw);
+  free(ext);
+}
+
+/* =====================================================================================
+ * Motion compensation
+ * ===================================================================================== */
+
+/* TComPrediction::xPredInterBlk (TComPrediction.cpp:660-698): one component of one block.
+ * Luma mv in quarter-pel; chroma (4:2:0) mv in eighth-pel; w,h in component samples.
+ * bi != 0 keeps the 14-bit intermediate (isLast = !bi). */
+void hmo_pred_inter_blk(int chroma, const int16_t* ref, int ref_stride, int mvx, int mvy,
+                        int w, int h, int bi, int bit_depth, int16_t* dst, int dst_stride)
+{
+  const int sh = chroma ? 3 : 2, ntaps = chroma ? 4 : 8, half = ntaps >> 1;
+  const int16_t* r = ref + (mvx >> sh) + (mvy >> sh) * ref_stride;
+  const int fx = mvx & ((1 << sh) - 1), fy = mvy & ((1 << sh) - 1);
+  if (fy == 0) hmo_filter_hor(chroma, r, ref_stride, dst, dst_stride, w, h, fx, !bi, bit_depth);
+  else if (fx == 0) hmo_filter_ver(chroma, r, ref_stride, dst, dst_stride, w, h, fy, 1, !bi, bit_depth);
+  else
+  {
+    int16_t* tmp = (int16_t*)malloc(sizeof(int16_t) * (size_t)w * (size_t)(h + ntaps));
+    hmo_filter_hor(chroma, r - (half - 1) * ref_stride, ref_stride, tmp, w, w, h + ntaps - 1, fx, 0, bit_depth);
+    hmo_filter_ver(chroma, tmp + (half - 1) * w, w, dst, dst_stride, w, h, fy, 0, !bi, bit_depth);
+    free(tmp);
+  }
+}
+
+/* TComYuv::addAvg (TComYuv.cpp:336-392): bi-prediction average of two 14-bit predictions. */
+void hmo_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1, int w, int h,
+                 int bit_depth, int16_t* dst, int dst_stride)
+{
+  const int shift = imax(2, IF_PREC - bit_depth) + 1;
+  const int offset = (1 << (shift - 1)) + 2 * IF_OFFS;
+  const int max_val = (1 << bit_depth) - 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int v = (s0[y * st0 + x] + s1[y * st1 + x] + offset) >> shift;
+      dst[y * dst_stride + x] = (int16_t)imin(max_val, imax(0, v));
+    }
+}
+
+/* Bi-pred key pattern 2*org - otherPred, unclipped (TComYuv::removeHighFreq,
+ * TComYuv.cpp:393-424 with DISABLING_CLIP_FOR_BIPREDME, TypeDef.h:117). */
+void hmo_bipred_key(const int16_t* org, int org_stride, const int16_t* other_pred, int pred_stride,
+                    int w, int h, int16_t* dst, int dst_stride)
+{
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      dst[y * dst_stride + x] = (int16_t)(2 * org[y * org_stride + x] - other_pred[y * pred_stride + x]);
+}
+
+/* =====================================================================================
+ * Integer searches
+ * ===================================================================================== */
+
+static int sub_shift_for(const hmo_search_t* s)
+{
+  /* FEN: sub-sampled SAD when rows > 8 (TEncSearch.cpp:347-353, 3950-3956) */
+  return (s->fen && s->h > 8) ? 1 : 0;
+}
+
+static uint32_t int_cost(hmo_search_t* s, int x, int y)
+{
+  s->n_cand++;
+  /* integer ME always dispatches a width-specialised SAD (AMP override, TComRdCost.cpp:320-333) */
+  const int generic = !(s->w == 4 || s->w == 8 || s->w == 16 || s->w == 32 || s->w == 64 ||
+                        s->w == 12 || s->w == 24 || s->w == 48);
+  return hmo_sad(s->org, s->org_stride, s->ref + y * s->ref_stride + x, s->ref_stride,
+                 s->w, s->h, sub_shift_for(s), s->bit_depth, generic)
+       + hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 2, x, y);
+}
+
+/* Exhaustive raster search, first strict minimum in (y outer, x inner) order.
+ * TEncSearch::xPatternSearch (TEncSearch.cpp:3932-3989). */
+void hmo_pattern_search(hmo_search_t* s)
+{
+  uint32_t best = UINT_MAX;
+  int bx = 0, by = 0;
+  s->n_cand = 0;
+  for (int y = s->t; y <= s->b; y++)
+    for (int x = s->l; x <= s->r; x++)
+    {
+      const uint32_t c = int_cost(s, x, y);
+      if (c < best) { best = c; bx = x; by = y; }
+    }
+  s->mv_x = bx; s->mv_y = by;
+  s->sad = best - hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 2, bx, by);
+}
+
+/* ---- TZ search --------------------------------------------------------------------- */
+
+typedef struct
+{
+  uint32_t best_cost;
+  int best_x, best_y;
+  unsigned best_dist, best_round;
+  int point_nr;
+} tz_state;
+
+/* xTZSearchHelp (TEncSearch.cpp:333-424), non-selective branch: strict '<' update. */
+static void tz_try(hmo_search_t* s, tz_state* z, int x, int y, int point_nr, unsigned dist)
+{
+  const uint32_t c = int_cost(s, x, y);
+  if (c < z->best_cost)
+  {
+    z->best_cost = c; z->best_x = x; z->best_y = y;
+    z->best_dist = dist; z->best_round = 0; z->point_nr = point_nr;
+  }
+}
+
+/* xTZ8PointDiamondSearch (TEncSearch.cpp:616-791).  The point emission order and the
+ * per-point window tests are what matter; the "fully inside" fast path (:668-679, :721-738)
+ * emits the same points in the same order as the per-point tests, so one code path serves. */
+static void tz_diamond(hmo_search_t* s, tz_state* z, const int win[4], int cx, int cy, int dist)
+{
+  const int L = win[0], T = win[1], R = win[2], B = win[3];
+  const int top = cy - dist, bot = cy + dist, lef = cx - dist, rig = cx + dist;
+  z->best_round += 1;
+  if (dist == 1)
+  {
+    if (top >= T) tz_try(s, z, cx, top, 2, dist);
+    if (lef >= L) tz_try(s, z, lef, cy, 4, dist);
+    if (rig <= R) tz_try(s, z, rig, cy, 5, dist);
+    if (bot <= B) tz_try(s, z, cx, bot, 7, dist);
+  }
+  else if (dist <= 8)
+  {
+    const int h = dist >> 1;
+    const int top2 = cy - h, bot2 = cy + h, lef2 = cx - h, rig2 = cx + h;
+    if (top >= T) tz_try(s, z, cx, top, 2, dist);
+    if (top2 >= T)
+    {
+      if (lef2 >= L) tz_try(s, z, lef2, top2, 1, h);
+      if (rig2 <= R) tz_try(s, z, rig2, top2, 3, h);
+    }
+    if (lef >= L) tz_try(s, z, lef, cy, 4, dist);
+    if (rig <= R) tz_try(s, z, rig, cy, 5, dist);
+    if (bot2 <= B)
+    {
+      if (lef2 >= L) tz_try(s, z, lef2, bot2, 6, h);
+      if (rig2 <= R) tz_try(s, z, rig2, bot2, 8, h);
+    }
+    if (bot <= B) tz_try(s, z, cx, bot, 7, dist);
+  }
+  else
+  {
+    if (top >= T) tz_try(s, z, cx, top, 0, dist);
+    if (lef >= L) tz_try(s, z, lef, cy, 0, dist);
+    if (rig <= R) tz_try(s, z, rig, cy, 0, dist);
+    if (bot <= B) tz_try(s, z, cx, bot, 0, dist);
+    for (int i = 1; i < 4; i++)
+    {
+      const int q = (dist >> 2) * i;
+      const int yt = top + q, yb = bot - q, xl = cx - q, xr = cx + q;
+      if (yt >= T)
+      {
+        if (xl >= L) tz_try(s, z, xl, yt, 0, dist);
+        if (xr <= R) tz_try(s, z, xr, yt, 0, dist);
+      }
+      if (yb <= B)
+      {
+        if (xl >= L) tz_try(s, z, xl, yb, 0, dist);
+        if (xr <= R) tz_try(s, z, xr, yb, 0, dist);
+      }
+    }
+  }
+}
+
+/* xTZ2PointSearch (TEncSearch.cpp:429-557): the two untested neighbours of the best point,
+ * both relative to the best position at entry. */
+static void tz_two_point(hmo_search_t* s, tz_state* z, const int win[4])
+{
+  const int L = win[0], T = win[1], R = win[2], B = win[3];
+  const int x = z->best_x, y = z->best_y;
+  /* per point-nr (1..8 = position of the best point on the last diamond): the two
+   * neighbours not yet tested, in the reference's order.  Each is evaluated iff the
+   * coordinate(s) that moved stay inside the window on the side they moved towards. */
+  static const int kTwo[9][2][2] = {
+    { {0,0}, {0,0} },
+    { {-1, 0}, { 0,-1} }, { {-1,-1}, { 1,-1} }, { { 0,-1}, { 1, 0} },
+    { {-1, 1}, {-1,-1} }, { { 1,-1}, { 1, 1} },
+    { {-1, 0}, { 0, 1} }, { {-1, 1}, { 1, 1} }, { { 1, 0}, { 0, 1} } };
+  if (z->point_nr < 1 || z->point_nr > 8) return;      /* the reference asserts here (:551-555) */
+  const int nr = z->point_nr;
+  for (int i = 0; i < 2; i++)
+  {
+    const int dx = kTwo[nr][i][0], dy = kTwo[nr][i][1];
+    if (dx < 0 && x + dx < L) continue;
+    if (dx > 0 && x + dx > R) continue;
+    if (dy < 0 && y + dy < T) continue;
+    if (dy > 0 && y + dy > B) continue;
+    tz_try(s, z, x + dx, y + dy, 0, 2);
+  }
+}
+
+/* TEncSearch::xTZSearch (TEncSearch.cpp:4027-4228) with TZ_SEARCH_CONFIGURATION (:298-314):
+ * diamond first search (stop after 3 rounds without improvement), zero-MV test, optional
+ * 2Nx2N integer-MV test + window re-centre (local bounds only),
+ * 2-point fill, raster step 5 when best distance > 5, star refinement. */
+void hmo_tz_search(hmo_search_t* s)
+{
+  const int raster = 5;
+  int bd[4];
+  hmo_clip_bounds(s->pic_w, s->pic_h, s->cu_x, s->cu_y, bd);
+  const int win[4] = { s->l, s->t, s->r, s->b };          /* what the pattern helpers see */
+  int rwin[4] = { s->l, s->t, s->r, s->b };               /* what the raster scan sees */
+  tz_state z; memset(&z, 0, sizeof z); z.best_cost = UINT_MAX;
+  s->n_cand = 0;
+
+  int st[2] = { s->start_x, s->start_y };
+  clip_with(bd, st);
+  tz_try(s, &z, st[0] >> 2, st[1] >> 2, 0, 0);             /* :4054 */
+  tz_try(s, &z, 0, 0, 0, 0);                               /* :4071 */
+  if (s->has_2nx2n)                                        /* :4074-4093 */
+  {
+    int m[2] = { s16(s->i2n_x << 2), s16(s->i2n_y << 2) };
+    clip_with(bd, m);
+    tz_try(s, &z, m[0] >> 2, m[1] >> 2, 0, 0);
+    search_range_with(bd, s16(z.best_x << 2), s16(z.best_y << 2), s->search_range, rwin);
+  }
+
+  int cx = z.best_x, cy = z.best_y;
+  for (int d = 1; d <= s->search_range; d *= 2)            /* :4101-4116 */
+  {
+    tz_diamond(s, &z, win, cx, cy, d);
+    if (z.best_round >= 3) break;
+  }
+  if (z.best_dist == 1)                                    /* :4137-4141 */
+  {
+    z.best_dist = 0;
+    tz_two_point(s, &z, win);
+  }
+  if ((int)z.best_dist > raster)                           /* :4144-4154 */
+  {
+    z.best_dist = raster;
+    for (int y = rwin[1]; y <= rwin[3]; y += raster)
+      for (int x = rwin[0]; x <= rwin[2]; x += raster)
+        tz_try(s, &z, x, y, 0, raster);
+  }
+  while (z.best_dist > 0)                                  /* :4189-4223 */
+  {
+    cx = z.best_x; cy = z.best_y;
+    z.best_dist = 0; z.point_nr = 0;
+    for (int d = 1; d < s->search_range + 1; d *= 2) tz_diamond(s, &z, win, cx, cy, d);
+    if (z.best_dist == 1)
+    {
+      z.best_dist = 0;
+      if (z.point_nr != 0) tz_two_point(s, &z, win);
+    }
+  }
+  s->mv_x = z.best_x; s->mv_y = z.best_y;
+  s->sad = z.best_cost - hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 2, z.best_x, z.best_y);
+}
+
+/* =====================================================================================
+ * Fractional refinement
+ * ===================================================================================== */
+
+/* candidate orders of s_acMvRefineH / s_acMvRefineQ (TEncSearch.cpp:51-75) */
+static const int kRefineH[9][2] = { {0,0},{0,-1},{0,1},{-1,0},{1,0},{-1,-1},{1,-1},{-1,1},{1,1} };
+static const int kRefineQ[9][2] = { {0,0},{0,-1},{0,1},{-1,-1},{1,-1},{-1,0},{1,0},{-1,1},{1,1} };
+
+/* distortion of the PU against the reference sampled at quarter-pel MV (qx,qy) */
+static uint32_t frac_dist(const hmo_search_t* s, int qx, int qy, int16_t* scratch)
+{
+  const int16_t* r = s->ref + (qx >> 2) + (qy >> 2) * s->ref_stride;
+  interp_block_luma(r, s->ref_stride, qx & 3, qy & 3, s->w, s->h, s->bit_depth, scratch, s->w);
+  if (s->hadme && !s->lossless)
+    return hmo_hads(s->org, s->org_stride, scratch, s->w, s->w, s->h, s->bit_depth);
+  /* SADS by width index; 12/24/48 take the AMP SAD (TComRdCost.cpp:340-381); no sub-sampling */
+  const int generic = !(s->w == 4 || s->w == 8 || s->w == 16 || s->w == 32 || s->w == 64 ||
+                        s->w == 12 || s->w == 24 || s->w == 48);
+  return hmo_sad(s->org, s->org_stride, scratch, s->w, s->w, s->h, 0, s->bit_depth, generic);
+}
+
+/* xPatternSearchFracDIF + xPatternRefinement (TEncSearch.cpp:4386-4422, 799-852).
+ * Half-pel: 9 candidates (table H) around the integer MV, MV cost at scale 1 on
+ * (2*int + h); quarter-pel: 9 candidates (table Q) around the best half, scale 0 on
+ * (4*int + 2*half + q).  First strict minimum in table order. */
+void hmo_frac_search(hmo_search_t* s)
+{
+  int16_t* scratch = (int16_t*)malloc(sizeof(int16_t) * (size_t)s->w * (size_t)s->h);
+  uint32_t best = UINT_MAX; int bi = 0;
+  for (int i = 0; i < 9; i++)
+  {
+    const int hx = kRefineH[i][0], hy = kRefineH[i][1];
+    uint32_t c = frac_dist(s, 4 * s->mv_x + 2 * hx, 4 * s->mv_y + 2 * hy, scratch);
+    c += hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 1, 2 * s->mv_x + hx, 2 * s->mv_y + hy);
+    s->n_cand++;
+    if (c < best) { best = c; bi = i; }
+  }
+  s->half_x = kRefineH[bi][0]; s->half_y = kRefineH[bi][1];
+  best = UINT_MAX; bi = 0;
+  for (int i = 0; i < 9; i++)
+  {
+    const int qx = 4 * s->mv_x + 2 * s->half_x + kRefineQ[i][0];
+    const int qy = 4 * s->mv_y + 2 * s->half_y + kRefineQ[i][1];
+    uint32_t c = frac_dist(s, qx, qy, scratch);
+    c += hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 0, qx, qy);
+    s->n_cand++;
+    if (c < best) { best = c; bi = i; }
+  }
+  s->qter_x = kRefineQ[bi][0]; s->qter_y = kRefineQ[bi][1];
+  s->frac_cost = best;
+  free(scratch);
+}
+
+/* Tail of TEncSearch::xMotionEstimation (TEncSearch.cpp:3870-3905): integer search, then
+ * fractional search, final MV = (int<<2) + (half<<1) + qter, and
+ * cost = floor(w*(cost - getCost(mvBits))) + getCost(bits+mvBits) in double, w = 0.5 for bi. */
+void hmo_motion_estimation(hmo_search_t* s, int full_search, int bi, uint32_t* io_bits,
+                           int out_mv[2], uint32_t* out_cost)
+{
+  uint32_t n = 0;
+  if (full_search || bi) hmo_pattern_search(s); else hmo_tz_search(s);
+  n = s->n_cand;
+  s->n_cand = 0;
+  hmo_frac_search(s);
+  s->n_cand += n;
+  out_mv[0] = s16(s16(s->mv_x << 2) + s16(s->half_x << 1) + s->qter_x);
+  out_mv[1] = s16(s16(s->mv_y << 2) + s16(s->half_y << 1) + s->qter_y);
+  const uint32_t mv_bits = hmo_mv_bits(s->pred_x, s->pred_y, 0, out_mv[0], out_mv[1]);
+  *io_bits += mv_bits;
+  const double wgt = bi ? 0.5 : 1.0;
+  *out_cost = (uint32_t)(floor(wgt * ((double)s->frac_cost - (double)hmo_bits_cost(s->ui_cost, mv_bits)))
+                         + (double)hmo_bits_cost(s->ui_cost, *io_bits));
+}
+
+/* =====================================================================================
+ * Forward transform + scalar quantiser
+ * ===================================================================================== */
+
+/* The 31 distinct magnitudes of the HEVC core transform (H.265 8.6.4.2, first column of the
+ * 32x32 matrix); the reference carries the same numbers as g_aiT4/8/16/32 (TComRom.cpp:456+,
+ * 6-bit set).  C[j] ~ 64*sqrt(2)*cos(j*pi/64). */
+static const int kDctC[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                               61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+static const int kDst4[4][4] = { { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };
+
+static int dct_coef(int n, int k, int i)
+{
+  if (k == 0) return 64;
+  int m = ((k * (32 / n)) * (2 * i + 1)) % 128;   /* angle in units of pi/64 */
+  if (m > 64) m = 128 - m;
+  return (m > 32) ? -kDctC[64 - m] : kDctC[m];
+}
+
+void hmo_transform_matrix(int n, int32_t* m)
+{
+  for (int k = 0; k < n; k++)
+    for (int i = 0; i < n; i++)
+      m[k * n + i] = dct_coef(n, k, i);
+}
+
+/* One 1-D stage over `line` rows of length n: dst[k*line + j] = (sum_i M[k][i]*src[j*n+i]
+ * + rnd) >> shift.  The reference's partialButterfly4/8/16/32 (TComTrQuant.cpp:387-758)
+ * factor exactly this integer sum (no intermediate rounding), fastForwardDst (:413-435)
+ * is the same with the DST matrix. */
+static void fwd_stage(const int32_t* src, int32_t* dst, int n, int line, int shift, int use_dst)
+{
+  const int32_t rnd = shift > 0 ? (1 << (shift - 1)) : 0;
+  for (int j = 0; j < line; j++)
+    for (int k = 0; k < n; k++)
+    {
+      int32_t acc = 0;
+      for (int i = 0; i < n; i++)
+        acc += (use_dst ? kDst4[k][i] : dct_coef(n, k, i)) * src[j * n + i];
+      dst[k * line + j] = (acc + rnd) >> shift;
+    }
+}
+
+/* xTrMxN (TComTrQuant.cpp:836-885): rows then columns; shift1 = log2(w) + bitDepth + 6 - 15,
+ * shift2 = log2(h) + 6.  DST only for 4x4 with useDST. */
+void hmo_fwd_transform(int bit_depth, const int32_t* block, int32_t* coeff, int w, int h, int use_dst)
+{
+  int lw = 0, lh = 0;
+  while ((1 << lw) < w) lw++;
+  while ((1 << lh) < h) lh++;
+  const int shift1 = lw + bit_depth + 6 - 15, shift2 = lh + 6;
+  const int dst = use_dst && w == 4 && h == 4;
+  int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (size_t)w * (size_t)h);
+  fwd_stage(block, tmp, w, h, shift1, dst);
+  fwd_stage(tmp, coeff, h, w, shift2, dst);
+  free(tmp);
+}
+
+/* Scalar (non-RDOQ) quantiser, flat scaling: TComTrQuant::xQuant else-branch
+ * (TComTrQuant.cpp:1120-1199) without the sign-hiding post-pass.
+ * qbits = 14 + per + transformShift; add = (I ? 171 : 85) << (qbits-9). Returns absSum. */
+uint32_t hmo_quant(const int32_t* coef, int n_coef, int qp_per, int qp_rem, int transform_shift,
+                   int is_intra_slice, int32_t* level, int32_t* delta_u)
+{
+  static const int kScale[6] = { 26214, 23302, 20560, 18396, 16384, 14564 }; /* g_quantScales, TComRom.cpp:321 */
+  const int qbits = 14 + qp_per + transform_shift;
+  const int64_t add = (int64_t)(is_intra_slice ? 171 : 85) << (qbits - 9);
+  const int qbits8 = qbits - 8;
+  uint32_t abs_sum = 0;
+  for (int i = 0; i < n_coef; i++)
+  {
+    const int32_t c = coef[i];
+    const int64_t t = (int64_t)iabs(c) * kScale[qp_rem];
+    const int32_t q = (int32_t)((t + add) >> qbits);
+    if (delta_u) delta_u[i] = (int32_t)((t - ((int64_t)q << qbits)) >> qbits8);
+    abs_sum += (uint32_t)q;
+    int32_t v = c < 0 ? -q : q;
+    if (v < -32768) v = -32768;
+    if (v > 32767) v = 32767;
+    level[i] = v;
+  }
+  return abs_sum;
+}

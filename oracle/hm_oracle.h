@@ -1,0 +1,84 @@
+/* oracle/hm_oracle.h -- TEST INFRASTRUCTURE ONLY (see hm_oracle.c). */
+#ifndef HM_ORACLE_H
+#define HM_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- distortion family (a3, a4, a5) ---- */
+uint32_t hmo_sad(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                 int w, int h, int sub_shift, int bit_depth, int generic);
+uint32_t hmo_hads(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                  int w, int h, int bit_depth);
+uint32_t hmo_sse(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                 int w, int h, int bit_depth);
+
+/* ---- MV rate cost (a6) ---- */
+uint32_t hmo_component_bits(int v);
+uint32_t hmo_mv_bits(int pred_x, int pred_y, int scale, int x, int y);
+uint32_t hmo_mv_cost(uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y);
+uint32_t hmo_bits_cost(uint32_t ui_cost, uint32_t bits);
+uint32_t hmo_lambda_to_cost(double lambda);
+double   hmo_calc_rd_cost_sad(double lambda, uint32_t bits, uint32_t dist);
+
+/* ---- window derivation (a8) ---- */
+void hmo_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int bounds[4]); /* hmin,hmax,vmin,vmax (qpel) */
+void hmo_clip_mv(int pic_w, int pic_h, int cu_x, int cu_y, int mv[2]);
+void hmo_set_search_range(int pic_w, int pic_h, int cu_x, int cu_y, int pred_x, int pred_y,
+                          int srch_rng, int ltrb[4]);
+
+/* ---- interpolation (a14) and picture padding (a19) ---- */
+void hmo_filter_hor(int chroma, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                    int w, int h, int frac, int is_last, int bit_depth);
+void hmo_filter_ver(int chroma, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                    int w, int h, int frac, int is_first, int is_last, int bit_depth);
+void hmo_extend_border(const int16_t* src, int w, int h, int margin, int16_t* dst);
+/* 16 quarter-pel luma planes of a padded picture; planes[(v*4+h)] each pw*ph, valid where the
+ * 8-tap support is inside the padded picture (source reads are clamped elsewhere). */
+void hmo_phase_planes(const int16_t* padded, int pw, int ph, int bit_depth, int16_t* planes);
+
+/* ---- motion compensation (a15) ---- */
+void hmo_pred_inter_blk(int chroma, const int16_t* ref, int ref_stride, int mvx, int mvy,
+                        int w, int h, int bi, int bit_depth, int16_t* dst, int dst_stride);
+void hmo_add_avg(const int16_t* s0, int st0, const int16_t* s1, int st1, int w, int h,
+                 int bit_depth, int16_t* dst, int dst_stride);
+void hmo_bipred_key(const int16_t* org, int org_stride, const int16_t* other_pred, int pred_stride,
+                    int w, int h, int16_t* dst, int dst_stride);
+
+/* ---- searches (a9, a10, a12/a13, a7) ---- */
+typedef struct
+{
+  /* inputs */
+  const int16_t* org; int org_stride; int w, h;      /* key pattern */
+  const int16_t* ref; int ref_stride;                /* PU origin inside a padded plane */
+  int l, t, r, b;                                    /* integer search window */
+  uint32_t ui_cost; int pred_x, pred_y;              /* m_uiCost, predictor (qpel) */
+  int fen, hadme, lossless, bit_depth;
+  int pic_w, pic_h, cu_x, cu_y, search_range;        /* TZ only (clipMv / re-centre) */
+  int start_x, start_y;                              /* TZ start MV (qpel, = the MVP) */
+  int has_2nx2n, i2n_x, i2n_y;                       /* TZ optional integer 2Nx2N MV */
+  /* outputs */
+  int mv_x, mv_y; uint32_t sad;                      /* integer search result */
+  int half_x, half_y, qter_x, qter_y; uint32_t frac_cost;
+  uint32_t n_cand;                                   /* candidates evaluated */
+} hmo_search_t;
+
+void hmo_pattern_search(hmo_search_t* s);
+void hmo_tz_search(hmo_search_t* s);
+void hmo_frac_search(hmo_search_t* s); /* uses s->mv_x/mv_y as integer MV */
+
+/* full xMotionEstimation tail: integer (fs: 0=TZ,1=full) + frac + final cost fix-up */
+void hmo_motion_estimation(hmo_search_t* s, int full_search, int bi, uint32_t* io_bits,
+                           int out_mv[2], uint32_t* out_cost);
+
+/* ---- forward transform + scalar quantiser (a17, a18) ---- */
+void hmo_fwd_transform(int bit_depth, const int32_t* block, int32_t* coeff, int w, int h, int use_dst);
+void hmo_transform_matrix(int n, int32_t* m /* n*n */);
+uint32_t hmo_quant(const int32_t* coef, int n_coef, int qp_per, int qp_rem, int transform_shift,
+                   int is_intra_slice, int32_t* level, int32_t* delta_u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,381 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Thin extern "C" shim (ours) linked against the UNMODIFIED HM-16.2 reference objects
+// (compiled from /root/reference by oracle/Makefile into oracle/_ref/libhmref.so) so
+// that python/ctypes can call the real reference functions of the inter-search hot
+// path.  It is used for two things only:
+//   * pinning oracle/hm_oracle.c (our restatement) against the real reference, and
+//   * generating the golden vectors committed under tests/golden/.
+// Nothing in the product path (libhmgpu) links, loads or calls this file.
+//
+// Access to protected/private members of TEncSearch / TComRdCost / TComDataCU is
+// obtained with the classic "#define private public" trick: it changes no layout
+// under the Itanium ABI / GCC, only access checks at compile time.
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cassert>
+#include <cmath>
+#include <limits>
+#include <vector>
+#include <list>
+#include <map>
+#include <string>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <algorithm>
+#include <iomanip>
+#include <stdint.h>
+
+#define private public
+#define protected public
+#include "TLibCommon/TypeDef.h"
+#include "TLibCommon/CommonDef.h"
+#include "TLibCommon/TComRom.h"
+#include "TLibCommon/TComMv.h"
+#include "TLibCommon/TComPattern.h"
+#include "TLibCommon/TComRdCost.h"
+#include "TLibCommon/TComInterpolationFilter.h"
+#include "TLibCommon/TComTrQuant.h"
+#include "TLibCommon/TComPicYuv.h"
+#include "TLibCommon/TComYuv.h"
+#include "TLibCommon/TComSlice.h"
+#include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/TComPrediction.h"
+#include "TLibEncoder/TEncCfg.h"
+#include "TLibEncoder/TEncSearch.h"
+#undef private
+#undef protected
+
+// free functions with external linkage in TComTrQuant.cpp:387-885 (not in any header)
+extern Void partialButterfly4 (TCoeff *src, TCoeff *dst, Int shift, Int line);
+extern Void partialButterfly8 (TCoeff *src, TCoeff *dst, Int shift, Int line);
+extern Void partialButterfly16(TCoeff *src, TCoeff *dst, Int shift, Int line);
+extern Void partialButterfly32(TCoeff *src, TCoeff *dst, Int shift, Int line);
+extern Void fastForwardDst(TCoeff *block, TCoeff *coeff, Int shift);
+extern Void xTrMxN(Int bitDepth, TCoeff *block, TCoeff *coeff, Int iWidth, Int iHeight, Bool useDST, const Int maxTrDynamicRange);
+
+namespace {
+
+struct RefState
+{
+  bool         inited;
+  TComRdCost   rd;
+  TEncCfg      cfg;
+  TEncSearch*  search;
+  TComSPS      sps;
+  TComSlice*   slice;
+  TComDataCU*  cu;
+  RefState() : inited(false), search(NULL), slice(NULL), cu(NULL) {}
+};
+RefState g;
+
+void ensure_init()
+{
+  if (g.inited) return;
+  initROM();
+  g.rd.init();
+  g.cfg.setChromaFormatIdc(CHROMA_420);
+  g.cfg.setQuadtreeTULog2MaxSize(5);
+  g.cfg.setQuadtreeTULog2MinSize(2);
+  g.cfg.setFastSearch(1);
+  g.cfg.setUseFastEnc(true);
+  g.cfg.setUseHADME(true);
+  g_uiMaxCUDepth = 4;
+  g.search = new TEncSearch;
+  g.search->init(&g.cfg, NULL, 64, 4, 1, 0, NULL, &g.rd, NULL, NULL);
+  g.slice = new TComSlice;
+  g.slice->setSPS(&g.sps);
+  g.cu = new TComDataCU;
+  g.cu->m_pcSlice = g.slice;
+  g.inited = true;
+}
+
+void set_bitdepth(int bd)
+{
+  g_bitDepth[CHANNEL_TYPE_LUMA] = bd;
+  g_bitDepth[CHANNEL_TYPE_CHROMA] = bd;
+  g_maxTrDynamicRange[CHANNEL_TYPE_LUMA] = 15;
+  g_maxTrDynamicRange[CHANNEL_TYPE_CHROMA] = 15;
+}
+
+void set_cu(int picW, int picH, int cuX, int cuY)
+{
+  g.sps.setPicWidthInLumaSamples(picW);
+  g.sps.setPicHeightInLumaSamples(picH);
+  g.cu->m_uiCUPelX = cuX;
+  g.cu->m_uiCUPelY = cuY;
+}
+
+void set_cost(unsigned uiCost, int predX, int predY, int scale)
+{
+  TComMv p(predX, predY);
+  g.rd.m_uiCost = uiCost;
+  g.rd.setPredictor(p);
+  g.rd.setCostScale(scale);
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_version() { return 1602; }
+
+// ---- a1/a2/a3: integer-ME SAD through setDistParam(TComPattern*,...) (TComRdCost.cpp:305-337),
+//      iSubShift applied by the caller exactly like TEncSearch.cpp:347-353 / 3950-3956.
+unsigned ref_sad_me(const int16_t* org, int orgStride, const int16_t* cur, int curStride,
+                    int w, int h, int subShift, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  TComPattern pat; pat.initPattern((Pel*)org, w, h, orgStride);
+  DistParam dp;
+  g.rd.setDistParam(&pat, (Pel*)cur, curStride, dp);
+  dp.iSubShift = subShift;
+  dp.bitDepth = bitDepth;
+  dp.bApplyWeight = false;
+  return dp.DistFunc(&dp);
+}
+
+// ---- sub-pel ME distortion through setDistParam(pattern, ref, stride, iStep=1, dp, bHADME)
+//      (TComRdCost.cpp:340-381): SADS (hadamard=0) or HADS (hadamard=1).
+unsigned ref_dist_subpel(const int16_t* org, int orgStride, const int16_t* cur, int curStride,
+                         int w, int h, int hadamard, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  TComPattern pat; pat.initPattern((Pel*)org, w, h, orgStride);
+  DistParam dp;
+  g.rd.setDistParam(&pat, (Pel*)cur, curStride, 1, dp, hadamard != 0);
+  dp.bitDepth = bitDepth;
+  dp.bApplyWeight = false;
+  return dp.DistFunc(&dp);
+}
+
+// ---- generic two-pointer setDistParam (TComRdCost.cpp:384-396): DF_SADS/DF_HADS by width index
+unsigned ref_dist_generic(const int16_t* p1, int s1, const int16_t* p2, int s2,
+                          int w, int h, int hadamard, int bitDepth, int subShift)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  DistParam dp;
+  g.rd.setDistParam(dp, bitDepth, (Pel*)p1, s1, (Pel*)p2, s2, w, h, hadamard != 0);
+  dp.iSubShift = subShift;
+  dp.bApplyWeight = false;
+  return dp.DistFunc(&dp);
+}
+
+unsigned ref_calc_had(const int16_t* p0, int s0, const int16_t* p1, int s1, int w, int h, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  return g.rd.calcHAD(bitDepth, (Pel*)p0, s0, (Pel*)p1, s1, w, h);
+}
+
+// ---- a5: SSE through getDistPart (TComRdCost.cpp:433-456), luma
+unsigned ref_sse(const int16_t* cur, int curStride, const int16_t* org, int orgStride, int w, int h, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  return g.rd.getDistPart(bitDepth, (Pel*)cur, curStride, (Pel*)org, orgStride, w, h, COMPONENT_Y, DF_SSE);
+}
+
+// ---- a6: MV rate cost (TComRdCost.h:163-189, .cpp:278-292)
+unsigned ref_lambda_to_cost(double lambda)
+{
+  ensure_init();
+  g.rd.setLambda(lambda);
+  g.rd.getMotionCost(true, 0, false);
+  return g.rd.m_uiCost;
+}
+unsigned ref_mv_cost(unsigned uiCost, int predX, int predY, int scale, int x, int y)
+{
+  ensure_init(); set_cost(uiCost, predX, predY, scale);
+  return g.rd.getCost(x, y);
+}
+unsigned ref_mv_bits(int predX, int predY, int scale, int x, int y)
+{
+  ensure_init(); set_cost(0, predX, predY, scale);
+  return g.rd.getBits(x, y);
+}
+unsigned ref_bits_cost(unsigned uiCost, unsigned bits)
+{
+  ensure_init(); g.rd.m_uiCost = uiCost;
+  return g.rd.getCost(bits);
+}
+double ref_calc_rd_cost_sad(double lambda, unsigned bits, unsigned dist)
+{
+  ensure_init(); g.rd.setLambda(lambda);
+  return g.rd.calcRdCost(bits, dist, false, DF_SAD);
+}
+
+// ---- a8: clipMv (TComDataCU.cpp:2917-2929) and xSetSearchRange (TEncSearch.cpp:3911-3927)
+void ref_clip_mv(int picW, int picH, int cuX, int cuY, int* mv)
+{
+  ensure_init(); set_cu(picW, picH, cuX, cuY);
+  TComMv m(mv[0], mv[1]); g.cu->clipMv(m); mv[0] = m.getHor(); mv[1] = m.getVer();
+}
+void ref_set_search_range(int picW, int picH, int cuX, int cuY, int predX, int predY, int srchRng, int* ltrb)
+{
+  ensure_init(); set_cu(picW, picH, cuX, cuY);
+  TComMv p(predX, predY), lt, rb;
+  g.search->xSetSearchRange(g.cu, p, srchRng, lt, rb);
+  ltrb[0] = lt.getHor(); ltrb[1] = lt.getVer(); ltrb[2] = rb.getHor(); ltrb[3] = rb.getVer();
+}
+
+// ---- a14: interpolation primitives (TComInterpolationFilter.cpp:331-381)
+void ref_filter_hor(int chroma, const int16_t* src, int srcStride, int16_t* dst, int dstStride,
+                    int w, int h, int frac, int isLast, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  TComInterpolationFilter f;
+  f.filterHor(chroma ? COMPONENT_Cb : COMPONENT_Y, (Pel*)src, srcStride, (Pel*)dst, dstStride, w, h, frac, isLast != 0, CHROMA_420);
+}
+void ref_filter_ver(int chroma, const int16_t* src, int srcStride, int16_t* dst, int dstStride,
+                    int w, int h, int frac, int isFirst, int isLast, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  TComInterpolationFilter f;
+  f.filterVer(chroma ? COMPONENT_Cb : COMPONENT_Y, (Pel*)src, srcStride, (Pel*)dst, dstStride, w, h, frac, isFirst != 0, isLast != 0, CHROMA_420);
+}
+
+// ---- a19: picture allocation + border extension (TComPicYuv.cpp:81-134,171-215)
+// in: unpadded w x h luma; out: (w+2*margin) x (h+2*margin) padded plane, returns margin
+int ref_extend_border(const int16_t* src, int w, int h, int16_t* dst, int dstCapacityElems)
+{
+  ensure_init();
+  TComPicYuv pic;
+  pic.create(w, h, CHROMA_420, g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth);
+  Pel* y = pic.getAddr(COMPONENT_Y);
+  const int stride = pic.getStride(COMPONENT_Y);
+  for (int r = 0; r < h; r++) memcpy(y + r * stride, src + r * w, w * sizeof(Pel));
+  pic.extendPicBorder();
+  const int mx = pic.getMarginX(COMPONENT_Y), my = pic.getMarginY(COMPONENT_Y);
+  const int W = w + 2 * mx, H = h + 2 * my;
+  if (W * H <= dstCapacityElems)
+  {
+    for (int r = 0; r < H; r++) memcpy(dst + r * W, y + (r - my) * stride - mx, W * sizeof(Pel));
+  }
+  pic.destroy();
+  return (mx == my) ? mx : -1;
+}
+
+// ---- a9: xPatternSearch (TEncSearch.cpp:3932-3989).  `ref` points at the PU origin inside a
+// padded reference plane (so negative offsets are readable).
+void ref_pattern_search(const int16_t* org, int orgStride, int w, int h,
+                        const int16_t* ref, int refStride,
+                        int l, int t, int r, int b,
+                        unsigned uiCost, int predX, int predY, int fen, int bitDepth,
+                        int* outMv, unsigned* outSad)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  g.cfg.setUseFastEnc(fen != 0);
+  set_cost(uiCost, predX, predY, 2);
+  TComPattern pat; pat.initPattern((Pel*)org, w, h, orgStride);
+  TComMv lt(l, t), rb(r, b), mv;
+  Distortion sad = 0;
+  g.search->m_cDistParam.bApplyWeight = false;
+  g.search->xPatternSearch(&pat, (Pel*)ref, refStride, &lt, &rb, mv, sad);
+  outMv[0] = mv.getHor(); outMv[1] = mv.getVer(); *outSad = sad;
+}
+
+// ---- a10: xTZSearch (TEncSearch.cpp:4027-4228); mvInOut = start MV in quarter-pel (the MVP)
+void ref_tz_search(const int16_t* org, int orgStride, int w, int h,
+                   const int16_t* ref, int refStride,
+                   int l, int t, int r, int b,
+                   unsigned uiCost, int predX, int predY, int fen, int bitDepth,
+                   int picW, int picH, int cuX, int cuY, int searchRange,
+                   int has2Nx2N, int i2NX, int i2NY,
+                   int* mvInOut, unsigned* outSad)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  g.cfg.setUseFastEnc(fen != 0);
+  g.cfg.setFastSearch(1);
+  set_cu(picW, picH, cuX, cuY);
+  set_cost(uiCost, predX, predY, 2);
+  g.search->m_iSearchRange = searchRange;
+  TComPattern pat; pat.initPattern((Pel*)org, w, h, orgStride);
+  TComMv lt(l, t), rb(r, b), mv(mvInOut[0], mvInOut[1]);
+  TComMv i2n(i2NX, i2NY);
+  Distortion sad = 0;
+  g.search->m_cDistParam.bApplyWeight = false;
+  g.search->xTZSearch(g.cu, &pat, (Pel*)ref, refStride, &lt, &rb, mv, sad, has2Nx2N ? &i2n : NULL);
+  mvInOut[0] = mv.getHor(); mvInOut[1] = mv.getVer(); *outSad = sad;
+}
+
+// ---- a12/a13: xPatternSearchFracDIF (TEncSearch.cpp:4386-4422); cost scale follows
+// xMotionEstimation (:3892): scale 1 on entry, the function itself switches to 0.
+void ref_frac_search(const int16_t* org, int orgStride, int w, int h,
+                     const int16_t* ref, int refStride, int mvIntX, int mvIntY,
+                     unsigned uiCost, int predX, int predY, int hadme, int lossless, int bitDepth,
+                     int* outHalf, int* outQter, unsigned* outCost)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  g.cfg.setUseHADME(hadme != 0);
+  set_cost(uiCost, predX, predY, 1);
+  TComPattern pat; pat.initPattern((Pel*)org, w, h, orgStride);
+  TComMv mvInt(mvIntX, mvIntY), half, qter;
+  Distortion cost = 0;
+  g.search->m_cDistParam.bApplyWeight = false;
+  g.search->xPatternSearchFracDIF(lossless != 0, &pat, (Pel*)ref, refStride, &mvInt, half, qter, cost, false);
+  outHalf[0] = half.getHor(); outHalf[1] = half.getVer();
+  outQter[0] = qter.getHor(); outQter[1] = qter.getVer();
+  *outCost = cost;
+}
+
+// ---- a17: forward transform (TComTrQuant.cpp:836-885); block is w*h TCoeff (int32) row-major
+void ref_fwd_transform(int bitDepth, const int32_t* block, int32_t* coeff, int w, int h, int useDST)
+{
+  ensure_init();
+  std::vector<TCoeff> tmp(block, block + w * h);
+  xTrMxN(bitDepth, &tmp[0], (TCoeff*)coeff, w, h, useDST != 0, 15);
+}
+void ref_partial_butterfly(int n, const int32_t* src, int32_t* dst, int shift, int line)
+{
+  std::vector<TCoeff> tmp(src, src + n * line);
+  switch (n)
+  {
+    case 4:  partialButterfly4 (&tmp[0], (TCoeff*)dst, shift, line); break;
+    case 8:  partialButterfly8 (&tmp[0], (TCoeff*)dst, shift, line); break;
+    case 16: partialButterfly16(&tmp[0], (TCoeff*)dst, shift, line); break;
+    case 32: partialButterfly32(&tmp[0], (TCoeff*)dst, shift, line); break;
+    default: break;
+  }
+}
+int ref_quant_scale(int rem) { return g_quantScales[rem]; }
+
+// ---- a15: luma/chroma uni-directional MC block (TComPrediction.cpp:660-698, xPredInterBlk).
+// `ref` = pointer to the block origin inside a padded plane; mv in quarter-pel (luma) or
+// eighth-pel units after the 4:2:0 scaling (chroma), exactly what xPredInterBlk derives.
+void ref_pred_inter_blk(int chroma, const int16_t* ref, int refStride, int mvx, int mvy,
+                        int w, int h, int bi, int bitDepth, int16_t* dst, int dstStride)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  // Restates the pointer arithmetic of xPredInterBlk with the reference's own filters:
+  TComInterpolationFilter f;
+  const ComponentID comp = chroma ? COMPONENT_Cb : COMPONENT_Y;
+  const int shiftHor = 2 + (chroma ? 1 : 0), shiftVer = 2 + (chroma ? 1 : 0);
+  const int16_t* r = ref + (mvx >> shiftHor) + (mvy >> shiftVer) * refStride;
+  const int xFrac = mvx & ((1 << shiftHor) - 1), yFrac = mvy & ((1 << shiftVer) - 1);
+  const int csxy = chroma ? 1 : 0; // getComponentScaleX for 4:2:0 chroma
+  const int fx = chroma ? xFrac : xFrac, fy = chroma ? yFrac : yFrac;
+  (void)csxy;
+  // the public filterHor/filterVer of the reference take frac in component units
+  // (TComInterpolationFilter.cpp:346,379 shift chroma frac by (1-csx)); for 4:2:0, csx=1.
+  if (yFrac == 0)
+  {
+    f.filterHor(comp, (Pel*)r, refStride, (Pel*)dst, dstStride, w, h, fx, !bi, CHROMA_420);
+  }
+  else if (xFrac == 0)
+  {
+    f.filterVer(comp, (Pel*)r, refStride, (Pel*)dst, dstStride, w, h, fy, true, !bi, CHROMA_420);
+  }
+  else
+  {
+    const int ntaps = chroma ? NTAPS_CHROMA : NTAPS_LUMA;
+    const int half = ntaps >> 1;
+    const int tmpStride = w;
+    std::vector<Pel> tmp((h + ntaps) * tmpStride);
+    f.filterHor(comp, (Pel*)r - (half - 1) * refStride, refStride, &tmp[0], tmpStride, w, h + ntaps - 1, fx, false, CHROMA_420);
+    f.filterVer(comp, &tmp[0] + (half - 1) * tmpStride, tmpStride, (Pel*)dst, dstStride, w, h, fy, false, !bi, CHROMA_420);
+  }
+}
+
+} // extern "C"
