@@ -1,0 +1,555 @@
+// api.cu -- extern "C" entry points of libhmgpu.so (see include/hmgpu.h for the reference
+// interfaces each one replaces).  Host buffers are staged through one pinned buffer and one
+// device buffer per context; everything runs on the context's stream.
+#include "hmgpu_internal.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <new>
+
+int hmgpu_launch_chroma(hmgpu_ctx* ctx, int16_t* d_dst, const int16_t* d_src, int src_stride);
+int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                    hmgpu_me_result* d_results, bool any_org_block);
+int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                      hmgpu_me_result* d_results, bool any_org_block, int max_win_bytes);
+int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                      hmgpu_me_result* d_results, bool any_frac);
+
+static char g_create_err[512] = "";
+
+int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int hmgpu_reserve_pinned(hmgpu_ctx* ctx, size_t bytes)
+{
+  if (bytes <= ctx->h_pin_bytes) return HMGPU_OK;
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  ctx->h_pin = NULL; ctx->h_pin_bytes = 0;
+  bytes = round_up(bytes + bytes / 4, 1 << 20);
+  HMGPU_CUDA(ctx, cudaMallocHost(&ctx->h_pin, bytes));
+  ctx->h_pin_bytes = bytes;
+  return HMGPU_OK;
+}
+
+int hmgpu_reserve_stage(hmgpu_ctx* ctx, size_t bytes)
+{
+  if (bytes <= ctx->d_stage_bytes) return HMGPU_OK;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  ctx->d_stage = NULL; ctx->d_stage_bytes = 0;
+  bytes = round_up(bytes + bytes / 4, 1 << 20);
+  HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_stage, bytes));
+  ctx->d_stage_bytes = bytes;
+  return HMGPU_OK;
+}
+
+int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes)
+{
+  if (bytes <= ctx->d_work_bytes) return HMGPU_OK;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_work) cudaFree(ctx->d_work);
+  ctx->d_work = NULL; ctx->d_work_bytes = 0;
+  bytes = round_up(bytes + bytes / 4, 1 << 20);
+  HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_work, bytes));
+  ctx->d_work_bytes = bytes;
+  return HMGPU_OK;
+}
+
+RefTable hmgpu_ref_table(const hmgpu_ctx* ctx)
+{
+  RefTable t;
+  memset(&t, 0, sizeof t);
+  for (int i = 0; i < ctx->max_refs; i++)
+    if (ctx->refs[i].valid)
+      t.base[i] = (const char*)ctx->refs[i].planes + ((size_t)HMGPU_MARGIN * ctx->pitch + HMGPU_MARGIN) * ctx->px_bytes;
+  t.plane_elems = (int64_t)ctx->plane_elems;
+  t.pitch = ctx->pitch;
+  t.pic_w = ctx->pic_w; t.pic_h = ctx->pic_h;
+  t.bit_depth = ctx->bit_depth;
+  return t;
+}
+
+int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                    hmgpu_me_result* d_results, bool any_org_block, bool any_full, bool any_tz, bool any_frac,
+                    int max_win_bytes)
+{
+  int rc;
+  if (any_tz && (rc = hmgpu_launch_tz(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block))) return rc;
+  if (any_full && (rc = hmgpu_launch_full(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, max_win_bytes))) return rc;
+  if ((rc = hmgpu_launch_frac(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_frac))) return rc;
+  return HMGPU_OK;
+}
+
+extern "C" {
+
+int hmgpu_abi_version(void) { return HMGPU_ABI_VERSION; }
+
+static_assert(sizeof(hmgpu_me_job) == 48 && sizeof(hmgpu_me_result) == 24 && sizeof(hmgpu_dist_item) == 20 &&
+              sizeof(hmgpu_mc_job) == 16, "ABI struct layout changed");
+void hmgpu_struct_sizes(int out[4])
+{
+  out[0] = (int)sizeof(hmgpu_me_job); out[1] = (int)sizeof(hmgpu_me_result);
+  out[2] = (int)sizeof(hmgpu_dist_item); out[3] = (int)sizeof(hmgpu_mc_job);
+}
+
+const char* hmgpu_last_error(const hmgpu_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* hmgpu_stream(const hmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : NULL; }
+
+int hmgpu_synchronize(hmgpu_ctx* ctx)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HMGPU_OK;
+}
+
+int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, hmgpu_ctx** out)
+{
+  if (!out) return hmgpu_fail(NULL, HMGPU_E_INVALID, "out is NULL");
+  *out = NULL;
+  if (pic_w < 8 || pic_h < 8 || (pic_w & 3) || (pic_h & 3) || pic_w > 8192 || pic_h > 8192)
+    return hmgpu_fail(NULL, HMGPU_E_INVALID, "picture size %dx%d unsupported (multiples of 4, 8..8192)", pic_w, pic_h);
+  if (bit_depth < 8 || bit_depth > 12) return hmgpu_fail(NULL, HMGPU_E_INVALID, "bit depth %d unsupported (8..12)", bit_depth);
+  if (max_refs < 1 || max_refs > HMGPU_MAX_REFS) return hmgpu_fail(NULL, HMGPU_E_INVALID, "max_refs %d not in 1..%d", max_refs, HMGPU_MAX_REFS);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return hmgpu_fail(NULL, HMGPU_E_CUDA, "no CUDA device (%s); libhmgpu has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return hmgpu_fail(NULL, HMGPU_E_INVALID, "device %d not in 0..%d", device, n_dev - 1);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return hmgpu_fail(NULL, HMGPU_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+  hmgpu_ctx* ctx = new (std::nothrow) hmgpu_ctx;
+  if (!ctx) return hmgpu_fail(NULL, HMGPU_E_NOMEM, "out of host memory");
+  memset(ctx, 0, sizeof *ctx);
+  ctx->device = device; ctx->pic_w = pic_w; ctx->pic_h = pic_h; ctx->bit_depth = bit_depth; ctx->max_refs = max_refs;
+  ctx->px_bytes = bit_depth == 8 ? 1 : 2;
+  ctx->pw = pic_w + 2 * HMGPU_MARGIN; ctx->ph = pic_h + 2 * HMGPU_MARGIN;
+  ctx->pitch = (int)round_up(ctx->pw + 32, 64);          // slack for aligned look-ahead loads
+  ctx->plane_elems = (size_t)ctx->pitch * ctx->ph;
+  ctx->cpw = pic_w / 2 + 2 * HMGPU_CMARGIN; ctx->cph = pic_h / 2 + 2 * HMGPU_CMARGIN;
+  ctx->cpitch = (int)round_up(ctx->cpw, 32);
+  ctx->org_pitch = (int)round_up(pic_w + 32, 64);
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ctx; return hmgpu_fail(NULL, HMGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  e = cudaMalloc(&ctx->d_org, (size_t)ctx->org_pitch * (pic_h + 1) * ctx->px_bytes + 256);
+  if (e != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return hmgpu_fail(NULL, HMGPU_E_NOMEM, "cudaMalloc org: %s", cudaGetErrorString(e)); }
+  cudaMemset(ctx->d_org, 0, (size_t)ctx->org_pitch * (pic_h + 1) * ctx->px_bytes + 256);
+  *out = ctx;
+  return HMGPU_OK;
+}
+
+void hmgpu_destroy(hmgpu_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < HMGPU_MAX_REFS; i++)
+  {
+    if (ctx->refs[i].planes) cudaFree(ctx->refs[i].planes);
+    if (ctx->refs[i].cb) cudaFree(ctx->refs[i].cb);
+    if (ctx->refs[i].cr) cudaFree(ctx->refs[i].cr);
+  }
+  if (ctx->d_org) cudaFree(ctx->d_org);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->d_work) cudaFree(ctx->d_work);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int ref_alloc(hmgpu_ctx* ctx, int slot, bool chroma)
+{
+  RefSlot& s = ctx->refs[slot];
+  if (!s.planes)
+  {
+    const size_t bytes = ctx->plane_elems * 16 * ctx->px_bytes + 512;
+    HMGPU_CUDA(ctx, cudaMalloc(&s.planes, bytes));
+    HMGPU_CUDA(ctx, cudaMemsetAsync(s.planes, 0, bytes, ctx->stream));
+  }
+  if (chroma && !s.cb)
+  {
+    const size_t bytes = (size_t)ctx->cpitch * ctx->cph * sizeof(int16_t);
+    HMGPU_CUDA(ctx, cudaMalloc(&s.cb, bytes));
+    HMGPU_CUDA(ctx, cudaMalloc(&s.cr, bytes));
+  }
+  return HMGPU_OK;
+}
+
+// copy a strided host plane into pinned memory (tight), then to the device staging buffer
+static int stage_plane(hmgpu_ctx* ctx, const int16_t* src, int stride, int w, int h, size_t pin_off, size_t dev_off)
+{
+  int16_t* pin = (int16_t*)((char*)ctx->h_pin + pin_off);
+  for (int y = 0; y < h; y++) memcpy(pin + (size_t)y * w, src + (size_t)y * stride, sizeof(int16_t) * w);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_stage + dev_off, pin, sizeof(int16_t) * (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+  return HMGPU_OK;
+}
+
+int hmgpu_ref_upload(hmgpu_ctx* ctx, int slot, const int16_t* luma, int luma_stride,
+                     const int16_t* cb, const int16_t* cr, int chroma_stride)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (slot < 0 || slot >= ctx->max_refs || !luma) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad slot %d or NULL luma", slot);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool chroma = cb && cr;
+  int rc = ref_alloc(ctx, slot, chroma);
+  if (rc) return rc;
+  const size_t ybytes = sizeof(int16_t) * (size_t)ctx->pic_w * ctx->pic_h;
+  const size_t cbytes = sizeof(int16_t) * (size_t)(ctx->pic_w / 2) * (ctx->pic_h / 2);
+  const size_t total = ybytes + (chroma ? 2 * cbytes : 0);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the pinned buffer is reused
+  if ((rc = hmgpu_reserve_pinned(ctx, total))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, total))) return rc;
+  if ((rc = stage_plane(ctx, luma, luma_stride, ctx->pic_w, ctx->pic_h, 0, 0))) return rc;
+  if ((rc = hmgpu_launch_planes(ctx, slot, (const int16_t*)ctx->d_stage, ctx->pic_w))) return rc;
+  if (chroma)
+  {
+    if ((rc = stage_plane(ctx, cb, chroma_stride, ctx->pic_w / 2, ctx->pic_h / 2, ybytes, ybytes))) return rc;
+    if ((rc = stage_plane(ctx, cr, chroma_stride, ctx->pic_w / 2, ctx->pic_h / 2, ybytes + cbytes, ybytes + cbytes))) return rc;
+    if ((rc = hmgpu_launch_chroma(ctx, (int16_t*)ctx->refs[slot].cb, (const int16_t*)((char*)ctx->d_stage + ybytes), ctx->pic_w / 2))) return rc;
+    if ((rc = hmgpu_launch_chroma(ctx, (int16_t*)ctx->refs[slot].cr, (const int16_t*)((char*)ctx->d_stage + ybytes + cbytes), ctx->pic_w / 2))) return rc;
+  }
+  ctx->refs[slot].valid = true;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HMGPU_OK;
+}
+
+int hmgpu_ref_upload_device(hmgpu_ctx* ctx, int slot, const void* d_luma, int luma_stride)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (slot < 0 || slot >= ctx->max_refs || !d_luma) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad slot %d or NULL luma", slot);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ref_alloc(ctx, slot, false);
+  if (rc) return rc;
+  if ((rc = hmgpu_launch_planes(ctx, slot, (const int16_t*)d_luma, luma_stride))) return rc;
+  ctx->refs[slot].valid = true;
+  return HMGPU_OK;
+}
+
+int hmgpu_ref_release(hmgpu_ctx* ctx, int slot)
+{
+  if (!ctx || slot < 0 || slot >= HMGPU_MAX_REFS) return HMGPU_E_INVALID;
+  ctx->refs[slot].valid = false;   // memory is kept for the next picture that takes the slot
+  return HMGPU_OK;
+}
+
+int hmgpu_ref_download_plane(hmgpu_ctx* ctx, int slot, int frac_x, int frac_y, int16_t* dst)
+{
+  if (!ctx || !dst) return HMGPU_E_INVALID;
+  if (slot < 0 || slot >= ctx->max_refs || !ctx->refs[slot].valid) return hmgpu_fail(ctx, HMGPU_E_STATE, "slot %d holds no reference", slot);
+  if (frac_x < 0 || frac_x > 3 || frac_y < 0 || frac_y > 3) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad phase");
+  const size_t bytes = ctx->plane_elems * ctx->px_bytes;
+  int rc = hmgpu_reserve_pinned(ctx, bytes);
+  if (rc) return rc;
+  const char* src = (const char*)ctx->refs[slot].planes + (size_t)(frac_y * 4 + frac_x) * bytes;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int y = 0; y < ctx->ph; y++)
+    for (int x = 0; x < ctx->pw; x++)
+      dst[(size_t)y * ctx->pw + x] = ctx->px_bytes == 1 ? (int16_t)((const uint8_t*)ctx->h_pin)[(size_t)y * ctx->pitch + x]
+                                                        : (int16_t)((const uint16_t*)ctx->h_pin)[(size_t)y * ctx->pitch + x];
+  return HMGPU_OK;
+}
+
+int hmgpu_org_upload(hmgpu_ctx* ctx, const int16_t* luma, int luma_stride)
+{
+  if (!ctx || !luma) return HMGPU_E_INVALID;
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t ybytes = sizeof(int16_t) * (size_t)ctx->pic_w * ctx->pic_h;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, ybytes))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, ybytes))) return rc;
+  if ((rc = stage_plane(ctx, luma, luma_stride, ctx->pic_w, ctx->pic_h, 0, 0))) return rc;
+  if ((rc = hmgpu_launch_org(ctx, (const int16_t*)ctx->d_stage, ctx->pic_w))) return rc;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HMGPU_OK;
+}
+
+int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride)
+{
+  if (!ctx || !d_luma) return HMGPU_E_INVALID;
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  return hmgpu_launch_org(ctx, (const int16_t*)d_luma, luma_stride);
+}
+
+// ---- motion search --------------------------------------------------------------------------
+
+static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_org_elems,
+                         bool* any_org, bool* any_full, bool* any_tz, bool* any_frac, int* max_win_bytes)
+{
+  *any_org = *any_full = *any_tz = *any_frac = false;
+  *max_win_bytes = 0;
+  for (int i = 0; i < n; i++)
+  {
+    const hmgpu_me_job& j = jobs[i];
+    if (j.pu_w < 4 || j.pu_w > 64 || j.pu_h < 4 || j.pu_h > 64 || (j.pu_w & 3) || (j.pu_h & 3))
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: PU %dx%d unsupported", i, j.pu_w, j.pu_h);
+    if (j.pu_x < 0 || j.pu_y < 0 || j.pu_x + j.pu_w > ctx->pic_w || j.pu_y + j.pu_h > ctx->pic_h || (j.pu_x & 3))
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: PU at (%d,%d) outside the picture or x not a multiple of 4", i, j.pu_x, j.pu_y);
+    if (j.ref_slot >= ctx->max_refs || !ctx->refs[j.ref_slot].valid)
+      return hmgpu_fail(ctx, HMGPU_E_STATE, "job %d: reference slot %d not uploaded", i, j.ref_slot);
+    // every sample the search can touch must lie inside the 80-sample padding
+    const int lo_x = j.pu_x + (j.clip_hmin >> 2) - 4, hi_x = j.pu_x + j.pu_w + (j.clip_hmax >> 2) + 4;
+    const int lo_y = j.pu_y + (j.clip_vmin >> 2) - 4, hi_y = j.pu_y + j.pu_h + (j.clip_vmax >> 2) + 4;
+    if (lo_x < -HMGPU_MARGIN || lo_y < -HMGPU_MARGIN || hi_x > ctx->pic_w + HMGPU_MARGIN || hi_y > ctx->pic_h + HMGPU_MARGIN)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: clip bounds reach outside the padded reference", i);
+    if ((j.win_l << 2) < j.clip_hmin - 3 || (j.win_r << 2) > j.clip_hmax || (j.win_t << 2) < j.clip_vmin - 3 || (j.win_b << 2) > j.clip_vmax)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: search window outside the clip bounds", i);
+    if (!(j.flags & HMGPU_F_INTEGER))
+    {
+      if ((j.start_x << 2) < j.clip_hmin - 3 || (j.start_x << 2) > j.clip_hmax || (j.start_y << 2) < j.clip_vmin - 3 || (j.start_y << 2) > j.clip_vmax)
+        return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: integer MV outside the clip bounds", i);
+    }
+    if (j.flags & HMGPU_F_ORG_BLOCK)
+    {
+      *any_org = true;
+      if ((size_t)j.org_offset + (size_t)j.pu_w * j.pu_h > (size_t)n_org_elems)
+        return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: org block outside org_blocks", i);
+    }
+    if (j.flags & HMGPU_F_FRAC) *any_frac = true;
+    if (j.flags & HMGPU_F_INTEGER)
+    {
+      if (j.flags & HMGPU_F_FULL)
+      {
+        *any_full = true;
+        const int nx = j.win_r - j.win_l + 1, ny = j.win_b - j.win_t + 1;
+        if (nx > 0 && ny > 0)
+        {
+          const int rows = ((j.flags & HMGPU_F_FEN) && j.pu_h > 8) ? j.pu_h >> 1 : j.pu_h;
+          const int win_w = 15 + nx - 1 + j.pu_w + 4;
+          const int spitch = ((win_w + 15) >> 4) * 16 + 16;
+          const int bytes = ((rows * j.pu_w + 15) & ~15) + spitch * (ny - 1 + j.pu_h);
+          if (bytes > *max_win_bytes) *max_win_bytes = bytes;
+        }
+      }
+      else
+      {
+        *any_tz = true;
+        if (j.search_range < 1 || j.search_range > 512) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: search range %d", i, j.search_range);
+      }
+    }
+  }
+  return HMGPU_OK;
+}
+
+int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
+                    const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !results || n_jobs < 0 || n_jobs > (1 << 26)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  bool any_org, any_full, any_tz, any_frac;
+  int max_win;
+  int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win);
+  if (rc) return rc;
+  const size_t jb = round_up(sizeof(hmgpu_me_job) * (size_t)n_jobs, 256);
+  const size_t ob = round_up(any_org ? sizeof(int16_t) * (size_t)n_org_elems : 0, 256);
+  const size_t rb = round_up(sizeof(hmgpu_me_result) * (size_t)n_jobs, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = hmgpu_reserve_pinned(ctx, jb + ob + rb))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, jb + ob + rb))) return rc;
+  char* hp = (char*)ctx->h_pin;
+  char* dp = (char*)ctx->d_stage;
+  memcpy(hp, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
+  if (any_org) memcpy(hp + jb, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, jb + ob, cudaMemcpyHostToDevice, ctx->stream));
+  rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n_jobs, any_org ? (const int16_t*)(dp + jb) : NULL,
+                       (hmgpu_me_result*)(dp + jb + ob), any_org, any_full, any_tz, any_frac, max_win);
+  if (rc) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + jb + ob, dp + jb + ob, sizeof(hmgpu_me_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(results, hp + jb + ob, sizeof(hmgpu_me_result) * (size_t)n_jobs);
+  return HMGPU_OK;
+}
+
+int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const void* d_org_blocks, void* d_results)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!d_jobs || !d_results || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  // jobs are not visible to the host: run every stage, worst-case full-search window (SR 64, 64x64)
+  return hmgpu_launch_me(ctx, (const hmgpu_me_job*)d_jobs, n_jobs, (const int16_t*)d_org_blocks,
+                         (hmgpu_me_result*)d_results, d_org_blocks != NULL, true, true, true, 64 * 1024);
+}
+
+void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4])
+{
+  // TComDataCU::clipMv (TComDataCU.cpp:2917-2929), g_uiMaxCUWidth = g_uiMaxCUHeight = 64
+  bounds[0] = (int16_t)((-64 - 8 - cu_x + 1) * 4);
+  bounds[1] = (int16_t)((pic_w + 8 - cu_x - 1) * 4);
+  bounds[2] = (int16_t)((-64 - 8 - cu_y + 1) * 4);
+  bounds[3] = (int16_t)((pic_h + 8 - cu_y - 1) * 4);
+}
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void hmgpu_search_range(const int16_t bd[4], int pred_x, int pred_y, int srch_rng, int16_t ltrb[4])
+{
+  // TEncSearch::xSetSearchRange (TEncSearch.cpp:3911-3927); TComMv stores Short
+  const int px = clampi(pred_x, bd[0], bd[1]), py = clampi(pred_y, bd[2], bd[3]);
+  const int r4 = srch_rng << 2;
+  ltrb[0] = (int16_t)(clampi((int16_t)(px - r4), bd[0], bd[1]) >> 2);
+  ltrb[1] = (int16_t)(clampi((int16_t)(py - r4), bd[2], bd[3]) >> 2);
+  ltrb[2] = (int16_t)(clampi((int16_t)(px + r4), bd[0], bd[1]) >> 2);
+  ltrb[3] = (int16_t)(clampi((int16_t)(py + r4), bd[2], bd[3]) >> 2);
+}
+
+static uint32_t component_bits(int v)
+{
+  uint32_t t = (v <= 0) ? (uint32_t)((-v << 1) + 1) : (uint32_t)(v << 1);
+  uint32_t len = 1;
+  while (t != 1) { t >>= 1; len += 2; }
+  return len;
+}
+
+uint32_t hmgpu_mv_bits(int pred_x, int pred_y, int scale, int x, int y)
+{
+  return component_bits((x << scale) - pred_x) + component_bits((y << scale) - pred_y);
+}
+
+uint32_t hmgpu_mv_cost(uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y)
+{
+  return (uint32_t)(ui_cost * hmgpu_mv_bits(pred_x, pred_y, scale, x, y)) >> 16;
+}
+
+// ---- distortion batch --------------------------------------------------------------------------
+
+int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_t* cur, int n_cur,
+                     const hmgpu_dist_item* items, int n_items, uint32_t* out)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_items == 0) return HMGPU_OK;
+  if (!org || !cur || !items || !out || n_items < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  for (int i = 0; i < n_items; i++)
+  {
+    const hmgpu_dist_item& it = items[i];
+    if (it.w < 1 || it.h < 1 || it.func > HMGPU_DF_SSE || it.sub_shift > 4)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "item %d: bad w/h/func/sub_shift", i);
+    if (it.func == HMGPU_DF_HADS && ((it.w & 1) || (it.h & 1)))
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "item %d: HADS needs even dimensions", i);
+    if (it.func == HMGPU_DF_SAD && (it.h & ((1 << it.sub_shift) - 1)))
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "item %d: rows not a multiple of the sub-sampling step", i);
+    const long long oe = (long long)it.org_offset + (long long)(it.h - 1) * it.org_stride + it.w;
+    const long long ce = (long long)it.cur_offset + (long long)(it.h - 1) * it.cur_stride + it.w;
+    if (it.org_stride < 0 || it.cur_stride < 0 || oe > n_org || ce > n_cur)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "item %d: block outside its array", i);
+  }
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b0 = round_up(sizeof(int16_t) * (size_t)n_org, 256), b1 = round_up(sizeof(int16_t) * (size_t)n_cur, 256);
+  const size_t b2 = round_up(sizeof(hmgpu_dist_item) * (size_t)n_items, 256), b3 = round_up(sizeof(uint32_t) * (size_t)n_items, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1 + b2 + b3))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1 + b2 + b3))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, org, sizeof(int16_t) * (size_t)n_org);
+  memcpy(hp + b0, cur, sizeof(int16_t) * (size_t)n_cur);
+  memcpy(hp + b0 + b1, items, sizeof(hmgpu_dist_item) * (size_t)n_items);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0 + b1 + b2, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_dist(ctx, (const int16_t*)dp, (const int16_t*)(dp + b0), (const hmgpu_dist_item*)(dp + b0 + b1), n_items,
+                              (uint32_t*)(dp + b0 + b1 + b2)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0 + b1 + b2, dp + b0 + b1 + b2, sizeof(uint32_t) * (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out, hp + b0 + b1 + b2, sizeof(uint32_t) * (size_t)n_items);
+  return HMGPU_OK;
+}
+
+// ---- motion compensation -----------------------------------------------------------------------
+
+int hmgpu_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* jobs, int n_jobs, int16_t* dst, int n_dst)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !dst || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const hmgpu_mc_job& j = jobs[i];
+    if (j.ref_slot >= ctx->max_refs || !ctx->refs[j.ref_slot].valid) return hmgpu_fail(ctx, HMGPU_E_STATE, "job %d: slot %d not uploaded", i, j.ref_slot);
+    const int x0 = j.pu_x + (j.mv_x >> 2), y0 = j.pu_y + (j.mv_y >> 2);
+    if (x0 < -HMGPU_MARGIN + 4 || y0 < -HMGPU_MARGIN + 4 || x0 + j.pu_w > ctx->pic_w + HMGPU_MARGIN - 4 || y0 + j.pu_h > ctx->pic_h + HMGPU_MARGIN - 4)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: MV reaches outside the padded reference", i);
+    if ((size_t)j.dst_offset + (size_t)j.pu_w * j.pu_h > (size_t)n_dst) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: dst block outside dst", i);
+  }
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b0 = round_up(sizeof(hmgpu_mc_job) * (size_t)n_jobs, 256), b1 = round_up(sizeof(int16_t) * (size_t)n_dst, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, jobs, sizeof(hmgpu_mc_job) * (size_t)n_jobs);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  HMGPU_CUDA(ctx, cudaMemsetAsync(dp + b0, 0, b1, ctx->stream));
+  if ((rc = hmgpu_launch_mc_luma(ctx, (const hmgpu_mc_job*)dp, n_jobs, (int16_t*)(dp + b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int16_t) * (size_t)n_dst, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(dst, hp + b0, sizeof(int16_t) * (size_t)n_dst);
+  return HMGPU_OK;
+}
+
+// ---- transform / quant -------------------------------------------------------------------------
+
+int hmgpu_fwd_transform(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, int use_dst, int32_t* coeff)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_tus == 0) return HMGPU_OK;
+  if (!resi || !coeff || n_tus < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t elems = (size_t)n_tus * n * n;
+  const size_t b0 = round_up(sizeof(int16_t) * elems, 256), b1 = round_up(sizeof(int32_t) * elems, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, resi, sizeof(int16_t) * elems);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_fwd_transform(ctx, (const int16_t*)dp, n_tus, n, use_dst, (int32_t*)(dp + b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int32_t) * elems, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(coeff, hp + b0, sizeof(int32_t) * elems);
+  return HMGPU_OK;
+}
+
+int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_per, int qp_rem,
+                int is_intra_slice, int32_t* level, int32_t* delta_u, uint32_t* abs_sum)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_tus == 0) return HMGPU_OK;
+  if (!coeff || !level || !abs_sum || n_tus < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  if (qp_rem < 0 || qp_rem > 5 || qp_per < 0 || qp_per > 12) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad qp per/rem");
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t elems = (size_t)n_tus * n * n;
+  const size_t b0 = round_up(sizeof(int32_t) * elems, 256), b3 = round_up(sizeof(uint32_t) * (size_t)n_tus, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, 3 * b0 + b3))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, 3 * b0 + b3))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, coeff, sizeof(int32_t) * elems);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_quant(ctx, (const int32_t*)dp, n_tus, n, qp_per, qp_rem, is_intra_slice, (int32_t*)(dp + b0),
+                               (int32_t*)(dp + 2 * b0), (uint32_t*)(dp + 3 * b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, 2 * b0 + sizeof(uint32_t) * (size_t)n_tus, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(level, hp + b0, sizeof(int32_t) * elems);
+  if (delta_u) memcpy(delta_u, hp + 2 * b0, sizeof(int32_t) * elems);
+  memcpy(abs_sum, hp + 3 * b0, sizeof(uint32_t) * (size_t)n_tus);
+  return HMGPU_OK;
+}
+
+} // extern "C"

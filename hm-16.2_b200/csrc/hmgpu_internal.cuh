@@ -1,0 +1,179 @@
+// hmgpu_internal.cuh -- shared declarations of libhmgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/hmgpu.h"
+
+#define HMGPU_MARGIN 80          // luma padding, g_uiMaxCUWidth + 16 (TComPicYuv.cpp:87-88)
+#define HMGPU_CMARGIN 40         // chroma padding (4:2:0)
+#define HMGPU_MAX_REFS 16
+#define HMGPU_NUM_SMS 148
+
+// Device view of the reference planes of one context, passed to kernels by value.
+// plane(slot, phase) sample (x, y), x in [-80, W+80): base[slot] + phase*plane_elems + y*pitch + x
+struct RefTable
+{
+  const void* base[HMGPU_MAX_REFS]; // pointer to sample (0,0) of phase plane 0 (integer plane)
+  int64_t plane_elems;              // elements between consecutive phase planes
+  int32_t pitch;                    // elements per padded row
+  int32_t pic_w, pic_h;
+  int32_t bit_depth;
+};
+
+struct OrgView
+{
+  const void* base;    // sample (0,0) of the source picture (Px elements)
+  int32_t pitch;
+};
+
+struct RefSlot
+{
+  bool  valid;
+  void* planes;        // 16 padded planes, Px elements
+  void* cb;            // padded chroma planes (int16), may be null
+  void* cr;
+};
+
+struct hmgpu_ctx
+{
+  int device, pic_w, pic_h, bit_depth, max_refs;
+  int px_bytes;                 // 1 (8-bit) or 2
+  int pw, ph, pitch;            // padded luma geometry (elements)
+  size_t plane_elems;
+  int cpw, cph, cpitch;         // padded chroma geometry
+  cudaStream_t stream;
+  RefSlot refs[HMGPU_MAX_REFS];
+  void* d_org; int org_pitch;   // source picture, Px
+  // staging (grow on demand)
+  void* h_pin; size_t h_pin_bytes;     // pinned host
+  void* d_stage; size_t d_stage_bytes; // device
+  void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
+  uint64_t launches;
+  char err[512];
+};
+
+int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...);
+int hmgpu_reserve_pinned(hmgpu_ctx* ctx, size_t bytes);
+int hmgpu_reserve_stage(hmgpu_ctx* ctx, size_t bytes);
+int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes);
+RefTable hmgpu_ref_table(const hmgpu_ctx* ctx);
+
+#define HMGPU_CUDA(ctx, call)                                                              \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return hmgpu_fail((ctx), HMGPU_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,    \
+                        cudaGetErrorString(e__));                                          \
+  } while (0)
+
+// launchers implemented in the .cu files (all asynchronous on ctx->stream)
+int hmgpu_launch_planes(hmgpu_ctx* ctx, int slot, const int16_t* d_src, int src_stride);
+int hmgpu_launch_org(hmgpu_ctx* ctx, const int16_t* d_src, int src_stride);
+int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                    hmgpu_me_result* d_results, bool any_org_block, bool any_full, bool any_tz, bool any_frac,
+                    int max_win_bytes);
+int hmgpu_launch_dist(hmgpu_ctx* ctx, const int16_t* d_org, const int16_t* d_cur,
+                      const hmgpu_dist_item* d_items, int n_items, uint32_t* d_out);
+int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst);
+int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff);
+int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int qp_per, int qp_rem,
+                       int is_intra, int32_t* d_level, int32_t* d_delta, uint32_t* d_abs_sum);
+
+// ---------------------------------------------------------------------------------------
+// device helpers shared by the search kernels
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Exp-Golomb length, TComRdCost::xGetComponentBits (TComRdCost.cpp:278-292):
+// 2*floor(log2(v<=0 ? -2v+1 : 2v)) + 1
+__device__ __forceinline__ uint32_t hm_component_bits(int v)
+{
+  const uint32_t t = (v <= 0) ? (uint32_t)((-v << 1) + 1) : (uint32_t)(v << 1);
+  return 2u * (31u - (uint32_t)__clz((int)t)) + 1u;
+}
+
+// TComRdCost::getCost(x,y) (TComRdCost.h:171-188): uint32 wrap-around (m_uiCost*bits)>>16
+__device__ __forceinline__ uint32_t hm_mv_cost(uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y)
+{
+  const uint32_t bits = hm_component_bits((x << scale) - pred_x) + hm_component_bits((y << scale) - pred_y);
+  return (ui_cost * bits) >> 16;
+}
+
+// sum of |a_i - b_i| over 4 packed unsigned bytes, accumulated: one VABSDIFF4.U8.ACC
+__device__ __forceinline__ uint32_t vabsdiff4_acc(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t r;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+__device__ __forceinline__ int hm_abs(int v) { return v < 0 ? -v : v; }
+
+// integer-pel SAD normalisation: (sum << iSubShift) >> (bitDepth-8)  (TComRdCost.cpp:520-521)
+__device__ __forceinline__ uint32_t hm_sad_norm(uint32_t sum, int sub_shift, int bit_depth)
+{
+  return (sum << sub_shift) >> (bit_depth - 8);
+}
+
+// 8-point Hadamard on 8 ints with stride S inside a register array (fully unrolled)
+template <int S>
+__device__ __forceinline__ void hm_hadamard8(int* v)
+{
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const int a = v[i * S], b = v[(i + 4) * S]; v[i * S] = a + b; v[(i + 4) * S] = a - b; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 4)
+#pragma unroll
+    for (int j = i; j < i + 2; j++) { const int a = v[j * S], b = v[(j + 2) * S]; v[j * S] = a + b; v[(j + 2) * S] = a - b; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) { const int a = v[i * S], b = v[(i + 1) * S]; v[i * S] = a + b; v[(i + 1) * S] = a - b; }
+}
+
+// SATD of one 8x8 tile of differences d[64] (row-major), rounding (s+2)>>2
+// (xCalcHADs8x8, TComRdCost.cpp:1439-1534).  The last vertical stage is folded into the
+// absolute-value sum with |a+b| + |a-b| = 2*max(|a|,|b|).
+__device__ __forceinline__ uint32_t hm_satd8x8(int* d)
+{
+#pragma unroll
+  for (int r = 0; r < 8; r++) hm_hadamard8<1>(d + r * 8);
+  uint32_t s = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+  {
+    int* v = d + c;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const int a = v[i * 8], b = v[(i + 4) * 8]; v[i * 8] = a + b; v[(i + 4) * 8] = a - b; }
+#pragma unroll
+    for (int i = 0; i < 8; i += 4)
+#pragma unroll
+      for (int j = i; j < i + 2; j++) { const int a = v[j * 8], b = v[(j + 2) * 8]; v[j * 8] = a + b; v[(j + 2) * 8] = a - b; }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) s += 2u * (uint32_t)max(hm_abs(v[i * 8]), hm_abs(v[(i + 1) * 8]));
+  }
+  return (s + 2) >> 2;
+}
+
+// SATD of one 4x4 tile, rounding (s+1)>>1 (xCalcHADs4x4, TComRdCost.cpp:1343-1437)
+__device__ __forceinline__ uint32_t hm_satd4x4(int* d)
+{
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+  {
+    int* v = d + r * 4;
+    const int a0 = v[0] + v[2], a1 = v[1] + v[3], a2 = v[0] - v[2], a3 = v[1] - v[3];
+    v[0] = a0 + a1; v[1] = a0 - a1; v[2] = a2 + a3; v[3] = a2 - a3;
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+  {
+    int* v = d + c;
+    const int a0 = v[0] + v[8], a1 = v[4] + v[12], a2 = v[0] - v[8], a3 = v[4] - v[12];
+    s += 2u * (uint32_t)max(hm_abs(a0), hm_abs(a1)) + 2u * (uint32_t)max(hm_abs(a2), hm_abs(a3));
+  }
+  return (s + 1) >> 1;
+}
+
+#endif // __CUDACC__

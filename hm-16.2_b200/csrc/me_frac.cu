@@ -1,0 +1,252 @@
+// me_frac.cu -- fractional (half- then quarter-pel) refinement over the precomputed phase planes.
+//
+// Replaces TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4386-4422), xPatternRefinement
+// (:799-852) and, through the phase planes, xExtDIFUpSamplingH/Q (:5565-5766).
+//
+// Batch-synchronous: the distortion of every (job, candidate, tile) triple is one independent
+// work item, so lanes stay busy regardless of PU size:
+//   frac_expand_kernel : one thread per job -> appends its tiles to a flat work list
+//   frac_dist_kernel   : one thread per (tile, candidate): SATD (8x8 or 4x4 tiles, rule of
+//                        TComRdCost.cpp:1555-1597) or SAD of the tile, accumulated per
+//                        (job, candidate) with a RED.ADD
+//   frac_select_kernel : one thread per job: adds the MV cost (TComRdCost::getCost, scale 1
+//                        for half-pel, 0 for quarter-pel) and keeps the first strict minimum
+//                        in table order (s_acMvRefineH / s_acMvRefineQ, TEncSearch.cpp:51-75)
+// The half-pel phase must finish before the quarter-pel phase starts (the quarter candidates
+// are centred on the best half), hence two dist/select rounds.
+#include "hmgpu_internal.cuh"
+
+__constant__ int8_t c_refine_h[9][2] = { {0,0},{0,-1},{0,1},{-1,0},{1,0},{-1,-1},{1,-1},{-1,1},{1,1} };
+__constant__ int8_t c_refine_q[9][2] = { {0,0},{0,-1},{0,1},{-1,-1},{1,-1},{-1,0},{1,0},{-1,1},{1,1} };
+
+// work item: job index (26 bits) | tile index (6 bits)
+#define WORK_TILE_BITS 6
+
+__device__ __forceinline__ int job_tile_size(const hmgpu_me_job& j) { return ((j.pu_w & 7) == 0 && (j.pu_h & 7) == 0) ? 8 : 4; }
+
+__global__ void frac_expand_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs,
+                                   hmgpu_me_result* __restrict__ results,
+                                   uint32_t* __restrict__ work, uint32_t* __restrict__ work_count,
+                                   uint32_t* __restrict__ acc)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int cnt = 0;
+  hmgpu_me_job jb;
+  if (j < n_jobs)
+  {
+    jb = jobs[j];
+    if (!(jb.flags & HMGPU_F_INTEGER))
+    {
+      // integer MV supplied by the caller (xPatternSearchFracDIF called on its own)
+      hmgpu_me_result r;
+      r.int_x = jb.start_x; r.int_y = jb.start_y; r.int_sad = 0;
+      r.half_x = r.half_y = r.qter_x = r.qter_y = 0; r.frac_cost = 0; r.n_cand = 0;
+      results[j] = r;
+    }
+    if (jb.flags & HMGPU_F_FRAC)
+    {
+      const int ts = job_tile_size(jb);
+      cnt = (jb.pu_w / ts) * (jb.pu_h / ts);
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) acc[(size_t)j * 9 + c] = 0;
+  }
+  // warp-aggregated reservation in the flat work list
+  const int lane = threadIdx.x & 31;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(work_count, (uint32_t)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t off = base + (uint32_t)(incl - cnt);
+  for (int t = 0; t < cnt; t++) work[off + t] = ((uint32_t)j << WORK_TILE_BITS) | (uint32_t)t;
+}
+
+// load n (4 or 8) consecutive pixels of a row at an arbitrary address into ints
+template <int N>
+__device__ __forceinline__ void load_row(const uint8_t* p, int* out)
+{
+  const uintptr_t a = (uintptr_t)p;
+  const int sh = (int)(a & 3) * 8;
+  const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+  uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+  const uint32_t v0 = __funnelshift_r(w0, w1, sh);
+  out[0] = v0 & 0xff; out[1] = (v0 >> 8) & 0xff; out[2] = (v0 >> 16) & 0xff; out[3] = v0 >> 24;
+  if (N == 8)
+  {
+    const uint32_t w2 = __ldg(q + 2);
+    const uint32_t v1 = __funnelshift_r(w1, w2, sh);
+    out[4] = v1 & 0xff; out[5] = (v1 >> 8) & 0xff; out[6] = (v1 >> 16) & 0xff; out[7] = v1 >> 24;
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_row(const uint16_t* p, int* out)
+{
+#pragma unroll
+  for (int k = 0; k < N; k++) out[k] = (int)__ldg(p + k);
+}
+template <int N>
+__device__ __forceinline__ void load_row(const int16_t* p, int* out)
+{
+#pragma unroll
+  for (int k = 0; k < N; k++) out[k] = (int)p[k];
+}
+
+// distortion of one TS x TS tile: d = org - ref, SATD or SAD
+template <typename Px, int TS>
+__device__ __forceinline__ uint32_t tile_dist(const hmgpu_me_job& jb, const int16_t* org_blocks, const OrgView& org,
+                                              const Px* ref, int pitch, int tx, int ty, bool satd)
+{
+  int d[TS * TS];
+  if (jb.flags & HMGPU_F_ORG_BLOCK)
+  {
+    const int16_t* o = org_blocks + jb.org_offset + (size_t)ty * jb.pu_w + tx;
+#pragma unroll
+    for (int r = 0; r < TS; r++) load_row<TS>(o + (size_t)r * jb.pu_w, d + r * TS);
+  }
+  else
+  {
+    const Px* o = (const Px*)org.base + (size_t)(jb.pu_y + ty) * org.pitch + jb.pu_x + tx;
+#pragma unroll
+    for (int r = 0; r < TS; r++) load_row<TS>(o + (size_t)r * org.pitch, d + r * TS);
+  }
+#pragma unroll
+  for (int r = 0; r < TS; r++)
+  {
+    int v[TS];
+    load_row<TS>(ref + (ptrdiff_t)(ty + r) * pitch + tx, v);
+#pragma unroll
+    for (int k = 0; k < TS; k++) d[r * TS + k] -= v[k];
+  }
+  if (satd) return TS == 8 ? hm_satd8x8(d) : hm_satd4x4(d);
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < TS * TS; i++) s += (uint32_t)hm_abs(d[i]);
+  return s;
+}
+
+// phase 0: half-pel candidates around the integer MV; phase 1: quarter-pel around the best half
+template <typename Px>
+__global__ void __launch_bounds__(128)
+frac_dist_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restrict__ org_blocks,
+                 RefTable refs, OrgView org, const hmgpu_me_result* __restrict__ results,
+                 const uint32_t* __restrict__ work, const uint32_t* __restrict__ work_count,
+                 uint32_t* __restrict__ acc, int phase)
+{
+  const uint32_t n_work = *work_count;
+  const uint64_t total = (uint64_t)n_work * 9u;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const int cand = (int)(i / n_work);
+    const uint32_t wi = work[(uint32_t)(i - (uint64_t)cand * n_work)];
+    const uint32_t j = wi >> WORK_TILE_BITS;
+    const int t = (int)(wi & ((1u << WORK_TILE_BITS) - 1));
+    const hmgpu_me_job jb = jobs[j];
+    const hmgpu_me_result res = results[j];
+    int qx, qy;
+    if (phase == 0)
+    {
+      qx = 4 * res.int_x + 2 * c_refine_h[cand][0];
+      qy = 4 * res.int_y + 2 * c_refine_h[cand][1];
+    }
+    else
+    {
+      qx = 4 * res.int_x + 2 * res.half_x + c_refine_q[cand][0];
+      qy = 4 * res.int_y + 2 * res.half_y + c_refine_q[cand][1];
+    }
+    const int ph = (qy & 3) * 4 + (qx & 3);
+    const int pitch = refs.pitch;
+    const Px* ref = (const Px*)refs.base[jb.ref_slot] + (size_t)ph * refs.plane_elems
+                  + (ptrdiff_t)(jb.pu_y + (qy >> 2)) * pitch + (jb.pu_x + (qx >> 2));
+    const bool satd = (jb.flags & HMGPU_F_HADME) && !(jb.flags & HMGPU_F_LOSSLESS);
+    uint32_t v;
+    if (job_tile_size(jb) == 8)
+    {
+      const int tw = jb.pu_w >> 3;
+      const int ty = t / tw, tx = t - ty * tw;
+      v = tile_dist<Px, 8>(jb, org_blocks, org, ref, pitch, tx * 8, ty * 8, satd);
+    }
+    else
+    {
+      const int tw = jb.pu_w >> 2;
+      const int ty = t / tw, tx = t - ty * tw;
+      v = tile_dist<Px, 4>(jb, org_blocks, org, ref, pitch, tx * 4, ty * 4, satd);
+    }
+    atomicAdd(&acc[(size_t)j * 9 + cand], v);
+  }
+}
+
+__global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs,
+                                   hmgpu_me_result* __restrict__ results, uint32_t* __restrict__ acc,
+                                   int bit_depth, int phase)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  const hmgpu_me_job jb = jobs[j];
+  if (!(jb.flags & HMGPU_F_FRAC)) return;
+  hmgpu_me_result res = results[j];
+  uint32_t best = 0xffffffffu;
+  int bi = 0;
+#pragma unroll
+  for (int c = 0; c < 9; c++)
+  {
+    const uint32_t dist = acc[(size_t)j * 9 + c] >> (bit_depth - 8);
+    acc[(size_t)j * 9 + c] = 0;
+    uint32_t cost;
+    if (phase == 0)
+      cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + c_refine_h[c][0], 2 * res.int_y + c_refine_h[c][1]);
+    else
+      cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 0, 4 * res.int_x + 2 * res.half_x + c_refine_q[c][0],
+                               4 * res.int_y + 2 * res.half_y + c_refine_q[c][1]);
+    if (cost < best) { best = cost; bi = c; }
+  }
+  if (phase == 0) { res.half_x = c_refine_h[bi][0]; res.half_y = c_refine_h[bi][1]; }
+  else { res.qter_x = c_refine_q[bi][0]; res.qter_y = c_refine_q[bi][1]; }
+  res.frac_cost = best;
+  res.n_cand += 9;
+  results[j] = res;
+}
+
+int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                      hmgpu_me_result* d_results, bool any_frac)
+{
+  // scratch: acc[n_jobs*9] | work_count[1 (+3 pad)] | work[n_jobs*64]
+  const size_t acc_bytes = (size_t)n_jobs * 9 * sizeof(uint32_t);
+  const size_t work_bytes = (size_t)n_jobs * 64 * sizeof(uint32_t);
+  const size_t acc_al = (acc_bytes + 255) & ~(size_t)255;
+  int rc = hmgpu_reserve_work(ctx, acc_al + 256 + work_bytes);
+  if (rc) return rc;
+  uint32_t* acc = (uint32_t*)ctx->d_work;
+  uint32_t* work_count = (uint32_t*)((char*)ctx->d_work + acc_al);
+  uint32_t* work = (uint32_t*)((char*)ctx->d_work + acc_al + 256);
+  HMGPU_CUDA(ctx, cudaMemsetAsync(work_count, 0, 16, ctx->stream));
+  const RefTable rt = hmgpu_ref_table(ctx);
+  OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  const int tb = 128;
+  frac_expand_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, work, work_count, acc);
+  ctx->launches += 1;
+  if (any_frac)
+  {
+    // grid-stride over a device-side item count: enough CTAs to fill the machine
+    const long long max_items = (long long)n_jobs * 64 * 9;
+    long long want = (max_items + 127) / 128;
+    const int grid = (int)(want < (long long)HMGPU_NUM_SMS * 16 ? (want < 1 ? 1 : want) : (long long)HMGPU_NUM_SMS * 16);
+    for (int phase = 0; phase < 2; phase++)
+    {
+      if (ctx->px_bytes == 1)
+        frac_dist_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase);
+      else
+        frac_dist_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase);
+      frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase);
+      ctx->launches += 2;
+    }
+  }
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}

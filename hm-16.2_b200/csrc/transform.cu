@@ -1,0 +1,142 @@
+// transform.cu -- forward core transform and scalar quantiser, batched over TUs; luma MC.
+//
+// hmgpu_launch_fwd_transform replaces TComTrQuant::xT -> xTrMxN (TComTrQuant.cpp:1805-1827,
+// 836-885): rows then columns, shift1 = log2(N) + bitDepth + 6 - 15, shift2 = log2(N) + 6,
+// round-to-nearest after each stage.  partialButterfly4/8/16/32 (:387-758) and fastForwardDst
+// (:413-435) factor an exact integer matrix product with no intermediate rounding, so the
+// kernel evaluates the product directly (int32, results fit 16 bits -- which is also why an
+// int8 tensor-core MMA cannot reproduce it).
+// hmgpu_launch_quant replaces the scalar branch of TComTrQuant::xQuant (:1120-1199).
+// hmgpu_launch_mc_luma replaces the luma part of TComPrediction::xPredInterBlk (:660-698) for
+// uni-prediction: a phase-plane gather.
+#include "hmgpu_internal.cuh"
+
+// magnitudes of the HEVC core transform, C[j] ~ 64*sqrt(2)*cos(j*pi/64) (H.265 8.6.4.2)
+__constant__ int c_dct_mag[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                   61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+__constant__ int c_dst4[4][4] = { { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };
+__constant__ int c_quant_scales[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };
+
+__device__ __forceinline__ int dct_coef(int n, int k, int i)
+{
+  if (k == 0) return 64;
+  int m = ((k * (32 / n)) * (2 * i + 1)) & 127;
+  if (m > 64) m = 128 - m;
+  return (m > 32) ? -c_dct_mag[64 - m] : c_dct_mag[m];
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, int bit_depth, int32_t* __restrict__ coeff)
+{
+  constexpr int TPB = (N * N >= 256) ? 1 : 256 / (N * N);   // TUs per block
+  constexpr int LOG2N = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
+  __shared__ int s_m[N * N];
+  __shared__ int s_a[TPB][N * N];
+  __shared__ int s_b[TPB][N * N];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N * N; i += 256)
+    s_m[i] = (use_dst && N == 4) ? c_dst4[i / N][i % N] : dct_coef(N, i / N, i % N);
+  const int tu0 = blockIdx.x * TPB;
+  for (int i = tid; i < TPB * N * N; i += 256)
+  {
+    const int t = i / (N * N);
+    if (tu0 + t < n_tus) s_a[t][i % (N * N)] = (int)resi[(size_t)(tu0 + t) * N * N + (i % (N * N))];
+  }
+  __syncthreads();
+  const int shift1 = LOG2N + bit_depth + 6 - 15, shift2 = LOG2N + 6;
+  const int rnd1 = shift1 > 0 ? (1 << (shift1 - 1)) : 0, rnd2 = 1 << (shift2 - 1);
+  // stage 1: b[k*N + j] = (sum_i M[k][i] * a[j*N + i] + rnd) >> shift1
+  for (int i = tid; i < TPB * N * N; i += 256)
+  {
+    const int t = i / (N * N), e = i % (N * N), k = e / N, j = e % N;
+    int acc = 0;
+#pragma unroll
+    for (int x = 0; x < N; x++) acc += s_m[k * N + x] * s_a[t][j * N + x];
+    s_b[t][k * N + j] = (acc + rnd1) >> shift1;
+  }
+  __syncthreads();
+  for (int i = tid; i < TPB * N * N; i += 256)
+  {
+    const int t = i / (N * N), e = i % (N * N), k = e / N, j = e % N;
+    if (tu0 + t >= n_tus) continue;
+    int acc = 0;
+#pragma unroll
+    for (int x = 0; x < N; x++) acc += s_m[k * N + x] * s_b[t][j * N + x];
+    coeff[(size_t)(tu0 + t) * N * N + k * N + j] = (acc + rnd2) >> shift2;
+  }
+}
+
+int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff)
+{
+  switch (n)
+  {
+    case 4:  fwd_transform_kernel<4><<<(n_tus + 15) / 16, 256, 0, ctx->stream>>>(d_resi, n_tus, use_dst, ctx->bit_depth, d_coeff); break;
+    case 8:  fwd_transform_kernel<8><<<(n_tus + 3) / 4, 256, 0, ctx->stream>>>(d_resi, n_tus, 0, ctx->bit_depth, d_coeff); break;
+    case 16: fwd_transform_kernel<16><<<n_tus, 256, 0, ctx->stream>>>(d_resi, n_tus, 0, ctx->bit_depth, d_coeff); break;
+    case 32: fwd_transform_kernel<32><<<n_tus, 256, 0, ctx->stream>>>(d_resi, n_tus, 0, ctx->bit_depth, d_coeff); break;
+    default: return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  }
+  ctx->launches += 1;
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}
+
+__global__ void quant_kernel(const int32_t* __restrict__ coeff, size_t total, int nn, int qbits, long long add,
+                             int scale, int32_t* __restrict__ level, int32_t* __restrict__ delta_u,
+                             uint32_t* __restrict__ abs_sum)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = coeff[i];
+  const long long t = (long long)hm_abs(c) * scale;
+  const int q = (int)((t + add) >> qbits);
+  if (delta_u) delta_u[i] = (int)((t - ((long long)q << qbits)) >> (qbits - 8));
+  int v = c < 0 ? -q : q;
+  v = min(32767, max(-32768, v));
+  level[i] = v;
+  if (q) atomicAdd(&abs_sum[i / nn], (uint32_t)q);
+}
+
+int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int qp_per, int qp_rem,
+                       int is_intra, int32_t* d_level, int32_t* d_delta, uint32_t* d_abs_sum)
+{
+  int log2n = 0;
+  while ((1 << log2n) < n) log2n++;
+  const int transform_shift = 15 - ctx->bit_depth - log2n;   // getTransformShift, TComTrQuant.h
+  const int qbits = 14 + qp_per + transform_shift;
+  const long long add = (long long)(is_intra ? 171 : 85) << (qbits - 9);
+  static const int scales[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };
+  const size_t total = (size_t)n_tus * n * n;
+  HMGPU_CUDA(ctx, cudaMemsetAsync(d_abs_sum, 0, sizeof(uint32_t) * n_tus, ctx->stream));
+  quant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_coeff, total, n * n, qbits, add, scales[qp_rem],
+                                                                         d_level, d_delta, d_abs_sum);
+  ctx->launches += 1;
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}
+
+template <typename Px>
+__global__ void mc_luma_kernel(const hmgpu_mc_job* __restrict__ jobs, RefTable refs, int16_t* __restrict__ dst)
+{
+  const hmgpu_mc_job jb = jobs[blockIdx.x];
+  const int ph = (jb.mv_y & 3) * 4 + (jb.mv_x & 3);
+  const Px* p = (const Px*)refs.base[jb.ref_slot] + (size_t)ph * refs.plane_elems
+              + (ptrdiff_t)(jb.pu_y + (jb.mv_y >> 2)) * refs.pitch + (jb.pu_x + (jb.mv_x >> 2));
+  int16_t* d = dst + jb.dst_offset;
+  for (int i = threadIdx.x; i < jb.pu_w * jb.pu_h; i += blockDim.x)
+  {
+    const int r = i / jb.pu_w, k = i - r * jb.pu_w;
+    d[i] = (int16_t)p[(ptrdiff_t)r * refs.pitch + k];
+  }
+}
+
+int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst)
+{
+  const RefTable rt = hmgpu_ref_table(ctx);
+  if (ctx->px_bytes == 1) mc_luma_kernel<uint8_t><<<n_jobs, 128, 0, ctx->stream>>>(d_jobs, rt, d_dst);
+  else mc_luma_kernel<uint16_t><<<n_jobs, 128, 0, ctx->stream>>>(d_jobs, rt, d_dst);
+  ctx->launches += 1;
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}

@@ -1,0 +1,219 @@
+"""ctypes binding of libhmgpu.so -- the host-side mirror used by tests/ and bench.py.
+
+Every call goes through the C ABI declared in include/hmgpu.h; there is no Python or CPU
+implementation behind it.  If the shared library is missing or no CUDA device is present the
+import / Context() fails loudly (no fallback).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhmgpu.so")
+
+# flags (include/hmgpu.h)
+F_FEN, F_HADME, F_LOSSLESS, F_HAS_2NX2N, F_FULL, F_INTEGER, F_FRAC, F_ORG_BLOCK = (1 << i for i in range(8))
+DF_SAD, DF_SAD_GENERIC, DF_HADS, DF_SSE = range(4)
+
+ME_JOB = np.dtype([
+    ("pu_x", "<i2"), ("pu_y", "<i2"), ("pu_w", "u1"), ("pu_h", "u1"), ("ref_slot", "u1"), ("flags", "u1"),
+    ("pred_x", "<i2"), ("pred_y", "<i2"), ("start_x", "<i2"), ("start_y", "<i2"),
+    ("win_l", "<i2"), ("win_t", "<i2"), ("win_r", "<i2"), ("win_b", "<i2"),
+    ("i2n_x", "<i2"), ("i2n_y", "<i2"),
+    ("clip_hmin", "<i2"), ("clip_hmax", "<i2"), ("clip_vmin", "<i2"), ("clip_vmax", "<i2"),
+    ("search_range", "<i2"), ("reserved", "<i2"),
+    ("ui_cost", "<u4"), ("org_offset", "<u4")], align=True)
+ME_RESULT = np.dtype([
+    ("int_x", "<i2"), ("int_y", "<i2"), ("int_sad", "<u4"),
+    ("half_x", "<i2"), ("half_y", "<i2"), ("qter_x", "<i2"), ("qter_y", "<i2"),
+    ("frac_cost", "<u4"), ("n_cand", "<u4")], align=True)
+DIST_ITEM = np.dtype([
+    ("org_offset", "<u4"), ("cur_offset", "<u4"), ("org_stride", "<i4"), ("cur_stride", "<i4"),
+    ("w", "u1"), ("h", "u1"), ("func", "u1"), ("sub_shift", "u1")], align=True)
+MC_JOB = np.dtype([
+    ("pu_x", "<i2"), ("pu_y", "<i2"), ("pu_w", "u1"), ("pu_h", "u1"), ("ref_slot", "u1"), ("reserved", "u1"),
+    ("mv_x", "<i2"), ("mv_y", "<i2"), ("dst_offset", "<u4")], align=True)
+assert ME_JOB.itemsize == 48 and ME_RESULT.itemsize == 24 and DIST_ITEM.itemsize == 20 and MC_JOB.itemsize == 16
+
+EXPORTS = [
+    "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
+    "hmgpu_stream", "hmgpu_synchronize", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
+    "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
+    "hmgpu_me_search", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
+    "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_fwd_transform",
+    "hmgpu_quant"]
+
+_lib = None
+
+
+class HmGpuError(RuntimeError):
+    pass
+
+
+def lib():
+    """load libhmgpu.so (fails loudly when it has not been built)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HmGpuError("libhmgpu.so not built: run `make -C hm-16.2_b200` (or __graft_entry__.build())")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cu = C.c_void_p, C.c_int, C.c_uint
+    L.hmgpu_create.argtypes = [ci, ci, ci, ci, ci, C.POINTER(vp)]
+    L.hmgpu_destroy.argtypes = [vp]
+    L.hmgpu_destroy.restype = None
+    L.hmgpu_last_error.argtypes = [vp]
+    L.hmgpu_last_error.restype = C.c_char_p
+    L.hmgpu_launch_count.argtypes = [vp]
+    L.hmgpu_launch_count.restype = C.c_uint64
+    L.hmgpu_stream.argtypes = [vp]
+    L.hmgpu_stream.restype = vp
+    L.hmgpu_synchronize.argtypes = [vp]
+    L.hmgpu_struct_sizes.argtypes = [vp]
+    L.hmgpu_struct_sizes.restype = None
+    L.hmgpu_ref_upload.argtypes = [vp, ci, vp, ci, vp, vp, ci]
+    L.hmgpu_ref_release.argtypes = [vp, ci]
+    L.hmgpu_ref_download_plane.argtypes = [vp, ci, ci, ci, vp]
+    L.hmgpu_ref_upload_device.argtypes = [vp, ci, vp, ci]
+    L.hmgpu_org_upload.argtypes = [vp, vp, ci]
+    L.hmgpu_org_upload_device.argtypes = [vp, vp, ci]
+    L.hmgpu_me_search.argtypes = [vp, vp, ci, vp, ci, vp]
+    L.hmgpu_me_search_device.argtypes = [vp, vp, ci, vp, vp]
+    L.hmgpu_clip_bounds.argtypes = [ci, ci, ci, ci, vp]
+    L.hmgpu_clip_bounds.restype = None
+    L.hmgpu_search_range.argtypes = [vp, ci, ci, ci, vp]
+    L.hmgpu_search_range.restype = None
+    L.hmgpu_dist_batch.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp]
+    L.hmgpu_mv_bits.argtypes = [ci] * 5
+    L.hmgpu_mv_bits.restype = cu
+    L.hmgpu_mv_cost.argtypes = [cu] + [ci] * 5
+    L.hmgpu_mv_cost.restype = cu
+    L.hmgpu_mc_luma.argtypes = [vp, vp, ci, vp, ci]
+    L.hmgpu_fwd_transform.argtypes = [vp, vp, ci, ci, ci, vp]
+    L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def clip_bounds(pic_w, pic_h, cu_x, cu_y):
+    b = np.zeros(4, np.int16)
+    lib().hmgpu_clip_bounds(pic_w, pic_h, cu_x, cu_y, b.ctypes.data)
+    return b
+
+
+def search_range(bounds, pred_x, pred_y, srch_rng):
+    b = np.ascontiguousarray(bounds, np.int16)
+    out = np.zeros(4, np.int16)
+    lib().hmgpu_search_range(b.ctypes.data, int(pred_x), int(pred_y), int(srch_rng), out.ctypes.data)
+    return out
+
+
+class Context:
+    """one encoder instance bound to one CUDA device (hmgpu_create / hmgpu_destroy)"""
+
+    def __init__(self, pic_w, pic_h, bit_depth=8, max_refs=4, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        rc = self.L.hmgpu_create(device, pic_w, pic_h, bit_depth, max_refs, C.byref(self.h))
+        if rc != 0:
+            raise HmGpuError("hmgpu_create failed (%d): %s" % (rc, self.L.hmgpu_last_error(None).decode()))
+        self.pic_w, self.pic_h, self.bit_depth = pic_w, pic_h, bit_depth
+
+    def close(self):
+        if self.h:
+            self.L.hmgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HmGpuError("libhmgpu error %d: %s" % (rc, self.L.hmgpu_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return int(self.L.hmgpu_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.L.hmgpu_stream(self.h)
+
+    def synchronize(self):
+        self._check(self.L.hmgpu_synchronize(self.h))
+
+    def ref_upload(self, slot, luma, cb=None, cr=None):
+        luma = np.ascontiguousarray(luma, np.int16)
+        assert luma.shape == (self.pic_h, self.pic_w)
+        if cb is not None:
+            cb = np.ascontiguousarray(cb, np.int16)
+            cr = np.ascontiguousarray(cr, np.int16)
+        self._check(self.L.hmgpu_ref_upload(self.h, slot, luma.ctypes.data, self.pic_w,
+                                            cb.ctypes.data if cb is not None else None,
+                                            cr.ctypes.data if cr is not None else None, self.pic_w // 2))
+
+    def ref_upload_device(self, slot, d_ptr, stride):
+        self._check(self.L.hmgpu_ref_upload_device(self.h, slot, d_ptr, stride))
+
+    def ref_release(self, slot):
+        self._check(self.L.hmgpu_ref_release(self.h, slot))
+
+    def ref_plane(self, slot, fx, fy):
+        out = np.zeros((self.pic_h + 160, self.pic_w + 160), np.int16)
+        self._check(self.L.hmgpu_ref_download_plane(self.h, slot, fx, fy, out.ctypes.data))
+        return out
+
+    def org_upload(self, luma):
+        luma = np.ascontiguousarray(luma, np.int16)
+        assert luma.shape == (self.pic_h, self.pic_w)
+        self._check(self.L.hmgpu_org_upload(self.h, luma.ctypes.data, self.pic_w))
+
+    def org_upload_device(self, d_ptr, stride):
+        self._check(self.L.hmgpu_org_upload_device(self.h, d_ptr, stride))
+
+    def me_search(self, jobs, org_blocks=None):
+        jobs = np.ascontiguousarray(jobs, ME_JOB)
+        res = np.zeros(len(jobs), ME_RESULT)
+        if org_blocks is not None:
+            org_blocks = np.ascontiguousarray(org_blocks, np.int16)
+        self._check(self.L.hmgpu_me_search(self.h, jobs.ctypes.data, len(jobs),
+                                           org_blocks.ctypes.data if org_blocks is not None else None,
+                                           org_blocks.size if org_blocks is not None else 0, res.ctypes.data))
+        return res
+
+    def me_search_device(self, d_jobs, n_jobs, d_org_blocks, d_results):
+        self._check(self.L.hmgpu_me_search_device(self.h, d_jobs, n_jobs, d_org_blocks, d_results))
+
+    def dist_batch(self, org, cur, items):
+        org = np.ascontiguousarray(org, np.int16)
+        cur = np.ascontiguousarray(cur, np.int16)
+        items = np.ascontiguousarray(items, DIST_ITEM)
+        out = np.zeros(len(items), np.uint32)
+        self._check(self.L.hmgpu_dist_batch(self.h, org.ctypes.data, org.size, cur.ctypes.data, cur.size,
+                                            items.ctypes.data, len(items), out.ctypes.data))
+        return out
+
+    def mc_luma(self, jobs, n_dst):
+        jobs = np.ascontiguousarray(jobs, MC_JOB)
+        dst = np.zeros(n_dst, np.int16)
+        self._check(self.L.hmgpu_mc_luma(self.h, jobs.ctypes.data, len(jobs), dst.ctypes.data, n_dst))
+        return dst
+
+    def fwd_transform(self, resi, n, use_dst=False):
+        resi = np.ascontiguousarray(resi, np.int16).reshape(-1, n, n)
+        out = np.zeros(resi.shape, np.int32)
+        self._check(self.L.hmgpu_fwd_transform(self.h, resi.ctypes.data, resi.shape[0], n, int(use_dst), out.ctypes.data))
+        return out
+
+    def quant(self, coeff, n, qp_per, qp_rem, is_intra):
+        coeff = np.ascontiguousarray(coeff, np.int32).reshape(-1, n, n)
+        level = np.zeros(coeff.shape, np.int32)
+        delta = np.zeros(coeff.shape, np.int32)
+        abs_sum = np.zeros(coeff.shape[0], np.uint32)
+        self._check(self.L.hmgpu_quant(self.h, coeff.ctypes.data, coeff.shape[0], n, qp_per, qp_rem, int(is_intra),
+                                       level.ctypes.data, delta.ctypes.data, abs_sum.ctypes.data))
+        return level, delta, abs_sum

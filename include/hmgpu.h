@@ -1,0 +1,204 @@
+/* include/hmgpu.h -- C ABI of libhmgpu.so, the B200 (sm_100a) implementation of the HM-16.2
+ * inter-search hot path.
+ *
+ * The reference (liron88/HM-16.2) has no plugin/FFI interface: the boundary is cut along its
+ * C++ seams and every entry point below names the reference interface it
+ * replaces (file:line relative to the reference root).  The HM-side binding that calls these
+ * (TEncSearch / TComRdCost shims selected by the GPUME cfg switch) is in
+ * hm-16.2_b200/host/ and described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative HMGPU_E_* code,
+ *     hmgpu_last_error() gives the text.  Nothing throws or aborts across the ABI.
+ *   - the caller owns every host buffer; the library has finished reading / writing it when
+ *     the call returns (blocking semantics -- HM needs the MV before its next line).
+ *   - one context per encoder instance, used from that encoder's single thread; several
+ *     contexts / processes may share one GPU.
+ *   - there is no CPU fallback: without a CUDA device hmgpu_create() fails.
+ *   - Pel = int16_t, TCoeff = int32_t, Distortion = uint32_t, MV = 2 x int16_t quarter-pel
+ *     (TypeDef.h:692-703, TComMv.h:53-55).
+ */
+#ifndef HMGPU_H
+#define HMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMGPU_ABI_VERSION 1
+
+enum
+{
+  HMGPU_OK = 0,
+  HMGPU_E_INVALID = -1,   /* bad argument */
+  HMGPU_E_CUDA = -2,      /* CUDA runtime error (text in hmgpu_last_error) */
+  HMGPU_E_NOMEM = -3,
+  HMGPU_E_STATE = -4      /* e.g. reference slot not uploaded */
+};
+
+typedef struct hmgpu_ctx hmgpu_ctx;
+
+/* ------------------------------------------------------------------------------------------
+ * Context.  Replaces nothing in the reference (it has no device); created once per encoder
+ * next to TEncTop::create (TEncTop.cpp:206-224 wires m_cSearch/m_cRdCost/m_cTrQuant).
+ * pic_w/pic_h: luma size as coded (multiple of the min CU size); bit_depth 8..12;
+ * max_refs: number of reference slots (DPB size).
+ * ------------------------------------------------------------------------------------------ */
+int  hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, hmgpu_ctx** out);
+void hmgpu_destroy(hmgpu_ctx* ctx);
+const char* hmgpu_last_error(const hmgpu_ctx* ctx);   /* ctx may be NULL (creation errors) */
+int  hmgpu_abi_version(void);
+/* number of kernels launched by this context so far (bench.py "gpu_launches") */
+uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx);
+/* the CUDA stream all work of this context is issued on (cudaStream_t as void*) */
+void* hmgpu_stream(const hmgpu_ctx* ctx);
+int  hmgpu_synchronize(hmgpu_ctx* ctx);
+/* sizeof of the four ABI structs: me_job, me_result, dist_item, mc_job (binding self-check) */
+void hmgpu_struct_sizes(int out[4]);
+
+/* ------------------------------------------------------------------------------------------
+ * Reference pictures.
+ * hmgpu_ref_upload replaces TComPicYuv::extendPicBorder (TComPicYuv.cpp:171-215, called from
+ * TComSlice::setRefPicList, TComSlice.cpp:346,359,372) plus the per-call interpolation of
+ * xExtDIFUpSamplingH/Q (TEncSearch.cpp:5565-5766): the reconstructed luma plane is uploaded
+ * once, replicate-padded by 80 samples on the device, and all 16 quarter-pel phase planes
+ * P[v][h] = clip(V_v(H_h(ref))) are built (IF_INTERNAL_OFFS / shift semantics of
+ * TComInterpolationFilter.cpp:166-251).  `luma` points at sample (0,0); stride in samples.
+ * Chroma (4:2:0, may be NULL) is padded by 40 and kept for motion compensation.
+ * ------------------------------------------------------------------------------------------ */
+int hmgpu_ref_upload(hmgpu_ctx* ctx, int slot, const int16_t* luma, int luma_stride,
+                     const int16_t* cb, const int16_t* cr, int chroma_stride);
+int hmgpu_ref_release(hmgpu_ctx* ctx, int slot);
+/* read back one padded phase plane (tests): dst is (pic_w+160) x (pic_h+160) int16 */
+int hmgpu_ref_download_plane(hmgpu_ctx* ctx, int slot, int frac_x, int frac_y, int16_t* dst);
+/* device-resident variant (no host copy): src is a device pointer to int16 luma */
+int hmgpu_ref_upload_device(hmgpu_ctx* ctx, int slot, const void* d_luma, int luma_stride);
+
+/* Original (source) picture of the frame being coded: the key pattern of uni-directional
+ * searches (TEncSearch.cpp:3852, pcYuvOrg = the CTU's copy of this picture). */
+int hmgpu_org_upload(hmgpu_ctx* ctx, const int16_t* luma, int luma_stride);
+int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride);
+
+/* ------------------------------------------------------------------------------------------
+ * Motion search.  One job = one TEncSearch::xMotionEstimation call (TEncSearch.cpp:3816-3906)
+ * minus its host-side prologue/epilogue: integer search (xPatternSearch :3932-3989 or
+ * xTZSearch :4027-4228) followed by xPatternSearchFracDIF (:4386-4422).
+ * ------------------------------------------------------------------------------------------ */
+enum
+{
+  HMGPU_F_FEN        = 1 << 0,  /* m_pcEncCfg->getUseFastEnc(): sub-sampled SAD when rows > 8 */
+  HMGPU_F_HADME      = 1 << 1,  /* m_pcEncCfg->getUseHADME(): SATD in the fractional search */
+  HMGPU_F_LOSSLESS   = 1 << 2,  /* CU transquant bypass: SAD in the fractional search */
+  HMGPU_F_HAS_2NX2N  = 1 << 3,  /* pIntegerMv2Nx2NPred != NULL (TEncSearch.cpp:3879-3883) */
+  HMGPU_F_FULL       = 1 << 4,  /* xPatternSearch (FastSearch=0 or bi-pred) instead of xTZSearch */
+  HMGPU_F_INTEGER    = 1 << 5,  /* run the integer search (else start_x/y IS the integer MV) */
+  HMGPU_F_FRAC       = 1 << 6,  /* run xPatternSearchFracDIF after it */
+  HMGPU_F_ORG_BLOCK  = 1 << 7   /* key pattern = explicit int16 block (bi-pred 2*org-pred,
+                                   TComYuv.cpp:393-424) at org_offset, stride pu_w */
+};
+
+typedef struct hmgpu_me_job
+{
+  int16_t  pu_x, pu_y;            /* PU origin, luma samples, picture coordinates */
+  uint8_t  pu_w, pu_h;            /* 4..64 */
+  uint8_t  ref_slot;
+  uint8_t  flags;                 /* HMGPU_F_* */
+  int16_t  pred_x, pred_y;        /* m_mvPredictor (quarter-pel), TComRdCost::setPredictor */
+  int16_t  start_x, start_y;      /* TZ: rcMv on entry (quarter-pel MVP); no INTEGER flag: integer MV */
+  int16_t  win_l, win_t, win_r, win_b;  /* cMvSrchRngLT/RB after xSetSearchRange (integer pel) */
+  int16_t  i2n_x, i2n_y;          /* m_integerMv2Nx2N[list][ref] (integer pel) */
+  int16_t  clip_hmin, clip_hmax, clip_vmin, clip_vmax; /* TComDataCU::clipMv bounds (quarter-pel) */
+  int16_t  search_range;          /* m_iSearchRange (adaptive SR), TZ only */
+  int16_t  reserved;
+  uint32_t ui_cost;               /* TComRdCost::m_uiCost after getMotionCost(true,0,..) */
+  uint32_t org_offset;            /* HMGPU_F_ORG_BLOCK: element offset into org_blocks */
+} hmgpu_me_job;                   /* 48 bytes */
+
+typedef struct hmgpu_me_result
+{
+  int16_t  int_x, int_y;          /* rcMv after the integer search (integer pel) */
+  uint32_t int_sad;               /* ruiSAD of the integer search (MV cost removed) */
+  int16_t  half_x, half_y;        /* cMvHalf */
+  int16_t  qter_x, qter_y;        /* cMvQter */
+  uint32_t frac_cost;             /* ruiCost after xPatternSearchFracDIF */
+  uint32_t n_cand;                /* candidates evaluated (integer + 18 sub-pel) */
+} hmgpu_me_result;                /* 24 bytes */
+
+/* host buffers in, host buffers out; blocking */
+int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
+                    const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results);
+/* device-resident variant used for kernel-only timing: d_jobs/d_results are device pointers,
+ * asynchronous on hmgpu_stream(); call hmgpu_synchronize() to wait */
+int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs,
+                           const void* d_org_blocks, void* d_results);
+
+/* Host-side helpers with the reference's exact arithmetic (cheap, scalar):
+ * TComDataCU::clipMv bounds (TComDataCU.cpp:2917-2929) and xSetSearchRange
+ * (TEncSearch.cpp:3911-3927). */
+void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4]);
+void hmgpu_search_range(const int16_t bounds[4], int pred_x, int pred_y, int srch_rng, int16_t ltrb[4]);
+
+/* ------------------------------------------------------------------------------------------
+ * Distortion family, batched.  Replaces DistParam::DistFunc / TComRdCost::m_afpDistortFunc
+ * (TComRdCost.h:60-109, TComRdCost.cpp:223-276) evaluated on caller-supplied Pel blocks:
+ * one item = one DistFunc(&DistParam) call.
+ * ------------------------------------------------------------------------------------------ */
+enum
+{
+  HMGPU_DF_SAD = 0,      /* xGetSAD4..64 / 12/24/48 (TComRdCost.cpp:493-964): honours sub_shift */
+  HMGPU_DF_SAD_GENERIC,  /* xGetSAD (:465-491): ignores sub_shift */
+  HMGPU_DF_HADS,         /* xGetHADs (:1537-1604) */
+  HMGPU_DF_SSE           /* xGetSSE* (:970-1315) */
+};
+
+typedef struct hmgpu_dist_item
+{
+  uint32_t org_offset, cur_offset; /* element offsets into the two Pel arrays */
+  int32_t  org_stride, cur_stride;
+  uint8_t  w, h;
+  uint8_t  func;                   /* HMGPU_DF_* */
+  uint8_t  sub_shift;              /* DistParam::iSubShift */
+} hmgpu_dist_item;
+
+int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_t* cur, int n_cur,
+                     const hmgpu_dist_item* items, int n_items, uint32_t* out);
+
+/* MV rate cost, TComRdCost::getCost(x,y)/getBits (TComRdCost.h:171-188); host-side scalar */
+uint32_t hmgpu_mv_bits(int pred_x, int pred_y, int scale, int x, int y);
+uint32_t hmgpu_mv_cost(uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y);
+
+/* ------------------------------------------------------------------------------------------
+ * Motion compensation from the phase planes: TComPrediction::xPredInterBlk
+ * (TComPrediction.cpp:660-698) for luma, uni-directional (clipped output).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmgpu_mc_job
+{
+  int16_t pu_x, pu_y;
+  uint8_t pu_w, pu_h;
+  uint8_t ref_slot;
+  uint8_t reserved;
+  int16_t mv_x, mv_y;             /* quarter-pel, already clipped by the caller (clipMv) */
+  uint32_t dst_offset;            /* element offset of the w x h output block (stride w) */
+} hmgpu_mc_job;
+
+int hmgpu_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* jobs, int n_jobs, int16_t* dst, int n_dst);
+
+/* ------------------------------------------------------------------------------------------
+ * Residual costing: forward core transform and scalar quantiser, batched over TUs.
+ * hmgpu_fwd_transform replaces TComTrQuant::xT -> xTrMxN -> partialButterfly4/8/16/32 /
+ * fastForwardDst (TComTrQuant.cpp:1805-1827, 836-885, 387-758).  Input: n_tus residual
+ * blocks of n x n Pel, each contiguous row-major; output n x n TCoeff each.
+ * hmgpu_quant replaces the scalar branch of TComTrQuant::xQuant (TComTrQuant.cpp:1120-1199,
+ * flat scaling list, no sign hiding); RDOQ stays on the host.
+ * ------------------------------------------------------------------------------------------ */
+int hmgpu_fwd_transform(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, int use_dst,
+                        int32_t* coeff);
+int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_per, int qp_rem,
+                int is_intra_slice, int32_t* level, int32_t* delta_u, uint32_t* abs_sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMGPU_H */

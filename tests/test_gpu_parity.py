@@ -1,0 +1,278 @@
+"""GPU parity tests: libhmgpu (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bit-exact: all of this is integer arithmetic."""
+import numpy as np
+import pytest
+
+import hmgpu
+import synth
+import worklist
+from oracle import binding as B
+from util import M, assert_results_equal, oracle_me, padded_ref
+
+pytestmark = pytest.mark.gpu
+
+W, H = 416, 240
+
+
+def _frames(bit_depth, n=5, noise=False, seed=1234):
+    if noise:
+        return np.random.default_rng(seed).integers(0, 1 << bit_depth, (n, H, W)).astype(np.int16)
+    return synth.luma_frames(W, H, n, bit_depth, seed).astype(np.int16)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_phase_planes_match_oracle(bit_depth):
+    fr = _frames(bit_depth, 1, noise=True)
+    pad = padded_ref(fr[0])
+    exp = np.zeros((16,) + pad.shape, np.int16)
+    B.oracle().hmo_phase_planes(pad, pad.shape[1], pad.shape[0], bit_depth, exp)
+    with hmgpu.Context(W, H, bit_depth, 2) as ctx:
+        ctx.ref_upload(1, fr[0])
+        for fy in range(4):
+            for fx in range(4):
+                got = ctx.ref_plane(1, fx, fy)
+                assert np.array_equal(got, exp[fy * 4 + fx]), (fx, fy)
+
+
+def _random_jobs(rng, n, bit_depth, mode, n_refs, org_blocks=None):
+    """jobs over all PU shapes; mode in {'tz','fs','frac'}"""
+    shapes = [(64, 64), (32, 32), (16, 16), (8, 8), (32, 64), (64, 32), (16, 32), (32, 16), (8, 16), (16, 8),
+              (8, 4), (4, 8), (12, 16), (16, 12), (24, 32), (32, 24), (4, 16), (16, 4), (32, 8), (8, 32),
+              (64, 16), (16, 64), (64, 48), (48, 64)]
+    jobs = np.zeros(n, hmgpu.ME_JOB)
+    blocks = []
+    off = 0
+    for i in range(n):
+        w, h = shapes[i % len(shapes)]
+        cus = 8 if max(w, h) <= 8 else 16 if max(w, h) <= 16 else 32 if max(w, h) <= 32 else 64
+        cx = int(rng.integers(0, W // cus)) * cus
+        cy = int(rng.integers(0, H // cus)) * cus
+        px = cx + int(rng.integers(0, (cus - w) // 4 + 1)) * 4
+        py = cy + int(rng.integers(0, (cus - h) // 4 + 1)) * 4
+        j = jobs[i]
+        j["pu_x"], j["pu_y"], j["pu_w"], j["pu_h"] = px, py, w, h
+        j["ref_slot"] = int(rng.integers(0, n_refs))
+        k = i % 11
+        if k == 0:
+            pred = (int(rng.integers(-3000, 3000)), int(rng.integers(-2000, 2000)))
+        elif k < 4:
+            pred = (int(rng.integers(-400, 400)), int(rng.integers(-400, 400)))
+        else:
+            pred = (int(rng.integers(-40, 40)), int(rng.integers(-40, 40)))
+        j["pred_x"], j["pred_y"] = pred
+        bd = hmgpu.clip_bounds(W, H, cx, cy)
+        j["clip_hmin"], j["clip_hmax"], j["clip_vmin"], j["clip_vmax"] = bd
+        sr = 64 if mode != "fs" else int(rng.choice([4, 8, 24, 64]))
+        j["search_range"] = sr
+        j["win_l"], j["win_t"], j["win_r"], j["win_b"] = hmgpu.search_range(bd, pred[0], pred[1], sr)
+        j["ui_cost"] = worklist.lambda_to_cost(float(rng.uniform(4, 200)))
+        fl = hmgpu.F_FRAC
+        if i % 5:
+            fl |= hmgpu.F_FEN
+        if i % 6:
+            fl |= hmgpu.F_HADME
+        if i % 13 == 0:
+            fl |= hmgpu.F_LOSSLESS
+        if mode == "frac":
+            ltrb = [int(v) for v in (j["win_l"], j["win_t"], j["win_r"], j["win_b"])]
+            j["start_x"] = int(rng.integers(ltrb[0], ltrb[2] + 1))
+            j["start_y"] = int(rng.integers(ltrb[1], ltrb[3] + 1))
+        else:
+            fl |= hmgpu.F_INTEGER
+            j["start_x"], j["start_y"] = pred
+            if mode == "fs":
+                fl |= hmgpu.F_FULL
+            elif i % 2:
+                fl |= hmgpu.F_HAS_2NX2N
+                j["i2n_x"], j["i2n_y"] = int(rng.integers(-30, 30)), int(rng.integers(-30, 30))
+        if org_blocks is not None and i % 3 == 0:
+            fl |= hmgpu.F_ORG_BLOCK
+            j["org_offset"] = off
+            blocks.append((i, w, h))
+            off += w * h
+        j["flags"] = fl
+    return jobs, blocks, off
+
+
+def _run(bit_depth, mode, n, noise=False, with_blocks=False, seed=5):
+    rng = np.random.default_rng(seed)
+    fr = _frames(bit_depth, 4, noise)
+    org = fr[3]
+    jobs, blocks, n_elems = _random_jobs(rng, n, bit_depth, mode, 3, org_blocks=True if with_blocks else None)
+    org_blocks = None
+    if with_blocks:
+        # bi-pred style key pattern 2*org - pred: leaves the pixel range (TComYuv.cpp:415)
+        org_blocks = np.zeros(max(1, n_elems), np.int16)
+        mx = (1 << bit_depth) - 1
+        for (i, w, h) in blocks:
+            j = jobs[i]
+            o = org[int(j["pu_y"]):int(j["pu_y"]) + h, int(j["pu_x"]):int(j["pu_x"]) + w].astype(np.int32)
+            p = rng.integers(0, mx + 1, (h, w))
+            org_blocks[int(j["org_offset"]):int(j["org_offset"]) + w * h] = (2 * o - p).astype(np.int16).ravel()
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    exp = oracle_me(jobs, pads, org, bit_depth, org_blocks)
+    with hmgpu.Context(W, H, bit_depth, 3) as ctx:
+        for k in range(3):
+            ctx.ref_upload(k, fr[k])
+        ctx.org_upload(org)
+        got = ctx.me_search(jobs, org_blocks)
+    assert_results_equal(got, exp, jobs)
+    return got
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+@pytest.mark.parametrize("noise", [False, True])
+def test_tz_search_and_frac(bit_depth, noise):
+    _run(bit_depth, "tz", 600, noise=noise)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_full_search_and_frac(bit_depth):
+    _run(bit_depth, "fs", 96)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_frac_only(bit_depth):
+    _run(bit_depth, "frac", 400)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+@pytest.mark.parametrize("mode", ["tz", "fs", "frac"])
+def test_bipred_key_pattern_blocks(bit_depth, mode):
+    _run(bit_depth, mode, 120 if mode != "fs" else 48, with_blocks=True)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_dist_batch_matches_oracle(bit_depth):
+    rng = np.random.default_rng(11)
+    O = B.oracle()
+    mx = (1 << bit_depth) - 1
+    org = rng.integers(-mx, 2 * mx + 1, 64 * 80).astype(np.int16)
+    cur = rng.integers(0, mx + 1, 64 * 96).astype(np.int16)
+    items, exp = [], []
+    sizes = [4, 8, 12, 16, 24, 32, 48, 64]
+    for w in sizes:
+        for h in sizes:
+            for func in (hmgpu.DF_SAD, hmgpu.DF_SAD_GENERIC, hmgpu.DF_HADS, hmgpu.DF_SSE):
+                for ss in ((0, 1, 2) if func in (hmgpu.DF_SAD, hmgpu.DF_SAD_GENERIC) else (0,)):
+                    oo, co = int(rng.integers(0, 16)), int(rng.integers(0, 32))
+                    items.append((oo, co, 80, 96, w, h, func, ss))
+                    po, pc = B.ptr(org, oo), B.ptr(cur, co)
+                    if func == hmgpu.DF_SAD:
+                        exp.append(O.hmo_sad(po, 80, pc, 96, w, h, ss, bit_depth, 0))
+                    elif func == hmgpu.DF_SAD_GENERIC:
+                        exp.append(O.hmo_sad(po, 80, pc, 96, w, h, ss, bit_depth, 1))
+                    elif func == hmgpu.DF_HADS:
+                        exp.append(O.hmo_hads(po, 80, pc, 96, w, h, bit_depth))
+                    else:
+                        exp.append(O.hmo_sse(po, 80, pc, 96, w, h, bit_depth))
+    # 2x2-tiled SATD (chroma-sized blocks) and ragged sizes
+    for (w, h) in [(2, 2), (6, 2), (2, 6), (6, 6), (10, 14)]:
+        items.append((0, 0, 80, 96, w, h, hmgpu.DF_HADS, 0))
+        exp.append(O.hmo_hads(B.ptr(org), 80, B.ptr(cur), 96, w, h, bit_depth))
+    for (w, h) in [(1, 1), (3, 5), (7, 64), (63, 1)]:
+        items.append((5, 9, 80, 96, w, h, hmgpu.DF_SAD_GENERIC, 0))
+        exp.append(O.hmo_sad(B.ptr(org, 5), 80, B.ptr(cur, 9), 96, w, h, 0, bit_depth, 1))
+        items.append((5, 9, 80, 96, w, h, hmgpu.DF_SSE, 0))
+        exp.append(O.hmo_sse(B.ptr(org, 5), 80, B.ptr(cur, 9), 96, w, h, bit_depth))
+    it = np.array(items, dtype=hmgpu.DIST_ITEM)
+    with hmgpu.Context(W, H, bit_depth, 1) as ctx:
+        got = ctx.dist_batch(org, cur, it)
+        assert len(ctx.dist_batch(org, cur, it[:0])) == 0      # empty batch
+    assert np.array_equal(got, np.array(exp, np.uint32))
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_fwd_transform_and_quant(bit_depth):
+    rng = np.random.default_rng(13)
+    O = B.oracle()
+    with hmgpu.Context(W, H, bit_depth, 1) as ctx:
+        for n in (4, 8, 16, 32):
+            for use_dst in ((False, True) if n == 4 else (False,)):
+                resi = rng.integers(-(1 << bit_depth) + 1, 1 << bit_depth, (37, n, n)).astype(np.int16)
+                resi[0] = (1 << bit_depth) - 1      # extremes
+                resi[1] = -(1 << bit_depth) + 1
+                got = ctx.fwd_transform(resi, n, use_dst)
+                exp = np.zeros_like(got)
+                for t in range(len(resi)):
+                    O.hmo_fwd_transform(bit_depth, np.ascontiguousarray(resi[t], np.int32), exp[t], n, n, int(use_dst))
+                assert np.array_equal(got, exp), (n, use_dst)
+                for (per, rem, intra) in [(5, 2, 0), (4, 3, 1), (6, 0, 0)]:
+                    lv, du, sm = ctx.quant(got, n, per, rem, intra)
+                    log2n = n.bit_length() - 1
+                    tshift = 15 - bit_depth - log2n
+                    for t in range(len(resi)):
+                        el = np.zeros(n * n, np.int32)
+                        ed = np.zeros(n * n, np.int32)
+                        es = O.hmo_quant(np.ascontiguousarray(got[t].ravel()), n * n, per, rem, tshift, intra, el, ed)
+                        assert np.array_equal(lv[t].ravel(), el) and np.array_equal(du[t].ravel(), ed) and sm[t] == es
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_mc_luma_matches_oracle(bit_depth):
+    rng = np.random.default_rng(17)
+    O = B.oracle()
+    fr = _frames(bit_depth, 2, noise=True)
+    pad = padded_ref(fr[0])
+    pw = pad.shape[1]
+    jobs = np.zeros(200, hmgpu.MC_JOB)
+    off = 0
+    exp = []
+    for i in range(len(jobs)):
+        w, h = [(8, 8), (16, 16), (64, 64), (4, 8), (12, 16), (32, 24)][i % 6]
+        x = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+        y = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+        mvx = int(rng.integers(max(-280, (-70 - x) * 4), min(280, (W + 6 - x - w) * 4)))
+        mvy = int(rng.integers(max(-280, (-70 - y) * 4), min(280, (H + 6 - y - h) * 4)))
+        jobs[i] = (x, y, w, h, 0, 0, mvx, mvy, off)
+        e = np.zeros((h, w), np.int16)
+        O.hmo_pred_inter_blk(0, B.ptr(pad, (y + M) * pw + x + M), pw, mvx, mvy, w, h, 0, bit_depth, B.ptr(e), w)
+        exp.append(e.ravel())
+        off += w * h
+    with hmgpu.Context(W, H, bit_depth, 1) as ctx:
+        ctx.ref_upload(0, fr[0])
+        got = ctx.mc_luma(jobs, off)
+    assert np.array_equal(got, np.concatenate(exp))
+
+
+def test_errors_are_reported_not_thrown():
+    with hmgpu.Context(W, H, 8, 2) as ctx:
+        jobs = worklist.frame_jobs(W, H, n_refs=1)[:4]
+        with pytest.raises(hmgpu.HmGpuError, match="not uploaded"):
+            ctx.me_search(jobs)
+        ctx.ref_upload(0, np.zeros((H, W), np.int16))
+        ctx.org_upload(np.zeros((H, W), np.int16))
+        bad = jobs.copy()
+        bad["pu_w"][0] = 5
+        with pytest.raises(hmgpu.HmGpuError, match="unsupported"):
+            ctx.me_search(bad)
+        assert len(ctx.me_search(jobs[:0])) == 0
+    with pytest.raises(hmgpu.HmGpuError):
+        hmgpu.Context(W + 1, H, 8, 2)
+
+
+def test_full_size_1080p_properties():
+    """BASELINE cfg-2 size: size-independent properties instead of a (slow) full oracle pass."""
+    w, h = 1920, 1080
+    fr = synth.luma_frames(w, h, 2, 8).astype(np.int16)
+    jobs = worklist.frame_jobs(w, h, n_refs=1)
+    with hmgpu.Context(w, h, 8, 1) as ctx:
+        ctx.ref_upload(0, fr[0])
+        # 1) a picture searched against itself finds the zero vector with zero SAD everywhere
+        ctx.org_upload(fr[0])
+        z = jobs.copy()
+        z["pred_x"] = z["pred_y"] = z["start_x"] = z["start_y"] = 0
+        bd = worklist.clip_bounds_np(w, h, -(z["clip_hmin"].astype(np.int32) // 4) - 71, -(z["clip_vmin"].astype(np.int32) // 4) - 71)
+        z["win_l"], z["win_t"], z["win_r"], z["win_b"] = worklist.search_range_np(bd, 0, 0, 64)
+        r = ctx.me_search(z)
+        assert (r["int_x"] == 0).all() and (r["int_y"] == 0).all() and (r["int_sad"] == 0).all()
+        assert (r["half_x"] == 0).all() and (r["qter_y"] == 0).all()
+        # 2) real motion: spot-check a seeded sample of the full job list against the oracle
+        ctx.org_upload(fr[1])
+        r = ctx.me_search(jobs)
+        idx = np.random.default_rng(3).choice(len(jobs), 300, replace=False)
+        exp = oracle_me(jobs[idx], [padded_ref(fr[0])], fr[1], 8)
+        assert_results_equal(r[idx], exp, jobs[idx])
+        # 3) idempotence: the same batch again gives the same bytes
+        r2 = ctx.me_search(jobs)
+        assert r.tobytes() == r2.tobytes()
