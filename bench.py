@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the HM-16.2 inter-search hot path on B200 (libhmgpu) beside the
+reference's own CPU implementation.
+
+Workload (BASELINE.json configs[1]): encoder_lowdelay_P_main.cfg, 1920x1080 8-bit, TZSearch
+(FastSearch=1, SearchRange=64), FEN=1, HadamardME=1, 4 reference pictures, QP 32 lambda.
+One "step" = the whole motion-estimation work of ONE P picture: the newest reference is turned
+into its 16 quarter-pel planes, the source picture is installed, and every PU of every CU of
+the CTU quadtree is searched against all 4 references (worklist.frame_jobs: ~760 k
+xMotionEstimation bodies = TZ integer search + half/quarter-pel SATD refinement each).
+
+  value : ME Gcandidates/s, inputs resident in HBM, CUDA events on the library's own stream.
+  e2e   : the same step through the C ABI with HOST buffers (reference upload, source upload,
+          job list in, results out), wall clock around blocking calls, copies included.
+  --impl reference : the reference's own xTZSearch + xPatternSearchFracDIF (oracle/_ref/libhmref.so,
+          compiled from the unmodified HM sources) over a bounded sample of the same job list
+          on all host cores.
+
+Run:  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hm-16.2_b200"))
+sys.path.insert(0, ROOT)
+
+PIC_W, PIC_H, BIT_DEPTH, N_REFS, SEARCH_RANGE, LAMBDA = 1920, 1080, 8, 4, 64, 57.9
+METRIC = "ME Gcand/s (1080p lowdelay_P TZSearch, bit-exact vs CPU HM)"
+UNIT = "Gcand/s"
+
+
+def workload_config(n_jobs):
+    return {"workload": "encoder_lowdelay_P_main.cfg 1920x1080 8-bit TZSearch SR64 FEN1 HADME1 4 refs QP32: "
+                        "all PUs of one P picture x 4 references per step",
+            "jobs_per_step": int(n_jobs), "pic": "%dx%d" % (PIC_W, PIC_H), "bit_depth": BIT_DEPTH,
+            "n_refs": N_REFS, "search_range": SEARCH_RANGE,
+            "l2": "inputs larger than L2 (4 refs x 16 planes = 165 MB + 36 MB jobs + work lists; rotating reference slot)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_work(jobs, results):
+    """SURVEY.md 8(d) per-unit figures x the units of one step (independent of GPU tricks).
+    -> dict stage -> (int_ops, bytes)"""
+    import hmgpu
+    w = jobs["pu_w"].astype(np.int64)
+    h = jobs["pu_h"].astype(np.int64)
+    fen = (jobs["flags"] & hmgpu.F_FEN) != 0
+    rows = np.where(fen & (h > 8), h // 2, h)
+    int_cand = results["n_cand"].astype(np.int64) - 18
+    # integer SAD candidate: W*(H>>s) abs-diff-accumulates (+1 MV cost); bytes: 1 B/sample org + ref footprint
+    tz_ops = int((int_cand * (w * rows + 1)).sum())
+    tz_bytes = int((int_cand * w * rows * 2).sum())
+    # SATD candidate: 576 int ops per 8x8 tile, 112 per 4x4 tile; 18 candidates share one (W+8)x(H+8) footprint
+    t8 = ((w % 8) == 0) & ((h % 8) == 0)
+    tiles = np.where(t8, (w // 8) * (h // 8), (w // 4) * (h // 4))
+    per_tile = np.where(t8, 576, 112)
+    frac_ops = int((18 * tiles * per_tile).sum())
+    frac_bytes = int(((w + 8) * (h + 8) + w * h).sum())
+    plane_bytes = (PIC_W + 160) * (PIC_H + 160)
+    return {"tz": (tz_ops, tz_bytes), "frac_dist": (frac_ops, frac_bytes),
+            "planes": (192 * plane_bytes, 17 * plane_bytes)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import hmgpu
+    import synth
+    import worklist
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+
+    # every rank codes its own picture (segment sharding: independent inputs, no exchange)
+    frames = synth.luma_frames(PIC_W, PIC_H, N_REFS + 2, BIT_DEPTH, seed=1234 + rank).astype(np.int16)
+    # slot k holds frame k, the picture being coded is frame N_REFS + 1
+    jobs = worklist.frame_jobs(PIC_W, PIC_H, n_refs=N_REFS, seed=7 + rank, search_range=SEARCH_RANGE, lam=LAMBDA,
+                               ref_dist=[N_REFS + 1 - k for k in range(N_REFS)])
+    n_jobs = len(jobs)
+    flags_any = int(np.bitwise_or.reduce(jobs["flags"]))
+    ctx = hmgpu.Context(PIC_W, PIC_H, BIT_DEPTH, N_REFS, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    d_frames = torch.from_numpy(frames).cuda()
+    d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(n_jobs, -1).copy()).cuda()
+    d_res = torch.zeros((n_jobs, hmgpu.ME_RESULT.itemsize), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for s in range(N_REFS):
+        ctx.ref_upload_device(s, d_frames[s].data_ptr(), PIC_W)
+    ctx.synchronize()
+
+    def step_device(i):
+        # the newest reconstructed picture replaces the oldest reference slot, then one picture of ME
+        ctx.ref_upload_device(i % N_REFS, d_frames[i % N_REFS].data_ptr(), PIC_W)
+        ctx.org_upload_device(d_frames[N_REFS + 1].data_ptr(), PIC_W)
+        ctx.me_search_device(d_jobs.data_ptr(), n_jobs, None, d_res.data_ptr(), flags_any)
+
+    def step_host(i):
+        ctx.ref_upload(i % N_REFS, frames[i % N_REFS])
+        ctx.org_upload(frames[N_REFS + 1])
+        return ctx.me_search(jobs)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    # ---- kernel-resident timing --------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    ctx.profile_read(reset=True)
+    ctx.profile_enable(True)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
+    res = d_res.cpu().numpy().view(hmgpu.ME_RESULT).reshape(-1)
+    cand_per_step = int(res["n_cand"].astype(np.int64).sum())
+
+    # ---- end-to-end through the C ABI with host buffers ----------------------------------------
+    for i in range(min(2, args.warmup)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res_h = step_host(args.warmup + i)
+    ctx.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    assert len(res_h) == n_jobs
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(cand_per_step)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_cand = float(c[0])
+
+    if rank == 0:
+        value = total_cand * args.steps / (dev_ms * 1e-3) / 1e9
+        e2e_value = total_cand * args.steps / (e2e_ms * 1e-3) / 1e9
+        frame_bytes = PIC_W * PIC_H * 2
+        work = algorithmic_work(jobs, res)
+        stage_ms = {k: v[0] / args.steps for k, v in prof.items() if v[1]}
+        dom = max((k for k in stage_ms if k in work), key=lambda k: stage_ms[k])
+        int_peak = ctx.microbench(0)
+        sad4_peak = ctx.microbench(1)
+        ops, byts = work[dom]
+        dur = stage_ms[dom] * 1e-3
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": byts / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": byts / dur / 1e9 / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "note": "this kernel is INT32-pipe bound, not HBM bound: see roofline_int32"}
+        roofline_int32 = {"kernel": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak,
+                          "unit": "Gop/s", "frac": ops / dur / 1e9 / int_peak,
+                          "peak_source": "hmgpu_microbench(0) LOP3+IADD lane-ops/s measured in this run",
+                          "vabsdiff4_peak_glaneops": sad4_peak,
+                          "per_stage": {k: {"ms": stage_ms[k], "gops": work[k][0] / (stage_ms[k] * 1e-3) / 1e9,
+                                            "gbs": work[k][1] / (stage_ms[k] * 1e-3) / 1e9} for k in stage_ms if k in work}}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8", "data": "synthetic", "config": workload_config(n_jobs),
+               "candidates_per_step": total_cand, "jobs_per_s": n_jobs * world * args.steps / (dev_ms * 1e-3),
+               "pictures_per_s_me_only": world * args.steps / (dev_ms * 1e-3),
+               "clocks": clocks, "gpu_launches": int(launches),
+               "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                       "h2d_bytes_per_step": int(2 * frame_bytes + jobs.nbytes),
+                       "d2h_bytes_per_step": int(res.nbytes), "timing": "wall clock around the blocking C-ABI calls"},
+               "stage_ms_per_step": stage_ms, "roofline": roofline, "roofline_int32": roofline_int32}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=1)
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---- the reference on the host cores ------------------------------------------------------------
+
+def _cpu_worker(a):
+    kind, jobs_bytes, n, frames, bit_depth = a
+    import hmgpu
+    from oracle import binding as B
+
+    def padded_ref(luma):
+        # the reference reads its padded reconstruction (TComPicYuv::extendPicBorder, margin 80)
+        out = np.zeros((PIC_H + 160, PIC_W + 160), np.int16)
+        B.oracle().hmo_extend_border(np.ascontiguousarray(luma, np.int16), PIC_W, PIC_H, 80, out)
+        return out
+
+    jobs = np.frombuffer(jobs_bytes, dtype=hmgpu.ME_JOB)
+    pads = [padded_ref(frames[k]) for k in range(N_REFS)]
+    fn = B.ref().ref_me_batch if kind == "reference" else B.oracle().hmo_me_batch
+    t0 = time.perf_counter()
+    _, cpu_s = B.me_batch(fn, jobs, pads, frames[N_REFS + 1], bit_depth)
+    wall = time.perf_counter() - t0
+    cnt, _ = B.me_batch(B.oracle().hmo_me_batch, jobs, pads, frames[N_REFS + 1], bit_depth)   # untimed: candidate count
+    cand = int(cnt.view(hmgpu.ME_RESULT)["n_cand"].astype(np.int64).sum())
+    return cpu_s, wall, cand
+
+
+def cpu_reference_run(jobs, frames, sample_jobs, procs):
+    """time the reference's xTZSearch + xPatternSearchFracDIF on a bounded, evenly spaced sample
+    of the step's job list, `procs` processes (the reference is single-threaded per process)."""
+    from oracle import binding as B
+    kind = "reference" if B.have_ref() else "port"
+    stride = max(1, len(jobs) // max(1, sample_jobs))
+    sample = np.ascontiguousarray(jobs[::stride][:sample_jobs])
+    chunks = np.array_split(sample, procs)
+    argsl = [(kind, np.ascontiguousarray(c).tobytes(), len(c), frames, BIT_DEPTH) for c in chunks if len(c)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        outs = [_cpu_worker(argsl[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            outs = pool.map(_cpu_worker, argsl)
+    wall = max(o[1] for o in outs)
+    cand = sum(o[2] for o in outs)
+    return {"value": cand / wall / 1e9, "unit": UNIT, "cores": procs, "kind": kind,
+            "sample": "%d of %d jobs of one step (every %dth), %s xTZSearch+xPatternSearchFracDIF, %.1f s wall"
+                      % (len(sample), len(jobs), stride, "libhmref.so" if kind == "reference" else "oracle/hm_oracle.c", wall),
+            "jobs_per_s": len(sample) / wall, "seconds": wall, "total_s_incl_setup": time.perf_counter() - t0}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import synth
+    import worklist
+    frames = synth.luma_frames(PIC_W, PIC_H, N_REFS + 2, BIT_DEPTH, seed=1234).astype(np.int16)
+    jobs = worklist.frame_jobs(PIC_W, PIC_H, n_refs=N_REFS, seed=7, search_range=SEARCH_RANGE, lam=LAMBDA,
+                               ref_dist=[N_REFS + 1 - k for k in range(N_REFS)])
+    procs = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample * procs // 4, procs=procs)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    secs = float(np.mean([r["seconds"] for r in vals]))
+    last = vals[-1]
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(len(jobs)),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=120000, help="jobs in the CPU baseline sample (1 core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -373,15 +373,18 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   return HMGPU_OK;
 }
 
-int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const void* d_org_blocks, void* d_results)
+int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const void* d_org_blocks, void* d_results,
+                           int flags_any)
 {
   if (!ctx) return HMGPU_E_INVALID;
   if (n_jobs == 0) return HMGPU_OK;
   if (!d_jobs || !d_results || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  // jobs are not visible to the host: run every stage, worst-case full-search window (SR 64, 64x64)
+  // jobs are not visible to the host: worst-case full-search window (SR 64, 64x64 PU)
+  const bool integer = (flags_any & HMGPU_F_INTEGER) != 0, full = (flags_any & HMGPU_F_FULL) != 0;
   return hmgpu_launch_me(ctx, (const hmgpu_me_job*)d_jobs, n_jobs, (const int16_t*)d_org_blocks,
-                         (hmgpu_me_result*)d_results, d_org_blocks != NULL, true, true, true, 64 * 1024);
+                         (hmgpu_me_result*)d_results, (flags_any & HMGPU_F_ORG_BLOCK) != 0, integer && full,
+                         integer, (flags_any & HMGPU_F_FRAC) != 0, 64 * 1024);
 }
 
 void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4])

@@ -90,8 +90,8 @@ int hmgpu_launch_dist(hmgpu_ctx* ctx, const int16_t* d_org, const int16_t* d_cur
 {
   const int warps_per_block = 4;
   const int blocks = (n_items + warps_per_block - 1) / warps_per_block;
+  HmgpuStage st(ctx, HMGPU_ST_DIST, 1);
   dist_batch_kernel<<<blocks, warps_per_block * 32, 0, ctx->stream>>>(d_org, d_cur, d_items, n_items, ctx->bit_depth, d_out);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

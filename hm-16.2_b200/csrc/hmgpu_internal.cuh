@@ -51,7 +51,36 @@ struct hmgpu_ctx
   void* d_stage; size_t d_stage_bytes; // device
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
   uint64_t launches;
+  // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
+  bool prof_on;
+  int prof_n;                          // event pairs in flight
+  cudaEvent_t prof_ev[2 * 1024];
+  int prof_stage[1024];
+  double prof_ms[16];
+  uint64_t prof_launches[16];
   char err[512];
+};
+
+enum
+{
+  HMGPU_ST_PLANES = 0, HMGPU_ST_ORG, HMGPU_ST_TZ, HMGPU_ST_FULL, HMGPU_ST_FRAC_EXPAND, HMGPU_ST_FRAC_DIST,
+  HMGPU_ST_FRAC_SELECT, HMGPU_ST_DIST, HMGPU_ST_TRANSFORM, HMGPU_ST_QUANT, HMGPU_ST_MC, HMGPU_ST_COUNT
+};
+
+void hmgpu_prof_begin(hmgpu_ctx* ctx, int stage);
+void hmgpu_prof_end(hmgpu_ctx* ctx);
+
+// RAII: counts the launches of one stage and, when profiling is on, brackets them with events
+struct HmgpuStage
+{
+  hmgpu_ctx* ctx;
+  HmgpuStage(hmgpu_ctx* c, int stage, int n_launches) : ctx(c)
+  {
+    c->launches += n_launches;
+    c->prof_launches[stage] += n_launches;
+    if (c->prof_on) hmgpu_prof_begin(c, stage);
+  }
+  ~HmgpuStage() { if (ctx->prof_on) hmgpu_prof_end(ctx); }
 };
 
 int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...);

@@ -229,8 +229,10 @@ int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
   const int tb = 128;
-  frac_expand_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, work, work_count, acc);
-  ctx->launches += 1;
+  {
+    HmgpuStage st(ctx, HMGPU_ST_FRAC_EXPAND, 1);
+    frac_expand_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, work, work_count, acc);
+  }
   if (any_frac)
   {
     // grid-stride over a device-side item count: enough CTAs to fill the machine
@@ -239,12 +241,15 @@ int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
     const int grid = (int)(want < (long long)HMGPU_NUM_SMS * 16 ? (want < 1 ? 1 : want) : (long long)HMGPU_NUM_SMS * 16);
     for (int phase = 0; phase < 2; phase++)
     {
+      {
+      HmgpuStage st(ctx, HMGPU_ST_FRAC_DIST, 1);
       if (ctx->px_bytes == 1)
         frac_dist_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase);
       else
         frac_dist_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase);
+      }
+      HmgpuStage st2(ctx, HMGPU_ST_FRAC_SELECT, 1);
       frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase);
-      ctx->launches += 2;
     }
   }
   HMGPU_CUDA(ctx, cudaGetLastError());

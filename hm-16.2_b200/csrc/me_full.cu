@@ -225,6 +225,7 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  HmgpuStage st(ctx, HMGPU_ST_FULL, 1);
   if (ctx->px_bytes == 1 && !any_org_block)
   {
     if (!s_attr_set)
@@ -239,7 +240,6 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
     full_search_generic_kernel<uint8_t><<<n_jobs, FS_THREADS, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
   else
     full_search_generic_kernel<uint16_t><<<n_jobs, FS_THREADS, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

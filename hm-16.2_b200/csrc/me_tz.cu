@@ -347,13 +347,13 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
   const int blocks = (n_jobs + TZ_WARPS - 1) / TZ_WARPS;
+  HmgpuStage st(ctx, HMGPU_ST_TZ, 1);
   if (ctx->px_bytes == 1 && !any_org_block)
     tz_search_kernel<uint8_t, true><<<blocks, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
   else if (ctx->px_bytes == 1)
     tz_search_kernel<uint8_t, false><<<blocks, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
   else
     tz_search_kernel<uint16_t, false><<<blocks, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

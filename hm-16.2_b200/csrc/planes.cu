@@ -142,10 +142,10 @@ static int launch_planes_t(hmgpu_ctx* ctx, int slot, const int16_t* d_src, int s
 {
   Px* planes = (Px*)ctx->refs[slot].planes;
   dim3 b(32, 8), g((ctx->pw + 31) / 32, (ctx->ph + 7) / 8);
+  HmgpuStage st(ctx, HMGPU_ST_PLANES, 2);
   pad_convert_kernel<Px><<<g, b, 0, ctx->stream>>>(d_src, src_stride, ctx->pic_w, ctx->pic_h, planes, ctx->pitch, ctx->pw, ctx->ph);
   dim3 g2((ctx->pw + PP_TX - 1) / PP_TX, (ctx->ph + PP_TY - 1) / PP_TY);
   phase_planes_kernel<Px><<<g2, 256, 0, ctx->stream>>>(planes, ctx->plane_elems, ctx->pitch, ctx->pw, ctx->ph, ctx->bit_depth);
-  ctx->launches += 2;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }
@@ -159,8 +159,8 @@ int hmgpu_launch_planes(hmgpu_ctx* ctx, int slot, const int16_t* d_src, int src_
 int hmgpu_launch_chroma(hmgpu_ctx* ctx, int16_t* d_dst, const int16_t* d_src, int src_stride)
 {
   dim3 b(32, 8), g((ctx->cpw + 31) / 32, (ctx->cph + 7) / 8);
+  HmgpuStage st(ctx, HMGPU_ST_PLANES, 1);
   pad_chroma_kernel<<<g, b, 0, ctx->stream>>>(d_src, src_stride, ctx->pic_w / 2, ctx->pic_h / 2, d_dst, ctx->cpitch, ctx->cpw, ctx->cph);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }
@@ -168,11 +168,11 @@ int hmgpu_launch_chroma(hmgpu_ctx* ctx, int16_t* d_dst, const int16_t* d_src, in
 int hmgpu_launch_org(hmgpu_ctx* ctx, const int16_t* d_src, int src_stride)
 {
   dim3 b(32, 8), g((ctx->pic_w + 31) / 32, (ctx->pic_h + 7) / 8);
+  HmgpuStage st(ctx, HMGPU_ST_ORG, 1);
   if (ctx->px_bytes == 1)
     copy_convert_kernel<uint8_t><<<g, b, 0, ctx->stream>>>(d_src, src_stride, ctx->pic_w, ctx->pic_h, (uint8_t*)ctx->d_org, ctx->org_pitch);
   else
     copy_convert_kernel<uint16_t><<<g, b, 0, ctx->stream>>>(d_src, src_stride, ctx->pic_w, ctx->pic_h, (uint16_t*)ctx->d_org, ctx->org_pitch);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

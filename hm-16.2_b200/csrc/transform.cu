@@ -69,6 +69,7 @@ fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, i
 
 int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff)
 {
+  HmgpuStage st(ctx, HMGPU_ST_TRANSFORM, 1);
   switch (n)
   {
     case 4:  fwd_transform_kernel<4><<<(n_tus + 15) / 16, 256, 0, ctx->stream>>>(d_resi, n_tus, use_dst, ctx->bit_depth, d_coeff); break;
@@ -77,7 +78,6 @@ int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus,
     case 32: fwd_transform_kernel<32><<<n_tus, 256, 0, ctx->stream>>>(d_resi, n_tus, 0, ctx->bit_depth, d_coeff); break;
     default: return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
   }
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }
@@ -109,9 +109,9 @@ int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n,
   static const int scales[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };
   const size_t total = (size_t)n_tus * n * n;
   HMGPU_CUDA(ctx, cudaMemsetAsync(d_abs_sum, 0, sizeof(uint32_t) * n_tus, ctx->stream));
+  HmgpuStage st(ctx, HMGPU_ST_QUANT, 1);
   quant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_coeff, total, n * n, qbits, add, scales[qp_rem],
                                                                          d_level, d_delta, d_abs_sum);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }
@@ -134,9 +134,9 @@ __global__ void mc_luma_kernel(const hmgpu_mc_job* __restrict__ jobs, RefTable r
 int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst)
 {
   const RefTable rt = hmgpu_ref_table(ctx);
+  HmgpuStage st(ctx, HMGPU_ST_MC, 1);
   if (ctx->px_bytes == 1) mc_luma_kernel<uint8_t><<<n_jobs, 128, 0, ctx->stream>>>(d_jobs, rt, d_dst);
   else mc_luma_kernel<uint16_t><<<n_jobs, 128, 0, ctx->stream>>>(d_jobs, rt, d_dst);
-  ctx->launches += 1;
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

@@ -42,7 +42,8 @@ EXPORTS = [
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_fwd_transform",
-    "hmgpu_quant"]
+    "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
+    "hmgpu_profile_read", "hmgpu_microbench"]
 
 _lib = None
 
@@ -79,7 +80,7 @@ def lib():
     L.hmgpu_org_upload.argtypes = [vp, vp, ci]
     L.hmgpu_org_upload_device.argtypes = [vp, vp, ci]
     L.hmgpu_me_search.argtypes = [vp, vp, ci, vp, ci, vp]
-    L.hmgpu_me_search_device.argtypes = [vp, vp, ci, vp, vp]
+    L.hmgpu_me_search_device.argtypes = [vp, vp, ci, vp, vp, ci]
     L.hmgpu_clip_bounds.argtypes = [ci, ci, ci, ci, vp]
     L.hmgpu_clip_bounds.restype = None
     L.hmgpu_search_range.argtypes = [vp, ci, ci, ci, vp]
@@ -92,6 +93,11 @@ def lib():
     L.hmgpu_mc_luma.argtypes = [vp, vp, ci, vp, ci]
     L.hmgpu_fwd_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.hmgpu_profile_enable.argtypes = [vp, ci]
+    L.hmgpu_profile_stage_name.argtypes = [ci]
+    L.hmgpu_profile_stage_name.restype = C.c_char_p
+    L.hmgpu_profile_read.argtypes = [vp, vp, vp, ci]
+    L.hmgpu_microbench.argtypes = [vp, ci, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -143,6 +149,22 @@ class Context:
     def stream(self):
         return self.L.hmgpu_stream(self.h)
 
+    def profile_enable(self, on=True):
+        self._check(self.L.hmgpu_profile_enable(self.h, int(on)))
+
+    def profile_read(self, reset=True):
+        """-> {stage: (device_ms, launches)} accumulated since the last reset"""
+        n = self.L.hmgpu_profile_stage_count()
+        ms = np.zeros(n, np.float64)
+        cnt = np.zeros(n, np.uint64)
+        self._check(self.L.hmgpu_profile_read(self.h, ms.ctypes.data, cnt.ctypes.data, int(reset)))
+        return {self.L.hmgpu_profile_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def microbench(self, which):
+        g = C.c_double()
+        self._check(self.L.hmgpu_microbench(self.h, which, C.byref(g)))
+        return g.value
+
     def synchronize(self):
         self._check(self.L.hmgpu_synchronize(self.h))
 
@@ -185,8 +207,8 @@ class Context:
                                            org_blocks.size if org_blocks is not None else 0, res.ctypes.data))
         return res
 
-    def me_search_device(self, d_jobs, n_jobs, d_org_blocks, d_results):
-        self._check(self.L.hmgpu_me_search_device(self.h, d_jobs, n_jobs, d_org_blocks, d_results))
+    def me_search_device(self, d_jobs, n_jobs, d_org_blocks, d_results, flags_any):
+        self._check(self.L.hmgpu_me_search_device(self.h, d_jobs, n_jobs, d_org_blocks, d_results, int(flags_any)))
 
     def dist_batch(self, org, cur, items):
         org = np.ascontiguousarray(org, np.int16)

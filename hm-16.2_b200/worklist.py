@@ -72,8 +72,10 @@ def search_range_np(bd, pred_x, pred_y, sr):
 
 
 def frame_jobs(pic_w, pic_h, n_refs=4, seed=7, full_search=False, search_range=64, fen=True, hadme=True,
-               lam=57.9, motion_qpel=(12, -8), jitter=6, amp=True, frac=True, pus=None):
-    """ME jobs of one P picture: every PU of every CU of the quadtree x every reference."""
+               lam=57.9, motion_qpel=(12, -8), jitter=6, amp=True, frac=True, pus=None, ref_dist=None):
+    """ME jobs of one P picture: every PU of every CU of the quadtree x every reference.
+    motion_qpel: true global motion per frame (synth.py translates by (+3,-2) px/frame);
+    ref_dist[slot]: temporal distance of the reference in that slot (default slot+1)."""
     rng = np.random.default_rng(seed)
     if pus is None:
         pus = pu_list(pic_w, pic_h, amp)
@@ -85,16 +87,17 @@ def frame_jobs(pic_w, pic_h, n_refs=4, seed=7, full_search=False, search_range=6
     jobs["pu_x"], jobs["pu_y"], jobs["pu_w"], jobs["pu_h"] = rep[:, 2], rep[:, 3], rep[:, 4], rep[:, 5]
     jobs["ref_slot"] = ref
     # the further the reference, the larger the displacement
-    mvx = motion_qpel[0] * (ref + 1) + rng.integers(-jitter, jitter + 1, n)
-    mvy = motion_qpel[1] * (ref + 1) + rng.integers(-jitter, jitter + 1, n)
+    dist = (ref + 1) if ref_dist is None else np.asarray(ref_dist)[ref]
+    mvx = motion_qpel[0] * dist + rng.integers(-jitter, jitter + 1, n)
+    mvy = motion_qpel[1] * dist + rng.integers(-jitter, jitter + 1, n)
     jobs["pred_x"], jobs["pred_y"] = mvx, mvy
     jobs["start_x"], jobs["start_y"] = mvx, mvy
     bd = clip_bounds_np(pic_w, pic_h, cu_x, cu_y)
     jobs["clip_hmin"], jobs["clip_hmax"], jobs["clip_vmin"], jobs["clip_vmax"] = bd
     left, top, right, bottom = search_range_np(bd, mvx, mvy, search_range)
     jobs["win_l"], jobs["win_t"], jobs["win_r"], jobs["win_b"] = left, top, right, bottom
-    jobs["i2n_x"] = (motion_qpel[0] * (ref + 1)) // 4 + rng.integers(-1, 2, n)
-    jobs["i2n_y"] = (motion_qpel[1] * (ref + 1)) // 4 + rng.integers(-1, 2, n)
+    jobs["i2n_x"] = (motion_qpel[0] * dist) // 4 + rng.integers(-1, 2, n)
+    jobs["i2n_y"] = (motion_qpel[1] * dist) // 4 + rng.integers(-1, 2, n)
     jobs["search_range"] = search_range
     jobs["ui_cost"] = lambda_to_cost(lam)
     flags = np.full(n, F_INTEGER | (F_FRAC if frac else 0) | (F_FEN if fen else 0) | (F_HADME if hadme else 0), np.uint8)

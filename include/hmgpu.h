@@ -58,6 +58,17 @@ int  hmgpu_synchronize(hmgpu_ctx* ctx);
 /* sizeof of the four ABI structs: me_job, me_result, dist_item, mc_job (binding self-check) */
 void hmgpu_struct_sizes(int out[4]);
 
+/* Per-stage device timing (CUDA events on hmgpu_stream()).  The reference's only timer is
+ * clock() (encmain.cpp:95-101, TEncGOP.cpp:646); these are what bench.py's roofline reads.
+ * hmgpu_profile_read fills ms[] / launches[] (hmgpu_profile_stage_count() entries each). */
+int  hmgpu_profile_enable(hmgpu_ctx* ctx, int on);
+int  hmgpu_profile_stage_count(void);
+const char* hmgpu_profile_stage_name(int stage);
+int  hmgpu_profile_read(hmgpu_ctx* ctx, double* ms, uint64_t* launches, int reset);
+/* integer-pipe microbenchmark: which = 0 -> 32-bit add/logic stream, 1 -> VABSDIFF4.U8.ACC;
+ * result in giga lane-operations per second (the INT32 roofline denominators) */
+int  hmgpu_microbench(hmgpu_ctx* ctx, int which, double* gops);
+
 /* ------------------------------------------------------------------------------------------
  * Reference pictures.
  * hmgpu_ref_upload replaces TComPicYuv::extendPicBorder (TComPicYuv.cpp:171-215, called from
@@ -130,9 +141,11 @@ typedef struct hmgpu_me_result
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                     const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results);
 /* device-resident variant used for kernel-only timing: d_jobs/d_results are device pointers,
- * asynchronous on hmgpu_stream(); call hmgpu_synchronize() to wait */
+ * asynchronous on hmgpu_stream(); call hmgpu_synchronize() to wait.  The host cannot inspect
+ * device-resident jobs: flags_any is the OR of the flags of all jobs (selects the kernels to
+ * launch) and the jobs must already satisfy the range checks hmgpu_me_search performs. */
 int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs,
-                           const void* d_org_blocks, void* d_results);
+                           const void* d_org_blocks, void* d_results, int flags_any);
 
 /* Host-side helpers with the reference's exact arithmetic (cheap, scalar):
  * TComDataCU::clipMv bounds (TComDataCU.cpp:2917-2929) and xSetSearchRange

@@ -99,6 +99,8 @@ def oracle():
     L.hmo_transform_matrix.argtypes = [ci, i32p]
     L.hmo_quant.restype = cu
     L.hmo_quant.argtypes = [i32p, ci, ci, ci, ci, ci, i32p, i32p]
+    L.hmo_me_batch.restype = C.c_double
+    L.hmo_me_batch.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, vp]
     _oracle = L
     return L
 
@@ -147,8 +149,28 @@ def ref():
     L.ref_quant_scale.restype = ci
     L.ref_quant_scale.argtypes = [ci]
     L.ref_pred_inter_blk.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci]
+    L.ref_me_batch.restype = C.c_double
+    L.ref_me_batch.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, vp]
     _ref = L
     return L
+
+
+def me_batch(lib_fn, jobs, refs_padded, org, bit_depth, org_blocks=None, margin=80):
+    """run a job batch (numpy structured array with the hmgpu_me_job layout) through
+    hmo_me_batch / ref_me_batch.  refs_padded: list of padded int16 planes by slot.
+    -> (results as raw bytes-compatible uint8 array [n, 24], cpu_seconds)"""
+    jobs = np.ascontiguousarray(jobs)
+    n = len(jobs)
+    res = np.zeros((n, 24), np.uint8)
+    if n == 0:
+        return res, 0.0
+    pw = refs_padded[0].shape[1]
+    ptrs = (C.c_void_p * len(refs_padded))(*[r.ctypes.data + (margin * pw + margin) * 2 for r in refs_padded])
+    org = np.ascontiguousarray(org, np.int16)
+    ob = None if org_blocks is None else np.ascontiguousarray(org_blocks, np.int16)
+    secs = lib_fn(jobs.ctypes.data, n, C.cast(ptrs, C.c_void_p), pw, org.ctypes.data, org.shape[1],
+                  None if ob is None else ob.ctypes.data, bit_depth, res.ctypes.data)
+    return res, secs
 
 
 def ptr(a, off=0):

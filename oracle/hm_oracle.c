@@ -16,6 +16,7 @@
  * reference file:line whose results it must reproduce bit-for-bit.
  */
 #include "hm_oracle.h"
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -742,4 +743,61 @@ uint32_t hmo_quant(const int32_t* coef, int n_coef, int qp_per, int qp_rem, int 
     level[i] = v;
   }
   return abs_sum;
+}
+
+/* =====================================================================================
+ * Batch driver over the job / result PODs of include/hmgpu.h (test + cpu_baseline "port")
+ * ===================================================================================== */
+#include <time.h>
+#include "../include/hmgpu.h"
+
+/* refs[slot] -> sample (0,0) of a padded int16 plane (stride ref_stride); org -> (0,0) of the
+ * source picture.  Returns CPU seconds (thread time). */
+double hmo_me_batch(const hmgpu_me_job* jobs, int n_jobs, const int16_t* const* refs, int ref_stride,
+                    const int16_t* org, int org_stride, const int16_t* org_blocks, int bit_depth,
+                    hmgpu_me_result* results)
+{
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t0);
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const hmgpu_me_job* j = &jobs[i];
+    hmgpu_me_result* r = &results[i];
+    hmo_search_t s;
+    memset(&s, 0, sizeof s);
+    memset(r, 0, sizeof *r);
+    s.w = j->pu_w; s.h = j->pu_h;
+    if (j->flags & HMGPU_F_ORG_BLOCK) { s.org = org_blocks + j->org_offset; s.org_stride = s.w; }
+    else { s.org = org + (size_t)j->pu_y * org_stride + j->pu_x; s.org_stride = org_stride; }
+    s.ref = refs[j->ref_slot] + (ptrdiff_t)j->pu_y * ref_stride + j->pu_x; s.ref_stride = ref_stride;
+    s.l = j->win_l; s.t = j->win_t; s.r = j->win_r; s.b = j->win_b;
+    s.ui_cost = j->ui_cost; s.pred_x = j->pred_x; s.pred_y = j->pred_y;
+    s.fen = (j->flags & HMGPU_F_FEN) != 0; s.hadme = (j->flags & HMGPU_F_HADME) != 0;
+    s.lossless = (j->flags & HMGPU_F_LOSSLESS) != 0; s.bit_depth = bit_depth;
+    s.cu_x = -(j->clip_hmin / 4) - 71; s.cu_y = -(j->clip_vmin / 4) - 71;
+    s.pic_w = j->clip_hmax / 4 - 7 + s.cu_x; s.pic_h = j->clip_vmax / 4 - 7 + s.cu_y;
+    s.search_range = j->search_range; s.start_x = j->start_x; s.start_y = j->start_y;
+    s.has_2nx2n = (j->flags & HMGPU_F_HAS_2NX2N) != 0; s.i2n_x = j->i2n_x; s.i2n_y = j->i2n_y;
+    uint32_t n = 0;
+    if (j->flags & HMGPU_F_INTEGER)
+    {
+      if (j->flags & HMGPU_F_FULL) hmo_pattern_search(&s); else hmo_tz_search(&s);
+      n = s.n_cand;
+      r->int_sad = s.sad;
+    }
+    else { s.mv_x = j->start_x; s.mv_y = j->start_y; }
+    r->int_x = (int16_t)s.mv_x; r->int_y = (int16_t)s.mv_y;
+    if (j->flags & HMGPU_F_FRAC)
+    {
+      s.n_cand = 0;
+      hmo_frac_search(&s);
+      n += s.n_cand;
+      r->half_x = (int16_t)s.half_x; r->half_y = (int16_t)s.half_y;
+      r->qter_x = (int16_t)s.qter_x; r->qter_y = (int16_t)s.qter_y;
+      r->frac_cost = s.frac_cost;
+    }
+    r->n_cand = n;
+  }
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t1);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }

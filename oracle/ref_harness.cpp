@@ -320,6 +320,71 @@ void ref_frac_search(const int16_t* org, int orgStride, int w, int h,
   *outCost = cost;
 }
 
+// ---- CPU baseline: a batch of xMotionEstimation bodies run by the real reference -------------
+// jobs/results use the POD layouts of include/hmgpu.h (hmgpu_me_job / hmgpu_me_result) so the
+// very same work-list can be given to the GPU library and to the reference.  refs[slot] points
+// at sample (0,0) of a padded int16 plane with stride ref_stride; org at (0,0) of the source
+// picture.  Returns the CPU seconds spent inside the reference calls (CLOCK_THREAD_CPUTIME_ID).
+#include <time.h>
+#include "../include/hmgpu.h"
+
+double ref_me_batch(const hmgpu_me_job* jobs, int n_jobs, const int16_t* const* refs, int ref_stride,
+                    const int16_t* org, int org_stride, const int16_t* org_blocks, int bitDepth,
+                    hmgpu_me_result* results)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  g.search->m_cDistParam.bApplyWeight = false;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t0);
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const hmgpu_me_job& j = jobs[i];
+    hmgpu_me_result& r = results[i];
+    memset(&r, 0, sizeof r);
+    const int w = j.pu_w, h = j.pu_h;
+    TComPattern pat;
+    if (j.flags & HMGPU_F_ORG_BLOCK) pat.initPattern((Pel*)org_blocks + j.org_offset, w, h, w);
+    else pat.initPattern((Pel*)org + (size_t)j.pu_y * org_stride + j.pu_x, w, h, org_stride);
+    Pel* ref = (Pel*)refs[j.ref_slot] + (ptrdiff_t)j.pu_y * ref_stride + j.pu_x;
+    g.cfg.setUseFastEnc((j.flags & HMGPU_F_FEN) != 0);
+    g.cfg.setUseHADME((j.flags & HMGPU_F_HADME) != 0);
+    g.cfg.setFastSearch(1);
+    // clipMv reads (pic size, CU origin): recover them from the bounds the job carries
+    const int cuX = -(j.clip_hmin / 4) - 71, cuY = -(j.clip_vmin / 4) - 71;
+    set_cu(j.clip_hmax / 4 - 7 + cuX, j.clip_vmax / 4 - 7 + cuY, cuX, cuY);
+    set_cost(j.ui_cost, j.pred_x, j.pred_y, 2);
+    g.search->m_iSearchRange = j.search_range;
+    TComMv lt(j.win_l, j.win_t), rb(j.win_r, j.win_b), mv(j.start_x, j.start_y);
+    Distortion sad = 0;
+    if (j.flags & HMGPU_F_INTEGER)
+    {
+      if (j.flags & HMGPU_F_FULL)
+      {
+        g.search->xPatternSearch(&pat, ref, ref_stride, &lt, &rb, mv, sad);
+      }
+      else
+      {
+        TComMv i2n(j.i2n_x, j.i2n_y);
+        g.search->xTZSearch(g.cu, &pat, ref, ref_stride, &lt, &rb, mv, sad, (j.flags & HMGPU_F_HAS_2NX2N) ? &i2n : NULL);
+      }
+      r.int_sad = sad;
+    }
+    r.int_x = mv.getHor(); r.int_y = mv.getVer();
+    if (j.flags & HMGPU_F_FRAC)
+    {
+      g.rd.setCostScale(1);
+      TComMv half, qter;
+      Distortion cost = 0;
+      g.search->xPatternSearchFracDIF((j.flags & HMGPU_F_LOSSLESS) != 0, &pat, ref, ref_stride, &mv, half, qter, cost, false);
+      r.half_x = half.getHor(); r.half_y = half.getVer();
+      r.qter_x = qter.getHor(); r.qter_y = qter.getVer();
+      r.frac_cost = cost;
+    }
+  }
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t1);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 // ---- a17: forward transform (TComTrQuant.cpp:836-885); block is w*h TCoeff (int32) row-major
 void ref_fwd_transform(int bitDepth, const int32_t* block, int32_t* coeff, int w, int h, int useDST)
 {
