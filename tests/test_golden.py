@@ -1,0 +1,104 @@
+"""The CPU oracle (oracle/hm_oracle.c) against the committed golden vectors, which are outputs
+of the unmodified reference (tests/golden/make_golden.py).  No GPU, no /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+import hmgpu
+import synth
+from oracle import binding as B
+from util import padded_ref
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hm162_golden.npz"))
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_distortion_family(bd):
+    O = B.oracle()
+    org, cur = G["dist_org_%d" % bd], G["dist_cur_%d" % bd]
+    for (w, h, oo, co, kind, ss, exp) in G["dist_rows_%d" % bd]:
+        w, h, oo, co, ss = int(w), int(h), int(oo), int(co), int(ss)
+        po, pc = B.ptr(org, oo), B.ptr(cur, co)
+        if kind == 0:
+            got = O.hmo_sad(po, 80, pc, 96, w, h, ss, bd, 0)
+        elif kind == 1:
+            got = O.hmo_hads(po, 80, pc, 96, w, h, bd)
+        elif kind == 2:
+            got = O.hmo_sse(po, 80, pc, 96, w, h, bd)
+        else:  # generic setDistParam: widths 12/24/48 fall to xGetSAD, which ignores iSubShift
+            got = O.hmo_sad(po, 80, pc, 96, w, h, ss, bd, 1 if w in (12, 24, 48) else 0)
+        assert got == exp, (w, h, kind, ss)
+
+
+def test_mv_cost_and_lambda():
+    O = B.oracle()
+    for (uc, px, py, sc, x, y, bits, cost) in G["cost_rows"]:
+        a = [int(v) for v in (px, py, sc, x, y)]
+        assert O.hmo_mv_bits(*a) == bits
+        assert O.hmo_mv_cost(int(uc), *a) == cost
+        assert hmgpu.lib().hmgpu_mv_bits(*a) == bits          # host-side helpers of the product
+        assert hmgpu.lib().hmgpu_mv_cost(int(uc), *a) == cost
+    for lam, ui in zip(G["cost_lambda"], G["cost_lambda_ui"]):
+        assert O.hmo_lambda_to_cost(float(lam)) == ui
+
+
+def test_clip_and_search_range():
+    O = B.oracle()
+    for r in G["clip_rows"]:
+        pw, ph, cx, cy, px, py, sr = [int(v) for v in r[:7]]
+        out = np.zeros(4, np.int32)
+        O.hmo_set_search_range(pw, ph, cx, cy, px, py, sr, out)
+        assert out.tolist() == r[7:11].tolist()
+        mv = np.array([px, py], np.int32)
+        O.hmo_clip_mv(pw, ph, cx, cy, mv)
+        assert mv.tolist() == r[11:13].tolist()
+        bd = hmgpu.clip_bounds(pw, ph, cx, cy)                # product host helpers
+        assert hmgpu.search_range(bd, px, py, sr).tolist() == r[7:11].tolist()
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_interpolation_filters(bd):
+    O = B.oracle()
+    src, mid = G["filt_src_%d" % bd], G["filt_mid_%d" % bd]
+    for chroma in (0, 1):
+        for frac in range(8 if chroma else 4):
+            for last in (0, 1):
+                d = np.zeros((17, 33), np.int16)
+                O.hmo_filter_hor(chroma, B.ptr(src, 8 * 64 + 8), 64, B.ptr(d), 33, 33, 17, frac, last, bd)
+                assert np.array_equal(d, G["filt_%d_h_%d_%d_%d" % (bd, chroma, frac, last)])
+                for first in (0, 1):
+                    s = src if first else mid
+                    d = np.zeros((17, 33), np.int16)
+                    O.hmo_filter_ver(chroma, B.ptr(s, 8 * 64 + 8), 64, B.ptr(d), 33, 33, 17, frac, first, last, bd)
+                    assert np.array_equal(d, G["filt_%d_v_%d_%d_%d_%d" % (bd, chroma, frac, first, last)])
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_forward_transform(bd):
+    O = B.oracle()
+    for n in (4, 8, 16, 32):
+        blk = G["tr_%d_blk_%d" % (bd, n)]
+        for dst in ((0, 1) if n == 4 else (0,)):
+            exp = G["tr_%d_coef_%d_%d" % (bd, n, dst)]
+            for t in range(len(blk)):
+                c = np.zeros((n, n), np.int32)
+                O.hmo_fwd_transform(bd, np.ascontiguousarray(blk[t]), c, n, n, dst)
+                assert np.array_equal(c, exp[t]), (n, dst, t)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("mode", ["tz", "fs"])
+def test_searches(bd, mode):
+    """xTZSearch / xPatternSearch + xPatternSearchFracDIF answers of the reference"""
+    jobs = np.ascontiguousarray(G["search_%s_jobs_%d" % (mode, bd)]).view(hmgpu.ME_JOB).reshape(-1)
+    exp = np.ascontiguousarray(G["search_%s_res_%d" % (mode, bd)]).view(hmgpu.ME_RESULT).reshape(-1)
+    fr = synth.luma_frames(416, 240, 4, bd).astype(np.int16)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    got, _ = B.me_batch(B.oracle().hmo_me_batch, jobs, pads, fr[3], bd)
+    got = got.view(hmgpu.ME_RESULT).reshape(-1)
+    for f in hmgpu.ME_RESULT.names:
+        if f == "n_cand":      # the reference does not count candidates
+            continue
+        assert np.array_equal(got[f], exp[f]), f
+    assert (got["n_cand"] >= 18).all()

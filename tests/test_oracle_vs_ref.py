@@ -1,0 +1,88 @@
+"""Pin the oracle against the real reference (oracle/_ref/libhmref.so, compiled from the
+unmodified HM sources) on fresh random inputs.  Skipped where the reference build is absent."""
+import numpy as np
+import pytest
+
+import hmgpu
+import synth
+from oracle import binding as B
+from util import padded_ref
+
+pytestmark = pytest.mark.skipif(not B.have_ref(), reason="oracle/_ref/libhmref.so not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_distortions_random(bd):
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(1)
+    mx = (1 << bd) - 1
+    for it in range(120):
+        w = int(rng.choice([4, 8, 12, 16, 24, 32, 48, 64]))
+        h = int(rng.choice([4, 8, 12, 16, 24, 32, 48, 64]))
+        o = (rng.integers(-mx, 2 * mx + 1, (64, 80)) if it % 3 == 0 else rng.integers(0, mx + 1, (64, 80))).astype(np.int16)
+        c = rng.integers(0, mx + 1, (64, 96)).astype(np.int16)
+        po, pc = B.ptr(o), B.ptr(c)
+        for ss in (0, 1):
+            assert R.ref_sad_me(po, 80, pc, 96, w, h, ss, bd) == O.hmo_sad(po, 80, pc, 96, w, h, ss, bd, 0)
+        assert R.ref_dist_subpel(po, 80, pc, 96, w, h, 1, bd) == O.hmo_hads(po, 80, pc, 96, w, h, bd)
+        assert R.ref_calc_had(po, 80, pc, 96, w, h, bd) == O.hmo_hads(po, 80, pc, 96, w, h, bd)
+        assert R.ref_dist_subpel(po, 80, pc, 96, w, h, 0, bd) == O.hmo_sad(po, 80, pc, 96, w, h, 0, bd, 0)
+        assert R.ref_sse(pc, 96, po, 80, w, h, bd) == O.hmo_sse(po, 80, pc, 96, w, h, bd)
+
+
+def test_border_and_rdcost():
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, 256, (24, 40)).astype(np.int16)
+    d1 = np.zeros((24 + 160, 40 + 160), np.int16)
+    d2 = np.zeros_like(d1)
+    assert R.ref_extend_border(src, 40, 24, d1, d1.size) == 80
+    O.hmo_extend_border(src, 40, 24, 80, d2)
+    assert np.array_equal(d1, d2)
+    for lam in rng.uniform(0.1, 5000, 100):
+        b, d = int(rng.integers(0, 60)), int(rng.integers(0, 100000))
+        assert R.ref_calc_rd_cost_sad(float(lam), b, d) == O.hmo_calc_rd_cost_sad(float(lam), b, d)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_motion_compensation(bd):
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(3)
+    mx = (1 << bd) - 1
+    for it in range(150):
+        chroma = it % 2
+        w = int(rng.choice([2, 4, 8, 16, 32])) if chroma else int(rng.choice([4, 8, 12, 16, 64]))
+        h = int(rng.choice([2, 4, 8, 16])) if chroma else int(rng.choice([4, 8, 16, 64]))
+        plane = rng.integers(0, mx + 1, (120, 140)).astype(np.int16)
+        mvx, mvy = [int(v) for v in rng.integers(-60, 60, 2)]
+        for bi in (0, 1):
+            d1 = np.zeros((h, w), np.int16)
+            d2 = np.zeros_like(d1)
+            R.ref_pred_inter_blk(chroma, B.ptr(plane, 30 * 140 + 30), 140, mvx, mvy, w, h, bi, bd, B.ptr(d1), w)
+            O.hmo_pred_inter_blk(chroma, B.ptr(plane, 30 * 140 + 30), 140, mvx, mvy, w, h, bi, bd, B.ptr(d2), w)
+            assert np.array_equal(d1, d2)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("noise", [False, True])
+def test_search_batches(bd, noise):
+    """hmo_me_batch vs ref_me_batch over HM-shaped job lists (TZ and full search + fractional)"""
+    import worklist
+    w, h = 416, 240
+    if noise:
+        fr = np.random.default_rng(9).integers(0, 1 << bd, (4, h, w)).astype(np.int16)
+    else:
+        fr = synth.luma_frames(w, h, 4, bd).astype(np.int16)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    tz = worklist.frame_jobs(w, h, n_refs=3, seed=5, ref_dist=[3, 2, 1])
+    tz = tz[:: max(1, len(tz) // 1500)]
+    fs = worklist.frame_jobs(w, h, n_refs=3, seed=6, full_search=True, search_range=12, ref_dist=[3, 2, 1])
+    fs = fs[:: max(1, len(fs) // 150)]
+    for jobs in (tz, fs):
+        a, _ = B.me_batch(B.oracle().hmo_me_batch, jobs, pads, fr[3], bd)
+        b, _ = B.me_batch(B.ref().ref_me_batch, jobs, pads, fr[3], bd)
+        a = a.view(hmgpu.ME_RESULT).reshape(-1)
+        b = b.view(hmgpu.ME_RESULT).reshape(-1)
+        for f in hmgpu.ME_RESULT.names:
+            if f != "n_cand":
+                assert np.array_equal(a[f], b[f]), f
