@@ -13,6 +13,18 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
                       hmgpu_me_result* d_results, bool any_org_block, int max_win_bytes);
 int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_frac);
+int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                        hmgpu_me_result* d_results, uint32_t* d_flags, uint32_t ticket, bool any_org_block, int max_win_bytes);
+
+// mailbox of the low-latency path: up to MAIL_JOBS jobs per call
+#define MAIL_JOBS 16
+struct Mailbox
+{
+  hmgpu_me_job    jobs[MAIL_JOBS];
+  hmgpu_me_result results[MAIL_JOBS];
+  uint32_t        flags[MAIL_JOBS];
+  int16_t         org_blocks[MAIL_JOBS * 64 * 64];
+};
 
 static char g_create_err[512] = "";
 
@@ -163,6 +175,7 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_work) cudaFree(ctx->d_work);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -353,6 +366,40 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   int max_win;
   int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win);
   if (rc) return rc;
+  if (n_jobs <= MAIL_JOBS && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64) && !getenv("HMGPU_NO_FASTPATH"))
+  {
+    // ---- low-latency path: mapped pinned mailbox, one fused kernel, host spins on the flags ----
+    if (!ctx->h_mail)
+    {
+      HMGPU_CUDA(ctx, cudaHostAlloc(&ctx->h_mail, sizeof(Mailbox), cudaHostAllocMapped));
+      memset(ctx->h_mail, 0, sizeof(Mailbox));
+    }
+    Mailbox* mb = (Mailbox*)ctx->h_mail;
+    memcpy(mb->jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
+    if (any_org) memcpy(mb->org_blocks, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+    const uint32_t ticket = ++ctx->mail_ticket;
+    __sync_synchronize();
+    rc = hmgpu_launch_single(ctx, mb->jobs, n_jobs, mb->org_blocks, mb->results, mb->flags, ticket, any_org, max_win);
+    if (rc) return rc;
+    volatile uint32_t* flags = mb->flags;
+    for (int i = 0; i < n_jobs; i++)
+    {
+      unsigned spins = 0;
+      while (flags[i] != ticket)
+      {
+        if (++spins > 4000000u)
+        {
+          spins = 0;
+          const cudaError_t e = cudaStreamQuery(ctx->stream);
+          if (e != cudaErrorNotReady && flags[i] != ticket)
+            return hmgpu_fail(ctx, HMGPU_E_CUDA, "low-latency search kernel ended without publishing job %d: %s", i, cudaGetErrorString(e));
+        }
+      }
+    }
+    __sync_synchronize();
+    memcpy(results, (const void*)mb->results, sizeof(hmgpu_me_result) * (size_t)n_jobs);
+    return HMGPU_OK;
+  }
   const size_t jb = round_up(sizeof(hmgpu_me_job) * (size_t)n_jobs, 256);
   const size_t ob = round_up(any_org ? sizeof(int16_t) * (size_t)n_org_elems : 0, 256);
   const size_t rb = round_up(sizeof(hmgpu_me_result) * (size_t)n_jobs, 256);

@@ -50,6 +50,7 @@ struct hmgpu_ctx
   void* h_pin; size_t h_pin_bytes;     // pinned host
   void* d_stage; size_t d_stage_bytes; // device
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
+  void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
   uint64_t launches;
   // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
   bool prof_on;
@@ -64,7 +65,7 @@ struct hmgpu_ctx
 enum
 {
   HMGPU_ST_PLANES = 0, HMGPU_ST_ORG, HMGPU_ST_TZ, HMGPU_ST_FULL, HMGPU_ST_FRAC_EXPAND, HMGPU_ST_FRAC_DIST,
-  HMGPU_ST_FRAC_SELECT, HMGPU_ST_DIST, HMGPU_ST_TRANSFORM, HMGPU_ST_QUANT, HMGPU_ST_MC, HMGPU_ST_COUNT
+  HMGPU_ST_FRAC_SELECT, HMGPU_ST_DIST, HMGPU_ST_TRANSFORM, HMGPU_ST_QUANT, HMGPU_ST_MC, HMGPU_ST_SINGLE, HMGPU_ST_COUNT
 };
 
 void hmgpu_prof_begin(hmgpu_ctx* ctx, int stage);

@@ -1,0 +1,164 @@
+// me_single.cu -- fused low-latency path: ONE kernel launch per small batch, one CTA per job.
+//
+// HM calls xMotionEstimation synchronously from the sequential xCompressCU recursion
+// (TEncCu.cpp:466, TEncSearch.cpp:3219-3227): it needs the MV of this PU before its next line.
+// For such calls (a handful of jobs: one PU x its reference pictures) the batch pipeline of
+// me_tz/me_full/me_frac (6 launches, 2 copies, several stream synchronisations) costs far more
+// than the search.  This kernel does the whole job -- integer search (TZ by warp 0, or the
+// block-wide full search) and both fractional phases -- in one launch, reads the job from and
+// writes the result to MAPPED pinned host memory, and signals completion with a system-scope
+// flag the host spins on, so a call is: write 48 bytes, one launch, poll.
+#include "me_tz_impl.cuh"
+#include "me_full_impl.cuh"
+#include "me_frac_impl.cuh"
+
+#define SG_THREADS FS_THREADS
+
+template <typename Px, int TS>
+__device__ __forceinline__ void sg_frac_phase(const hmgpu_me_job& jb, const int16_t* org_blocks, const RefTable& refs,
+                                              const OrgView& org, const hmgpu_me_result& res, int phase, uint32_t* s_acc)
+{
+  const int tw = jb.pu_w / TS, nt = tw * (jb.pu_h / TS);
+  const bool satd = (jb.flags & HMGPU_F_HADME) && !(jb.flags & HMGPU_F_LOSSLESS);
+  const int pitch = refs.pitch;
+  for (int i = threadIdx.x; i < nt * 9; i += SG_THREADS)
+  {
+    const int cand = i / nt, t = i - cand * nt;
+    int qx, qy;
+    if (phase == 0)
+    {
+      qx = 4 * res.int_x + 2 * c_refine_h[cand][0];
+      qy = 4 * res.int_y + 2 * c_refine_h[cand][1];
+    }
+    else
+    {
+      qx = 4 * res.int_x + 2 * res.half_x + c_refine_q[cand][0];
+      qy = 4 * res.int_y + 2 * res.half_y + c_refine_q[cand][1];
+    }
+    const int ph = (qy & 3) * 4 + (qx & 3);
+    const Px* ref = (const Px*)refs.base[jb.ref_slot] + (size_t)ph * refs.plane_elems
+                  + (ptrdiff_t)(jb.pu_y + (qy >> 2)) * pitch + (jb.pu_x + (qx >> 2));
+    const int ty = t / tw, tx = t - ty * tw;
+    const uint32_t v = tile_dist<Px, TS>(jb, org_blocks, org, ref, pitch, tx * TS, ty * TS, satd);
+    atomicAdd(&s_acc[cand], v);
+  }
+}
+
+template <typename Px, bool PACKED>
+__global__ void __launch_bounds__(SG_THREADS)
+me_single_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
+                 hmgpu_me_result* results, volatile uint32_t* done_flags, uint32_t ticket)
+{
+  extern __shared__ __align__(16) unsigned char s_dyn[];       // packed full-search window
+  __shared__ __align__(16) unsigned char s_org[8192];          // PU block: packed bytes or int16
+  __shared__ unsigned long long s_red[SG_THREADS / 32];
+  __shared__ hmgpu_me_job s_job;
+  __shared__ hmgpu_me_result s_res;
+  __shared__ uint32_t s_acc[9];
+
+  const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(hmgpu_me_job) / 4)) ((uint32_t*)&s_job)[tid] = ((const uint32_t*)&jobs[blockIdx.x])[tid];
+  __syncthreads();
+  const hmgpu_me_job jb = s_job;
+
+  // ---- integer search --------------------------------------------------------------------
+  if (jb.flags & HMGPU_F_INTEGER)
+  {
+    if (jb.flags & HMGPU_F_FULL)
+    {
+      if (PACKED) full_search_block_packed(jb, refs, org, s_dyn, s_red, &s_res);
+      else full_search_block_generic<Px>(jb, org_blocks, refs, org, (int16_t*)s_org, s_red, &s_res);
+    }
+    else if (tid < 32)
+    {
+      hmgpu_me_result r;
+      tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r);
+      if (tid == 0) s_res = r;
+    }
+  }
+  else if (tid == 0)
+  {
+    hmgpu_me_result r;
+    r.int_x = jb.start_x; r.int_y = jb.start_y; r.int_sad = 0;
+    r.half_x = r.half_y = r.qter_x = r.qter_y = 0; r.frac_cost = 0; r.n_cand = 0;
+    s_res = r;
+  }
+  __syncthreads();
+
+  // ---- fractional refinement -----------------------------------------------------------------
+  if (jb.flags & HMGPU_F_FRAC)
+  {
+    const int16_t* key = org_blocks;
+    if (jb.flags & HMGPU_F_ORG_BLOCK)
+    {
+      // stage the int16 key pattern once (it lives in mapped host memory): tile_dist then reads
+      // shared memory through a rebased pointer
+      int16_t* so = (int16_t*)s_org;
+      for (int i = tid; i < jb.pu_w * jb.pu_h; i += SG_THREADS) so[i] = org_blocks[jb.org_offset + i];
+      key = so - jb.org_offset;
+    }
+    const int bit_depth = refs.bit_depth;
+    for (int phase = 0; phase < 2; phase++)
+    {
+      if (tid < 9) s_acc[tid] = 0;
+      __syncthreads();
+      const hmgpu_me_result res = s_res;
+      if (job_tile_size(jb) == 8) sg_frac_phase<Px, 8>(jb, key, refs, org, res, phase, s_acc);
+      else sg_frac_phase<Px, 4>(jb, key, refs, org, res, phase, s_acc);
+      __syncthreads();
+      if (tid == 0)
+      {
+        uint32_t best = 0xffffffffu;
+        int bi = 0;
+        for (int c = 0; c < 9; c++)
+        {
+          const uint32_t dist = s_acc[c] >> (bit_depth - 8);
+          uint32_t cost;
+          if (phase == 0)
+            cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + c_refine_h[c][0], 2 * res.int_y + c_refine_h[c][1]);
+          else
+            cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 0, 4 * res.int_x + 2 * res.half_x + c_refine_q[c][0],
+                                     4 * res.int_y + 2 * res.half_y + c_refine_q[c][1]);
+          if (cost < best) { best = cost; bi = c; }
+        }
+        if (phase == 0) { s_res.half_x = c_refine_h[bi][0]; s_res.half_y = c_refine_h[bi][1]; }
+        else { s_res.qter_x = c_refine_q[bi][0]; s_res.qter_y = c_refine_q[bi][1]; }
+        s_res.frac_cost = best;
+        s_res.n_cand += 9;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- publish: result first, then the flag, both visible to the host --------------------------
+  if (tid < (int)(sizeof(hmgpu_me_result) / 4)) ((volatile uint32_t*)&results[blockIdx.x])[tid] = ((const uint32_t*)&s_res)[tid];
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) done_flags[blockIdx.x] = ticket;
+}
+
+static bool s_sg_attr_set = false;
+
+int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
+                        hmgpu_me_result* d_results, uint32_t* d_flags, uint32_t ticket, bool any_org_block, int max_win_bytes)
+{
+  const RefTable rt = hmgpu_ref_table(ctx);
+  OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  HmgpuStage st(ctx, HMGPU_ST_SINGLE, 1);
+  if (ctx->px_bytes == 1 && !any_org_block)
+  {
+    if (!s_sg_attr_set)
+    {
+      HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_single_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+      s_sg_attr_set = true;
+    }
+    if (max_win_bytes > 180 * 1024) return hmgpu_fail(ctx, HMGPU_E_INVALID, "full-search window needs %d bytes of shared memory", max_win_bytes);
+    me_single_kernel<uint8_t, true><<<n_jobs, SG_THREADS, max_win_bytes, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, d_flags, ticket);
+  }
+  else if (ctx->px_bytes == 1)
+    me_single_kernel<uint8_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, d_flags, ticket);
+  else
+    me_single_kernel<uint16_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, d_flags, ticket);
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}

@@ -1,203 +1,7 @@
-// me_tz.cu -- integer TZ search, one warp per job.
-//
-// Replaces TEncSearch::xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:298-314,
-// 4027-4228), xTZSearchHelp (:333-424), xTZ8PointDiamondSearch (:616-791), xTZ2PointSearch
-// (:429-557).  The state machine is warp-uniform; the points of one round (<= 16, or 32 per
-// chunk for the step-5 raster scan) are evaluated concurrently by lane groups.  Because the
-// reference updates its best with a strict '<' after every point in emission order, the
-// result of a round is the minimum cost of the round, earliest emission index among ties,
-// taken only if it is strictly below the running best -- which is what a (cost, lane) min
-// over lanes ordered by emission index yields.
-//
-// SAD arithmetic: 8-bit pictures use packed bytes and VABSDIFF4.U8.ACC against the PU block
-// staged in shared memory; >8-bit pictures and explicit int16 key patterns (bi-pred
-// 2*org-pred, values outside the pixel range) use 16-bit elements and scalar |a-b|.
-#include "hmgpu_internal.cuh"
-
-#define TZ_WARPS 4
-#define FULL_MASK 0xffffffffu
-
-struct TzJob
-{
-  int pu_w, pu_h, sub_shift, rows;     // rows = visited rows (pu_h >> sub_shift)
-  int pred_x, pred_y;
-  uint32_t ui_cost;
-  int L, T, R, B;
-  int bit_depth;
-};
-
-struct TzBest
-{
-  uint32_t cost;
-  int x, y;
-  int dist, round, pnr;
-  uint32_t n_cand;
-};
-
-// ---- per-lane partial SAD over rows r0, r0+rstep, ... (indices of visited rows) -------------
-
-// packed 8-bit path. org_s: pu_h rows of pu_w bytes (row pitch wq words); ref = plane pointer at
-// the PU origin displaced by the candidate.
-__device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitch, const uint32_t* org_s,
-                                                    int wq, int rows, int row_mul, int r0, int rstep)
-{
-  uint32_t acc = 0;
-  const uintptr_t a0 = (uintptr_t)ref;
-  const int sh = (int)(a0 & 3) * 8;
-  const uint32_t* q0 = (const uint32_t*)(a0 & ~(uintptr_t)3);
-  const int pitch_w = pitch >> 2;                      // pitch is a multiple of 4 bytes
-  for (int r = r0; r < rows; r += rstep)
-  {
-    const uint32_t* q = q0 + (size_t)(r * row_mul) * pitch_w;
-    const uint32_t* o = org_s + (r * row_mul) * wq;
-    uint32_t lo = __ldg(q);
-    for (int k = 0; k < wq; k++)
-    {
-      const uint32_t hi = __ldg(q + k + 1);
-      acc = vabsdiff4_acc(__funnelshift_r(lo, hi, sh), o[k], acc);
-      lo = hi;
-    }
-  }
-  return acc;
-}
-
-// generic path: org int16 in shared memory (row pitch pu_w), ref elements of type Px
-template <typename Px>
-__device__ __forceinline__ uint32_t sad_rows_generic(const Px* ref, int pitch, const int16_t* org_s,
-                                                     int w, int rows, int row_mul, int r0, int rstep)
-{
-  uint32_t acc = 0;
-  for (int r = r0; r < rows; r += rstep)
-  {
-    const Px* p = ref + (size_t)(r * row_mul) * pitch;
-    const int16_t* o = org_s + (r * row_mul) * w;
-    for (int k = 0; k < w; k++) acc += (uint32_t)hm_abs((int)o[k] - (int)__ldg(p + k));
-  }
-  return acc;
-}
-
-// Evaluate up to 32 points at once. Lane group g = lane / lanes_per_point owns point g.
-// (x, y, valid, pnr, dist) are the data of THIS lane's point. Updates `best` warp-uniformly.
-template <typename Px, bool PACKED>
-__device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
-                                        int lanes_per_point, int x, int y, bool valid, int pnr, int dist,
-                                        TzBest& best)
-{
-  const int lane = threadIdx.x & 31;
-  const int sub = lane & (lanes_per_point - 1);
-  uint32_t part = 0;
-  if (valid)
-  {
-    const Px* ref = ref00 + (ptrdiff_t)y * pitch + x;
-    if (PACKED)
-      part = sad_rows_packed((const uint8_t*)ref, pitch, (const uint32_t*)org_s, J.pu_w >> 2, J.rows, 1 << J.sub_shift, sub, lanes_per_point);
-    else
-      part = sad_rows_generic<Px>(ref, pitch, (const int16_t*)org_s, J.pu_w, J.rows, 1 << J.sub_shift, sub, lanes_per_point);
-  }
-  for (int o = lanes_per_point >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(FULL_MASK, part, o);
-  uint32_t cost = 0xffffffffu;
-  if (valid) cost = hm_sad_norm(part, J.sub_shift, J.bit_depth) + hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, x, y);
-  best.n_cand += __popc(__ballot_sync(FULL_MASK, valid && sub == 0));
-  const uint32_t m = __reduce_min_sync(FULL_MASK, cost);
-  if (m < best.cost)                                   // strict '<' (TEncSearch.cpp:414)
-  {
-    const int src = __ffs(__ballot_sync(FULL_MASK, valid && cost == m)) - 1;
-    best.cost = m;
-    best.x = __shfl_sync(FULL_MASK, x, src);
-    best.y = __shfl_sync(FULL_MASK, y, src);
-    best.dist = __shfl_sync(FULL_MASK, dist, src);
-    best.pnr = __shfl_sync(FULL_MASK, pnr, src);
-    best.round = 0;
-  }
-}
-
-// side-specific window test of the reference: a coordinate is tested only against the bound it
-// moved towards (TEncSearch.cpp:634-790, 443-549)
-__device__ __forceinline__ bool tz_in_window(const TzJob& J, int cx, int cy, int x, int y)
-{
-  if (x < cx && x < J.L) return false;
-  if (x > cx && x > J.R) return false;
-  if (y < cy && y < J.T) return false;
-  if (y > cy && y > J.B) return false;
-  return true;
-}
-
-// xTZ8PointDiamondSearch (TEncSearch.cpp:616-791): point i of the round in emission order
-template <typename Px, bool PACKED>
-__device__ __forceinline__ void tz_diamond(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
-                                           int cx, int cy, int d, TzBest& best)
-{
-  const int lane = threadIdx.x & 31;
-  best.round += 1;
-  int n, lpp;
-  if (d == 1) { n = 4; lpp = 8; } else if (d <= 8) { n = 8; lpp = 4; } else { n = 16; lpp = 2; }
-  lpp = min(lpp, J.rows);                               // never more lanes than rows (rows is a power of two or 6/12/24... )
-  // lanes-per-point must be a power of two: round down
-  lpp = 1 << (31 - __clz(lpp));
-  const int i = lane / lpp;
-  int x = cx, y = cy, pnr = 0, dist = d;
-  if (d == 1)
-  {
-    // (cx,top,2) (left,cy,4) (right,cy,5) (cx,bottom,7)
-    if (i == 0) { y = cy - 1; pnr = 2; } else if (i == 1) { x = cx - 1; pnr = 4; }
-    else if (i == 2) { x = cx + 1; pnr = 5; } else { y = cy + 1; pnr = 7; }
-  }
-  else if (d <= 8)
-  {
-    const int h = d >> 1;
-    switch (i)
-    {
-      case 0: y = cy - d; pnr = 2; break;
-      case 1: x = cx - h; y = cy - h; pnr = 1; dist = h; break;
-      case 2: x = cx + h; y = cy - h; pnr = 3; dist = h; break;
-      case 3: x = cx - d; pnr = 4; break;
-      case 4: x = cx + d; pnr = 5; break;
-      case 5: x = cx - h; y = cy + h; pnr = 6; dist = h; break;
-      case 6: x = cx + h; y = cy + h; pnr = 8; dist = h; break;
-      default: y = cy + d; pnr = 7; break;
-    }
-  }
-  else
-  {
-    if (i < 4)
-    {
-      if (i == 0) y = cy - d; else if (i == 1) x = cx - d; else if (i == 2) x = cx + d; else y = cy + d;
-    }
-    else
-    {
-      const int idx = ((i - 4) >> 2) + 1, k = (i - 4) & 3;   // k: 0 (xl,yt) 1 (xr,yt) 2 (xl,yb) 3 (xr,yb)
-      const int q = (d >> 2) * idx;
-      x = (k & 1) ? cx + q : cx - q;
-      y = (k & 2) ? cy + d - q : cy - d + q;
-    }
-  }
-  const bool valid = (i < n) && tz_in_window(J, cx, cy, x, y);
-  tz_eval<Px, PACKED>(J, ref00, pitch, org_s, lpp, x, y, valid, pnr, dist, best);
-}
-
-// xTZ2PointSearch (TEncSearch.cpp:429-557): offsets (dx0,dy0,dx1,dy1) of the two untested
-// neighbours for best-point numbers 1..8, in the reference's evaluation order
-__constant__ int8_t c_two_point[9][4] = {
-  { 0, 0, 0, 0 },
-  { -1, 0, 0, -1 }, { -1, -1, 1, -1 }, { 0, -1, 1, 0 },
-  { -1, 1, -1, -1 }, { 1, -1, 1, 1 },
-  { -1, 0, 0, 1 }, { -1, 1, 1, 1 }, { 1, 0, 0, 1 } };
-
-template <typename Px, bool PACKED>
-__device__ __forceinline__ void tz_two_point(const TzJob& J, const Px* ref00, int pitch, const void* org_s, TzBest& best)
-{
-  const int lane = threadIdx.x & 31;
-  const int nr = best.pnr;
-  if (nr < 1 || nr > 8) return;
-  int lpp = min(16, J.rows);
-  lpp = 1 << (31 - __clz(lpp));
-  const int i = lane / lpp;
-  const int cx = best.x, cy = best.y;
-  const int x = cx + c_two_point[nr][i == 0 ? 0 : 2];
-  const int y = cy + c_two_point[nr][i == 0 ? 1 : 3];
-  const bool valid = (i < 2) && tz_in_window(J, cx, cy, x, y);
-  tz_eval<Px, PACKED>(J, ref00, pitch, org_s, lpp, x, y, valid, 0, 2, best);
-}
+// me_tz.cu -- batch TZ search kernel: one warp per job, TZ_WARPS jobs per CTA.
+// Replaces TEncSearch::xTZSearch (TEncSearch.cpp:4027-4228); the search itself is in
+// me_tz_impl.cuh.
+#include "me_tz_impl.cuh"
 
 template <typename Px, bool PACKED>
 __global__ void __launch_bounds__(TZ_WARPS * 32)
@@ -211,134 +15,9 @@ tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs, const int16_
   if (job_id >= n_jobs) return;
   const hmgpu_me_job jb = jobs[job_id];
   if (!(jb.flags & HMGPU_F_INTEGER) || (jb.flags & HMGPU_F_FULL)) return;
-
-  TzJob J;
-  J.pu_w = jb.pu_w; J.pu_h = jb.pu_h;
-  J.sub_shift = ((jb.flags & HMGPU_F_FEN) && jb.pu_h > 8) ? 1 : 0;   // TEncSearch.cpp:347-353
-  J.rows = J.pu_h >> J.sub_shift;
-  J.pred_x = jb.pred_x; J.pred_y = jb.pred_y; J.ui_cost = jb.ui_cost;
-  J.L = jb.win_l; J.T = jb.win_t; J.R = jb.win_r; J.B = jb.win_b;
-  J.bit_depth = refs.bit_depth;
-
-  const int pitch = refs.pitch;
-  const Px* ref00 = (const Px*)refs.base[jb.ref_slot] + (ptrdiff_t)jb.pu_y * pitch + jb.pu_x;
-  unsigned char* s_org = s_org_all[warp];
-
-  // ---- stage the key pattern -------------------------------------------------------------
-  if (PACKED)
-  {
-    const int wq = J.pu_w >> 2;
-    const uint8_t* o = (const uint8_t*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
-    uint32_t* so = (uint32_t*)s_org;
-    for (int i = lane; i < J.pu_h * wq; i += 32)
-    {
-      const int r = i / wq, k = i - r * wq;
-      so[i] = __ldg((const uint32_t*)(o + (size_t)r * org.pitch) + k);   // pu_x % 4 == 0, pitch % 4 == 0
-    }
-  }
-  else
-  {
-    int16_t* so = (int16_t*)s_org;
-    if (jb.flags & HMGPU_F_ORG_BLOCK)
-    {
-      const int16_t* o = org_blocks + jb.org_offset;
-      for (int i = lane; i < J.pu_h * J.pu_w; i += 32) so[i] = o[i];
-    }
-    else
-    {
-      const Px* o = (const Px*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
-      for (int i = lane; i < J.pu_h * J.pu_w; i += 32)
-      {
-        const int r = i / J.pu_w, k = i - r * J.pu_w;
-        so[i] = (int16_t)o[(size_t)r * org.pitch + k];
-      }
-    }
-  }
-  __syncwarp();
-
-  TzBest best; best.cost = 0xffffffffu; best.x = 0; best.y = 0; best.dist = 0; best.round = 0; best.pnr = 0; best.n_cand = 0;
-
-  // ---- start points (TEncSearch.cpp:4045-4093): clipped MVP>>2, zero, clipped 2Nx2N integer MV.
-  // Evaluated sequentially in the reference; concurrently here with emission order = group index.
-  const bool has2n = (jb.flags & HMGPU_F_HAS_2NX2N) != 0;
-  {
-    int lpp = min(8, J.rows);
-    lpp = 1 << (31 - __clz(lpp));
-    const int i = lane / lpp;
-    int x = 0, y = 0;
-    if (i == 0)
-    {
-      x = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)jb.start_x)) >> 2;
-      y = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)jb.start_y)) >> 2;
-    }
-    else if (i == 2)
-    {
-      x = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(jb.i2n_x << 2))) >> 2;
-      y = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(jb.i2n_y << 2))) >> 2;
-    }
-    const bool valid = i < (has2n ? 3 : 2);
-    tz_eval<Px, PACKED>(J, ref00, pitch, s_org, lpp, x, y, valid, 0, 0, best);
-  }
-  // raster window: re-centred on the best start point when the 2Nx2N MV was tested (:4083-4092)
-  int rL = J.L, rT = J.T, rR = J.R, rB = J.B;
-  if (has2n)
-  {
-    const int px = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(best.x << 2)));
-    const int py = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(best.y << 2)));
-    const int sr4 = jb.search_range << 2;
-    rL = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(px - sr4))) >> 2;
-    rT = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(py - sr4))) >> 2;
-    rR = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(px + sr4))) >> 2;
-    rB = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(py + sr4))) >> 2;
-  }
-
-  // ---- first search: diamonds at distance 1,2,4,.. ; stop 3 rounds after the last improvement
-  int cx = best.x, cy = best.y;
-  for (int d = 1; d <= jb.search_range; d <<= 1)
-  {
-    tz_diamond<Px, PACKED>(J, ref00, pitch, s_org, cx, cy, d, best);
-    if (best.round >= 3) break;
-  }
-  if (best.dist == 1)                                   // :4137-4141
-  {
-    best.dist = 0;
-    tz_two_point<Px, PACKED>(J, ref00, pitch, s_org, best);
-  }
-  if (best.dist > 5)                                    // raster, step 5 (:4144-4154)
-  {
-    best.dist = 5;
-    const int nx = (rR - rL) / 5 + 1, ny = (rB - rT) / 5 + 1;
-    const int total = (rR >= rL && rB >= rT) ? nx * ny : 0;
-    for (int base = 0; base < total; base += 32)
-    {
-      const int i = base + lane;
-      const int gy = i / nx, gx = i - gy * nx;
-      tz_eval<Px, PACKED>(J, ref00, pitch, s_org, 1, rL + gx * 5, rT + gy * 5, i < total, 0, 5, best);
-    }
-  }
-  while (best.dist > 0)                                 // star refinement (:4189-4223)
-  {
-    cx = best.x; cy = best.y;
-    best.dist = 0; best.pnr = 0;
-    for (int d = 1; d < jb.search_range + 1; d <<= 1)
-      tz_diamond<Px, PACKED>(J, ref00, pitch, s_org, cx, cy, d, best);
-    if (best.dist == 1)
-    {
-      best.dist = 0;
-      if (best.pnr != 0) tz_two_point<Px, PACKED>(J, ref00, pitch, s_org, best);
-    }
-  }
-
-  if (lane == 0)
-  {
-    hmgpu_me_result r;
-    r.int_x = (int16_t)best.x; r.int_y = (int16_t)best.y;
-    r.int_sad = best.cost - hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, best.x, best.y);
-    r.half_x = r.half_y = r.qter_x = r.qter_y = 0;
-    r.frac_cost = 0;
-    r.n_cand = best.n_cand;
-    results[job_id] = r;
-  }
+  hmgpu_me_result r;
+  tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org_all[warp], r);
+  if (lane == 0) results[job_id] = r;
 }
 
 int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,

@@ -11,7 +11,7 @@
 #include "hmgpu_internal.cuh"
 
 static const char* const k_stage_names[HMGPU_ST_COUNT] = {
-  "planes", "org", "tz", "full", "frac_expand", "frac_dist", "frac_select", "dist", "transform", "quant", "mc" };
+  "planes", "org", "tz", "full", "frac_expand", "frac_dist", "frac_select", "dist", "transform", "quant", "mc", "single" };
 
 static void prof_drain(hmgpu_ctx* ctx)
 {

@@ -1,0 +1,211 @@
+// HmGpuHost.cpp -- HM-side binding of libhmgpu (see HmGpuHost.h).
+#include "HmGpuHost.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <ctime>
+
+#include "TLibCommon/TComRom.h"
+#include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/TComPic.h"
+#include "TLibCommon/TComPicYuv.h"
+#include "TLibCommon/TComPattern.h"
+#include "TLibCommon/TComSlice.h"
+
+#include "hmgpu.h"
+
+static Double xNow()
+{
+  struct timespec t;
+  clock_gettime( CLOCK_MONOTONIC, &t );
+  return (Double)t.tv_sec + 1e-9 * (Double)t.tv_nsec;
+}
+
+HmGpuHost& HmGpuHost::instance()
+{
+  static HmGpuHost s_host;
+  return s_host;
+}
+
+HmGpuHost::HmGpuHost()
+: m_ctx( NULL ), m_picW( 0 ), m_picH( 0 ), m_tick( 0 ), m_orgPic( NULL ), m_orgPoc( -1 ), m_keyBlock( NULL )
+, m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
+{
+  for ( Int i = 0; i < NUM_SLOTS; i++ )
+  {
+    m_slotPic[i] = NULL; m_slotPoc[i] = -1; m_slotUse[i] = 0;
+  }
+}
+
+HmGpuHost::~HmGpuHost()
+{
+  if ( m_ctx )
+  {
+    fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
+                     "%.3f s one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
+             (unsigned long long)m_calls, (unsigned long long)m_cands, m_seconds, m_calls ? m_seconds / (Double)m_calls * 1e6 : 0.0,
+             m_seconds > 0 ? (Double)m_cands / m_seconds / 1e6 : 0.0, m_initSeconds,
+             (unsigned long long)m_uploads, m_uploadSeconds,
+             (unsigned long long)hmgpu_launch_count( m_ctx ), (unsigned long long)m_checked );
+    hmgpu_destroy( m_ctx );
+  }
+  delete [] m_keyBlock;
+}
+
+Void HmGpuHost::xFail( const char* what )
+{
+  // no CPU fallback by design: a GPU error aborts the encode
+  fprintf( stderr, "[GPUME] %s: %s\n", what, hmgpu_last_error( m_ctx ) );
+  exit( 1 );
+}
+
+Void HmGpuHost::xInit( TComDataCU* pcCU )
+{
+  if ( m_ctx ) return;
+  const Double t0 = xNow();
+  m_picW = pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples();
+  m_picH = pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples();
+  const char* dev = getenv( "HMGPU_DEVICE" );
+  if ( hmgpu_create( dev ? atoi( dev ) : 0, m_picW, m_picH, g_bitDepth[CHANNEL_TYPE_LUMA], NUM_SLOTS, &m_ctx ) != HMGPU_OK )
+  {
+    xFail( "hmgpu_create" );
+  }
+  m_keyBlock = new Pel[MAX_CU_SIZE * MAX_CU_SIZE];
+  m_initSeconds = xNow() - t0;
+}
+
+/// reference reconstruction -> device slot (uploaded once: TComSlice.cpp:346 pads it once, too)
+Int HmGpuHost::xRefSlot( TComPic* pcRefPic )
+{
+  const Int poc = pcRefPic->getPOC();
+  Int lru = 0;
+  for ( Int i = 0; i < NUM_SLOTS; i++ )
+  {
+    if ( m_slotPic[i] == pcRefPic && m_slotPoc[i] == poc )
+    {
+      m_slotUse[i] = ++m_tick;
+      return i;
+    }
+    if ( m_slotUse[i] < m_slotUse[lru] ) lru = i;
+  }
+  const Double t0 = xNow();
+  TComPicYuv* rec = pcRefPic->getPicYuvRec();
+  if ( hmgpu_ref_upload( m_ctx, lru, rec->getAddr( COMPONENT_Y ), rec->getStride( COMPONENT_Y ), NULL, NULL, 0 ) != HMGPU_OK )
+  {
+    xFail( "hmgpu_ref_upload" );
+  }
+  m_slotPic[lru] = pcRefPic; m_slotPoc[lru] = poc; m_slotUse[lru] = ++m_tick;
+  m_uploads++; m_uploadSeconds += xNow() - t0;
+  return lru;
+}
+
+Void HmGpuHost::xUploadOrg( TComDataCU* pcCU )
+{
+  TComPic* pic = pcCU->getPic();
+  if ( m_orgPic == pic && m_orgPoc == pic->getPOC() ) return;
+  const Double t0 = xNow();
+  TComPicYuv* org = pic->getPicYuvOrg();
+  if ( hmgpu_org_upload( m_ctx, org->getAddr( COMPONENT_Y ), org->getStride( COMPONENT_Y ) ) != HMGPU_OK )
+  {
+    xFail( "hmgpu_org_upload" );
+  }
+  m_orgPic = pic; m_orgPoc = pic->getPOC();
+  m_uploads++; m_uploadSeconds += xNow() - t0;
+  // a new picture: references of the previous one may have been replaced in the DPB objects
+}
+
+Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
+                              const TComMv& rcMvSrchRngLT, const TComMv& rcMvSrchRngRB, const TComMv& rcMvPred, const TComMv& rcMvIn,
+                              Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
+                              Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut )
+{
+  xInit( pcCU );
+  xUploadOrg( pcCU );
+
+  hmgpu_me_job j;
+  memset( &j, 0, sizeof( j ) );
+  // PU origin in picture coordinates, recovered from the reference pointer (TEncSearch.cpp:3857)
+  TComPicYuv* rec = pcRefPic->getPicYuvRec();
+  const ptrdiff_t off = piRefY - rec->getAddr( COMPONENT_Y );
+  j.pu_y = (int16_t)( off / iRefStride );
+  j.pu_x = (int16_t)( off - (ptrdiff_t)j.pu_y * iRefStride );
+  j.pu_w = (uint8_t)pcPatternKey->getROIYWidth();
+  j.pu_h = (uint8_t)pcPatternKey->getROIYHeight();
+  j.ref_slot = (uint8_t)xRefSlot( pcRefPic );
+  const Double t0 = xNow();
+  j.pred_x = rcMvPred.getHor(); j.pred_y = rcMvPred.getVer();
+  j.win_l = rcMvSrchRngLT.getHor(); j.win_t = rcMvSrchRngLT.getVer();
+  j.win_r = rcMvSrchRngRB.getHor(); j.win_b = rcMvSrchRngRB.getVer();
+  hmgpu_clip_bounds( m_picW, m_picH, pcCU->getCUPelX(), pcCU->getCUPelY(), &j.clip_hmin );  // TComDataCU::clipMv
+  j.search_range = (int16_t)iSearchRange;
+  // m_uiCost = m_uiLambdaMotionSAD[0] = floor(65536 * sqrt(lambda)) (TComRdCost.cpp:209, TComRdCost.h:165)
+  j.ui_cost = (UInt)floor( 65536.0 * dSqrtLambda );
+  UInt flags = HMGPU_F_INTEGER | HMGPU_F_FRAC;
+  if ( bFastEnc )    flags |= HMGPU_F_FEN;
+  if ( bHADME )      flags |= HMGPU_F_HADME;
+  if ( bLossless )   flags |= HMGPU_F_LOSSLESS;
+  if ( bFullSearch ) flags |= HMGPU_F_FULL;
+  Int keyElems = 0;
+  if ( bBi )
+  {
+    // bi-prediction: the key pattern is 2*org - otherPred (TComYuv.cpp:393-424), not the source picture
+    flags |= HMGPU_F_ORG_BLOCK;
+    const Pel* src = pcPatternKey->getROIY();
+    const Int  st  = pcPatternKey->getPatternLStride();
+    for ( Int y = 0; y < j.pu_h; y++ )
+    {
+      memcpy( m_keyBlock + y * j.pu_w, src + y * st, sizeof( Pel ) * j.pu_w );
+    }
+    keyElems = j.pu_w * j.pu_h;
+    j.start_x = rcMvIn.getHor(); j.start_y = rcMvIn.getVer();
+  }
+  else
+  {
+    j.start_x = rcMvPred.getHor(); j.start_y = rcMvPred.getVer();   // rcMv = *pcMvPred (TEncSearch.cpp:3878)
+    if ( pIntegerMv2Nx2NPred )
+    {
+      flags |= HMGPU_F_HAS_2NX2N;
+      j.i2n_x = pIntegerMv2Nx2NPred->getHor(); j.i2n_y = pIntegerMv2Nx2NPred->getVer();
+    }
+  }
+  j.flags = (uint8_t)flags;
+
+  hmgpu_me_result r;
+  if ( hmgpu_me_search( m_ctx, &j, 1, keyElems ? m_keyBlock : NULL, keyElems, &r ) != HMGPU_OK )
+  {
+    xFail( "hmgpu_me_search" );
+  }
+  rcOut.mvInt.set ( r.int_x,  r.int_y  );
+  rcOut.mvHalf.set( r.half_x, r.half_y );
+  rcOut.mvQter.set( r.qter_x, r.qter_y );
+  rcOut.sadInt = r.int_sad;
+  rcOut.cost   = r.frac_cost;
+  m_calls++;
+  m_cands   += r.n_cand;
+  m_seconds += xNow() - t0;
+}
+
+Void HmGpuHost::checkInteger( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu )
+{
+  if ( rcOut.mvInt.getHor() != rcMvCpu.getHor() || rcOut.mvInt.getVer() != rcMvCpu.getVer() )
+  {
+    fprintf( stderr, "[GPUME] MISMATCH at call %llu: integer MV gpu (%d,%d) cpu (%d,%d)\n", (unsigned long long)m_calls,
+             rcOut.mvInt.getHor(), rcOut.mvInt.getVer(), rcMvCpu.getHor(), rcMvCpu.getVer() );
+    exit( 2 );
+  }
+}
+
+Void HmGpuHost::checkFractional( const HmGpuSearchOut& rcOut, const TComMv& rcHalfCpu, const TComMv& rcQterCpu, Distortion uiCostCpu )
+{
+  if ( rcOut.mvHalf.getHor() != rcHalfCpu.getHor() || rcOut.mvHalf.getVer() != rcHalfCpu.getVer() ||
+       rcOut.mvQter.getHor() != rcQterCpu.getHor() || rcOut.mvQter.getVer() != rcQterCpu.getVer() || rcOut.cost != uiCostCpu )
+  {
+    fprintf( stderr, "[GPUME] MISMATCH at call %llu: half gpu (%d,%d) cpu (%d,%d), quarter gpu (%d,%d) cpu (%d,%d), cost gpu %u cpu %u\n",
+             (unsigned long long)m_calls, rcOut.mvHalf.getHor(), rcOut.mvHalf.getVer(), rcHalfCpu.getHor(), rcHalfCpu.getVer(),
+             rcOut.mvQter.getHor(), rcOut.mvQter.getVer(), rcQterCpu.getHor(), rcQterCpu.getVer(), rcOut.cost, uiCostCpu );
+    exit( 2 );
+  }
+  m_checked++;
+}

@@ -1,0 +1,70 @@
+// HmGpuHost.h -- HM-side binding of libhmgpu (the GPUME cfg switch).
+//
+// This is the host half of the drop-in: C++ that lives inside the HM encoder, keeps the
+// TEncSearch / TComRdCost interfaces and turns one TEncSearch::xMotionEstimation call
+// (TEncSearch.cpp:3816-3906) into one hmgpu_me_job for the extern "C" library.  It is compiled
+// together with the reference sources by hm-16.2_b200/host/Makefile after hm_gpume.patch has
+// added the hook lines; nothing here is needed when GPUME=0.
+#ifndef HM_GPU_HOST_H
+#define HM_GPU_HOST_H
+
+#include "TLibCommon/CommonDef.h"
+#include "TLibCommon/TComMv.h"
+
+class TComDataCU;
+class TComPic;
+class TComPattern;
+struct hmgpu_ctx;
+
+struct HmGpuSearchOut
+{
+  TComMv     mvInt;    ///< rcMv after the integer search (integer pel)
+  TComMv     mvHalf;   ///< cMvHalf
+  TComMv     mvQter;   ///< cMvQter
+  Distortion sadInt;   ///< ruiSAD of the integer search
+  Distortion cost;     ///< ruiCost after xPatternSearchFracDIF
+};
+
+class HmGpuHost
+{
+public:
+  static HmGpuHost& instance();
+
+  /// Replaces xPatternSearch / xPatternSearchFast + xPatternSearchFracDIF of one xMotionEstimation call.
+  /// piRefY points at the PU origin inside the reference reconstruction (TEncSearch.cpp:3857).
+  Void motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
+                     const TComMv& rcMvSrchRngLT, const TComMv& rcMvSrchRngRB, const TComMv& rcMvPred, const TComMv& rcMvIn,
+                     Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
+                     Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut );
+
+  /// GPUME=2: compare with what the CPU search just produced; abort on the first mismatch
+  Void checkInteger   ( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu );
+  Void checkFractional( const HmGpuSearchOut& rcOut, const TComMv& rcHalfCpu, const TComMv& rcQterCpu, Distortion uiCostCpu );
+
+private:
+  HmGpuHost();
+  ~HmGpuHost();
+  Void xInit        ( TComDataCU* pcCU );
+  Int  xRefSlot     ( TComPic* pcRefPic );
+  Void xUploadOrg   ( TComDataCU* pcCU );
+  Void xFail        ( const char* what );
+
+  static const Int NUM_SLOTS = 16;
+  hmgpu_ctx*  m_ctx;
+  Int         m_picW, m_picH;
+  const void* m_slotPic[NUM_SLOTS];
+  Int         m_slotPoc[NUM_SLOTS];
+  UInt64      m_slotUse[NUM_SLOTS];
+  UInt64      m_tick;
+  const void* m_orgPic;
+  Int         m_orgPoc;
+  Pel*        m_keyBlock;
+  // statistics
+  UInt64      m_calls, m_cands, m_checked;
+  Double      m_seconds;        ///< inside hmgpu_me_search
+  Double      m_initSeconds;    ///< CUDA context + library set-up (once)
+  Double      m_uploadSeconds;  ///< reference / source picture uploads
+  UInt64      m_uploads;
+};
+
+#endif

@@ -94,7 +94,7 @@ def _random_jobs(rng, n, bit_depth, mode, n_refs, org_blocks=None):
     return jobs, blocks, off
 
 
-def _run(bit_depth, mode, n, noise=False, with_blocks=False, seed=5):
+def _run(bit_depth, mode, n, noise=False, with_blocks=False, seed=5, chunk=None):
     rng = np.random.default_rng(seed)
     fr = _frames(bit_depth, 4, noise)
     org = fr[3]
@@ -115,7 +115,28 @@ def _run(bit_depth, mode, n, noise=False, with_blocks=False, seed=5):
         for k in range(3):
             ctx.ref_upload(k, fr[k])
         ctx.org_upload(org)
-        got = ctx.me_search(jobs, org_blocks)
+        if chunk is None:
+            got = ctx.me_search(jobs, org_blocks)
+        else:
+            # small calls take the fused low-latency kernel (me_single.cu): 1..chunk jobs per call
+            parts, i, k = [], 0, 1
+            while i < len(jobs):
+                sub_jobs = jobs[i:i + k].copy()
+                sub_blocks = None
+                if org_blocks is not None:
+                    # re-base the key-pattern blocks of this call
+                    bl, off = [], 0
+                    for j in sub_jobs:
+                        if j["flags"] & hmgpu.F_ORG_BLOCK:
+                            sz = int(j["pu_w"]) * int(j["pu_h"])
+                            bl.append(org_blocks[int(j["org_offset"]):int(j["org_offset"]) + sz])
+                            j["org_offset"] = off
+                            off += sz
+                    sub_blocks = np.concatenate(bl) if bl else None
+                parts.append(ctx.me_search(sub_jobs, sub_blocks))
+                i += k
+                k = k % chunk + 1
+            got = np.concatenate(parts)
     assert_results_equal(got, exp, jobs)
     return got
 
@@ -140,6 +161,13 @@ def test_frac_only(bit_depth):
 @pytest.mark.parametrize("mode", ["tz", "fs", "frac"])
 def test_bipred_key_pattern_blocks(bit_depth, mode):
     _run(bit_depth, mode, 120 if mode != "fs" else 48, with_blocks=True)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+@pytest.mark.parametrize("mode", ["tz", "fs", "frac"])
+@pytest.mark.parametrize("with_blocks", [False, True])
+def test_low_latency_path(bit_depth, mode, with_blocks):
+    _run(bit_depth, mode, 96 if mode != "fs" else 40, with_blocks=with_blocks, chunk=5, seed=21)
 
 
 @pytest.mark.parametrize("bit_depth", [8, 10])
