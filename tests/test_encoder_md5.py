@@ -45,4 +45,4 @@ def test_lowdelay_b_bipred():
 
 
 def test_randomaccess_closed_gop():
-    _compare("--cfg", "randomaccess_main", "--frames", "9", "--gpume", "1", "--", "--DecodingRefreshType=2", "--IntraPeriod=8")
+    _compare("--cfg", "randomaccess_main", "--frames", "18", "--gpume", "1", "--", "--DecodingRefreshType=2", "--IntraPeriod=16")
