@@ -13,6 +13,7 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
                       hmgpu_me_result* d_results, bool any_org_block, int max_win_bytes);
 int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_frac);
+int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, hmgpu_me_result* d_results, bool any_frac);
 int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                         hmgpu_me_result* d_results, uint32_t* d_flags, uint32_t ticket, bool any_org_block, int max_win_bytes);
 
@@ -95,7 +96,11 @@ int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   int rc;
   if (any_tz && (rc = hmgpu_launch_tz(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block))) return rc;
   if (any_full && (rc = hmgpu_launch_full(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, max_win_bytes))) return rc;
-  if ((rc = hmgpu_launch_frac(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_frac))) return rc;
+  if (ctx->px_bytes == 1 && !any_org_block && !getenv("HMGPU_FRAC_V1"))
+  {
+    if ((rc = hmgpu_launch_frac_packed(ctx, d_jobs, n_jobs, d_results, any_frac))) return rc;
+  }
+  else if ((rc = hmgpu_launch_frac(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_frac))) return rc;
   return HMGPU_OK;
 }
 

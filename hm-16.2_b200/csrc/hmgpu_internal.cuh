@@ -139,6 +139,14 @@ __device__ __forceinline__ uint32_t vabsdiff4_acc(uint32_t a, uint32_t b, uint32
   return r;
 }
 
+// 4-way dot product of UNSIGNED bytes a with SIGNED bytes b, accumulated: one IDP.4A.U8.S8
+__device__ __forceinline__ int hm_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+  int r;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 __device__ __forceinline__ int hm_abs(int v) { return v < 0 ? -v : v; }
 
 // integer-pel SAD normalisation: (sum << iSubShift) >> (bitDepth-8)  (TComRdCost.cpp:520-521)

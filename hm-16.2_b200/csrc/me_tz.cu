@@ -4,7 +4,7 @@
 #include "me_tz_impl.cuh"
 
 template <typename Px, bool PACKED>
-__global__ void __launch_bounds__(TZ_WARPS * 32)
+__global__ void __launch_bounds__(TZ_WARPS * 32, 8)
 tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs, const int16_t* __restrict__ org_blocks,
                  RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results)
 {

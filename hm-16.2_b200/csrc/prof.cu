@@ -79,6 +79,43 @@ __global__ void __launch_bounds__(256) mb_vabsdiff4_kernel(uint32_t* out, uint32
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// IDP.4A.U8.S8 stream (the horizontal Hadamard pass of the SATD kernel is built from it)
+__global__ void __launch_bounds__(256) mb_dp4a_kernel(uint32_t* out, uint32_t seed, int iters)
+{
+  int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+  const uint32_t x = seed + threadIdx.x * 0x01010101u;
+  const int y = (int)(seed * 7 + blockIdx.x);
+  for (int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+    {
+      a0 = hm_dp4a_us(x, (uint32_t)y, a0); a1 = hm_dp4a_us(x, (uint32_t)a0, a1); a2 = hm_dp4a_us(x, (uint32_t)a1, a2); a3 = hm_dp4a_us(x, (uint32_t)a2, a3);
+      a4 = hm_dp4a_us(x, (uint32_t)a3, a4); a5 = hm_dp4a_us(x, (uint32_t)a4, a5); a6 = hm_dp4a_us(x, (uint32_t)a5, a6); a7 = hm_dp4a_us(x, (uint32_t)a6, a7);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7);
+}
+
+// dp4a + independent add stream: do the FMA-side IDP and the ALU-side adds overlap?
+__global__ void __launch_bounds__(256) mb_dp4a_add_kernel(uint32_t* out, uint32_t seed, int iters)
+{
+  int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  uint32_t b0 = seed, b1 = seed * 3, b2 = seed * 5, b3 = seed * 7;
+  const uint32_t x = seed + threadIdx.x * 0x01010101u;
+  const int y = (int)(seed * 7 + blockIdx.x);
+  for (int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+    {
+      a0 = hm_dp4a_us(x, (uint32_t)y, a0); a1 = hm_dp4a_us(x, (uint32_t)a0, a1); a2 = hm_dp4a_us(x, (uint32_t)a1, a2); a3 = hm_dp4a_us(x, (uint32_t)a2, a3);
+      b0 = max(b0, b1) ^ b2; b1 = max(b1, b2) ^ b3; b2 = max(b2, b3) ^ b0; b3 = max(b3, b0) ^ b1;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(a0 + a1 + a2 + a3) + b0 + b1 + b2 + b3;
+}
+
 extern "C" {
 
 int hmgpu_profile_enable(hmgpu_ctx* ctx, int on)
@@ -127,7 +164,9 @@ int hmgpu_microbench(hmgpu_ctx* ctx, int which, double* gops)
   {
     HMGPU_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (which == 0) mb_iadd_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->d_work, 12345u + rep, iters);
-    else mb_vabsdiff4_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->d_work, 12345u + rep, iters);
+    else if (which == 1) mb_vabsdiff4_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->d_work, 12345u + rep, iters);
+    else if (which == 2) mb_dp4a_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->d_work, 12345u + rep, iters);
+    else mb_dp4a_add_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->d_work, 12345u + rep, iters);
     HMGPU_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     HMGPU_CUDA(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -137,7 +176,8 @@ int hmgpu_microbench(hmgpu_ctx* ctx, int which, double* gops)
   ctx->launches += 5;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   // instructions per thread: iadd kernel = 2 per statement (xor + add) * 64 statements per iteration
-  const double per_thread = (which == 0 ? 2.0 : 1.0) * 64.0 * iters;
+  // dp4a kernel: 64 per iteration; dp4a+add kernel: 16 * (4 dp4a + 8 alu) = 192 per iteration
+  const double per_thread = (which == 0 ? 128.0 : which == 3 ? 192.0 : 64.0) * iters;
   *gops = per_thread * blocks * threads / (best * 1e-3) / 1e9;
   return HMGPU_OK;
 }
