@@ -156,10 +156,17 @@ def run_ours(args, rank, world, local_rank):
         ctx.org_upload_device(d_frames[N_REFS + 1].data_ptr(), PIC_W)
         ctx.me_search_device(d_jobs.data_ptr(), n_jobs, None, d_res.data_ptr(), flags_any)
 
+    # end-to-end inputs live in page-locked host memory (hmgpu_host_alloc): the library copies them directly
+    h_frames = ctx.host_array(frames.shape, np.int16)
+    h_frames[...] = frames
+    h_jobs = ctx.host_array((n_jobs,), hmgpu.ME_JOB)
+    h_jobs[...] = jobs
+    h_res = ctx.host_array((n_jobs,), hmgpu.ME_RESULT)
+
     def step_host(i):
-        ctx.ref_upload(i % N_REFS, frames[i % N_REFS])
-        ctx.org_upload(frames[N_REFS + 1])
-        return ctx.me_search(jobs)
+        ctx.ref_upload(i % N_REFS, h_frames[i % N_REFS])
+        ctx.org_upload(h_frames[N_REFS + 1])
+        return ctx.me_search(h_jobs, out=h_res)
 
     def barrier():
         if dist is not None:
@@ -246,10 +253,33 @@ def run_ours(args, rank, world, local_rank):
                "stage_ms_per_step": stage_ms, "roofline": roofline, "roofline_int32": roofline_int32}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=1)
+        if world == 1 and not args.no_encode:
+            out["encode"] = encode_runs()
         print(json.dumps(out))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def encode_runs():
+    """whole-encoder numbers (BASELINE.json: encode fps, bitstream MD5-identical): the HM encoder with
+    GPUME=1 beside the unmodified CPU encoder on bounded clips.  Uses the CPU reference encoder
+    (oracle/_ref) as the baseline leg only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import encode_compare
+    if not encode_compare.available():
+        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
+    runs = {}
+    for name, a in (("cfg1_lowdelay_P_fullsearch_SR64_416x240_3f", ("lowdelay_P_main", "416x240", 3, 32, 1, ["--FastSearch=0", "--SearchRange=64"])),
+                    ("cfg2_lowdelay_P_TZ_1920x1080_2f", ("lowdelay_P_main", "1920x1080", 2, 32, 1, []))):
+        try:
+            r = encode_compare.compare(*a)
+            runs[name] = {"cpu_fps": r["cpu"]["fps"], "gpu_fps": r["gpu"]["fps"], "cpu_s": r["cpu"]["wall_s"], "gpu_s": r["gpu"]["wall_s"],
+                          "bitstream_md5_identical": r["bitstream_identical"], "recon_md5_identical": r["recon_identical"],
+                          "gpume": r["gpu"]["gpume"]}
+        except SystemExit as e:
+            runs[name] = {"error": str(e)}
+    return runs
 
 
 # ---- the reference on the host cores ------------------------------------------------------------
@@ -334,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=120000, help="jobs in the CPU baseline sample (1 core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encode", action="store_true", help="skip the whole-encoder CPU vs GPUME runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

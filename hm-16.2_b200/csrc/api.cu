@@ -40,6 +40,14 @@ int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...)
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// true when p is page-locked host memory known to CUDA (hmgpu_host_alloc or the caller's own cudaHostAlloc)
+static bool is_pinned(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int hmgpu_reserve_pinned(hmgpu_ctx* ctx, size_t bytes)
 {
   if (bytes <= ctx->h_pin_bytes) return HMGPU_OK;
@@ -121,6 +129,21 @@ const char* hmgpu_last_error(const hmgpu_ctx* ctx) { return ctx ? ctx->err : g_c
 uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void* hmgpu_stream(const hmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : NULL; }
+
+int hmgpu_host_alloc(hmgpu_ctx* ctx, size_t bytes, void** out)
+{
+  if (!ctx || !out) return HMGPU_E_INVALID;
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  HMGPU_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return HMGPU_OK;
+}
+
+int hmgpu_host_free(hmgpu_ctx* ctx, void* p)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  HMGPU_CUDA(ctx, cudaFreeHost(p));
+  return HMGPU_OK;
+}
 
 int hmgpu_synchronize(hmgpu_ctx* ctx)
 {
@@ -206,6 +229,11 @@ static int ref_alloc(hmgpu_ctx* ctx, int slot, bool chroma)
 // copy a strided host plane into pinned memory (tight), then to the device staging buffer
 static int stage_plane(hmgpu_ctx* ctx, const int16_t* src, int stride, int w, int h, size_t pin_off, size_t dev_off)
 {
+  if (stride == w && is_pinned(src))
+  {
+    HMGPU_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_stage + dev_off, src, sizeof(int16_t) * (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+    return HMGPU_OK;
+  }
   int16_t* pin = (int16_t*)((char*)ctx->h_pin + pin_off);
   for (int y = 0; y < h; y++) memcpy(pin + (size_t)y * w, src + (size_t)y * stride, sizeof(int16_t) * w);
   HMGPU_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_stage + dev_off, pin, sizeof(int16_t) * (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
@@ -413,15 +441,27 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   if ((rc = hmgpu_reserve_stage(ctx, jb + ob + rb))) return rc;
   char* hp = (char*)ctx->h_pin;
   char* dp = (char*)ctx->d_stage;
-  memcpy(hp, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
-  if (any_org) memcpy(hp + jb, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
-  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, jb + ob, cudaMemcpyHostToDevice, ctx->stream));
+  // page-locked caller buffers are copied directly; pageable ones go through the pinned staging buffer
+  const bool jobs_pinned = is_pinned(jobs), res_pinned = is_pinned(results);
+  if (jobs_pinned)
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+  else
+  {
+    memcpy(hp, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, jb, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (any_org)
+  {
+    memcpy(hp + jb, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(dp + jb, hp + jb, ob, cudaMemcpyHostToDevice, ctx->stream));
+  }
   rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n_jobs, any_org ? (const int16_t*)(dp + jb) : NULL,
                        (hmgpu_me_result*)(dp + jb + ob), any_org, any_full, any_tz, any_frac, max_win);
   if (rc) return rc;
-  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + jb + ob, dp + jb + ob, sizeof(hmgpu_me_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(res_pinned ? (void*)results : (void*)(hp + jb + ob), dp + jb + ob,
+                                  sizeof(hmgpu_me_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(results, hp + jb + ob, sizeof(hmgpu_me_result) * (size_t)n_jobs);
+  if (!res_pinned) memcpy(results, hp + jb + ob, sizeof(hmgpu_me_result) * (size_t)n_jobs);
   return HMGPU_OK;
 }
 

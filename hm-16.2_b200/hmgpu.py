@@ -38,7 +38,7 @@ assert ME_JOB.itemsize == 48 and ME_RESULT.itemsize == 24 and DIST_ITEM.itemsize
 
 EXPORTS = [
     "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
-    "hmgpu_stream", "hmgpu_synchronize", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
+    "hmgpu_stream", "hmgpu_synchronize", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_fwd_transform",
@@ -71,6 +71,8 @@ def lib():
     L.hmgpu_stream.argtypes = [vp]
     L.hmgpu_stream.restype = vp
     L.hmgpu_synchronize.argtypes = [vp]
+    L.hmgpu_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.hmgpu_host_free.argtypes = [vp, vp]
     L.hmgpu_struct_sizes.argtypes = [vp]
     L.hmgpu_struct_sizes.restype = None
     L.hmgpu_ref_upload.argtypes = [vp, ci, vp, ci, vp, vp, ci]
@@ -128,6 +130,9 @@ class Context:
 
     def close(self):
         if self.h:
+            for p in getattr(self, "_pinned", []):
+                self.L.hmgpu_host_free(self.h, p)
+            self._pinned = []
             self.L.hmgpu_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -165,6 +170,17 @@ class Context:
         self._check(self.L.hmgpu_microbench(self.h, which, C.byref(g)))
         return g.value
 
+    def host_array(self, shape, dtype):
+        """numpy array backed by page-locked memory (hmgpu_host_alloc); freed with the context"""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self.L.hmgpu_host_alloc(self.h, max(n, 1), C.byref(p)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def synchronize(self):
         self._check(self.L.hmgpu_synchronize(self.h))
 
@@ -197,9 +213,9 @@ class Context:
     def org_upload_device(self, d_ptr, stride):
         self._check(self.L.hmgpu_org_upload_device(self.h, d_ptr, stride))
 
-    def me_search(self, jobs, org_blocks=None):
+    def me_search(self, jobs, org_blocks=None, out=None):
         jobs = np.ascontiguousarray(jobs, ME_JOB)
-        res = np.zeros(len(jobs), ME_RESULT)
+        res = np.zeros(len(jobs), ME_RESULT) if out is None else out
         if org_blocks is not None:
             org_blocks = np.ascontiguousarray(org_blocks, np.int16)
         self._check(self.L.hmgpu_me_search(self.h, jobs.ctypes.data, len(jobs),

@@ -1,0 +1,54 @@
+"""Segment sharding: the only way this path scales across GPUs.
+
+An intra period that starts with an IDR (--DecodingRefreshType=2) is a closed segment: no
+reference crosses its boundary, so segments are independent encodes (`-fs start -f length`,
+TAppEncTop.cpp:369) and need no exchange step -- no collective, only a final concatenation of the
+Annex-B streams.  Segment k goes to rank k mod N; several segments (encoder processes) share one
+GPU because a single sequential encoder cannot fill it.
+"""
+import os
+import subprocess
+
+
+def plan_segments(n_frames, intra_period, n_ranks):
+    """-> list of dicts {segment, rank, frame_start, n_frames}; covers [0, n_frames) exactly once"""
+    assert intra_period > 0 and n_ranks > 0
+    segs = []
+    k = 0
+    for start in range(0, n_frames, intra_period):
+        segs.append({"segment": k, "rank": k % n_ranks, "frame_start": start,
+                     "n_frames": min(intra_period, n_frames - start)})
+        k += 1
+    return segs
+
+
+def segments_of_rank(plan, rank):
+    return [s for s in plan if s["rank"] == rank]
+
+
+def encoder_cmd(encoder, cfg, yuv, width, height, qp, seg, out_prefix, extra=()):
+    """command line of one segment encode (the reference's own options)"""
+    return [encoder, "-c", cfg, "-i", yuv, "-wdt", str(width), "-hgt", str(height), "-fr", "30",
+            "-fs", str(seg["frame_start"]), "-f", str(seg["n_frames"]), "-q", str(qp),
+            "-b", "%s_seg%03d.bin" % (out_prefix, seg["segment"]), "-o", "%s_seg%03d.yuv" % (out_prefix, seg["segment"])] + list(extra)
+
+
+def run_rank(encoder, cfg, yuv, width, height, qp, plan, rank, out_prefix, extra=(), device=None, max_parallel=4):
+    """encode this rank's segments, up to max_parallel encoder processes at a time on its GPU"""
+    env = dict(os.environ)
+    if device is not None:
+        env["HMGPU_DEVICE"] = str(device)
+    todo = segments_of_rank(plan, rank)
+    running, done = [], []
+    while todo or running:
+        while todo and len(running) < max_parallel:
+            seg = todo.pop(0)
+            p = subprocess.Popen(encoder_cmd(encoder, cfg, yuv, width, height, qp, seg, out_prefix, extra),
+                                 stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+            running.append((seg, p))
+        seg, p = running.pop(0)
+        _, err = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("segment %d failed: %s" % (seg["segment"], err.decode()[-500:]))
+        done.append(seg["segment"])
+    return done

@@ -55,6 +55,11 @@ uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx);
 /* the CUDA stream all work of this context is issued on (cudaStream_t as void*) */
 void* hmgpu_stream(const hmgpu_ctx* ctx);
 int  hmgpu_synchronize(hmgpu_ctx* ctx);
+/* Page-locked host memory.  Buffers passed to hmgpu_me_search / hmgpu_ref_upload / hmgpu_org_upload that
+ * come from here (or from the caller's own cudaHostAlloc) are copied directly, without the library's
+ * internal staging copy. */
+int  hmgpu_host_alloc(hmgpu_ctx* ctx, size_t bytes, void** out);
+int  hmgpu_host_free(hmgpu_ctx* ctx, void* p);
 /* sizeof of the four ABI structs: me_job, me_result, dist_item, mc_job (binding self-check) */
 void hmgpu_struct_sizes(int out[4]);
 

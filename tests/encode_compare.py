@@ -16,8 +16,8 @@ import sys
 import tempfile
 import time
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "hm-16.2_b200")
 sys.path.insert(0, HERE)
 import synth  # noqa: E402
 
@@ -52,6 +52,32 @@ def run(enc, cfg, yuv, w, h, frames, qp, out_prefix, extra, bit_depth=8, env=Non
             "recon_md5": md5(out_prefix + ".yuv"), "bytes": os.path.getsize(out_prefix + ".bin"), "gpume": stats}
 
 
+def available():
+    return all(os.path.exists(p) for p in (REF_ENC, GPU_ENC, CFG_DIR))
+
+
+def compare(cfg_name, size, frames, qp, gpume=1, extra=(), bit_depth=8, skip_cpu=False):
+    """encode the synthetic clip with CPU HM and with the GPUME encoder; -> dict with MD5s, times, fps"""
+    extra = list(extra)
+    w, h = [int(v) for v in size.split("x")]
+    cfg = os.path.join(CFG_DIR, "encoder_%s.cfg" % cfg_name)
+    tmp = tempfile.mkdtemp(prefix="hmenc_")
+    yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), w, h, frames, bit_depth)
+    out = {"cfg": cfg_name, "size": size, "frames": frames, "qp": qp, "extra": extra}
+    if not skip_cpu:
+        out["cpu"] = run(REF_ENC, cfg, yuv, w, h, frames, qp, os.path.join(tmp, "cpu"), extra, bit_depth)
+        out["cpu"]["fps"] = frames / out["cpu"]["wall_s"]
+    out["gpu"] = run(GPU_ENC, cfg, yuv, w, h, frames, qp, os.path.join(tmp, "gpu"), extra + ["--GPUME=%d" % gpume], bit_depth)
+    out["gpu"]["fps"] = frames / out["gpu"]["wall_s"]
+    if "cpu" in out:
+        out["bitstream_identical"] = out["cpu"]["bitstream_md5"] == out["gpu"]["bitstream_md5"]
+        out["recon_identical"] = out["cpu"]["recon_md5"] == out["gpu"]["recon_md5"]
+        out["speedup_wall"] = out["cpu"]["wall_s"] / out["gpu"]["wall_s"]
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="lowdelay_P_main")
@@ -63,18 +89,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("extra", nargs="*")
     a = ap.parse_args()
-    w, h = [int(v) for v in a.size.split("x")]
-    cfg = os.path.join(CFG_DIR, "encoder_%s.cfg" % a.cfg)
-    tmp = tempfile.mkdtemp(prefix="hmenc_")
-    yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), w, h, a.frames, a.bit_depth)
-    out = {"cfg": a.cfg, "size": a.size, "frames": a.frames, "qp": a.qp, "extra": a.extra}
-    if not a.skip_cpu:
-        out["cpu"] = run(REF_ENC, cfg, yuv, w, h, a.frames, a.qp, os.path.join(tmp, "cpu"), a.extra, a.bit_depth)
-    out["gpu"] = run(GPU_ENC, cfg, yuv, w, h, a.frames, a.qp, os.path.join(tmp, "gpu"), a.extra + ["--GPUME=%d" % a.gpume], a.bit_depth)
-    if "cpu" in out:
-        out["bitstream_identical"] = out["cpu"]["bitstream_md5"] == out["gpu"]["bitstream_md5"]
-        out["recon_identical"] = out["cpu"]["recon_md5"] == out["gpu"]["recon_md5"]
-        out["speedup_wall"] = out["cpu"]["wall_s"] / out["gpu"]["wall_s"]
+    out = compare(a.cfg, a.size, a.frames, a.qp, a.gpume, a.extra, a.bit_depth, a.skip_cpu)
     print(json.dumps(out, indent=1))
     if "cpu" in out and not (out["bitstream_identical"] and out["recon_identical"]):
         raise SystemExit(3)

@@ -10,7 +10,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SCRIPT = os.path.join(ROOT, "hm-16.2_b200", "encode_compare.py")
+SCRIPT = os.path.join(ROOT, "tests", "encode_compare.py")
 NEEDED = [os.path.join(ROOT, "oracle", "_ref", "TAppEncoderRef"),
           os.path.join(ROOT, "hm-16.2_b200", "host", "build", "TAppEncoderGpu"),
           os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_lowdelay_P_main.cfg")]
