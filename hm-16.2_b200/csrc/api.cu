@@ -83,6 +83,18 @@ int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes)
   return HMGPU_OK;
 }
 
+int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes)
+{
+  if (bytes <= ctx->d_tzlist_bytes) return HMGPU_OK;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_tzlist) cudaFree(ctx->d_tzlist);
+  ctx->d_tzlist = NULL; ctx->d_tzlist_bytes = 0;
+  bytes = round_up(bytes + bytes / 4, 1 << 20);
+  HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_tzlist, bytes));
+  ctx->d_tzlist_bytes = bytes;
+  return HMGPU_OK;
+}
+
 RefTable hmgpu_ref_table(const hmgpu_ctx* ctx)
 {
   RefTable t;
@@ -202,6 +214,7 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   if (ctx->d_org) cudaFree(ctx->d_org);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_work) cudaFree(ctx->d_work);
+  if (ctx->d_tzlist) cudaFree(ctx->d_tzlist);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   cudaStreamDestroy(ctx->stream);

@@ -50,6 +50,7 @@ struct hmgpu_ctx
   void* h_pin; size_t h_pin_bytes;     // pinned host
   void* d_stage; size_t d_stage_bytes; // device
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
+  void* d_tzlist; size_t d_tzlist_bytes; // device index lists of the TZ size classes (me_tz.cu)
   void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
   uint64_t launches;
   // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
@@ -88,6 +89,7 @@ int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...);
 int hmgpu_reserve_pinned(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_stage(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes);
+int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes);
 RefTable hmgpu_ref_table(const hmgpu_ctx* ctx);
 
 #define HMGPU_CUDA(ctx, call)                                                              \

@@ -1,14 +1,23 @@
-// me_tz_impl.cuh -- integer TZ search executed by one warp per job (device code shared by the
-// batch kernel in me_tz.cu and the fused low-latency kernel in me_single.cu).
+// me_tz_impl.cuh -- integer TZ search executed by a group of GS lanes per job (device code shared
+// by the batch kernels in me_tz.cu and the fused low-latency kernel in me_single.cu).
 //
 // Replaces TEncSearch::xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:298-314,
 // 4027-4228), xTZSearchHelp (:333-424), xTZ8PointDiamondSearch (:616-791), xTZ2PointSearch
-// (:429-557).  The state machine is warp-uniform; the points of one round (<= 16, or 32 per
-// chunk for the step-5 raster scan) are evaluated concurrently by lane groups.  Because the
-// reference updates its best with a strict '<' after every point in emission order, the
-// result of a round is the minimum cost of the round, earliest emission index among ties,
-// taken only if it is strictly below the running best -- which is what a (cost, lane) min
-// over lanes ordered by emission index yields.
+// (:429-557).
+//
+// The state machine is uniform inside a lane group; the points of one diamond round are
+// evaluated concurrently by sub-groups of lanes.  Because the reference updates its best with a
+// strict '<' after every point in emission order, the result of a round is the minimum cost of
+// the round, earliest emission index among ties, taken only if it is strictly below the running
+// best -- which is what a (cost, lane) min over lanes ordered by emission index yields.  Rounds
+// with more points than the group can hold are evaluated in consecutive passes, in order.
+//
+// GS = 32: one warp per job (large PUs: the lanes of a point split its rows).
+// GS = 8 : four jobs per warp (PUs up to 128 visited pixels): the ncu capture of round 1 showed the
+//          one-warp-per-job kernel issuing ~2500 warp instructions per job for ~30 useful
+//          VABSDIFF4 -- per-job control overhead, not arithmetic, bounds small PUs, so four
+//          independent searches share each instruction stream.  All warp primitives take the
+//          group's member mask; groups of one warp may diverge freely.
 //
 // SAD arithmetic: 8-bit pictures use packed bytes and VABSDIFF4.U8.ACC against the PU block
 // staged in shared memory; >8-bit pictures and explicit int16 key patterns (bi-pred
@@ -17,7 +26,6 @@
 #include "hmgpu_internal.cuh"
 
 #define TZ_WARPS 4
-#define FULL_MASK 0xffffffffu
 
 struct TzJob
 {
@@ -36,12 +44,25 @@ struct TzBest
   uint32_t n_cand;
 };
 
+template <int GS> struct TzGroup
+{
+  // lane index inside the group, member mask of the group, first lane of the group
+  __device__ __forceinline__ static int lane() { return threadIdx.x & (GS - 1); }
+  __device__ __forceinline__ static int base() { return (threadIdx.x & 31) & ~(GS - 1); }
+  __device__ __forceinline__ static uint32_t mask() { return GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << base()); }
+};
+
 // ---- per-lane partial SAD over rows r0, r0+rstep, ... (indices of visited rows) -------------
 
 // packed 8-bit path. org_s: pu_h rows of pu_w bytes (row pitch wq words); ref = plane pointer at
 // the PU origin displaced by the candidate.
+// raw_bound: the smallest raw sum at which this point can no longer beat the running best (the
+// reference's compare is a strict '<', TEncSearch.cpp:414): a lane stops as soon as its own partial
+// sum reaches it -- the point then loses whatever the remaining rows add, so the truncated value is
+// never selected and the result stays exact.  The far rings of the star refinement end after a
+// row or two this way.
 __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitch, const uint32_t* org_s,
-                                                    int wq, int rows, int row_mul, int r0, int rstep)
+                                                    int wq, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
 {
   uint32_t acc = 0;
   const uintptr_t a0 = (uintptr_t)ref;
@@ -59,6 +80,7 @@ __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitc
       acc = vabsdiff4_acc(__funnelshift_r(lo, hi, sh), o[k], acc);
       lo = hi;
     }
+    if (acc >= raw_bound) break;
   }
   return acc;
 }
@@ -66,7 +88,7 @@ __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitc
 // generic path: org int16 in shared memory (row pitch pu_w), ref elements of type Px
 template <typename Px>
 __device__ __forceinline__ uint32_t sad_rows_generic(const Px* ref, int pitch, const int16_t* org_s,
-                                                     int w, int rows, int row_mul, int r0, int rstep)
+                                                     int w, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
 {
   uint32_t acc = 0;
   for (int r = r0; r < rows; r += rstep)
@@ -74,41 +96,49 @@ __device__ __forceinline__ uint32_t sad_rows_generic(const Px* ref, int pitch, c
     const Px* p = ref + (size_t)(r * row_mul) * pitch;
     const int16_t* o = org_s + (r * row_mul) * w;
     for (int k = 0; k < w; k++) acc += (uint32_t)hm_abs((int)o[k] - (int)__ldg(p + k));
+    if (acc >= raw_bound) break;
   }
   return acc;
 }
 
-// Evaluate up to 32 points at once. Lane group g = lane / lanes_per_point owns point g.
-// (x, y, valid, pnr, dist) are the data of THIS lane's point. Updates `best` warp-uniformly.
-template <typename Px, bool PACKED>
+// Evaluate up to GS / lanes_per_point points at once.  Sub-group lane / lanes_per_point owns one
+// point; (x, y, valid, pnr, dist) are the data of THIS lane's point.  Updates `best` uniformly
+// across the group.
+template <typename Px, bool PACKED, int GS>
 __device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
                                         int lanes_per_point, int x, int y, bool valid, int pnr, int dist,
                                         TzBest& best)
 {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane & (lanes_per_point - 1);
+  const uint32_t gm = TzGroup<GS>::mask();
+  const int sub = TzGroup<GS>::lane() & (lanes_per_point - 1);
   uint32_t part = 0;
-  if (valid)
+  const uint32_t mvc = hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, x, y);
+  if (valid && mvc < best.cost)
   {
+    // smallest raw sum whose normalised value (sum << sub_shift) >> (bitDepth-8) reaches best.cost - mvc
+    const uint32_t need = best.cost - mvc;
+    const int shift = J.bit_depth - 8;
+    const uint64_t nb = (((uint64_t)need << shift) + ((1u << J.sub_shift) - 1u)) >> J.sub_shift;
+    const uint32_t raw_bound = nb > 0xffffffffull ? 0xffffffffu : (uint32_t)nb;
     const Px* ref = ref00 + (ptrdiff_t)y * pitch + x;
     if (PACKED)
-      part = sad_rows_packed((const uint8_t*)ref, pitch, (const uint32_t*)org_s, J.pu_w >> 2, J.rows, 1 << J.sub_shift, sub, lanes_per_point);
+      part = sad_rows_packed((const uint8_t*)ref, pitch, (const uint32_t*)org_s, J.pu_w >> 2, J.rows, 1 << J.sub_shift, sub, lanes_per_point, raw_bound);
     else
-      part = sad_rows_generic<Px>(ref, pitch, (const int16_t*)org_s, J.pu_w, J.rows, 1 << J.sub_shift, sub, lanes_per_point);
+      part = sad_rows_generic<Px>(ref, pitch, (const int16_t*)org_s, J.pu_w, J.rows, 1 << J.sub_shift, sub, lanes_per_point, raw_bound);
   }
-  for (int o = lanes_per_point >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(FULL_MASK, part, o);
+  for (int o = lanes_per_point >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(gm, part, o);
   uint32_t cost = 0xffffffffu;
-  if (valid) cost = hm_sad_norm(part, J.sub_shift, J.bit_depth) + hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, x, y);
-  best.n_cand += __popc(__ballot_sync(FULL_MASK, valid && sub == 0));
-  const uint32_t m = __reduce_min_sync(FULL_MASK, cost);
+  if (valid) cost = mvc < best.cost ? hm_sad_norm(part, J.sub_shift, J.bit_depth) + mvc : 0xffffffffu;
+  best.n_cand += __popc(__ballot_sync(gm, valid && sub == 0));
+  const uint32_t m = __reduce_min_sync(gm, cost);
   if (m < best.cost)                                   // strict '<' (TEncSearch.cpp:414)
   {
-    const int src = __ffs(__ballot_sync(FULL_MASK, valid && cost == m)) - 1;
+    const int src = __ffs(__ballot_sync(gm, valid && cost == m)) - 1;   // absolute lane of the earliest minimum
     best.cost = m;
-    best.x = __shfl_sync(FULL_MASK, x, src);
-    best.y = __shfl_sync(FULL_MASK, y, src);
-    best.dist = __shfl_sync(FULL_MASK, dist, src);
-    best.pnr = __shfl_sync(FULL_MASK, pnr, src);
+    best.x = __shfl_sync(gm, x, src);
+    best.y = __shfl_sync(gm, y, src);
+    best.dist = __shfl_sync(gm, dist, src);
+    best.pnr = __shfl_sync(gm, pnr, src);
     best.round = 0;
   }
 }
@@ -124,20 +154,11 @@ __device__ __forceinline__ bool tz_in_window(const TzJob& J, int cx, int cy, int
   return true;
 }
 
-// xTZ8PointDiamondSearch (TEncSearch.cpp:616-791): point i of the round in emission order
-template <typename Px, bool PACKED>
-__device__ __forceinline__ void tz_diamond(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
-                                           int cx, int cy, int d, TzBest& best)
+// Point i (emission order) of the diamond at distance d around (cx, cy): xTZ8PointDiamondSearch
+// (TEncSearch.cpp:616-791)
+__device__ __forceinline__ void tz_diamond_point(int cx, int cy, int d, int i, int& x, int& y, int& pnr, int& dist)
 {
-  const int lane = threadIdx.x & 31;
-  best.round += 1;
-  int n, lpp;
-  if (d == 1) { n = 4; lpp = 8; } else if (d <= 8) { n = 8; lpp = 4; } else { n = 16; lpp = 2; }
-  lpp = min(lpp, J.rows);                               // never more lanes than rows (rows is a power of two or 6/12/24... )
-  // lanes-per-point must be a power of two: round down
-  lpp = 1 << (31 - __clz(lpp));
-  const int i = lane / lpp;
-  int x = cx, y = cy, pnr = 0, dist = d;
+  x = cx; y = cy; pnr = 0; dist = d;
   if (d == 1)
   {
     // (cx,top,2) (left,cy,4) (right,cy,5) (cx,bottom,7)
@@ -159,22 +180,42 @@ __device__ __forceinline__ void tz_diamond(const TzJob& J, const Px* ref00, int 
       default: y = cy + d; pnr = 7; break;
     }
   }
+  else if (i < 4)
+  {
+    if (i == 0) y = cy - d; else if (i == 1) x = cx - d; else if (i == 2) x = cx + d; else y = cy + d;
+  }
   else
   {
-    if (i < 4)
-    {
-      if (i == 0) y = cy - d; else if (i == 1) x = cx - d; else if (i == 2) x = cx + d; else y = cy + d;
-    }
-    else
-    {
-      const int idx = ((i - 4) >> 2) + 1, k = (i - 4) & 3;   // k: 0 (xl,yt) 1 (xr,yt) 2 (xl,yb) 3 (xr,yb)
-      const int q = (d >> 2) * idx;
-      x = (k & 1) ? cx + q : cx - q;
-      y = (k & 2) ? cy + d - q : cy - d + q;
-    }
+    const int idx = ((i - 4) >> 2) + 1, k = (i - 4) & 3;   // k: 0 (xl,yt) 1 (xr,yt) 2 (xl,yb) 3 (xr,yb)
+    const int q = (d >> 2) * idx;
+    x = (k & 1) ? cx + q : cx - q;
+    y = (k & 2) ? cy + d - q : cy - d + q;
   }
-  const bool valid = (i < n) && tz_in_window(J, cx, cy, x, y);
-  tz_eval<Px, PACKED>(J, ref00, pitch, org_s, lpp, x, y, valid, pnr, dist, best);
+}
+
+// largest power of two <= v (v >= 1)
+__device__ __forceinline__ int pow2_floor(int v) { return 1 << (31 - __clz(v)); }
+
+// xTZ8PointDiamondSearch (TEncSearch.cpp:616-791): all points of the round, in emission order
+template <typename Px, bool PACKED, int GS>
+__device__ __forceinline__ void tz_diamond(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
+                                           int cx, int cy, int d, TzBest& best)
+{
+  const int gl = TzGroup<GS>::lane();
+  best.round += 1;
+  const int n = d == 1 ? 4 : (d <= 8 ? 8 : 16);
+  // lanes per point: as many as the group allows for n points, never more than the visited rows
+  const int per_pass = min(n, GS);                       // points evaluated concurrently
+  const int lpp = pow2_floor(min(GS / per_pass, J.rows));
+  const int slot = gl / lpp;
+  for (int i0 = 0; i0 < n; i0 += per_pass)
+  {
+    const int i = i0 + slot;
+    int x, y, pnr, dist;
+    tz_diamond_point(cx, cy, d, i, x, y, pnr, dist);
+    const bool valid = (slot < per_pass) && (i < n) && tz_in_window(J, cx, cy, x, y);
+    tz_eval<Px, PACKED, GS>(J, ref00, pitch, org_s, lpp, x, y, valid, pnr, dist, best);
+  }
 }
 
 // xTZ2PointSearch (TEncSearch.cpp:429-557): offsets (dx0,dy0,dx1,dy1) of the two untested
@@ -185,31 +226,31 @@ static __constant__ int8_t c_two_point[9][4] = {
   { -1, 1, -1, -1 }, { 1, -1, 1, 1 },
   { -1, 0, 0, 1 }, { -1, 1, 1, 1 }, { 1, 0, 0, 1 } };
 
-template <typename Px, bool PACKED>
+template <typename Px, bool PACKED, int GS>
 __device__ __forceinline__ void tz_two_point(const TzJob& J, const Px* ref00, int pitch, const void* org_s, TzBest& best)
 {
-  const int lane = threadIdx.x & 31;
   const int nr = best.pnr;
   if (nr < 1 || nr > 8) return;
-  int lpp = min(16, J.rows);
-  lpp = 1 << (31 - __clz(lpp));
-  const int i = lane / lpp;
+  const int lpp = pow2_floor(min(GS / 2, J.rows));
+  const int i = TzGroup<GS>::lane() / lpp;
   const int cx = best.x, cy = best.y;
   const int x = cx + c_two_point[nr][i == 0 ? 0 : 2];
   const int y = cy + c_two_point[nr][i == 0 ? 1 : 3];
   const bool valid = (i < 2) && tz_in_window(J, cx, cy, x, y);
-  tz_eval<Px, PACKED>(J, ref00, pitch, org_s, lpp, x, y, valid, 0, 2, best);
+  tz_eval<Px, PACKED, GS>(J, ref00, pitch, org_s, lpp, x, y, valid, 0, 2, best);
 }
 
-// The whole TZ search of one job, executed by ONE WARP (all 32 lanes call it together).
-// s_org: per-warp shared memory for the PU block, 4 KB (PACKED) or 8 KB (int16).
-// Lane 0 returns the result in `out` (integer MV, SAD without MV cost, candidate count).
-template <typename Px, bool PACKED>
-__device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
-                                               const RefTable& refs, const OrgView& org, unsigned char* s_org,
-                                               hmgpu_me_result& out)
+// The whole TZ search of one job, executed by ONE GROUP of GS lanes (all of them call it together).
+// s_org: per-group shared memory for the PU block: pu_w*pu_h bytes (PACKED) or 2*pu_w*pu_h (int16).
+// The first lane of the group returns the result in `out` (integer MV, SAD without MV cost,
+// candidate count).
+template <typename Px, bool PACKED, int GS>
+__device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
+                                                const RefTable& refs, const OrgView& org, unsigned char* s_org,
+                                                hmgpu_me_result& out)
 {
-  const int lane = threadIdx.x & 31;
+  const int gl = TzGroup<GS>::lane();
+  const uint32_t gm = TzGroup<GS>::mask();
 
   TzJob J;
   J.pu_w = jb.pu_w; J.pu_h = jb.pu_h;
@@ -228,7 +269,7 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
     const int wq = J.pu_w >> 2;
     const uint8_t* o = (const uint8_t*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
     uint32_t* so = (uint32_t*)s_org;
-    for (int i = lane; i < J.pu_h * wq; i += 32)
+    for (int i = gl; i < J.pu_h * wq; i += GS)
     {
       const int r = i / wq, k = i - r * wq;
       so[i] = __ldg((const uint32_t*)(o + (size_t)r * org.pitch) + k);   // pu_x % 4 == 0, pitch % 4 == 0
@@ -240,29 +281,28 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
     if (jb.flags & HMGPU_F_ORG_BLOCK)
     {
       const int16_t* o = org_blocks + jb.org_offset;
-      for (int i = lane; i < J.pu_h * J.pu_w; i += 32) so[i] = o[i];
+      for (int i = gl; i < J.pu_h * J.pu_w; i += GS) so[i] = o[i];
     }
     else
     {
       const Px* o = (const Px*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
-      for (int i = lane; i < J.pu_h * J.pu_w; i += 32)
+      for (int i = gl; i < J.pu_h * J.pu_w; i += GS)
       {
         const int r = i / J.pu_w, k = i - r * J.pu_w;
         so[i] = (int16_t)o[(size_t)r * org.pitch + k];
       }
     }
   }
-  __syncwarp();
+  __syncwarp(gm);
 
   TzBest best; best.cost = 0xffffffffu; best.x = 0; best.y = 0; best.dist = 0; best.round = 0; best.pnr = 0; best.n_cand = 0;
 
   // ---- start points (TEncSearch.cpp:4045-4093): clipped MVP>>2, zero, clipped 2Nx2N integer MV.
-  // Evaluated sequentially in the reference; concurrently here with emission order = group index.
+  // Evaluated sequentially in the reference; concurrently here with emission order = sub-group index.
   const bool has2n = (jb.flags & HMGPU_F_HAS_2NX2N) != 0;
   {
-    int lpp = min(8, J.rows);
-    lpp = 1 << (31 - __clz(lpp));
-    const int i = lane / lpp;
+    const int lpp = pow2_floor(min(GS / 4, J.rows));
+    const int i = gl / lpp;
     int x = 0, y = 0;
     if (i == 0)
     {
@@ -275,7 +315,7 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
       y = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(jb.i2n_y << 2))) >> 2;
     }
     const bool valid = i < (has2n ? 3 : 2);
-    tz_eval<Px, PACKED>(J, ref00, pitch, s_org, lpp, x, y, valid, 0, 0, best);
+    tz_eval<Px, PACKED, GS>(J, ref00, pitch, s_org, lpp, x, y, valid, 0, 0, best);
   }
   // raster window: re-centred on the best start point when the 2Nx2N MV was tested (:4083-4092)
   int rL = J.L, rT = J.T, rR = J.R, rB = J.B;
@@ -294,24 +334,24 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
   int cx = best.x, cy = best.y;
   for (int d = 1; d <= jb.search_range; d <<= 1)
   {
-    tz_diamond<Px, PACKED>(J, ref00, pitch, s_org, cx, cy, d, best);
+    tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, d, best);
     if (best.round >= 3) break;
   }
   if (best.dist == 1)                                   // :4137-4141
   {
     best.dist = 0;
-    tz_two_point<Px, PACKED>(J, ref00, pitch, s_org, best);
+    tz_two_point<Px, PACKED, GS>(J, ref00, pitch, s_org, best);
   }
   if (best.dist > 5)                                    // raster, step 5 (:4144-4154)
   {
     best.dist = 5;
     const int nx = (rR - rL) / 5 + 1, ny = (rB - rT) / 5 + 1;
     const int total = (rR >= rL && rB >= rT) ? nx * ny : 0;
-    for (int base = 0; base < total; base += 32)
+    for (int base = 0; base < total; base += GS)
     {
-      const int i = base + lane;
+      const int i = base + gl;
       const int gy = i / nx, gx = i - gy * nx;
-      tz_eval<Px, PACKED>(J, ref00, pitch, s_org, 1, rL + gx * 5, rT + gy * 5, i < total, 0, 5, best);
+      tz_eval<Px, PACKED, GS>(J, ref00, pitch, s_org, 1, rL + gx * 5, rT + gy * 5, i < total, 0, 5, best);
     }
   }
   while (best.dist > 0)                                 // star refinement (:4189-4223)
@@ -319,15 +359,15 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
     cx = best.x; cy = best.y;
     best.dist = 0; best.pnr = 0;
     for (int d = 1; d < jb.search_range + 1; d <<= 1)
-      tz_diamond<Px, PACKED>(J, ref00, pitch, s_org, cx, cy, d, best);
+      tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, d, best);
     if (best.dist == 1)
     {
       best.dist = 0;
-      if (best.pnr != 0) tz_two_point<Px, PACKED>(J, ref00, pitch, s_org, best);
+      if (best.pnr != 0) tz_two_point<Px, PACKED, GS>(J, ref00, pitch, s_org, best);
     }
   }
 
-  if (lane == 0)
+  if (gl == 0)
   {
     out.int_x = (int16_t)best.x; out.int_y = (int16_t)best.y;
     out.int_sad = best.cost - hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, best.x, best.y);
@@ -335,4 +375,13 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
     out.frac_cost = 0;
     out.n_cand = best.n_cand;
   }
+}
+
+// one warp per job (kept for the fused low-latency kernel)
+template <typename Px, bool PACKED>
+__device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
+                                               const RefTable& refs, const OrgView& org, unsigned char* s_org,
+                                               hmgpu_me_result& out)
+{
+  tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org, out);
 }
