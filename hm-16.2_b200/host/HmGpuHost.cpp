@@ -31,7 +31,7 @@ HmGpuHost& HmGpuHost::instance()
 
 HmGpuHost::HmGpuHost()
 : m_ctx( NULL ), m_picW( 0 ), m_picH( 0 ), m_tick( 0 ), m_orgPic( NULL ), m_orgPoc( -1 ), m_keyBlock( NULL )
-, m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
+, m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_totalSeconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
 {
   for ( Int i = 0; i < NUM_SLOTS; i++ )
   {
@@ -44,9 +44,9 @@ HmGpuHost::~HmGpuHost()
   if ( m_ctx )
   {
     fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
-                     "%.3f s one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
+                     "%.3f s in motionSearch overall, %.3f s one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
              (unsigned long long)m_calls, (unsigned long long)m_cands, m_seconds, m_calls ? m_seconds / (Double)m_calls * 1e6 : 0.0,
-             m_seconds > 0 ? (Double)m_cands / m_seconds / 1e6 : 0.0, m_initSeconds,
+             m_seconds > 0 ? (Double)m_cands / m_seconds / 1e6 : 0.0, m_totalSeconds, m_initSeconds,
              (unsigned long long)m_uploads, m_uploadSeconds,
              (unsigned long long)hmgpu_launch_count( m_ctx ), (unsigned long long)m_checked );
     hmgpu_destroy( m_ctx );
@@ -121,6 +121,7 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
                               Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
                               Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut )
 {
+  const Double tEnter = xNow();
   xInit( pcCU );
   xUploadOrg( pcCU );
 
@@ -184,7 +185,9 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
   rcOut.cost   = r.frac_cost;
   m_calls++;
   m_cands   += r.n_cand;
-  m_seconds += xNow() - t0;
+  const Double tExit = xNow();
+  m_seconds += tExit - t0;
+  m_totalSeconds += tExit - tEnter;
 }
 
 Void HmGpuHost::checkInteger( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu )

@@ -62,6 +62,7 @@ private:
   // statistics
   UInt64      m_calls, m_cands, m_checked;
   Double      m_seconds;        ///< inside hmgpu_me_search
+  Double      m_totalSeconds;   ///< inside motionSearch (set-up, uploads, job marshalling included)
   Double      m_initSeconds;    ///< CUDA context + library set-up (once)
   Double      m_uploadSeconds;  ///< reference / source picture uploads
   UInt64      m_uploads;
