@@ -95,6 +95,24 @@ int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes)
   return HMGPU_OK;
 }
 
+void hmgpu_use_lane(hmgpu_ctx* ctx, int lane)
+{
+  if (lane == ctx->cur_lane) return;
+  HmgpuLane& cur = ctx->lane_store[ctx->cur_lane];
+  cur.stream = ctx->stream;
+  cur.h_pin = ctx->h_pin; cur.h_pin_bytes = ctx->h_pin_bytes;
+  cur.d_stage = ctx->d_stage; cur.d_stage_bytes = ctx->d_stage_bytes;
+  cur.d_work = ctx->d_work; cur.d_work_bytes = ctx->d_work_bytes;
+  cur.d_tzlist = ctx->d_tzlist; cur.d_tzlist_bytes = ctx->d_tzlist_bytes;
+  const HmgpuLane& nx = ctx->lane_store[lane];
+  ctx->stream = nx.stream;
+  ctx->h_pin = nx.h_pin; ctx->h_pin_bytes = nx.h_pin_bytes;
+  ctx->d_stage = nx.d_stage; ctx->d_stage_bytes = nx.d_stage_bytes;
+  ctx->d_work = nx.d_work; ctx->d_work_bytes = nx.d_work_bytes;
+  ctx->d_tzlist = nx.d_tzlist; ctx->d_tzlist_bytes = nx.d_tzlist_bytes;
+  ctx->cur_lane = lane;
+}
+
 RefTable hmgpu_ref_table(const hmgpu_ctx* ctx)
 {
   RefTable t;
@@ -204,7 +222,20 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  hmgpu_use_lane(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
+  {
+    HmgpuLane& l1 = ctx->lane_store[1];
+    if (l1.stream) cudaStreamSynchronize(l1.stream);
+    if (l1.d_stage) cudaFree(l1.d_stage);
+    if (l1.d_work) cudaFree(l1.d_work);
+    if (l1.d_tzlist) cudaFree(l1.d_tzlist);
+    if (l1.h_pin) cudaFreeHost(l1.h_pin);
+    if (l1.stream) cudaStreamDestroy(l1.stream);
+    for (int i = 0; i < 2; i++) if (ctx->lane_done[i]) cudaEventDestroy(ctx->lane_done[i]);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->d_orgblk) cudaFree(ctx->d_orgblk);
+  }
   for (int i = 0; i < HMGPU_MAX_REFS; i++)
   {
     if (ctx->refs[i].planes) cudaFree(ctx->refs[i].planes);
@@ -344,11 +375,12 @@ int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride)
 // ---- motion search --------------------------------------------------------------------------
 
 static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_org_elems,
-                         bool* any_org, bool* any_full, bool* any_tz, bool* any_frac, int* max_win_bytes)
+                         bool* any_org, bool* any_full, bool* any_tz, bool* any_frac, int* max_win_bytes, int first = 0)
 {
   *any_org = *any_full = *any_tz = *any_frac = false;
   *max_win_bytes = 0;
-  for (int i = 0; i < n; i++)
+  jobs -= first;                                           // messages carry the index in the caller's array
+  for (int i = first; i < first + n; i++)
   {
     const hmgpu_me_job& j = jobs[i];
     if (j.pu_w < 4 || j.pu_w > 64 || j.pu_h < 4 || j.pu_h > 64 || (j.pu_w & 3) || (j.pu_h & 3))
@@ -401,6 +433,101 @@ static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_
   return HMGPU_OK;
 }
 
+// Large batches: chunks alternate between the two lanes, so the H2D copy (and the host-side validation)
+// of chunk k+1 and the D2H copy of chunk k-1 overlap the search kernels of chunk k.
+#define PIPE_MIN_JOBS 65536
+static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
+                               const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
+{
+  static const int s_chunk = getenv("HMGPU_PIPE_CHUNK") ? atoi(getenv("HMGPU_PIPE_CHUNK")) : 0;
+  int chunk = s_chunk > 0 ? s_chunk : (n_jobs + 7) / 8;
+  if (s_chunk <= 0) chunk = chunk < 32768 ? 32768 : (chunk > 262144 ? 262144 : chunk);
+  chunk = (chunk + 255) & ~255;
+  const int n_chunks = (n_jobs + chunk - 1) / chunk;
+  if (!ctx->lane_store[1].stream)
+  {
+    HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_store[1].stream, cudaStreamNonBlocking));
+    HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[0], cudaEventDisableTiming));
+    HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[1], cudaEventDisableTiming));
+    HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  }
+  // bi-pred key patterns: the whole array goes up once, on lane 0, before the lanes fork
+  const bool have_org = org_blocks && n_org_elems > 0;
+  if (have_org)
+  {
+    const size_t ob = sizeof(int16_t) * (size_t)n_org_elems;
+    if (ob > ctx->d_orgblk_bytes)
+    {
+      HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_orgblk) cudaFree(ctx->d_orgblk);
+      ctx->d_orgblk = NULL; ctx->d_orgblk_bytes = 0;
+      HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_orgblk, round_up(ob + ob / 4, 1 << 20)));
+      ctx->d_orgblk_bytes = round_up(ob + ob / 4, 1 << 20);
+    }
+    if (is_pinned(org_blocks))
+      HMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_orgblk, org_blocks, ob, cudaMemcpyHostToDevice, ctx->stream));
+    else
+    {
+      HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      int rc0 = hmgpu_reserve_pinned(ctx, ob);
+      if (rc0) return rc0;
+      memcpy(ctx->h_pin, org_blocks, ob);
+      HMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_orgblk, ctx->h_pin, ob, cudaMemcpyHostToDevice, ctx->stream));
+      HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_pin is reused for the job chunks below
+    }
+  }
+  HMGPU_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_store[1].stream, ctx->fork_ev, 0));
+
+  const bool jobs_pinned = is_pinned(jobs), res_pinned = is_pinned(results);
+  const size_t jb = round_up(sizeof(hmgpu_me_job) * (size_t)chunk, 256), rb = round_up(sizeof(hmgpu_me_result) * (size_t)chunk, 256);
+  int rc = HMGPU_OK;
+  // copy the results of chunk k out of its lane's pinned staging buffer (pageable `results` only)
+  auto retire = [&](int k) -> int {
+    hmgpu_use_lane(ctx, k & 1);
+    const cudaError_t e = cudaEventSynchronize(ctx->lane_done[k & 1]);
+    if (e != cudaSuccess) return hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search, chunk %d: %s", k, cudaGetErrorString(e));
+    const int first = k * chunk, n = (n_jobs - first < chunk) ? n_jobs - first : chunk;
+    if (!res_pinned) memcpy(results + first, (char*)ctx->h_pin + jb, sizeof(hmgpu_me_result) * (size_t)n);
+    return HMGPU_OK;
+  };
+  int retired = 0;
+  for (int k = 0; k < n_chunks && rc == HMGPU_OK; k++)
+  {
+    const int first = k * chunk, n = (n_jobs - first < chunk) ? n_jobs - first : chunk;
+    if (k >= 2) { if ((rc = retire(k - 2))) break; retired = k - 1; }
+    hmgpu_use_lane(ctx, k & 1);
+    bool any_org, any_full, any_tz, any_frac;
+    int max_win;
+    if ((rc = validate_jobs(ctx, jobs + first, n, have_org ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, first))) break;
+    if ((rc = hmgpu_reserve_stage(ctx, jb + rb))) break;
+    if (!(jobs_pinned && res_pinned) && (rc = hmgpu_reserve_pinned(ctx, jb + rb))) break;
+    char* dp = (char*)ctx->d_stage;
+    char* hp = (char*)ctx->h_pin;
+    cudaError_t e;
+    if (jobs_pinned) e = cudaMemcpyAsync(dp, jobs + first, sizeof(hmgpu_me_job) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    else
+    {
+      memcpy(hp, jobs + first, sizeof(hmgpu_me_job) * (size_t)n);
+      e = cudaMemcpyAsync(dp, hp, sizeof(hmgpu_me_job) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search H2D: %s", cudaGetErrorString(e)); break; }
+    if ((rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n, any_org ? (const int16_t*)ctx->d_orgblk : NULL,
+                              (hmgpu_me_result*)(dp + jb), any_org, any_full, any_tz, any_frac, max_win))) break;
+    e = cudaMemcpyAsync(res_pinned ? (void*)(results + first) : (void*)(hp + jb), dp + jb, sizeof(hmgpu_me_result) * (size_t)n,
+                        cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->lane_done[k & 1], ctx->stream);
+    if (e != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search D2H: %s", cudaGetErrorString(e)); break; }
+  }
+  if (rc == HMGPU_OK)
+    for (int k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks && rc == HMGPU_OK; k++)
+      if (k >= retired) rc = retire(k);
+  // leave both lanes idle and lane 0 current, whatever happened
+  hmgpu_use_lane(ctx, 1); cudaStreamSynchronize(ctx->stream);
+  hmgpu_use_lane(ctx, 0); cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                     const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
 {
@@ -408,6 +535,7 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || !results || n_jobs < 0 || n_jobs > (1 << 26)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n_jobs >= PIPE_MIN_JOBS && !getenv("HMGPU_NO_PIPELINE")) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
   bool any_org, any_full, any_tz, any_frac;
   int max_win;
   int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win);

@@ -36,6 +36,19 @@ struct RefSlot
   void* cr;
 };
 
+// A pipeline lane: its own stream and its own staging / scratch buffers.  Lane 0 is the context's
+// ordinary stream; lane 1 exists so that large hmgpu_me_search batches can copy chunk k+1 in and
+// chunk k-1 out while chunk k is being searched.  The launchers always use the CURRENT view
+// (ctx->stream, ctx->d_work, ...); hmgpu_use_lane() swaps a lane into that view.
+struct HmgpuLane
+{
+  cudaStream_t stream;
+  void* h_pin; size_t h_pin_bytes;
+  void* d_stage; size_t d_stage_bytes;
+  void* d_work; size_t d_work_bytes;
+  void* d_tzlist; size_t d_tzlist_bytes;
+};
+
 struct hmgpu_ctx
 {
   int device, pic_w, pic_h, bit_depth, max_refs;
@@ -51,6 +64,9 @@ struct hmgpu_ctx
   void* d_stage; size_t d_stage_bytes; // device
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
   void* d_tzlist; size_t d_tzlist_bytes; // device index lists of the TZ size classes (me_tz.cu)
+  HmgpuLane lane_store[2]; int cur_lane; // parked lanes (the current one lives in the fields above)
+  cudaEvent_t lane_done[2], fork_ev;
+  void* d_orgblk; size_t d_orgblk_bytes; // bi-pred key patterns of a pipelined batch
   void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
   uint64_t launches;
   // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
@@ -91,6 +107,7 @@ int hmgpu_reserve_stage(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes);
 RefTable hmgpu_ref_table(const hmgpu_ctx* ctx);
+void hmgpu_use_lane(hmgpu_ctx* ctx, int lane);
 
 #define HMGPU_CUDA(ctx, call)                                                              \
   do {                                                                                     \

@@ -147,7 +147,8 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // TS = 8: rows 8, 3 words per staged row segment; TS = 4: rows 4, 2 words
 template <int TS>
@@ -158,8 +159,8 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 {
   constexpr int NW = TS / 4 + 1;                         // staged words per row segment
   constexpr int OW = TS / 4;                             // source-picture words per row (aligned)
-  __shared__ uint32_t s_ref[TS][F2_THREADS * NW];        // [row][tile * NW + word]
-  __shared__ const uint32_t* s_base[F2_THREADS];         // aligned address of row 0 of each tile for the current candidate
+  __shared__ uint32_t s_ref[2][TS][F2_THREADS * NW];     // double buffer of [row][tile * NW + word]
+  __shared__ const uint32_t* s_base[2][F2_THREADS];      // aligned address of row 0 of each tile for the candidate of each buffer
 
   const int tid = threadIdx.x;
   const uint32_t n_work = *work_count;
@@ -197,24 +198,31 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
         for (int w = 0; w < OW; w++) ow[r][w] = __ldg(o + (size_t)r * org_pitch_w + w);
     }
 
-    for (int cand = 0; cand < 9; cand++)
-    {
+    // candidate c+1 is fetched (cp.async into the other buffer) while candidate c is being transformed
+    auto issue = [&](int cand, int buf) -> int {
       const int qx = qx0 + (phase ? c_refine_q[cand][0] : 2 * c_refine_h[cand][0]);
       const int qy = qy0 + (phase ? c_refine_q[cand][1] : 2 * c_refine_h[cand][1]);
       const uint8_t* p = plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * refs.plane_elems
                        + (ptrdiff_t)(pu_y + (qy >> 2)) * pitch + (pu_x + (qx >> 2));
-      const int sh = (int)((uintptr_t)p & 3) * 8;
-      __syncthreads();                                    // previous candidate's s_ref / s_base fully consumed
-      s_base[tid] = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
-      __syncthreads();
+      s_base[buf][tid] = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+      __syncthreads();                                    // s_base visible; every thread is done with s_ref[buf]
 #pragma unroll
       for (int k = 0; k < NW; k++)
       {
-        const uint32_t* src = s_base[ld_tile[k]] + ld_word[k];
+        const uint32_t* src = s_base[buf][ld_tile[k]] + ld_word[k];
 #pragma unroll
-        for (int r = 0; r < TS; r++) cp_async4(&s_ref[r][tid + k * F2_THREADS], src + (size_t)r * pitch_w);
+        for (int r = 0; r < TS; r++) cp_async4(&s_ref[buf][r][tid + k * F2_THREADS], src + (size_t)r * pitch_w);
       }
-      cp_async_wait_all();
+      cp_async_commit();
+      return (int)((uintptr_t)p & 3) * 8;
+    };
+    __syncthreads();                                      // previous chunk fully consumed
+    int sh_next = issue(0, 0);
+    for (int cand = 0; cand < 9; cand++)
+    {
+      const int sh = sh_next, buf = cand & 1;
+      if (cand + 1 < 9) { sh_next = issue(cand + 1, buf ^ 1); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
       __syncthreads();
       uint32_t v;
       if (satd)
@@ -226,10 +234,10 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 #pragma unroll
         for (int r = 0; r < TS; r++)
         {
-          const uint32_t w0 = s_ref[r][tid * NW + 0], w1 = s_ref[r][tid * NW + 1];
+          const uint32_t w0 = s_ref[buf][r][tid * NW + 0], w1 = s_ref[buf][r][tid * NW + 1];
           if (TS == 8)
           {
-            const uint32_t w2 = s_ref[r][tid * NW + NW - 1];
+            const uint32_t w2 = s_ref[buf][r][tid * NW + NW - 1];
             int h[TS];
             had_row8<false>(ow[r][0], ow[r][OW - 1], zero, h);                       // + H(org row)
             had_row8<true>(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), h, d + r * TS);   // - H(ref row)
@@ -249,11 +257,11 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 #pragma unroll
         for (int r = 0; r < TS; r++)
         {
-          const uint32_t w0 = s_ref[r][tid * NW + 0], w1 = s_ref[r][tid * NW + 1];
+          const uint32_t w0 = s_ref[buf][r][tid * NW + 0], w1 = s_ref[buf][r][tid * NW + 1];
           v = vabsdiff4_acc(__funnelshift_r(w0, w1, sh), ow[r][0], v);
           if (TS == 8)
           {
-            const uint32_t w2 = s_ref[r][tid * NW + NW - 1];
+            const uint32_t w2 = s_ref[buf][r][tid * NW + NW - 1];
             v = vabsdiff4_acc(__funnelshift_r(w1, w2, sh), ow[r][OW - 1], v);
           }
         }

@@ -17,6 +17,7 @@ static void prof_drain(hmgpu_ctx* ctx)
 {
   if (ctx->prof_n == 0) return;
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->lane_store[1 - ctx->cur_lane].stream) cudaStreamSynchronize(ctx->lane_store[1 - ctx->cur_lane].stream);
   for (int i = 0; i < ctx->prof_n; i++)
   {
     float ms = 0.f;

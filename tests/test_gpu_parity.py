@@ -304,3 +304,38 @@ def test_full_size_1080p_properties():
         # 3) idempotence: the same batch again gives the same bytes
         r2 = ctx.me_search(jobs)
         assert r.tobytes() == r2.tobytes()
+        # 4) the chunked two-lane pipeline (large batches) and the single-shot path give the same bytes
+        import os
+        os.environ["HMGPU_NO_PIPELINE"] = "1"
+        try:
+            r3 = ctx.me_search(jobs)
+        finally:
+            del os.environ["HMGPU_NO_PIPELINE"]
+        assert r.tobytes() == r3.tobytes()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pipelined_batch_with_key_blocks(pinned):
+    """>= 65536 jobs take the two-lane pipeline; bi-pred key-pattern blocks travel once for all chunks.
+    Checked against the oracle on the distinct jobs the batch is tiled from."""
+    rng = np.random.default_rng(5)
+    fr = _frames(8, 4)
+    n_base = 96
+    base, blocks, n_elems = _random_jobs(rng, n_base, 8, "tz", 2, org_blocks=True)
+    org_blocks = np.zeros(max(1, n_elems), np.int16)
+    for (i, w, h) in blocks:
+        j = base[i]
+        o = fr[2][int(j["pu_y"]):int(j["pu_y"]) + h, int(j["pu_x"]):int(j["pu_x"]) + w].astype(np.int32)
+        org_blocks[int(j["org_offset"]):int(j["org_offset"]) + w * h] = (2 * o - rng.integers(0, 256, (h, w))).astype(np.int16).ravel()
+    exp = oracle_me(base, [padded_ref(fr[0]), padded_ref(fr[1])], fr[2], 8, org_blocks)
+    reps = 70000 // n_base + 1
+    jobs = np.tile(base, reps)
+    with hmgpu.Context(W, H, 8, 2) as ctx:
+        ctx.ref_upload(0, fr[0]); ctx.ref_upload(1, fr[1]); ctx.org_upload(fr[2])
+        if pinned:
+            hj = ctx.host_array(jobs.shape, hmgpu.ME_JOB); hj[...] = jobs
+            hr = ctx.host_array(jobs.shape, hmgpu.ME_RESULT)
+            got = ctx.me_search(hj, org_blocks, out=hr).copy()   # the pinned buffer dies with the context
+        else:
+            got = ctx.me_search(jobs, org_blocks)
+    assert_results_equal(got, np.tile(exp, reps), jobs)
