@@ -234,6 +234,10 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
     if (l1.stream) cudaStreamDestroy(l1.stream);
     for (int i = 0; i < 2; i++) if (ctx->lane_done[i]) cudaEventDestroy(ctx->lane_done[i]);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (int i = 0; i < 2; i++) if (ctx->scan_done[i]) cudaEventDestroy(ctx->scan_done[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->d_scan) cudaFree(ctx->d_scan);
+    if (ctx->h_scan) cudaFreeHost(ctx->h_scan);
     if (ctx->d_orgblk) cudaFree(ctx->d_orgblk);
   }
   for (int i = 0; i < HMGPU_MAX_REFS; i++)
@@ -433,9 +437,78 @@ static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_
   return HMGPU_OK;
 }
 
-// Large batches: chunks alternate between the two lanes, so the H2D copy (and the host-side validation)
-// of chunk k+1 and the D2H copy of chunk k-1 overlap the search kernels of chunk k.
+// ---- large batches -----------------------------------------------------------------------------------
+// Chunks alternate between the two lanes: the H2D copy of chunk k+1 and the D2H copy of chunk k-1
+// overlap the search kernels of chunk k.  The per-job range checks of validate_jobs() cost more host
+// time per job than the device needs for the whole search (measured: ~10 ns/job on the host, 5 ns/job
+// on the B200), so for these batches the same checks run as a kernel on the freshly copied chunk
+// (job_scan_kernel, on the copy stream) and the host only reads its 16-byte verdict.
 #define PIPE_MIN_JOBS 65536
+
+struct ScanOut { uint32_t first_bad; uint32_t flags_any; uint32_t max_win; uint32_t int_kinds; /* bit0 tz, bit1 full */ };
+
+enum { SCAN_OK = 0, SCAN_PU_SIZE, SCAN_PU_POS, SCAN_SLOT, SCAN_CLIP, SCAN_WINDOW, SCAN_START, SCAN_ORG, SCAN_RANGE };
+static const char* const k_scan_msg[] = {
+  "ok", "PU size unsupported", "PU outside the picture or x not a multiple of 4", "reference slot not uploaded",
+  "clip bounds reach outside the padded reference", "search window outside the clip bounds", "integer MV outside the clip bounds",
+  "org block outside org_blocks", "search range not in 1..512" };
+
+__host__ __device__ static inline int job_check(const hmgpu_me_job& j, int pic_w, int pic_h, uint32_t valid_slots, unsigned long long n_org_elems)
+{
+  if (j.pu_w < 4 || j.pu_w > 64 || j.pu_h < 4 || j.pu_h > 64 || (j.pu_w & 3) || (j.pu_h & 3)) return SCAN_PU_SIZE;
+  if (j.pu_x < 0 || j.pu_y < 0 || j.pu_x + j.pu_w > pic_w || j.pu_y + j.pu_h > pic_h || (j.pu_x & 3)) return SCAN_PU_POS;
+  if (j.ref_slot >= 32 || !((valid_slots >> j.ref_slot) & 1u)) return SCAN_SLOT;
+  const int lo_x = j.pu_x + (j.clip_hmin >> 2) - 4, hi_x = j.pu_x + j.pu_w + (j.clip_hmax >> 2) + 4;
+  const int lo_y = j.pu_y + (j.clip_vmin >> 2) - 4, hi_y = j.pu_y + j.pu_h + (j.clip_vmax >> 2) + 4;
+  if (lo_x < -HMGPU_MARGIN || lo_y < -HMGPU_MARGIN || hi_x > pic_w + HMGPU_MARGIN || hi_y > pic_h + HMGPU_MARGIN) return SCAN_CLIP;
+  if ((j.win_l << 2) < j.clip_hmin - 3 || (j.win_r << 2) > j.clip_hmax || (j.win_t << 2) < j.clip_vmin - 3 || (j.win_b << 2) > j.clip_vmax) return SCAN_WINDOW;
+  if (!(j.flags & HMGPU_F_INTEGER) &&
+      ((j.start_x << 2) < j.clip_hmin - 3 || (j.start_x << 2) > j.clip_hmax || (j.start_y << 2) < j.clip_vmin - 3 || (j.start_y << 2) > j.clip_vmax)) return SCAN_START;
+  if ((j.flags & HMGPU_F_ORG_BLOCK) && (unsigned long long)j.org_offset + (unsigned long long)j.pu_w * j.pu_h > n_org_elems) return SCAN_ORG;
+  if ((j.flags & HMGPU_F_INTEGER) && !(j.flags & HMGPU_F_FULL) && (j.search_range < 1 || j.search_range > 512)) return SCAN_RANGE;
+  return SCAN_OK;
+}
+
+__host__ __device__ static inline int job_full_window_bytes(const hmgpu_me_job& j)
+{
+  const int nx = j.win_r - j.win_l + 1, ny = j.win_b - j.win_t + 1;
+  if (nx <= 0 || ny <= 0) return 0;
+  const int rows = ((j.flags & HMGPU_F_FEN) && j.pu_h > 8) ? j.pu_h >> 1 : j.pu_h;
+  const int win_w = 15 + nx - 1 + j.pu_w + 4;
+  const int spitch = ((win_w + 15) >> 4) * 16 + 16;
+  return ((rows * j.pu_w + 15) & ~15) + spitch * (ny - 1 + j.pu_h);
+}
+
+__global__ void job_scan_kernel(const hmgpu_me_job* __restrict__ jobs, int n, int pic_w, int pic_h, uint32_t valid_slots,
+                                unsigned long long n_org_elems, ScanOut* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bad = 0xffffffffu, fl = 0, win = 0, kinds = 0;
+  if (i < n)
+  {
+    const hmgpu_me_job j = jobs[i];
+    const int code = job_check(j, pic_w, pic_h, valid_slots, n_org_elems);
+    if (code) bad = ((uint32_t)i << 4) | (uint32_t)code;       // i < 2^26: (index, reason) ordered by index
+    fl = j.flags;
+    if (j.flags & HMGPU_F_INTEGER)
+    {
+      if (j.flags & HMGPU_F_FULL) { kinds = 2; if (!code) win = (uint32_t)job_full_window_bytes(j); }
+      else kinds = 1;
+    }
+  }
+  bad = __reduce_min_sync(0xffffffffu, bad);
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  win = __reduce_max_sync(0xffffffffu, win);
+  kinds = __reduce_or_sync(0xffffffffu, kinds);
+  if ((threadIdx.x & 31) == 0)
+  {
+    if (bad != 0xffffffffu) atomicMin(&out->first_bad, bad);
+    atomicOr(&out->flags_any, fl);
+    if (win) atomicMax(&out->max_win, win);
+    atomicOr(&out->int_kinds, kinds);
+  }
+}
+
 static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                                const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
 {
@@ -447,10 +520,21 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
   if (!ctx->lane_store[1].stream)
   {
     HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_store[1].stream, cudaStreamNonBlocking));
-    HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[0], cudaEventDisableTiming));
-    HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[1], cudaEventDisableTiming));
+    HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++)
+    {
+      HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[i], cudaEventDisableTiming));
+      HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->scan_done[i], cudaEventDisableTiming));
+    }
     HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_scan, 2 * sizeof(ScanOut)));
+    HMGPU_CUDA(ctx, cudaMallocHost(&ctx->h_scan, 2 * sizeof(ScanOut)));
   }
+  ScanOut* d_scan = (ScanOut*)ctx->d_scan;
+  ScanOut* h_scan = (ScanOut*)ctx->h_scan;
+  uint32_t valid_slots = 0;
+  for (int i = 0; i < ctx->max_refs; i++) if (ctx->refs[i].valid) valid_slots |= 1u << i;
+
   // bi-pred key patterns: the whole array goes up once, on lane 0, before the lanes fork
   const bool have_org = org_blocks && n_org_elems > 0;
   if (have_org)
@@ -478,51 +562,84 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
   }
   HMGPU_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
   HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_store[1].stream, ctx->fork_ev, 0));
+  HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
 
   const bool jobs_pinned = is_pinned(jobs), res_pinned = is_pinned(results);
   const size_t jb = round_up(sizeof(hmgpu_me_job) * (size_t)chunk, 256), rb = round_up(sizeof(hmgpu_me_result) * (size_t)chunk, 256);
   int rc = HMGPU_OK;
+  // both lanes' staging buffers up front (allocation synchronises the device)
+  for (int l = 0; l < 2 && rc == HMGPU_OK; l++)
+  {
+    hmgpu_use_lane(ctx, l);
+    rc = hmgpu_reserve_stage(ctx, jb + rb);
+    if (rc == HMGPU_OK && !(jobs_pinned && res_pinned)) rc = hmgpu_reserve_pinned(ctx, jb + rb);
+  }
+  auto chunk_n = [&](int k) { const int first = k * chunk; return (n_jobs - first < chunk) ? n_jobs - first : chunk; };
+  // copy stream: jobs of chunk k into its lane's staging buffer (once the lane's previous chunk is done with it), then the scan
+  auto prefetch = [&](int k) -> int {
+    const int l = k & 1, first = k * chunk, n = chunk_n(k);
+    hmgpu_use_lane(ctx, l);
+    char* dp = (char*)ctx->d_stage;
+    if (k >= 2) HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->lane_done[l], 0));
+    const ScanOut init = { 0xffffffffu, 0u, 0u, 0u };
+    h_scan[l] = init;                                       // chunk k-2's verdict was read long ago
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(&d_scan[l], &h_scan[l], sizeof(ScanOut), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (jobs_pinned)
+      HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, jobs + first, sizeof(hmgpu_me_job) * (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    else
+    {
+      memcpy(ctx->h_pin, jobs + first, sizeof(hmgpu_me_job) * (size_t)n);   // its previous H2D was awaited through scan_done
+      HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, ctx->h_pin, sizeof(hmgpu_me_job) * (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    job_scan_kernel<<<(n + 255) / 256, 256, 0, ctx->copy_stream>>>((const hmgpu_me_job*)dp, n, ctx->pic_w, ctx->pic_h, valid_slots,
+                                                                  have_org ? (unsigned long long)n_org_elems : 0ull, &d_scan[l]);
+    ctx->launches++;
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(&h_scan[l], &d_scan[l], sizeof(ScanOut), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    HMGPU_CUDA(ctx, cudaEventRecord(ctx->scan_done[l], ctx->copy_stream));
+    return HMGPU_OK;
+  };
   // copy the results of chunk k out of its lane's pinned staging buffer (pageable `results` only)
   auto retire = [&](int k) -> int {
     hmgpu_use_lane(ctx, k & 1);
     const cudaError_t e = cudaEventSynchronize(ctx->lane_done[k & 1]);
     if (e != cudaSuccess) return hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search, chunk %d: %s", k, cudaGetErrorString(e));
-    const int first = k * chunk, n = (n_jobs - first < chunk) ? n_jobs - first : chunk;
-    if (!res_pinned) memcpy(results + first, (char*)ctx->h_pin + jb, sizeof(hmgpu_me_result) * (size_t)n);
+    if (!res_pinned) memcpy(results + (size_t)k * chunk, (char*)ctx->h_pin + jb, sizeof(hmgpu_me_result) * (size_t)chunk_n(k));
     return HMGPU_OK;
   };
-  int retired = 0;
+  int next_retire = 0;
+  if (rc == HMGPU_OK) rc = prefetch(0);
   for (int k = 0; k < n_chunks && rc == HMGPU_OK; k++)
   {
-    const int first = k * chunk, n = (n_jobs - first < chunk) ? n_jobs - first : chunk;
-    if (k >= 2) { if ((rc = retire(k - 2))) break; retired = k - 1; }
-    hmgpu_use_lane(ctx, k & 1);
-    bool any_org, any_full, any_tz, any_frac;
-    int max_win;
-    if ((rc = validate_jobs(ctx, jobs + first, n, have_org ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, first))) break;
-    if ((rc = hmgpu_reserve_stage(ctx, jb + rb))) break;
-    if (!(jobs_pinned && res_pinned) && (rc = hmgpu_reserve_pinned(ctx, jb + rb))) break;
+    const int l = k & 1, n = chunk_n(k);
+    hmgpu_use_lane(ctx, l);
+    cudaError_t e = cudaEventSynchronize(ctx->scan_done[l]);
+    if (e != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search, scan of chunk %d: %s", k, cudaGetErrorString(e)); break; }
+    const ScanOut so = h_scan[l];
+    if (so.first_bad != 0xffffffffu)
+    {
+      rc = hmgpu_fail(ctx, (so.first_bad & 15u) == SCAN_SLOT ? HMGPU_E_STATE : HMGPU_E_INVALID, "job %d: %s",
+                      k * chunk + (int)(so.first_bad >> 4), k_scan_msg[so.first_bad & 15u]);
+      break;
+    }
     char* dp = (char*)ctx->d_stage;
     char* hp = (char*)ctx->h_pin;
-    cudaError_t e;
-    if (jobs_pinned) e = cudaMemcpyAsync(dp, jobs + first, sizeof(hmgpu_me_job) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    else
-    {
-      memcpy(hp, jobs + first, sizeof(hmgpu_me_job) * (size_t)n);
-      e = cudaMemcpyAsync(dp, hp, sizeof(hmgpu_me_job) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    }
-    if (e != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search H2D: %s", cudaGetErrorString(e)); break; }
-    if ((rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n, any_org ? (const int16_t*)ctx->d_orgblk : NULL,
-                              (hmgpu_me_result*)(dp + jb), any_org, any_full, any_tz, any_frac, max_win))) break;
-    e = cudaMemcpyAsync(res_pinned ? (void*)(results + first) : (void*)(hp + jb), dp + jb, sizeof(hmgpu_me_result) * (size_t)n,
+    const bool any_org = (so.flags_any & HMGPU_F_ORG_BLOCK) != 0;
+    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->scan_done[l], 0)) != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "%s", cudaGetErrorString(e)); break; }
+    if ((rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n, any_org ? (const int16_t*)ctx->d_orgblk : NULL, (hmgpu_me_result*)(dp + jb),
+                              any_org, (so.int_kinds & 2u) != 0, (so.int_kinds & 1u) != 0, (so.flags_any & HMGPU_F_FRAC) != 0, (int)so.max_win))) break;
+    e = cudaMemcpyAsync(res_pinned ? (void*)(results + (size_t)k * chunk) : (void*)(hp + jb), dp + jb, sizeof(hmgpu_me_result) * (size_t)n,
                         cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->lane_done[k & 1], ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->lane_done[l], ctx->stream);
     if (e != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search D2H: %s", cudaGetErrorString(e)); break; }
+    // pageable `results`: chunk k-1 must have left its lane's pinned result buffer before chunk k+1 (same lane) is queued;
+    // the wait happens with chunk k already queued, so the device does not idle
+    if (k >= 1 && !res_pinned) { if ((rc = retire(k - 1))) break; next_retire = k; }
+    if (k + 1 < n_chunks && (rc = prefetch(k + 1))) break;
   }
   if (rc == HMGPU_OK)
-    for (int k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks && rc == HMGPU_OK; k++)
-      if (k >= retired) rc = retire(k);
-  // leave both lanes idle and lane 0 current, whatever happened
+    for (int k = next_retire; k < n_chunks && rc == HMGPU_OK; k++) rc = retire(k);
+  // leave everything idle and lane 0 current, whatever happened
+  cudaStreamSynchronize(ctx->copy_stream);
   hmgpu_use_lane(ctx, 1); cudaStreamSynchronize(ctx->stream);
   hmgpu_use_lane(ctx, 0); cudaStreamSynchronize(ctx->stream);
   return rc;

@@ -65,7 +65,9 @@ struct hmgpu_ctx
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
   void* d_tzlist; size_t d_tzlist_bytes; // device index lists of the TZ size classes (me_tz.cu)
   HmgpuLane lane_store[2]; int cur_lane; // parked lanes (the current one lives in the fields above)
-  cudaEvent_t lane_done[2], fork_ev;
+  cudaEvent_t lane_done[2], scan_done[2], fork_ev;
+  cudaStream_t copy_stream;              // H2D of the next chunk + its validation scan
+  void* d_scan; void* h_scan;            // per-lane verdict of the scan (device / pinned host copy)
   void* d_orgblk; size_t d_orgblk_bytes; // bi-pred key patterns of a pipelined batch
   void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
   uint64_t launches;

@@ -339,3 +339,22 @@ def test_pipelined_batch_with_key_blocks(pinned):
         else:
             got = ctx.me_search(jobs, org_blocks)
     assert_results_equal(got, np.tile(exp, reps), jobs)
+
+
+def test_pipelined_batch_reports_bad_job():
+    """large batches are range-checked on the device (job_scan_kernel): same error contract as the host check"""
+    fr = _frames(8, 2)
+    jobs = worklist.frame_jobs(W, H, n_refs=1)
+    jobs = np.tile(jobs, 70000 // len(jobs) + 1)
+    bad = jobs.copy()
+    bad[66001]["pu_w"] = 7
+    worse = jobs.copy()
+    worse[40000]["ref_slot"] = 1          # slot never uploaded
+    with hmgpu.Context(W, H, 8, 2) as ctx:
+        ctx.ref_upload(0, fr[0]); ctx.org_upload(fr[1])
+        with pytest.raises(hmgpu.HmGpuError, match="job 66001"):
+            ctx.me_search(bad)
+        with pytest.raises(hmgpu.HmGpuError, match="job 40000"):
+            ctx.me_search(worse)
+        r = ctx.me_search(jobs)            # the context stays usable
+        assert int(r["n_cand"].min()) >= 18
