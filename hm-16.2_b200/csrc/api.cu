@@ -18,7 +18,7 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, 
                         hmgpu_me_result* d_results, uint32_t* d_flags, uint32_t ticket, bool any_org_block, int max_win_bytes);
 
 // mailbox of the low-latency path: up to MAIL_JOBS jobs per call
-#define MAIL_JOBS 16
+#define MAIL_JOBS 32
 struct Mailbox
 {
   hmgpu_me_job    jobs[MAIL_JOBS];

@@ -31,7 +31,8 @@ HmGpuHost& HmGpuHost::instance()
 
 HmGpuHost::HmGpuHost()
 : m_ctx( NULL ), m_picW( 0 ), m_picH( 0 ), m_tick( 0 ), m_orgPic( NULL ), m_orgPoc( -1 ), m_keyBlock( NULL )
-, m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_totalSeconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
+, m_queueing( false ), m_queueLen( 0 ), m_queueDone( false ), m_queueJobs( NULL ), m_queueRes( NULL )
+, m_gpuCalls( 0 ), m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_totalSeconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
 {
   for ( Int i = 0; i < NUM_SLOTS; i++ )
   {
@@ -43,15 +44,17 @@ HmGpuHost::~HmGpuHost()
 {
   if ( m_ctx )
   {
-    fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
+    fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu in %llu GPU calls, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
                      "%.3f s in motionSearch overall, %.3f s one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
-             (unsigned long long)m_calls, (unsigned long long)m_cands, m_seconds, m_calls ? m_seconds / (Double)m_calls * 1e6 : 0.0,
+             (unsigned long long)m_calls, (unsigned long long)m_gpuCalls, (unsigned long long)m_cands, m_seconds, m_calls ? m_seconds / (Double)m_calls * 1e6 : 0.0,
              m_seconds > 0 ? (Double)m_cands / m_seconds / 1e6 : 0.0, m_totalSeconds, m_initSeconds,
              (unsigned long long)m_uploads, m_uploadSeconds,
              (unsigned long long)hmgpu_launch_count( m_ctx ), (unsigned long long)m_checked );
     hmgpu_destroy( m_ctx );
   }
   delete [] m_keyBlock;
+  delete [] m_queueJobs;
+  delete [] m_queueRes;
 }
 
 Void HmGpuHost::xFail( const char* what )
@@ -73,6 +76,8 @@ Void HmGpuHost::xInit( TComDataCU* pcCU )
     xFail( "hmgpu_create" );
   }
   m_keyBlock = new Pel[MAX_CU_SIZE * MAX_CU_SIZE];
+  m_queueJobs = new hmgpu_me_job[MAX_QUEUE];
+  m_queueRes  = new hmgpu_me_result[MAX_QUEUE];
   m_initSeconds = xNow() - t0;
 }
 
@@ -174,9 +179,36 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
   j.flags = (uint8_t)flags;
 
   hmgpu_me_result r;
-  if ( hmgpu_me_search( m_ctx, &j, 1, keyElems ? m_keyBlock : NULL, keyElems, &r ) != HMGPU_OK )
+  if ( m_queueing && !bBi )
   {
-    xFail( "hmgpu_me_search" );
+    // pass 0 of the patched predInterSearch loop: remember the job, the result is handed out in pass 1
+    if ( m_queueLen < MAX_QUEUE )
+    {
+      m_queueJobs[m_queueLen++] = j;
+    }
+    m_totalSeconds += xNow() - tEnter;
+    return;
+  }
+  Int hit = -1;
+  if ( m_queueDone && !bBi )
+  {
+    for ( Int k = 0; k < m_queueLen; k++ )
+    {
+      if ( !m_queueUsed[k] && memcmp( &m_queueJobs[k], &j, sizeof( j ) ) == 0 ) { hit = k; break; }
+    }
+  }
+  if ( hit >= 0 )
+  {
+    r = m_queueRes[hit];
+    m_queueUsed[hit] = true;
+  }
+  else
+  {
+    if ( hmgpu_me_search( m_ctx, &j, 1, keyElems ? m_keyBlock : NULL, keyElems, &r ) != HMGPU_OK )
+    {
+      xFail( "hmgpu_me_search" );
+    }
+    m_gpuCalls++;
   }
   rcOut.mvInt.set ( r.int_x,  r.int_y  );
   rcOut.mvHalf.set( r.half_x, r.half_y );
@@ -188,6 +220,31 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
   const Double tExit = xNow();
   m_seconds += tExit - t0;
   m_totalSeconds += tExit - tEnter;
+}
+
+Void HmGpuHost::beginQueue()
+{
+  m_queueing  = true;
+  m_queueDone = false;
+  m_queueLen  = 0;
+}
+
+Void HmGpuHost::flushQueue()
+{
+  m_queueing = false;
+  if ( m_queueLen > 0 )
+  {
+    const Double t0 = xNow();
+    if ( hmgpu_me_search( m_ctx, m_queueJobs, m_queueLen, NULL, 0, m_queueRes ) != HMGPU_OK )
+    {
+      xFail( "hmgpu_me_search (queued)" );
+    }
+    m_gpuCalls++;
+    const Double dt = xNow() - t0;
+    m_seconds += dt; m_totalSeconds += dt;
+  }
+  for ( Int k = 0; k < MAX_QUEUE; k++ ) m_queueUsed[k] = false;
+  m_queueDone = true;
 }
 
 Void HmGpuHost::checkInteger( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu )

@@ -37,6 +37,14 @@ public:
                      Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
                      Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut );
 
+  /// Batching of the uni-directional searches of one PU (TEncSearch::predInterSearch, TEncSearch.cpp:3177-3257): the
+  /// searches of the different lists / reference pictures of a PU do not depend on each other, so the patched loop
+  /// first queues them all (beginQueue, motionSearch x N), sends them to the GPU as ONE hmgpu_me_search call
+  /// (flushQueue) and then runs its original body, where motionSearch hands out the queued results.
+  Void beginQueue   ();
+  Void flushQueue   ();
+  Bool queueing     () const { return m_queueing; }
+
   /// GPUME=2: compare with what the CPU search just produced; abort on the first mismatch
   Void checkInteger   ( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu );
   Void checkFractional( const HmGpuSearchOut& rcOut, const TComMv& rcHalfCpu, const TComMv& rcQterCpu, Distortion uiCostCpu );
@@ -50,6 +58,7 @@ private:
   Void xFail        ( const char* what );
 
   static const Int NUM_SLOTS = 16;
+  static const Int MAX_QUEUE = 32;   ///< 2 lists x 16 reference pictures
   hmgpu_ctx*  m_ctx;
   Int         m_picW, m_picH;
   const void* m_slotPic[NUM_SLOTS];
@@ -59,8 +68,16 @@ private:
   const void* m_orgPic;
   Int         m_orgPoc;
   Pel*        m_keyBlock;
+  // queue of the current PU (see beginQueue): jobs as submitted, results once flushed
+  Bool        m_queueing;
+  Int         m_queueLen;
+  Bool        m_queueDone;
+  struct hmgpu_me_job*    m_queueJobs;
+  struct hmgpu_me_result* m_queueRes;
+  Bool        m_queueUsed[MAX_QUEUE];
   // statistics
   UInt64      m_calls, m_cands, m_checked;
+  UInt64      m_gpuCalls;       ///< hmgpu_me_search invocations (<= m_calls: queued searches share one)
   Double      m_seconds;        ///< inside hmgpu_me_search
   Double      m_totalSeconds;   ///< inside motionSearch (set-up, uploads, job marshalling included)
   Double      m_initSeconds;    ///< CUDA context + library set-up (once)
