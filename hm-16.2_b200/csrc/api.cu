@@ -4,6 +4,7 @@
 #include "hmgpu_internal.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
+#include <time.h>
 #include <new>
 
 int hmgpu_launch_chroma(hmgpu_ctx* ctx, int16_t* d_dst, const int16_t* d_src, int src_stride);
@@ -14,18 +15,24 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
 int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_frac);
 int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, hmgpu_me_result* d_results, bool any_frac);
-int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
-                        hmgpu_me_result* d_results, uint32_t* d_flags, uint32_t ticket, bool any_org_block, int max_win_bytes);
+int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, const int16_t* d_org_blocks,
+                        HmgpuMailSlot* d_slots, uint32_t ticket, bool any_org_block, int max_win_bytes,
+                        unsigned long long* trace);
 
 // mailbox of the low-latency path: up to MAIL_JOBS jobs per call
-#define MAIL_JOBS 32
+#define MAIL_JOBS HMGPU_MAIL_JOBS
 struct Mailbox
 {
-  hmgpu_me_job    jobs[MAIL_JOBS];
-  hmgpu_me_result results[MAIL_JOBS];
-  uint32_t        flags[MAIL_JOBS];
+  HmgpuMailSlot   slots[MAIL_JOBS];
+  unsigned long long trace[8];          // HMGPU_TRACE: globaltimer stamps of the kernel phases
   int16_t         org_blocks[MAIL_JOBS * 64 * 64];
 };
+
+// HMGPU_TRACE=1: where the time of a low-latency call goes (host clock around the launch / the poll, device
+// globaltimer inside the kernel); printed by hmgpu_destroy
+struct TraceAcc { double host_prep, host_launch, host_wait, host_copy, dev[5]; unsigned long long n; };
+static TraceAcc g_trace;
+static double now_us() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
 
 static char g_create_err[512] = "";
 
@@ -221,6 +228,14 @@ int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, 
 void hmgpu_destroy(hmgpu_ctx* ctx)
 {
   if (!ctx) return;
+  if (g_trace.n)
+  {
+    const double n = (double)g_trace.n;
+    fprintf(stderr, "[hmgpu trace] %llu low-latency calls, us/call: host prep %.2f, launch %.2f, wait %.2f, copy-out %.2f | device (block 0): "
+                    "job fetch %.2f, integer %.2f, half %.2f, quarter %.2f, publish %.2f\n", g_trace.n, g_trace.host_prep / n, g_trace.host_launch / n,
+            g_trace.host_wait / n, g_trace.host_copy / n, g_trace.dev[0] / n, g_trace.dev[1] / n, g_trace.dev[2] / n, g_trace.dev[3] / n, g_trace.dev[4] / n);
+    memset(&g_trace, 0, sizeof g_trace);
+  }
   cudaSetDevice(ctx->device);
   hmgpu_use_lane(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
@@ -666,29 +681,47 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
       memset(ctx->h_mail, 0, sizeof(Mailbox));
     }
     Mailbox* mb = (Mailbox*)ctx->h_mail;
-    memcpy(mb->jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
+    static const bool s_trace = getenv("HMGPU_TRACE") != NULL;
+    const double t0 = s_trace ? now_us() : 0.0;
+    HmgpuJobPack pack;
+    memcpy(pack.jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
     if (any_org) memcpy(mb->org_blocks, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
     const uint32_t ticket = ++ctx->mail_ticket;
     __sync_synchronize();
-    rc = hmgpu_launch_single(ctx, mb->jobs, n_jobs, mb->org_blocks, mb->results, mb->flags, ticket, any_org, max_win);
+    const double t1 = s_trace ? now_us() : 0.0;
+    rc = hmgpu_launch_single(ctx, pack, n_jobs, mb->org_blocks, mb->slots, ticket, any_org, max_win, s_trace ? mb->trace : NULL);
     if (rc) return rc;
-    volatile uint32_t* flags = mb->flags;
+    const double t2 = s_trace ? now_us() : 0.0;
     for (int i = 0; i < n_jobs; i++)
     {
+      const volatile uint32_t* slot = (const volatile uint32_t*)&mb->slots[i];
       unsigned spins = 0;
-      while (flags[i] != ticket)
+      for (;;)
       {
-        if (++spins > 4000000u)
+        uint32_t w[8];
+        for (int k = 0; k < 8; k++) w[k] = slot[k];
+        if (w[6] == ticket && w[7] == hmgpu_mail_check(w, ticket)) { memcpy(&results[i], w, sizeof(hmgpu_me_result)); break; }
+        if (++spins > 2000000u)
         {
           spins = 0;
           const cudaError_t e = cudaStreamQuery(ctx->stream);
-          if (e != cudaErrorNotReady && flags[i] != ticket)
+          if (e != cudaErrorNotReady)
+          {
+            for (int k = 0; k < 8; k++) w[k] = slot[k];
+            if (w[6] == ticket && w[7] == hmgpu_mail_check(w, ticket)) { memcpy(&results[i], w, sizeof(hmgpu_me_result)); break; }
             return hmgpu_fail(ctx, HMGPU_E_CUDA, "low-latency search kernel ended without publishing job %d: %s", i, cudaGetErrorString(e));
+          }
         }
       }
     }
-    __sync_synchronize();
-    memcpy(results, (const void*)mb->results, sizeof(hmgpu_me_result) * (size_t)n_jobs);
+    const double t3 = s_trace ? now_us() : 0.0;
+    if (s_trace)
+    {
+      cudaStreamSynchronize(ctx->stream);                   // the last stamp is written after the flag
+      g_trace.host_prep += t1 - t0; g_trace.host_launch += t2 - t1; g_trace.host_wait += t3 - t2; g_trace.host_copy += now_us() - t3;
+      for (int k = 0; k < 5; k++) g_trace.dev[k] += (double)(mb->trace[k + 1] - mb->trace[k]) * 1e-3;
+      g_trace.n++;
+    }
     return HMGPU_OK;
   }
   const size_t jb = round_up(sizeof(hmgpu_me_job) * (size_t)n_jobs, 256);

@@ -81,6 +81,24 @@ struct hmgpu_ctx
   char err[512];
 };
 
+// ---- low-latency path (me_single.cu): mapped pinned mailbox --------------------------------------
+#define HMGPU_MAIL_JOBS 32
+// the jobs of one call travel as a kernel parameter (no PCIe read on the device side)
+struct HmgpuJobPack { hmgpu_me_job jobs[HMGPU_MAIL_JOBS]; };
+// One result slot = 32 bytes written by ONE warp-wide store of 8 consecutive words, so it crosses PCIe as a
+// single write.  No system-scope fence is issued (it cost 4 us per call): instead the slot validates itself --
+// the host accepts it only when the ticket matches and the check word matches the six result words.
+struct HmgpuMailSlot { hmgpu_me_result r; uint32_t ticket; uint32_t check; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline uint32_t hmgpu_mail_check(const uint32_t* w, uint32_t ticket)
+{
+  uint32_t h = ticket * 0x9E3779B9u + 0x7F4A7C15u;
+  for (int i = 0; i < 6; i++) h = (h ^ w[i]) * 0x85EBCA6Bu + (h >> 15);
+  return h;
+}
+
 enum
 {
   HMGPU_ST_PLANES = 0, HMGPU_ST_ORG, HMGPU_ST_TZ, HMGPU_ST_FULL, HMGPU_ST_FRAC_EXPAND, HMGPU_ST_FRAC_DIST,

@@ -44,22 +44,25 @@ __device__ __forceinline__ void sg_frac_phase(const hmgpu_me_job& jb, const int1
   }
 }
 
+#define SG_WIN_BYTES (10 * 1024)   // staged TZ window: <= (64 + 12) rows x <= 112 bytes
+
 template <typename Px, bool PACKED>
 __global__ void __launch_bounds__(SG_THREADS)
-me_single_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
-                 hmgpu_me_result* results, volatile uint32_t* done_flags, uint32_t ticket)
+me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
+                 HmgpuMailSlot* slots, uint32_t ticket, unsigned long long* trace)
 {
-  extern __shared__ __align__(16) unsigned char s_dyn[];       // packed full-search window
+  // optional phase trace (HMGPU_TRACE=1): globaltimer stamps of block 0, read by the host after the call
+#define SG_STAMP(k) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); trace[k] = t_; } } while (0)
+  SG_STAMP(0);
+  extern __shared__ __align__(16) unsigned char s_dyn[];       // packed full-search window, or the staged TZ window
   __shared__ __align__(16) unsigned char s_org[8192];          // PU block: packed bytes or int16
   __shared__ unsigned long long s_red[SG_THREADS / 32];
-  __shared__ hmgpu_me_job s_job;
   __shared__ hmgpu_me_result s_res;
   __shared__ uint32_t s_acc[9];
 
   const int tid = threadIdx.x;
-  if (tid < (int)(sizeof(hmgpu_me_job) / 4)) ((uint32_t*)&s_job)[tid] = ((const uint32_t*)&jobs[blockIdx.x])[tid];
-  __syncthreads();
-  const hmgpu_me_job jb = s_job;
+  const hmgpu_me_job jb = pack.jobs[blockIdx.x];               // kernel parameter: no PCIe read
+  SG_STAMP(1);
 
   // ---- integer search --------------------------------------------------------------------
   if (jb.flags & HMGPU_F_INTEGER)
@@ -69,11 +72,35 @@ me_single_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restric
       if (PACKED) full_search_block_packed(jb, refs, org, s_dyn, s_red, &s_res);
       else full_search_block_generic<Px>(jb, org_blocks, refs, org, (int16_t*)s_org, s_red, &s_res);
     }
-    else if (tid < 32)
+    else
     {
-      hmgpu_me_result r;
-      tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r);
-      if (tid == 0) s_res = r;
+      // TZ is a chain of dependent rounds executed by warp 0.  Every round that reads the reference from global
+      // memory pays a full memory round trip (~0.6 us, measured with HMGPU_TRACE), so the whole CTA first copies
+      // the neighbourhood of the start point into shared memory -- one round trip -- and the rounds within
+      // TZ_WIN_RADIUS of it (the common case: distances 1, 2, 4 and the two-point fill) run out of it.
+      TzWindow win;
+      bool have_win = false;
+      if (PACKED)
+      {
+        have_win = tz_window_geometry(jb, refs, win) && win.pitch * win.rows <= SG_WIN_BYTES;
+        if (have_win)
+        {
+          const uint8_t* src = (const uint8_t*)refs.base[jb.ref_slot] + (ptrdiff_t)(jb.pu_y + win.oy) * refs.pitch + (jb.pu_x + win.ox);
+          const int c16 = win.pitch >> 4;
+          for (int i = tid; i < win.rows * c16; i += SG_THREADS)
+          {
+            const int r = i / c16, c = i - r * c16;
+            *(uint4*)(s_dyn + r * win.pitch + c * 16) = __ldg((const uint4*)(src + (size_t)r * refs.pitch) + c);
+          }
+        }
+        __syncthreads();
+      }
+      if (tid < 32)
+      {
+        hmgpu_me_result r;
+        tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r, have_win ? s_dyn : NULL, &win);
+        if (tid == 0) s_res = r;
+      }
     }
   }
   else if (tid == 0)
@@ -84,6 +111,7 @@ me_single_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restric
     s_res = r;
   }
   __syncthreads();
+  SG_STAMP(2);
 
   // ---- fractional refinement -----------------------------------------------------------------
   if (jb.flags & HMGPU_F_FRAC)
@@ -127,20 +155,25 @@ me_single_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restric
         s_res.n_cand += 9;
       }
       __syncthreads();
+      SG_STAMP(3 + phase);
     }
   }
 
-  // ---- publish: result first, then the flag, both visible to the host --------------------------
-  if (tid < (int)(sizeof(hmgpu_me_result) / 4)) ((volatile uint32_t*)&results[blockIdx.x])[tid] = ((const uint32_t*)&s_res)[tid];
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) done_flags[blockIdx.x] = ticket;
+  // ---- publish: ONE warp-wide 32-byte store (6 result words, ticket, check word); the host validates it -------
+  if (tid < 8)
+  {
+    const uint32_t* rw = (const uint32_t*)&s_res;
+    const uint32_t v = tid < 6 ? rw[tid] : (tid == 6 ? ticket : hmgpu_mail_check(rw, ticket));
+    ((volatile uint32_t*)&slots[blockIdx.x])[tid] = v;
+  }
+  SG_STAMP(5);
+#undef SG_STAMP
 }
 
 static bool s_sg_attr_set = false;
 
-int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
-                        hmgpu_me_result* d_results, uint32_t* d_flags, uint32_t ticket, bool any_org_block, int max_win_bytes)
+int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, const int16_t* d_org_blocks,
+                        HmgpuMailSlot* d_slots, uint32_t ticket, bool any_org_block, int max_win_bytes, unsigned long long* trace)
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
@@ -153,12 +186,13 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, 
       s_sg_attr_set = true;
     }
     if (max_win_bytes > 180 * 1024) return hmgpu_fail(ctx, HMGPU_E_INVALID, "full-search window needs %d bytes of shared memory", max_win_bytes);
-    me_single_kernel<uint8_t, true><<<n_jobs, SG_THREADS, max_win_bytes, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, d_flags, ticket);
+    const int dyn = max_win_bytes > SG_WIN_BYTES ? max_win_bytes : SG_WIN_BYTES;
+    me_single_kernel<uint8_t, true><<<n_jobs, SG_THREADS, dyn, ctx->stream>>>(pack, d_org_blocks, rt, ov, d_slots, ticket, trace);
   }
   else if (ctx->px_bytes == 1)
-    me_single_kernel<uint8_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, d_flags, ticket);
+    me_single_kernel<uint8_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(pack, d_org_blocks, rt, ov, d_slots, ticket, trace);
   else
-    me_single_kernel<uint16_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, d_flags, ticket);
+    me_single_kernel<uint16_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(pack, d_org_blocks, rt, ov, d_slots, ticket, trace);
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

@@ -34,7 +34,39 @@ struct TzJob
   uint32_t ui_cost;
   int L, T, R, B;
   int bit_depth;
+  // optional copy of the reference around the start point in shared memory (fused low-latency kernel only):
+  // candidates with wx0 <= x <= wx1, wy0 <= y <= wy1 read every sample from it
+  const uint8_t* win_s; int win_pitch, wx0, wy0, wx1, wy1, win_ox, win_oy;
 };
+
+// geometry of that window, computed the same way by the threads that fill it and by the search
+struct TzWindow
+{
+  int ox, oy;          // picture-relative position (bytes / rows from the PU origin) of window byte (0,0): ox is 16-aligned in memory
+  int pitch, rows;     // bytes per staged row (multiple of 16), staged rows
+  int x0, y0, x1, y1;  // candidate range fully served by the window
+};
+#define TZ_WIN_RADIUS 6
+__device__ __forceinline__ int tz_clip_q(int v, int lo, int hi) { return min(hi, max(lo, v)); }
+// returns false when no useful window exists (start point too close to the padded border)
+__device__ __forceinline__ bool tz_window_geometry(const hmgpu_me_job& jb, const RefTable& refs, TzWindow& w)
+{
+  const int sx = tz_clip_q(jb.start_x, jb.clip_hmin, jb.clip_hmax) >> 2, sy = tz_clip_q(jb.start_y, jb.clip_vmin, jb.clip_vmax) >> 2;
+  // absolute picture coordinates of the samples needed by candidates sx-R..sx+R, sy-R..sy+R (+4 bytes funnel look-ahead)
+  int ax0 = jb.pu_x + sx - TZ_WIN_RADIUS, ax1 = jb.pu_x + sx + TZ_WIN_RADIUS + jb.pu_w + 4;
+  int ay0 = jb.pu_y + sy - TZ_WIN_RADIUS, ay1 = jb.pu_y + sy + TZ_WIN_RADIUS + jb.pu_h;
+  ax0 = max(ax0, -HMGPU_MARGIN); ay0 = max(ay0, -HMGPU_MARGIN);
+  ax1 = min(ax1, refs.pic_w + HMGPU_MARGIN); ay1 = min(ay1, refs.pic_h + HMGPU_MARGIN);
+  const int al0 = (ax0 + HMGPU_MARGIN) & ~15;               // rows start 64-byte aligned at x = -80
+  const int al1 = (ax1 + HMGPU_MARGIN + 15) & ~15;          // the row pitch has >= 32 bytes of slack
+  w.ox = al0 - HMGPU_MARGIN - jb.pu_x; w.oy = ay0 - jb.pu_y;
+  w.pitch = al1 - al0; w.rows = ay1 - ay0;
+  // candidate x reads bytes [x & ~3 (in memory), x + pu_w + 3]: inside [al0, al1) when
+  w.x0 = w.ox; w.x1 = w.ox + w.pitch - jb.pu_w - 4;
+  w.y0 = w.oy; w.y1 = w.oy + w.rows - jb.pu_h;
+  return w.x1 >= w.x0 && w.y1 >= w.y0 && w.rows > 0 && w.pitch > 0;
+}
+
 
 struct TzBest
 {
@@ -61,6 +93,7 @@ template <int GS> struct TzGroup
 // sum reaches it -- the point then loses whatever the remaining rows add, so the truncated value is
 // never selected and the result stays exact.  The far rings of the star refinement end after a
 // row or two this way.
+template <bool SMEM = false>
 __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitch, const uint32_t* org_s,
                                                     int wq, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
 {
@@ -73,10 +106,10 @@ __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitc
   {
     const uint32_t* q = q0 + (size_t)(r * row_mul) * pitch_w;
     const uint32_t* o = org_s + (r * row_mul) * wq;
-    uint32_t lo = __ldg(q);
+    uint32_t lo = SMEM ? q[0] : __ldg(q);
     for (int k = 0; k < wq; k++)
     {
-      const uint32_t hi = __ldg(q + k + 1);
+      const uint32_t hi = SMEM ? q[k + 1] : __ldg(q + k + 1);
       acc = vabsdiff4_acc(__funnelshift_r(lo, hi, sh), o[k], acc);
       lo = hi;
     }
@@ -121,7 +154,10 @@ __device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pit
     const uint64_t nb = (((uint64_t)need << shift) + ((1u << J.sub_shift) - 1u)) >> J.sub_shift;
     const uint32_t raw_bound = nb > 0xffffffffull ? 0xffffffffu : (uint32_t)nb;
     const Px* ref = ref00 + (ptrdiff_t)y * pitch + x;
-    if (PACKED)
+    if (PACKED && J.win_s && x >= J.wx0 && x <= J.wx1 && y >= J.wy0 && y <= J.wy1)
+      part = sad_rows_packed<true>(J.win_s + (y - J.win_oy) * J.win_pitch + (x - J.win_ox), J.win_pitch, (const uint32_t*)org_s, J.pu_w >> 2, J.rows,
+                                   1 << J.sub_shift, sub, lanes_per_point, raw_bound);
+    else if (PACKED)
       part = sad_rows_packed((const uint8_t*)ref, pitch, (const uint32_t*)org_s, J.pu_w >> 2, J.rows, 1 << J.sub_shift, sub, lanes_per_point, raw_bound);
     else
       part = sad_rows_generic<Px>(ref, pitch, (const int16_t*)org_s, J.pu_w, J.rows, 1 << J.sub_shift, sub, lanes_per_point, raw_bound);
@@ -247,7 +283,7 @@ __device__ __forceinline__ void tz_two_point(const TzJob& J, const Px* ref00, in
 template <typename Px, bool PACKED, int GS>
 __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
                                                 const RefTable& refs, const OrgView& org, unsigned char* s_org,
-                                                hmgpu_me_result& out)
+                                                hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL)
 {
   const int gl = TzGroup<GS>::lane();
   const uint32_t gm = TzGroup<GS>::mask();
@@ -259,6 +295,12 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
   J.pred_x = jb.pred_x; J.pred_y = jb.pred_y; J.ui_cost = jb.ui_cost;
   J.L = jb.win_l; J.T = jb.win_t; J.R = jb.win_r; J.B = jb.win_b;
   J.bit_depth = refs.bit_depth;
+  J.win_s = NULL; J.win_pitch = 0; J.wx0 = J.wy0 = 0; J.wx1 = J.wy1 = -1; J.win_ox = J.win_oy = 0;
+  if (win_s && win)
+  {
+    J.win_s = win_s; J.win_pitch = win->pitch; J.wx0 = win->x0; J.wy0 = win->y0; J.wx1 = win->x1; J.wy1 = win->y1;
+    J.win_ox = win->ox; J.win_oy = win->oy;
+  }
 
   const int pitch = refs.pitch;
   const Px* ref00 = (const Px*)refs.base[jb.ref_slot] + (ptrdiff_t)jb.pu_y * pitch + jb.pu_x;
@@ -381,7 +423,7 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
 template <typename Px, bool PACKED>
 __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
                                                const RefTable& refs, const OrgView& org, unsigned char* s_org,
-                                               hmgpu_me_result& out)
+                                               hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL)
 {
-  tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org, out);
+  tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org, out, win_s, win);
 }
