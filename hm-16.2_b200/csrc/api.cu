@@ -155,10 +155,12 @@ int hmgpu_abi_version(void) { return HMGPU_ABI_VERSION; }
 
 static_assert(sizeof(hmgpu_me_job) == 48 && sizeof(hmgpu_me_result) == 24 && sizeof(hmgpu_dist_item) == 20 &&
               sizeof(hmgpu_mc_job) == 16, "ABI struct layout changed");
-void hmgpu_struct_sizes(int out[4])
+static_assert(sizeof(hmgpu_pred_job) == 20, "ABI struct layout changed");
+void hmgpu_struct_sizes(int out[5])
 {
   out[0] = (int)sizeof(hmgpu_me_job); out[1] = (int)sizeof(hmgpu_me_result);
   out[2] = (int)sizeof(hmgpu_dist_item); out[3] = (int)sizeof(hmgpu_mc_job);
+  out[4] = (int)sizeof(hmgpu_pred_job);
 }
 
 const char* hmgpu_last_error(const hmgpu_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
@@ -328,6 +330,7 @@ int hmgpu_ref_upload(hmgpu_ctx* ctx, int slot, const int16_t* luma, int luma_str
     if ((rc = hmgpu_launch_chroma(ctx, (int16_t*)ctx->refs[slot].cr, (const int16_t*)((char*)ctx->d_stage + ybytes + cbytes), ctx->pic_w / 2))) return rc;
   }
   ctx->refs[slot].valid = true;
+  ctx->refs[slot].has_chroma = chroma;
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HMGPU_OK;
 }
@@ -341,6 +344,7 @@ int hmgpu_ref_upload_device(hmgpu_ctx* ctx, int slot, const void* d_luma, int lu
   if (rc) return rc;
   if ((rc = hmgpu_launch_planes(ctx, slot, (const int16_t*)d_luma, luma_stride))) return rc;
   ctx->refs[slot].valid = true;
+  ctx->refs[slot].has_chroma = false;
   return HMGPU_OK;
 }
 
@@ -882,6 +886,91 @@ int hmgpu_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* jobs, int n_jobs, int16_t*
   HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int16_t) * (size_t)n_dst, cudaMemcpyDeviceToHost, ctx->stream));
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(dst, hp + b0, sizeof(int16_t) * (size_t)n_dst);
+  return HMGPU_OK;
+}
+
+// PU prediction (luma + chroma, uni / bi) and prediction-error costs -------------------------------------------------
+
+static int validate_pred_jobs(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n, bool chroma, int n_dst, bool need_dst)
+{
+  for (int i = 0; i < n; i++)
+  {
+    const hmgpu_pred_job& j = jobs[i];
+    if (j.pu_w < 4 || j.pu_w > 64 || j.pu_h < 4 || j.pu_h > 64 || (j.pu_w & 3) || (j.pu_h & 3))
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: PU %dx%d unsupported", i, j.pu_w, j.pu_h);
+    if (j.pu_x < 0 || j.pu_y < 0 || j.pu_x + j.pu_w > ctx->pic_w || j.pu_y + j.pu_h > ctx->pic_h || (j.pu_x & 1) || (j.pu_y & 1))
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: PU at (%d,%d) outside the picture or odd", i, j.pu_x, j.pu_y);
+    if (j.ref_slot[0] < 0 && j.ref_slot[1] < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: no reference list used", i);
+    for (int l = 0; l < 2; l++)
+    {
+      if (j.ref_slot[l] < 0) continue;
+      if (j.ref_slot[l] >= ctx->max_refs || !ctx->refs[j.ref_slot[l]].valid)
+        return hmgpu_fail(ctx, HMGPU_E_STATE, "job %d: reference slot %d not uploaded", i, j.ref_slot[l]);
+      if (chroma && !ctx->refs[j.ref_slot[l]].has_chroma)
+        return hmgpu_fail(ctx, HMGPU_E_STATE, "job %d: reference slot %d was uploaded without chroma", i, j.ref_slot[l]);
+      // 8-tap luma support: 3 samples before, 4 after; 4-tap chroma: 1 before, 2 after
+      const int x0 = j.pu_x + (j.mv_x[l] >> 2) - 3, x1 = j.pu_x + j.pu_w + (j.mv_x[l] >> 2) + 4;
+      const int y0 = j.pu_y + (j.mv_y[l] >> 2) - 3, y1 = j.pu_y + j.pu_h + (j.mv_y[l] >> 2) + 4;
+      if (x0 < -HMGPU_MARGIN || y0 < -HMGPU_MARGIN || x1 > ctx->pic_w + HMGPU_MARGIN || y1 > ctx->pic_h + HMGPU_MARGIN)
+        return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: MV reaches outside the padded reference", i);
+      if (chroma)
+      {
+        const int cx0 = (j.pu_x >> 1) + (j.mv_x[l] >> 3) - 1, cx1 = ((j.pu_x + j.pu_w) >> 1) + (j.mv_x[l] >> 3) + 2;
+        const int cy0 = (j.pu_y >> 1) + (j.mv_y[l] >> 3) - 1, cy1 = ((j.pu_y + j.pu_h) >> 1) + (j.mv_y[l] >> 3) + 2;
+        if (cx0 < -HMGPU_CMARGIN || cy0 < -HMGPU_CMARGIN || cx1 > ctx->pic_w / 2 + HMGPU_CMARGIN || cy1 > ctx->pic_h / 2 + HMGPU_CMARGIN)
+          return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: MV reaches outside the padded chroma reference", i);
+      }
+    }
+    const size_t need = (size_t)j.pu_w * j.pu_h * (chroma ? 3 : 2) / 2;
+    if (need_dst && (size_t)j.dst_offset + need > (size_t)n_dst) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: output block outside dst", i);
+  }
+  return HMGPU_OK;
+}
+
+int hmgpu_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int with_chroma, int16_t* dst, int n_dst)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !dst || n_jobs < 0 || n_dst < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  int rc = validate_pred_jobs(ctx, jobs, n_jobs, with_chroma != 0, n_dst, true);
+  if (rc) return rc;
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b0 = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256), b1 = round_up(sizeof(int16_t) * (size_t)n_dst, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, jobs, sizeof(hmgpu_pred_job) * (size_t)n_jobs);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  HMGPU_CUDA(ctx, cudaMemsetAsync(dp + b0, 0, b1, ctx->stream));
+  if ((rc = hmgpu_launch_predict(ctx, (const hmgpu_pred_job*)dp, n_jobs, with_chroma, (int16_t*)(dp + b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int16_t) * (size_t)n_dst, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(dst, hp + b0, sizeof(int16_t) * (size_t)n_dst);
+  return HMGPU_OK;
+}
+
+int hmgpu_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int func, uint32_t* out)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !out || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  if (func != HMGPU_DF_SAD && func != HMGPU_DF_SAD_GENERIC && func != HMGPU_DF_HADS)
+    return hmgpu_fail(ctx, HMGPU_E_INVALID, "func %d: only SAD and HADS prediction errors exist in the reference", func);
+  int rc = validate_pred_jobs(ctx, jobs, n_jobs, false, 0, false);
+  if (rc) return rc;
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b0 = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256), b1 = round_up(sizeof(uint32_t) * (size_t)n_jobs, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, jobs, sizeof(hmgpu_pred_job) * (size_t)n_jobs);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_pred_error(ctx, (const hmgpu_pred_job*)dp, n_jobs, func == HMGPU_DF_HADS ? 1 : 0, (uint32_t*)(dp + b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(uint32_t) * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out, hp + b0, sizeof(uint32_t) * (size_t)n_jobs);
   return HMGPU_OK;
 }
 

@@ -31,6 +31,7 @@ struct OrgView
 struct RefSlot
 {
   bool  valid;
+  bool  has_chroma;    // cb / cr hold this picture (hmgpu_ref_upload with chroma planes)
   void* planes;        // 16 padded planes, Px elements
   void* cb;            // padded chroma planes (int16), may be null
   void* cr;
@@ -146,6 +147,8 @@ int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
 int hmgpu_launch_dist(hmgpu_ctx* ctx, const int16_t* d_org, const int16_t* d_cur,
                       const hmgpu_dist_item* d_items, int n_items, uint32_t* d_out);
 int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst);
+int hmgpu_launch_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int with_chroma, int16_t* d_dst);
+int hmgpu_launch_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int func, uint32_t* d_out);
 int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff);
 int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int qp_per, int qp_rem,
                        int is_intra, int32_t* d_level, int32_t* d_delta, uint32_t* d_abs_sum);

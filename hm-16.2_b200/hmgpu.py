@@ -34,14 +34,18 @@ DIST_ITEM = np.dtype([
 MC_JOB = np.dtype([
     ("pu_x", "<i2"), ("pu_y", "<i2"), ("pu_w", "u1"), ("pu_h", "u1"), ("ref_slot", "u1"), ("reserved", "u1"),
     ("mv_x", "<i2"), ("mv_y", "<i2"), ("dst_offset", "<u4")], align=True)
+PRED_JOB = np.dtype([
+    ("pu_x", "<i2"), ("pu_y", "<i2"), ("pu_w", "u1"), ("pu_h", "u1"), ("ref_slot", "i1", (2,)),
+    ("mv_x", "<i2", (2,)), ("mv_y", "<i2", (2,)), ("dst_offset", "<u4")], align=True)
 assert ME_JOB.itemsize == 48 and ME_RESULT.itemsize == 24 and DIST_ITEM.itemsize == 20 and MC_JOB.itemsize == 16
+assert PRED_JOB.itemsize == 20
 
 EXPORTS = [
     "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
-    "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_fwd_transform",
+    "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
@@ -93,6 +97,8 @@ def lib():
     L.hmgpu_mv_cost.argtypes = [cu] + [ci] * 5
     L.hmgpu_mv_cost.restype = cu
     L.hmgpu_mc_luma.argtypes = [vp, vp, ci, vp, ci]
+    L.hmgpu_predict.argtypes = [vp, vp, ci, ci, vp, ci]
+    L.hmgpu_pred_error.argtypes = [vp, vp, ci, ci, vp]
     L.hmgpu_fwd_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.hmgpu_profile_enable.argtypes = [vp, ci]
@@ -240,6 +246,20 @@ class Context:
         dst = np.zeros(n_dst, np.int16)
         self._check(self.L.hmgpu_mc_luma(self.h, jobs.ctypes.data, len(jobs), dst.ctypes.data, n_dst))
         return dst
+
+    def predict(self, jobs, n_dst, with_chroma=True):
+        """motionCompensation of whole PUs (Y [+ Cb, Cr], uni / bi): -> int16 array of n_dst elements"""
+        jobs = np.ascontiguousarray(jobs, PRED_JOB)
+        dst = np.zeros(n_dst, np.int16)
+        self._check(self.L.hmgpu_predict(self.h, jobs.ctypes.data, len(jobs), int(with_chroma), dst.ctypes.data, n_dst))
+        return dst
+
+    def pred_error(self, jobs, func):
+        """luma prediction error (DF_SAD / DF_HADS) of every job against the source picture"""
+        jobs = np.ascontiguousarray(jobs, PRED_JOB)
+        out = np.zeros(len(jobs), np.uint32)
+        self._check(self.L.hmgpu_pred_error(self.h, jobs.ctypes.data, len(jobs), int(func), out.ctypes.data))
+        return out
 
     def fwd_transform(self, resi, n, use_dst=False):
         resi = np.ascontiguousarray(resi, np.int16).reshape(-1, n, n)

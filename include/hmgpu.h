@@ -60,8 +60,8 @@ int  hmgpu_synchronize(hmgpu_ctx* ctx);
  * internal staging copy. */
 int  hmgpu_host_alloc(hmgpu_ctx* ctx, size_t bytes, void** out);
 int  hmgpu_host_free(hmgpu_ctx* ctx, void* p);
-/* sizeof of the four ABI structs: me_job, me_result, dist_item, mc_job (binding self-check) */
-void hmgpu_struct_sizes(int out[4]);
+/* sizeof of the ABI structs: me_job, me_result, dist_item, mc_job, pred_job (binding self-check) */
+void hmgpu_struct_sizes(int out[5]);
 
 /* Per-stage device timing (CUDA events on hmgpu_stream()).  The reference's only timer is
  * clock() (encmain.cpp:95-101, TEncGOP.cpp:646); these are what bench.py's roofline reads.
@@ -202,6 +202,31 @@ typedef struct hmgpu_mc_job
 } hmgpu_mc_job;
 
 int hmgpu_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* jobs, int n_jobs, int16_t* dst, int n_dst);
+
+/* Motion compensation of a whole PU: TComPrediction::motionCompensation -> xPredInterUni / xPredInterBi ->
+ * xPredInterBlk (TComPrediction.cpp:514-698) for luma (quarter-pel, 8 taps) and 4:2:0 chroma (eighth-pel,
+ * 4 taps; the chroma planes given to hmgpu_ref_upload), and TComYuv::addAvg (TComYuv.cpp:336-392) when both
+ * lists are used (14-bit intermediates).  A list is unused when its ref_slot is negative.  The caller
+ * applies xCheckIdenticalMotion (TComPrediction.cpp:497) itself: identical motion is submitted as list 0 only.
+ * Output of a job at dst_offset: the w x h luma block, then (with_chroma) the w/2 x h/2 Cb and Cr blocks. */
+typedef struct hmgpu_pred_job
+{
+  int16_t pu_x, pu_y;             /* luma samples, picture coordinates */
+  uint8_t pu_w, pu_h;             /* luma size, multiples of 4, 4..64 */
+  int8_t  ref_slot[2];            /* per reference list; < 0: list unused */
+  int16_t mv_x[2], mv_y[2];       /* quarter-pel luma MVs, already clipped by the caller (clipMv) */
+  uint32_t dst_offset;            /* element offset of this job's output */
+} hmgpu_pred_job;                 /* 20 bytes */
+
+int hmgpu_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int with_chroma, int16_t* dst, int n_dst);
+
+/* Prediction-error cost of luma predictions against the source picture, batched:
+ *   func = HMGPU_DF_HADS: TEncSearch::xGetInterPredictionError (TEncSearch.cpp:2952-2972), the merge-candidate
+ *          cost of xMergeEstimation (:2987-3040) -- luma MC (uni or bi) + xGetHADs;
+ *   func = HMGPU_DF_SAD_GENERIC / HMGPU_DF_SAD: the distortion of xGetTemplateCost (:3771-3811), the AMVP
+ *          candidate cost -- luma MC (uni) + SAD without sub-sampling.
+ * The double-precision calcRdCost that follows (TComRdCost.cpp:106) stays on the host.  dst_offset is ignored. */
+int hmgpu_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int func, uint32_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * Residual costing: forward core transform and scalar quantiser, batched over TUs.

@@ -29,9 +29,10 @@ def test_header_symbols_exported():
 
 
 def test_struct_layouts_match_binding():
-    out = np.zeros(4, np.int32)
+    out = np.zeros(5, np.int32)
     hmgpu.lib().hmgpu_struct_sizes(out.ctypes.data)
-    assert out.tolist() == [hmgpu.ME_JOB.itemsize, hmgpu.ME_RESULT.itemsize, hmgpu.DIST_ITEM.itemsize, hmgpu.MC_JOB.itemsize]
+    assert out.tolist() == [hmgpu.ME_JOB.itemsize, hmgpu.ME_RESULT.itemsize, hmgpu.DIST_ITEM.itemsize, hmgpu.MC_JOB.itemsize,
+                            hmgpu.PRED_JOB.itemsize]
 
 
 def test_no_cpu_fallback():
