@@ -253,12 +253,61 @@ def run_ours(args, rank, world, local_rank):
                "stage_ms_per_step": stage_ms, "roofline": roofline, "roofline_int32": roofline_int32}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=1)
+        if world == 1 and not args.no_full_search:
+            out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak)
         if world == 1 and not args.no_encode:
             out["encode"] = encode_runs()
         print(json.dumps(out))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def full_search_leg(local_rank, steps, sad4_peak):
+    """BASELINE.json configs[0] as a batch: encoder_lowdelay_P_main.cfg 416x240, FastSearch=0, SearchRange=64, 4 references --
+    every PU of one P picture against its full +-64 window (xPatternSearch), device-resident.  This is the stage whose
+    roofline is the integer pipe: algorithmic work = W*(H>>s) abs-diff-accumulates per candidate."""
+    import torch
+    import hmgpu
+    import synth
+    import worklist
+    w, h, n_refs = 416, 240, 4
+    frames = synth.luma_frames(w, h, n_refs + 2, 8, seed=99).astype(np.int16)
+    jobs = worklist.frame_jobs(w, h, n_refs=n_refs, full_search=True, search_range=64, lam=LAMBDA, frac=False,
+                               ref_dist=[n_refs + 1 - k for k in range(n_refs)])
+    ctx = hmgpu.Context(w, h, 8, n_refs, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    d_frames = torch.from_numpy(frames).cuda()
+    d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(len(jobs), -1).copy()).cuda()
+    d_res = torch.zeros((len(jobs), hmgpu.ME_RESULT.itemsize), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for s in range(n_refs):
+        ctx.ref_upload_device(s, d_frames[s].data_ptr(), w)
+    ctx.org_upload_device(d_frames[n_refs + 1].data_ptr(), w)
+    flags_any = int(np.bitwise_or.reduce(jobs["flags"]))
+    for _ in range(2):
+        ctx.me_search_device(d_jobs.data_ptr(), len(jobs), None, d_res.data_ptr(), flags_any)
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.me_search_device(d_jobs.data_ptr(), len(jobs), None, d_res.data_ptr(), flags_any)
+    e1.record(stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = d_res.cpu().numpy().view(hmgpu.ME_RESULT).reshape(-1)
+    cand = res["n_cand"].astype(np.int64)
+    pw, ph = jobs["pu_w"].astype(np.int64), jobs["pu_h"].astype(np.int64)
+    rows = np.where(ph > 8, ph // 2, ph)                       # FEN
+    px_sads = int((cand * pw * rows).sum())
+    ctx.close()
+    achieved = px_sads / 4 / (ms * 1e-3) / 1e9                 # giga VABSDIFF4-lane-ops/s that the algorithm needs
+    return {"workload": "encoder_lowdelay_P_main.cfg 416x240 FastSearch=0 SearchRange=64 FEN1, all PUs of one P picture x 4 references",
+            "jobs_per_step": int(len(jobs)), "candidates_per_step": int(cand.sum()), "ms_per_step": ms,
+            "gcand_per_s": float(cand.sum()) / (ms * 1e-3) / 1e9, "pixel_sads_per_s": px_sads / (ms * 1e-3),
+            "roofline": {"kernel": "full_search_packed_kernel", "bound": "int32 (VABSDIFF4.U8.ACC issue rate)", "achieved": achieved,
+                         "peak": sad4_peak, "unit": "G lane-op/s", "frac": achieved / sad4_peak,
+                         "peak_source": "hmgpu_microbench(1) measured in this run"}}
 
 
 def encode_runs():
@@ -365,6 +414,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=120000, help="jobs in the CPU baseline sample (1 core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the whole-encoder CPU vs GPUME runs")
+    ap.add_argument("--no-full-search", action="store_true", help="skip the full-search (BASELINE configs[0]) leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

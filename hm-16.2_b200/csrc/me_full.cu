@@ -2,7 +2,7 @@
 // (TEncSearch.cpp:3932-3989); the search itself is in me_full_impl.cuh.
 #include "me_full_impl.cuh"
 
-__global__ void __launch_bounds__(FS_THREADS)
+__global__ void __launch_bounds__(FS_THREADS, 2)
 full_search_packed_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs, RefTable refs, OrgView org,
                           hmgpu_me_result* __restrict__ results)
 {

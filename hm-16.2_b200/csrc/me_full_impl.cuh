@@ -14,8 +14,10 @@
 // VABSDIFF4.U8.ACC.  >8-bit pictures and int16 key patterns (bi-pred) take a scalar path.
 #pragma once
 #include "hmgpu_internal.cuh"
+#include <type_traits>
 
 #define FS_THREADS 256
+#define FS_YT 4            // candidate rows per work item of the packed full search
 
 __device__ __forceinline__ unsigned long long fs_block_min(unsigned long long key, unsigned long long* s_red)
 {
@@ -39,6 +41,64 @@ __device__ __forceinline__ unsigned long long fs_block_min(unsigned long long ke
     }
   }
   return key; // valid in warp 0
+}
+
+// ---- SAD of one work item of the packed full search (see full_search_block_packed) --------------------------
+struct FsItem
+{
+  const unsigned char* s_win; const uint32_t* s_org;
+  int spitch, wq, rows, rmul, cy0, g, win_h;
+};
+
+// window row u of the item (u = 0 .. rows + FS_YT - 2), word chunk [kc, kc + KC): candidate rows JLO..JHI are
+// active, candidate row j sees PU row u - j
+template <int KC, int JLO, int JHI>
+__device__ __forceinline__ void fs_step(const FsItem& it, int u, int kc, uint32_t (&acc)[FS_YT][4])
+{
+  // (clamped: rows past the window belong to candidate rows >= ny, which the caller discards)
+  const int wr = min(it.cy0 + u * it.rmul, it.win_h - 1);
+  const uint32_t* wrow = (const uint32_t*)(it.s_win + (size_t)wr * it.spitch) + it.g + kc;
+  uint32_t w[KC + 1];
+#pragma unroll
+  for (int k = 0; k <= KC; k++) w[k] = wrow[k];
+  uint32_t o[JHI - JLO + 1][KC];
+#pragma unroll
+  for (int j = JLO; j <= JHI; j++)
+  {
+    const uint32_t* orow = it.s_org + (u - j) * it.wq + kc;
+    if (KC == 4) { const uint4 q = *(const uint4*)orow; o[j - JLO][0] = q.x; o[j - JLO][1] = q.y; o[j - JLO][2] = q.z; o[j - JLO][3] = q.w; }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < KC; k++) o[j - JLO][k] = orow[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KC; k++)
+  {
+    const uint32_t v1 = __funnelshift_r(w[k], w[k + 1], 8), v2 = __funnelshift_r(w[k], w[k + 1], 16), v3 = __funnelshift_r(w[k], w[k + 1], 24);
+#pragma unroll
+    for (int j = JLO; j <= JHI; j++)
+    {
+      acc[j][0] = vabsdiff4_acc(w[k], o[j - JLO][k], acc[j][0]);
+      acc[j][1] = vabsdiff4_acc(v1, o[j - JLO][k], acc[j][1]);
+      acc[j][2] = vabsdiff4_acc(v2, o[j - JLO][k], acc[j][2]);
+      acc[j][3] = vabsdiff4_acc(v3, o[j - JLO][k], acc[j][3]);
+    }
+  }
+}
+
+template <int KC>
+__device__ __forceinline__ void fs_item_sad(const FsItem& it, uint32_t (&acc)[FS_YT][4])
+{
+  static_assert(FS_YT == 4, "the ramps below are written for 4 candidate rows");
+  for (int kc = 0; kc < it.wq; kc += KC)
+  {
+    // ramp up (rows >= 4 always), branch-free steady state with all FS_YT candidate rows active, ramp down
+    fs_step<KC, 0, 0>(it, 0, kc, acc); fs_step<KC, 0, 1>(it, 1, kc, acc); fs_step<KC, 0, 2>(it, 2, kc, acc);
+    for (int u = FS_YT - 1; u < it.rows; u++) fs_step<KC, 0, 3>(it, u, kc, acc);
+    fs_step<KC, 1, 3>(it, it.rows, kc, acc); fs_step<KC, 2, 3>(it, it.rows + 1, kc, acc); fs_step<KC, 3, 3>(it, it.rows + 2, kc, acc);
+  }
 }
 
 // ---- packed 8-bit path -------------------------------------------------------------------------
@@ -84,50 +144,68 @@ __device__ __forceinline__ void full_search_block_packed(const hmgpu_me_job& jb,
       const int r = i / wq, k = i - r * wq;
       s_org[i] = __ldg((const uint32_t*)(o + (size_t)(r * rmul) * org.pitch) + k);
     }
-    for (int i = threadIdx.x; i < win_h * rw16; i += FS_THREADS)
+    // window: 16 lanes per row (a row is 10..15 chunks of 16 bytes), 16 rows per pass of the CTA, no index division
     {
-      const int r = i / rw16, k = i - r * rw16;
-      const uint4 v = __ldg((const uint4*)(wbase + (size_t)r * pitch) + k);
-      *(uint4*)(s_win + (size_t)r * spitch + k * 16) = v;
+      const int rr = threadIdx.x >> 4, k = threadIdx.x & 15;
+      if (k < rw16)
+        for (int r = rr; r < win_h; r += FS_THREADS / 16)
+          *(uint4*)(s_win + (size_t)r * spitch + k * 16) = __ldg((const uint4*)(wbase + (size_t)r * pitch) + k);
+      for (int k2 = 16 + k; k2 < rw16; k2 += 16)             // rows wider than 256 bytes (not reached by 8..64-wide PUs at SR 64)
+        for (int r = rr; r < win_h; r += FS_THREADS / 16)
+          *(uint4*)(s_win + (size_t)r * spitch + k2 * 16) = __ldg((const uint4*)(wbase + (size_t)r * pitch) + k2);
     }
   }
   __syncthreads();
 
-  // work items: (candidate row y, aligned 4-byte column group g). group g covers window byte
-  // offsets 4g .. 4g+3, i.e. candidates x = L + 4g - mis + s, s = 0..3.
+  // Work item = FS_YT candidate rows x the 4 candidates of one aligned 32-bit column group g (window byte offsets
+  // 4g .. 4g+3, i.e. x = L + 4g - mis + s).  The FS_YT candidate rows cy0 + j*rmul of an item visit the SAME window
+  // rows (candidate row c pairs PU row r with window row c + r*rmul), so the three funnel shifts that build the
+  // byte-shifted operands of a window word are shared by FS_YT * 4 candidates: per window word 1 load + 3 SHF feed
+  // 4 * FS_YT VABSDIFF4.U8.ACC -- the ALU pipe spends 16 of 19 slots on SADs (the one-row version spent 4 of 7).
+  // The PU row is walked in chunks of KC words with KC a template parameter, so the inner loops unroll completely
+  // and every shared-memory operand is a base register + immediate.
   const int wq = W >> 2;
   const int ng = (mis + nx + 3) >> 2;
+  const int ngy = ((ny + FS_YT * rmul - 1) / (FS_YT * rmul)) * rmul;   // row groups: block b, parity p -> gy = b*rmul + p
   unsigned long long best = ~0ull;
-  for (int it = threadIdx.x; it < ny * ng; it += FS_THREADS)
+  for (int it = threadIdx.x; it < ngy * ng; it += FS_THREADS)
   {
-    const int cy = it / ng, g = it - cy * ng;
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int r = 0; r < rows; r++)
+    const int gy = it / ng, g = it - gy * ng;
+    const int cy0 = (gy / rmul) * (FS_YT * rmul) + (gy % rmul);
+    uint32_t acc[FS_YT][4];
+#pragma unroll
+    for (int j = 0; j < FS_YT; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0; }
+    const FsItem item = { s_win, s_org, spitch, wq, rows, rmul, cy0, g, win_h };
+    if ((wq & 3) == 0) fs_item_sad<4>(item, acc);
+    else if (wq == 2) fs_item_sad<2>(item, acc);
+    else if (wq == 1) fs_item_sad<1>(item, acc);
+    else fs_item_sad<3>(item, acc);                          // 12- and 24-wide AMP parts
+    // MV cost: the exp-Golomb length of a component depends on x or on y alone (TComRdCost.h:171-188)
+    uint32_t bx[4];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) bx[s4] = hm_component_bits(((L + 4 * g - mis + s4) << 2) - jb.pred_x);
+    // the 16 candidates of the item, ordered (cost, raster position): inside an item the raster order is (j, s4), so
+    // (cost << 4 | j*4 + s4) is a 32-bit key (8-bit video: cost < 2^21) and the item minimum takes 15 VIMNMX;
+    // one 64-bit (cost, raster index) key per item then joins the thread's running minimum
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < FS_YT; j++)
     {
-      const uint32_t* wrow = (const uint32_t*)(s_win + (size_t)(cy + r * rmul) * spitch) + g;
-      const uint32_t* orow = s_org + r * wq;
-      uint32_t lo = wrow[0];
-      for (int k = 0; k < wq; k++)
+      const int cy = cy0 + j * rmul;
+      const uint32_t by = hm_component_bits(((T + cy) << 2) - jb.pred_y);
+#pragma unroll
+      for (int s4 = 0; s4 < 4; s4++)
       {
-        const uint32_t hi = wrow[k + 1];
-        const uint32_t o = orow[k];
-        a0 = vabsdiff4_acc(lo, o, a0);
-        a1 = vabsdiff4_acc(__funnelshift_r(lo, hi, 8), o, a1);
-        a2 = vabsdiff4_acc(__funnelshift_r(lo, hi, 16), o, a2);
-        a3 = vabsdiff4_acc(__funnelshift_r(lo, hi, 24), o, a3);
-        lo = hi;
+        const int xi = 4 * g - mis + s4;                     // candidate index along x
+        const bool ok = cy < ny && xi >= 0 && xi < nx;
+        const uint32_t cost = hm_sad_norm(acc[j][s4], sub, 8) + ((jb.ui_cost * (bx[s4] + by)) >> 16);
+        m = min(m, ok ? ((cost << 4) | (uint32_t)(j * 4 + s4)) : 0xffffffffu);
       }
     }
-    const int y = T + cy;
-    const uint32_t acc[4] = { a0, a1, a2, a3 };
-#pragma unroll
-    for (int s = 0; s < 4; s++)
+    if (m != 0xffffffffu)
     {
-      const int xi = 4 * g - mis + s;                      // candidate index along x
-      if (xi < 0 || xi >= nx) continue;
-      const int x = L + xi;
-      const uint32_t cost = hm_sad_norm(acc[s], sub, 8) + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 2, x, y);
-      const unsigned long long key = ((unsigned long long)cost << 32) | (uint32_t)(cy * nx + xi);
+      const int j = (m >> 2) & 3, s4 = m & 3;
+      const unsigned long long key = ((unsigned long long)(m >> 4) << 32) | (uint32_t)((cy0 + j * rmul) * nx + (4 * g - mis + s4));
       best = key < best ? key : best;
     }
   }
