@@ -114,6 +114,19 @@ def algorithmic_work(jobs, results):
             "planes": (192 * plane_bytes, 17 * plane_bytes)}
 
 
+def ncu_traffic(kernel_csv):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` summary under profiles/ (written by profiles/summarize_ncu.py); None when absent."""
+    import csv
+    try:
+        rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", kernel_csv)))}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
+        return float(rd[2]) * scale[rd[1]] + float(wr[2]) * scale[wr[1]]
+    except (OSError, KeyError, ValueError, IndexError):
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import hmgpu
@@ -219,6 +232,8 @@ def run_ours(args, rank, world, local_rank):
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     total_cand = float(c[0])
 
+    seg = None if args.no_encode else encode_segment_leg(rank, world, local_rank, dist)
+
     if rank == 0:
         value = total_cand * args.steps / (dev_ms * 1e-3) / 1e9
         e2e_value = total_cand * args.steps / (e2e_ms * 1e-3) / 1e9
@@ -231,10 +246,15 @@ def run_ours(args, rank, world, local_rank):
         ops, byts = work[dom]
         dur = stage_ms[dom] * 1e-3
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic_csv = {"tz": "r1d_ncu_tz_search.csv", "frac_dist": "r1d_ncu_frac2_dist.csv"}.get(dom)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": byts / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": byts / dur / 1e9 / hbm_peak, "traffic": None,
+                    "frac": byts / dur / 1e9 / hbm_peak, "traffic": ncu_traffic(traffic_csv) if traffic_csv else None,
+                    "traffic_source": ("profiles/" + traffic_csv) if traffic_csv else None,
+                    "algorithmic_bytes_per_launch": byts,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "note": "this kernel is INT32-pipe bound, not HBM bound: see roofline_int32"}
+                    "note": "TZ is a chain of dependent rounds of ~8 points: it is bound by instruction issue and L1 wavefronts, "
+                            "not by HBM (DRAM traffic << algorithmic bytes: the planes are served by L2); see roofline_int32 "
+                            "and full_search.roofline for the integer-pipe view"}
         roofline_int32 = {"kernel": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak,
                           "unit": "Gop/s", "frac": ops / dur / 1e9 / int_peak,
                           "peak_source": "hmgpu_microbench(0) LOP3+IADD lane-ops/s measured in this run",
@@ -253,8 +273,10 @@ def run_ours(args, rank, world, local_rank):
                "stage_ms_per_step": stage_ms, "roofline": roofline, "roofline_int32": roofline_int32}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=1)
+        if seg is not None:
+            out["encode_segments"] = seg
         if world == 1 and not args.no_full_search:
-            out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak)
+            out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak, int_peak)
         if world == 1 and not args.no_encode:
             out["encode"] = encode_runs()
         print(json.dumps(out))
@@ -263,7 +285,7 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def full_search_leg(local_rank, steps, sad4_peak):
+def full_search_leg(local_rank, steps, sad4_peak, int_peak=None):
     """BASELINE.json configs[0] as a batch: encoder_lowdelay_P_main.cfg 416x240, FastSearch=0, SearchRange=64, 4 references --
     every PU of one P picture against its full +-64 window (xPatternSearch), device-resident.  This is the stage whose
     roofline is the integer pipe: algorithmic work = W*(H>>s) abs-diff-accumulates per candidate."""
@@ -305,9 +327,14 @@ def full_search_leg(local_rank, steps, sad4_peak):
     return {"workload": "encoder_lowdelay_P_main.cfg 416x240 FastSearch=0 SearchRange=64 FEN1, all PUs of one P picture x 4 references",
             "jobs_per_step": int(len(jobs)), "candidates_per_step": int(cand.sum()), "ms_per_step": ms,
             "gcand_per_s": float(cand.sum()) / (ms * 1e-3) / 1e9, "pixel_sads_per_s": px_sads / (ms * 1e-3),
-            "roofline": {"kernel": "full_search_packed_kernel", "bound": "int32 (VABSDIFF4.U8.ACC issue rate)", "achieved": achieved,
-                         "peak": sad4_peak, "unit": "G lane-op/s", "frac": achieved / sad4_peak,
-                         "peak_source": "hmgpu_microbench(1) measured in this run"}}
+            "roofline": {"kernel": "full_search_packed_kernel", "bound": "int32",
+                         # one abs-diff-accumulate per pixel-candidate, against the measured INT32 lane-op rate
+                         "achieved": px_sads / (ms * 1e-3) / 1e9, "peak": int_peak, "unit": "G int-op/s",
+                         "frac": (px_sads / (ms * 1e-3) / 1e9 / int_peak) if int_peak else None,
+                         "peak_source": "hmgpu_microbench(0): LOP3 + IMAD.IADD lane-ops/s on both integer pipes, measured in this run",
+                         # the same work as the kernel issues it: 4 pixel-candidates per VABSDIFF4.U8.ACC lane-op (ALU pipe only)
+                         "packed": {"achieved": achieved, "peak": sad4_peak, "unit": "G VABSDIFF4 lane-op/s", "frac": achieved / sad4_peak,
+                                    "peak_source": "hmgpu_microbench(1) measured in this run"}}}
 
 
 def encode_runs():
@@ -329,6 +356,43 @@ def encode_runs():
         except SystemExit as e:
             runs[name] = {"error": str(e)}
     return runs
+
+
+def encode_segment_leg(rank, world, local_rank, dist):
+    """Multi-GPU encode throughput over the natural shard: every rank encodes ITS OWN closed intra-period
+    segment (encoder_randomaccess_main.cfg, --DecodingRefreshType=2, one 16-frame IDR period, 416x240) with GPUME=1 on its
+    GPU; no exchange step.  fps = all frames / slowest rank.  Rank 0 also encodes its segment with the unmodified CPU
+    encoder (baseline leg) and compares the MD5s."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import encode_compare
+    import torch
+    if not encode_compare.available():
+        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
+    import synth
+    import tempfile
+    w, h, n = 416, 240, 16
+    tmp = tempfile.mkdtemp(prefix="hmseg_")
+    yuv = synth.write_yuv(os.path.join(tmp, "seg.yuv"), w, h, n, 8, seed=1234 + rank)
+    cfg = os.path.join(encode_compare.CFG_DIR, "encoder_randomaccess_main.cfg")
+    extra = ["--DecodingRefreshType=2", "--IntraPeriod=16"]
+    env = dict(os.environ, HMGPU_DEVICE=str(local_rank))
+    if dist is not None:
+        dist.barrier()
+    g = encode_compare.run(encode_compare.GPU_ENC, cfg, yuv, w, h, n, 32, os.path.join(tmp, "gpu"), extra + ["--GPUME=1"], env=env)
+    t = torch.tensor([g["wall_s"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        c = encode_compare.run(encode_compare.REF_ENC, cfg, yuv, w, h, n, 32, os.path.join(tmp, "cpu"), extra)
+        out = {"workload": "encoder_randomaccess_main.cfg --DecodingRefreshType=2 --IntraPeriod=16, 416x240, one 16-frame closed segment per GPU",
+               "segments": world, "frames": world * n, "gpu_fps_total": world * n / float(t[0]), "slowest_rank_s": float(t[0]),
+               "cpu_fps_one_process": n / c["wall_s"], "cpu_s": c["wall_s"],
+               "bitstream_md5_identical": c["bitstream_md5"] == g["bitstream_md5"], "recon_md5_identical": c["recon_md5"] == g["recon_md5"],
+               "gpume": g["gpume"]}
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 # ---- the reference on the host cores ------------------------------------------------------------
@@ -390,7 +454,7 @@ def run_reference(args, rank, world):
     procs = os.cpu_count() or 1
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample * procs // 4, procs=procs)
+        r = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=procs)
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
@@ -411,7 +475,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=120000, help="jobs in the CPU baseline sample (1 core)")
+    ap.add_argument("--cpu-sample", type=int, default=1200000,
+                    help="jobs of the step in the CPU baseline sample (default: the whole step, ~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the whole-encoder CPU vs GPUME runs")
     ap.add_argument("--no-full-search", action="store_true", help="skip the full-search (BASELINE configs[0]) leg")

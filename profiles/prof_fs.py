@@ -7,4 +7,4 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-print(bench.full_search_leg(0, 1, 1.0))
+print(bench.full_search_leg(0, 1, 1.0, 1.0))
