@@ -13,6 +13,12 @@
 #define TZ_SMALL_PIXELS 128                 // visited pixels (pu_w * rows) of the small class
 #define TZ_SMALL_BYTES 256                  // staged PU bytes per small job (<= 16x16)
 
+int hmgpu_launch_tz_lockstep(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, const uint32_t* d_idx, const uint32_t* d_count, uint32_t* d_cursor,
+                             int n_jobs_max, hmgpu_me_result* d_results);
+
+// class of the lock-step kernel (me_tz_lock.cu): PUs up to 16x16
+__device__ __forceinline__ bool tz_is_lockstep(const hmgpu_me_job& jb) { return jb.pu_w <= 16 && jb.pu_h <= 16; }
+
 __device__ __forceinline__ bool tz_is_small(const hmgpu_me_job& jb)
 {
   const int rows = ((jb.flags & HMGPU_F_FEN) && jb.pu_h > 8) ? jb.pu_h >> 1 : jb.pu_h;
@@ -29,7 +35,7 @@ __global__ void tz_classify_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
   if (j < n_jobs)
   {
     const hmgpu_me_job jb = jobs[j];
-    if ((jb.flags & HMGPU_F_INTEGER) && !(jb.flags & HMGPU_F_FULL)) cls = (split && tz_is_small(jb)) ? 0 : 1;
+    if ((jb.flags & HMGPU_F_INTEGER) && !(jb.flags & HMGPU_F_FULL)) cls = ((split == 1 && tz_is_small(jb)) || (split >= 2 && tz_is_lockstep(jb))) ? 0 : 1;
   }
   const int lane = threadIdx.x & 31;
   const uint32_t m0 = __ballot_sync(0xffffffffu, cls == 0), m1 = __ballot_sync(0xffffffffu, cls == 1);
@@ -90,6 +96,42 @@ tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restri
   }
 }
 
+// 8-bit pictures, one warp per job, WITH the neighbourhood of the start point staged in shared memory: the ncu capture of
+// the kernel above (profiles/r1d_ncu_tz_search*) shows 8.4 L1 sectors per load request -- every (point, row) pair is a
+// separate cache line -- so the rounds at distance 1, 2, 4 and the two-point fill (the common case) read a window that the
+// warp copied once with coalesced 16-byte loads.  ORG_BYTES / WIN_BYTES size the per-warp buffers of a PU size class.
+template <int ORG_BYTES, int WIN_BYTES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 8)
+tz_search_win_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count,
+                     RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results)
+{
+  __shared__ __align__(16) unsigned char s_org_all[WARPS][ORG_BYTES];
+  __shared__ __align__(16) unsigned char s_win_all[WARPS][WIN_BYTES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = *count;
+  for (uint32_t k = blockIdx.x * WARPS + warp; k < n; k += gridDim.x * WARPS)
+  {
+    const uint32_t job_id = idx[k];
+    const hmgpu_me_job jb = jobs[job_id];
+    TzWindow win;
+    const bool have_win = tz_window_geometry(jb, refs, win) && win.pitch * win.rows <= WIN_BYTES;
+    if (have_win)
+    {
+      const uint8_t* src = (const uint8_t*)refs.base[jb.ref_slot] + (ptrdiff_t)(jb.pu_y + win.oy) * refs.pitch + (jb.pu_x + win.ox);
+      const int c16 = win.pitch >> 4;
+      for (int i = lane; i < win.rows * c16; i += 32)
+      {
+        const int r = i / c16, c = i - r * c16;
+        *(uint4*)(s_win_all[warp] + r * win.pitch + c * 16) = __ldg((const uint4*)(src + (size_t)r * refs.pitch) + c);
+      }
+    }
+    hmgpu_me_result r;
+    tz_search_group<uint8_t, true, 32>(jb, NULL, refs, org, s_org_all[warp], r, have_win ? s_win_all[warp] : NULL, &win);   // syncs the warp after staging
+    if (lane == 0) results[job_id] = r;
+    __syncwarp();
+  }
+}
+
 int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                     hmgpu_me_result* d_results, bool any_org_block)
 {
@@ -104,16 +146,31 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   uint32_t* idx_big = (uint32_t*)((char*)ctx->d_tzlist + 256 + list_bytes);
   HMGPU_CUDA(ctx, cudaMemsetAsync(counts, 0, 16, ctx->stream));
   const bool packed = ctx->px_bytes == 1 && !any_org_block;
-  static const int s_split = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 0;   // 4-jobs-per-warp class: measured slower (3.6 vs 3.2 ms), kept for study
+  // HMGPU_TZ_SPLIT selects the mapping.  0 (default) = one warp per job for everything: 3.22 ms per 1.18 M jobs.  The
+  // alternatives are bit-exact (the parity suite passes with each) but measured SLOWER on the 1080p workload and are kept for
+  // study: 3 = one warp per job with the start neighbourhood staged in shared memory (5.46 ms: the copy costs more than the
+  // ~23 near points save); 2 = PUs up to 16x16 in the lock-step kernel of me_tz_lock.cu, four jobs per warp (4.72 ms: the
+  // phase-specific branches of its state machine serialise and every lane walks a whole SAD); 1 = the first
+  // four-jobs-per-warp attempt, tz_search_small_kernel (3.6 ms).
+  static const int s_split = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 0;
   HmgpuStage st(ctx, HMGPU_ST_TZ, packed ? 3 : 2);
-  tz_classify_kernel<<<(n_jobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, n_jobs, (packed && s_split) ? 1 : 0, idx_small, idx_big, counts);
+  tz_classify_kernel<<<(n_jobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, n_jobs, packed ? s_split : 0, idx_small, idx_big, counts);
   // persistent grids: enough CTAs to fill the machine, never more than the work could use
   const int cap = HMGPU_NUM_SMS * 16;
   const int grid_small = min(cap, (n_jobs + 15) / 16), grid_big = min(cap, (n_jobs + TZ_WARPS - 1) / TZ_WARPS);
   if (packed)
   {
-    tz_search_small_kernel<<<grid_small, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
-    tz_search_kernel<uint8_t, true><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
+    if (s_split == 3)
+    {
+      tz_search_win_kernel<256, 28 * 64, 4><<<grid_big, 4 * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
+      tz_search_win_kernel<4096, 76 * 112, 2><<<min(cap, (n_jobs + 1) / 2), 2 * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, rt, ov, d_results);
+    }
+    else
+    {
+      if (s_split == 2) { if ((rc = hmgpu_launch_tz_lockstep(ctx, d_jobs, idx_small, counts + 0, counts + 2, n_jobs, d_results))) return rc; }
+      else tz_search_small_kernel<<<grid_small, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
+      tz_search_kernel<uint8_t, true><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
+    }
   }
   else if (ctx->px_bytes == 1)
     tz_search_kernel<uint8_t, false><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
