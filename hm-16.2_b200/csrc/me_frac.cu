@@ -41,7 +41,7 @@ __global__ void frac_expand_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
       cnt = (jb.pu_w / ts) * (jb.pu_h / ts);
     }
 #pragma unroll
-    for (int c = 0; c < 9; c++) acc[(size_t)j * 9 + c] = 0;
+    for (int c = 0; c < 18; c++) acc[(size_t)c * n_jobs + j] = 0;   // both phases
   }
   // warp-aggregated reservation in the flat work list
   const int lane = threadIdx.x & 31;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128)
 frac_dist_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restrict__ org_blocks,
                  RefTable refs, OrgView org, const hmgpu_me_result* __restrict__ results,
                  const uint32_t* __restrict__ work, const uint32_t* __restrict__ work_count,
-                 uint32_t* __restrict__ acc, int phase)
+                 uint32_t* __restrict__ acc, int phase, int n_jobs)
 {
   const uint32_t n_work = *work_count;
   const uint64_t total = (uint64_t)n_work * 9u;
@@ -107,7 +107,7 @@ frac_dist_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restric
       const int ty = t / tw, tx = t - ty * tw;
       v = tile_dist<Px, 4>(jb, org_blocks, org, ref, pitch, tx * 4, ty * 4, satd);
     }
-    atomicAdd(&acc[(size_t)j * 9 + cand], v);
+    atomicAdd(&acc[(size_t)(phase * 9 + cand) * n_jobs + j], v);
   }
 }
 
@@ -120,13 +120,16 @@ __global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
   const hmgpu_me_job jb = jobs[j];
   if (!(jb.flags & HMGPU_F_FRAC)) return;
   hmgpu_me_result res = results[j];
+  // all nine sums first (independent loads in flight together), then the costs in table order
+  uint32_t d9[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) d9[c] = __ldcg(&acc[(size_t)(phase * 9 + c) * n_jobs + j]);
   uint32_t best = 0xffffffffu;
   int bi = 0;
 #pragma unroll
   for (int c = 0; c < 9; c++)
   {
-    const uint32_t dist = acc[(size_t)j * 9 + c] >> (bit_depth - 8);
-    acc[(size_t)j * 9 + c] = 0;
+    const uint32_t dist = d9[c] >> (bit_depth - 8);
     uint32_t cost;
     if (phase == 0)
       cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + c_refine_h[c][0], 2 * res.int_y + c_refine_h[c][1]);
@@ -145,8 +148,8 @@ __global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
 int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_frac)
 {
-  // scratch: acc[n_jobs*9] | work_count[1 (+3 pad)] | work[n_jobs*64]
-  const size_t acc_bytes = (size_t)n_jobs * 9 * sizeof(uint32_t);
+  // scratch: acc[2 phases][9][n_jobs] (candidate-major: coalesced in the select kernel; cleared once by the expand kernel) | work_count[1 (+3 pad)] | work[n_jobs*64]
+  const size_t acc_bytes = (size_t)n_jobs * 18 * sizeof(uint32_t);
   const size_t work_bytes = (size_t)n_jobs * 64 * sizeof(uint32_t);
   const size_t acc_al = (acc_bytes + 255) & ~(size_t)255;
   int rc = hmgpu_reserve_work(ctx, acc_al + 256 + work_bytes);
@@ -173,9 +176,9 @@ int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
       {
       HmgpuStage st(ctx, HMGPU_ST_FRAC_DIST, 1);
       if (ctx->px_bytes == 1)
-        frac_dist_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase);
+        frac_dist_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase, n_jobs);
       else
-        frac_dist_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase);
+        frac_dist_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase, n_jobs);
       }
       HmgpuStage st2(ctx, HMGPU_ST_FRAC_SELECT, 1);
       frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase);

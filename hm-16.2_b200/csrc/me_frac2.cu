@@ -116,7 +116,7 @@ __global__ void frac2_expand_kernel(const hmgpu_me_job* __restrict__ jobs, int n
       else cnt4 = (jb.pu_w >> 2) * (jb.pu_h >> 2);
     }
 #pragma unroll
-    for (int c = 0; c < 9; c++) acc[(size_t)j * 9 + c] = 0;
+    for (int c = 0; c < 18; c++) acc[(size_t)c * n_jobs + j] = 0;   // both phases
   }
   const int lane = threadIdx.x & 31;
   // warp-aggregated reservations (packed: high half = 4x4 tiles, low half = 8x8 tiles; both < 65536 per warp)
@@ -155,7 +155,7 @@ template <int TS>
 __global__ void __launch_bounds__(F2_THREADS, 4)
 frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView org,
                   const hmgpu_me_result* __restrict__ results, const uint32_t* __restrict__ work,
-                  const uint32_t* __restrict__ work_count, uint32_t* __restrict__ acc, int phase)
+                  const uint32_t* __restrict__ work_count, uint32_t* __restrict__ acc, int phase, int n_jobs)
 {
   constexpr int NW = TS / 4 + 1;                         // staged words per row segment
   constexpr int OW = TS / 4;                             // source-picture words per row (aligned)
@@ -266,7 +266,7 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
           }
         }
       }
-      if (have) atomicAdd(&acc[(size_t)j * 9 + cand], v);
+      if (have) atomicAdd(&acc[(size_t)(phase * 9 + cand) * n_jobs + j], v);
     }
   }
 }
@@ -277,8 +277,8 @@ __global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
 
 int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, hmgpu_me_result* d_results, bool any_frac)
 {
-  // scratch: acc[n_jobs*9] | counts | work8[n_jobs*64] | work4[n_jobs*64 (4x4-tiled PUs have <= 48 tiles)]
-  const size_t acc_al = ((size_t)n_jobs * 9 * sizeof(uint32_t) + 255) & ~(size_t)255;
+  // scratch: acc[2][9][n_jobs] | counts | work8[n_jobs*64] | work4[n_jobs*64 (4x4-tiled PUs have <= 48 tiles)]
+  const size_t acc_al = ((size_t)n_jobs * 18 * sizeof(uint32_t) + 255) & ~(size_t)255;
   const size_t work_bytes = (size_t)n_jobs * 64 * sizeof(uint32_t);
   int rc = hmgpu_reserve_work(ctx, acc_al + 256 + 2 * work_bytes);
   if (rc) return rc;
@@ -303,8 +303,8 @@ int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_j
     {
       {
         HmgpuStage st(ctx, HMGPU_ST_FRAC_DIST, 2);
-        frac2_dist_kernel<8><<<grid, F2_THREADS, 0, ctx->stream>>>(d_jobs, rt, ov, d_results, work8, counts + 0, acc, phase);
-        frac2_dist_kernel<4><<<grid, F2_THREADS, 0, ctx->stream>>>(d_jobs, rt, ov, d_results, work4, counts + 1, acc, phase);
+        frac2_dist_kernel<8><<<grid, F2_THREADS, 0, ctx->stream>>>(d_jobs, rt, ov, d_results, work8, counts + 0, acc, phase, n_jobs);
+        frac2_dist_kernel<4><<<grid, F2_THREADS, 0, ctx->stream>>>(d_jobs, rt, ov, d_results, work4, counts + 1, acc, phase, n_jobs);
       }
       HmgpuStage st2(ctx, HMGPU_ST_FRAC_SELECT, 1);
       frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase);
