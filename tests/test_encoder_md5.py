@@ -46,3 +46,9 @@ def test_lowdelay_b_bipred():
 
 def test_randomaccess_closed_gop():
     _compare("--cfg", "randomaccess_main", "--frames", "18", "--gpume", "1", "--", "--DecodingRefreshType=2", "--IntraPeriod=16")
+
+
+def test_randomaccess_main10_closed_gop():
+    # BASELINE cfg 5 semantics at a small size: 10-bit pictures (uint16 planes, >>2 distortion shift), SearchRange 128
+    _compare("--cfg", "randomaccess_main10", "--frames", "18", "--gpume", "2", "--bit-depth", "10", "--",
+             "--DecodingRefreshType=2", "--IntraPeriod=16", "--SearchRange=128")
