@@ -21,9 +21,14 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, co
 
 // mailbox of the low-latency path: up to MAIL_JOBS jobs per call
 #define MAIL_JOBS HMGPU_MAIL_JOBS
+int hmgpu_launch_server(hmgpu_ctx* ctx, cudaStream_t stream, const uint32_t* d_lines, const int16_t* d_org_blocks, HmgpuMailSlot* d_slots,
+                        uint32_t* d_exited, uint32_t gen, uint32_t last_ticket, unsigned long long idle_ns, int n_ctas, int dyn_bytes);
+
 struct Mailbox
 {
   HmgpuMailSlot   slots[MAIL_JOBS];
+  uint32_t        lines[HMGPU_SERVER_CTAS][16];   // host -> server: job (12 words), ticket, generation, flags, check
+  uint32_t        exited[HMGPU_SERVER_CTAS];      // server -> host: generation of the server CTA that stopped polling
   unsigned long long trace[8];          // HMGPU_TRACE: globaltimer stamps of the kernel phases
   int16_t         org_blocks[MAIL_JOBS * 64 * 64];
 };
@@ -33,6 +38,8 @@ struct Mailbox
 struct TraceAcc { double host_prep, host_launch, host_wait, host_copy, dev[5]; unsigned long long n; };
 static TraceAcc g_trace;
 static double now_us() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
+
+extern "C" { static int hmgpu_server_stop(hmgpu_ctx* ctx); }
 
 static char g_create_err[512] = "";
 
@@ -239,6 +246,10 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
     memset(&g_trace, 0, sizeof g_trace);
   }
   cudaSetDevice(ctx->device);
+  hmgpu_server_stop(ctx);
+  if (ctx->srv_stream) { cudaStreamSynchronize(ctx->srv_stream); cudaStreamDestroy(ctx->srv_stream); }
+  if (getenv("HMGPU_TRACE") || getenv("HMGPU_SERVER_STATS"))
+    fprintf(stderr, "[hmgpu server] %u calls served by %u server generations\n", ctx->srv_calls, ctx->srv_starts);
   hmgpu_use_lane(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
   {
@@ -311,6 +322,7 @@ int hmgpu_ref_upload(hmgpu_ctx* ctx, int slot, const int16_t* luma, int luma_str
   if (!ctx) return HMGPU_E_INVALID;
   if (slot < 0 || slot >= ctx->max_refs || !luma) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad slot %d or NULL luma", slot);
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   const bool chroma = cb && cr;
   int rc = ref_alloc(ctx, slot, chroma);
   if (rc) return rc;
@@ -340,6 +352,7 @@ int hmgpu_ref_upload_device(hmgpu_ctx* ctx, int slot, const void* d_luma, int lu
   if (!ctx) return HMGPU_E_INVALID;
   if (slot < 0 || slot >= ctx->max_refs || !d_luma) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad slot %d or NULL luma", slot);
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   int rc = ref_alloc(ctx, slot, false);
   if (rc) return rc;
   if ((rc = hmgpu_launch_planes(ctx, slot, (const int16_t*)d_luma, luma_stride))) return rc;
@@ -377,6 +390,7 @@ int hmgpu_org_upload(hmgpu_ctx* ctx, const int16_t* luma, int luma_stride)
 {
   if (!ctx || !luma) return HMGPU_E_INVALID;
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   const size_t ybytes = sizeof(int16_t) * (size_t)ctx->pic_w * ctx->pic_h;
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int rc;
@@ -392,6 +406,7 @@ int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride)
 {
   if (!ctx || !d_luma) return HMGPU_E_INVALID;
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   return hmgpu_launch_org(ctx, (const int16_t*)d_luma, luma_stride);
 }
 
@@ -664,6 +679,111 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
   return rc;
 }
 
+// ---- mailbox server (host side) --------------------------------------------------------------------------
+static uint32_t line_check(const uint32_t* w)
+{
+  uint32_t h = 0x7F4A7C15u;
+  for (int i = 0; i < 15; i++) h = (h ^ w[i]) * 0x85EBCA6Bu + (h >> 15);
+  return h;
+}
+
+// (re)write all lines: jobs (or no-op lines) of call `ticket` for server generation `gen`
+static void server_write_lines(Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, uint32_t ticket, uint32_t gen)
+{
+  for (int b = 0; b < HMGPU_SERVER_CTAS; b++)
+  {
+    uint32_t w[16];
+    memset(w, 0, sizeof w);
+    if (b < n_jobs) memcpy(w, &jobs[b], sizeof(hmgpu_me_job));
+    w[12] = ticket; w[13] = gen; w[14] = b < n_jobs ? 1u : 0u; w[15] = line_check(w);
+    volatile uint32_t* dst = mb->lines[b];
+    for (int i = 0; i < 16; i++) dst[i] = w[i];
+  }
+  __sync_synchronize();
+}
+
+// make the server leave (new generation in every line) and wait for it.  Called before anything that rewrites the
+// planes the server reads through the read-only path, and before work that wants the whole GPU.
+static int hmgpu_server_stop(hmgpu_ctx* ctx)
+{
+  if (!ctx->srv_alive) return HMGPU_OK;
+  Mailbox* mb = (Mailbox*)ctx->h_mail;
+  ctx->srv_gen++;
+  server_write_lines(mb, NULL, 0, ctx->mail_ticket, ctx->srv_gen);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->srv_stream));
+  ctx->srv_alive = false;
+  return HMGPU_OK;
+}
+
+static int server_start(hmgpu_ctx* ctx, Mailbox* mb, int dyn_bytes)
+{
+  static const int s_idle_us = getenv("HMGPU_SERVER_IDLE_US") ? atoi(getenv("HMGPU_SERVER_IDLE_US")) : 200;
+  if (!ctx->srv_stream) HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->srv_stream, cudaStreamNonBlocking));
+  // ordered after everything already queued on the context's stream (uploads are synchronous, this is belt and braces)
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->srv_dyn = dyn_bytes;
+  int rc = hmgpu_launch_server(ctx, ctx->srv_stream, &mb->lines[0][0], mb->org_blocks, mb->slots, mb->exited, ctx->srv_gen,
+                               ctx->mail_ticket - 1, (unsigned long long)s_idle_us * 1000ull, HMGPU_SERVER_CTAS, dyn_bytes);
+  if (rc) return rc;
+  ctx->srv_alive = true;
+  ctx->srv_starts++;
+  return HMGPU_OK;
+}
+
+static bool slot_ready(const volatile uint32_t* slot, uint32_t ticket, hmgpu_me_result* out)
+{
+  uint32_t w[8];
+  for (int k = 0; k < 8; k++) w[k] = slot[k];
+  if (w[6] != ticket || w[7] != hmgpu_mail_check(w, ticket)) return false;
+  memcpy(out, w, sizeof(hmgpu_me_result));
+  return true;
+}
+
+// one call through the resident server: write the lines, (start a generation if none is alive), poll the slots
+static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, bool any_org,
+                            const int16_t* org_blocks, int n_org_elems, int max_win, hmgpu_me_result* results)
+{
+  const int need_dyn = max_win > 10 * 1024 ? max_win : 10 * 1024;
+  int rc;
+  if (ctx->srv_alive && need_dyn > ctx->srv_dyn && (rc = hmgpu_server_stop(ctx))) return rc;
+  if (ctx->srv_alive && ((volatile uint32_t*)mb->exited)[0] == ctx->srv_gen)
+  {
+    // the server left on its own (idle): its stream is drained by the next start
+    ctx->srv_alive = false;
+    ctx->srv_gen++;
+  }
+  if (any_org) memcpy(mb->org_blocks, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+  const uint32_t ticket = ++ctx->mail_ticket;
+  server_write_lines(mb, jobs, n_jobs, ticket, ctx->srv_gen);
+  if (!ctx->srv_alive && (rc = server_start(ctx, mb, need_dyn > ctx->srv_dyn ? need_dyn : ctx->srv_dyn))) return rc;
+  ctx->srv_calls++;
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const volatile uint32_t* slot = (const volatile uint32_t*)&mb->slots[i];
+    unsigned spins = 0;
+    while (!slot_ready(slot, ticket, &results[i]))
+    {
+      if ((++spins & 63u) == 0 && ((volatile uint32_t*)mb->exited)[i] == ctx->srv_gen)
+      {
+        // this CTA stopped polling (idle exit racing with the call); anything it published is already visible
+        if (slot_ready(slot, ticket, &results[i])) break;
+        ctx->srv_alive = false;
+        ctx->srv_gen++;
+        server_write_lines(mb, jobs, n_jobs, ticket, ctx->srv_gen);
+        if ((rc = server_start(ctx, mb, ctx->srv_dyn))) return rc;
+      }
+      if (spins > 4000000u)
+      {
+        spins = 0;
+        const cudaError_t e = cudaStreamQuery(ctx->srv_stream);
+        if (e != cudaErrorNotReady && e != cudaSuccess)
+          return hmgpu_fail(ctx, HMGPU_E_CUDA, "mailbox server failed: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  return HMGPU_OK;
+}
+
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                     const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
 {
@@ -671,6 +791,7 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || !results || n_jobs < 0 || n_jobs > (1 << 26)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n_jobs > MAIL_JOBS) { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // a batch wants the whole GPU
   if (n_jobs >= PIPE_MIN_JOBS && !getenv("HMGPU_NO_PIPELINE")) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
   bool any_org, any_full, any_tz, any_frac;
   int max_win;
@@ -686,6 +807,9 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
     }
     Mailbox* mb = (Mailbox*)ctx->h_mail;
     static const bool s_trace = getenv("HMGPU_TRACE") != NULL;
+    static const bool s_server = !(getenv("HMGPU_SERVER") && atoi(getenv("HMGPU_SERVER")) == 0);
+    if (s_server && !s_trace && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024)
+      return me_search_server(ctx, mb, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win, results);
     const double t0 = s_trace ? now_us() : 0.0;
     HmgpuJobPack pack;
     memcpy(pack.jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
@@ -767,6 +891,7 @@ int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const
   if (n_jobs == 0) return HMGPU_OK;
   if (!d_jobs || !d_results || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   // jobs are not visible to the host: worst-case full-search window (SR 64, 64x64 PU)
   const bool integer = (flags_any & HMGPU_F_INTEGER) != 0, full = (flags_any & HMGPU_F_FULL) != 0;
   return hmgpu_launch_me(ctx, (const hmgpu_me_job*)d_jobs, n_jobs, (const int16_t*)d_org_blocks,

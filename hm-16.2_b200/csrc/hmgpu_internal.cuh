@@ -71,6 +71,8 @@ struct hmgpu_ctx
   void* d_scan; void* h_scan;            // per-lane verdict of the scan (device / pinned host copy)
   void* d_orgblk; size_t d_orgblk_bytes; // bi-pred key patterns of a pipelined batch
   void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
+  // mailbox server (me_server_kernel): a kernel that stays resident between calls
+  cudaStream_t srv_stream; bool srv_alive; uint32_t srv_gen; int srv_dyn; uint32_t srv_calls, srv_starts;
   uint64_t launches;
   // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
   bool prof_on;
@@ -84,6 +86,7 @@ struct hmgpu_ctx
 
 // ---- low-latency path (me_single.cu): mapped pinned mailbox --------------------------------------
 #define HMGPU_MAIL_JOBS 32
+#define HMGPU_SERVER_CTAS 16     // CTAs of the mailbox server = jobs it takes per call
 // the jobs of one call travel as a kernel parameter (no PCIe read on the device side)
 struct HmgpuJobPack { hmgpu_me_job jobs[HMGPU_MAIL_JOBS]; };
 // One result slot = 32 bytes written by ONE warp-wide store of 8 consecutive words, so it crosses PCIe as a

@@ -249,7 +249,7 @@ __device__ __forceinline__ void full_search_block_generic(const hmgpu_me_job& jb
   if (jb.flags & HMGPU_F_ORG_BLOCK)
   {
     const int16_t* o = org_blocks + jb.org_offset;
-    for (int i = threadIdx.x; i < W * H; i += FS_THREADS) s_org[i] = o[i];
+    for (int i = threadIdx.x; i < W * H; i += FS_THREADS) s_org[i] = __ldcv(o + i);   // see me_tz_impl.cuh: may be rewritten host memory
   }
   else
   {

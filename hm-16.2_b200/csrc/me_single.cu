@@ -46,38 +46,46 @@ __device__ __forceinline__ void sg_frac_phase(const hmgpu_me_job& jb, const int1
 
 #define SG_WIN_BYTES (10 * 1024)   // staged TZ window: <= (64 + 12) rows x <= 112 bytes
 
-template <typename Px, bool PACKED>
-__global__ void __launch_bounds__(SG_THREADS)
-me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
-                 HmgpuMailSlot* slots, uint32_t ticket, unsigned long long* trace)
+// shared-memory scratch of one job (static part; s_dyn is the CTA's dynamic shared memory)
+struct SgShared
 {
-  // optional phase trace (HMGPU_TRACE=1): globaltimer stamps of block 0, read by the host after the call
-#define SG_STAMP(k) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); trace[k] = t_; } } while (0)
-  SG_STAMP(0);
-  extern __shared__ __align__(16) unsigned char s_dyn[];       // packed full-search window, or the staged TZ window
-  __shared__ __align__(16) unsigned char s_org[8192];          // PU block: packed bytes or int16
-  __shared__ unsigned long long s_red[SG_THREADS / 32];
-  __shared__ hmgpu_me_result s_res;
-  __shared__ uint32_t s_acc[9];
+  unsigned long long red[SG_THREADS / 32];
+  hmgpu_me_result res;
+  uint32_t acc[9];
+};
 
+// optional phase trace (HMGPU_TRACE=1): globaltimer stamps of block 0, read by the host after the call
+__device__ __forceinline__ void sg_stamp(unsigned long long* trace, int k)
+{
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[k] = t;
+  }
+}
+
+// One xMotionEstimation body by the whole CTA: integer search (TZ by warp 0 out of a staged window, or the block-wide full
+// search), both fractional phases.  The result is left in sh.res (valid after the final barrier).
+template <typename Px, bool PACKED>
+__device__ __forceinline__ void sg_job(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks, const RefTable& refs, const OrgView& org,
+                                       unsigned char* s_dyn, unsigned char* s_org, SgShared& sh, unsigned long long* trace)
+{
   const int tid = threadIdx.x;
-  const hmgpu_me_job jb = pack.jobs[blockIdx.x];               // kernel parameter: no PCIe read
-  SG_STAMP(1);
-
   // ---- integer search --------------------------------------------------------------------
   if (jb.flags & HMGPU_F_INTEGER)
   {
     if (jb.flags & HMGPU_F_FULL)
     {
-      if (PACKED) full_search_block_packed(jb, refs, org, s_dyn, s_red, &s_res);
-      else full_search_block_generic<Px>(jb, org_blocks, refs, org, (int16_t*)s_org, s_red, &s_res);
+      if (PACKED) full_search_block_packed(jb, refs, org, s_dyn, sh.red, &sh.res);
+      else full_search_block_generic<Px>(jb, org_blocks, refs, org, (int16_t*)s_org, sh.red, &sh.res);
     }
     else
     {
       // TZ is a chain of dependent rounds executed by warp 0.  Every round that reads the reference from global
-      // memory pays a full memory round trip (~0.6 us, measured with HMGPU_TRACE), so the whole CTA first copies
-      // the neighbourhood of the start point into shared memory -- one round trip -- and the rounds within
-      // TZ_WIN_RADIUS of it (the common case: distances 1, 2, 4 and the two-point fill) run out of it.
+      // memory pays a full memory round trip, so the whole CTA first copies the neighbourhood of the start point
+      // into shared memory -- one round trip -- and the rounds within TZ_WIN_RADIUS of it (the common case:
+      // distances 1, 2, 4 and the two-point fill) run out of it.
       TzWindow win;
       bool have_win = false;
       if (PACKED)
@@ -99,7 +107,7 @@ me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __res
       {
         hmgpu_me_result r;
         tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r, have_win ? s_dyn : NULL, &win);
-        if (tid == 0) s_res = r;
+        if (tid == 0) sh.res = r;
       }
     }
   }
@@ -108,10 +116,10 @@ me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __res
     hmgpu_me_result r;
     r.int_x = jb.start_x; r.int_y = jb.start_y; r.int_sad = 0;
     r.half_x = r.half_y = r.qter_x = r.qter_y = 0; r.frac_cost = 0; r.n_cand = 0;
-    s_res = r;
+    sh.res = r;
   }
   __syncthreads();
-  SG_STAMP(2);
+  sg_stamp(trace, 2);
 
   // ---- fractional refinement -----------------------------------------------------------------
   if (jb.flags & HMGPU_F_FRAC)
@@ -122,17 +130,17 @@ me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __res
       // stage the int16 key pattern once (it lives in mapped host memory): tile_dist then reads
       // shared memory through a rebased pointer
       int16_t* so = (int16_t*)s_org;
-      for (int i = tid; i < jb.pu_w * jb.pu_h; i += SG_THREADS) so[i] = org_blocks[jb.org_offset + i];
+      for (int i = tid; i < jb.pu_w * jb.pu_h; i += SG_THREADS) so[i] = __ldcv(org_blocks + jb.org_offset + i);
       key = so - jb.org_offset;
     }
     const int bit_depth = refs.bit_depth;
     for (int phase = 0; phase < 2; phase++)
     {
-      if (tid < 9) s_acc[tid] = 0;
+      if (tid < 9) sh.acc[tid] = 0;
       __syncthreads();
-      const hmgpu_me_result res = s_res;
-      if (job_tile_size(jb) == 8) sg_frac_phase<Px, 8>(jb, key, refs, org, res, phase, s_acc);
-      else sg_frac_phase<Px, 4>(jb, key, refs, org, res, phase, s_acc);
+      const hmgpu_me_result res = sh.res;
+      if (job_tile_size(jb) == 8) sg_frac_phase<Px, 8>(jb, key, refs, org, res, phase, sh.acc);
+      else sg_frac_phase<Px, 4>(jb, key, refs, org, res, phase, sh.acc);
       __syncthreads();
       if (tid == 0)
       {
@@ -140,7 +148,7 @@ me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __res
         int bi = 0;
         for (int c = 0; c < 9; c++)
         {
-          const uint32_t dist = s_acc[c] >> (bit_depth - 8);
+          const uint32_t dist = sh.acc[c] >> (bit_depth - 8);
           uint32_t cost;
           if (phase == 0)
             cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + c_refine_h[c][0], 2 * res.int_y + c_refine_h[c][1]);
@@ -149,25 +157,115 @@ me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __res
                                      4 * res.int_y + 2 * res.half_y + c_refine_q[c][1]);
           if (cost < best) { best = cost; bi = c; }
         }
-        if (phase == 0) { s_res.half_x = c_refine_h[bi][0]; s_res.half_y = c_refine_h[bi][1]; }
-        else { s_res.qter_x = c_refine_q[bi][0]; s_res.qter_y = c_refine_q[bi][1]; }
-        s_res.frac_cost = best;
-        s_res.n_cand += 9;
+        if (phase == 0) { sh.res.half_x = c_refine_h[bi][0]; sh.res.half_y = c_refine_h[bi][1]; }
+        else { sh.res.qter_x = c_refine_q[bi][0]; sh.res.qter_y = c_refine_q[bi][1]; }
+        sh.res.frac_cost = best;
+        sh.res.n_cand += 9;
       }
       __syncthreads();
-      SG_STAMP(3 + phase);
+      sg_stamp(trace, 3 + phase);
     }
   }
+}
 
-  // ---- publish: ONE warp-wide 32-byte store (6 result words, ticket, check word); the host validates it -------
+// publish: ONE warp-wide 32-byte store (6 result words, ticket, check word); the host validates it
+__device__ __forceinline__ void sg_publish(const hmgpu_me_result& res, HmgpuMailSlot* slot, uint32_t ticket)
+{
+  const int tid = threadIdx.x;
   if (tid < 8)
   {
-    const uint32_t* rw = (const uint32_t*)&s_res;
+    const uint32_t* rw = (const uint32_t*)&res;
     const uint32_t v = tid < 6 ? rw[tid] : (tid == 6 ? ticket : hmgpu_mail_check(rw, ticket));
-    ((volatile uint32_t*)&slots[blockIdx.x])[tid] = v;
+    ((volatile uint32_t*)slot)[tid] = v;
   }
-  SG_STAMP(5);
-#undef SG_STAMP
+}
+
+template <typename Px, bool PACKED>
+__global__ void __launch_bounds__(SG_THREADS)
+me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
+                 HmgpuMailSlot* slots, uint32_t ticket, unsigned long long* trace)
+{
+  sg_stamp(trace, 0);
+  extern __shared__ __align__(16) unsigned char s_dyn[];       // packed full-search window, or the staged TZ window
+  __shared__ __align__(16) unsigned char s_org[8192];          // PU block: packed bytes or int16
+  __shared__ SgShared sh;
+  const hmgpu_me_job jb = pack.jobs[blockIdx.x];               // kernel parameter: no PCIe read
+  sg_stamp(trace, 1);
+  sg_job<Px, PACKED>(jb, org_blocks, refs, org, s_dyn, s_org, sh, trace);
+  sg_publish(sh.res, &slots[blockIdx.x], ticket);
+  sg_stamp(trace, 5);
+}
+
+// ---- the mailbox server: a kernel that stays resident between calls --------------------------------------------------
+// CTA b polls line b of the mailbox (64 bytes of mapped pinned host memory: the job, the ticket, the server generation and
+// a check word, fetched with ONE 64-byte read).  A new valid ticket = a new call: the CTA runs the job and publishes slot b.
+// The host writes every line on every call (CTAs without a job get a no-op line), so all CTAs see all tickets and their
+// idle clocks run together.  A CTA leaves when its line names another generation (the host stopped the server: before every
+// picture upload, so the planes are read-only for the life of a server and __ldg stays valid) or when it has been idle for
+// idle_ns -- it then reports exited[b] = generation AFTER its last poll, so the host can tell "will never answer" from
+// "still working" and start a new generation for the pending call.
+template <typename Px>
+__global__ void __launch_bounds__(SG_THREADS)
+me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
+                 HmgpuMailSlot* slots, volatile uint32_t* exited, uint32_t gen, uint32_t last_ticket, unsigned long long idle_ns,
+                 int packed_ok)
+{
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ __align__(16) unsigned char s_org[8192];
+  __shared__ SgShared sh;
+  __shared__ uint32_t s_line[16];
+  __shared__ int s_cmd;                                        // 0 keep polling, 1 run the job in s_line, 2 leave
+  const int tid = threadIdx.x;
+  const volatile uint32_t* line = lines + blockIdx.x * 16;
+  unsigned long long t_last = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+  for (;;)
+  {
+    if (tid < 32)
+    {
+      // one 64-byte read of the line by lanes 0..15, validated by its check word
+      uint32_t w = tid < 16 ? line[tid] : 0u;
+      uint32_t h = 0x7F4A7C15u;
+#pragma unroll
+      for (int i = 0; i < 15; i++) h = (h ^ __shfl_sync(0xffffffffu, w, i)) * 0x85EBCA6Bu + (h >> 15);
+      const uint32_t chk = __shfl_sync(0xffffffffu, w, 15), tk = __shfl_sync(0xffffffffu, w, 12), gn = __shfl_sync(0xffffffffu, w, 13);
+      int cmd = 0;
+      if (h == chk)
+      {
+        if (gn != gen) cmd = 2;
+        else if (tk != last_ticket) cmd = 1;
+      }
+      if (tid == 0 && cmd == 0)
+      {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t_last > idle_ns) cmd = 2;
+      }
+      cmd = __shfl_sync(0xffffffffu, cmd, 0) == 2 ? 2 : cmd;    // lane 0 alone watches the clock
+      if (cmd == 1 && tid < 16) s_line[tid] = w;
+      if (tid == 0) s_cmd = cmd;
+    }
+    __syncthreads();
+    const int cmd = s_cmd;
+    if (cmd == 2) break;
+    if (cmd == 1)
+    {
+      last_ticket = s_line[12];
+      if (s_line[14] & 1u)                                     // this CTA has a job in this call
+      {
+        hmgpu_me_job jb;
+#pragma unroll
+        for (int i = 0; i < 12; i++) ((uint32_t*)&jb)[i] = s_line[i];
+        if (packed_ok && !(jb.flags & HMGPU_F_ORG_BLOCK)) sg_job<uint8_t, true>(jb, org_blocks, refs, org, s_dyn, s_org, sh, NULL);
+        else sg_job<Px, false>(jb, org_blocks, refs, org, s_dyn, s_org, sh, NULL);
+        sg_publish(sh.res, &slots[blockIdx.x], last_ticket);
+      }
+      if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+    }
+    __syncthreads();                                           // s_cmd / s_line are rewritten by the next poll
+  }
+  // only after the last poll: the host may now assume this CTA will not answer
+  if (tid == 0) exited[blockIdx.x] = gen;
 }
 
 static bool s_sg_attr_set = false;
@@ -193,6 +291,29 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, co
     me_single_kernel<uint8_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(pack, d_org_blocks, rt, ov, d_slots, ticket, trace);
   else
     me_single_kernel<uint16_t, false><<<n_jobs, SG_THREADS, 0, ctx->stream>>>(pack, d_org_blocks, rt, ov, d_slots, ticket, trace);
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}
+
+static bool s_srv_attr_set = false;
+
+// start a server generation: n_ctas CTAs, dyn_bytes of dynamic shared memory each
+int hmgpu_launch_server(hmgpu_ctx* ctx, cudaStream_t stream, const uint32_t* d_lines, const int16_t* d_org_blocks, HmgpuMailSlot* d_slots,
+                        uint32_t* d_exited, uint32_t gen, uint32_t last_ticket, unsigned long long idle_ns, int n_ctas, int dyn_bytes)
+{
+  const RefTable rt = hmgpu_ref_table(ctx);
+  OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  if (!s_srv_attr_set)
+  {
+    HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_server_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_server_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    s_srv_attr_set = true;
+  }
+  ctx->launches += 1; ctx->prof_launches[HMGPU_ST_SINGLE] += 1;
+  if (ctx->px_bytes == 1)
+    me_server_kernel<uint8_t><<<n_ctas, SG_THREADS, dyn_bytes, stream>>>(d_lines, d_org_blocks, rt, ov, d_slots, d_exited, gen, last_ticket, idle_ns, 1);
+  else
+    me_server_kernel<uint16_t><<<n_ctas, SG_THREADS, dyn_bytes, stream>>>(d_lines, d_org_blocks, rt, ov, d_slots, d_exited, gen, last_ticket, idle_ns, 0);
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

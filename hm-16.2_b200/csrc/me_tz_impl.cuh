@@ -322,8 +322,10 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
     int16_t* so = (int16_t*)s_org;
     if (jb.flags & HMGPU_F_ORG_BLOCK)
     {
+      // key patterns may live in mapped host memory that a resident server kernel sees rewritten call after call:
+      // ld.cv (never served from a stale cache line)
       const int16_t* o = org_blocks + jb.org_offset;
-      for (int i = gl; i < J.pu_h * J.pu_w; i += GS) so[i] = o[i];
+      for (int i = gl; i < J.pu_h * J.pu_w; i += GS) so[i] = __ldcv(o + i);
     }
     else
     {
