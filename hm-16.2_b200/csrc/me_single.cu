@@ -52,6 +52,7 @@ struct SgShared
   unsigned long long red[SG_THREADS / 32];
   hmgpu_me_result res;
   uint32_t acc[9];
+  TzSpec spec;
 };
 
 // optional phase trace (HMGPU_TRACE=1): globaltimer stamps of block 0, read by the host after the call
@@ -101,12 +102,14 @@ __device__ __forceinline__ void sg_job(const hmgpu_me_job& jb, const int16_t* __
             *(uint4*)(s_dyn + r * win.pitch + c * 16) = __ldg((const uint4*)(src + (size_t)r * refs.pitch) + c);
           }
         }
-        __syncthreads();
       }
-      if (tid < 32)
+      // the key pattern with all threads, then the search by warps 0..2 (speculative first rounds, see TzSpec)
+      tz_stage_org<Px, PACKED>(jb, org_blocks, org, s_org, tid, SG_THREADS);
+      __syncthreads();
+      if (tid < 96)
       {
         hmgpu_me_result r;
-        tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r, have_win ? s_dyn : NULL, &win);
+        tz_search_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r, have_win ? s_dyn : NULL, &win, &sh.spec, tid >> 5);
         if (tid == 0) sh.res = r;
       }
     }
@@ -142,25 +145,27 @@ __device__ __forceinline__ void sg_job(const hmgpu_me_job& jb, const int16_t* __
       if (job_tile_size(jb) == 8) sg_frac_phase<Px, 8>(jb, key, refs, org, res, phase, sh.acc);
       else sg_frac_phase<Px, 4>(jb, key, refs, org, res, phase, sh.acc);
       __syncthreads();
-      if (tid == 0)
+      if (tid < 32)
       {
-        uint32_t best = 0xffffffffu;
-        int bi = 0;
-        for (int c = 0; c < 9; c++)
+        // first strict minimum in table order (TEncSearch.cpp:816-847): lane c costs candidate c, (cost, c) minimum
+        const int c = tid < 9 ? tid : 0;
+        const uint32_t dist = sh.acc[c] >> (bit_depth - 8);
+        uint32_t cost;
+        if (phase == 0)
+          cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + c_refine_h[c][0], 2 * res.int_y + c_refine_h[c][1]);
+        else
+          cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 0, 4 * res.int_x + 2 * res.half_x + c_refine_q[c][0],
+                                   4 * res.int_y + 2 * res.half_y + c_refine_q[c][1]);
+        if (tid >= 9) cost = 0xffffffffu;
+        const uint32_t best = __reduce_min_sync(0xffffffffu, cost);
+        const int bi = __ffs(__ballot_sync(0xffffffffu, cost == best && tid < 9)) - 1;
+        if (tid == 0)
         {
-          const uint32_t dist = sh.acc[c] >> (bit_depth - 8);
-          uint32_t cost;
-          if (phase == 0)
-            cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + c_refine_h[c][0], 2 * res.int_y + c_refine_h[c][1]);
-          else
-            cost = dist + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 0, 4 * res.int_x + 2 * res.half_x + c_refine_q[c][0],
-                                     4 * res.int_y + 2 * res.half_y + c_refine_q[c][1]);
-          if (cost < best) { best = cost; bi = c; }
+          if (phase == 0) { sh.res.half_x = c_refine_h[bi][0]; sh.res.half_y = c_refine_h[bi][1]; }
+          else { sh.res.qter_x = c_refine_q[bi][0]; sh.res.qter_y = c_refine_q[bi][1]; }
+          sh.res.frac_cost = best;
+          sh.res.n_cand += 9;
         }
-        if (phase == 0) { sh.res.half_x = c_refine_h[bi][0]; sh.res.half_y = c_refine_h[bi][1]; }
-        else { sh.res.qter_x = c_refine_q[bi][0]; sh.res.qter_y = c_refine_q[bi][1]; }
-        sh.res.frac_cost = best;
-        sh.res.n_cand += 9;
       }
       __syncthreads();
       sg_stamp(trace, 3 + phase);

@@ -276,6 +276,51 @@ __device__ __forceinline__ void tz_two_point(const TzJob& J, const Px* ref00, in
   tz_eval<Px, PACKED, GS>(J, ref00, pitch, org_s, lpp, x, y, valid, 0, 2, best);
 }
 
+// stage the key pattern of a job into shared memory: packed bytes (PACKED) or int16; executed by `nthr` threads, this one is `t`
+template <typename Px, bool PACKED>
+__device__ __forceinline__ void tz_stage_org(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks, const OrgView& org,
+                                             unsigned char* s_org, int t, int nthr)
+{
+  if (PACKED)
+  {
+    const int wq = jb.pu_w >> 2;
+    const uint8_t* o = (const uint8_t*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
+    uint32_t* so = (uint32_t*)s_org;
+    for (int i = t; i < jb.pu_h * wq; i += nthr)
+    {
+      const int r = i / wq, k = i - r * wq;
+      so[i] = __ldg((const uint32_t*)(o + (size_t)r * org.pitch) + k);   // pu_x % 4 == 0, pitch % 4 == 0
+    }
+  }
+  else
+  {
+    int16_t* so = (int16_t*)s_org;
+    if (jb.flags & HMGPU_F_ORG_BLOCK)
+    {
+      // key patterns may live in mapped host memory that a resident server kernel sees rewritten call after call:
+      // ld.cv (never served from a stale cache line)
+      const int16_t* o = org_blocks + jb.org_offset;
+      for (int i = t; i < jb.pu_h * jb.pu_w; i += nthr) so[i] = __ldcv(o + i);
+    }
+    else
+    {
+      const Px* o = (const Px*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
+      for (int i = t; i < jb.pu_h * jb.pu_w; i += nthr)
+      {
+        const int r = i / jb.pu_w, k = i - r * jb.pu_w;
+        so[i] = (int16_t)o[(size_t)r * org.pitch + k];
+      }
+    }
+  }
+}
+
+// Speculative first rounds (fused low-latency kernel only): the diamonds at distance 1, 2, 4 of the first search all sit
+// around the SAME centre (the best start point), so three warps evaluate them at once and warp 0 replays the reference's
+// sequential bookkeeping on their results.  A round reports its minimum only if it beats the best start point; whether it
+// also beats what the earlier rounds found is decided in the replay -- exactly the strict-'<' scan of the reference.
+struct TzSpecRound { uint32_t cost; int x, y, dist, pnr; uint32_t n_valid; };
+struct TzSpec { TzSpecRound r[3]; };
+
 // The whole TZ search of one job, executed by ONE GROUP of GS lanes (all of them call it together).
 // s_org: per-group shared memory for the PU block: pu_w*pu_h bytes (PACKED) or 2*pu_w*pu_h (int16).
 // The first lane of the group returns the result in `out` (integer MV, SAD without MV cost,
@@ -283,7 +328,8 @@ __device__ __forceinline__ void tz_two_point(const TzJob& J, const Px* ref00, in
 template <typename Px, bool PACKED, int GS>
 __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
                                                 const RefTable& refs, const OrgView& org, unsigned char* s_org,
-                                                hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL)
+                                                hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL,
+                                                TzSpec* spec = NULL, int role = 0)
 {
   const int gl = TzGroup<GS>::lane();
   const uint32_t gm = TzGroup<GS>::mask();
@@ -305,38 +351,8 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
   const int pitch = refs.pitch;
   const Px* ref00 = (const Px*)refs.base[jb.ref_slot] + (ptrdiff_t)jb.pu_y * pitch + jb.pu_x;
 
-  // ---- stage the key pattern -------------------------------------------------------------
-  if (PACKED)
-  {
-    const int wq = J.pu_w >> 2;
-    const uint8_t* o = (const uint8_t*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
-    uint32_t* so = (uint32_t*)s_org;
-    for (int i = gl; i < J.pu_h * wq; i += GS)
-    {
-      const int r = i / wq, k = i - r * wq;
-      so[i] = __ldg((const uint32_t*)(o + (size_t)r * org.pitch) + k);   // pu_x % 4 == 0, pitch % 4 == 0
-    }
-  }
-  else
-  {
-    int16_t* so = (int16_t*)s_org;
-    if (jb.flags & HMGPU_F_ORG_BLOCK)
-    {
-      // key patterns may live in mapped host memory that a resident server kernel sees rewritten call after call:
-      // ld.cv (never served from a stale cache line)
-      const int16_t* o = org_blocks + jb.org_offset;
-      for (int i = gl; i < J.pu_h * J.pu_w; i += GS) so[i] = __ldcv(o + i);
-    }
-    else
-    {
-      const Px* o = (const Px*)org.base + (size_t)jb.pu_y * org.pitch + jb.pu_x;
-      for (int i = gl; i < J.pu_h * J.pu_w; i += GS)
-      {
-        const int r = i / J.pu_w, k = i - r * J.pu_w;
-        so[i] = (int16_t)o[(size_t)r * org.pitch + k];
-      }
-    }
-  }
+  // ---- stage the key pattern (unless the caller did it with more threads) ---------------------
+  if (!spec) tz_stage_org<Px, PACKED>(jb, org_blocks, org, s_org, gl, GS);
   __syncwarp(gm);
 
   TzBest best; best.cost = 0xffffffffu; best.x = 0; best.y = 0; best.dist = 0; best.round = 0; best.pnr = 0; best.n_cand = 0;
@@ -376,7 +392,35 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
 
   // ---- first search: diamonds at distance 1,2,4,.. ; stop 3 rounds after the last improvement
   int cx = best.x, cy = best.y;
-  for (int d = 1; d <= jb.search_range; d <<= 1)
+  int d0 = 1;
+  if (spec)
+  {
+    // warps `role` = 0, 1, 2 of the CTA run this function together (same job, same start evaluation)
+    if (jb.search_range < 4) { if (role != 0) return; }
+    else
+    {
+      TzBest b2 = best;
+      tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, 1 << role, b2);
+      if (gl == 0)
+      {
+        TzSpecRound rr;
+        rr.cost = b2.cost < best.cost ? b2.cost : 0xffffffffu;
+        rr.x = b2.x; rr.y = b2.y; rr.dist = b2.dist; rr.pnr = b2.pnr; rr.n_valid = b2.n_cand - best.n_cand;
+        spec->r[role] = rr;
+      }
+      asm volatile("bar.sync 1, 96;" ::: "memory");         // the three role warps
+      if (role != 0) return;
+      for (int w = 0; w < 3; w++)                           // replay: rounds d = 1, 2, 4 in order
+      {
+        const TzSpecRound rr = spec->r[w];
+        best.round += 1;
+        best.n_cand += rr.n_valid;
+        if (rr.cost < best.cost) { best.cost = rr.cost; best.x = rr.x; best.y = rr.y; best.dist = rr.dist; best.pnr = rr.pnr; best.round = 0; }
+      }
+      d0 = best.round >= 3 ? jb.search_range + 1 : 8;       // the reference stops 3 rounds after the last improvement
+    }
+  }
+  for (int d = d0; d <= jb.search_range; d <<= 1)
   {
     tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, d, best);
     if (best.round >= 3) break;
@@ -425,7 +469,8 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
 template <typename Px, bool PACKED>
 __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
                                                const RefTable& refs, const OrgView& org, unsigned char* s_org,
-                                               hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL)
+                                               hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL,
+                                               TzSpec* spec = NULL, int role = 0)
 {
-  tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org, out, win_s, win);
+  tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org, out, win_s, win, spec, role);
 }
