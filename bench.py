@@ -347,7 +347,7 @@ def encode_runs():
         return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
     runs = {}
     for name, a in (("cfg1_lowdelay_P_fullsearch_SR64_416x240_3f", ("lowdelay_P_main", "416x240", 3, 32, 1, ["--FastSearch=0", "--SearchRange=64"])),
-                    ("cfg2_lowdelay_P_TZ_1920x1080_2f", ("lowdelay_P_main", "1920x1080", 2, 32, 1, []))):
+                    ("cfg2_lowdelay_P_TZ_1920x1080_4f", ("lowdelay_P_main", "1920x1080", 4, 32, 1, []))):
         try:
             r = encode_compare.compare(*a)
             runs[name] = {"cpu_fps": r["cpu"]["fps"], "gpu_fps": r["gpu"]["fps"], "cpu_s": r["cpu"]["wall_s"], "gpu_s": r["gpu"]["wall_s"],

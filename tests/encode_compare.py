@@ -64,10 +64,15 @@ def compare(cfg_name, size, frames, qp, gpume=1, extra=(), bit_depth=8, skip_cpu
     tmp = tempfile.mkdtemp(prefix="hmenc_")
     yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), w, h, frames, bit_depth)
     out = {"cfg": cfg_name, "size": size, "frames": frames, "qp": qp, "extra": extra}
-    if not skip_cpu:
-        out["cpu"] = run(REF_ENC, cfg, yuv, w, h, frames, qp, os.path.join(tmp, "cpu"), extra, bit_depth)
-        out["cpu"]["fps"] = frames / out["cpu"]["wall_s"]
-    out["gpu"] = run(GPU_ENC, cfg, yuv, w, h, frames, qp, os.path.join(tmp, "gpu"), extra + ["--GPUME=%d" % gpume], bit_depth)
+    # the two encoders are single-threaded: they run side by side on different cores
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as pool:
+        fc = None if skip_cpu else pool.submit(run, REF_ENC, cfg, yuv, w, h, frames, qp, os.path.join(tmp, "cpu"), extra, bit_depth)
+        fg = pool.submit(run, GPU_ENC, cfg, yuv, w, h, frames, qp, os.path.join(tmp, "gpu"), extra + ["--GPUME=%d" % gpume], bit_depth)
+        if fc is not None:
+            out["cpu"] = fc.result()
+            out["cpu"]["fps"] = frames / out["cpu"]["wall_s"]
+        out["gpu"] = fg.result()
     out["gpu"]["fps"] = frames / out["gpu"]["wall_s"]
     if "cpu" in out:
         out["bitstream_identical"] = out["cpu"]["bitstream_md5"] == out["gpu"]["bitstream_md5"]
