@@ -44,6 +44,28 @@ __device__ __forceinline__ void sg_frac_phase(const hmgpu_me_job& jb, const int1
   }
 }
 
+// Small PUs: the distortion of ALL 49 quarter-pel positions (-3..3)^2 around the integer MV in one pass -- every position the
+// half-pel stage or any quarter-pel stage can ask for -- so the two dependent refinement stages become two table look-ups.
+template <typename Px, int TS>
+__device__ __forceinline__ void sg_frac_all(const hmgpu_me_job& jb, const int16_t* org_blocks, const RefTable& refs,
+                                            const OrgView& org, const hmgpu_me_result& res, uint32_t* s_acc49)
+{
+  const int tw = jb.pu_w / TS, nt = tw * (jb.pu_h / TS);
+  const bool satd = (jb.flags & HMGPU_F_HADME) && !(jb.flags & HMGPU_F_LOSSLESS);
+  const int pitch = refs.pitch;
+  for (int i = threadIdx.x; i < nt * 49; i += SG_THREADS)
+  {
+    const int pos = i / nt, t = i - pos * nt;
+    const int qx = 4 * res.int_x + (pos % 7) - 3, qy = 4 * res.int_y + (pos / 7) - 3;
+    const int ph = (qy & 3) * 4 + (qx & 3);
+    const Px* ref = (const Px*)refs.base[jb.ref_slot] + (size_t)ph * refs.plane_elems
+                  + (ptrdiff_t)(jb.pu_y + (qy >> 2)) * pitch + (jb.pu_x + (qx >> 2));
+    const int ty = t / tw, tx = t - ty * tw;
+    const uint32_t v = tile_dist<Px, TS>(jb, org_blocks, org, ref, pitch, tx * TS, ty * TS, satd);
+    atomicAdd(&s_acc49[pos], v);
+  }
+}
+
 #define SG_WIN_BYTES (10 * 1024)   // staged TZ window: <= (64 + 12) rows x <= 112 bytes
 
 // shared-memory scratch of one job (static part; s_dyn is the CTA's dynamic shared memory)
@@ -52,6 +74,7 @@ struct SgShared
   unsigned long long red[SG_THREADS / 32];
   hmgpu_me_result res;
   uint32_t acc[9];
+  uint32_t acc49[49];                   // small PUs: distortion of all 7x7 quarter-pel positions around the integer MV
   TzSpec spec;
 };
 
@@ -137,6 +160,47 @@ __device__ __forceinline__ void sg_job(const hmgpu_me_job& jb, const int16_t* __
       key = so - jb.org_offset;
     }
     const int bit_depth = refs.bit_depth;
+    const int ts = job_tile_size(jb);
+    const int n_tiles = (jb.pu_w / ts) * (jb.pu_h / ts);
+    if (n_tiles * 49 <= SG_THREADS)
+    {
+      // ---- all 49 positions at once, then both stages by warp 0 from the table ----
+      if (tid < 49) sh.acc49[tid] = 0;
+      __syncthreads();
+      const hmgpu_me_result res = sh.res;
+      if (ts == 8) sg_frac_all<Px, 8>(jb, key, refs, org, res, sh.acc49);
+      else sg_frac_all<Px, 4>(jb, key, refs, org, res, sh.acc49);
+      __syncthreads();
+      if (tid < 32)
+      {
+        const int c = tid < 9 ? tid : 0;
+        // half-pel stage (s_acMvRefineH order, TEncSearch.cpp:51-63), cost scale 1
+        const int hx = c_refine_h[c][0], hy = c_refine_h[c][1];
+        uint32_t cost = (sh.acc49[(2 * hy + 3) * 7 + (2 * hx + 3)] >> (bit_depth - 8))
+                      + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 1, 2 * res.int_x + hx, 2 * res.int_y + hy);
+        if (tid >= 9) cost = 0xffffffffu;
+        uint32_t best = __reduce_min_sync(0xffffffffu, cost);
+        int bi = __ffs(__ballot_sync(0xffffffffu, cost == best && tid < 9)) - 1;
+        const int half_x = c_refine_h[bi][0], half_y = c_refine_h[bi][1];
+        // quarter-pel stage around the best half position (s_acMvRefineQ order, :65-75), cost scale 0
+        const int qx = c_refine_q[c][0], qy = c_refine_q[c][1];
+        cost = (sh.acc49[(2 * half_y + qy + 3) * 7 + (2 * half_x + qx + 3)] >> (bit_depth - 8))
+             + hm_mv_cost(jb.ui_cost, jb.pred_x, jb.pred_y, 0, 4 * res.int_x + 2 * half_x + qx, 4 * res.int_y + 2 * half_y + qy);
+        if (tid >= 9) cost = 0xffffffffu;
+        best = __reduce_min_sync(0xffffffffu, cost);
+        bi = __ffs(__ballot_sync(0xffffffffu, cost == best && tid < 9)) - 1;
+        if (tid == 0)
+        {
+          sh.res.half_x = (int16_t)half_x; sh.res.half_y = (int16_t)half_y;
+          sh.res.qter_x = c_refine_q[bi][0]; sh.res.qter_y = c_refine_q[bi][1];
+          sh.res.frac_cost = best;
+          sh.res.n_cand += 18;
+        }
+      }
+      __syncthreads();
+      sg_stamp(trace, 4);
+      return;
+    }
     for (int phase = 0; phase < 2; phase++)
     {
       if (tid < 9) sh.acc[tid] = 0;

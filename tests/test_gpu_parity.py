@@ -358,3 +358,28 @@ def test_pipelined_batch_reports_bad_job():
             ctx.me_search(worse)
         r = ctx.me_search(jobs)            # the context stays usable
         assert int(r["n_cand"].min()) >= 18
+
+
+def test_full_size_4k_main10_properties():
+    """BASELINE cfg-5 size (3840x2160, 10-bit, SearchRange 128): size-independent properties + a sampled oracle check."""
+    w, h, bd = 3840, 2160, 10
+    fr = synth.luma_frames(w, h, 2, bd).astype(np.int16)
+    pus = worklist.pu_list(w, h)
+    pus = pus[::7]                                   # every 7th PU of the quadtree: ~170 k jobs, all shapes
+    jobs = worklist.frame_jobs(w, h, n_refs=1, search_range=128, pus=pus)
+    with hmgpu.Context(w, h, bd, 1) as ctx:
+        ctx.ref_upload(0, fr[0])
+        ctx.org_upload(fr[0])
+        z = jobs.copy()
+        z["pred_x"] = z["pred_y"] = z["start_x"] = z["start_y"] = 0
+        bdn = worklist.clip_bounds_np(w, h, -(z["clip_hmin"].astype(np.int32) // 4) - 71, -(z["clip_vmin"].astype(np.int32) // 4) - 71)
+        z["win_l"], z["win_t"], z["win_r"], z["win_b"] = worklist.search_range_np(bdn, 0, 0, 128)
+        r = ctx.me_search(z)
+        assert (r["int_x"] == 0).all() and (r["int_y"] == 0).all() and (r["int_sad"] == 0).all()
+        assert (r["half_x"] == 0).all() and (r["qter_y"] == 0).all()
+        ctx.org_upload(fr[1])
+        r = ctx.me_search(jobs)
+        idx = np.random.default_rng(4).choice(len(jobs), 200, replace=False)
+        exp = oracle_me(jobs[idx], [padded_ref(fr[0])], fr[1], bd)
+        assert_results_equal(r[idx], exp, jobs[idx])
+        assert r.tobytes() == ctx.me_search(jobs).tobytes()
