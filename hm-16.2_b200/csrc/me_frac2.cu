@@ -159,23 +159,25 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 {
   constexpr int NW = TS / 4 + 1;                         // staged words per row segment
   constexpr int OW = TS / 4;                             // source-picture words per row (aligned)
-  __shared__ uint32_t s_ref[2][TS][F2_THREADS * NW];     // double buffer of [row][tile * NW + word]
-  __shared__ const uint32_t* s_base[2][F2_THREADS];      // aligned address of row 0 of each tile for the candidate of each buffer
+  // every WARP stages for itself (its 32 tiles, double-buffered) and synchronises with __syncwarp only: the CTA-wide
+  // barriers of the first version (two per candidate) were 25-35 % of the stall samples (profiles/r1d_ncu_frac2_dist*)
+  __shared__ uint32_t s_ref_all[F2_THREADS / 32][2][TS][32 * NW];   // [warp][buffer][row][tile * NW + word]
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t (*s_ref)[TS][32 * NW] = s_ref_all[warp];
   const uint32_t n_work = *work_count;
   const int pitch = refs.pitch;
   const int pitch_w = pitch >> 2, org_pitch_w = org.pitch >> 2;
-  // loader role of this thread: elements tid + k*128 of a staged row (tile = idx / NW, word = idx % NW)
+  // loader role of this lane: elements lane + k*32 of a staged row of the warp (tile = idx / NW, word = idx % NW)
   int ld_tile[NW], ld_word[NW];
 #pragma unroll
-  for (int k = 0; k < NW; k++) { const int idx = tid + k * F2_THREADS; ld_tile[k] = idx / NW; ld_word[k] = idx - (idx / NW) * NW; }
+  for (int k = 0; k < NW; k++) { const int idx = lane + k * 32; ld_tile[k] = idx / NW; ld_word[k] = idx - (idx / NW) * NW; }
 
-  for (uint32_t chunk = blockIdx.x * F2_THREADS; chunk < n_work; chunk += gridDim.x * F2_THREADS)
+  for (uint32_t chunk = (blockIdx.x * (F2_THREADS / 32) + warp) * 32; chunk < n_work; chunk += gridDim.x * F2_THREADS)
   {
-    const bool have = chunk + tid < n_work;
-    // threads past the end of the list shadow the last tile (loads stay in bounds, nothing is accumulated)
-    const uint32_t wi = work[min(chunk + tid, n_work - 1)];
+    const bool have = chunk + lane < n_work;
+    // lanes past the end of the list shadow the last tile (loads stay in bounds, nothing is accumulated)
+    const uint32_t wi = work[min(chunk + lane, n_work - 1)];
     const uint32_t j = wi >> WORK_TILE_BITS;
     const int t = (int)(wi & ((1u << WORK_TILE_BITS) - 1));
     const hmgpu_me_job jb = jobs[j];
@@ -204,26 +206,26 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
       const int qy = qy0 + (phase ? c_refine_q[cand][1] : 2 * c_refine_h[cand][1]);
       const uint8_t* p = plane0 + (size_t)((qy & 3) * 4 + (qx & 3)) * refs.plane_elems
                        + (ptrdiff_t)(pu_y + (qy >> 2)) * pitch + (pu_x + (qx >> 2));
-      s_base[buf][tid] = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
-      __syncthreads();                                    // s_base visible; every thread is done with s_ref[buf]
+      const unsigned long long base = (unsigned long long)((uintptr_t)p & ~(uintptr_t)3);   // aligned address of row 0 of MY tile
+      __syncwarp();                                       // every lane is done with s_ref[buf]
 #pragma unroll
       for (int k = 0; k < NW; k++)
       {
-        const uint32_t* src = s_base[buf][ld_tile[k]] + ld_word[k];
+        // the lane that loads word ld_word[k] of tile ld_tile[k] takes that tile's row address from its owner
+        const uint32_t* src = (const uint32_t*)(uintptr_t)__shfl_sync(0xffffffffu, base, ld_tile[k]) + ld_word[k];
 #pragma unroll
-        for (int r = 0; r < TS; r++) cp_async4(&s_ref[buf][r][tid + k * F2_THREADS], src + (size_t)r * pitch_w);
+        for (int r = 0; r < TS; r++) cp_async4(&s_ref[buf][r][lane + k * 32], src + (size_t)r * pitch_w);
       }
       cp_async_commit();
       return (int)((uintptr_t)p & 3) * 8;
     };
-    __syncthreads();                                      // previous chunk fully consumed
     int sh_next = issue(0, 0);
     for (int cand = 0; cand < 9; cand++)
     {
       const int sh = sh_next, buf = cand & 1;
       if (cand + 1 < 9) { sh_next = issue(cand + 1, buf ^ 1); cp_async_wait<1>(); }
       else cp_async_wait<0>();
-      __syncthreads();
+      __syncwarp();
       uint32_t v;
       if (satd)
       {
@@ -234,10 +236,10 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 #pragma unroll
         for (int r = 0; r < TS; r++)
         {
-          const uint32_t w0 = s_ref[buf][r][tid * NW + 0], w1 = s_ref[buf][r][tid * NW + 1];
+          const uint32_t w0 = s_ref[buf][r][lane * NW + 0], w1 = s_ref[buf][r][lane * NW + 1];
           if (TS == 8)
           {
-            const uint32_t w2 = s_ref[buf][r][tid * NW + NW - 1];
+            const uint32_t w2 = s_ref[buf][r][lane * NW + NW - 1];
             int h[TS];
             had_row8<false>(ow[r][0], ow[r][OW - 1], zero, h);                       // + H(org row)
             had_row8<true>(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), h, d + r * TS);   // - H(ref row)
@@ -257,11 +259,11 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 #pragma unroll
         for (int r = 0; r < TS; r++)
         {
-          const uint32_t w0 = s_ref[buf][r][tid * NW + 0], w1 = s_ref[buf][r][tid * NW + 1];
+          const uint32_t w0 = s_ref[buf][r][lane * NW + 0], w1 = s_ref[buf][r][lane * NW + 1];
           v = vabsdiff4_acc(__funnelshift_r(w0, w1, sh), ow[r][0], v);
           if (TS == 8)
           {
-            const uint32_t w2 = s_ref[buf][r][tid * NW + NW - 1];
+            const uint32_t w2 = s_ref[buf][r][lane * NW + NW - 1];
             v = vabsdiff4_acc(__funnelshift_r(w1, w2, sh), ow[r][OW - 1], v);
           }
         }
