@@ -153,7 +153,7 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   // phase-specific branches of its state machine serialise and every lane walks a whole SAD); 1 = the first
   // four-jobs-per-warp attempt, tz_search_small_kernel (3.6 ms).
   static const int s_split = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 0;
-  HmgpuStage st(ctx, HMGPU_ST_TZ, packed ? 3 : 2);
+  HmgpuStage st(ctx, HMGPU_ST_TZ, (packed && s_split) ? 3 : 2);
   tz_classify_kernel<<<(n_jobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, n_jobs, packed ? s_split : 0, idx_small, idx_big, counts);
   // persistent grids: enough CTAs to fill the machine, never more than the work could use
   const int cap = HMGPU_NUM_SMS * 16;
@@ -168,7 +168,7 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
     else
     {
       if (s_split == 2) { if ((rc = hmgpu_launch_tz_lockstep(ctx, d_jobs, idx_small, counts + 0, counts + 2, n_jobs, d_results))) return rc; }
-      else tz_search_small_kernel<<<grid_small, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
+      else if (s_split == 1) tz_search_small_kernel<<<grid_small, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
       tz_search_kernel<uint8_t, true><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
     }
   }

@@ -104,7 +104,7 @@ __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitc
   const int pitch_w = pitch >> 2;                      // pitch is a multiple of 4 bytes
   for (int r = r0; r < rows; r += rstep)
   {
-    const uint32_t* q = q0 + (size_t)(r * row_mul) * pitch_w;
+    const uint32_t* q = q0 + (r * row_mul) * pitch_w;     // < 2^31 words inside a plane
     const uint32_t* o = org_s + (r * row_mul) * wq;
     uint32_t lo = SMEM ? q[0] : __ldg(q);
     for (int k = 0; k < wq; k++)
@@ -150,9 +150,14 @@ __device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pit
   {
     // smallest raw sum whose normalised value (sum << sub_shift) >> (bitDepth-8) reaches best.cost - mvc
     const uint32_t need = best.cost - mvc;
-    const int shift = J.bit_depth - 8;
-    const uint64_t nb = (((uint64_t)need << shift) + ((1u << J.sub_shift) - 1u)) >> J.sub_shift;
-    const uint32_t raw_bound = nb > 0xffffffffull ? 0xffffffffu : (uint32_t)nb;
+    uint32_t raw_bound;
+    if (PACKED) raw_bound = (need >> J.sub_shift) + ((need & ((1u << J.sub_shift) - 1u)) ? 1u : 0u);   // 8-bit pictures: no 64-bit math
+    else
+    {
+      const int shift = J.bit_depth - 8;
+      const uint64_t nb = (((uint64_t)need << shift) + ((1u << J.sub_shift) - 1u)) >> J.sub_shift;
+      raw_bound = nb > 0xffffffffull ? 0xffffffffu : (uint32_t)nb;
+    }
     const Px* ref = ref00 + (ptrdiff_t)y * pitch + x;
     if (PACKED && J.win_s && x >= J.wx0 && x <= J.wx1 && y >= J.wy0 && y <= J.wy1)
       part = sad_rows_packed<true>(J.win_s + (y - J.win_oy) * J.win_pitch + (x - J.win_ox), J.win_pitch, (const uint32_t*)org_s, J.pu_w >> 2, J.rows,
@@ -191,42 +196,27 @@ __device__ __forceinline__ bool tz_in_window(const TzJob& J, int cx, int cy, int
 }
 
 // Point i (emission order) of the diamond at distance d around (cx, cy): xTZ8PointDiamondSearch
-// (TEncSearch.cpp:616-791)
+// (TEncSearch.cpp:616-791).  Every offset of a round is a small multiple of one unit -- d for d = 1, d/2 for 2 <= d <= 8
+// (axis points at 2 units, diagonal points at 1), d/4 for d > 8 (16 points on the diamond of radius 4 units) -- so the
+// points come branch-free out of nibble-packed tables (one table per class: signed 4-bit multipliers, point numbers,
+// distance multipliers), indexed by the lane's emission index.
+__device__ __forceinline__ int tz_nib(unsigned long long t, int i) { return (int)((t >> (4 * i)) & 15ull); }
+__device__ __forceinline__ int tz_snib(unsigned long long t, int i) { return (tz_nib(t, i) ^ 8) - 8; }   // sign-extend 4 bits
 __device__ __forceinline__ void tz_diamond_point(int cx, int cy, int d, int i, int& x, int& y, int& pnr, int& dist)
 {
-  x = cx; y = cy; pnr = 0; dist = d;
-  if (d == 1)
-  {
-    // (cx,top,2) (left,cy,4) (right,cy,5) (cx,bottom,7)
-    if (i == 0) { y = cy - 1; pnr = 2; } else if (i == 1) { x = cx - 1; pnr = 4; }
-    else if (i == 2) { x = cx + 1; pnr = 5; } else { y = cy + 1; pnr = 7; }
-  }
-  else if (d <= 8)
-  {
-    const int h = d >> 1;
-    switch (i)
-    {
-      case 0: y = cy - d; pnr = 2; break;
-      case 1: x = cx - h; y = cy - h; pnr = 1; dist = h; break;
-      case 2: x = cx + h; y = cy - h; pnr = 3; dist = h; break;
-      case 3: x = cx - d; pnr = 4; break;
-      case 4: x = cx + d; pnr = 5; break;
-      case 5: x = cx - h; y = cy + h; pnr = 6; dist = h; break;
-      case 6: x = cx + h; y = cy + h; pnr = 8; dist = h; break;
-      default: y = cy + d; pnr = 7; break;
-    }
-  }
-  else if (i < 4)
-  {
-    if (i == 0) y = cy - d; else if (i == 1) x = cx - d; else if (i == 2) x = cx + d; else y = cy + d;
-  }
-  else
-  {
-    const int idx = ((i - 4) >> 2) + 1, k = (i - 4) & 3;   // k: 0 (xl,yt) 1 (xr,yt) 2 (xl,yb) 3 (xr,yb)
-    const int q = (d >> 2) * idx;
-    x = (k & 1) ? cx + q : cx - q;
-    y = (k & 2) ? cy + d - q : cy - d + q;
-  }
+  // nibble i of each table = value for emission index i (two's-complement nibbles for the multipliers)
+  //   d == 1 : (0,-1) (-1,0) (1,0) (0,1)                                   pnr 2 4 5 7
+  //   d <= 8 : (0,-2) (-1,-1) (1,-1) (-2,0) (2,0) (-1,1) (1,1) (0,2)        pnr 2 1 3 4 5 6 8 7, dist 2 1 1 2 2 1 1 2 units
+  //   d  > 8 : (0,-4) (-4,0) (4,0) (0,4) then idx = 1..3: (-q,-(4-q)) (q,-(4-q)) (-q,4-q) (q,4-q) with q = idx
+  unsigned long long mx, my, pn, dm;
+  int unit;
+  if (d == 1)      { mx = 0x01F0ull; my = 0x100Full; pn = 0x7542ull; dm = 0x1111ull; unit = 1; }
+  else if (d <= 8) { mx = 0x01F2E1F0ull; my = 0x21100FFEull; pn = 0x78654312ull; dm = 0x21122112ull; unit = d >> 1; }
+  else             { mx = 0x3D3D2E2E1F1F04C0ull; my = 0x11FF22EE33DD400Cull; pn = 0ull; dm = 0x4444444444444444ull; unit = d >> 2; }
+  x = cx + tz_snib(mx, i) * unit;
+  y = cy + tz_snib(my, i) * unit;
+  pnr = tz_nib(pn, i);
+  dist = tz_nib(dm, i) * unit;
 }
 
 // largest power of two <= v (v >= 1)

@@ -383,3 +383,28 @@ def test_full_size_4k_main10_properties():
         exp = oracle_me(jobs[idx], [padded_ref(fr[0])], fr[1], bd)
         assert_results_equal(r[idx], exp, jobs[idx])
         assert r.tobytes() == ctx.me_search(jobs).tobytes()
+
+
+def test_mailbox_server_restarts_and_uploads():
+    """small calls go through the resident mailbox server: it must survive its own idle exit (a pause longer than the idle
+    limit between calls), picture uploads in between (the host stops it, the planes change) and bursts of calls"""
+    import time
+    rng = np.random.default_rng(77)
+    fr = _frames(8, 4)
+    jobs, _, _ = _random_jobs(rng, 64, 8, "tz", 2)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    with hmgpu.Context(W, H, 8, 2) as ctx:
+        ctx.ref_upload(0, fr[0]); ctx.ref_upload(1, fr[1]); ctx.org_upload(fr[3])
+        exp = oracle_me(jobs, [pads[0], pads[1]], fr[3], 8)
+        for i in range(0, 32, 4):                       # burst
+            assert_results_equal(ctx.me_search(jobs[i:i + 4]), exp[i:i + 4], jobs[i:i + 4])
+        time.sleep(0.02)                                # the server leaves (idle), the next call starts a new generation
+        assert_results_equal(ctx.me_search(jobs[32:35]), exp[32:35], jobs[32:35])
+        ctx.ref_upload(1, fr[2])                        # new picture in slot 1: the server is stopped and restarted
+        exp2 = oracle_me(jobs, [pads[0], pads[2]], fr[3], 8)
+        for i in range(32, 64, 8):
+            assert_results_equal(ctx.me_search(jobs[i:i + 8]), exp2[i:i + 8], jobs[i:i + 8])
+            time.sleep(0.001)
+        ctx.org_upload(fr[2])
+        exp3 = oracle_me(jobs[:16], [pads[0], pads[2]], fr[2], 8)
+        assert_results_equal(ctx.me_search(jobs[:16]), exp3, jobs[:16])
