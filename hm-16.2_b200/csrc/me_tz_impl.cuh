@@ -93,29 +93,54 @@ template <int GS> struct TzGroup
 // sum reaches it -- the point then loses whatever the remaining rows add, so the truncated value is
 // never selected and the result stays exact.  The far rings of the star refinement end after a
 // row or two this way.
-template <bool SMEM = false>
-__device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitch, const uint32_t* org_s,
-                                                    int wq, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
+// WQ > 0: words per row known at compile time (the row unrolls, every operand is base + immediate); WQ = 0: run-time wq
+template <bool SMEM, int WQ>
+__device__ __forceinline__ uint32_t sad_rows_packed_w(const uint32_t* q0, int sh, int pitch_w, const uint32_t* org_s,
+                                                      int wq_rt, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
 {
+  const int wq = WQ ? WQ : wq_rt;
   uint32_t acc = 0;
-  const uintptr_t a0 = (uintptr_t)ref;
-  const int sh = (int)(a0 & 3) * 8;
-  const uint32_t* q0 = (const uint32_t*)(a0 & ~(uintptr_t)3);
-  const int pitch_w = pitch >> 2;                      // pitch is a multiple of 4 bytes
   for (int r = r0; r < rows; r += rstep)
   {
     const uint32_t* q = q0 + (r * row_mul) * pitch_w;     // < 2^31 words inside a plane
     const uint32_t* o = org_s + (r * row_mul) * wq;
-    uint32_t lo = SMEM ? q[0] : __ldg(q);
-    for (int k = 0; k < wq; k++)
+    if (WQ)
     {
-      const uint32_t hi = SMEM ? q[k + 1] : __ldg(q + k + 1);
-      acc = vabsdiff4_acc(__funnelshift_r(lo, hi, sh), o[k], acc);
-      lo = hi;
+      uint32_t w[WQ + 1];
+#pragma unroll
+      for (int k = 0; k <= WQ; k++) w[k] = SMEM ? q[k] : __ldg(q + k);
+#pragma unroll
+      for (int k = 0; k < WQ; k++) acc = vabsdiff4_acc(__funnelshift_r(w[k], w[k + 1], sh), o[k], acc);
+    }
+    else
+    {
+      uint32_t lo = SMEM ? q[0] : __ldg(q);
+      for (int k = 0; k < wq; k++)
+      {
+        const uint32_t hi = SMEM ? q[k + 1] : __ldg(q + k + 1);
+        acc = vabsdiff4_acc(__funnelshift_r(lo, hi, sh), o[k], acc);
+        lo = hi;
+      }
     }
     if (acc >= raw_bound) break;
   }
   return acc;
+}
+
+template <bool SMEM = false>
+__device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitch, const uint32_t* org_s,
+                                                    int wq, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
+{
+  const uintptr_t a0 = (uintptr_t)ref;
+  const int sh = (int)(a0 & 3) * 8;
+  const uint32_t* q0 = (const uint32_t*)(a0 & ~(uintptr_t)3);
+  const int pitch_w = pitch >> 2;                      // pitch is a multiple of 4 bytes
+  // the common PU widths (8, 16, 4, 32 samples) get unrolled rows; wq is uniform across the lanes of a job
+  if (wq == 2) return sad_rows_packed_w<SMEM, 2>(q0, sh, pitch_w, org_s, wq, rows, row_mul, r0, rstep, raw_bound);
+  if (wq == 4) return sad_rows_packed_w<SMEM, 4>(q0, sh, pitch_w, org_s, wq, rows, row_mul, r0, rstep, raw_bound);
+  if (wq == 1) return sad_rows_packed_w<SMEM, 1>(q0, sh, pitch_w, org_s, wq, rows, row_mul, r0, rstep, raw_bound);
+  if (wq == 8) return sad_rows_packed_w<SMEM, 8>(q0, sh, pitch_w, org_s, wq, rows, row_mul, r0, rstep, raw_bound);
+  return sad_rows_packed_w<SMEM, 0>(q0, sh, pitch_w, org_s, wq, rows, row_mul, r0, rstep, raw_bound);
 }
 
 // generic path: org int16 in shared memory (row pitch pu_w), ref elements of type Px
@@ -233,7 +258,7 @@ __device__ __forceinline__ void tz_diamond(const TzJob& J, const Px* ref00, int 
   // lanes per point: as many as the group allows for n points, never more than the visited rows
   const int per_pass = min(n, GS);                       // points evaluated concurrently
   const int lpp = pow2_floor(min(GS / per_pass, J.rows));
-  const int slot = gl / lpp;
+  const int slot = gl >> (31 - __clz(lpp));              // lpp is a power of two
   for (int i0 = 0; i0 < n; i0 += per_pass)
   {
     const int i = i0 + slot;
@@ -258,7 +283,7 @@ __device__ __forceinline__ void tz_two_point(const TzJob& J, const Px* ref00, in
   const int nr = best.pnr;
   if (nr < 1 || nr > 8) return;
   const int lpp = pow2_floor(min(GS / 2, J.rows));
-  const int i = TzGroup<GS>::lane() / lpp;
+  const int i = TzGroup<GS>::lane() >> (31 - __clz(lpp));
   const int cx = best.x, cy = best.y;
   const int x = cx + c_two_point[nr][i == 0 ? 0 : 2];
   const int y = cy + c_two_point[nr][i == 0 ? 1 : 3];
@@ -352,7 +377,7 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
   const bool has2n = (jb.flags & HMGPU_F_HAS_2NX2N) != 0;
   {
     const int lpp = pow2_floor(min(GS / 4, J.rows));
-    const int i = gl / lpp;
+    const int i = gl >> (31 - __clz(lpp));
     int x = 0, y = 0;
     if (i == 0)
     {
