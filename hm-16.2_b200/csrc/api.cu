@@ -280,6 +280,7 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   if (ctx->d_tzlist) cudaFree(ctx->d_tzlist);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+  free(ctx->defer_org);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -739,9 +740,10 @@ static bool slot_ready(const volatile uint32_t* slot, uint32_t ticket, hmgpu_me_
   return true;
 }
 
-// one call through the resident server: write the lines, (start a generation if none is alive), poll the slots
-static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, bool any_org,
-                            const int16_t* org_blocks, int n_org_elems, int max_win, hmgpu_me_result* results)
+// one call through the resident server, in two halves so that the caller can work while the device searches:
+// submit = write the lines (start a generation if none is alive); wait = poll the result slots
+static int server_submit(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, bool any_org,
+                         const int16_t* org_blocks, int n_org_elems, int max_win)
 {
   const int need_dyn = max_win > 10 * 1024 ? max_win : 10 * 1024;
   int rc;
@@ -754,9 +756,19 @@ static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* job
   }
   if (any_org) memcpy(mb->org_blocks, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
   const uint32_t ticket = ++ctx->mail_ticket;
+  memcpy(ctx->pend_jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);   // kept for a re-submit if the server must be restarted
+  ctx->pend_n = n_jobs;
   server_write_lines(mb, jobs, n_jobs, ticket, ctx->srv_gen);
   if (!ctx->srv_alive && (rc = server_start(ctx, mb, need_dyn > ctx->srv_dyn ? need_dyn : ctx->srv_dyn))) return rc;
   ctx->srv_calls++;
+  return HMGPU_OK;
+}
+
+static int server_wait(hmgpu_ctx* ctx, Mailbox* mb, hmgpu_me_result* results)
+{
+  const uint32_t ticket = ctx->mail_ticket;
+  const int n_jobs = ctx->pend_n;
+  int rc;
   for (int i = 0; i < n_jobs; i++)
   {
     const volatile uint32_t* slot = (const volatile uint32_t*)&mb->slots[i];
@@ -769,7 +781,7 @@ static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* job
         if (slot_ready(slot, ticket, &results[i])) break;
         ctx->srv_alive = false;
         ctx->srv_gen++;
-        server_write_lines(mb, jobs, n_jobs, ticket, ctx->srv_gen);
+        server_write_lines(mb, ctx->pend_jobs, n_jobs, ticket, ctx->srv_gen);
         if ((rc = server_start(ctx, mb, ctx->srv_dyn))) return rc;
       }
       if (spins > 4000000u)
@@ -781,7 +793,77 @@ static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* job
       }
     }
   }
+  ctx->pend_n = 0;
   return HMGPU_OK;
+}
+
+static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, bool any_org,
+                            const int16_t* org_blocks, int n_org_elems, int max_win, hmgpu_me_result* results)
+{
+  const int rc = server_submit(ctx, mb, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win);
+  return rc ? rc : server_wait(ctx, mb, results);
+}
+
+static bool server_enabled()
+{
+  static const bool s_on = !(getenv("HMGPU_SERVER") && atoi(getenv("HMGPU_SERVER")) == 0) && getenv("HMGPU_TRACE") == NULL;
+  return s_on;
+}
+
+// Asynchronous pair ("async submit/poll for the mailbox path").  hmgpu_me_submit returns as soon as the jobs are
+// visible to the device; the caller does host work that does not need the vectors (HM: the merge estimation of the PU) and
+// collects them with hmgpu_me_wait.  Batches the resident server cannot take are kept and searched inside hmgpu_me_wait.
+int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (ctx->pend_n || ctx->defer_n) return hmgpu_fail(ctx, HMGPU_E_STATE, "hmgpu_me_submit: the previous submit has not been waited for");
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || n_jobs < 0 || n_jobs > MAIL_JOBS) return hmgpu_fail(ctx, HMGPU_E_INVALID, "hmgpu_me_submit takes 1..%d jobs", MAIL_JOBS);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  bool any_org, any_full, any_tz, any_frac;
+  int max_win;
+  int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win);
+  if (rc) return rc;
+  if (server_enabled() && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024 && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64))
+  {
+    if (!ctx->h_mail)
+    {
+      HMGPU_CUDA(ctx, cudaHostAlloc(&ctx->h_mail, sizeof(Mailbox), cudaHostAllocMapped));
+      memset(ctx->h_mail, 0, sizeof(Mailbox));
+    }
+    return server_submit(ctx, (Mailbox*)ctx->h_mail, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win);
+  }
+  // deferred: the blocking search runs in hmgpu_me_wait (the caller's buffers may be gone by then: copy)
+  if (any_org)
+  {
+    if ((size_t)n_org_elems > ctx->defer_org_cap)
+    {
+      free(ctx->defer_org);
+      ctx->defer_org = (int16_t*)malloc(sizeof(int16_t) * (size_t)n_org_elems);
+      if (!ctx->defer_org) { ctx->defer_org_cap = 0; return hmgpu_fail(ctx, HMGPU_E_NOMEM, "out of host memory"); }
+      ctx->defer_org_cap = (size_t)n_org_elems;
+    }
+    memcpy(ctx->defer_org, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+  }
+  memcpy(ctx->pend_jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
+  ctx->defer_n = n_jobs; ctx->defer_org_n = any_org ? n_org_elems : 0;
+  return HMGPU_OK;
+}
+
+int hmgpu_me_wait(hmgpu_ctx* ctx, hmgpu_me_result* results)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (ctx->defer_n)
+  {
+    const int n = ctx->defer_n;
+    ctx->defer_n = 0;
+    hmgpu_me_job jobs[MAIL_JOBS];
+    memcpy(jobs, ctx->pend_jobs, sizeof(hmgpu_me_job) * (size_t)n);
+    return hmgpu_me_search(ctx, jobs, n, ctx->defer_org_n ? ctx->defer_org : NULL, ctx->defer_org_n, results);
+  }
+  if (!ctx->pend_n) return HMGPU_OK;
+  if (!results) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL results");
+  return server_wait(ctx, (Mailbox*)ctx->h_mail, results);
 }
 
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
@@ -807,8 +889,7 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
     }
     Mailbox* mb = (Mailbox*)ctx->h_mail;
     static const bool s_trace = getenv("HMGPU_TRACE") != NULL;
-    static const bool s_server = !(getenv("HMGPU_SERVER") && atoi(getenv("HMGPU_SERVER")) == 0);
-    if (s_server && !s_trace && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024)
+    if (server_enabled() && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024)
       return me_search_server(ctx, mb, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win, results);
     const double t0 = s_trace ? now_us() : 0.0;
     HmgpuJobPack pack;

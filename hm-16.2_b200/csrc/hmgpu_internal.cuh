@@ -10,6 +10,8 @@
 #define HMGPU_CMARGIN 40         // chroma padding (4:2:0)
 #define HMGPU_MAX_REFS 16
 #define HMGPU_NUM_SMS 148
+#define HMGPU_MAIL_JOBS 32       // jobs per call of the low-latency path (me_single.cu)
+#define HMGPU_SERVER_CTAS 16     // CTAs of the mailbox server = jobs it takes per call
 
 // Device view of the reference planes of one context, passed to kernels by value.
 // plane(slot, phase) sample (x, y), x in [-80, W+80): base[slot] + phase*plane_elems + y*pitch + x
@@ -72,6 +74,8 @@ struct hmgpu_ctx
   void* d_orgblk; size_t d_orgblk_bytes; // bi-pred key patterns of a pipelined batch
   void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
   // mailbox server (me_server_kernel): a kernel that stays resident between calls
+  hmgpu_me_job pend_jobs[HMGPU_MAIL_JOBS]; int pend_n;   // jobs of a submit that has not been waited for (server path)
+  int defer_n, defer_org_n; int16_t* defer_org; size_t defer_org_cap;   // hmgpu_me_submit batches searched inside hmgpu_me_wait
   cudaStream_t srv_stream; bool srv_alive; uint32_t srv_gen; int srv_dyn; uint32_t srv_calls, srv_starts;
   uint64_t launches;
   // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
@@ -85,8 +89,6 @@ struct hmgpu_ctx
 };
 
 // ---- low-latency path (me_single.cu): mapped pinned mailbox --------------------------------------
-#define HMGPU_MAIL_JOBS 32
-#define HMGPU_SERVER_CTAS 16     // CTAs of the mailbox server = jobs it takes per call
 // the jobs of one call travel as a kernel parameter (no PCIe read on the device side)
 struct HmgpuJobPack { hmgpu_me_job jobs[HMGPU_MAIL_JOBS]; };
 // One result slot = 32 bytes written by ONE warp-wide store of 8 consecutive words, so it crosses PCIe as a

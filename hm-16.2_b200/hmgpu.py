@@ -44,7 +44,7 @@ EXPORTS = [
     "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
-    "hmgpu_me_search", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
+    "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
@@ -87,6 +87,8 @@ def lib():
     L.hmgpu_org_upload_device.argtypes = [vp, vp, ci]
     L.hmgpu_me_search.argtypes = [vp, vp, ci, vp, ci, vp]
     L.hmgpu_me_search_device.argtypes = [vp, vp, ci, vp, vp, ci]
+    L.hmgpu_me_submit.argtypes = [vp, vp, ci, vp, ci]
+    L.hmgpu_me_wait.argtypes = [vp, vp]
     L.hmgpu_clip_bounds.argtypes = [ci, ci, ci, ci, vp]
     L.hmgpu_clip_bounds.restype = None
     L.hmgpu_search_range.argtypes = [vp, ci, ci, ci, vp]
@@ -227,6 +229,22 @@ class Context:
         self._check(self.L.hmgpu_me_search(self.h, jobs.ctypes.data, len(jobs),
                                            org_blocks.ctypes.data if org_blocks is not None else None,
                                            org_blocks.size if org_blocks is not None else 0, res.ctypes.data))
+        return res
+
+    def me_submit(self, jobs, org_blocks=None):
+        """asynchronous half of me_search for small batches; collect with me_wait()"""
+        jobs = np.ascontiguousarray(jobs, ME_JOB)
+        if org_blocks is not None:
+            org_blocks = np.ascontiguousarray(org_blocks, np.int16)
+        self._check(self.L.hmgpu_me_submit(self.h, jobs.ctypes.data, len(jobs),
+                                           org_blocks.ctypes.data if org_blocks is not None else None,
+                                           org_blocks.size if org_blocks is not None else 0))
+        self._pending = len(jobs)
+
+    def me_wait(self):
+        res = np.zeros(self._pending, ME_RESULT)
+        self._check(self.L.hmgpu_me_wait(self.h, res.ctypes.data))
+        self._pending = 0
         return res
 
     def me_search_device(self, d_jobs, n_jobs, d_org_blocks, d_results, flags_any):

@@ -229,17 +229,31 @@ Void HmGpuHost::beginQueue()
   m_queueLen  = 0;
 }
 
-Void HmGpuHost::flushQueue()
+Void HmGpuHost::submitQueue()
 {
   m_queueing = false;
   if ( m_queueLen > 0 )
   {
     const Double t0 = xNow();
-    if ( hmgpu_me_search( m_ctx, m_queueJobs, m_queueLen, NULL, 0, m_queueRes ) != HMGPU_OK )
+    if ( hmgpu_me_submit( m_ctx, m_queueJobs, m_queueLen, NULL, 0 ) != HMGPU_OK )
     {
-      xFail( "hmgpu_me_search (queued)" );
+      xFail( "hmgpu_me_submit" );
     }
     m_gpuCalls++;
+    const Double dt = xNow() - t0;
+    m_seconds += dt; m_totalSeconds += dt;
+  }
+}
+
+Void HmGpuHost::waitQueue()
+{
+  if ( m_queueLen > 0 )
+  {
+    const Double t0 = xNow();
+    if ( hmgpu_me_wait( m_ctx, m_queueRes ) != HMGPU_OK )
+    {
+      xFail( "hmgpu_me_wait" );
+    }
     const Double dt = xNow() - t0;
     m_seconds += dt; m_totalSeconds += dt;
   }

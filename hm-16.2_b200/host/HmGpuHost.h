@@ -42,7 +42,9 @@ public:
   /// first queues them all (beginQueue, motionSearch x N), sends them to the GPU as ONE hmgpu_me_search call
   /// (flushQueue) and then runs its original body, where motionSearch hands out the queued results.
   Void beginQueue   ();
-  Void flushQueue   ();
+  Void submitQueue  ();   ///< hands the queued searches to the GPU and returns (hmgpu_me_submit)
+  Void waitQueue    ();   ///< collects their results (hmgpu_me_wait); host work in between overlaps the device
+  Void flushQueue   () { submitQueue(); waitQueue(); }
   Bool queueing     () const { return m_queueing; }
 
   /// GPUME=2: compare with what the CPU search just produced; abort on the first mismatch

@@ -145,6 +145,13 @@ typedef struct hmgpu_me_result
 /* host buffers in, host buffers out; blocking */
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                     const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results);
+/* Asynchronous pair for small batches (1..32 jobs): hmgpu_me_submit returns once the jobs are visible to the device (the
+ * resident mailbox server), the caller does host work that does not need the vectors -- in HM the merge estimation
+ * of the PU (TEncSearch::xMergeEstimation, TEncSearch.cpp:2987), which predInterSearch otherwise runs after the searches -- and
+ * hmgpu_me_wait blocks until the results are complete.  The buffers passed to hmgpu_me_submit may be reused when it returns.
+ * One submit may be outstanding per context; no search or upload call between a submit and its wait. */
+int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems);
+int hmgpu_me_wait(hmgpu_ctx* ctx, hmgpu_me_result* results);
 /* device-resident variant used for kernel-only timing: d_jobs/d_results are device pointers,
  * asynchronous on hmgpu_stream(); call hmgpu_synchronize() to wait.  The host cannot inspect
  * device-resident jobs: flags_any is the OR of the flags of all jobs (selects the kernels to
