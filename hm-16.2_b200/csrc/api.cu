@@ -9,7 +9,7 @@
 
 int hmgpu_launch_chroma(hmgpu_ctx* ctx, int16_t* d_dst, const int16_t* d_src, int src_stride);
 int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
-                    hmgpu_me_result* d_results, bool any_org_block);
+                    hmgpu_me_result* d_results, bool any_org_block, bool any_sel);
 int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_org_block, int max_win_bytes);
 int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
@@ -143,10 +143,10 @@ RefTable hmgpu_ref_table(const hmgpu_ctx* ctx)
 
 int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                     hmgpu_me_result* d_results, bool any_org_block, bool any_full, bool any_tz, bool any_frac,
-                    int max_win_bytes)
+                    int max_win_bytes, bool any_sel)
 {
   int rc;
-  if (any_tz && (rc = hmgpu_launch_tz(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block))) return rc;
+  if (any_tz && (rc = hmgpu_launch_tz(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, any_sel))) return rc;
   if (any_full && (rc = hmgpu_launch_full(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, max_win_bytes))) return rc;
   if (ctx->px_bytes == 1 && !any_org_block && !getenv("HMGPU_FRAC_V1"))
   {
@@ -414,9 +414,11 @@ int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride)
 // ---- motion search --------------------------------------------------------------------------
 
 static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_org_elems,
-                         bool* any_org, bool* any_full, bool* any_tz, bool* any_frac, int* max_win_bytes, int first = 0)
+                         bool* any_org, bool* any_full, bool* any_tz, bool* any_frac, int* max_win_bytes, int first = 0,
+                         bool* any_sel = NULL)
 {
   *any_org = *any_full = *any_tz = *any_frac = false;
+  if (any_sel) *any_sel = false;
   *max_win_bytes = 0;
   jobs -= first;                                           // messages carry the index in the caller's array
   for (int i = first; i < first + n; i++)
@@ -445,6 +447,15 @@ static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_
       *any_org = true;
       if ((size_t)j.org_offset + (size_t)j.pu_w * j.pu_h > (size_t)n_org_elems)
         return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: org block outside org_blocks", i);
+    }
+    if (j.kind != HMGPU_KIND_DEFAULT)
+    {
+      if (j.kind != HMGPU_KIND_SELECTIVE || !(j.flags & HMGPU_F_INTEGER) || (j.flags & (HMGPU_F_FULL | HMGPU_F_ORG_BLOCK)))
+        return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: kind %d needs an integer TZ search without a key-pattern block", i, j.kind);
+      if (!any_sel) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: selective search is not available on this entry point", i);
+      if ((size_t)j.org_offset + 6 > (size_t)n_org_elems)
+        return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: the three MV predictors of the selective search lie outside org_blocks", i);
+      *any_sel = true;
     }
     if (j.flags & HMGPU_F_FRAC) *any_frac = true;
     if (j.flags & HMGPU_F_INTEGER)
@@ -480,13 +491,14 @@ static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_
 // (job_scan_kernel, on the copy stream) and the host only reads its 16-byte verdict.
 #define PIPE_MIN_JOBS 65536
 
-struct ScanOut { uint32_t first_bad; uint32_t flags_any; uint32_t max_win; uint32_t int_kinds; /* bit0 tz, bit1 full */ };
+struct ScanOut { uint32_t first_bad; uint32_t flags_any; uint32_t max_win; uint32_t int_kinds; /* bit0 tz, bit1 full, bit2 selective */ };
 
-enum { SCAN_OK = 0, SCAN_PU_SIZE, SCAN_PU_POS, SCAN_SLOT, SCAN_CLIP, SCAN_WINDOW, SCAN_START, SCAN_ORG, SCAN_RANGE };
+enum { SCAN_OK = 0, SCAN_PU_SIZE, SCAN_PU_POS, SCAN_SLOT, SCAN_CLIP, SCAN_WINDOW, SCAN_START, SCAN_ORG, SCAN_RANGE, SCAN_KIND };
 static const char* const k_scan_msg[] = {
   "ok", "PU size unsupported", "PU outside the picture or x not a multiple of 4", "reference slot not uploaded",
   "clip bounds reach outside the padded reference", "search window outside the clip bounds", "integer MV outside the clip bounds",
-  "org block outside org_blocks", "search range not in 1..512" };
+  "org block outside org_blocks", "search range not in 1..512",
+  "job kind needs an integer TZ search without a key-pattern block and its MV predictors inside org_blocks" };
 
 __host__ __device__ static inline int job_check(const hmgpu_me_job& j, int pic_w, int pic_h, uint32_t valid_slots, unsigned long long n_org_elems)
 {
@@ -501,6 +513,9 @@ __host__ __device__ static inline int job_check(const hmgpu_me_job& j, int pic_w
       ((j.start_x << 2) < j.clip_hmin - 3 || (j.start_x << 2) > j.clip_hmax || (j.start_y << 2) < j.clip_vmin - 3 || (j.start_y << 2) > j.clip_vmax)) return SCAN_START;
   if ((j.flags & HMGPU_F_ORG_BLOCK) && (unsigned long long)j.org_offset + (unsigned long long)j.pu_w * j.pu_h > n_org_elems) return SCAN_ORG;
   if ((j.flags & HMGPU_F_INTEGER) && !(j.flags & HMGPU_F_FULL) && (j.search_range < 1 || j.search_range > 512)) return SCAN_RANGE;
+  if (j.kind != HMGPU_KIND_DEFAULT &&
+      (j.kind != HMGPU_KIND_SELECTIVE || !(j.flags & HMGPU_F_INTEGER) || (j.flags & (HMGPU_F_FULL | HMGPU_F_ORG_BLOCK)) ||
+       (unsigned long long)j.org_offset + 6ull > n_org_elems)) return SCAN_KIND;
   return SCAN_OK;
 }
 
@@ -528,7 +543,7 @@ __global__ void job_scan_kernel(const hmgpu_me_job* __restrict__ jobs, int n, in
     if (j.flags & HMGPU_F_INTEGER)
     {
       if (j.flags & HMGPU_F_FULL) { kinds = 2; if (!code) win = (uint32_t)job_full_window_bytes(j); }
-      else kinds = 1;
+      else kinds = j.kind == HMGPU_KIND_SELECTIVE ? 5 : 1;
     }
   }
   bad = __reduce_min_sync(0xffffffffu, bad);
@@ -660,8 +675,9 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
     char* hp = (char*)ctx->h_pin;
     const bool any_org = (so.flags_any & HMGPU_F_ORG_BLOCK) != 0;
     if ((e = cudaStreamWaitEvent(ctx->stream, ctx->scan_done[l], 0)) != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "%s", cudaGetErrorString(e)); break; }
-    if ((rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n, any_org ? (const int16_t*)ctx->d_orgblk : NULL, (hmgpu_me_result*)(dp + jb),
-                              any_org, (so.int_kinds & 2u) != 0, (so.int_kinds & 1u) != 0, (so.flags_any & HMGPU_F_FRAC) != 0, (int)so.max_win))) break;
+    const bool any_sel = (so.int_kinds & 4u) != 0;
+    if ((rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n, (any_org || any_sel) ? (const int16_t*)ctx->d_orgblk : NULL, (hmgpu_me_result*)(dp + jb),
+                              any_org, (so.int_kinds & 2u) != 0, (so.int_kinds & 1u) != 0, (so.flags_any & HMGPU_F_FRAC) != 0, (int)so.max_win, any_sel))) break;
     e = cudaMemcpyAsync(res_pinned ? (void*)(results + (size_t)k * chunk) : (void*)(hp + jb), dp + jb, sizeof(hmgpu_me_result) * (size_t)n,
                         cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->lane_done[l], ctx->stream);
@@ -820,10 +836,11 @@ int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const 
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || n_jobs < 0 || n_jobs > MAIL_JOBS) return hmgpu_fail(ctx, HMGPU_E_INVALID, "hmgpu_me_submit takes 1..%d jobs", MAIL_JOBS);
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  bool any_org, any_full, any_tz, any_frac;
+  bool any_org, any_full, any_tz, any_frac, any_sel;
   int max_win;
-  int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win);
+  int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, 0, &any_sel);
   if (rc) return rc;
+  any_org = any_org || any_sel;                            // here: "the side array travels" (key patterns or MV predictors)
   if (server_enabled() && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024 && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64))
   {
     if (!ctx->h_mail)
@@ -875,10 +892,12 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n_jobs > MAIL_JOBS) { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // a batch wants the whole GPU
   if (n_jobs >= PIPE_MIN_JOBS && !getenv("HMGPU_NO_PIPELINE")) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
-  bool any_org, any_full, any_tz, any_frac;
+  bool any_org, any_full, any_tz, any_frac, any_sel;
   int max_win;
-  int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win);
+  int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, 0, &any_sel);
   if (rc) return rc;
+  const bool key_blocks = any_org;                         // int16 key patterns present: selects the non-packed kernels
+  any_org = any_org || any_sel;                            // below: "the side array travels" (key patterns or MV predictors)
   if (n_jobs <= MAIL_JOBS && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64) && !getenv("HMGPU_NO_FASTPATH"))
   {
     // ---- low-latency path: mapped pinned mailbox, one fused kernel, host spins on the flags ----
@@ -898,7 +917,7 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
     const uint32_t ticket = ++ctx->mail_ticket;
     __sync_synchronize();
     const double t1 = s_trace ? now_us() : 0.0;
-    rc = hmgpu_launch_single(ctx, pack, n_jobs, mb->org_blocks, mb->slots, ticket, any_org, max_win, s_trace ? mb->trace : NULL);
+    rc = hmgpu_launch_single(ctx, pack, n_jobs, mb->org_blocks, mb->slots, ticket, key_blocks, max_win, s_trace ? mb->trace : NULL);
     if (rc) return rc;
     const double t2 = s_trace ? now_us() : 0.0;
     for (int i = 0; i < n_jobs; i++)
@@ -956,7 +975,7 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
     HMGPU_CUDA(ctx, cudaMemcpyAsync(dp + jb, hp + jb, ob, cudaMemcpyHostToDevice, ctx->stream));
   }
   rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n_jobs, any_org ? (const int16_t*)(dp + jb) : NULL,
-                       (hmgpu_me_result*)(dp + jb + ob), any_org, any_full, any_tz, any_frac, max_win);
+                       (hmgpu_me_result*)(dp + jb + ob), key_blocks, any_full, any_tz, any_frac, max_win, any_sel);
   if (rc) return rc;
   HMGPU_CUDA(ctx, cudaMemcpyAsync(res_pinned ? (void*)results : (void*)(hp + jb + ob), dp + jb + ob,
                                   sizeof(hmgpu_me_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
@@ -977,7 +996,7 @@ int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const
   const bool integer = (flags_any & HMGPU_F_INTEGER) != 0, full = (flags_any & HMGPU_F_FULL) != 0;
   return hmgpu_launch_me(ctx, (const hmgpu_me_job*)d_jobs, n_jobs, (const int16_t*)d_org_blocks,
                          (hmgpu_me_result*)d_results, (flags_any & HMGPU_F_ORG_BLOCK) != 0, integer && full,
-                         integer, (flags_any & HMGPU_F_FRAC) != 0, 64 * 1024);
+                         integer, (flags_any & HMGPU_F_FRAC) != 0, 64 * 1024, false);
 }
 
 void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4])

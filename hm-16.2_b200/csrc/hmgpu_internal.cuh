@@ -148,7 +148,7 @@ int hmgpu_launch_planes(hmgpu_ctx* ctx, int slot, const int16_t* d_src, int src_
 int hmgpu_launch_org(hmgpu_ctx* ctx, const int16_t* d_src, int src_stride);
 int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                     hmgpu_me_result* d_results, bool any_org_block, bool any_full, bool any_tz, bool any_frac,
-                    int max_win_bytes);
+                    int max_win_bytes, bool any_sel);
 int hmgpu_launch_dist(hmgpu_ctx* ctx, const int16_t* d_org, const int16_t* d_cur,
                       const hmgpu_dist_item* d_items, int n_items, uint32_t* d_out);
 int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst);

@@ -104,6 +104,16 @@ __device__ __forceinline__ void sg_job(const hmgpu_me_job& jb, const int16_t* __
       if (PACKED) full_search_block_packed(jb, refs, org, s_dyn, sh.red, &sh.res);
       else full_search_block_generic<Px>(jb, org_blocks, refs, org, (int16_t*)s_org, sh.red, &sh.res);
     }
+    else if (jb.kind == HMGPU_KIND_SELECTIVE)
+    {
+      // xTZSearchSelective (FastSearch = 2): warp 0, compute-then-replay (me_tz_impl.cuh)
+      if (tid < 32)
+      {
+        hmgpu_me_result r;
+        tz_selective_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org, r);
+        if (tid == 0) sh.res = r;
+      }
+    }
     else
     {
       // TZ is a chain of dependent rounds executed by warp 0.  Every round that reads the reference from global

@@ -35,7 +35,7 @@ __global__ void tz_classify_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
   if (j < n_jobs)
   {
     const hmgpu_me_job jb = jobs[j];
-    if ((jb.flags & HMGPU_F_INTEGER) && !(jb.flags & HMGPU_F_FULL)) cls = ((split == 1 && tz_is_small(jb)) || (split >= 2 && tz_is_lockstep(jb))) ? 0 : 1;
+    if ((jb.flags & HMGPU_F_INTEGER) && !(jb.flags & HMGPU_F_FULL) && jb.kind != HMGPU_KIND_SELECTIVE) cls = ((split == 1 && tz_is_small(jb)) || (split >= 2 && tz_is_lockstep(jb))) ? 0 : 1;
   }
   const int lane = threadIdx.x & 31;
   const uint32_t m0 = __ballot_sync(0xffffffffu, cls == 0), m1 = __ballot_sync(0xffffffffu, cls == 1);
@@ -132,8 +132,27 @@ tz_search_win_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __re
   }
 }
 
+// xTZSearchSelective jobs (FastSearch = 2): one warp per job over the whole batch, other jobs skipped
+template <typename Px, bool PACKED>
+__global__ void __launch_bounds__(TZ_WARPS * 32)
+tz_selective_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs, const int16_t* __restrict__ org_blocks,
+                    RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results)
+{
+  __shared__ __align__(16) unsigned char s_org_all[TZ_WARPS][PACKED ? 4096 : 8192];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = blockIdx.x * TZ_WARPS + warp; k < n_jobs; k += gridDim.x * TZ_WARPS)
+  {
+    const hmgpu_me_job jb = jobs[k];
+    if (!(jb.flags & HMGPU_F_INTEGER) || (jb.flags & HMGPU_F_FULL) || jb.kind != HMGPU_KIND_SELECTIVE) continue;
+    hmgpu_me_result r;
+    tz_selective_warp<Px, PACKED>(jb, org_blocks, refs, org, s_org_all[warp], r);
+    if (lane == 0) results[k] = r;
+    __syncwarp();
+  }
+}
+
 int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
-                    hmgpu_me_result* d_results, bool any_org_block)
+                    hmgpu_me_result* d_results, bool any_org_block, bool any_sel)
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
@@ -176,6 +195,14 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
     tz_search_kernel<uint8_t, false><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
   else
     tz_search_kernel<uint16_t, false><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
+  if (any_sel)
+  {
+    ctx->launches += 1; ctx->prof_launches[HMGPU_ST_TZ] += 1;
+    const int grid = min(cap, (n_jobs + TZ_WARPS - 1) / TZ_WARPS);
+    if (packed) tz_selective_kernel<uint8_t, true><<<grid, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
+    else if (ctx->px_bytes == 1) tz_selective_kernel<uint8_t, false><<<grid, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
+    else tz_selective_kernel<uint16_t, false><<<grid, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
+  }
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

@@ -489,3 +489,238 @@ __device__ __forceinline__ void tz_search_warp(const hmgpu_me_job& jb, const int
 {
   tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org, out, win_s, win, spec, role);
 }
+
+// =====================================================================================================================
+// xTZSearchSelective (FastSearch = 2; TEncSearch.cpp:4231-4383 with SEL_SEARCH_CONFIGURATION :317-330), one warp per job.
+//
+// Its xTZSearchHelp branch (:360-406) costs a point progressively -- a coarse row-sampled SAD, then the rows in between level
+// by level -- and abandons the point when an ESTIMATE (not a bound) fails to beat the running best, so whether a point is
+// accepted depends on the best cost at the moment the reference reaches it.  The device therefore separates arithmetic from
+// decisions: every lane computes, for ITS point, the raw row sums of all levels (no early exit), and the warp then replays the
+// reference's decisions point by point in emission order on those sums (sel_replay).  This keeps the mode bit-exact; it is not
+// tuned (no BASELINE configuration uses FastSearch = 2).
+// =====================================================================================================================
+
+struct SelPoint { int x, y, pnr, dist; bool valid; };
+
+// raw row sums of one point by one lane: level 0 = rows 0, 2^S, ..; level l = rows at offset 2^(S-l), step 2^(S-l+1)
+template <typename Px, bool PACKED>
+__device__ __forceinline__ void sel_point_sums(const TzJob& J, const Px* ref00, int pitch, const void* org_s, int S,
+                                               const SelPoint& p, uint32_t (&raw)[5])
+{
+#pragma unroll
+  for (int l = 0; l < 5; l++) raw[l] = 0;
+  if (!p.valid) return;
+  const Px* ref = ref00 + (ptrdiff_t)p.y * pitch + p.x;
+  for (int r = 0; r < J.pu_h; r++)
+  {
+    uint32_t rs = 0;
+    if (PACKED)
+    {
+      const uint8_t* q8 = (const uint8_t*)ref + (ptrdiff_t)r * pitch;
+      const uintptr_t a0 = (uintptr_t)q8;
+      const int sh = (int)(a0 & 3) * 8;
+      const uint32_t* q = (const uint32_t*)(a0 & ~(uintptr_t)3);
+      const uint32_t* o = (const uint32_t*)org_s + r * (J.pu_w >> 2);
+      uint32_t lo = __ldg(q);
+      for (int k = 0; k < (J.pu_w >> 2); k++)
+      {
+        const uint32_t hi = __ldg(q + k + 1);
+        rs = vabsdiff4_acc(__funnelshift_r(lo, hi, sh), o[k], rs);
+        lo = hi;
+      }
+    }
+    else
+    {
+      const Px* pr = ref + (ptrdiff_t)r * pitch;
+      const int16_t* o = (const int16_t*)org_s + r * J.pu_w;
+      for (int k = 0; k < J.pu_w; k++) rs += (uint32_t)hm_abs((int)o[k] - (int)__ldg(pr + k));
+    }
+    // level of row r: multiples of 2^S are level 0, otherwise S - ctz(r)
+    const int tzc = __ffs(r | (1 << S)) - 1;               // min(ctz(r), S)
+    const int lvl = tzc >= S ? 0 : S - tzc;
+#pragma unroll
+    for (int l = 0; l < 5; l++) if (lvl == l) raw[l] += rs;
+  }
+}
+
+// replay of xTZSearchHelp's selective branch over the points held by lanes 0 .. n-1, in lane (= emission) order
+__device__ __forceinline__ void sel_replay(const TzJob& J, int S, int n, const SelPoint& p, const uint32_t (&raw)[5], TzBest& best)
+{
+  const int bds = J.bit_depth - 8;
+  const uint32_t bit = hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, p.x, p.y);
+  for (int i = 0; i < n; i++)
+  {
+    const bool v = __shfl_sync(0xffffffffu, (int)p.valid, i) != 0;
+    if (!v) continue;                                      // uniform
+    const int x = __shfl_sync(0xffffffffu, p.x, i), y = __shfl_sync(0xffffffffu, p.y, i);
+    const int pnr = __shfl_sync(0xffffffffu, p.pnr, i), dist = __shfl_sync(0xffffffffu, p.dist, i);
+    const uint32_t bc = __shfl_sync(0xffffffffu, bit, i);
+    uint32_t r[5];
+#pragma unroll
+    for (int l = 0; l < 5; l++) r[l] = __shfl_sync(0xffffffffu, raw[l], i);
+    best.n_cand += 1;
+    int sh = S;
+    uint32_t tmp = (r[0] << sh) >> bds;
+    if (tmp + bc < best.cost)
+    {
+      uint32_t sad = tmp >> sh;
+      int l = 1;
+      while (sh > 0)
+      {
+        const int is = sh - 1;
+        const uint32_t rl = l == 1 ? r[1] : (l == 2 ? r[2] : (l == 3 ? r[3] : r[4]));
+        tmp = (rl << sh) >> bds;
+        sad += tmp >> sh;
+        if (((sad << is) + bc) > best.cost) break;
+        sh--; l++;
+      }
+      if (sh == 0)
+      {
+        sad += bc;
+        if (sad < best.cost) { best.cost = sad; best.x = x; best.y = y; best.dist = dist; best.pnr = pnr; best.round = 0; }
+      }
+    }
+  }
+}
+
+template <typename Px, bool PACKED>
+__device__ __forceinline__ void sel_batch(const TzJob& J, const Px* ref00, int pitch, const void* org_s, int S, int n,
+                                          const SelPoint& p, TzBest& best)
+{
+  uint32_t raw[5];
+  sel_point_sums<Px, PACKED>(J, ref00, pitch, org_s, S, p, raw);
+  sel_replay(J, S, n, p, raw, best);
+}
+
+// side data of a selective job: m_acMvPredictors[MD_LEFT, MD_ABOVE, MD_ABOVE_RIGHT] as 6 int16 at org_blocks[org_offset]
+template <typename Px, bool PACKED>
+__device__ __forceinline__ void tz_selective_warp(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
+                                                  const RefTable& refs, const OrgView& org, unsigned char* s_org,
+                                                  hmgpu_me_result& out)
+{
+  const int lane = threadIdx.x & 31;
+  TzJob J;
+  J.pu_w = jb.pu_w; J.pu_h = jb.pu_h; J.sub_shift = 0; J.rows = jb.pu_h;
+  J.pred_x = jb.pred_x; J.pred_y = jb.pred_y; J.ui_cost = jb.ui_cost;
+  J.L = jb.win_l; J.T = jb.win_t; J.R = jb.win_r; J.B = jb.win_b;
+  J.bit_depth = refs.bit_depth;
+  J.win_s = NULL; J.win_pitch = 0; J.wx0 = J.wy0 = 0; J.wx1 = J.wy1 = -1; J.win_ox = J.win_oy = 0;
+  const int pitch = refs.pitch;
+  const Px* ref00 = (const Px*)refs.base[jb.ref_slot] + (ptrdiff_t)jb.pu_y * pitch + jb.pu_x;
+  tz_stage_org<Px, PACKED>(jb, org_blocks, org, s_org, lane, 32);
+  __syncwarp();
+  const int S = jb.pu_h > 32 ? 4 : (jb.pu_h > 16 ? 3 : (jb.pu_h > 8 ? 2 : 1));      // :367-374
+  TzBest best; best.cost = 0xffffffffu; best.x = 0; best.y = 0; best.dist = 0; best.round = 0; best.pnr = 0; best.n_cand = 0;
+  const bool has2n = (jb.flags & HMGPU_F_HAS_2NX2N) != 0;
+  auto clipq = [&](int vx, int vy, int& ox, int& oy) {
+    ox = min((int)jb.clip_hmax, max((int)jb.clip_hmin, vx)) >> 2;
+    oy = min((int)jb.clip_vmax, max((int)jb.clip_vmin, vy)) >> 2;
+  };
+
+  // ---- start points (:4267-4295): the MVP, the three spatial predictors, zero, the 2Nx2N integer MV ----
+  {
+    SelPoint p; p.x = 0; p.y = 0; p.pnr = 0; p.dist = 0; p.valid = lane < (has2n ? 6 : 5);
+    if (lane == 0) clipq(jb.start_x, jb.start_y, p.x, p.y);
+    else if (lane >= 1 && lane <= 3)
+      clipq((int)__ldcv(org_blocks + jb.org_offset + 2 * (lane - 1)), (int)__ldcv(org_blocks + jb.org_offset + 2 * (lane - 1) + 1), p.x, p.y);
+    else if (lane == 5) clipq((int)(int16_t)(jb.i2n_x << 2), (int)(int16_t)(jb.i2n_y << 2), p.x, p.y);
+    sel_batch<Px, PACKED>(J, ref00, pitch, s_org, S, has2n ? 6 : 5, p, best);
+  }
+  int rL = J.L, rT = J.T, rR = J.R, rB = J.B;              // iSrchRng*: re-centred when the 2Nx2N MV was tested (:4297-4306)
+  if (has2n)
+  {
+    const int px = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(best.x << 2)));
+    const int py = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(best.y << 2)));
+    const int sr4 = jb.search_range << 2;
+    rL = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(px - sr4))) >> 2;
+    rT = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(py - sr4))) >> 2;
+    rR = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(px + sr4))) >> 2;
+    rB = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(py + sr4))) >> 2;
+  }
+
+  // ---- initial search (:4308-4324): step-4 grid of centres, each with the diamonds at distance 1 and 2 (13 points) ----
+  const int bx0 = best.x, by0 = best.y;
+  {
+    const int sri = jb.search_range >> 2;
+    const int fl = max(bx0 - sri, rL), ft = max(by0 - sri, rT), fr = min(bx0 + sri, rR), fb = min(by0 + sri, rB);
+    const int gnx = fr >= fl ? (fr - fl) / 4 + 1 : 0, gny = fb >= ft ? (fb - ft) / 4 + 1 : 0;
+    const int n_centres = gnx * gny;
+    for (int c0 = 0; c0 < n_centres; c0 += 2)              // two centres (26 points) per pass, emission order = lane order
+    {
+      const int ci = c0 + (lane >= 13 ? 1 : 0), k = lane >= 13 ? lane - 13 : lane;
+      SelPoint p; p.x = 0; p.y = 0; p.pnr = 0; p.dist = 0; p.valid = false;
+      if (lane < 26 && ci < n_centres)
+      {
+        const int cx = fl + (ci % gnx) * 4, cy = ft + (ci / gnx) * 4;
+        if (k == 0) { p.x = cx; p.y = cy; p.valid = true; }
+        else
+        {
+          const int d = k <= 4 ? 1 : 2, i = k <= 4 ? k - 1 : k - 5;
+          tz_diamond_point(cx, cy, d, i, p.x, p.y, p.pnr, p.dist);
+          p.valid = tz_in_window(J, cx, cy, p.x, p.y);
+        }
+      }
+      sel_batch<Px, PACKED>(J, ref00, pitch, s_org, S, 26, p, best);
+    }
+  }
+
+  const bool far_from_pred = abs(best.x - bx0) > 8 || abs(best.y - by0) > 8;          // iMVDistThresh (:4326)
+  if (far_from_pred)
+  {
+    // every position of the window, raster order, distance 1 (:4329-4338)
+    const int nx = rR - rL + 1, ny = rB - rT + 1;
+    const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
+    for (int b0 = 0; b0 < total; b0 += 32)
+    {
+      const int i = b0 + lane;
+      SelPoint p; p.pnr = 0; p.dist = 1; p.valid = i < total;
+      p.x = rL + (p.valid ? i % nx : 0); p.y = rT + (p.valid ? i / nx : 0);
+      sel_batch<Px, PACKED>(J, ref00, pitch, s_org, S, 32, p, best);
+    }
+  }
+  else
+  {
+    while (best.dist > 0)                                  // star refinement (:4340-4375)
+    {
+      const int cx = best.x, cy = best.y;
+      best.dist = 0; best.pnr = 0;
+      for (int d = 1; d < jb.search_range + 1; d <<= 1)
+      {
+        const int npts = d == 1 ? 4 : (d <= 8 ? 8 : 16);
+        SelPoint p; p.x = 0; p.y = 0; p.pnr = 0; p.dist = 0; p.valid = false;
+        if (lane < npts)
+        {
+          tz_diamond_point(cx, cy, d, lane, p.x, p.y, p.pnr, p.dist);
+          p.valid = tz_in_window(J, cx, cy, p.x, p.y);
+        }
+        sel_batch<Px, PACKED>(J, ref00, pitch, s_org, S, npts, p, best);
+      }
+      if (best.dist == 1)
+      {
+        best.dist = 0;
+        if (best.pnr >= 1 && best.pnr <= 8)
+        {
+          const int nr = best.pnr, tcx = best.x, tcy = best.y;
+          SelPoint p; p.pnr = 0; p.dist = 2; p.valid = false; p.x = 0; p.y = 0;
+          if (lane < 2)
+          {
+            p.x = tcx + c_two_point[nr][lane == 0 ? 0 : 2];
+            p.y = tcy + c_two_point[nr][lane == 0 ? 1 : 3];
+            p.valid = tz_in_window(J, tcx, tcy, p.x, p.y);
+          }
+          sel_batch<Px, PACKED>(J, ref00, pitch, s_org, S, 2, p, best);
+        }
+      }
+    }
+  }
+
+  if (lane == 0)
+  {
+    out.int_x = (int16_t)best.x; out.int_y = (int16_t)best.y;
+    out.int_sad = best.cost - hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, best.x, best.y);
+    out.half_x = out.half_y = out.qter_x = out.qter_y = 0;
+    out.frac_cost = 0;
+    out.n_cand = best.n_cand;
+  }
+}

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libhmgpu.so")
 # flags (include/hmgpu.h)
 F_FEN, F_HADME, F_LOSSLESS, F_HAS_2NX2N, F_FULL, F_INTEGER, F_FRAC, F_ORG_BLOCK = (1 << i for i in range(8))
 DF_SAD, DF_SAD_GENERIC, DF_HADS, DF_SSE = range(4)
+KIND_DEFAULT, KIND_SELECTIVE = 0, 1
 
 ME_JOB = np.dtype([
     ("pu_x", "<i2"), ("pu_y", "<i2"), ("pu_w", "u1"), ("pu_h", "u1"), ("ref_slot", "u1"), ("flags", "u1"),
@@ -22,7 +23,7 @@ ME_JOB = np.dtype([
     ("win_l", "<i2"), ("win_t", "<i2"), ("win_r", "<i2"), ("win_b", "<i2"),
     ("i2n_x", "<i2"), ("i2n_y", "<i2"),
     ("clip_hmin", "<i2"), ("clip_hmax", "<i2"), ("clip_vmin", "<i2"), ("clip_vmax", "<i2"),
-    ("search_range", "<i2"), ("reserved", "<i2"),
+    ("search_range", "<i2"), ("kind", "<i2"),
     ("ui_cost", "<u4"), ("org_offset", "<u4")], align=True)
 ME_RESULT = np.dtype([
     ("int_x", "<i2"), ("int_y", "<i2"), ("int_sad", "<u4"),

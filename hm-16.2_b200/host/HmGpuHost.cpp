@@ -124,7 +124,8 @@ Void HmGpuHost::xUploadOrg( TComDataCU* pcCU )
 Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
                               const TComMv& rcMvSrchRngLT, const TComMv& rcMvSrchRngRB, const TComMv& rcMvPred, const TComMv& rcMvIn,
                               Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
-                              Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut )
+                              Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut,
+                              const TComMv* pacSelectivePred )
 {
   const Double tEnter = xNow();
   xInit( pcCU );
@@ -177,6 +178,15 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
     }
   }
   j.flags = (uint8_t)flags;
+  Short side[6] = { 0, 0, 0, 0, 0, 0 };
+  if ( pacSelectivePred && !bBi && !bFullSearch )
+  {
+    // FastSearch=2: xTZSearchSelective; its three spatial MV predictors travel in the side array
+    j.kind = HMGPU_KIND_SELECTIVE;
+    for ( Int k = 0; k < 3; k++ ) { side[2 * k] = pacSelectivePred[k].getHor(); side[2 * k + 1] = pacSelectivePred[k].getVer(); }
+    memcpy( m_keyBlock, side, sizeof( side ) );
+    keyElems = 6;
+  }
 
   hmgpu_me_result r;
   if ( m_queueing && !bBi )
@@ -184,7 +194,10 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
     // pass 0 of the patched predInterSearch loop: remember the job, the result is handed out in pass 1
     if ( m_queueLen < MAX_QUEUE )
     {
-      m_queueJobs[m_queueLen++] = j;
+      memcpy( m_queueSide + 6 * m_queueLen, side, sizeof( side ) );
+      m_queueJobs[m_queueLen] = j;
+      m_queueJobs[m_queueLen].org_offset = 6 * m_queueLen;
+      m_queueLen++;
     }
     m_totalSeconds += xNow() - tEnter;
     return;
@@ -194,7 +207,9 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
   {
     for ( Int k = 0; k < m_queueLen; k++ )
     {
-      if ( !m_queueUsed[k] && memcmp( &m_queueJobs[k], &j, sizeof( j ) ) == 0 ) { hit = k; break; }
+      hmgpu_me_job q = m_queueJobs[k];
+      q.org_offset = j.org_offset;
+      if ( !m_queueUsed[k] && memcmp( &q, &j, sizeof( j ) ) == 0 && memcmp( m_queueSide + 6 * k, side, sizeof( side ) ) == 0 ) { hit = k; break; }
     }
   }
   if ( hit >= 0 )
@@ -235,7 +250,7 @@ Void HmGpuHost::submitQueue()
   if ( m_queueLen > 0 )
   {
     const Double t0 = xNow();
-    if ( hmgpu_me_submit( m_ctx, m_queueJobs, m_queueLen, NULL, 0 ) != HMGPU_OK )
+    if ( hmgpu_me_submit( m_ctx, m_queueJobs, m_queueLen, m_queueSide, 6 * m_queueLen ) != HMGPU_OK )
     {
       xFail( "hmgpu_me_submit" );
     }

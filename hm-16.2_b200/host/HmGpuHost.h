@@ -35,7 +35,8 @@ public:
   Void motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
                      const TComMv& rcMvSrchRngLT, const TComMv& rcMvSrchRngRB, const TComMv& rcMvPred, const TComMv& rcMvIn,
                      Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
-                     Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut );
+                     Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut,
+                     const TComMv* pacSelectivePred = 0 );   ///< FastSearch=2: m_acMvPredictors[3] (xPatternSearchFast, TEncSearch.cpp:4004-4008)
 
   /// Batching of the uni-directional searches of one PU (TEncSearch::predInterSearch, TEncSearch.cpp:3177-3257): the
   /// searches of the different lists / reference pictures of a PU do not depend on each other, so the patched loop
@@ -77,6 +78,7 @@ private:
   struct hmgpu_me_job*    m_queueJobs;
   struct hmgpu_me_result* m_queueRes;
   Bool        m_queueUsed[MAX_QUEUE];
+  Short       m_queueSide[MAX_QUEUE * 6];   ///< MV predictors of queued selective searches (6 per job)
   // statistics
   UInt64      m_calls, m_cands, m_checked;
   UInt64      m_gpuCalls;       ///< hmgpu_me_search invocations (<= m_calls: queued searches share one)

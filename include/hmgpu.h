@@ -115,6 +115,11 @@ enum
                                    TComYuv.cpp:393-424) at org_offset, stride pu_w */
 };
 
+/* job.kind.  HMGPU_KIND_SELECTIVE: the integer search is xTZSearchSelective (FastSearch = 2, TEncSearch.cpp:4231-4383); needs
+ * HMGPU_F_INTEGER without HMGPU_F_FULL / HMGPU_F_ORG_BLOCK; org_offset then addresses six int16 in org_blocks:
+ * m_acMvPredictors[MD_LEFT], [MD_ABOVE], [MD_ABOVE_RIGHT] (hor, ver; quarter-pel) as xPatternSearchFast collects them (:4004-4008). */
+enum { HMGPU_KIND_DEFAULT = 0, HMGPU_KIND_SELECTIVE = 1 };
+
 typedef struct hmgpu_me_job
 {
   int16_t  pu_x, pu_y;            /* PU origin, luma samples, picture coordinates */
@@ -127,7 +132,7 @@ typedef struct hmgpu_me_job
   int16_t  i2n_x, i2n_y;          /* m_integerMv2Nx2N[list][ref] (integer pel) */
   int16_t  clip_hmin, clip_hmax, clip_vmin, clip_vmax; /* TComDataCU::clipMv bounds (quarter-pel) */
   int16_t  search_range;          /* m_iSearchRange (adaptive SR), TZ only */
-  int16_t  reserved;
+  int16_t  kind;                  /* HMGPU_KIND_*: 0 = the search the flags select */
   uint32_t ui_cost;               /* TComRdCost::m_uiCost after getMotionCost(true,0,..) */
   uint32_t org_offset;            /* HMGPU_F_ORG_BLOCK: element offset into org_blocks */
 } hmgpu_me_job;                   /* 48 bytes */

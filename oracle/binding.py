@@ -38,6 +38,7 @@ class SearchT(C.Structure):
         ("mv_x", ci), ("mv_y", ci), ("sad", cu),
         ("half_x", ci), ("half_y", ci), ("qter_x", ci), ("qter_y", ci), ("frac_cost", cu),
         ("n_cand", cu),
+        ("sel_pred", ci * 2 * 3),
     ]
 
 
@@ -143,6 +144,8 @@ def ref():
     L.ref_pattern_search.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cu, ci, ci, ci, ci, i32p, u32p]
     L.ref_tz_search.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cu, ci, ci, ci, ci,
                                 ci, ci, ci, ci, ci, ci, ci, ci, i32p, u32p]
+    L.ref_tz_selective.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cu, ci, ci, ci,
+                                   ci, ci, ci, ci, ci, ci, ci, ci, i32p, i32p, u32p]
     L.ref_frac_search.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, cu, ci, ci, ci, ci, ci, i32p, i32p, u32p]
     L.ref_fwd_transform.argtypes = [ci, i32p, i32p, ci, ci, ci]
     L.ref_partial_butterfly.argtypes = [ci, i32p, i32p, ci, ci]

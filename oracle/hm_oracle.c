@@ -430,11 +430,59 @@ typedef struct
   int best_x, best_y;
   unsigned best_dist, best_round;
   int point_nr;
+  int selective;                        /* FastSearch == SELECTIVE: xTZSearchHelp takes its progressive branch */
 } tz_state;
+
+/* DistFunc of the selective branch: SAD over rows row0, row0 + 2^sh, ... (H >> sh of them), "<< sh", then the bit-depth
+ * shift -- what xGetSAD* return with pOrg/pCur moved down by row0 rows and iSubShift = sh (TComRdCost.cpp:493-964). */
+static uint32_t sel_sad(const hmo_search_t* s, int x, int y, int row0, int sh)
+{
+  const int16_t* cur = s->ref + y * s->ref_stride + x;
+  uint32_t sum = 0;
+  for (int k = 0; k < (s->h >> sh); k++)
+  {
+    const int r = row0 + (k << sh);
+    for (int i = 0; i < s->w; i++) sum += (uint32_t)iabs(s->org[r * s->org_stride + i] - cur[r * s->ref_stride + i]);
+  }
+  return (sum << sh) >> (s->bit_depth - 8);
+}
+
+/* xTZSearchHelp (TEncSearch.cpp:333-424), selective branch (:360-406): a coarse row-sampled SAD first, refined level by level,
+ * abandoned as soon as the running estimate cannot beat the best cost. */
+static void tz_try_selective(hmo_search_t* s, tz_state* z, int x, int y, int point_nr, unsigned dist)
+{
+  s->n_cand++;
+  const uint32_t bit_cost = hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 2, x, y);
+  int sh = s->h > 32 ? 4 : (s->h > 16 ? 3 : (s->h > 8 ? 2 : 1));
+  uint32_t sad = 0;
+  uint32_t tmp = sel_sad(s, x, y, 0, sh);
+  if (tmp + bit_cost < z->best_cost)
+  {
+    sad += tmp >> sh;
+    while (sh > 0)
+    {
+      const int is = sh - 1;
+      tmp = sel_sad(s, x, y, 1 << is, sh);
+      sad += tmp >> sh;
+      if (((sad << is) + bit_cost) > z->best_cost) break;
+      sh--;
+    }
+    if (sh == 0)
+    {
+      sad += bit_cost;
+      if (sad < z->best_cost)
+      {
+        z->best_cost = sad; z->best_x = x; z->best_y = y;
+        z->best_dist = dist; z->best_round = 0; z->point_nr = point_nr;
+      }
+    }
+  }
+}
 
 /* xTZSearchHelp (TEncSearch.cpp:333-424), non-selective branch: strict '<' update. */
 static void tz_try(hmo_search_t* s, tz_state* z, int x, int y, int point_nr, unsigned dist)
 {
+  if (z->selective) { tz_try_selective(s, z, x, y, point_nr, dist); return; }
   const uint32_t c = int_cost(s, x, y);
   if (c < z->best_cost)
   {
@@ -581,6 +629,75 @@ void hmo_tz_search(hmo_search_t* s)
     {
       z.best_dist = 0;
       if (z.point_nr != 0) tz_two_point(s, &z, win);
+    }
+  }
+  s->mv_x = z.best_x; s->mv_y = z.best_y;
+  s->sad = z.best_cost - hmo_mv_cost(s->ui_cost, s->pred_x, s->pred_y, 2, z.best_x, z.best_y);
+}
+
+/* TEncSearch::xTZSearchSelective (TEncSearch.cpp:4231-4383) with SEL_SEARCH_CONFIGURATION (:317-330): start points = the MVP,
+ * the left / above / above-right predictors, zero and the optional 2Nx2N integer MV (window re-centred, local bounds only);
+ * a step-4 grid of centres within SearchRange/4 of the best start, each followed by the diamonds at distance 1 and 2; then a
+ * full raster of the window when the best moved more than 8 samples away, else the star refinement of xTZSearch. */
+void hmo_tz_selective(hmo_search_t* s)
+{
+  int bd[4];
+  hmo_clip_bounds(s->pic_w, s->pic_h, s->cu_x, s->cu_y, bd);
+  const int win[4] = { s->l, s->t, s->r, s->b };          /* what the pattern helpers see (pcMvSrchRngLT/RB) */
+  int rwin[4] = { s->l, s->t, s->r, s->b };               /* iSrchRngHorLeft.. : re-centred when the 2Nx2N MV was tested */
+  tz_state z; memset(&z, 0, sizeof z); z.best_cost = UINT_MAX; z.selective = 1;
+  s->n_cand = 0;
+
+  int st[2] = { s->start_x, s->start_y };
+  clip_with(bd, st);
+  tz_try(s, &z, st[0] >> 2, st[1] >> 2, 0, 0);             /* :4267 */
+  for (int i = 0; i < 3; i++)                              /* :4270-4279 bTestOtherPredictedMV */
+  {
+    int m[2] = { s->sel_pred[i][0], s->sel_pred[i][1] };
+    clip_with(bd, m);
+    tz_try(s, &z, m[0] >> 2, m[1] >> 2, 0, 0);
+  }
+  tz_try(s, &z, 0, 0, 0, 0);                               /* :4282-4285 */
+  if (s->has_2nx2n)                                        /* :4287-4306 */
+  {
+    int m[2] = { s16(s->i2n_x << 2), s16(s->i2n_y << 2) };
+    clip_with(bd, m);
+    tz_try(s, &z, m[0] >> 2, m[1] >> 2, 0, 0);
+    search_range_with(bd, s16(z.best_x << 2), s16(z.best_y << 2), s->search_range, rwin);
+  }
+
+  /* initial search (:4308-4324) */
+  const int bx0 = z.best_x, by0 = z.best_y;
+  const int sri = s->search_range >> 2, step = 4;
+  const int fl = imax(bx0 - sri, rwin[0]), ft = imax(by0 - sri, rwin[1]);
+  const int fr = imin(bx0 + sri, rwin[2]), fb = imin(by0 + sri, rwin[3]);
+  for (int y = ft; y <= fb; y += step)
+    for (int x = fl; x <= fr; x += step)
+    {
+      tz_try(s, &z, x, y, 0, 0);
+      tz_diamond(s, &z, win, x, y, 1);
+      tz_diamond(s, &z, win, x, y, 2);
+    }
+
+  const int far_from_pred = iabs(z.best_x - bx0) > 8 || iabs(z.best_y - by0) > 8;   /* iMVDistThresh, :4326 */
+  if (far_from_pred)                                       /* :4329-4338: every position of the window */
+  {
+    for (int y = rwin[1]; y <= rwin[3]; y++)
+      for (int x = rwin[0]; x <= rwin[2]; x++)
+        tz_try(s, &z, x, y, 0, 1);
+  }
+  else if (z.best_dist > 0)                                /* :4340-4375 star refinement */
+  {
+    while (z.best_dist > 0)
+    {
+      const int cx = z.best_x, cy = z.best_y;
+      z.best_dist = 0; z.point_nr = 0;
+      for (int d = 1; d < s->search_range + 1; d *= 2) tz_diamond(s, &z, win, cx, cy, d);
+      if (z.best_dist == 1)
+      {
+        z.best_dist = 0;
+        if (z.point_nr != 0) tz_two_point(s, &z, win);
+      }
     }
   }
   s->mv_x = z.best_x; s->mv_y = z.best_y;

@@ -62,10 +62,13 @@ typedef struct
   int mv_x, mv_y; uint32_t sad;                      /* integer search result */
   int half_x, half_y, qter_x, qter_y; uint32_t frac_cost;
   uint32_t n_cand;                                   /* candidates evaluated */
+  /* selective TZ only (FastSearch=2): m_acMvPredictors[MD_LEFT, MD_ABOVE, MD_ABOVE_RIGHT], quarter-pel */
+  int sel_pred[3][2];
 } hmo_search_t;
 
 void hmo_pattern_search(hmo_search_t* s);
 void hmo_tz_search(hmo_search_t* s);
+void hmo_tz_selective(hmo_search_t* s);   /* xTZSearchSelective (FastSearch=2) */
 void hmo_frac_search(hmo_search_t* s); /* uses s->mv_x/mv_y as integer MV */
 
 /* full xMotionEstimation tail: integer (fs: 0=TZ,1=full) + frac + final cost fix-up */

@@ -300,6 +300,32 @@ void ref_tz_search(const int16_t* org, int orgStride, int w, int h,
   mvInOut[0] = mv.getHor(); mvInOut[1] = mv.getVer(); *outSad = sad;
 }
 
+// ---- a11: xTZSearchSelective (TEncSearch.cpp:4231-4383), FastSearch = 2; selPred = m_acMvPredictors (left, above,
+// above-right; quarter-pel hor/ver pairs)
+void ref_tz_selective(const int16_t* org, int orgStride, int w, int h,
+                      const int16_t* ref, int refStride,
+                      int l, int t, int r, int b,
+                      unsigned uiCost, int predX, int predY, int bitDepth,
+                      int picW, int picH, int cuX, int cuY, int searchRange,
+                      int has2Nx2N, int i2NX, int i2NY,
+                      const int* selPred, int* mvInOut, unsigned* outSad)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  g.cfg.setFastSearch(2);
+  set_cu(picW, picH, cuX, cuY);
+  set_cost(uiCost, predX, predY, 2);
+  g.search->m_iSearchRange = searchRange;
+  for (int i = 0; i < 3; i++) g.search->m_acMvPredictors[i].set(selPred[2 * i], selPred[2 * i + 1]);
+  TComPattern pat; pat.initPattern((Pel*)org, w, h, orgStride);
+  TComMv lt(l, t), rb(r, b), mv(mvInOut[0], mvInOut[1]);
+  TComMv i2n(i2NX, i2NY);
+  Distortion sad = 0;
+  g.search->m_cDistParam.bApplyWeight = false;
+  g.search->xTZSearchSelective(g.cu, &pat, (Pel*)ref, refStride, &lt, &rb, mv, sad, has2Nx2N ? &i2n : NULL);
+  g.cfg.setFastSearch(1);
+  mvInOut[0] = mv.getHor(); mvInOut[1] = mv.getVer(); *outSad = sad;
+}
+
 // ---- a12/a13: xPatternSearchFracDIF (TEncSearch.cpp:4386-4422); cost scale follows
 // xMotionEstimation (:3892): scale 1 on entry, the function itself switches to 0.
 void ref_frac_search(const int16_t* org, int orgStride, int w, int h,

@@ -52,3 +52,9 @@ def test_randomaccess_main10_closed_gop():
     # BASELINE cfg 5 semantics at a small size: 10-bit pictures (uint16 planes, >>2 distortion shift), SearchRange 128
     _compare("--cfg", "randomaccess_main10", "--frames", "18", "--gpume", "2", "--bit-depth", "10", "--",
              "--DecodingRefreshType=2", "--IntraPeriod=16", "--SearchRange=128")
+
+
+def test_lowdelay_p_selective_search():
+    # FastSearch=2 (xTZSearchSelective): GPUME=2 cross-checks every call, GPUME=1 exercises the batched path
+    _compare("--cfg", "lowdelay_P_main", "--frames", "3", "--gpume", "2", "--", "--FastSearch=2")
+    _compare("--cfg", "lowdelay_P_main", "--frames", "3", "--gpume", "1", "--", "--FastSearch=2")

@@ -408,3 +408,43 @@ def test_mailbox_server_restarts_and_uploads():
         ctx.org_upload(fr[2])
         exp3 = oracle_me(jobs[:16], [pads[0], pads[2]], fr[2], 8)
         assert_results_equal(ctx.me_search(jobs[:16]), exp3, jobs[:16])
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+@pytest.mark.parametrize("path", ["batch", "small_calls"])
+def test_selective_search(bit_depth, path):
+    """xTZSearchSelective (FastSearch = 2): job.kind = KIND_SELECTIVE, the three spatial MV predictors in the
+    side array; batch kernels and the low-latency path against the oracle (itself pinned to the reference)"""
+    rng = np.random.default_rng(61)
+    noise = bit_depth == 10
+    fr = _frames(bit_depth, 4, noise)
+    n = 72 if path == "batch" else 30
+    jobs, _, _ = _random_jobs(rng, n, bit_depth, "tz", 2)
+    side = np.zeros(6 * n, np.int16)
+    for i in range(n):
+        jobs[i]["kind"] = hmgpu.KIND_SELECTIVE
+        jobs[i]["org_offset"] = 6 * i
+        jobs[i]["search_range"] = int(rng.choice([8, 16, 64]))
+        bd = [int(jobs[i][k]) for k in ("clip_hmin", "clip_hmax", "clip_vmin", "clip_vmax")]
+        jobs[i]["win_l"], jobs[i]["win_t"], jobs[i]["win_r"], jobs[i]["win_b"] = hmgpu.search_range(
+            bd, int(jobs[i]["pred_x"]), int(jobs[i]["pred_y"]), int(jobs[i]["search_range"]))
+        side[6 * i:6 * i + 6] = rng.integers(-80, 81, 6)
+        if i % 4 == 0:
+            side[6 * i:6 * i + 2] = (int(jobs[i]["pred_x"]) + 12, int(jobs[i]["pred_y"]) - 8)
+    pads = [padded_ref(fr[k]) for k in range(2)]
+    exp = oracle_me(jobs, pads, fr[3], bit_depth, side)
+    with hmgpu.Context(W, H, bit_depth, 2) as ctx:
+        ctx.ref_upload(0, fr[0]); ctx.ref_upload(1, fr[1]); ctx.org_upload(fr[3])
+        if path == "batch":
+            got = ctx.me_search(jobs, side)
+        else:
+            parts = []
+            for i in range(0, n, 3):
+                sub = jobs[i:i + 3].copy()
+                sub_side = np.concatenate([side[int(o):int(o) + 6] for o in sub["org_offset"]])
+                sub["org_offset"] = np.arange(len(sub)) * 6
+                parts.append(ctx.me_search(sub, sub_side))
+            got = np.concatenate(parts)
+        with pytest.raises(hmgpu.HmGpuError, match="predictors"):
+            ctx.me_search(jobs[:2], side[:6])
+    assert_results_equal(got, exp, jobs)

@@ -86,3 +86,50 @@ def test_search_batches(bd, noise):
         for f in hmgpu.ME_RESULT.names:
             if f != "n_cand":
                 assert np.array_equal(a[f], b[f]), f
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("noise", [False, True])
+def test_selective_search(bd, noise):
+    """xTZSearchSelective (FastSearch=2): oracle vs the compiled reference, job by job"""
+    import ctypes as C
+    import worklist
+    from util import M
+    O, R = B.oracle(), B.ref()
+    w, h = 416, 240
+    rng = np.random.default_rng(31)
+    if noise:
+        fr = rng.integers(0, 1 << bd, (2, h, w)).astype(np.int16)
+    else:
+        fr = synth.luma_frames(w, h, 2, bd).astype(np.int16)
+    pad = padded_ref(fr[0])
+    pw = pad.shape[1]
+    jobs = worklist.frame_jobs(w, h, n_refs=1, seed=8, search_range=int(16 if noise else 64))
+    jobs = jobs[:: max(1, len(jobs) // (40 if noise else 160))]
+    for k, j in enumerate(jobs):
+        pu_w, pu_h, x0, y0 = int(j["pu_w"]), int(j["pu_h"]), int(j["pu_x"]), int(j["pu_y"])
+        blk = np.ascontiguousarray(fr[1][y0:y0 + pu_h, x0:x0 + pu_w])
+        cu_x = -(int(j["clip_hmin"]) // 4) - 71
+        cu_y = -(int(j["clip_vmin"]) // 4) - 71
+        sel = rng.integers(-60, 61, 6).astype(np.int32)
+        if k % 3 == 0:
+            sel[:2] = (int(j["pred_x"]) + 8, int(j["pred_y"]) - 4)
+        has2n = int(bool(int(j["flags"]) & hmgpu.F_HAS_2NX2N))
+        s = B.SearchT()
+        s.org = B.ptr(blk); s.org_stride = pu_w; s.w = pu_w; s.h = pu_h
+        s.ref = B.ptr(pad, (y0 + M) * pw + x0 + M); s.ref_stride = pw
+        s.l, s.t, s.r, s.b = int(j["win_l"]), int(j["win_t"]), int(j["win_r"]), int(j["win_b"])
+        s.ui_cost = int(j["ui_cost"]); s.pred_x = int(j["pred_x"]); s.pred_y = int(j["pred_y"])
+        s.bit_depth = bd; s.cu_x = cu_x; s.cu_y = cu_y; s.pic_w = w; s.pic_h = h
+        s.search_range = int(j["search_range"])
+        s.start_x, s.start_y = int(j["start_x"]), int(j["start_y"])
+        s.has_2nx2n = has2n; s.i2n_x = int(j["i2n_x"]); s.i2n_y = int(j["i2n_y"])
+        for i in range(3):
+            s.sel_pred[i][0] = int(sel[2 * i]); s.sel_pred[i][1] = int(sel[2 * i + 1])
+        O.hmo_tz_selective(C.byref(s))
+        mv = np.array([s.start_x, s.start_y], np.int32)
+        sad = np.zeros(1, np.uint32)
+        R.ref_tz_selective(B.ptr(blk), pu_w, pu_w, pu_h, B.ptr(pad, (y0 + M) * pw + x0 + M), pw, s.l, s.t, s.r, s.b,
+                           s.ui_cost, s.pred_x, s.pred_y, bd, w, h, cu_x, cu_y, s.search_range, has2n, s.i2n_x, s.i2n_y,
+                           sel, mv, sad)
+        assert (s.mv_x, s.mv_y, s.sad) == (int(mv[0]), int(mv[1]), int(sad[0])), (k, j)

@@ -52,6 +52,11 @@ def oracle_me(jobs, refs_padded, org, bit_depth, org_blocks=None):
         if fl & hmgpu.F_INTEGER:
             if fl & hmgpu.F_FULL:
                 O.hmo_pattern_search(C.byref(s))
+            elif int(j["kind"]) == hmgpu.KIND_SELECTIVE:
+                off = int(j["org_offset"])
+                for k in range(3):
+                    s.sel_pred[k][0] = int(org_blocks[off + 2 * k]); s.sel_pred[k][1] = int(org_blocks[off + 2 * k + 1])
+                O.hmo_tz_selective(C.byref(s))
             else:
                 O.hmo_tz_search(C.byref(s))
             n = s.n_cand
