@@ -147,6 +147,40 @@ def golden_search(rng, bit_depth, n, mode):
     return jobs, res
 
 
+def golden_selective(rng, bit_depth, n):
+    """xTZSearchSelective (FastSearch=2): jobs with kind = KIND_SELECTIVE, their MV predictors (side array) and the reference's
+    integer MV / SAD (ref_tz_selective)"""
+    w_, h_ = 416, 240
+    fr = synth.luma_frames(w_, h_, 4, bit_depth).astype(np.int16)
+    jobs, _ = golden_search(rng, bit_depth, n, "tz")
+    side = rng.integers(-80, 81, 6 * n).astype(np.int16)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    pw = pads[0].shape[1]
+    rows = np.zeros((n, 3), np.int64)
+    for i in range(n):
+        j = jobs[i]
+        j["kind"] = hmgpu.KIND_SELECTIVE
+        j["org_offset"] = 6 * i
+        j["search_range"] = int(rng.choice([8, 16, 64]))
+        cu_x, cu_y = -(int(j["clip_hmin"]) // 4) - 71, -(int(j["clip_vmin"]) // 4) - 71
+        ltrb = np.zeros(4, np.int32)
+        B.ref().ref_set_search_range(w_, h_, cu_x, cu_y, int(j["pred_x"]), int(j["pred_y"]), int(j["search_range"]), ltrb)
+        j["win_l"], j["win_t"], j["win_r"], j["win_b"] = ltrb
+        if i % 4 == 0:
+            side[6 * i:6 * i + 2] = (int(j["pred_x"]) + 12, int(j["pred_y"]) - 8)
+        w, h, x0, y0 = int(j["pu_w"]), int(j["pu_h"]), int(j["pu_x"]), int(j["pu_y"])
+        blk = np.ascontiguousarray(fr[3][y0:y0 + h, x0:x0 + w])
+        pad = pads[int(j["ref_slot"])]
+        mv = np.array([int(j["start_x"]), int(j["start_y"])], np.int32)
+        sad = np.zeros(1, np.uint32)
+        B.ref().ref_tz_selective(B.ptr(blk), w, w, h, B.ptr(pad, (y0 + M) * pw + x0 + M), pw, int(ltrb[0]), int(ltrb[1]), int(ltrb[2]), int(ltrb[3]),
+                                 int(j["ui_cost"]), int(j["pred_x"]), int(j["pred_y"]), bit_depth, w_, h_, cu_x, cu_y, int(j["search_range"]),
+                                 int(bool(int(j["flags"]) & hmgpu.F_HAS_2NX2N)), int(j["i2n_x"]), int(j["i2n_y"]),
+                                 np.ascontiguousarray(side[6 * i:6 * i + 6].astype(np.int32)), mv, sad)
+        rows[i] = (int(mv[0]), int(mv[1]), int(sad[0]))
+    return jobs, side, rows
+
+
 def main():
     assert B.have_ref(), "build oracle/_ref/libhmref.so first (make -C oracle ref)"
     rng = np.random.default_rng(20261018)
@@ -164,6 +198,11 @@ def main():
             out["search_%s_res_%d" % (mode, bd)] = res
     rows, lam, lc = golden_cost(rng)
     out.update({"cost_rows": rows, "cost_lambda": lam, "cost_lambda_ui": lc, "clip_rows": golden_clip(rng)})
+    for bd in (8, 10):                                   # appended last: the arrays above keep their values
+        jobs, side, rows = golden_selective(rng, bd, 48)
+        out["sel_jobs_%d" % bd] = jobs.view(np.uint8).reshape(len(jobs), -1)
+        out["sel_side_%d" % bd] = side
+        out["sel_rows_%d" % bd] = rows
     path = os.path.join(HERE, "hm162_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -102,3 +102,17 @@ def test_searches(bd, mode):
             continue
         assert np.array_equal(got[f], exp[f]), f
     assert (got["n_cand"] >= 18).all()
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_selective_search(bd):
+    """xTZSearchSelective (FastSearch=2) answers of the reference: integer MV and SAD"""
+    from util import oracle_me
+    jobs = np.ascontiguousarray(G["sel_jobs_%d" % bd]).view(hmgpu.ME_JOB).reshape(-1).copy()
+    jobs["flags"] &= np.uint8(~hmgpu.F_FRAC & 0xff)          # the fixture holds the integer search only
+    side, rows = G["sel_side_%d" % bd], G["sel_rows_%d" % bd]
+    fr = synth.luma_frames(416, 240, 4, bd).astype(np.int16)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    got = oracle_me(jobs, pads, fr[3], bd, side)
+    assert np.array_equal(got["int_x"], rows[:, 0]) and np.array_equal(got["int_y"], rows[:, 1])
+    assert np.array_equal(got["int_sad"].astype(np.int64), rows[:, 2])
