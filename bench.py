@@ -246,7 +246,7 @@ def run_ours(args, rank, world, local_rank):
         ops, byts = work[dom]
         dur = stage_ms[dom] * 1e-3
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic_csv = {"tz": "r1d_ncu_tz_search.csv", "frac_dist": "r1d_ncu_frac2_dist.csv"}.get(dom)
+        traffic_csv = {"tz": "r1k_ncu_tz_search.csv", "frac_dist": "r1j_ncu_frac2_dist.csv"}.get(dom)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": byts / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": byts / dur / 1e9 / hbm_peak, "traffic": ncu_traffic(traffic_csv) if traffic_csv else None,
                     "traffic_source": ("profiles/" + traffic_csv) if traffic_csv else None,
