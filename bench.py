@@ -279,6 +279,7 @@ def run_ours(args, rank, world, local_rank):
             out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak, int_peak)
         if world == 1 and not args.no_encode:
             out["encode"] = encode_runs()
+            out["encode_shared_gpu"] = encode_shared_gpu_leg(local_rank)
         print(json.dumps(out))
     ctx.close()
     if dist is not None:
@@ -393,6 +394,43 @@ def encode_segment_leg(rank, world, local_rank, dist):
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
     return out
+
+
+def encode_shared_gpu_leg(local_rank, n_procs=8):
+    """Several encoder instances on ONE GPU (under CUDA MPS), beside the same number of CPU HM processes on the host cores:
+    n_procs closed 16-frame segments (encoder_randomaccess_main.cfg, 416x240), one process per segment, all at once."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import encode_compare
+    if not encode_compare.available():
+        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
+    import segments
+    import synth
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    w, h, n = 416, 240, 16
+    tmp = tempfile.mkdtemp(prefix="hmshare_")
+    cfg = os.path.join(encode_compare.CFG_DIR, "encoder_randomaccess_main.cfg")
+    extra = ["--DecodingRefreshType=2", "--IntraPeriod=16"]
+    yuvs = [synth.write_yuv(os.path.join(tmp, "s%d.yuv" % k), w, h, n, 8, seed=4321 + k) for k in range(n_procs)]
+
+    def many(enc, tag, more, env):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(n_procs) as pool:
+            outs = list(pool.map(lambda k: encode_compare.run(enc, cfg, yuvs[k], w, h, n, 32, os.path.join(tmp, "%s%d" % (tag, k)),
+                                                              extra + more, env=env), range(n_procs)))
+        return time.perf_counter() - t0, outs
+
+    with segments.MpsDaemon() as mps:
+        env = dict(mps.env, HMGPU_DEVICE=str(local_rank))
+        g_s, g = many(encode_compare.GPU_ENC, "g", ["--GPUME=1"], env)
+        mps_ok = mps.ok
+    c_s, c = many(encode_compare.REF_ENC, "c", [], None)
+    same = all(a["bitstream_md5"] == b["bitstream_md5"] and a["recon_md5"] == b["recon_md5"] for a, b in zip(g, c))
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return {"workload": "%d encoder processes, one closed 16-frame segment each (randomaccess_main, 416x240), started together" % n_procs,
+            "mps": mps_ok, "host_cores": os.cpu_count(), "gpu_procs_on_one_gpu_fps_total": n_procs * n / g_s, "gpu_s": g_s,
+            "cpu_procs_fps_total": n_procs * n / c_s, "cpu_s": c_s, "all_md5_identical": same}
 
 
 # ---- the reference on the host cores ------------------------------------------------------------
