@@ -396,7 +396,7 @@ def encode_segment_leg(rank, world, local_rank, dist):
     return out
 
 
-def encode_shared_gpu_leg(local_rank, n_procs=8):
+def encode_shared_gpu_leg(local_rank, n_procs=4):
     """Several encoder instances on ONE GPU (under CUDA MPS), beside the same number of CPU HM processes on the host cores:
     n_procs closed 16-frame segments (encoder_randomaccess_main.cfg, 416x240), one process per segment, all at once."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -426,11 +426,16 @@ def encode_shared_gpu_leg(local_rank, n_procs=8):
         mps_ok = mps.ok
     c_s, c = many(encode_compare.REF_ENC, "c", [], None)
     same = all(a["bitstream_md5"] == b["bitstream_md5"] and a["recon_md5"] == b["recon_md5"] for a, b in zip(g, c))
+    import re
+    setup = [float(m.group(1)) for o in g for m in [re.search(r"([0-9.]+) s waiting for the one-time CUDA set-up", " ".join(o["gpume"]))] if m]
+    search = [float(m.group(1)) for o in g for m in [re.search(r"([0-9.]+) s in motionSearch overall", " ".join(o["gpume"]))] if m]
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
     return {"workload": "%d encoder processes, one closed 16-frame segment each (randomaccess_main, 416x240), started together" % n_procs,
             "mps": mps_ok, "host_cores": os.cpu_count(), "gpu_procs_on_one_gpu_fps_total": n_procs * n / g_s, "gpu_s": g_s,
-            "cpu_procs_fps_total": n_procs * n / c_s, "cpu_s": c_s, "all_md5_identical": same}
+            "cpu_procs_fps_total": n_procs * n / c_s, "cpu_s": c_s, "all_md5_identical": same,
+            "gpu_proc_cuda_setup_s_mean": float(np.mean(setup)) if setup else None,
+            "gpu_proc_binding_s_mean_incl_setup": float(np.mean(search)) if search else None}
 
 
 # ---- the reference on the host cores ------------------------------------------------------------

@@ -747,6 +747,13 @@ static int server_start(hmgpu_ctx* ctx, Mailbox* mb, int dyn_bytes)
   return HMGPU_OK;
 }
 
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();                                  // be kind to the sibling hyper-thread while spinning
+#endif
+}
+
 static bool slot_ready(const volatile uint32_t* slot, uint32_t ticket, hmgpu_me_result* out)
 {
   uint32_t w[8];
@@ -791,6 +798,7 @@ static int server_wait(hmgpu_ctx* ctx, Mailbox* mb, hmgpu_me_result* results)
     unsigned spins = 0;
     while (!slot_ready(slot, ticket, &results[i]))
     {
+      cpu_relax();
       if ((++spins & 63u) == 0 && ((volatile uint32_t*)mb->exited)[i] == ctx->srv_gen)
       {
         // this CTA stopped polling (idle exit racing with the call); anything it published is already visible

@@ -298,8 +298,12 @@ me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org
   const volatile uint32_t* line = lines + blockIdx.x * 16;
   unsigned long long t_last = 0;
   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+  // A CTA whose line has carried no job for a while polls less often: with several encoder processes on one GPU (MPS) the
+  // 16 x 64-byte reads per poll period of every server add up on PCIe.  CTA 0 (every call has a job 0) always polls flat out.
+  int cold = 0;
   for (;;)
   {
+    if (blockIdx.x > 0 && cold > 16) __nanosleep(2000);
     if (tid < 32)
     {
       // one 64-byte read of the line by lanes 0..15, validated by its check word
@@ -330,6 +334,7 @@ me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org
     if (cmd == 1)
     {
       last_ticket = s_line[12];
+      cold = (s_line[14] & 1u) ? 0 : cold + 1;
       if (s_line[14] & 1u)                                     // this CTA has a job in this call
       {
         hmgpu_me_job jb;

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cmath>
 #include <ctime>
+#include <thread>
 
 #include "TLibCommon/TComRom.h"
 #include "TLibCommon/TComDataCU.h"
@@ -30,7 +31,7 @@ HmGpuHost& HmGpuHost::instance()
 }
 
 HmGpuHost::HmGpuHost()
-: m_ctx( NULL ), m_picW( 0 ), m_picH( 0 ), m_tick( 0 ), m_orgPic( NULL ), m_orgPoc( -1 ), m_keyBlock( NULL )
+: m_ctx( NULL ), m_warmThread( NULL ), m_warmCtx( NULL ), m_warmW( 0 ), m_warmH( 0 ), m_warmBitDepth( 0 ), m_picW( 0 ), m_picH( 0 ), m_tick( 0 ), m_orgPic( NULL ), m_orgPoc( -1 ), m_keyBlock( NULL )
 , m_queueing( false ), m_queueLen( 0 ), m_queueDone( false ), m_queueJobs( NULL ), m_queueRes( NULL )
 , m_gpuCalls( 0 ), m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_totalSeconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
 {
@@ -45,7 +46,7 @@ HmGpuHost::~HmGpuHost()
   if ( m_ctx )
   {
     fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu in %llu GPU calls, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
-                     "%.3f s in motionSearch overall, %.3f s one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
+                     "%.3f s in motionSearch overall, %.3f s waiting for the one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
              (unsigned long long)m_calls, (unsigned long long)m_gpuCalls, (unsigned long long)m_cands, m_seconds, m_calls ? m_seconds / (Double)m_calls * 1e6 : 0.0,
              m_seconds > 0 ? (Double)m_cands / m_seconds / 1e6 : 0.0, m_totalSeconds, m_initSeconds,
              (unsigned long long)m_uploads, m_uploadSeconds,
@@ -64,14 +65,40 @@ Void HmGpuHost::xFail( const char* what )
   exit( 1 );
 }
 
+Void HmGpuHost::prewarm( Int iPicWidth, Int iPicHeight, Int iBitDepth )
+{
+  if ( m_ctx || m_warmThread ) return;
+  m_warmW = iPicWidth; m_warmH = iPicHeight; m_warmBitDepth = iBitDepth;
+  const char* dev = getenv( "HMGPU_DEVICE" );
+  const Int iDev = dev ? atoi( dev ) : 0;
+  m_warmThread = new std::thread( [this, iDev]() {
+    hmgpu_ctx* c = NULL;
+    if ( hmgpu_create( iDev, m_warmW, m_warmH, m_warmBitDepth, NUM_SLOTS, &c ) == HMGPU_OK ) m_warmCtx = c;
+  } );
+}
+
 Void HmGpuHost::xInit( TComDataCU* pcCU )
 {
   if ( m_ctx ) return;
   const Double t0 = xNow();
   m_picW = pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples();
   m_picH = pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples();
+  if ( m_warmThread )
+  {
+    std::thread* t = (std::thread*)m_warmThread;
+    t->join();
+    delete t;
+    m_warmThread = NULL;
+    if ( m_warmCtx && ( m_warmW != m_picW || m_warmH != m_picH || m_warmBitDepth != g_bitDepth[CHANNEL_TYPE_LUMA] ) )
+    {
+      hmgpu_destroy( m_warmCtx );                          // configured for another picture format: start over
+      m_warmCtx = NULL;
+    }
+    m_ctx = m_warmCtx;
+    m_warmCtx = NULL;
+  }
   const char* dev = getenv( "HMGPU_DEVICE" );
-  if ( hmgpu_create( dev ? atoi( dev ) : 0, m_picW, m_picH, g_bitDepth[CHANNEL_TYPE_LUMA], NUM_SLOTS, &m_ctx ) != HMGPU_OK )
+  if ( !m_ctx && hmgpu_create( dev ? atoi( dev ) : 0, m_picW, m_picH, g_bitDepth[CHANNEL_TYPE_LUMA], NUM_SLOTS, &m_ctx ) != HMGPU_OK )
   {
     xFail( "hmgpu_create" );
   }

@@ -30,6 +30,10 @@ class HmGpuHost
 public:
   static HmGpuHost& instance();
 
+  /// Starts the CUDA context / library set-up on a helper thread as soon as the encoder is configured, so that it runs
+  /// under the first (intra) picture instead of in front of the first inter search (0.3 - 4 s, box and load dependent).
+  Void prewarm      ( Int iPicWidth, Int iPicHeight, Int iBitDepth );
+
   /// Replaces xPatternSearch / xPatternSearchFast + xPatternSearchFracDIF of one xMotionEstimation call.
   /// piRefY points at the PU origin inside the reference reconstruction (TEncSearch.cpp:3857).
   Void motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
@@ -63,6 +67,9 @@ private:
   static const Int NUM_SLOTS = 16;
   static const Int MAX_QUEUE = 32;   ///< 2 lists x 16 reference pictures
   hmgpu_ctx*  m_ctx;
+  void*       m_warmThread;     ///< std::thread of prewarm(), joined by xInit
+  hmgpu_ctx*  m_warmCtx;        ///< what it created (NULL on failure: xInit then creates and reports)
+  Int         m_warmW, m_warmH, m_warmBitDepth;
   Int         m_picW, m_picH;
   const void* m_slotPic[NUM_SLOTS];
   Int         m_slotPoc[NUM_SLOTS];

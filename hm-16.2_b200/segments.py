@@ -9,6 +9,7 @@ GPU because a single sequential encoder cannot fill it.
 import os
 import shutil
 import subprocess
+import sys
 import tempfile
 import time
 
@@ -79,6 +80,11 @@ class MpsDaemon:
             try:
                 self.ok = subprocess.run([exe, "-d"], env=self.env, timeout=30).returncode == 0
                 time.sleep(0.5)
+                if self.ok:
+                    # the MPS server itself starts with the first client (seconds): do that before anybody is timed
+                    here = os.path.dirname(os.path.abspath(__file__))
+                    subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import hmgpu; hmgpu.Context(64, 64, 8, 1).close()" % here],
+                                   env=self.env, timeout=120, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             except (OSError, subprocess.TimeoutExpired):
                 self.ok = False
         return self
