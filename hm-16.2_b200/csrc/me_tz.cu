@@ -9,6 +9,9 @@
 #include "me_tz_impl.cuh"
 #include <stdlib.h>
 
+#ifndef TZ_MIN_CTAS
+#define TZ_MIN_CTAS 8
+#endif
 #define TZ_SMALL_GS 8
 #define TZ_SMALL_PIXELS 128                 // visited pixels (pu_w * rows) of the small class
 #define TZ_SMALL_BYTES 256                  // staged PU bytes per small job (<= 16x16)
@@ -77,7 +80,7 @@ tz_search_small_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __
 }
 
 template <typename Px, bool PACKED>
-__global__ void __launch_bounds__(TZ_WARPS * 32, 8)
+__global__ void __launch_bounds__(TZ_WARPS * 32, TZ_MIN_CTAS)
 tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count,
                  const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results)
 {
