@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HMGPU_ABI_VERSION 1
+#define HMGPU_ABI_VERSION 2   /* 2: hmgpu_me_submit / hmgpu_me_wait, hmgpu_predict / hmgpu_pred_error, job.kind */
 
 enum
 {
@@ -147,7 +147,9 @@ typedef struct hmgpu_me_result
   uint32_t n_cand;                /* candidates evaluated (integer + 18 sub-pel) */
 } hmgpu_me_result;                /* 24 bytes */
 
-/* host buffers in, host buffers out; blocking */
+/* host buffers in, host buffers out; blocking.  Up to 16 jobs: the resident mailbox server (no kernel launch); up to 32: one fused
+ * launch; larger batches: the batch kernels, from 65 536 jobs on as a two-lane pipeline whose range checks run on the device.
+ * On an error return the contents of `results` are unspecified (a pipelined batch may have been searched in part). */
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                     const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results);
 /* Asynchronous pair for small batches (1..32 jobs): hmgpu_me_submit returns once the jobs are visible to the device (the
