@@ -274,6 +274,8 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
     if (ctx->refs[i].cb) cudaFree(ctx->refs[i].cb);
     if (ctx->refs[i].cr) cudaFree(ctx->refs[i].cr);
   }
+  for (int i = 0; i < HMGPU_TZ_STREAMS; i++) if (ctx->tz_streams[i]) { cudaStreamSynchronize(ctx->tz_streams[i]); cudaStreamDestroy(ctx->tz_streams[i]); }
+  for (int i = 0; i <= HMGPU_TZ_STREAMS; i++) if (ctx->tz_ev[i]) cudaEventDestroy(ctx->tz_ev[i]);
   if (ctx->d_org) cudaFree(ctx->d_org);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_work) cudaFree(ctx->d_work);

@@ -11,6 +11,7 @@
 #define HMGPU_MAX_REFS 16
 #define HMGPU_NUM_SMS 148
 #define HMGPU_MAIL_JOBS 32       // jobs per call of the low-latency path (me_single.cu)
+#define HMGPU_TZ_STREAMS 6       // side streams of the TZ stage (me_tz_thread.cu)
 #define HMGPU_SERVER_CTAS 16     // CTAs of the mailbox server = jobs it takes per call
 
 // Device view of the reference planes of one context, passed to kernels by value.
@@ -67,6 +68,7 @@ struct hmgpu_ctx
   void* d_stage; size_t d_stage_bytes; // device
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
   void* d_tzlist; size_t d_tzlist_bytes; // device index lists of the TZ size classes (me_tz.cu)
+  cudaStream_t tz_streams[HMGPU_TZ_STREAMS]; cudaEvent_t tz_ev[HMGPU_TZ_STREAMS + 1]; // side streams of the TZ stage (me_tz_thread.cu): kernels of different PU shapes overlap
   HmgpuLane lane_store[2]; int cur_lane; // parked lanes (the current one lives in the fields above)
   cudaEvent_t lane_done[2], scan_done[2], fork_ev;
   cudaStream_t copy_stream;              // H2D of the next chunk + its validation scan

@@ -16,10 +16,11 @@
 #define TZ_SMALL_PIXELS 128                 // visited pixels (pu_w * rows) of the small class
 #define TZ_SMALL_BYTES 256                  // staged PU bytes per small job (<= 16x16)
 
+int hmgpu_launch_tz_thread(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks, hmgpu_me_result* d_results);
 int hmgpu_launch_tz_lockstep(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, const uint32_t* d_idx, const uint32_t* d_count, uint32_t* d_cursor,
                              int n_jobs_max, hmgpu_me_result* d_results);
 
-// class of the lock-step kernel (me_tz_lock.cu): PUs up to 16x16
+// class of the lock-step kernel (me_tz_lock.cu) and of tz_search_near_kernel: PUs up to 16x16
 __device__ __forceinline__ bool tz_is_lockstep(const hmgpu_me_job& jb) { return jb.pu_w <= 16 && jb.pu_h <= 16; }
 
 __device__ __forceinline__ bool tz_is_small(const hmgpu_me_job& jb)
@@ -79,7 +80,7 @@ tz_search_small_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __
   }
 }
 
-template <typename Px, bool PACKED>
+template <typename Px, bool PACKED, bool MERGE = false>
 __global__ void __launch_bounds__(TZ_WARPS * 32, TZ_MIN_CTAS)
 tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count,
                  const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results)
@@ -93,7 +94,7 @@ tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restri
     const uint32_t job_id = idx[k];
     const hmgpu_me_job jb = jobs[job_id];
     hmgpu_me_result r;
-    tz_search_group<Px, PACKED, 32>(jb, org_blocks, refs, org, s_org_all[warp], r);
+    tz_search_group<Px, PACKED, 32, MERGE>(jb, org_blocks, refs, org, s_org_all[warp], r);
     if (lane == 0) results[job_id] = r;
     __syncwarp();
   }
@@ -135,6 +136,47 @@ tz_search_win_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __re
   }
 }
 
+// 8-bit pictures, PUs up to 16x16 (91 % of the jobs of a picture), one warp per job.  Two changes against tz_search_kernel:
+//  * the neighbourhood of the start point (+-TZN_RADIUS) is copied once into shared memory with coalesced 16-byte loads -- the
+//    generic kernel spends 8.4 L1 sectors per load request because every (point, row) pair of a round is a separate line;
+//  * the rounds at distance 1, 2, 4, 8 of the first search are ONE pass over that window (MERGE in tz_search_group), which
+//    divides the number of dependent passes per job by about three -- the per-pass control (point generation, MV cost,
+//    reductions) is what the generic kernel spends its instructions on, not the SADs.
+// Points outside the window (far rings, star refinement, a zero vector far from the predictor) are read from global memory.
+#ifndef TZN_MIN_CTAS
+#define TZN_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(TZ_WARPS * 32, TZN_MIN_CTAS)
+tz_search_near_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count,
+                      RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results)
+{
+  __shared__ __align__(16) unsigned char s_org_all[TZ_WARPS][TZN_MAX_PU * TZN_MAX_PU];
+  __shared__ __align__(16) unsigned char s_win_all[TZ_WARPS][TZN_ROWS * TZN_PITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = *count;
+  for (uint32_t k = blockIdx.x * TZ_WARPS + warp; k < n; k += gridDim.x * TZ_WARPS)
+  {
+    const uint32_t job_id = idx[k];
+    const hmgpu_me_job jb = jobs[job_id];
+    TzWindow win;
+    int n16;
+    const bool have_win = tz_near_geometry(jb, refs, win, n16);
+    if (have_win)
+    {
+      // 8 rows per pass: lane = 4 * row + 16-byte column
+      const uint8_t* src = (const uint8_t*)refs.base[jb.ref_slot] + (ptrdiff_t)(jb.pu_y + win.oy) * refs.pitch + (jb.pu_x + win.ox);
+      const int c = lane & 3;
+      if (c < n16)
+        for (int r = lane >> 2; r < win.rows; r += 8)
+          *(uint4*)(s_win_all[warp] + r * TZN_PITCH + c * 16) = __ldg((const uint4*)(src + (size_t)r * refs.pitch) + c);
+    }
+    hmgpu_me_result r;
+    tz_search_group<uint8_t, true, 32, true>(jb, NULL, refs, org, s_org_all[warp], r, have_win ? s_win_all[warp] : NULL, &win);   // syncs the warp after staging
+    if (lane == 0) results[job_id] = r;
+    __syncwarp();
+  }
+}
+
 // xTZSearchSelective jobs (FastSearch = 2): one warp per job over the whole batch, other jobs skipped
 template <typename Px, bool PACKED>
 __global__ void __launch_bounds__(TZ_WARPS * 32)
@@ -154,11 +196,51 @@ tz_selective_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs, const int
   }
 }
 
+// the warp-per-job kernel (8-bit packed path) over an index list whose length is on the device, on a stream of the caller's choice
+int hmgpu_launch_tz_list(hmgpu_ctx* ctx, cudaStream_t stream, const hmgpu_me_job* d_jobs, const uint32_t* idx, const uint32_t* count,
+                         int n_jobs_max, const int16_t* d_org_blocks, hmgpu_me_result* d_results)
+{
+  const RefTable rt = hmgpu_ref_table(ctx);
+  OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  const int grid = max(1, min(HMGPU_NUM_SMS * 16, (n_jobs_max + TZ_WARPS - 1) / TZ_WARPS));
+  // HMGPU_TZ_MERGE=1: the rounds at distance 1, 2, 4, 8 of the first search as one pass of 28 lanes (see tz_search_group)
+  static const int s_merge = getenv("HMGPU_TZ_MERGE") ? atoi(getenv("HMGPU_TZ_MERGE")) : 0;
+  // HMGPU_TZ_CARVE=k: shared-memory carve-out (percent) asked for this kernel.  Kernels whose L1 / shared split differs do not share
+  // an SM; the one-thread-per-job kernels next to it need (almost) all of it as shared memory.
+  static const int s_carve = getenv("HMGPU_TZ_CARVE") ? atoi(getenv("HMGPU_TZ_CARVE")) : -1;
+  static bool s_carve_set = false;
+  if (s_carve >= 0 && !s_carve_set)
+  {
+    HMGPU_CUDA(ctx, cudaFuncSetAttribute(tz_search_kernel<uint8_t, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, s_carve));
+    HMGPU_CUDA(ctx, cudaFuncSetAttribute(tz_search_kernel<uint8_t, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, s_carve));
+    s_carve_set = true;
+  }
+  if (s_merge) tz_search_kernel<uint8_t, true, true><<<grid, TZ_WARPS * 32, 0, stream>>>(d_jobs, idx, count, d_org_blocks, rt, ov, d_results);
+  else tz_search_kernel<uint8_t, true><<<grid, TZ_WARPS * 32, 0, stream>>>(d_jobs, idx, count, d_org_blocks, rt, ov, d_results);
+  return HMGPU_OK;
+}
+
 int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                     hmgpu_me_result* d_results, bool any_org_block, bool any_sel)
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  static const int s_mode = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 5;
+  if (s_mode == 5 && ctx->px_bytes == 1 && !any_org_block)
+  {
+    // default: PUs up to 16x16 one THREAD per job (me_tz_thread.cu), the rest -- and what those kernels hand over -- one warp per job
+    HmgpuStage st(ctx, HMGPU_ST_TZ, 23);
+    int rc5 = hmgpu_launch_tz_thread(ctx, d_jobs, n_jobs, d_org_blocks, d_results);
+    if (rc5) return rc5;
+    if (any_sel)
+    {
+      ctx->launches += 1; ctx->prof_launches[HMGPU_ST_TZ] += 1;
+      const int grid = min(HMGPU_NUM_SMS * 16, (n_jobs + TZ_WARPS - 1) / TZ_WARPS);
+      tz_selective_kernel<uint8_t, true><<<grid, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, d_org_blocks, rt, ov, d_results);
+    }
+    HMGPU_CUDA(ctx, cudaGetLastError());
+    return HMGPU_OK;
+  }
   // index lists live in their own scratch buffer (the fractional stage reuses d_work)
   const size_t list_bytes = ((size_t)n_jobs * sizeof(uint32_t) + 255) & ~(size_t)255;
   int rc = hmgpu_reserve_tzlist(ctx, 256 + 2 * list_bytes);
@@ -174,7 +256,8 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   // ~23 near points save); 2 = PUs up to 16x16 in the lock-step kernel of me_tz_lock.cu, four jobs per warp (4.72 ms: the
   // phase-specific branches of its state machine serialise and every lane walks a whole SAD); 1 = the first
   // four-jobs-per-warp attempt, tz_search_small_kernel (3.6 ms).
-  static const int s_split = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 0;
+  // 4 (default since round 1n) = PUs up to 16x16 in tz_search_near_kernel (window + merged first rounds), the rest one warp per job.
+  static const int s_split = s_mode == 5 ? 0 : s_mode;
   HmgpuStage st(ctx, HMGPU_ST_TZ, (packed && s_split) ? 3 : 2);
   tz_classify_kernel<<<(n_jobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, n_jobs, packed ? s_split : 0, idx_small, idx_big, counts);
   // persistent grids: enough CTAs to fill the machine, never more than the work could use
@@ -189,7 +272,8 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
     }
     else
     {
-      if (s_split == 2) { if ((rc = hmgpu_launch_tz_lockstep(ctx, d_jobs, idx_small, counts + 0, counts + 2, n_jobs, d_results))) return rc; }
+      if (s_split == 4) tz_search_near_kernel<<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
+      else if (s_split == 2) { if ((rc = hmgpu_launch_tz_lockstep(ctx, d_jobs, idx_small, counts + 0, counts + 2, n_jobs, d_results))) return rc; }
       else if (s_split == 1) tz_search_small_kernel<<<grid_small, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_small, counts + 0, rt, ov, d_results);
       tz_search_kernel<uint8_t, true><<<grid_big, TZ_WARPS * 32, 0, ctx->stream>>>(d_jobs, idx_big, counts + 1, d_org_blocks, rt, ov, d_results);
     }

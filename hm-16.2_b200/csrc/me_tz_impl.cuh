@@ -67,6 +67,29 @@ __device__ __forceinline__ bool tz_window_geometry(const hmgpu_me_job& jb, const
   return w.x1 >= w.x0 && w.y1 >= w.y0 && w.rows > 0 && w.pitch > 0;
 }
 
+// Window of the batch kernel for small PUs (tz_search_near_kernel): candidates within TZN_RADIUS of the clipped start point, rows of
+// up to 64 bytes staged at a fixed pitch of 80 bytes (20 words: consecutive rows start 20 banks apart, so the lanes of a pass, which
+// read different rows, spread over the banks).
+#define TZN_RADIUS 10
+#define TZN_PITCH 80
+#define TZN_MAX_PU 16
+#define TZN_ROWS (TZN_MAX_PU + 2 * TZN_RADIUS)
+__device__ __forceinline__ bool tz_near_geometry(const hmgpu_me_job& jb, const RefTable& refs, TzWindow& w, int& n16)
+{
+  const int sx = tz_clip_q(jb.start_x, jb.clip_hmin, jb.clip_hmax) >> 2, sy = tz_clip_q(jb.start_y, jb.clip_vmin, jb.clip_vmax) >> 2;
+  int ax0 = jb.pu_x + sx - TZN_RADIUS, ax1 = jb.pu_x + sx + TZN_RADIUS + jb.pu_w + 4;
+  int ay0 = jb.pu_y + sy - TZN_RADIUS, ay1 = jb.pu_y + sy + TZN_RADIUS + jb.pu_h;
+  ax0 = max(ax0, -HMGPU_MARGIN); ay0 = max(ay0, -HMGPU_MARGIN);
+  ax1 = min(ax1, refs.pic_w + HMGPU_MARGIN); ay1 = min(ay1, refs.pic_h + HMGPU_MARGIN);
+  const int al0 = (ax0 + HMGPU_MARGIN) & ~15;               // rows start 64-byte aligned at x = -80
+  const int al1 = min((ax1 + HMGPU_MARGIN + 15) & ~15, al0 + 64);
+  w.ox = al0 - HMGPU_MARGIN - jb.pu_x; w.oy = ay0 - jb.pu_y;
+  w.pitch = TZN_PITCH; w.rows = ay1 - ay0;
+  n16 = (al1 - al0) >> 4;
+  w.x0 = w.ox; w.x1 = w.ox + (al1 - al0) - jb.pu_w - 4;
+  w.y0 = w.oy; w.y1 = w.oy + w.rows - jb.pu_h;
+  return w.x1 >= w.x0 && w.y1 >= w.y0 && w.rows > 0 && w.rows <= TZN_ROWS && n16 > 0;
+}
 
 struct TzBest
 {
@@ -131,9 +154,11 @@ template <bool SMEM = false>
 __device__ __forceinline__ uint32_t sad_rows_packed(const uint8_t* ref, int pitch, const uint32_t* org_s,
                                                     int wq, int rows, int row_mul, int r0, int rstep, uint32_t raw_bound)
 {
-  const uintptr_t a0 = (uintptr_t)ref;
+  // SMEM: `ref` may have travelled through a struct member that can be NULL, which hides its address space from the compiler
+  // (it then emits generic LD instead of LDS): rebuild the pointer from the 32-bit shared-window address
+  const uintptr_t a0 = SMEM ? (uintptr_t)__cvta_generic_to_shared(ref) : (uintptr_t)ref;
   const int sh = (int)(a0 & 3) * 8;
-  const uint32_t* q0 = (const uint32_t*)(a0 & ~(uintptr_t)3);
+  const uint32_t* q0 = SMEM ? (const uint32_t*)__cvta_shared_to_generic((size_t)(a0 & ~(uintptr_t)3)) : (const uint32_t*)(a0 & ~(uintptr_t)3);
   const int pitch_w = pitch >> 2;                      // pitch is a multiple of 4 bytes
   // the common PU widths (8, 16, 4, 32 samples) get unrolled rows; wq is uniform across the lanes of a job
   if (wq == 2) return sad_rows_packed_w<SMEM, 2>(q0, sh, pitch_w, org_s, wq, rows, row_mul, r0, rstep, raw_bound);
@@ -159,22 +184,20 @@ __device__ __forceinline__ uint32_t sad_rows_generic(const Px* ref, int pitch, c
   return acc;
 }
 
-// Evaluate up to GS / lanes_per_point points at once.  Sub-group lane / lanes_per_point owns one
-// point; (x, y, valid, pnr, dist) are the data of THIS lane's point.  Updates `best` uniformly
-// across the group.
+// Cost (SAD + MV cost) of THIS lane's point, summed over the `lanes_per_point` lanes that share it; 0xffffffff when the point is
+// not valid or cannot beat `best_cost` (MV cost alone too high, or the row sums reached the bound -- see sad_rows_packed_w).
 template <typename Px, bool PACKED, int GS>
-__device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
-                                        int lanes_per_point, int x, int y, bool valid, int pnr, int dist,
-                                        TzBest& best)
+__device__ __forceinline__ uint32_t tz_point_cost(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
+                                                  int lanes_per_point, int x, int y, bool valid, uint32_t best_cost)
 {
   const uint32_t gm = TzGroup<GS>::mask();
   const int sub = TzGroup<GS>::lane() & (lanes_per_point - 1);
   uint32_t part = 0;
   const uint32_t mvc = hm_mv_cost(J.ui_cost, J.pred_x, J.pred_y, 2, x, y);
-  if (valid && mvc < best.cost)
+  if (valid && mvc < best_cost)
   {
     // smallest raw sum whose normalised value (sum << sub_shift) >> (bitDepth-8) reaches best.cost - mvc
-    const uint32_t need = best.cost - mvc;
+    const uint32_t need = best_cost - mvc;
     uint32_t raw_bound;
     if (PACKED) raw_bound = (need >> J.sub_shift) + ((need & ((1u << J.sub_shift) - 1u)) ? 1u : 0u);   // 8-bit pictures: no 64-bit math
     else
@@ -194,7 +217,21 @@ __device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pit
   }
   for (int o = lanes_per_point >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(gm, part, o);
   uint32_t cost = 0xffffffffu;
-  if (valid) cost = mvc < best.cost ? hm_sad_norm(part, J.sub_shift, J.bit_depth) + mvc : 0xffffffffu;
+  if (valid) cost = mvc < best_cost ? hm_sad_norm(part, J.sub_shift, J.bit_depth) + mvc : 0xffffffffu;
+  return cost;
+}
+
+// Evaluate up to GS / lanes_per_point points at once.  Sub-group lane / lanes_per_point owns one
+// point; (x, y, valid, pnr, dist) are the data of THIS lane's point.  Updates `best` uniformly
+// across the group.
+template <typename Px, bool PACKED, int GS>
+__device__ __forceinline__ void tz_eval(const TzJob& J, const Px* ref00, int pitch, const void* org_s,
+                                        int lanes_per_point, int x, int y, bool valid, int pnr, int dist,
+                                        TzBest& best)
+{
+  const uint32_t gm = TzGroup<GS>::mask();
+  const int sub = TzGroup<GS>::lane() & (lanes_per_point - 1);
+  const uint32_t cost = tz_point_cost<Px, PACKED, GS>(J, ref00, pitch, org_s, lanes_per_point, x, y, valid, best.cost);
   best.n_cand += __popc(__ballot_sync(gm, valid && sub == 0));
   const uint32_t m = __reduce_min_sync(gm, cost);
   if (m < best.cost)                                   // strict '<' (TEncSearch.cpp:414)
@@ -340,7 +377,7 @@ struct TzSpec { TzSpecRound r[3]; };
 // s_org: per-group shared memory for the PU block: pu_w*pu_h bytes (PACKED) or 2*pu_w*pu_h (int16).
 // The first lane of the group returns the result in `out` (integer MV, SAD without MV cost,
 // candidate count).
-template <typename Px, bool PACKED, int GS>
+template <typename Px, bool PACKED, int GS, bool MERGE = false>
 __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
                                                 const RefTable& refs, const OrgView& org, unsigned char* s_org,
                                                 hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL,
@@ -433,6 +470,42 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
         if (rr.cost < best.cost) { best.cost = rr.cost; best.x = rr.x; best.y = rr.y; best.dist = rr.dist; best.pnr = rr.pnr; best.round = 0; }
       }
       d0 = best.round >= 3 ? jb.search_range + 1 : 8;       // the reference stops 3 rounds after the last improvement
+    }
+  }
+  if (MERGE && GS == 32)
+  {
+    // Merged first rounds (batch kernel of the small PUs): the diamonds at distance 1, 2, 4, 8 all sit around the SAME centre, so
+    // their 4 + 8 + 8 + 8 = 28 points are costed in ONE pass, one lane per point in emission order, against the best START point
+    // (a point that cannot beat it cannot beat anything later either -- the best only decreases), and the reference's sequential
+    // bookkeeping -- strict '<' per round, the round counter, the stop three rounds after the last improvement, the candidate
+    // count of the rounds it actually runs -- is replayed on the 28 costs.
+    const int rr = gl < 4 ? 0 : (gl < 12 ? 1 : (gl < 20 ? 2 : 3));         // lanes 0-3: d = 1, 4-11: d = 2, 12-19: d = 4, 20-27: d = 8
+    int x, y, pnr, dist;
+    tz_diamond_point(cx, cy, 1 << rr, rr == 0 ? gl : ((gl + 4) & 7), x, y, pnr, dist);
+    const bool valid = gl < 28 && (1 << rr) <= jb.search_range && tz_in_window(J, cx, cy, x, y);
+    const uint32_t cost = tz_point_cost<Px, PACKED, GS>(J, ref00, pitch, s_org, 1, x, y, valid, best.cost);
+    const uint32_t vm = __ballot_sync(gm, valid);
+    d0 = 16;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+      if ((1 << r) > jb.search_range) { d0 = jb.search_range + 1; break; }
+      const uint32_t rmask = r == 0 ? 0xFu : (0xFFu << (8 * r - 4));
+      best.round += 1;
+      best.n_cand += __popc(vm & rmask);
+      const uint32_t c = ((rmask >> gl) & 1u) ? cost : 0xffffffffu;
+      const uint32_t m = __reduce_min_sync(gm, c);
+      if (m < best.cost)
+      {
+        const int src = __ffs(__ballot_sync(gm, c == m)) - 1;
+        best.cost = m;
+        best.x = __shfl_sync(gm, x, src);
+        best.y = __shfl_sync(gm, y, src);
+        best.dist = __shfl_sync(gm, dist, src);
+        best.pnr = __shfl_sync(gm, pnr, src);
+        best.round = 0;
+      }
+      if (best.round >= 3) { d0 = jb.search_range + 1; break; }
     }
   }
   for (int d = d0; d <= jb.search_range; d <<= 1)
