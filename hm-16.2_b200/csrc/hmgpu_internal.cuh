@@ -11,7 +11,7 @@
 #define HMGPU_MAX_REFS 16
 #define HMGPU_NUM_SMS 148
 #define HMGPU_MAIL_JOBS 32       // jobs per call of the low-latency path (me_single.cu)
-#define HMGPU_TZ_STREAMS 6       // side streams of the TZ stage (me_tz_thread.cu)
+#define HMGPU_TZ_STREAMS 15      // side streams of the TZ stage (me_tz_thread.cu)
 #define HMGPU_SERVER_CTAS 16     // CTAs of the mailbox server = jobs it takes per call
 
 // Device view of the reference planes of one context, passed to kernels by value.

@@ -12,6 +12,7 @@
 #ifndef TZ_MIN_CTAS
 #define TZ_MIN_CTAS 8
 #endif
+#define TZ_THREAD_MIN_JOBS 4096
 #define TZ_SMALL_GS 8
 #define TZ_SMALL_PIXELS 128                 // visited pixels (pu_w * rows) of the small class
 #define TZ_SMALL_BYTES 256                  // staged PU bytes per small job (<= 16x16)
@@ -204,10 +205,10 @@ int hmgpu_launch_tz_list(hmgpu_ctx* ctx, cudaStream_t stream, const hmgpu_me_job
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
   const int grid = max(1, min(HMGPU_NUM_SMS * 16, (n_jobs_max + TZ_WARPS - 1) / TZ_WARPS));
   // HMGPU_TZ_MERGE=1: the rounds at distance 1, 2, 4, 8 of the first search as one pass of 28 lanes (see tz_search_group)
-  static const int s_merge = getenv("HMGPU_TZ_MERGE") ? atoi(getenv("HMGPU_TZ_MERGE")) : 0;
+  static const int s_merge = getenv("HMGPU_TZ_MERGE") ? atoi(getenv("HMGPU_TZ_MERGE")) : 1;
   // HMGPU_TZ_CARVE=k: shared-memory carve-out (percent) asked for this kernel.  Kernels whose L1 / shared split differs do not share
   // an SM; the one-thread-per-job kernels next to it need (almost) all of it as shared memory.
-  static const int s_carve = getenv("HMGPU_TZ_CARVE") ? atoi(getenv("HMGPU_TZ_CARVE")) : -1;
+  static const int s_carve = getenv("HMGPU_TZ_CARVE") ? atoi(getenv("HMGPU_TZ_CARVE")) : 50;
   static bool s_carve_set = false;
   if (s_carve >= 0 && !s_carve_set)
   {
@@ -225,11 +226,15 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
-  static const int s_mode = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 5;
-  if (s_mode == 5 && ctx->px_bytes == 1 && !any_org_block)
+  // read per launch (tests switch the mapping inside one process): HMGPU_TZ_SPLIT selects it, HMGPU_TZ_THREAD_MIN the batch size
+  // from which the one-thread-per-job kernels are used
+  const int s_mode = getenv("HMGPU_TZ_SPLIT") ? atoi(getenv("HMGPU_TZ_SPLIT")) : 5;
+  const int thread_min = getenv("HMGPU_TZ_THREAD_MIN") ? atoi(getenv("HMGPU_TZ_THREAD_MIN")) : TZ_THREAD_MIN_JOBS;
+  if (s_mode == 5 && ctx->px_bytes == 1 && !any_org_block && n_jobs >= thread_min)
   {
-    // default: PUs up to 16x16 one THREAD per job (me_tz_thread.cu), the rest -- and what those kernels hand over -- one warp per job
-    HmgpuStage st(ctx, HMGPU_ST_TZ, 23);
+    // default for large batches: PUs up to 32x16 one THREAD per job (me_tz_thread.cu), the rest -- and what those kernels hand
+    // over -- one warp per job.  Small batches keep the two-launch path below (16 launches cost more than they save there).
+    HmgpuStage st(ctx, HMGPU_ST_TZ, 17);
     int rc5 = hmgpu_launch_tz_thread(ctx, d_jobs, n_jobs, d_org_blocks, d_results);
     if (rc5) return rc5;
     if (any_sel)
@@ -257,7 +262,7 @@ int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   // phase-specific branches of its state machine serialise and every lane walks a whole SAD); 1 = the first
   // four-jobs-per-warp attempt, tz_search_small_kernel (3.6 ms).
   // 4 (default since round 1n) = PUs up to 16x16 in tz_search_near_kernel (window + merged first rounds), the rest one warp per job.
-  static const int s_split = s_mode == 5 ? 0 : s_mode;
+  const int s_split = s_mode == 5 ? 0 : s_mode;
   HmgpuStage st(ctx, HMGPU_ST_TZ, (packed && s_split) ? 3 : 2);
   tz_classify_kernel<<<(n_jobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, n_jobs, packed ? s_split : 0, idx_small, idx_big, counts);
   // persistent grids: enough CTAs to fill the machine, never more than the work could use

@@ -1,4 +1,4 @@
-// me_tz_thread.cu -- TZ search of the small PUs (up to 16x16, 8-bit pictures), ONE THREAD per job.
+// me_tz_thread.cu -- TZ search of the small and medium PUs (up to 32x16 / 16x32, 8-bit pictures), ONE THREAD per job.
 // Replaces TEncSearch::xTZSearch (TEncSearch.cpp:4027-4228) with xTZSearchHelp (:333-424),
 // xTZ8PointDiamondSearch (:616-791) and xTZ2PointSearch (:429-557) for those jobs.
 //
@@ -6,42 +6,51 @@
 // profiles/r1k_ncu_tz_search*): the per-round control of the search -- point generation, MV cost, reductions, the update of
 // the best -- is executed by a whole warp for a handful of points.  Here a warp instruction serves 32 jobs: every thread runs
 // the reference's sequential loop for its own job, exactly as written (strict '<' after every point, in emission order), so
-// there is nothing to reduce and nothing to replay.  What makes that affordable:
+// there is nothing to reduce and nothing to replay (~230 warp instructions per job).  What makes that affordable:
 //   * jobs are binned by PU shape (tzt_classify_kernel), one launch per shape with (words per row, visited rows, row step) as
 //     template parameters: the threads of a warp run the same trip counts and the SAD of a point is straight-line code;
-//   * the neighbourhood of each job's start point (+-TZT_R samples) is copied by the WHOLE warp, coalesced, into a private
-//     window in shared memory (row-major, odd stride between the jobs of a warp: threads in lock-step read the same
-//     (row, word) of their own window, i.e. 32 different banks); the key pattern lives in registers;
-//   * the rare continuations -- raster scan, star refinement, a best start point far from the predictor, windows that touch
-//     the edge of the padded plane -- are not done here: the job is appended to the list of the warp-per-job kernel, which
-//     searches it from scratch (exact either way; 4-5 % of the jobs of the 1080p workload).
-// Points outside the window (the zero vector, the rings at distance >= 16) are read from global memory with the exact early
-// termination of the row loop (see sad_rows_packed_w in me_tz_impl.cuh).
+//   * the neighbourhood of each job's likely start points (+-TZT_R samples around the predictor, or around the point between
+//     the predictor and the 2Nx2N integer MV) is copied by the WHOLE warp, coalesced, with cp.async, into a private window in
+//     shared memory (row-major, odd word stride between the jobs of a warp); the key pattern lives in registers;
+//   * a thread has no parallelism of its own, so the points of the near rings are costed four at a time as independent
+//     instruction streams (updates applied afterwards in emission order), and a far ring reads the first row of all its points
+//     in one round trip and finishes only the few that have not already lost;
+//   * what would make 31 threads wait for one is handed over: star refinement, raster scan, a best start point that is not
+//     near the window centre, windows that touch the edge of the padded plane.  Those jobs (about one in ten on the 1080p
+//     workload) are appended to the list of the warp-per-job kernel, which searches them from scratch -- exact either way.
+//     (A second one-thread-per-job pass for them exists, P2 / HMGPU_TZ_P2=1; measured slower: its kernels are a few very long
+//     warps each.)
+//   * the kernels of the 14 shapes and the warp-per-job kernel of the larger PUs run on side streams, so that the tail of one
+//     overlaps the body of the next.
+// Measured (1080p, 4 references, 1.18 M jobs): TZ stage 2.65 ms (one warp per job for everything) -> 1.75 ms; results are
+// byte-identical (profiles/tz_ab.py prints an MD5 of the result array for either mapping).
 #include "me_tz_impl.cuh"
 #include <stdlib.h>
 #include <type_traits>
 
-#define TZT_R 5                      // window radius: the rings up to distance TZT_NEAR around a best start <= 1 away from its centre
+#define TZT_R 6                      // window radius: the rings up to distance TZT_NEAR around a best start <= 1 away from its centre
 #define TZT_NEAR 4                   // rings up to this distance are costed from the window, the others from global memory
 #define TZT_PITCH(WQ) (((2 * TZT_R + 3) >> 2) + (WQ) + 1)   // words per window row: 3 (alignment) + 2R + 4 WQ + 3 (funnel look-ahead) bytes
 #define TZT_MAX_REFINE 3              // star-refinement rounds a thread runs before it hands the job over
-#define TZT_CLASSES 10               // PU shapes with their own launch; list TZT_CLASSES = everything else
+#define TZT_CLASSES 14               // PU shapes with their own launch; list TZT_CLASSES = everything else
 
 struct TztShape { int w, h, wq, vr, rm; };
 // (width, height) -> words per row, visited rows, row step (2 = FEN sub-sampling, TEncSearch.cpp:347-353)
 static const TztShape k_tzt_shapes[TZT_CLASSES] = {
   { 4, 8, 1, 8, 1 }, { 4, 16, 1, 8, 2 }, { 8, 4, 2, 4, 1 }, { 8, 8, 2, 8, 1 }, { 8, 16, 2, 8, 2 },
-  { 12, 16, 3, 8, 2 }, { 16, 4, 4, 4, 1 }, { 16, 8, 4, 8, 1 }, { 16, 12, 4, 6, 2 }, { 16, 16, 4, 8, 2 } };
+  { 12, 16, 3, 8, 2 }, { 16, 4, 4, 4, 1 }, { 16, 8, 4, 8, 1 }, { 16, 12, 4, 6, 2 }, { 16, 16, 4, 8, 2 },
+  { 32, 8, 8, 8, 1 }, { 8, 32, 2, 16, 2 }, { 16, 32, 4, 16, 2 }, { 32, 16, 8, 8, 2 } };
 
 __device__ __forceinline__ int tzt_class(const hmgpu_me_job& jb)
 {
   const int w = jb.pu_w, h = jb.pu_h;
   int c = -1;
   if (w == 4) c = h == 8 ? 0 : (h == 16 ? 1 : -1);
-  else if (w == 8) c = h == 4 ? 2 : (h == 8 ? 3 : (h == 16 ? 4 : -1));
+  else if (w == 8) c = h == 4 ? 2 : (h == 8 ? 3 : (h == 16 ? 4 : (h == 32 ? 11 : -1)));
   else if (w == 12) c = h == 16 ? 5 : -1;
-  else if (w == 16) c = h == 4 ? 6 : (h == 8 ? 7 : (h == 12 ? 8 : (h == 16 ? 9 : -1)));
-  if (c >= 0 && h > 8 && !(jb.flags & HMGPU_F_FEN)) c = -1;      // more than 8 visited rows: not held in registers here
+  else if (w == 16) c = h == 4 ? 6 : (h == 8 ? 7 : (h == 12 ? 8 : (h == 16 ? 9 : (h == 32 ? 12 : -1))));
+  else if (w == 32) c = h == 8 ? 10 : (h == 16 ? 13 : -1);
+  if (c >= 0 && h > 8 && !(jb.flags & HMGPU_F_FEN)) c = -1;      // all rows visited: the key pattern would not fit the registers
   return c;
 }
 
@@ -107,7 +116,7 @@ template <int WQ, int VR, int RM, bool P2>
 __global__ void __launch_bounds__(32, TZT_PER_SM(WQ, VR, RM))
 tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restrict__ idx, uint32_t* __restrict__ counts, int cls,
                   RefTable refs, OrgView org, hmgpu_me_result* __restrict__ results,
-                  uint32_t* __restrict__ lists2, uint32_t* __restrict__ rest_idx)
+                  uint32_t* __restrict__ lists2, uint32_t* __restrict__ rest_idx, int use_p2)
 {
   constexpr int H = VR * RM;
   constexpr int R = TZT_R;
@@ -356,7 +365,7 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
       }
       const int cx = bx, cy = by;
       park_x = cx; park_y = cy;
-      if (!P2 && (abs(cx - sx) > R - TZT_NEAR || abs(cy - sy) > R - TZT_NEAR)) ovf = 1;    // the near rings would leave the window
+      if (!P2 && (abs(cx - sx) > R - TZT_NEAR || abs(cy - sy) > R - TZT_NEAR)) ovf = use_p2 ? 1 : 2;    // the near rings would leave the window
       else
       {
         TzJob J;                                                 // only the window fields are read by tz_in_window
@@ -403,28 +412,29 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
             evaln(std::integral_constant<int, 2>(), px, py, pv, zero4, two4);
           }
         };
-        // ---- first search (:4100-4115): diamonds at distance 1, 2, 4, ..; stop 3 rounds after the last improvement ----
-        for (int d = 1; d <= jb.search_range; d <<= 1)
+        // ---- first search (:4100-4115): diamonds at distance 1, 2, 4, .. around the best start point, stop 3 rounds after the
+        // last improvement; two-point fill (:4137-4141); raster scan when the best is far (:4144-4154, handed over); then the
+        // star refinement (:4189-4223): all rings around the best, two-point fill, until a round brings nothing.  One loop
+        // for both, so that the ring and two-point code exists once.
+        int rcx = cx, rcy = cy;
+        bool first = true;
+        for (int iter = 0; ; iter++)
         {
-          ring(cx, cy, d);
-          if (bround >= 3) break;
-        }
-        if (bdist == 1) { bdist = 0; two_point(); }              // :4137-4141
-        if (bdist > 5) ovf = 2;                                  // raster scan (:4144-4154): warp-per-job kernel
-        else if (bdist > 0)
-        {
-          if (!P2) ovf = 1;
-          else
-            for (int iter = 0; bdist > 0; iter++)                // star refinement (:4189-4223)
-            {
-              // a long walk (the optimum far from every start point) would keep 31 threads waiting for one: after a few
-              // rounds the job goes to the warp-per-job kernel, which costs the points of a round in parallel
-              if (iter == TZT_MAX_REFINE) { ovf = 2; break; }
-              const int rcx = bx, rcy = by;
-              bdist = 0; bpnr = 0;
-              for (int d = 1; d < jb.search_range + 1; d <<= 1) ring(rcx, rcy, d);
-              if (bdist == 1) { bdist = 0; if (bpnr != 0) two_point(); }
-            }
+          for (int d = 1; d <= jb.search_range; d <<= 1)
+          {
+            ring(rcx, rcy, d);
+            if (first && bround >= 3) break;
+          }
+          if (bdist == 1) { bdist = 0; two_point(); }            // (the refinement skips it for point number 0; so does two_point)
+          if (first && bdist > 5) { ovf = 2; break; }            // raster scan: warp-per-job kernel
+          first = false;
+          if (bdist == 0) break;
+          if (!P2) { ovf = use_p2 ? 1 : 2; break; }              // needs the refinement: second pass (or the warp-per-job kernel)
+          // a long walk (the optimum far from every start point) would keep 31 threads waiting for one: after a few
+          // rounds the job goes to the warp-per-job kernel, which costs the points of a round in parallel
+          if (iter == TZT_MAX_REFINE) { ovf = 2; break; }
+          rcx = bx; rcy = by;
+          bdist = 0; bpnr = 0;
         }
       }
     }
@@ -472,7 +482,8 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
 
 template <int WQ, int VR, int RM, bool P2>
 static int tzt_launch_one(hmgpu_ctx* ctx, cudaStream_t stream, const hmgpu_me_job* d_jobs, const uint32_t* idx, uint32_t* counts, int cls,
-                          int n_jobs, const RefTable& rt, const OrgView& ov, hmgpu_me_result* d_results, uint32_t* lists2, uint32_t* rest_idx)
+                          int n_jobs, const RefTable& rt, const OrgView& ov, hmgpu_me_result* d_results, uint32_t* lists2, uint32_t* rest_idx,
+                          int use_p2)
 {
   constexpr int ITEMS = (VR * RM + 2 * TZT_R) * TZT_PITCH(WQ);
   constexpr int smem = (ITEMS | 1) * 32 * 4;
@@ -484,7 +495,7 @@ static int tzt_launch_one(hmgpu_ctx* ctx, cudaStream_t stream, const hmgpu_me_jo
   }
   const int per_sm = TZT_PER_SM(WQ, VR, RM);
   const int grid = max(1, min(HMGPU_NUM_SMS * per_sm, (n_jobs + 31) / 32));
-  tzt_search_kernel<WQ, VR, RM, P2><<<grid, 32, smem, stream>>>(d_jobs, idx, counts, cls, rt, ov, d_results, lists2, rest_idx);
+  tzt_search_kernel<WQ, VR, RM, P2><<<grid, 32, smem, stream>>>(d_jobs, idx, counts, cls, rt, ov, d_results, lists2, rest_idx, use_p2);
   return HMGPU_OK;
 }
 
@@ -517,21 +528,24 @@ int hmgpu_launch_tz_thread(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_job
   HMGPU_CUDA(ctx, cudaEventRecord(ctx->tz_ev[HMGPU_TZ_STREAMS], ctx->stream));
   for (int i = 0; i < HMGPU_TZ_STREAMS; i++) HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->tz_streams[i], ctx->tz_ev[HMGPU_TZ_STREAMS], 0));
   // the larger PUs (one warp per job) on side stream 0, the shapes round-robin on the others, each second pass behind its first
-  static const int order[TZT_CLASSES] = { 0, 2, 3, 7, 4, 5, 8, 1, 6, 9 };      // most jobs first
+  // HMGPU_TZ_P2=0: no second pass, the jobs that need the refinement go to the warp-per-job kernel with the rest
+  static const int s_use_p2 = getenv("HMGPU_TZ_P2") ? atoi(getenv("HMGPU_TZ_P2")) : 0;
+  static const int order[TZT_CLASSES] = { 0, 2, 3, 7, 4, 5, 8, 1, 6, 9, 10, 11, 12, 13 };      // most jobs first
   for (int k = 0; k < TZT_CLASSES; k++)
   {
     const int c = order[k];
     cudaStream_t stream = ctx->tz_streams[1 + k % (HMGPU_TZ_STREAMS - 1)];
     const uint32_t* idx = lists + (size_t)c * cap;
     const TztShape& s = k_tzt_shapes[c];
-    for (int pass = 0; pass < 2; pass++)
+    for (int pass = 0; pass < (s_use_p2 ? 2 : 1); pass++)
     {
 #define TZT_CASE(WQ_, VR_, RM_) \
       if (s.wq == WQ_ && s.vr == VR_ && s.rm == RM_) \
-        rc = pass == 0 ? tzt_launch_one<WQ_, VR_, RM_, false>(ctx, stream, d_jobs, idx, counts, c, n_jobs, rt, ov, d_results, lists2, rest_idx) \
-                       : tzt_launch_one<WQ_, VR_, RM_, true>(ctx, stream, d_jobs, idx, counts, c, n_jobs, rt, ov, d_results, lists2, rest_idx)
+        rc = pass == 0 ? tzt_launch_one<WQ_, VR_, RM_, false>(ctx, stream, d_jobs, idx, counts, c, n_jobs, rt, ov, d_results, lists2, rest_idx, s_use_p2) \
+                       : tzt_launch_one<WQ_, VR_, RM_, true>(ctx, stream, d_jobs, idx, counts, c, n_jobs, rt, ov, d_results, lists2, rest_idx, s_use_p2)
       TZT_CASE(1, 8, 1); TZT_CASE(1, 8, 2); TZT_CASE(2, 4, 1); TZT_CASE(2, 8, 1); TZT_CASE(2, 8, 2);
       TZT_CASE(3, 8, 2); TZT_CASE(4, 4, 1); TZT_CASE(4, 8, 1); TZT_CASE(4, 6, 2); TZT_CASE(4, 8, 2);
+      TZT_CASE(8, 8, 1); TZT_CASE(2, 16, 2); TZT_CASE(4, 16, 2); TZT_CASE(8, 8, 2);
 #undef TZT_CASE
       if (rc) return rc;
     }

@@ -448,3 +448,43 @@ def test_selective_search(bit_depth, path):
         with pytest.raises(hmgpu.HmGpuError, match="predictors"):
             ctx.me_search(jobs[:2], side[:6])
     assert_results_equal(got, exp, jobs)
+
+
+@pytest.mark.parametrize("noise", [False, True])
+@pytest.mark.parametrize("p2", ["0", "1"])
+def test_tz_thread_per_job_kernels(noise, p2, monkeypatch):
+    """The one-thread-per-job TZ kernels (me_tz_thread.cu: per-shape launches, per-job windows in shared memory, hand-over of
+    refinement / raster / far-start jobs to the warp-per-job kernel or, with HMGPU_TZ_P2=1, to their second pass) against the
+    oracle, forced onto a batch far below the size from which the library picks them.  The job mix stresses what decides their
+    control flow: 2Nx2N integer MVs next to and far from the predictor, predictors at the picture edge (windows touching the
+    padded border are handed over), small search ranges (rings cut short), FEN on and off (without it the tall shapes go to
+    the warp-per-job kernel), every PU shape."""
+    monkeypatch.setenv("HMGPU_TZ_THREAD_MIN", "1")
+    monkeypatch.setenv("HMGPU_TZ_P2", p2)
+    rng = np.random.default_rng(77)
+    fr = _frames(8, 4, noise)
+    org = fr[3]
+    jobs, _, _ = _random_jobs(rng, 3000, 8, "tz", 3)
+    for i in range(len(jobs)):
+        j = jobs[i]
+        if i % 3 == 0:      # 2Nx2N integer MV within a few samples of the predictor (the common case in the encoder)
+            j["flags"] |= hmgpu.F_HAS_2NX2N
+            j["i2n_x"] = (int(j["pred_x"]) >> 2) + int(rng.integers(-3, 4))
+            j["i2n_y"] = (int(j["pred_y"]) >> 2) + int(rng.integers(-3, 4))
+        if i % 7 == 0:      # adaptive search range smaller than the far rings
+            sr = int(rng.choice([1, 2, 4, 8, 16]))
+            bd = [int(j[k]) for k in ("clip_hmin", "clip_hmax", "clip_vmin", "clip_vmax")]
+            j["search_range"] = sr
+            j["win_l"], j["win_t"], j["win_r"], j["win_b"] = hmgpu.search_range(bd, int(j["pred_x"]), int(j["pred_y"]), sr)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    exp = oracle_me(jobs, pads, org, 8)
+    with hmgpu.Context(W, H, 8, 3) as ctx:
+        for k in range(3):
+            ctx.ref_upload(k, fr[k])
+        ctx.org_upload(org)
+        got = ctx.me_search(jobs)
+        assert_results_equal(got, exp, jobs)
+        # the warp-per-job mapping gives the same bytes
+        monkeypatch.setenv("HMGPU_TZ_SPLIT", "0")
+        got0 = ctx.me_search(jobs)
+        assert got.tobytes() == got0.tobytes()
