@@ -274,6 +274,8 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
     if (ctx->refs[i].cb) cudaFree(ctx->refs[i].cb);
     if (ctx->refs[i].cr) cudaFree(ctx->refs[i].cr);
   }
+  if (ctx->frac_stream) { cudaStreamSynchronize(ctx->frac_stream); cudaStreamDestroy(ctx->frac_stream); }
+  for (int i = 0; i < 2; i++) if (ctx->frac_ev[i]) cudaEventDestroy(ctx->frac_ev[i]);
   for (int i = 0; i < HMGPU_TZ_STREAMS; i++) if (ctx->tz_streams[i]) { cudaStreamSynchronize(ctx->tz_streams[i]); cudaStreamDestroy(ctx->tz_streams[i]); }
   for (int i = 0; i <= HMGPU_TZ_STREAMS; i++) if (ctx->tz_ev[i]) cudaEventDestroy(ctx->tz_ev[i]);
   if (ctx->d_org) cudaFree(ctx->d_org);

@@ -69,6 +69,7 @@ struct hmgpu_ctx
   void* d_work; size_t d_work_bytes;   // device scratch for the search kernels
   void* d_tzlist; size_t d_tzlist_bytes; // device index lists of the TZ size classes (me_tz.cu)
   cudaStream_t tz_streams[HMGPU_TZ_STREAMS]; cudaEvent_t tz_ev[HMGPU_TZ_STREAMS + 1]; // side streams of the TZ stage (me_tz_thread.cu): kernels of different PU shapes overlap
+  cudaStream_t frac_stream; cudaEvent_t frac_ev[2];  // side stream of the fractional stage (me_frac2.cu)
   HmgpuLane lane_store[2]; int cur_lane; // parked lanes (the current one lives in the fields above)
   cudaEvent_t lane_done[2], scan_done[2], fork_ev;
   cudaStream_t copy_stream;              // H2D of the next chunk + its validation scan

@@ -111,9 +111,12 @@ frac_dist_kernel(const hmgpu_me_job* __restrict__ jobs, const int16_t* __restric
   }
 }
 
+// reuse_centre (packed path, me_frac2.cu): candidate 0 of the quarter-pel phase is the best half-pel position itself (both tables
+// start with (0,0)), i.e. the same block of the same phase plane: its distortion is copied from the half-pel phase instead of being
+// computed again (the dist kernel of phase 1 then skips candidate 0)
 __global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs,
                                    hmgpu_me_result* __restrict__ results, uint32_t* __restrict__ acc,
-                                   int bit_depth, int phase)
+                                   int bit_depth, int phase, int reuse_centre)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_jobs) return;
@@ -138,7 +141,17 @@ __global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_
                                4 * res.int_y + 2 * res.half_y + c_refine_q[c][1]);
     if (cost < best) { best = cost; bi = c; }
   }
-  if (phase == 0) { res.half_x = c_refine_h[bi][0]; res.half_y = c_refine_h[bi][1]; }
+  if (phase == 0)
+  {
+    res.half_x = c_refine_h[bi][0]; res.half_y = c_refine_h[bi][1];
+    if (reuse_centre)
+    {
+      uint32_t dsel = d9[0];
+#pragma unroll
+      for (int c = 1; c < 9; c++) if (c == bi) dsel = d9[c];
+      acc[(size_t)9 * n_jobs + j] = dsel;
+    }
+  }
   else { res.qter_x = c_refine_q[bi][0]; res.qter_y = c_refine_q[bi][1]; }
   res.frac_cost = best;
   res.n_cand += 9;
@@ -181,7 +194,7 @@ int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
         frac_dist_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(d_jobs, d_org_blocks, rt, ov, d_results, work, work_count, acc, phase, n_jobs);
       }
       HmgpuStage st2(ctx, HMGPU_ST_FRAC_SELECT, 1);
-      frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase);
+      frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase, 0);
     }
   }
   HMGPU_CUDA(ctx, cudaGetLastError());

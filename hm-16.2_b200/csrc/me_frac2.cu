@@ -17,6 +17,7 @@
 //     segments of horizontally adjacent tiles fall into the same 128-byte line (one L1 wavefront
 //     per row segment instead of one per word).
 #include "me_frac_impl.cuh"
+#include <stdlib.h>
 
 #define F2_THREADS 128
 
@@ -161,7 +162,7 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
   constexpr int OW = TS / 4;                             // source-picture words per row (aligned)
   // every WARP stages for itself (its 32 tiles, double-buffered) and synchronises with __syncwarp only: the CTA-wide
   // barriers of the first version (two per candidate) were 25-35 % of the stall samples (profiles/r1d_ncu_frac2_dist*)
-  __shared__ uint32_t s_ref_all[F2_THREADS / 32][2][TS][32 * NW];   // [warp][buffer][row][tile * NW + word]
+  __shared__ __align__(16) uint32_t s_ref_all[F2_THREADS / 32][2][TS][32 * NW];   // [warp][buffer][row][tile * NW + word]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t (*s_ref)[TS][32 * NW] = s_ref_all[warp];
@@ -219,8 +220,11 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
       cp_async_commit();
       return (int)((uintptr_t)p & 3) * 8;
     };
-    int sh_next = issue(0, 0);
-    for (int cand = 0; cand < 9; cand++)
+    // quarter-pel phase: candidate 0 is the best half-pel position, already costed in the half-pel phase (frac_select_kernel
+    // copies that sum)
+    const int c0 = phase ? 1 : 0;
+    int sh_next = issue(c0, c0 & 1);
+    for (int cand = c0; cand < 9; cand++)
     {
       const int sh = sh_next, buf = cand & 1;
       if (cand + 1 < 9) { sh_next = issue(cand + 1, buf ^ 1); cp_async_wait<1>(); }
@@ -236,7 +240,9 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 #pragma unroll
         for (int r = 0; r < TS; r++)
         {
-          const uint32_t w0 = s_ref[buf][r][lane * NW + 0], w1 = s_ref[buf][r][lane * NW + 1];
+          uint32_t w0, w1;
+          if (TS == 4) { const uint2 ww = *(const uint2*)&s_ref[buf][r][lane * NW]; w0 = ww.x; w1 = ww.y; }   // one LDS.64: the two words of a lane are 2-way bank-conflicted as LDS.32
+          else { w0 = s_ref[buf][r][lane * NW + 0]; w1 = s_ref[buf][r][lane * NW + 1]; }
           if (TS == 8)
           {
             const uint32_t w2 = s_ref[buf][r][lane * NW + NW - 1];
@@ -259,7 +265,9 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 #pragma unroll
         for (int r = 0; r < TS; r++)
         {
-          const uint32_t w0 = s_ref[buf][r][lane * NW + 0], w1 = s_ref[buf][r][lane * NW + 1];
+          uint32_t w0, w1;
+          if (TS == 4) { const uint2 ww = *(const uint2*)&s_ref[buf][r][lane * NW]; w0 = ww.x; w1 = ww.y; }
+          else { w0 = s_ref[buf][r][lane * NW + 0]; w1 = s_ref[buf][r][lane * NW + 1]; }
           v = vabsdiff4_acc(__funnelshift_r(w0, w1, sh), ow[r][0], v);
           if (TS == 8)
           {
@@ -275,7 +283,7 @@ frac2_dist_kernel(const hmgpu_me_job* __restrict__ jobs, RefTable refs, OrgView 
 
 __global__ void frac_select_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs,
                                    hmgpu_me_result* __restrict__ results, uint32_t* __restrict__ acc,
-                                   int bit_depth, int phase);
+                                   int bit_depth, int phase, int reuse_centre);
 
 int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, hmgpu_me_result* d_results, bool any_frac)
 {
@@ -304,12 +312,32 @@ int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_j
     for (int phase = 0; phase < 2; phase++)
     {
       {
+        // the two tile sizes side by side: the 8x8 kernel is issue-bound, the 4x4 kernel waits on L1 wavefronts (ncu,
+        // profiles/r1j_ncu_frac2_dist.csv), so they fill each other's gaps (HMGPU_FRAC_OVERLAP=0: one after the other)
         HmgpuStage st(ctx, HMGPU_ST_FRAC_DIST, 2);
+        static const int s_overlap = getenv("HMGPU_FRAC_OVERLAP") ? atoi(getenv("HMGPU_FRAC_OVERLAP")) : 1;
+        cudaStream_t side = ctx->stream;
+        if (s_overlap)
+        {
+          if (!ctx->frac_stream)
+          {
+            HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->frac_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; i++) HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frac_ev[i], cudaEventDisableTiming));
+          }
+          side = ctx->frac_stream;
+          HMGPU_CUDA(ctx, cudaEventRecord(ctx->frac_ev[0], ctx->stream));
+          HMGPU_CUDA(ctx, cudaStreamWaitEvent(side, ctx->frac_ev[0], 0));
+        }
+        frac2_dist_kernel<4><<<grid, F2_THREADS, 0, side>>>(d_jobs, rt, ov, d_results, work4, counts + 1, acc, phase, n_jobs);
         frac2_dist_kernel<8><<<grid, F2_THREADS, 0, ctx->stream>>>(d_jobs, rt, ov, d_results, work8, counts + 0, acc, phase, n_jobs);
-        frac2_dist_kernel<4><<<grid, F2_THREADS, 0, ctx->stream>>>(d_jobs, rt, ov, d_results, work4, counts + 1, acc, phase, n_jobs);
+        if (s_overlap)
+        {
+          HMGPU_CUDA(ctx, cudaEventRecord(ctx->frac_ev[1], side));
+          HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frac_ev[1], 0));
+        }
       }
       HmgpuStage st2(ctx, HMGPU_ST_FRAC_SELECT, 1);
-      frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase);
+      frac_select_kernel<<<(n_jobs + tb - 1) / tb, tb, 0, ctx->stream>>>(d_jobs, n_jobs, d_results, acc, ctx->bit_depth, phase, 1);
     }
   }
   HMGPU_CUDA(ctx, cudaGetLastError());
