@@ -122,7 +122,8 @@ def ncu_traffic(kernel_csv):
         rows = {r[0]: r for r in csv.reader(open(os.path.join(ROOT, "profiles", kernel_csv)))}
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
-        return float(rd[2]) * scale[rd[1]] + float(wr[2]) * scale[wr[1]]
+        # a stage is several launches (one column each): their sum is the traffic of the stage
+        return (sum(float(v) for v in rd[2:] if v) * scale[rd[1]] + sum(float(v) for v in wr[2:] if v) * scale[wr[1]])
     except (OSError, KeyError, ValueError, IndexError):
         return None
 
@@ -246,15 +247,21 @@ def run_ours(args, rank, world, local_rank):
         ops, byts = work[dom]
         dur = stage_ms[dom] * 1e-3
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic_csv = {"tz": "r1k_ncu_tz_search.csv", "frac_dist": "r1j_ncu_frac2_dist.csv"}.get(dom)
+        traffic_csv = {"tz": "r1n_ncu_tz_stage.csv", "frac_dist": "r1n_ncu_frac2_dist.csv"}.get(dom)
+        notes = {
+            "tz": "the TZ stage (classify + 14 one-thread-per-job shape kernels + 2 warp-per-job launches) is a chain of dependent "
+                  "points per job: bound by latency / instruction issue, not by HBM (DRAM traffic << algorithmic bytes: the planes "
+                  "are served by L2); see roofline_int32 and full_search.roofline for the integer-pipe view",
+            "frac_dist": "the fractional stage (8x8-tile and 4x4-tile SATD kernels, half- and quarter-pel phase) is bound by L1 / "
+                         "shared-memory wavefronts and integer issue (ncu: profiles/r1n_ncu_frac2_dist.csv), not by HBM: its 18 "
+                         "candidates per job re-read one small footprint from L2; see roofline_int32"}
         roofline = {"kernel": dom, "bound": "hbm", "achieved": byts / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": byts / dur / 1e9 / hbm_peak, "traffic": ncu_traffic(traffic_csv) if traffic_csv else None,
                     "traffic_source": ("profiles/" + traffic_csv) if traffic_csv else None,
                     "algorithmic_bytes_per_launch": byts,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "note": "TZ is a chain of dependent rounds of ~8 points: it is bound by instruction issue and L1 wavefronts, "
-                            "not by HBM (DRAM traffic << algorithmic bytes: the planes are served by L2); see roofline_int32 "
-                            "and full_search.roofline for the integer-pipe view"}
+                    "launches_per_step": int(prof[dom][1] // args.steps),
+                    "note": notes.get(dom, "")}
         roofline_int32 = {"kernel": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak,
                           "unit": "Gop/s", "frac": ops / dur / 1e9 / int_peak,
                           "peak_source": "hmgpu_microbench(0) LOP3+IADD lane-ops/s measured in this run",

@@ -92,10 +92,14 @@ tz_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restri
   const uint32_t n = *count;
   for (uint32_t k = blockIdx.x * TZ_WARPS + warp; k < n; k += gridDim.x * TZ_WARPS)
   {
-    const uint32_t job_id = idx[k];
+    // bit 31 of a list entry: the job comes from a one-thread-per-job kernel with its state parked in the result slot
+    const uint32_t e = idx[k];
+    const uint32_t job_id = e & 0x7fffffffu;
     const hmgpu_me_job jb = jobs[job_id];
+    hmgpu_me_result park;
+    if (e >> 31) park = results[job_id];
     hmgpu_me_result r;
-    tz_search_group<Px, PACKED, 32, MERGE>(jb, org_blocks, refs, org, s_org_all[warp], r);
+    tz_search_group<Px, PACKED, 32, MERGE>(jb, org_blocks, refs, org, s_org_all[warp], r, NULL, NULL, NULL, 0, (e >> 31) ? &park : NULL);
     if (lane == 0) results[job_id] = r;
     __syncwarp();
   }

@@ -381,7 +381,7 @@ template <typename Px, bool PACKED, int GS, bool MERGE = false>
 __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const int16_t* __restrict__ org_blocks,
                                                 const RefTable& refs, const OrgView& org, unsigned char* s_org,
                                                 hmgpu_me_result& out, const uint8_t* win_s = NULL, const TzWindow* win = NULL,
-                                                TzSpec* spec = NULL, int role = 0)
+                                                TzSpec* spec = NULL, int role = 0, const hmgpu_me_result* park = NULL)
 {
   const int gl = TzGroup<GS>::lane();
   const uint32_t gm = TzGroup<GS>::mask();
@@ -412,6 +412,19 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
   // ---- start points (TEncSearch.cpp:4045-4093): clipped MVP>>2, zero, clipped 2Nx2N integer MV.
   // Evaluated sequentially in the reference; concurrently here with emission order = sub-group index.
   const bool has2n = (jb.flags & HMGPU_F_HAS_2NX2N) != 0;
+  // park != NULL: the one-thread-per-job kernel (me_tz_thread.cu) has run the start points, the first search and its two-point
+  // fill of this job and parked the state in the result slot (int_x/int_y/int_sad = best point and its cost, half_x/half_y =
+  // its distance and point number, qter_x/qter_y = the best START point, n_cand): only the raster scan and the star refinement
+  // remain -- the parts where a warp per job pays.
+  const bool resumed = park != NULL;
+  int bsx = 0, bsy = 0;                                  // best start point
+  if (resumed)
+  {
+    best.cost = park->int_sad; best.x = park->int_x; best.y = park->int_y;
+    best.dist = park->half_x; best.pnr = park->half_y; best.n_cand = park->n_cand;
+    bsx = park->qter_x; bsy = park->qter_y;
+  }
+  else
   {
     const int lpp = pow2_floor(min(GS / 4, J.rows));
     const int i = gl >> (31 - __clz(lpp));
@@ -428,13 +441,14 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
     }
     const bool valid = i < (has2n ? 3 : 2);
     tz_eval<Px, PACKED, GS>(J, ref00, pitch, s_org, lpp, x, y, valid, 0, 0, best);
+    bsx = best.x; bsy = best.y;
   }
   // raster window: re-centred on the best start point when the 2Nx2N MV was tested (:4083-4092)
   int rL = J.L, rT = J.T, rR = J.R, rB = J.B;
   if (has2n)
   {
-    const int px = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(best.x << 2)));
-    const int py = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(best.y << 2)));
+    const int px = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(bsx << 2)));
+    const int py = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(bsy << 2)));
     const int sr4 = jb.search_range << 2;
     rL = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(px - sr4))) >> 2;
     rT = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(py - sr4))) >> 2;
@@ -444,7 +458,7 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
 
   // ---- first search: diamonds at distance 1,2,4,.. ; stop 3 rounds after the last improvement
   int cx = best.x, cy = best.y;
-  int d0 = 1;
+  int d0 = resumed ? jb.search_range + 1 : 1;
   if (spec)
   {
     // warps `role` = 0, 1, 2 of the CTA run this function together (same job, same start evaluation)
@@ -472,7 +486,7 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
       d0 = best.round >= 3 ? jb.search_range + 1 : 8;       // the reference stops 3 rounds after the last improvement
     }
   }
-  if (MERGE && GS == 32)
+  if (MERGE && GS == 32 && !resumed)
   {
     // Merged first rounds (batch kernel of the small PUs): the diamonds at distance 1, 2, 4, 8 all sit around the SAME centre, so
     // their 4 + 8 + 8 + 8 = 28 points are costed in ONE pass, one lane per point in emission order, against the best START point
@@ -513,12 +527,12 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
     tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, d, best);
     if (best.round >= 3) break;
   }
-  if (best.dist == 1)                                   // :4137-4141
+  if (best.dist == 1 && !resumed)                       // :4137-4141
   {
     best.dist = 0;
     tz_two_point<Px, PACKED, GS>(J, ref00, pitch, s_org, best);
   }
-  if (best.dist > 5)                                    // raster, step 5 (:4144-4154)
+  if (best.dist > 5 && !(resumed && park->frac_cost))   // raster, step 5 (:4144-4154); parked in the middle of the refinement: already behind it
   {
     best.dist = 5;
     const int nx = (rR - rL) / 5 + 1, ny = (rB - rT) / 5 + 1;
@@ -534,8 +548,31 @@ __device__ __forceinline__ void tz_search_group(const hmgpu_me_job& jb, const in
   {
     cx = best.x; cy = best.y;
     best.dist = 0; best.pnr = 0;
-    for (int d = 1; d < jb.search_range + 1; d <<= 1)
-      tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, d, best);
+    if (MERGE && GS == 32)
+    {
+      // All rings of a refinement round sit around the same centre and there is no early stop, so their points are costed
+      // together, one lane per point in emission order: distances 1, 2, 4, 8 (28 points) in one pass, then two 16-point rings
+      // per pass.  The strict-'<' scan over the whole round keeps the first minimum, which is what the passes, taken in order,
+      // keep (tz_eval).  Three passes instead of seven for SearchRange 64.
+      {
+        const int rr = gl < 4 ? 0 : (gl < 12 ? 1 : (gl < 20 ? 2 : 3));
+        int x, y, pnr, dist;
+        tz_diamond_point(cx, cy, 1 << rr, rr == 0 ? gl : ((gl + 4) & 7), x, y, pnr, dist);
+        const bool valid = gl < 28 && (1 << rr) <= jb.search_range && tz_in_window(J, cx, cy, x, y);
+        tz_eval<Px, PACKED, GS>(J, ref00, pitch, s_org, 1, x, y, valid, pnr, dist, best);
+      }
+      for (int d = 16; d <= jb.search_range; d <<= 2)
+      {
+        const int dd = gl < 16 ? d : d << 1;
+        int x, y, pnr, dist;
+        tz_diamond_point(cx, cy, dd, gl & 15, x, y, pnr, dist);
+        const bool valid = dd <= jb.search_range && tz_in_window(J, cx, cy, x, y);
+        tz_eval<Px, PACKED, GS>(J, ref00, pitch, s_org, 1, x, y, valid, pnr, dist, best);
+      }
+    }
+    else
+      for (int d = 1; d < jb.search_range + 1; d <<= 1)
+        tz_diamond<Px, PACKED, GS>(J, ref00, pitch, s_org, cx, cy, d, best);
     if (best.dist == 1)
     {
       best.dist = 0;

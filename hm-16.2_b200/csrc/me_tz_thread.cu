@@ -159,12 +159,15 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
     const int mvp_x = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)jb.start_x)) >> 2;
     const int mvp_y = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)jb.start_y)) >> 2;
     // window centre: the clipped predictor, or -- the two likely best start points being the predictor and the 2Nx2N integer MV --
-    // the point between them when they are at most 2 apart (both are then within 1 of it)
+    // the point between them when they are at most 2 (TZT_R - TZT_NEAR) apart (both are then within TZT_R - TZT_NEAR of it)
     const bool has2n = (jb.flags & HMGPU_F_HAS_2NX2N) != 0;
     const int i2n_x = min((int)jb.clip_hmax, max((int)jb.clip_hmin, (int)(int16_t)(jb.i2n_x << 2))) >> 2;
     const int i2n_y = min((int)jb.clip_vmax, max((int)jb.clip_vmin, (int)(int16_t)(jb.i2n_y << 2))) >> 2;
     int sx = mvp_x, sy = mvp_y;
-    if (has2n && abs(i2n_x - mvp_x) <= 2 && abs(i2n_y - mvp_y) <= 2) { sx = (mvp_x + i2n_x) >> 1; sy = (mvp_y + i2n_y) >> 1; }
+    if (has2n && abs(i2n_x - mvp_x) <= 2 * (TZT_R - TZT_NEAR) && abs(i2n_y - mvp_y) <= 2 * (TZT_R - TZT_NEAR))
+    {
+      sx = (mvp_x + i2n_x) >> 1; sy = (mvp_y + i2n_y) >> 1;
+    }
     if (P2 && have) { const hmgpu_me_result park = results[job_id]; sx = park.int_x; sy = park.int_y; }
     const uint8_t* plane_pu = (const uint8_t*)refs.base[have ? jb.ref_slot : 0] + (ptrdiff_t)jb.pu_y * gpitch + jb.pu_x;
     const int gx0 = jb.pu_x + sx - R, gy0 = jb.pu_y + sy - R;
@@ -349,6 +352,8 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
     // where the job goes if it is not finished here: 1 = second pass of this shape, 2 = warp-per-job kernel
     int ovf = (have && !ok) ? 2 : 0;
     int park_x = 0, park_y = 0;
+    bool resumable = false;                                      // handed over with the first search done: state parked for the warp
+    bool past_raster = false;                                    // ... in the middle of the star refinement
     if (ok)
     {
       // ---- start points (:4045-4093): clipped predictor, zero, clipped 2Nx2N integer MV ----
@@ -426,13 +431,13 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
             if (first && bround >= 3) break;
           }
           if (bdist == 1) { bdist = 0; two_point(); }            // (the refinement skips it for point number 0; so does two_point)
-          if (first && bdist > 5) { ovf = 2; break; }            // raster scan: warp-per-job kernel
+          if (first && bdist > 5) { ovf = 2; resumable = true; break; }   // raster scan: warp-per-job kernel
           first = false;
           if (bdist == 0) break;
-          if (!P2) { ovf = use_p2 ? 1 : 2; break; }              // needs the refinement: second pass (or the warp-per-job kernel)
+          if (!P2) { ovf = use_p2 ? 1 : 2; resumable = !use_p2; break; }   // needs the refinement: second pass (or the warp-per-job kernel)
           // a long walk (the optimum far from every start point) would keep 31 threads waiting for one: after a few
           // rounds the job goes to the warp-per-job kernel, which costs the points of a round in parallel
-          if (iter == TZT_MAX_REFINE) { ovf = 2; break; }
+          if (iter == TZT_MAX_REFINE) { ovf = 2; resumable = true; past_raster = true; break; }
           rcx = bx; rcy = by;
           bdist = 0; bpnr = 0;
         }
@@ -474,7 +479,20 @@ tzt_search_kernel(const hmgpu_me_job* __restrict__ jobs, const uint32_t* __restr
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(rest_count, (uint32_t)__popc(m2));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (ovf == 2) rest_idx[base + __popc(m2 & ((1u << lane) - 1u))] = job_id;
+      if (ovf == 2)
+      {
+        rest_idx[base + __popc(m2 & ((1u << lane) - 1u))] = job_id | (resumable ? 0x80000000u : 0u);
+        if (resumable)
+        {
+          // what tz_search_group needs to go on from here (see its `park` argument)
+          hmgpu_me_result park;
+          park.int_x = (int16_t)bx; park.int_y = (int16_t)by; park.int_sad = best_cost;
+          park.half_x = (int16_t)bdist; park.half_y = (int16_t)bpnr;
+          park.qter_x = (int16_t)park_x; park.qter_y = (int16_t)park_y;
+          park.frac_cost = past_raster ? 1u : 0u; park.n_cand = n_cand;
+          results[job_id] = park;
+        }
+      }
     }
     __syncwarp();                                                // the windows are rewritten by the next task
   }

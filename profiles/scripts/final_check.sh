@@ -1,3 +1,12 @@
 cd /root/repo
-python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-python bench.py --steps 5 --warmup 3 --no-encode --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -c 1500 gpurun_out/bench_quick.json | cut -c1-1500
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python __graft_entry__.py --smoke 2>&1 | tail -1
+python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_ref.json 2>/dev/null
+python bench.py --steps 2 --warmup 3 --no-encode --no-cpu-baseline --no-full-search > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench_final.csv python bench.py --steps 2 --warmup 3 --no-encode --no-cpu-baseline --no-full-search > gpurun_out/ncu_bench.log 2>&1
+# one step of the bench workload under ncu --set full: the TZ stage (17 launches) and the fractional stage (4 launches) of the second step
+python profiles/prof_step.py 2 > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"tz" -s 17 -c 17 -f -o gpurun_out/prof_r1n_tz python profiles/prof_step.py 2 > gpurun_out/ncu_tz.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"frac2_dist" -s 4 -c 4 -f -o gpurun_out/prof_r1n_frac python profiles/prof_step.py 2 > gpurun_out/ncu_frac.log 2>&1
+tail -1 gpurun_out/ncu_tz.log gpurun_out/ncu_frac.log
