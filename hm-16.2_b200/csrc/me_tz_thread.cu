@@ -21,8 +21,10 @@
 //     (A second one-thread-per-job pass for them exists, P2 / HMGPU_TZ_P2=1; measured slower: its kernels are a few very long
 //     warps each.)
 //   * the kernels of the 14 shapes and the warp-per-job kernel of the larger PUs run on side streams, so that the tail of one
-//     overlaps the body of the next.
-// Measured (1080p, 4 references, 1.18 M jobs): TZ stage 2.65 ms (one warp per job for everything) -> 1.75 ms; results are
+//     overlaps the body of the next.  (Tried and dropped: the shapes of similar window size in ONE launch, their tasks dealt out
+//     round-robin -- 2.15 ms instead of 1.40 ms for the stage: five instantiations in one kernel issue 11 % more instructions and
+//     run slower than the five launches.)
+// Measured (1080p, 4 references, 1.18 M jobs): TZ stage 2.65 ms (one warp per job for everything) -> 1.40 ms; results are
 // byte-identical (profiles/tz_ab.py prints an MD5 of the result array for either mapping).
 #include "me_tz_impl.cuh"
 #include <stdlib.h>
@@ -570,12 +572,16 @@ int hmgpu_launch_tz_thread(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_job
   }
   // launched last: its persistent CTAs would otherwise take every register of the machine before the first shape kernel starts
   if ((rc = hmgpu_launch_tz_list(ctx, ctx->tz_streams[0], d_jobs, big_idx, counts + TZT_CLASSES, n_jobs, d_org_blocks, d_results))) return rc;
-  for (int i = 0; i < HMGPU_TZ_STREAMS; i++)
+  // the hand-over list is complete when the shape kernels are done; it does not wait for the larger PUs (side stream 0),
+  // whose kernel it overlaps
+  for (int i = 1; i < HMGPU_TZ_STREAMS; i++)
   {
     HMGPU_CUDA(ctx, cudaEventRecord(ctx->tz_ev[i], ctx->tz_streams[i]));
     HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tz_ev[i], 0));
   }
   if ((rc = hmgpu_launch_tz_list(ctx, ctx->stream, d_jobs, rest_idx, counts + TZT_CLASSES + 1, n_jobs, d_org_blocks, d_results))) return rc;
+  HMGPU_CUDA(ctx, cudaEventRecord(ctx->tz_ev[0], ctx->tz_streams[0]));
+  HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tz_ev[0], 0));
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }
