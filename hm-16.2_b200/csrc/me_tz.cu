@@ -209,7 +209,7 @@ int hmgpu_launch_tz_list(hmgpu_ctx* ctx, cudaStream_t stream, const hmgpu_me_job
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
   const int grid = max(1, min(HMGPU_NUM_SMS * 16, (n_jobs_max + TZ_WARPS - 1) / TZ_WARPS));
   // HMGPU_TZ_MERGE=1: the rounds at distance 1, 2, 4, 8 of the first search as one pass of 28 lanes (see tz_search_group)
-  static const int s_merge = getenv("HMGPU_TZ_MERGE") ? atoi(getenv("HMGPU_TZ_MERGE")) : 1;
+  const int s_merge = getenv("HMGPU_TZ_MERGE") ? atoi(getenv("HMGPU_TZ_MERGE")) : 1;
   // HMGPU_TZ_CARVE=k: shared-memory carve-out (percent) asked for this kernel.  Kernels whose L1 / shared split differs do not share
   // an SM; the one-thread-per-job kernels next to it need (almost) all of it as shared memory.
   static const int s_carve = getenv("HMGPU_TZ_CARVE") ? atoi(getenv("HMGPU_TZ_CARVE")) : 50;

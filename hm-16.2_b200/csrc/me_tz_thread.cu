@@ -549,7 +549,7 @@ int hmgpu_launch_tz_thread(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_job
   for (int i = 0; i < HMGPU_TZ_STREAMS; i++) HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->tz_streams[i], ctx->tz_ev[HMGPU_TZ_STREAMS], 0));
   // the larger PUs (one warp per job) on side stream 0, the shapes round-robin on the others, each second pass behind its first
   // HMGPU_TZ_P2=0: no second pass, the jobs that need the refinement go to the warp-per-job kernel with the rest
-  static const int s_use_p2 = getenv("HMGPU_TZ_P2") ? atoi(getenv("HMGPU_TZ_P2")) : 0;
+  const int s_use_p2 = getenv("HMGPU_TZ_P2") ? atoi(getenv("HMGPU_TZ_P2")) : 0;
   static const int order[TZT_CLASSES] = { 0, 2, 3, 7, 4, 5, 8, 1, 6, 9, 10, 11, 12, 13 };      // most jobs first
   for (int k = 0; k < TZT_CLASSES; k++)
   {

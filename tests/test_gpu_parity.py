@@ -488,3 +488,8 @@ def test_tz_thread_per_job_kernels(noise, p2, monkeypatch):
         monkeypatch.setenv("HMGPU_TZ_SPLIT", "0")
         got0 = ctx.me_search(jobs)
         assert got.tobytes() == got0.tobytes()
+        # ... and so does the warp-per-job kernel without its merged passes (hand-over jobs resume in it either way)
+        monkeypatch.setenv("HMGPU_TZ_MERGE", "0")
+        assert ctx.me_search(jobs).tobytes() == got.tobytes()
+        monkeypatch.setenv("HMGPU_TZ_SPLIT", "5")
+        assert ctx.me_search(jobs).tobytes() == got.tobytes()
