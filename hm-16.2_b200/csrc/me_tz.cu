@@ -1,11 +1,15 @@
 // me_tz.cu -- batch TZ search kernels.  Replaces TEncSearch::xTZSearch (TEncSearch.cpp:4027-4228);
 // the search itself is in me_tz_impl.cuh.
 //
-//   tz_classify_kernel      : splits the TZ jobs of a batch into two index lists by PU size
-//   tz_search_small_kernel  : PUs of <= 128 visited pixels, FOUR jobs per warp (8 lanes each)
-//   tz_search_kernel        : everything else, one warp per job
-// Both search kernels are persistent grid-stride loops over their list (its length is only known
-// on the device).
+//   tz_search_kernel        : one warp per job over an index list (persistent grid-stride loop; the list length is only known on
+//                             the device).  In the default mapping of large 8-bit batches (HMGPU_TZ_SPLIT=5, hmgpu_launch_tz) it
+//                             searches the larger PUs and the jobs handed over by the one-thread-per-job kernels of
+//                             me_tz_thread.cu -- those resume from the state parked in their result slot (bit 31 of the list
+//                             entry) -- with the first rounds and the refinement rounds merged into passes of up to 32 points
+//                             (MERGE).  Small batches, >8-bit pictures and explicit key patterns: every TZ job, unmerged.
+//   tz_selective_kernel     : xTZSearchSelective jobs (FastSearch = 2)
+//   tz_classify_kernel, tz_search_small_kernel, tz_search_win_kernel, tz_search_near_kernel (and me_tz_lock.cu): the earlier
+//                             mappings HMGPU_TZ_SPLIT=1..4, bit-exact, slower, kept for study (numbers in hmgpu_launch_tz).
 #include "me_tz_impl.cuh"
 #include <stdlib.h>
 
