@@ -100,9 +100,12 @@ def algorithmic_work(jobs, results):
     fen = (jobs["flags"] & hmgpu.F_FEN) != 0
     rows = np.where(fen & (h > 8), h // 2, h)
     int_cand = results["n_cand"].astype(np.int64) - 18
-    # integer SAD candidate: W*(H>>s) abs-diff-accumulates (+1 MV cost); bytes: 1 B/sample org + ref footprint
+    # integer SAD candidate: W*(H>>s) abs-diff-accumulates (+1 MV cost).  Compulsory bytes: the search window is
+    # read ONCE per search, (W + R - L) x (H + B - T) reference samples, plus the W x H source block (1 B/sample at 8 bit)
     tz_ops = int((int_cand * (w * rows + 1)).sum())
-    tz_bytes = int((int_cand * w * rows * 2).sum())
+    win_w = w + jobs["win_r"].astype(np.int64) - jobs["win_l"].astype(np.int64)
+    win_h = h + jobs["win_b"].astype(np.int64) - jobs["win_t"].astype(np.int64)
+    tz_bytes = int((win_w * win_h + w * h).sum())
     # SATD candidate: 576 int ops per 8x8 tile, 112 per 4x4 tile; 18 candidates share one (W+8)x(H+8) footprint
     t8 = ((w % 8) == 0) & ((h % 8) == 0)
     tiles = np.where(t8, (w // 8) * (h // 8), (w // 4) * (h // 4))
@@ -255,18 +258,22 @@ def run_ours(args, rank, world, local_rank):
             "frac_dist": "the fractional stage (8x8-tile and 4x4-tile SATD kernels, half- and quarter-pel phase) is bound by L1 / "
                          "shared-memory wavefronts and integer issue (ncu: profiles/r1n_ncu_frac2_dist.csv), not by HBM: its 18 "
                          "candidates per job re-read one small footprint from L2; see roofline_int32"}
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": byts / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": byts / dur / 1e9 / hbm_peak, "traffic": ncu_traffic(traffic_csv) if traffic_csv else None,
+        # The dominant stage is integer-pipe work out of L1 / shared memory (the north star's "INT32-pipe roofline"; the task's
+        # schema only names hbm | tensor, neither of which bounds it), so the headline roofline is the measured INT32 lane-op
+        # rate; the same stage in HBM terms is kept as a sub-object.
+        roofline = {"kernel": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak, "unit": "G int-op/s",
+                    "frac": ops / dur / 1e9 / int_peak,
+                    "peak_source": "hmgpu_microbench(0): LOP3 + IMAD.IADD lane-ops/s on both integer pipes, measured in this run",
+                    "algorithmic_ops_per_step": ops, "launches_per_step": int(prof[dom][1] // args.steps),
+                    "traffic": ncu_traffic(traffic_csv) if traffic_csv else None,
                     "traffic_source": ("profiles/" + traffic_csv) if traffic_csv else None,
-                    "algorithmic_bytes_per_launch": byts,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "launches_per_step": int(prof[dom][1] // args.steps),
+                    "hbm": {"achieved": byts / dur / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / dur / 1e9 / hbm_peak,
+                            "algorithmic_bytes_per_step": byts,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
                     "note": notes.get(dom, "")}
-        roofline_int32 = {"kernel": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak,
-                          "unit": "Gop/s", "frac": ops / dur / 1e9 / int_peak,
-                          "peak_source": "hmgpu_microbench(0) LOP3+IADD lane-ops/s measured in this run",
-                          "vabsdiff4_peak_glaneops": sad4_peak,
+        roofline_int32 = {"peak": int_peak, "unit": "Gop/s", "vabsdiff4_peak_glaneops": sad4_peak,
                           "per_stage": {k: {"ms": stage_ms[k], "gops": work[k][0] / (stage_ms[k] * 1e-3) / 1e9,
+                                            "frac": work[k][0] / (stage_ms[k] * 1e-3) / 1e9 / int_peak,
                                             "gbs": work[k][1] / (stage_ms[k] * 1e-3) / 1e9} for k in stage_ms if k in work}}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -480,7 +487,9 @@ def cpu_reference_run(jobs, frames, sample_jobs, procs):
     kind = "reference" if B.have_ref() else "port"
     stride = max(1, len(jobs) // max(1, sample_jobs))
     sample = np.ascontiguousarray(jobs[::stride][:sample_jobs])
-    chunks = np.array_split(sample, procs)
+    # dealt round-robin: the job list is ordered by CU depth (64x64 PUs first, 8x4 / 4x8 last), so contiguous chunks would give
+    # the first worker several times the work of the last and the wall clock (max over workers) would flatter the GPU
+    chunks = [sample[k::procs] for k in range(procs)]
     argsl = [(kind, np.ascontiguousarray(c).tobytes(), len(c), frames, BIT_DEPTH) for c in chunks if len(c)]
     t0 = time.perf_counter()
     if procs == 1:

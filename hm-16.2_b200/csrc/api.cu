@@ -54,6 +54,35 @@ int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...)
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
+// the environment is read here, once per context, and nowhere else
+static void tuning_from_env(HmgpuTuning* t)
+{
+  t->tz_thread      = env_int("HMGPU_TZ_SPLIT", 5) != 0;
+  t->tz_thread_min  = env_int("HMGPU_TZ_THREAD_MIN", 4096);
+  t->tz_merge       = env_int("HMGPU_TZ_MERGE", 1);
+  t->tz_carve       = env_int("HMGPU_TZ_CARVE", 50);
+  t->tz_p2          = env_int("HMGPU_TZ_P2", 0);
+  t->frac_v1        = env_int("HMGPU_FRAC_V1", 0);
+  t->frac_overlap   = env_int("HMGPU_FRAC_OVERLAP", 1);
+  t->pipe_chunk     = env_int("HMGPU_PIPE_CHUNK", 0);
+  t->pipeline       = !env_int("HMGPU_NO_PIPELINE", 0);
+  t->fastpath       = !env_int("HMGPU_NO_FASTPATH", 0);
+  t->server         = env_int("HMGPU_SERVER", 1);
+  t->server_idle_us = env_int("HMGPU_SERVER_IDLE_US", 200);
+  t->trace          = getenv("HMGPU_TRACE") != NULL;
+  t->server_stats   = getenv("HMGPU_SERVER_STATS") != NULL;
+}
+
+struct TuneName { const char* name; int HmgpuTuning::* field; };
+static const TuneName k_tune_names[] = {
+  { "tz_thread", &HmgpuTuning::tz_thread }, { "tz_thread_min", &HmgpuTuning::tz_thread_min }, { "tz_merge", &HmgpuTuning::tz_merge },
+  { "tz_carve", &HmgpuTuning::tz_carve }, { "tz_p2", &HmgpuTuning::tz_p2 }, { "frac_v1", &HmgpuTuning::frac_v1 },
+  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipeline", &HmgpuTuning::pipeline },
+  { "fastpath", &HmgpuTuning::fastpath }, { "server", &HmgpuTuning::server }, { "server_idle_us", &HmgpuTuning::server_idle_us },
+  { "trace", &HmgpuTuning::trace }, { "server_stats", &HmgpuTuning::server_stats } };
+
 // true when p is page-locked host memory known to CUDA (hmgpu_host_alloc or the caller's own cudaHostAlloc)
 static bool is_pinned(const void* p)
 {
@@ -148,7 +177,7 @@ int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   int rc;
   if (any_tz && (rc = hmgpu_launch_tz(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, any_sel))) return rc;
   if (any_full && (rc = hmgpu_launch_full(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, max_win_bytes))) return rc;
-  if (ctx->px_bytes == 1 && !any_org_block && !getenv("HMGPU_FRAC_V1"))
+  if (ctx->px_bytes == 1 && !any_org_block && !ctx->tune.frac_v1)
   {
     if ((rc = hmgpu_launch_frac_packed(ctx, d_jobs, n_jobs, d_results, any_frac))) return rc;
   }
@@ -191,6 +220,19 @@ int hmgpu_host_free(hmgpu_ctx* ctx, void* p)
   return HMGPU_OK;
 }
 
+int hmgpu_set_option(hmgpu_ctx* ctx, const char* name, int value)
+{
+  if (!ctx || !name) return HMGPU_E_INVALID;
+  for (size_t i = 0; i < sizeof k_tune_names / sizeof k_tune_names[0]; i++)
+    if (!strcmp(name, k_tune_names[i].name))
+    {
+      if (&(ctx->tune.*k_tune_names[i].field) == &ctx->tune.server && !value) { const int rc = hmgpu_server_stop(ctx); if (rc) return rc; }
+      ctx->tune.*k_tune_names[i].field = value;
+      return HMGPU_OK;
+    }
+  return hmgpu_fail(ctx, HMGPU_E_INVALID, "unknown option '%s'", name);
+}
+
 int hmgpu_synchronize(hmgpu_ctx* ctx)
 {
   if (!ctx) return HMGPU_E_INVALID;
@@ -202,8 +244,8 @@ int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, 
 {
   if (!out) return hmgpu_fail(NULL, HMGPU_E_INVALID, "out is NULL");
   *out = NULL;
-  if (pic_w < 8 || pic_h < 8 || (pic_w & 3) || (pic_h & 3) || pic_w > 8192 || pic_h > 8192)
-    return hmgpu_fail(NULL, HMGPU_E_INVALID, "picture size %dx%d unsupported (multiples of 4, 8..8192)", pic_w, pic_h);
+  if (pic_w < 8 || pic_h < 8 || (pic_w & 3) || (pic_h & 3) || pic_w > 8184 || pic_h > 8184)
+    return hmgpu_fail(NULL, HMGPU_E_INVALID, "picture size %dx%d unsupported (multiples of 4, 8..8184: quarter-pel clipMv bounds are int16)", pic_w, pic_h);
   if (bit_depth < 8 || bit_depth > 12) return hmgpu_fail(NULL, HMGPU_E_INVALID, "bit depth %d unsupported (8..12)", bit_depth);
   if (max_refs < 1 || max_refs > HMGPU_MAX_REFS) return hmgpu_fail(NULL, HMGPU_E_INVALID, "max_refs %d not in 1..%d", max_refs, HMGPU_MAX_REFS);
   int n_dev = 0;
@@ -218,6 +260,7 @@ int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, 
   if (!ctx) return hmgpu_fail(NULL, HMGPU_E_NOMEM, "out of host memory");
   memset(ctx, 0, sizeof *ctx);
   ctx->device = device; ctx->pic_w = pic_w; ctx->pic_h = pic_h; ctx->bit_depth = bit_depth; ctx->max_refs = max_refs;
+  tuning_from_env(&ctx->tune);
   ctx->px_bytes = bit_depth == 8 ? 1 : 2;
   ctx->pw = pic_w + 2 * HMGPU_MARGIN; ctx->ph = pic_h + 2 * HMGPU_MARGIN;
   ctx->pitch = (int)round_up(ctx->pw + 32, 64);          // slack for aligned look-ahead loads
@@ -248,7 +291,7 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   cudaSetDevice(ctx->device);
   hmgpu_server_stop(ctx);
   if (ctx->srv_stream) { cudaStreamSynchronize(ctx->srv_stream); cudaStreamDestroy(ctx->srv_stream); }
-  if (getenv("HMGPU_TRACE") || getenv("HMGPU_SERVER_STATS"))
+  if (ctx->tune.trace || ctx->tune.server_stats)
     fprintf(stderr, "[hmgpu server] %u calls served by %u server generations\n", ctx->srv_calls, ctx->srv_starts);
   hmgpu_use_lane(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
@@ -417,6 +460,16 @@ int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride)
 
 // ---- motion search --------------------------------------------------------------------------
 
+// PU shapes the search kernels take: sides multiples of 4 in 4..64 and at most 64 SATD tiles (8x8 tiles iff both sides are
+// multiples of 8, else 4x4: TComRdCost.cpp:1555-1597) -- the fractional stage packs (job, tile) with 6 tile bits.  Every HEVC PU
+// shape qualifies (4x4-tiled HEVC shapes have at most 12x16/16 = 12 tiles); 36x32 or 60x64 do not.
+__host__ __device__ static inline bool hmgpu_pu_shape_ok(int w, int h)
+{
+  if (w < 4 || w > 64 || h < 4 || h > 64 || (w & 3) || (h & 3)) return false;
+  const int ts = ((w & 7) == 0 && (h & 7) == 0) ? 8 : 4;
+  return (w / ts) * (h / ts) <= 64;
+}
+
 static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_org_elems,
                          bool* any_org, bool* any_full, bool* any_tz, bool* any_frac, int* max_win_bytes, int first = 0,
                          bool* any_sel = NULL)
@@ -428,7 +481,7 @@ static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_
   for (int i = first; i < first + n; i++)
   {
     const hmgpu_me_job& j = jobs[i];
-    if (j.pu_w < 4 || j.pu_w > 64 || j.pu_h < 4 || j.pu_h > 64 || (j.pu_w & 3) || (j.pu_h & 3))
+    if (!hmgpu_pu_shape_ok(j.pu_w, j.pu_h))
       return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: PU %dx%d unsupported", i, j.pu_w, j.pu_h);
     if (j.pu_x < 0 || j.pu_y < 0 || j.pu_x + j.pu_w > ctx->pic_w || j.pu_y + j.pu_h > ctx->pic_h || (j.pu_x & 3))
       return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: PU at (%d,%d) outside the picture or x not a multiple of 4", i, j.pu_x, j.pu_y);
@@ -506,7 +559,7 @@ static const char* const k_scan_msg[] = {
 
 __host__ __device__ static inline int job_check(const hmgpu_me_job& j, int pic_w, int pic_h, uint32_t valid_slots, unsigned long long n_org_elems)
 {
-  if (j.pu_w < 4 || j.pu_w > 64 || j.pu_h < 4 || j.pu_h > 64 || (j.pu_w & 3) || (j.pu_h & 3)) return SCAN_PU_SIZE;
+  if (!hmgpu_pu_shape_ok(j.pu_w, j.pu_h)) return SCAN_PU_SIZE;
   if (j.pu_x < 0 || j.pu_y < 0 || j.pu_x + j.pu_w > pic_w || j.pu_y + j.pu_h > pic_h || (j.pu_x & 3)) return SCAN_PU_POS;
   if (j.ref_slot >= 32 || !((valid_slots >> j.ref_slot) & 1u)) return SCAN_SLOT;
   const int lo_x = j.pu_x + (j.clip_hmin >> 2) - 4, hi_x = j.pu_x + j.pu_w + (j.clip_hmax >> 2) + 4;
@@ -566,7 +619,7 @@ __global__ void job_scan_kernel(const hmgpu_me_job* __restrict__ jobs, int n, in
 static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                                const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
 {
-  static const int s_chunk = getenv("HMGPU_PIPE_CHUNK") ? atoi(getenv("HMGPU_PIPE_CHUNK")) : 0;
+  const int s_chunk = ctx->tune.pipe_chunk;
   // a quarter of the batch per chunk: the TZ stage of a chunk is ~17 launches on side streams whose tails overlap best when the
   // chunk is large (1.18 M jobs, measured end to end: 8 chunks 5.32 ms, 4 chunks 4.72 ms, 2 chunks 4.70 ms)
   int chunk = s_chunk > 0 ? s_chunk : (n_jobs + 3) / 4;
@@ -740,7 +793,7 @@ static int hmgpu_server_stop(hmgpu_ctx* ctx)
 
 static int server_start(hmgpu_ctx* ctx, Mailbox* mb, int dyn_bytes)
 {
-  static const int s_idle_us = getenv("HMGPU_SERVER_IDLE_US") ? atoi(getenv("HMGPU_SERVER_IDLE_US")) : 200;
+  const int s_idle_us = ctx->tune.server_idle_us;
   if (!ctx->srv_stream) HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->srv_stream, cudaStreamNonBlocking));
   // ordered after everything already queued on the context's stream (uploads are synchronous, this is belt and braces)
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -834,11 +887,7 @@ static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* job
   return rc ? rc : server_wait(ctx, mb, results);
 }
 
-static bool server_enabled()
-{
-  static const bool s_on = !(getenv("HMGPU_SERVER") && atoi(getenv("HMGPU_SERVER")) == 0) && getenv("HMGPU_TRACE") == NULL;
-  return s_on;
-}
+static bool server_enabled(const hmgpu_ctx* ctx) { return ctx->tune.server && !ctx->tune.trace; }
 
 // Asynchronous pair ("async submit/poll for the mailbox path").  hmgpu_me_submit returns as soon as the jobs are
 // visible to the device; the caller does host work that does not need the vectors (HM: the merge estimation of the PU) and
@@ -849,13 +898,14 @@ int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const 
   if (ctx->pend_n || ctx->defer_n) return hmgpu_fail(ctx, HMGPU_E_STATE, "hmgpu_me_submit: the previous submit has not been waited for");
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || n_jobs < 0 || n_jobs > MAIL_JOBS) return hmgpu_fail(ctx, HMGPU_E_INVALID, "hmgpu_me_submit takes 1..%d jobs", MAIL_JOBS);
+  if (org_blocks && n_org_elems < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "n_org_elems is negative");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   bool any_org, any_full, any_tz, any_frac, any_sel;
   int max_win;
   int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, 0, &any_sel);
   if (rc) return rc;
   any_org = any_org || any_sel;                            // here: "the side array travels" (key patterns or MV predictors)
-  if (server_enabled() && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024 && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64))
+  if (server_enabled(ctx) && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024 && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64))
   {
     if (!ctx->h_mail)
     {
@@ -903,16 +953,17 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   if (!ctx) return HMGPU_E_INVALID;
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || !results || n_jobs < 0 || n_jobs > (1 << 26)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
+  if (org_blocks && n_org_elems < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "n_org_elems is negative");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n_jobs > MAIL_JOBS) { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // a batch wants the whole GPU
-  if (n_jobs >= PIPE_MIN_JOBS && !getenv("HMGPU_NO_PIPELINE")) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
+  if (n_jobs >= PIPE_MIN_JOBS && ctx->tune.pipeline) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
   bool any_org, any_full, any_tz, any_frac, any_sel;
   int max_win;
   int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, 0, &any_sel);
   if (rc) return rc;
   const bool key_blocks = any_org;                         // int16 key patterns present: selects the non-packed kernels
   any_org = any_org || any_sel;                            // below: "the side array travels" (key patterns or MV predictors)
-  if (n_jobs <= MAIL_JOBS && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64) && !getenv("HMGPU_NO_FASTPATH"))
+  if (n_jobs <= MAIL_JOBS && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64) && ctx->tune.fastpath)
   {
     // ---- low-latency path: mapped pinned mailbox, one fused kernel, host spins on the flags ----
     if (!ctx->h_mail)
@@ -921,8 +972,8 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
       memset(ctx->h_mail, 0, sizeof(Mailbox));
     }
     Mailbox* mb = (Mailbox*)ctx->h_mail;
-    static const bool s_trace = getenv("HMGPU_TRACE") != NULL;
-    if (server_enabled() && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024)
+    const bool s_trace = ctx->tune.trace != 0;
+    if (server_enabled(ctx) && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024)
       return me_search_server(ctx, mb, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win, results);
     const double t0 = s_trace ? now_us() : 0.0;
     HmgpuJobPack pack;
@@ -1013,13 +1064,19 @@ int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const
                          integer, (flags_any & HMGPU_F_FRAC) != 0, 64 * 1024, false);
 }
 
+void hmgpu_clip_bounds_ctu(int pic_w, int pic_h, int cu_x, int cu_y, int max_cu_w, int max_cu_h, int16_t bounds[4])
+{
+  // TComDataCU::clipMv (TComDataCU.cpp:2917-2929): iOffset = 8, bounds relative to the CU origin, g_uiMaxCUWidth / Height on the
+  // low side.  With pictures up to 8184 samples (hmgpu_create) every bound fits int16.
+  bounds[0] = (int16_t)((-max_cu_w - 8 - cu_x + 1) * 4);
+  bounds[1] = (int16_t)((pic_w + 8 - cu_x - 1) * 4);
+  bounds[2] = (int16_t)((-max_cu_h - 8 - cu_y + 1) * 4);
+  bounds[3] = (int16_t)((pic_h + 8 - cu_y - 1) * 4);
+}
+
 void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4])
 {
-  // TComDataCU::clipMv (TComDataCU.cpp:2917-2929), g_uiMaxCUWidth = g_uiMaxCUHeight = 64
-  bounds[0] = (int16_t)((-64 - 8 - cu_x + 1) * 4);
-  bounds[1] = (int16_t)((pic_w + 8 - cu_x - 1) * 4);
-  bounds[2] = (int16_t)((-64 - 8 - cu_y + 1) * 4);
-  bounds[3] = (int16_t)((pic_h + 8 - cu_y - 1) * 4);
+  hmgpu_clip_bounds_ctu(pic_w, pic_h, cu_x, cu_y, 64, 64, bounds);      // g_uiMaxCUWidth = g_uiMaxCUHeight = 64 (every BASELINE cfg)
 }
 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

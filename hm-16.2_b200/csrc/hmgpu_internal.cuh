@@ -53,9 +53,32 @@ struct HmgpuLane
   void* d_tzlist; size_t d_tzlist_bytes;
 };
 
+// Tuning knobs, read from the environment ONCE (hmgpu_create) and changed afterwards only through hmgpu_set_option:
+// nothing on a launch path calls getenv.
+struct HmgpuTuning
+{
+  int tz_thread;        // HMGPU_TZ_SPLIT != 0: one-thread-per-job TZ kernels for large 8-bit batches (me_tz_thread.cu)
+  int tz_thread_min;    // HMGPU_TZ_THREAD_MIN: batch size from which they are used
+  int tz_merge;         // HMGPU_TZ_MERGE: merged passes in the warp-per-job kernel
+  int tz_carve;         // HMGPU_TZ_CARVE: shared-memory carve-out (percent) of the warp-per-job kernel, < 0: driver default
+  int tz_p2;            // HMGPU_TZ_P2: second one-thread-per-job pass for hand-over jobs
+  int frac_v1;          // HMGPU_FRAC_V1: generic fractional kernels for 8-bit pictures too
+  int frac_overlap;     // HMGPU_FRAC_OVERLAP: 8x8 / 4x4 tile kernels side by side
+  int pipe_chunk;       // HMGPU_PIPE_CHUNK: jobs per chunk of the pipelined batch path (0: a quarter of the batch)
+  int pipeline;         // !HMGPU_NO_PIPELINE
+  int fastpath;         // !HMGPU_NO_FASTPATH
+  int server;           // HMGPU_SERVER: resident mailbox server for calls of <= HMGPU_SERVER_CTAS jobs
+  int server_idle_us;   // HMGPU_SERVER_IDLE_US
+  int trace;            // HMGPU_TRACE
+  int server_stats;     // HMGPU_SERVER_STATS
+};
+
 struct hmgpu_ctx
 {
   int device, pic_w, pic_h, bit_depth, max_refs;
+  HmgpuTuning tune;
+  uint32_t attr_tzt;            // same, one bit per (shape, pass) instantiation of tzt_search_kernel
+  uint32_t attr_done;           // per-context record of the cudaFuncSetAttribute calls made (attributes are per device)
   int px_bytes;                 // 1 (8-bit) or 2
   int pw, ph, pitch;            // padded luma geometry (elements)
   size_t plane_elems;
@@ -137,6 +160,9 @@ int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes);
 RefTable hmgpu_ref_table(const hmgpu_ctx* ctx);
 void hmgpu_use_lane(hmgpu_ctx* ctx, int lane);
+
+// bits of hmgpu_ctx::attr_done
+enum { HMGPU_ATTR_SINGLE = 1, HMGPU_ATTR_SERVER = 2, HMGPU_ATTR_FULL = 4, HMGPU_ATTR_TZT = 8, HMGPU_ATTR_TZ_CARVE = 16, HMGPU_ATTR_FRAC3 = 32 };
 
 #define HMGPU_CUDA(ctx, call)                                                              \
   do {                                                                                     \

@@ -315,7 +315,7 @@ int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_j
         // the two tile sizes side by side: the 8x8 kernel is issue-bound, the 4x4 kernel waits on L1 wavefronts (ncu,
         // profiles/r1j_ncu_frac2_dist.csv), so they fill each other's gaps (HMGPU_FRAC_OVERLAP=0: one after the other)
         HmgpuStage st(ctx, HMGPU_ST_FRAC_DIST, 2);
-        static const int s_overlap = getenv("HMGPU_FRAC_OVERLAP") ? atoi(getenv("HMGPU_FRAC_OVERLAP")) : 1;
+        const int s_overlap = ctx->tune.frac_overlap;
         cudaStream_t side = ctx->stream;
         if (s_overlap)
         {

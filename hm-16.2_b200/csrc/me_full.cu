@@ -25,8 +25,6 @@ full_search_generic_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jobs, co
   full_search_block_generic<Px>(jb, org_blocks, refs, org, s_org, s_red, &results[blockIdx.x]);
 }
 
-static bool s_attr_set = false;
-
 int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_org_block, int max_win_bytes)
 {
@@ -35,10 +33,10 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
   HmgpuStage st(ctx, HMGPU_ST_FULL, 1);
   if (ctx->px_bytes == 1 && !any_org_block)
   {
-    if (!s_attr_set)
+    if (!(ctx->attr_done & HMGPU_ATTR_FULL))
     {
       HMGPU_CUDA(ctx, cudaFuncSetAttribute(full_search_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      s_attr_set = true;
+      ctx->attr_done |= HMGPU_ATTR_FULL;
     }
     if (max_win_bytes > 200 * 1024) return hmgpu_fail(ctx, HMGPU_E_INVALID, "full-search window needs %d bytes of shared memory", max_win_bytes);
     full_search_packed_kernel<<<n_jobs, FS_THREADS, max_win_bytes, ctx->stream>>>(d_jobs, n_jobs, rt, ov, d_results);

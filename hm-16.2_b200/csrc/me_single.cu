@@ -352,8 +352,6 @@ me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org
   if (tid == 0) exited[blockIdx.x] = gen;
 }
 
-static bool s_sg_attr_set = false;
-
 int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, const int16_t* d_org_blocks,
                         HmgpuMailSlot* d_slots, uint32_t ticket, bool any_org_block, int max_win_bytes, unsigned long long* trace)
 {
@@ -362,10 +360,10 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, co
   HmgpuStage st(ctx, HMGPU_ST_SINGLE, 1);
   if (ctx->px_bytes == 1 && !any_org_block)
   {
-    if (!s_sg_attr_set)
+    if (!(ctx->attr_done & HMGPU_ATTR_SINGLE))
     {
       HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_single_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-      s_sg_attr_set = true;
+      ctx->attr_done |= HMGPU_ATTR_SINGLE;
     }
     if (max_win_bytes > 180 * 1024) return hmgpu_fail(ctx, HMGPU_E_INVALID, "full-search window needs %d bytes of shared memory", max_win_bytes);
     const int dyn = max_win_bytes > SG_WIN_BYTES ? max_win_bytes : SG_WIN_BYTES;
@@ -379,19 +377,17 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, co
   return HMGPU_OK;
 }
 
-static bool s_srv_attr_set = false;
-
 // start a server generation: n_ctas CTAs, dyn_bytes of dynamic shared memory each
 int hmgpu_launch_server(hmgpu_ctx* ctx, cudaStream_t stream, const uint32_t* d_lines, const int16_t* d_org_blocks, HmgpuMailSlot* d_slots,
                         uint32_t* d_exited, uint32_t gen, uint32_t last_ticket, unsigned long long idle_ns, int n_ctas, int dyn_bytes)
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
-  if (!s_srv_attr_set)
+  if (!(ctx->attr_done & HMGPU_ATTR_SERVER))
   {
     HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_server_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
     HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_server_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-    s_srv_attr_set = true;
+    ctx->attr_done |= HMGPU_ATTR_SERVER;
   }
   ctx->launches += 1; ctx->prof_launches[HMGPU_ST_SINGLE] += 1;
   if (ctx->px_bytes == 1)

@@ -12,12 +12,9 @@
 // best -- which is what a (cost, lane) min over lanes ordered by emission index yields.  Rounds
 // with more points than the group can hold are evaluated in consecutive passes, in order.
 //
-// GS = 32: one warp per job (large PUs: the lanes of a point split its rows).
-// GS = 8 : four jobs per warp (PUs up to 128 visited pixels): the ncu capture of round 1 showed the
-//          one-warp-per-job kernel issuing ~2500 warp instructions per job for ~30 useful
-//          VABSDIFF4 -- per-job control overhead, not arithmetic, bounds small PUs, so four
-//          independent searches share each instruction stream.  All warp primitives take the
-//          group's member mask; groups of one warp may diverge freely.
+// GS = 32: one warp per job (large PUs: the lanes of a point split its rows).  The code is written for any power-of-two group
+// size (all warp primitives take the group's member mask); only GS = 32 is instantiated -- small PUs in large batches go to the
+// one-thread-per-job kernels of me_tz_thread.cu instead.
 //
 // SAD arithmetic: 8-bit pictures use packed bytes and VABSDIFF4.U8.ACC against the PU block
 // staged in shared memory; >8-bit pictures and explicit int16 key patterns (bi-pred
@@ -65,30 +62,6 @@ __device__ __forceinline__ bool tz_window_geometry(const hmgpu_me_job& jb, const
   w.x0 = w.ox; w.x1 = w.ox + w.pitch - jb.pu_w - 4;
   w.y0 = w.oy; w.y1 = w.oy + w.rows - jb.pu_h;
   return w.x1 >= w.x0 && w.y1 >= w.y0 && w.rows > 0 && w.pitch > 0;
-}
-
-// Window of the batch kernel for small PUs (tz_search_near_kernel): candidates within TZN_RADIUS of the clipped start point, rows of
-// up to 64 bytes staged at a fixed pitch of 80 bytes (20 words: consecutive rows start 20 banks apart, so the lanes of a pass, which
-// read different rows, spread over the banks).
-#define TZN_RADIUS 10
-#define TZN_PITCH 80
-#define TZN_MAX_PU 16
-#define TZN_ROWS (TZN_MAX_PU + 2 * TZN_RADIUS)
-__device__ __forceinline__ bool tz_near_geometry(const hmgpu_me_job& jb, const RefTable& refs, TzWindow& w, int& n16)
-{
-  const int sx = tz_clip_q(jb.start_x, jb.clip_hmin, jb.clip_hmax) >> 2, sy = tz_clip_q(jb.start_y, jb.clip_vmin, jb.clip_vmax) >> 2;
-  int ax0 = jb.pu_x + sx - TZN_RADIUS, ax1 = jb.pu_x + sx + TZN_RADIUS + jb.pu_w + 4;
-  int ay0 = jb.pu_y + sy - TZN_RADIUS, ay1 = jb.pu_y + sy + TZN_RADIUS + jb.pu_h;
-  ax0 = max(ax0, -HMGPU_MARGIN); ay0 = max(ay0, -HMGPU_MARGIN);
-  ax1 = min(ax1, refs.pic_w + HMGPU_MARGIN); ay1 = min(ay1, refs.pic_h + HMGPU_MARGIN);
-  const int al0 = (ax0 + HMGPU_MARGIN) & ~15;               // rows start 64-byte aligned at x = -80
-  const int al1 = min((ax1 + HMGPU_MARGIN + 15) & ~15, al0 + 64);
-  w.ox = al0 - HMGPU_MARGIN - jb.pu_x; w.oy = ay0 - jb.pu_y;
-  w.pitch = TZN_PITCH; w.rows = ay1 - ay0;
-  n16 = (al1 - al0) >> 4;
-  w.x0 = w.ox; w.x1 = w.ox + (al1 - al0) - jb.pu_w - 4;
-  w.y0 = w.oy; w.y1 = w.oy + w.rows - jb.pu_h;
-  return w.x1 >= w.x0 && w.y1 >= w.y0 && w.rows > 0 && w.rows <= TZN_ROWS && n16 > 0;
 }
 
 struct TzBest

@@ -507,11 +507,11 @@ static int tzt_launch_one(hmgpu_ctx* ctx, cudaStream_t stream, const hmgpu_me_jo
 {
   constexpr int ITEMS = (VR * RM + 2 * TZT_R) * TZT_PITCH(WQ);
   constexpr int smem = (ITEMS | 1) * 32 * 4;
-  static bool s_attr = false;
-  if (!s_attr)
+  const uint32_t attr_bit = 1u << (2 * cls + (P2 ? 1 : 0));
+  if (!(ctx->attr_tzt & attr_bit))
   {
     HMGPU_CUDA(ctx, cudaFuncSetAttribute(tzt_search_kernel<WQ, VR, RM, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    s_attr = true;
+    ctx->attr_tzt |= attr_bit;
   }
   const int per_sm = TZT_PER_SM(WQ, VR, RM);
   const int grid = max(1, min(HMGPU_NUM_SMS * per_sm, (n_jobs + 31) / 32));
@@ -549,7 +549,7 @@ int hmgpu_launch_tz_thread(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_job
   for (int i = 0; i < HMGPU_TZ_STREAMS; i++) HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->tz_streams[i], ctx->tz_ev[HMGPU_TZ_STREAMS], 0));
   // the larger PUs (one warp per job) on side stream 0, the shapes round-robin on the others, each second pass behind its first
   // HMGPU_TZ_P2=0: no second pass, the jobs that need the refinement go to the warp-per-job kernel with the rest
-  const int s_use_p2 = getenv("HMGPU_TZ_P2") ? atoi(getenv("HMGPU_TZ_P2")) : 0;
+  const int s_use_p2 = ctx->tune.tz_p2;
   static const int order[TZT_CLASSES] = { 0, 2, 3, 7, 4, 5, 8, 1, 6, 9, 10, 11, 12, 13 };      // most jobs first
   for (int k = 0; k < TZT_CLASSES; k++)
   {

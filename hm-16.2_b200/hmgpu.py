@@ -43,7 +43,7 @@ assert PRED_JOB.itemsize == 20
 
 EXPORTS = [
     "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
-    "hmgpu_stream", "hmgpu_synchronize", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
+    "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
@@ -76,6 +76,9 @@ def lib():
     L.hmgpu_stream.argtypes = [vp]
     L.hmgpu_stream.restype = vp
     L.hmgpu_synchronize.argtypes = [vp]
+    L.hmgpu_set_option.argtypes = [vp, C.c_char_p, ci]
+    L.hmgpu_clip_bounds_ctu.argtypes = [ci, ci, ci, ci, ci, ci, vp]
+    L.hmgpu_clip_bounds_ctu.restype = None
     L.hmgpu_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.hmgpu_host_free.argtypes = [vp, vp]
     L.hmgpu_struct_sizes.argtypes = [vp]
@@ -113,10 +116,21 @@ def lib():
     return L
 
 
-def clip_bounds(pic_w, pic_h, cu_x, cu_y):
+def clip_bounds(pic_w, pic_h, cu_x, cu_y, max_cu=None):
     b = np.zeros(4, np.int16)
-    lib().hmgpu_clip_bounds(pic_w, pic_h, cu_x, cu_y, b.ctypes.data)
+    if max_cu is None:
+        lib().hmgpu_clip_bounds(pic_w, pic_h, cu_x, cu_y, b.ctypes.data)
+    else:
+        lib().hmgpu_clip_bounds_ctu(pic_w, pic_h, cu_x, cu_y, max_cu, max_cu, b.ctypes.data)
     return b
+
+
+def mv_bits(pred_x, pred_y, scale, x, y):
+    return int(lib().hmgpu_mv_bits(int(pred_x), int(pred_y), int(scale), int(x), int(y)))
+
+
+def mv_cost(ui_cost, pred_x, pred_y, scale, x, y):
+    return int(lib().hmgpu_mv_cost(int(ui_cost) & 0xffffffff, int(pred_x), int(pred_y), int(scale), int(x), int(y)))
 
 
 def search_range(bounds, pred_x, pred_y, srch_rng):
@@ -192,6 +206,10 @@ class Context:
 
     def synchronize(self):
         self._check(self.L.hmgpu_synchronize(self.h))
+
+    def set_option(self, name, value):
+        """tuning knob of this context (hmgpu_set_option): kernel mapping switches, the resident server, ..."""
+        self._check(self.L.hmgpu_set_option(self.h, name.encode(), int(value)))
 
     def ref_upload(self, slot, luma, cb=None, cr=None):
         luma = np.ascontiguousarray(luma, np.int16)

@@ -83,6 +83,19 @@ Void HmGpuHost::xInit( TComDataCU* pcCU )
   const Double t0 = xNow();
   m_picW = pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples();
   m_picH = pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples();
+  // configurations the device path does not model are refused, not silently coded differently (no CPU fallback either):
+  // weighted prediction swaps in xGetSADw / xGetHADsw (setWpScalingDistParam, TEncSearch.cpp:5790), and the 80-sample
+  // reference margin the kernels rely on is g_uiMaxCUWidth + 16 with CTUs of at most 64
+  if ( pcCU->getSlice()->getPPS()->getUseWP() || pcCU->getSlice()->getPPS()->getWPBiPred() )
+  {
+    fprintf( stderr, "[GPUME] weighted prediction (WeightedPredP / WeightedPredB) is not supported by libhmgpu\n" );
+    exit( 1 );
+  }
+  if ( g_uiMaxCUWidth > 64 || g_uiMaxCUHeight > 64 )
+  {
+    fprintf( stderr, "[GPUME] MaxCUWidth / MaxCUHeight above 64 is not supported by libhmgpu\n" );
+    exit( 1 );
+  }
   if ( m_warmThread )
   {
     std::thread* t = (std::thread*)m_warmThread;
@@ -151,7 +164,7 @@ Void HmGpuHost::xUploadOrg( TComDataCU* pcCU )
 Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
                               const TComMv& rcMvSrchRngLT, const TComMv& rcMvSrchRngRB, const TComMv& rcMvPred, const TComMv& rcMvIn,
                               Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
-                              Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut,
+                              UInt uiMotionCost, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut,
                               const TComMv* pacSelectivePred )
 {
   const Double tEnter = xNow();
@@ -172,10 +185,11 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
   j.pred_x = rcMvPred.getHor(); j.pred_y = rcMvPred.getVer();
   j.win_l = rcMvSrchRngLT.getHor(); j.win_t = rcMvSrchRngLT.getVer();
   j.win_r = rcMvSrchRngRB.getHor(); j.win_b = rcMvSrchRngRB.getVer();
-  hmgpu_clip_bounds( m_picW, m_picH, pcCU->getCUPelX(), pcCU->getCUPelY(), &j.clip_hmin );  // TComDataCU::clipMv
+  hmgpu_clip_bounds_ctu( m_picW, m_picH, pcCU->getCUPelX(), pcCU->getCUPelY(), g_uiMaxCUWidth, g_uiMaxCUHeight, &j.clip_hmin );  // TComDataCU::clipMv
   j.search_range = (int16_t)iSearchRange;
-  // m_uiCost = m_uiLambdaMotionSAD[0] = floor(65536 * sqrt(lambda)) (TComRdCost.cpp:209, TComRdCost.h:165)
-  j.ui_cost = (UInt)floor( 65536.0 * dSqrtLambda );
+  // TComRdCost::m_uiCost exactly as getMotionCost() selected it (m_uiLambdaMotionSAD[0], or [1] for transquant-bypass CUs
+  // under COST_MIXED_LOSSLESS_LOSSY_CODING; TComRdCost.h:165), recovered by the caller through getCost(UInt)
+  j.ui_cost = uiMotionCost;
   UInt flags = HMGPU_F_INTEGER | HMGPU_F_FRAC;
   if ( bFastEnc )    flags |= HMGPU_F_FEN;
   if ( bHADME )      flags |= HMGPU_F_HADME;

@@ -39,7 +39,7 @@ public:
   Void motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
                      const TComMv& rcMvSrchRngLT, const TComMv& rcMvSrchRngRB, const TComMv& rcMvPred, const TComMv& rcMvIn,
                      Bool bBi, Bool bFullSearch, Int iSearchRange, Bool bFastEnc, Bool bHADME, Bool bLossless,
-                     Double dSqrtLambda, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut,
+                     UInt uiMotionCost, const TComMv* pIntegerMv2Nx2NPred, HmGpuSearchOut& rcOut,
                      const TComMv* pacSelectivePred = 0 );   ///< FastSearch=2: m_acMvPredictors[3] (xPatternSearchFast, TEncSearch.cpp:4004-4008)
 
   /// Batching of the uni-directional searches of one PU (TEncSearch::predInterSearch, TEncSearch.cpp:3177-3257): the

@@ -55,6 +55,11 @@ uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx);
 /* the CUDA stream all work of this context is issued on (cudaStream_t as void*) */
 void* hmgpu_stream(const hmgpu_ctx* ctx);
 int  hmgpu_synchronize(hmgpu_ctx* ctx);
+/* Tuning knobs of a context (kernel mapping switches, the resident server, tracing).  Their defaults come from the environment
+ * (HMGPU_* variables, read once by hmgpu_create); nothing on a launch path reads the environment.  Names: tz_thread,
+ * tz_thread_min, tz_merge, tz_carve, tz_p2, frac_v1, frac_overlap, pipe_chunk, pipeline, fastpath, server, server_idle_us,
+ * trace, server_stats.  Every setting produces the same results (tests/test_gpu_parity.py switches them). */
+int  hmgpu_set_option(hmgpu_ctx* ctx, const char* name, int value);
 /* Page-locked host memory.  Buffers passed to hmgpu_me_search / hmgpu_ref_upload / hmgpu_org_upload that
  * come from here (or from the caller's own cudaHostAlloc) are copied directly, without the library's
  * internal staging copy. */
@@ -123,7 +128,8 @@ enum { HMGPU_KIND_DEFAULT = 0, HMGPU_KIND_SELECTIVE = 1 };
 typedef struct hmgpu_me_job
 {
   int16_t  pu_x, pu_y;            /* PU origin, luma samples, picture coordinates */
-  uint8_t  pu_w, pu_h;            /* 4..64 */
+  uint8_t  pu_w, pu_h;            /* multiples of 4 in 4..64 with at most 64 SATD tiles (8x8 tiles iff both are multiples of 8,
+                                     else 4x4): every HEVC PU shape; e.g. 36x32 is rejected */
   uint8_t  ref_slot;
   uint8_t  flags;                 /* HMGPU_F_* */
   int16_t  pred_x, pred_y;        /* m_mvPredictor (quarter-pel), TComRdCost::setPredictor */
@@ -169,7 +175,8 @@ int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs,
 /* Host-side helpers with the reference's exact arithmetic (cheap, scalar):
  * TComDataCU::clipMv bounds (TComDataCU.cpp:2917-2929) and xSetSearchRange
  * (TEncSearch.cpp:3911-3927). */
-void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4]);
+void hmgpu_clip_bounds(int pic_w, int pic_h, int cu_x, int cu_y, int16_t bounds[4]);   /* g_uiMaxCUWidth = Height = 64 */
+void hmgpu_clip_bounds_ctu(int pic_w, int pic_h, int cu_x, int cu_y, int max_cu_w, int max_cu_h, int16_t bounds[4]);
 void hmgpu_search_range(const int16_t bounds[4], int pred_x, int pred_y, int srch_rng, int16_t ltrb[4]);
 
 /* ------------------------------------------------------------------------------------------

@@ -274,9 +274,26 @@ def test_errors_are_reported_not_thrown():
         bad["pu_w"][0] = 5
         with pytest.raises(hmgpu.HmGpuError, match="unsupported"):
             ctx.me_search(bad)
+        # shapes with more than 64 SATD tiles (not HEVC PU shapes) would overflow the (job, tile) packing of the
+        # fractional stage: refused on the small-batch path and by the device-side scan of the pipelined path alike
+        for w_, h_ in ((36, 32), (60, 64), (64, 60), (44, 28)):
+            bad = jobs.copy()
+            bad["pu_x"][1], bad["pu_y"][1], bad["pu_w"][1], bad["pu_h"][1] = 0, 0, w_, h_
+            with pytest.raises(hmgpu.HmGpuError, match="job 1: PU %dx%d unsupported" % (w_, h_)):
+                ctx.me_search(bad)
+        big = np.tile(jobs, 20000)
+        big["pu_x"][70001], big["pu_y"][70001], big["pu_w"][70001], big["pu_h"][70001] = 0, 0, 36, 32
+        with pytest.raises(hmgpu.HmGpuError, match="job 70001: PU size unsupported"):
+            ctx.me_search(big)
+        # a negative element count of the key-pattern array is an argument error, not a huge memcpy
+        blk = np.zeros(64, np.int16)
+        rc = ctx.L.hmgpu_me_search(ctx.h, jobs.ctypes.data, len(jobs), blk.ctypes.data, -5, np.zeros(len(jobs), hmgpu.ME_RESULT).ctypes.data)
+        assert rc == -1 and b"negative" in ctx.L.hmgpu_last_error(ctx.h)
         assert len(ctx.me_search(jobs[:0])) == 0
     with pytest.raises(hmgpu.HmGpuError):
         hmgpu.Context(W + 1, H, 8, 2)
+    with pytest.raises(hmgpu.HmGpuError, match="int16"):
+        hmgpu.Context(8188, 64, 8, 1)      # (w + 7) * 4 would not fit the int16 quarter-pel clip bounds
 
 
 def test_full_size_1080p_properties():
@@ -305,12 +322,9 @@ def test_full_size_1080p_properties():
         r2 = ctx.me_search(jobs)
         assert r.tobytes() == r2.tobytes()
         # 4) the chunked two-lane pipeline (large batches) and the single-shot path give the same bytes
-        import os
-        os.environ["HMGPU_NO_PIPELINE"] = "1"
-        try:
-            r3 = ctx.me_search(jobs)
-        finally:
-            del os.environ["HMGPU_NO_PIPELINE"]
+        ctx.set_option("pipeline", 0)
+        r3 = ctx.me_search(jobs)
+        ctx.set_option("pipeline", 1)
         assert r.tobytes() == r3.tobytes()
 
 
@@ -452,15 +466,13 @@ def test_selective_search(bit_depth, path):
 
 @pytest.mark.parametrize("noise", [False, True])
 @pytest.mark.parametrize("p2", ["0", "1"])
-def test_tz_thread_per_job_kernels(noise, p2, monkeypatch):
+def test_tz_thread_per_job_kernels(noise, p2):
     """The one-thread-per-job TZ kernels (me_tz_thread.cu: per-shape launches, per-job windows in shared memory, hand-over of
     refinement / raster / far-start jobs to the warp-per-job kernel or, with HMGPU_TZ_P2=1, to their second pass) against the
     oracle, forced onto a batch far below the size from which the library picks them.  The job mix stresses what decides their
     control flow: 2Nx2N integer MVs next to and far from the predictor, predictors at the picture edge (windows touching the
     padded border are handed over), small search ranges (rings cut short), FEN on and off (without it the tall shapes go to
     the warp-per-job kernel), every PU shape."""
-    monkeypatch.setenv("HMGPU_TZ_THREAD_MIN", "1")
-    monkeypatch.setenv("HMGPU_TZ_P2", p2)
     rng = np.random.default_rng(77)
     fr = _frames(8, 4, noise)
     org = fr[3]
@@ -482,14 +494,16 @@ def test_tz_thread_per_job_kernels(noise, p2, monkeypatch):
         for k in range(3):
             ctx.ref_upload(k, fr[k])
         ctx.org_upload(org)
+        ctx.set_option("tz_thread_min", 1)
+        ctx.set_option("tz_p2", int(p2))
         got = ctx.me_search(jobs)
         assert_results_equal(got, exp, jobs)
         # the warp-per-job mapping gives the same bytes
-        monkeypatch.setenv("HMGPU_TZ_SPLIT", "0")
+        ctx.set_option("tz_thread", 0)
         got0 = ctx.me_search(jobs)
         assert got.tobytes() == got0.tobytes()
         # ... and so does the warp-per-job kernel without its merged passes (hand-over jobs resume in it either way)
-        monkeypatch.setenv("HMGPU_TZ_MERGE", "0")
+        ctx.set_option("tz_merge", 0)
         assert ctx.me_search(jobs).tobytes() == got.tobytes()
-        monkeypatch.setenv("HMGPU_TZ_SPLIT", "5")
+        ctx.set_option("tz_thread", 1)
         assert ctx.me_search(jobs).tobytes() == got.tobytes()
