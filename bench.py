@@ -228,6 +228,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     assert len(res_h) == n_jobs
 
+    int_peak = ctx.microbench(0) if rank == 0 else None
+    sad4_peak = ctx.microbench(1) if rank == 0 else None
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     c = torch.tensor([float(cand_per_step)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -236,7 +238,8 @@ def run_ours(args, rank, world, local_rank):
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     total_cand = float(c[0])
 
-    seg = None if args.no_encode else encode_segment_leg(rank, world, local_rank, dist)
+    ctx.close()                                            # the encode legs run through broker daemons: free this rank's context first
+    seg = None if args.no_encode else encode_segment_leg(rank, world, local_rank, dist, args.full)
 
     if rank == 0:
         value = total_cand * args.steps / (dev_ms * 1e-3) / 1e9
@@ -245,8 +248,6 @@ def run_ours(args, rank, world, local_rank):
         work = algorithmic_work(jobs, res)
         stage_ms = {k: v[0] / args.steps for k, v in prof.items() if v[1]}
         dom = max((k for k in stage_ms if k in work), key=lambda k: stage_ms[k])
-        int_peak = ctx.microbench(0)
-        sad4_peak = ctx.microbench(1)
         ops, byts = work[dom]
         dur = stage_ms[dom] * 1e-3
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -292,10 +293,9 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_full_search:
             out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak, int_peak)
         if world == 1 and not args.no_encode:
-            out["encode"] = encode_runs()
-            out["encode_shared_gpu"] = encode_shared_gpu_leg(local_rank)
+            out["encode"] = encode_runs(local_rank, args.full)
+            out["encode_shared_gpu"] = encode_shared_gpu_leg(local_rank, args.full)
         print(json.dumps(out))
-    ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -352,114 +352,166 @@ def full_search_leg(local_rank, steps, sad4_peak, int_peak=None):
                                     "peak_source": "hmgpu_microbench(1) measured in this run"}}}
 
 
-def encode_runs():
-    """whole-encoder numbers (BASELINE.json: encode fps, bitstream MD5-identical): the HM encoder with
-    GPUME=1 beside the unmodified CPU encoder on bounded clips.  Uses the CPU reference encoder
-    (oracle/_ref) as the baseline leg only."""
+def _enc():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import encode_compare
-    if not encode_compare.available():
-        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
-    runs = {}
-    for name, a in (("cfg1_lowdelay_P_fullsearch_SR64_416x240_3f", ("lowdelay_P_main", "416x240", 3, 32, 1, ["--FastSearch=0", "--SearchRange=64"])),
-                    ("cfg2_lowdelay_P_TZ_1920x1080_4f", ("lowdelay_P_main", "1920x1080", 4, 32, 1, []))):
-        try:
-            r = encode_compare.compare(*a)
-            runs[name] = {"cpu_fps": r["cpu"]["fps"], "gpu_fps": r["gpu"]["fps"], "cpu_s": r["cpu"]["wall_s"], "gpu_s": r["gpu"]["wall_s"],
-                          "bitstream_md5_identical": r["bitstream_identical"], "recon_md5_identical": r["recon_identical"],
-                          "gpume": r["gpu"]["gpume"]}
-        except SystemExit as e:
-            runs[name] = {"error": str(e)}
-    return runs
+    return encode_compare if encode_compare.available() else None
 
 
-def encode_segment_leg(rank, world, local_rank, dist):
-    """Multi-GPU encode throughput over the natural shard: every rank encodes ITS OWN closed intra-period
-    segment (encoder_randomaccess_main.cfg, --DecodingRefreshType=2, one 16-frame IDR period, 416x240) with GPUME=1 on its
-    GPU; no exchange step.  fps = all frames / slowest rank.  Rank 0 also encodes its segment with the unmodified CPU
-    encoder (baseline leg) and compares the MD5s."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import encode_compare
-    import torch
-    if not encode_compare.available():
-        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
-    import synth
-    import tempfile
-    w, h, n = 416, 240, 16
-    tmp = tempfile.mkdtemp(prefix="hmseg_")
-    yuv = synth.write_yuv(os.path.join(tmp, "seg.yuv"), w, h, n, 8, seed=1234 + rank)
-    cfg = os.path.join(encode_compare.CFG_DIR, "encoder_randomaccess_main.cfg")
-    extra = ["--DecodingRefreshType=2", "--IntraPeriod=16"]
-    env = dict(os.environ, HMGPU_DEVICE=str(local_rank))
-    if dist is not None:
-        dist.barrier()
-    g = encode_compare.run(encode_compare.GPU_ENC, cfg, yuv, w, h, n, 32, os.path.join(tmp, "gpu"), extra + ["--GPUME=1"], env=env)
-    t = torch.tensor([g["wall_s"]], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out = None
-    if rank == 0:
-        c = encode_compare.run(encode_compare.REF_ENC, cfg, yuv, w, h, n, 32, os.path.join(tmp, "cpu"), extra)
-        out = {"workload": "encoder_randomaccess_main.cfg --DecodingRefreshType=2 --IntraPeriod=16, 416x240, one 16-frame closed segment per GPU",
-               "segments": world, "frames": world * n, "gpu_fps_total": world * n / float(t[0]), "slowest_rank_s": float(t[0]),
-               "cpu_fps_one_process": n / c["wall_s"], "cpu_s": c["wall_s"],
-               "bitstream_md5_identical": c["bitstream_md5"] == g["bitstream_md5"], "recon_md5_identical": c["recon_md5"] == g["recon_md5"],
-               "gpume": g["gpume"]}
-    import shutil
-    shutil.rmtree(tmp, ignore_errors=True)
-    return out
-
-
-def encode_shared_gpu_leg(local_rank, n_procs=4):
-    """Several encoder instances on ONE GPU (under CUDA MPS), beside the same number of CPU HM processes on the host cores:
-    n_procs closed 16-frame segments (encoder_randomaccess_main.cfg, 416x240), one process per segment, all at once."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import encode_compare
-    if not encode_compare.available():
+def encode_runs(local_rank, full=False):
+    """whole-encoder numbers (BASELINE.json: encode fps, bitstream MD5-identical): ONE HM encoder with GPUME=1, attached to the
+    per-GPU broker daemon, beside the unmodified CPU encoder (oracle/_ref, baseline leg only) on the same clip; the two run side
+    by side on different host cores.  Default: bounded clips; --full: BASELINE cfg 2 at its stated size (32 frames, QP 27/32/37)."""
+    ec = _enc()
+    if ec is None:
         return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
     import segments
     import synth
     import tempfile
     from concurrent.futures import ThreadPoolExecutor
-    w, h, n = 416, 240, 16
+    cases = [("cfg1_lowdelay_P_fullsearch_SR64_416x240_3f", "lowdelay_P_main", 416, 240, 3, 32, ["--FastSearch=0", "--SearchRange=64"]),
+             ("cfg2_lowdelay_P_TZ_1920x1080_4f_qp32", "lowdelay_P_main", 1920, 1080, 4, 32, [])]
+    if full:
+        cases = [("cfg2_lowdelay_P_TZ_1920x1080_32f_qp%d" % qp, "lowdelay_P_main", 1920, 1080, 32, qp, []) for qp in (27, 32, 37)]
+    runs = {}
+    tmp = tempfile.mkdtemp(prefix="hmenc_")
+    with segments.BrokerDaemon(device=local_rank) as brk:
+        env = dict(brk.env, HMGPU_SERVER_STATS="1")
+
+        def one(case):
+            name, cfg_name, w, h, n, qp, extra = case
+            cfg = os.path.join(ec.CFG_DIR, "encoder_%s.cfg" % cfg_name)
+            yuv = os.path.join(tmp, "in_%dx%d_%d.yuv" % (w, h, n))
+            with ThreadPoolExecutor(2) as pool:
+                fc = pool.submit(ec.run, ec.REF_ENC, cfg, yuv, w, h, n, qp, os.path.join(tmp, name + "_cpu"), extra)
+                fg = pool.submit(ec.run, ec.GPU_ENC, cfg, yuv, w, h, n, qp, os.path.join(tmp, name + "_gpu"), extra + ["--GPUME=1"], 8, env)
+                c, g = fc.result(), fg.result()
+            return name, {"cpu_fps": n / c["wall_s"], "gpu_fps": n / g["wall_s"], "cpu_s": c["wall_s"], "gpu_s": g["wall_s"],
+                          "speedup": c["wall_s"] / g["wall_s"],
+                          "bitstream_md5_identical": c["bitstream_md5"] == g["bitstream_md5"],
+                          "recon_md5_identical": c["recon_md5"] == g["recon_md5"], "gpume": g["gpume"]}
+        for w, h, n in sorted({(c[2], c[3], c[4]) for c in cases}):
+            synth.write_yuv(os.path.join(tmp, "in_%dx%d_%d.yuv" % (w, h, n)), w, h, n, 8)
+        try:
+            if full:                                          # the three QPs side by side (6 processes, 6 host cores)
+                with ThreadPoolExecutor(len(cases)) as pool:
+                    for name, r in pool.map(one, cases):
+                        runs[name] = r
+            else:
+                for case in cases:
+                    name, r = one(case)
+                    runs[name] = r
+        except SystemExit as e:
+            runs["error"] = str(e)
+        runs["broker"] = {"banner": brk.banner, "startup_s": brk.startup_s}
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return runs
+
+
+def encode_segment_leg(rank, world, local_rank, dist, full=False):
+    """Multi-GPU encode throughput over the natural shard (BASELINE cfg 4): closed intra-period segments of
+    encoder_randomaccess_main.cfg (--DecodingRefreshType=2) at 1920x1080, S = host cores / 8 segments per GPU (so that 8 GPUs
+    use every host core: each encoder needs a core for its serial part), one encoder process per segment, all processes of a
+    GPU attached to that GPU's broker daemon.  No exchange step.  fps = all frames / slowest rank.  Beside it the unmodified CPU
+    encoder over the SAME segments with the same number of processes (at N = 8: all host cores).  MD5 compared per segment.
+    Default: 8-frame segments (IntraPeriod 8: one I + one hierarchical-B GOP); --full: 32-frame segments (cfg 4's size)."""
+    ec = _enc()
+    import torch
+    if ec is None:
+        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
+    import segments
+    import synth
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    w, h = 1920, 1080
+    n = 32 if full else 8
+    cores = os.cpu_count() or 8
+    per_gpu = max(1, cores // 8)
+    tmp = tempfile.mkdtemp(prefix="hmseg_")
+    cfg = os.path.join(ec.CFG_DIR, "encoder_randomaccess_main.cfg")
+    extra = ["--DecodingRefreshType=2", "--IntraPeriod=%d" % n]
+    yuvs = [synth.write_yuv(os.path.join(tmp, "seg%d.yuv" % k), w, h, n, 8, seed=1234 + rank * per_gpu + k) for k in range(per_gpu)]
+
+    def many(enc, tag, more, env):
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(per_gpu) as pool:
+            outs = list(pool.map(lambda k: ec.run(enc, cfg, yuvs[k], w, h, n, 32, os.path.join(tmp, "%s%d" % (tag, k)), extra + more, 8, env), range(per_gpu)))
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), outs
+
+    with segments.BrokerDaemon(device=local_rank) as brk:
+        g_s, g = many(ec.GPU_ENC, "g", ["--GPUME=1"], brk.env)
+        startup = brk.startup_s
+    c_s, c = many(ec.REF_ENC, "c", [], None)
+    same = torch.tensor([int(all(a["bitstream_md5"] == b["bitstream_md5"] and a["recon_md5"] == b["recon_md5"] for a, b in zip(g, c)))], device="cuda")
+    if dist is not None:
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out = None
+    if rank == 0:
+        frames = world * per_gpu * n
+        out = {"workload": "encoder_randomaccess_main.cfg --DecodingRefreshType=2 --IntraPeriod=%d, 1920x1080 QP32, %d closed %d-frame segment(s) "
+                           "per GPU, one encoder process per segment, attached to the GPU's broker daemon" % (n, per_gpu, n),
+               "segments": world * per_gpu, "frames": frames, "host_cores": cores, "encoder_processes": world * per_gpu,
+               "gpu_fps_total": frames / g_s, "slowest_rank_s": g_s,
+               "cpu_fps_total_same_processes": frames / c_s, "cpu_s": c_s, "gpu_over_cpu": c_s / g_s,
+               "all_md5_identical": bool(int(same[0])), "broker_startup_s_not_timed": startup, "gpume_rank0": g[0]["gpume"]}
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+def encode_shared_gpu_leg(local_rank, full=False):
+    """Several encoder instances on ONE GPU through the broker daemon, beside the same number of CPU HM processes: one process
+    per host core, each coding its own closed segment (encoder_randomaccess_main.cfg, --DecodingRefreshType=2), all started
+    together.  Default: 832x480, 16-frame segments; --full: 1920x1080, 32-frame segments (cfg 4)."""
+    ec = _enc()
+    if ec is None:
+        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
+    import re
+    import segments
+    import synth
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    w, h, n = (1920, 1080, 32) if full else (832, 480, 16)
+    n_procs = os.cpu_count() or 8
     tmp = tempfile.mkdtemp(prefix="hmshare_")
-    cfg = os.path.join(encode_compare.CFG_DIR, "encoder_randomaccess_main.cfg")
-    extra = ["--DecodingRefreshType=2", "--IntraPeriod=16"]
+    cfg = os.path.join(ec.CFG_DIR, "encoder_randomaccess_main.cfg")
+    extra = ["--DecodingRefreshType=2", "--IntraPeriod=%d" % n]
     yuvs = [synth.write_yuv(os.path.join(tmp, "s%d.yuv" % k), w, h, n, 8, seed=4321 + k) for k in range(n_procs)]
 
     def many(enc, tag, more, env):
         t0 = time.perf_counter()
         with ThreadPoolExecutor(n_procs) as pool:
-            outs = list(pool.map(lambda k: encode_compare.run(enc, cfg, yuvs[k], w, h, n, 32, os.path.join(tmp, "%s%d" % (tag, k)),
-                                                              extra + more, env=env), range(n_procs)))
+            outs = list(pool.map(lambda k: ec.run(enc, cfg, yuvs[k], w, h, n, 32, os.path.join(tmp, "%s%d" % (tag, k)),
+                                                  extra + more, 8, env), range(n_procs)))
         return time.perf_counter() - t0, outs
 
-    with segments.MpsDaemon() as mps:
-        env = dict(mps.env, HMGPU_DEVICE=str(local_rank))
-        mps_ok = mps.ok
-        if not mps_ok:
-            # without MPS the processes time-slice the GPU (5x slower each): keep the leg short and say so
-            n_procs = min(n_procs, 2)
-            yuvs = yuvs[:n_procs]
-        g_s, g = many(encode_compare.GPU_ENC, "g", ["--GPUME=1"], env)
-    c_s, c = many(encode_compare.REF_ENC, "c", [], None)
+    with segments.BrokerDaemon(device=local_rank) as brk:
+        g_s, g = many(ec.GPU_ENC, "g", ["--GPUME=1"], dict(brk.env, HMGPU_SERVER_STATS="1"))
+        startup = brk.startup_s
+    c_s, c = many(ec.REF_ENC, "c", [], None)
     same = all(a["bitstream_md5"] == b["bitstream_md5"] and a["recon_md5"] == b["recon_md5"] for a, b in zip(g, c))
-    import re
-    setup = [float(m.group(1)) for o in g for m in [re.search(r"([0-9.]+) s waiting for the one-time CUDA set-up", " ".join(o["gpume"]))] if m]
+    attach = [float(m.group(1)) for o in g for m in [re.search(r"([0-9.]+) s waiting for the one-time", " ".join(o["gpume"]))] if m]
     search = [float(m.group(1)) for o in g for m in [re.search(r"([0-9.]+) s in motionSearch overall", " ".join(o["gpume"]))] if m]
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
-    return {"workload": "%d encoder processes, one closed 16-frame segment each (randomaccess_main, 416x240), started together" % n_procs,
-            "mps": mps_ok, "host_cores": os.cpu_count(), "gpu_procs_on_one_gpu_fps_total": n_procs * n / g_s, "gpu_s": g_s,
-            "cpu_procs_fps_total": n_procs * n / c_s, "cpu_s": c_s, "all_md5_identical": same,
-            "gpu_proc_cuda_setup_s_mean": float(np.mean(setup)) if setup else None,
-            "gpu_proc_binding_s_mean_incl_setup": float(np.mean(search)) if search else None}
+    return {"workload": "%d encoder processes (= host cores) on ONE GPU through the broker daemon, one closed %d-frame segment each "
+                        "(randomaccess_main, %dx%d, QP32), started together; CPU arm: the same %d segments on the same cores" % (n_procs, n, w, h, n_procs),
+            "host_cores": os.cpu_count(), "encoder_processes": n_procs, "gpu_procs_on_one_gpu_fps_total": n_procs * n / g_s, "gpu_s": g_s,
+            "cpu_procs_fps_total": n_procs * n / c_s, "cpu_s": c_s, "gpu_over_cpu": c_s / g_s, "all_md5_identical": same,
+            "broker_startup_s_not_timed": startup, "gpu_proc_attach_s_mean": float(np.mean(attach)) if attach else None,
+            "gpu_proc_binding_s_mean": float(np.mean(search)) if search else None, "gpume_proc0": g[0]["gpume"]}
 
 
 # ---- the reference on the host cores ------------------------------------------------------------
 
 def _cpu_worker(a):
-    kind, jobs_bytes, n, frames, bit_depth = a
+    kind, jobs_bytes, n, frames, bit_depth, want_count = a
     import hmgpu
     from oracle import binding as B
 
@@ -475,12 +527,14 @@ def _cpu_worker(a):
     t0 = time.perf_counter()
     _, cpu_s = B.me_batch(fn, jobs, pads, frames[N_REFS + 1], bit_depth)
     wall = time.perf_counter() - t0
-    cnt, _ = B.me_batch(B.oracle().hmo_me_batch, jobs, pads, frames[N_REFS + 1], bit_depth)   # untimed: candidate count
-    cand = int(cnt.view(hmgpu.ME_RESULT)["n_cand"].astype(np.int64).sum())
+    cand = None
+    if want_count:                                           # untimed: the candidate count (the reference does not count them)
+        cnt, _ = B.me_batch(B.oracle().hmo_me_batch, jobs, pads, frames[N_REFS + 1], bit_depth)
+        cand = int(cnt.view(hmgpu.ME_RESULT)["n_cand"].astype(np.int64).sum())
     return cpu_s, wall, cand
 
 
-def cpu_reference_run(jobs, frames, sample_jobs, procs):
+def cpu_reference_run(jobs, frames, sample_jobs, procs, cand_known=None):
     """time the reference's xTZSearch + xPatternSearchFracDIF on a bounded, evenly spaced sample
     of the step's job list, `procs` processes (the reference is single-threaded per process)."""
     from oracle import binding as B
@@ -490,7 +544,7 @@ def cpu_reference_run(jobs, frames, sample_jobs, procs):
     # dealt round-robin: the job list is ordered by CU depth (64x64 PUs first, 8x4 / 4x8 last), so contiguous chunks would give
     # the first worker several times the work of the last and the wall clock (max over workers) would flatter the GPU
     chunks = [sample[k::procs] for k in range(procs)]
-    argsl = [(kind, np.ascontiguousarray(c).tobytes(), len(c), frames, BIT_DEPTH) for c in chunks if len(c)]
+    argsl = [(kind, np.ascontiguousarray(c).tobytes(), len(c), frames, BIT_DEPTH, cand_known is None) for c in chunks if len(c)]
     t0 = time.perf_counter()
     if procs == 1:
         outs = [_cpu_worker(argsl[0])]
@@ -499,8 +553,8 @@ def cpu_reference_run(jobs, frames, sample_jobs, procs):
         with mp.get_context("fork").Pool(procs) as pool:
             outs = pool.map(_cpu_worker, argsl)
     wall = max(o[1] for o in outs)
-    cand = sum(o[2] for o in outs)
-    return {"value": cand / wall / 1e9, "unit": UNIT, "cores": procs, "kind": kind,
+    cand = cand_known if cand_known is not None else sum(o[2] for o in outs)
+    return {"value": cand / wall / 1e9, "candidates": cand, "unit": UNIT, "cores": procs, "kind": kind,
             "sample": "%d of %d jobs of one step (every %dth), %s xTZSearch+xPatternSearchFracDIF, %.1f s wall"
                       % (len(sample), len(jobs), stride, "libhmref.so" if kind == "reference" else "oracle/hm_oracle.c", wall),
             "jobs_per_s": len(sample) / wall, "seconds": wall, "total_s_incl_setup": time.perf_counter() - t0}
@@ -516,8 +570,10 @@ def run_reference(args, rank, world):
                                ref_dist=[N_REFS + 1 - k for k in range(N_REFS)])
     procs = os.cpu_count() or 1
     vals = []
+    cand = None
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=procs)
+        r = cpu_reference_run(jobs, frames, sample_jobs=args.cpu_sample, procs=procs, cand_known=cand)
+        cand = r["candidates"]                               # counted once (an untimed oracle pass), the same for every step
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
@@ -543,6 +599,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the whole-encoder CPU vs GPUME runs")
     ap.add_argument("--no-full-search", action="store_true", help="skip the full-search (BASELINE configs[0]) leg")
+    ap.add_argument("--full", action="store_true", help="encode legs at BASELINE size (cfg 2: 32 frames at QP 27/32/37; cfg 4: 32-frame "
+                                                        "1080p segments) -- tens of minutes; logs of such runs are under profiles/")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -6,6 +6,9 @@
 #include <stdlib.h>
 #include <time.h>
 #include <new>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 int hmgpu_launch_chroma(hmgpu_ctx* ctx, int16_t* d_dst, const int16_t* d_src, int src_stride);
 int hmgpu_launch_tz(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
@@ -24,15 +27,6 @@ int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, co
 int hmgpu_launch_server(hmgpu_ctx* ctx, cudaStream_t stream, const uint32_t* d_lines, const int16_t* d_org_blocks, HmgpuMailSlot* d_slots,
                         uint32_t* d_exited, uint32_t gen, uint32_t last_ticket, unsigned long long idle_ns, int n_ctas, int dyn_bytes);
 
-struct Mailbox
-{
-  HmgpuMailSlot   slots[MAIL_JOBS];
-  uint32_t        lines[HMGPU_SERVER_CTAS][16];   // host -> server: job (12 words), ticket, generation, flags, check
-  uint32_t        exited[HMGPU_SERVER_CTAS];      // server -> host: generation of the server CTA that stopped polling
-  unsigned long long trace[8];          // HMGPU_TRACE: globaltimer stamps of the kernel phases
-  int16_t         org_blocks[MAIL_JOBS * 64 * 64];
-};
-
 // HMGPU_TRACE=1: where the time of a low-latency call goes (host clock around the launch / the poll, device
 // globaltimer inside the kernel); printed by hmgpu_destroy
 struct TraceAcc { double host_prep, host_launch, host_wait, host_copy, dev[5]; unsigned long long n; };
@@ -40,6 +34,9 @@ static TraceAcc g_trace;
 static double now_us() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
 
 extern "C" { static int hmgpu_server_stop(hmgpu_ctx* ctx); }
+extern "C" { static void server_write_lines(const hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, const hmgpu_pred_job* pjobs,
+                               const uint8_t* pfuncs, int n_pred, uint32_t ticket, uint32_t gen); }
+extern "C" { static int hmgpu_server_launch(hmgpu_ctx* ctx, uint32_t gen, uint32_t last_ticket, int dyn_bytes); }
 
 static char g_create_err[512] = "";
 
@@ -53,6 +50,63 @@ int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...)
 }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- allocation pool (broker daemon) ------------------------------------------------------------------------------------
+// cudaFree / cudaFreeHost synchronise the device: with the resident server kernels of other clients spinning they would not
+// return before every one of them has gone idle.  In pool mode freed blocks are therefore parked and handed to the next request
+// they fit (a daemon serves encoders of a few picture formats over and over, so the sizes repeat).
+struct PoolState
+{
+  std::mutex mu;
+  bool on = false;
+  std::unordered_map<void*, size_t> size[2];               // live + parked blocks -> bytes; [0] device, [1] pinned host
+  std::vector<std::pair<void*, size_t> > parked[2];
+};
+static PoolState& pool() { static PoolState* p = new PoolState; return *p; }
+
+static cudaError_t pool_alloc(int kind, void** out, size_t bytes)
+{
+  PoolState& P = pool();
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    if (P.on)
+    {
+      int best = -1;
+      for (size_t i = 0; i < P.parked[kind].size(); i++)
+      {
+        const size_t b = P.parked[kind][i].second;
+        if (b >= bytes && b <= bytes + bytes / 2 + 4096 && (best < 0 || b < P.parked[kind][best].second)) best = (int)i;
+      }
+      if (best >= 0)
+      {
+        *out = P.parked[kind][best].first;
+        P.parked[kind].erase(P.parked[kind].begin() + best);
+        return cudaSuccess;
+      }
+    }
+  }
+  const cudaError_t e = kind == 0 ? cudaMalloc(out, bytes) : cudaMallocHost(out, bytes);
+  if (e == cudaSuccess) { std::lock_guard<std::mutex> g(P.mu); if (P.on) P.size[kind][*out] = bytes; }
+  return e;
+}
+
+static void pool_free(int kind, void* p)
+{
+  if (!p) return;
+  PoolState& P = pool();
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    auto it = P.size[kind].find(p);
+    if (P.on && it != P.size[kind].end()) { P.parked[kind].push_back(std::make_pair(p, it->second)); return; }
+    if (it != P.size[kind].end()) P.size[kind].erase(it);
+  }
+  if (kind == 0) cudaFree(p); else cudaFreeHost(p);
+}
+
+cudaError_t hmgpu_dmalloc(void** p, size_t bytes) { return pool_alloc(0, p, bytes); }
+void hmgpu_dfree(void* p) { pool_free(0, p); }
+cudaError_t hmgpu_hmalloc(void** p, size_t bytes) { return pool_alloc(1, p, bytes); }
+void hmgpu_hfree(void* p) { pool_free(1, p); }
 
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
@@ -94,10 +148,10 @@ static bool is_pinned(const void* p)
 int hmgpu_reserve_pinned(hmgpu_ctx* ctx, size_t bytes)
 {
   if (bytes <= ctx->h_pin_bytes) return HMGPU_OK;
-  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_pin) hmgpu_hfree(ctx->h_pin);
   ctx->h_pin = NULL; ctx->h_pin_bytes = 0;
   bytes = round_up(bytes + bytes / 4, 1 << 20);
-  HMGPU_CUDA(ctx, cudaMallocHost(&ctx->h_pin, bytes));
+  HMGPU_CUDA(ctx, hmgpu_hmalloc((void**)&ctx->h_pin, bytes));
   ctx->h_pin_bytes = bytes;
   return HMGPU_OK;
 }
@@ -106,10 +160,10 @@ int hmgpu_reserve_stage(hmgpu_ctx* ctx, size_t bytes)
 {
   if (bytes <= ctx->d_stage_bytes) return HMGPU_OK;
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->d_stage) hmgpu_dfree(ctx->d_stage);
   ctx->d_stage = NULL; ctx->d_stage_bytes = 0;
   bytes = round_up(bytes + bytes / 4, 1 << 20);
-  HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_stage, bytes));
+  HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&ctx->d_stage, bytes));
   ctx->d_stage_bytes = bytes;
   return HMGPU_OK;
 }
@@ -118,10 +172,10 @@ int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes)
 {
   if (bytes <= ctx->d_work_bytes) return HMGPU_OK;
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->d_work) cudaFree(ctx->d_work);
+  if (ctx->d_work) hmgpu_dfree(ctx->d_work);
   ctx->d_work = NULL; ctx->d_work_bytes = 0;
   bytes = round_up(bytes + bytes / 4, 1 << 20);
-  HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_work, bytes));
+  HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&ctx->d_work, bytes));
   ctx->d_work_bytes = bytes;
   return HMGPU_OK;
 }
@@ -130,10 +184,10 @@ int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes)
 {
   if (bytes <= ctx->d_tzlist_bytes) return HMGPU_OK;
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->d_tzlist) cudaFree(ctx->d_tzlist);
+  if (ctx->d_tzlist) hmgpu_dfree(ctx->d_tzlist);
   ctx->d_tzlist = NULL; ctx->d_tzlist_bytes = 0;
   bytes = round_up(bytes + bytes / 4, 1 << 20);
-  HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_tzlist, bytes));
+  HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&ctx->d_tzlist, bytes));
   ctx->d_tzlist_bytes = bytes;
   return HMGPU_OK;
 }
@@ -185,6 +239,10 @@ int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   return HMGPU_OK;
 }
 
+// entry points a broker client does not have (test / measurement surface, device pointers): refused, never emulated
+#define HMGPU_NOT_REMOTE(ctx, what) \
+  do { if ((ctx)->remote) return hmgpu_fail((ctx), HMGPU_E_STATE, "%s is not available through the broker daemon (HMGPU_BROKER is set)", what); } while (0)
+
 extern "C" {
 
 int hmgpu_abi_version(void) { return HMGPU_ABI_VERSION; }
@@ -201,13 +259,23 @@ void hmgpu_struct_sizes(int out[5])
 
 const char* hmgpu_last_error(const hmgpu_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 
-uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t hmgpu_launch_count(const hmgpu_ctx* ctx)
+{
+  if (!ctx) return 0;
+  if (ctx->remote)
+  {
+    BrokerReply r;
+    return hmgpu_remote_call((hmgpu_ctx*)ctx, HMB_OP_LAUNCH_COUNT, NULL, NULL, &r) == HMGPU_OK ? r.v64 : 0;
+  }
+  return ctx->launches;
+}
 
-void* hmgpu_stream(const hmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : NULL; }
+void* hmgpu_stream(const hmgpu_ctx* ctx) { return ctx && !ctx->remote ? (void*)ctx->stream : NULL; }
 
 int hmgpu_host_alloc(hmgpu_ctx* ctx, size_t bytes, void** out)
 {
   if (!ctx || !out) return HMGPU_E_INVALID;
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_host_alloc");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   HMGPU_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
   return HMGPU_OK;
@@ -216,6 +284,7 @@ int hmgpu_host_alloc(hmgpu_ctx* ctx, size_t bytes, void** out)
 int hmgpu_host_free(hmgpu_ctx* ctx, void* p)
 {
   if (!ctx) return HMGPU_E_INVALID;
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_host_free");
   HMGPU_CUDA(ctx, cudaFreeHost(p));
   return HMGPU_OK;
 }
@@ -228,6 +297,8 @@ int hmgpu_set_option(hmgpu_ctx* ctx, const char* name, int value)
     {
       if (&(ctx->tune.*k_tune_names[i].field) == &ctx->tune.server && !value) { const int rc = hmgpu_server_stop(ctx); if (rc) return rc; }
       ctx->tune.*k_tune_names[i].field = value;
+      // the kernel-mapping switches of a broker client live in the daemon's context
+      if (ctx->remote) { const int32_t a[6] = { value, 0, 0, 0, 0, 0 }; return hmgpu_remote_call(ctx, HMB_OP_SET_OPTION, a, name, NULL); }
       return HMGPU_OK;
     }
   return hmgpu_fail(ctx, HMGPU_E_INVALID, "unknown option '%s'", name);
@@ -236,11 +307,64 @@ int hmgpu_set_option(hmgpu_ctx* ctx, const char* name, int value)
 int hmgpu_synchronize(hmgpu_ctx* ctx)
 {
   if (!ctx) return HMGPU_E_INVALID;
+  if (ctx->remote) return HMGPU_OK;                        // every remote operation is complete when its call returns
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HMGPU_OK;
 }
 
+static int create_local(int device, int pic_w, int pic_h, int bit_depth, int max_refs, void* ext_mail, int srv_ctas, hmgpu_ctx** out);
+
 int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, hmgpu_ctx** out)
+{
+  // HMGPU_BROKER=<socket path>: this process becomes a client of the per-GPU daemon (hmgpud) and never creates a CUDA context;
+  // `device` is then the daemon's business
+  const char* broker = getenv("HMGPU_BROKER");
+  if (broker && *broker)
+  {
+    if (!out) return hmgpu_fail(NULL, HMGPU_E_INVALID, "out is NULL");
+    *out = NULL;
+    return hmgpu_remote_create(broker, pic_w, pic_h, bit_depth, max_refs, out);
+  }
+  return create_local(device, pic_w, pic_h, bit_depth, max_refs, NULL, 0, out);
+}
+
+int hmgpu_internal_create_shared(int device, int pic_w, int pic_h, int bit_depth, int max_refs, void* mail, int srv_ctas, hmgpu_ctx** out)
+{
+  return create_local(device, pic_w, pic_h, bit_depth, max_refs, mail, srv_ctas, out);
+}
+
+void hmgpu_internal_pool_mode(int on) { std::lock_guard<std::mutex> g(pool().mu); pool().on = on != 0; }
+int  hmgpu_internal_server_launch(hmgpu_ctx* ctx, uint32_t gen, uint32_t last_ticket, int dyn_bytes)
+{
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  return hmgpu_server_launch(ctx, gen, last_ticket, dyn_bytes);
+}
+int  hmgpu_internal_server_sync(hmgpu_ctx* ctx)
+{
+  if (ctx->srv_stream) HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->srv_stream));
+  return HMGPU_OK;
+}
+int  hmgpu_internal_server_query(hmgpu_ctx* ctx)
+{
+  if (!ctx->srv_stream) return HMGPU_OK;
+  const cudaError_t e = cudaStreamQuery(ctx->srv_stream);
+  if (e != cudaErrorNotReady && e != cudaSuccess) return hmgpu_fail(ctx, HMGPU_E_CUDA, "mailbox server failed: %s", cudaGetErrorString(e));
+  return HMGPU_OK;
+}
+size_t hmgpu_internal_mailbox_bytes(void) { return sizeof(Mailbox); }
+// the daemon's last word to a client's server kernel, whatever the client's state was: a generation no kernel runs as
+int  hmgpu_internal_server_kill(hmgpu_ctx* ctx)
+{
+  if (!ctx->h_mail || !ctx->srv_stream) return HMGPU_OK;
+  const int keep = ctx->srv_ctas;
+  ctx->srv_ctas = HMGPU_SERVER_CTAS;
+  server_write_lines(ctx, (Mailbox*)ctx->h_mail, NULL, 0, NULL, NULL, 0, 0u, 0xffffffffu);
+  ctx->srv_ctas = keep;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->srv_stream));
+  return HMGPU_OK;
+}
+
+static int create_local(int device, int pic_w, int pic_h, int bit_depth, int max_refs, void* ext_mail, int srv_ctas, hmgpu_ctx** out)
 {
   if (!out) return hmgpu_fail(NULL, HMGPU_E_INVALID, "out is NULL");
   *out = NULL;
@@ -261,6 +385,8 @@ int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, 
   memset(ctx, 0, sizeof *ctx);
   ctx->device = device; ctx->pic_w = pic_w; ctx->pic_h = pic_h; ctx->bit_depth = bit_depth; ctx->max_refs = max_refs;
   tuning_from_env(&ctx->tune);
+  ctx->srv_ctas = srv_ctas > 0 ? (srv_ctas > HMGPU_SERVER_CTAS ? HMGPU_SERVER_CTAS : srv_ctas) : env_int("HMGPU_SERVER_CTAS", HMGPU_SERVER_CTAS);
+  if (ctx->srv_ctas < 1 || ctx->srv_ctas > HMGPU_SERVER_CTAS) ctx->srv_ctas = HMGPU_SERVER_CTAS;
   ctx->px_bytes = bit_depth == 8 ? 1 : 2;
   ctx->pw = pic_w + 2 * HMGPU_MARGIN; ctx->ph = pic_h + 2 * HMGPU_MARGIN;
   ctx->pitch = (int)round_up(ctx->pw + 32, 64);          // slack for aligned look-ahead loads
@@ -270,9 +396,18 @@ int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, 
   ctx->org_pitch = (int)round_up(pic_w + 32, 64);
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete ctx; return hmgpu_fail(NULL, HMGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-  e = cudaMalloc(&ctx->d_org, (size_t)ctx->org_pitch * (pic_h + 1) * ctx->px_bytes + 256);
+  e = hmgpu_dmalloc((void**)&ctx->d_org, (size_t)ctx->org_pitch * (pic_h + 1) * ctx->px_bytes + 256);
   if (e != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return hmgpu_fail(NULL, HMGPU_E_NOMEM, "cudaMalloc org: %s", cudaGetErrorString(e)); }
-  cudaMemset(ctx->d_org, 0, (size_t)ctx->org_pitch * (pic_h + 1) * ctx->px_bytes + 256);
+  cudaMemsetAsync(ctx->d_org, 0, (size_t)ctx->org_pitch * (pic_h + 1) * ctx->px_bytes + 256, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (ext_mail)
+  {
+    // the daemon's view of a client: the mailbox is part of the shared segment (already registered with CUDA)
+    ctx->h_mail = ext_mail; ctx->mail_external = true;
+    e = cudaHostGetDevicePointer(&ctx->d_mail, ext_mail, 0);
+    if (e != cudaSuccess) { hmgpu_dfree(ctx->d_org); cudaStreamDestroy(ctx->stream); delete ctx; return hmgpu_fail(NULL, HMGPU_E_CUDA, "cudaHostGetDevicePointer(mailbox): %s", cudaGetErrorString(e)); }
+    ctx->tune.fastpath = 0;                               // batches of any size go to the batch kernels: the mailbox belongs to the client
+  }
   *out = ctx;
   return HMGPU_OK;
 }
@@ -280,6 +415,15 @@ int hmgpu_create(int device, int pic_w, int pic_h, int bit_depth, int max_refs, 
 void hmgpu_destroy(hmgpu_ctx* ctx)
 {
   if (!ctx) return;
+  if (ctx->remote)
+  {
+    hmgpu_server_stop(ctx);
+    if (ctx->tune.trace || ctx->tune.server_stats)
+      fprintf(stderr, "[hmgpu server] %u calls served by %u server generations (through the broker)\n", ctx->srv_calls, ctx->srv_starts);
+    free(ctx->defer_org);
+    hmgpu_remote_destroy(ctx);
+    return;
+  }
   if (g_trace.n)
   {
     const double n = (double)g_trace.n;
@@ -298,35 +442,35 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   {
     HmgpuLane& l1 = ctx->lane_store[1];
     if (l1.stream) cudaStreamSynchronize(l1.stream);
-    if (l1.d_stage) cudaFree(l1.d_stage);
-    if (l1.d_work) cudaFree(l1.d_work);
-    if (l1.d_tzlist) cudaFree(l1.d_tzlist);
-    if (l1.h_pin) cudaFreeHost(l1.h_pin);
+    if (l1.d_stage) hmgpu_dfree(l1.d_stage);
+    if (l1.d_work) hmgpu_dfree(l1.d_work);
+    if (l1.d_tzlist) hmgpu_dfree(l1.d_tzlist);
+    if (l1.h_pin) hmgpu_hfree(l1.h_pin);
     if (l1.stream) cudaStreamDestroy(l1.stream);
     for (int i = 0; i < 2; i++) if (ctx->lane_done[i]) cudaEventDestroy(ctx->lane_done[i]);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     for (int i = 0; i < 2; i++) if (ctx->scan_done[i]) cudaEventDestroy(ctx->scan_done[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-    if (ctx->d_scan) cudaFree(ctx->d_scan);
-    if (ctx->h_scan) cudaFreeHost(ctx->h_scan);
-    if (ctx->d_orgblk) cudaFree(ctx->d_orgblk);
+    if (ctx->d_scan) hmgpu_dfree(ctx->d_scan);
+    if (ctx->h_scan) hmgpu_hfree(ctx->h_scan);
+    if (ctx->d_orgblk) hmgpu_dfree(ctx->d_orgblk);
   }
   for (int i = 0; i < HMGPU_MAX_REFS; i++)
   {
-    if (ctx->refs[i].planes) cudaFree(ctx->refs[i].planes);
-    if (ctx->refs[i].cb) cudaFree(ctx->refs[i].cb);
-    if (ctx->refs[i].cr) cudaFree(ctx->refs[i].cr);
+    if (ctx->refs[i].planes) hmgpu_dfree(ctx->refs[i].planes);
+    if (ctx->refs[i].cb) hmgpu_dfree(ctx->refs[i].cb);
+    if (ctx->refs[i].cr) hmgpu_dfree(ctx->refs[i].cr);
   }
   if (ctx->frac_stream) { cudaStreamSynchronize(ctx->frac_stream); cudaStreamDestroy(ctx->frac_stream); }
   for (int i = 0; i < 2; i++) if (ctx->frac_ev[i]) cudaEventDestroy(ctx->frac_ev[i]);
   for (int i = 0; i < HMGPU_TZ_STREAMS; i++) if (ctx->tz_streams[i]) { cudaStreamSynchronize(ctx->tz_streams[i]); cudaStreamDestroy(ctx->tz_streams[i]); }
   for (int i = 0; i <= HMGPU_TZ_STREAMS; i++) if (ctx->tz_ev[i]) cudaEventDestroy(ctx->tz_ev[i]);
-  if (ctx->d_org) cudaFree(ctx->d_org);
-  if (ctx->d_stage) cudaFree(ctx->d_stage);
-  if (ctx->d_work) cudaFree(ctx->d_work);
-  if (ctx->d_tzlist) cudaFree(ctx->d_tzlist);
-  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-  if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+  if (ctx->d_org) hmgpu_dfree(ctx->d_org);
+  if (ctx->d_stage) hmgpu_dfree(ctx->d_stage);
+  if (ctx->d_work) hmgpu_dfree(ctx->d_work);
+  if (ctx->d_tzlist) hmgpu_dfree(ctx->d_tzlist);
+  if (ctx->h_pin) hmgpu_hfree(ctx->h_pin);
+  if (ctx->h_mail && !ctx->mail_external) cudaFreeHost(ctx->h_mail);
   free(ctx->defer_org);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -338,14 +482,14 @@ static int ref_alloc(hmgpu_ctx* ctx, int slot, bool chroma)
   if (!s.planes)
   {
     const size_t bytes = ctx->plane_elems * 16 * ctx->px_bytes + 512;
-    HMGPU_CUDA(ctx, cudaMalloc(&s.planes, bytes));
+    HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&s.planes, bytes));
     HMGPU_CUDA(ctx, cudaMemsetAsync(s.planes, 0, bytes, ctx->stream));
   }
   if (chroma && !s.cb)
   {
     const size_t bytes = (size_t)ctx->cpitch * ctx->cph * sizeof(int16_t);
-    HMGPU_CUDA(ctx, cudaMalloc(&s.cb, bytes));
-    HMGPU_CUDA(ctx, cudaMalloc(&s.cr, bytes));
+    HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&s.cb, bytes));
+    HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&s.cr, bytes));
   }
   return HMGPU_OK;
 }
@@ -364,11 +508,35 @@ static int stage_plane(hmgpu_ctx* ctx, const int16_t* src, int stride, int w, in
   return HMGPU_OK;
 }
 
+// broker client: the picture travels through the upload area of the shared segment (tight rows), one round trip
+static int remote_upload(hmgpu_ctx* ctx, int op, int slot, const int16_t* luma, int luma_stride, const int16_t* cb, const int16_t* cr, int chroma_stride)
+{
+  int rc = hmgpu_server_stop(ctx);                         // the server reads the planes through the read-only path
+  if (rc) return rc;
+  size_t cap = 0;
+  int16_t* area = (int16_t*)hmgpu_remote_area(ctx, 0, &cap);
+  const size_t yel = (size_t)ctx->pic_w * ctx->pic_h, cel = (size_t)(ctx->pic_w / 2) * (ctx->pic_h / 2);
+  const bool chroma = cb && cr;
+  if ((yel + (chroma ? 2 * cel : 0)) * sizeof(int16_t) > cap) return hmgpu_fail(ctx, HMGPU_E_NOMEM, "picture does not fit the broker's upload area");
+  for (int y = 0; y < ctx->pic_h; y++) memcpy(area + (size_t)y * ctx->pic_w, luma + (size_t)y * luma_stride, sizeof(int16_t) * ctx->pic_w);
+  if (chroma)
+    for (int y = 0; y < ctx->pic_h / 2; y++)
+    {
+      memcpy(area + yel + (size_t)y * (ctx->pic_w / 2), cb + (size_t)y * chroma_stride, sizeof(int16_t) * (ctx->pic_w / 2));
+      memcpy(area + yel + cel + (size_t)y * (ctx->pic_w / 2), cr + (size_t)y * chroma_stride, sizeof(int16_t) * (ctx->pic_w / 2));
+    }
+  const int32_t a[6] = { slot, chroma ? 1 : 0, 0, 0, 0, 0 };
+  if ((rc = hmgpu_remote_call(ctx, op, a, NULL, NULL))) return rc;
+  if (op == HMB_OP_REF_UPLOAD) { ctx->refs[slot].valid = true; ctx->refs[slot].has_chroma = chroma; }
+  return HMGPU_OK;
+}
+
 int hmgpu_ref_upload(hmgpu_ctx* ctx, int slot, const int16_t* luma, int luma_stride,
                      const int16_t* cb, const int16_t* cr, int chroma_stride)
 {
   if (!ctx) return HMGPU_E_INVALID;
   if (slot < 0 || slot >= ctx->max_refs || !luma) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad slot %d or NULL luma", slot);
+  if (ctx->remote) return remote_upload(ctx, HMB_OP_REF_UPLOAD, slot, luma, luma_stride, cb, cr, chroma_stride);
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   const bool chroma = cb && cr;
@@ -399,6 +567,7 @@ int hmgpu_ref_upload_device(hmgpu_ctx* ctx, int slot, const void* d_luma, int lu
 {
   if (!ctx) return HMGPU_E_INVALID;
   if (slot < 0 || slot >= ctx->max_refs || !d_luma) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad slot %d or NULL luma", slot);
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_ref_upload_device");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   int rc = ref_alloc(ctx, slot, false);
@@ -412,6 +581,7 @@ int hmgpu_ref_upload_device(hmgpu_ctx* ctx, int slot, const void* d_luma, int lu
 int hmgpu_ref_release(hmgpu_ctx* ctx, int slot)
 {
   if (!ctx || slot < 0 || slot >= HMGPU_MAX_REFS) return HMGPU_E_INVALID;
+  if (ctx->remote) { const int32_t a[6] = { slot, 0, 0, 0, 0, 0 }; const int rc = hmgpu_remote_call(ctx, HMB_OP_REF_RELEASE, a, NULL, NULL); if (rc) return rc; }
   ctx->refs[slot].valid = false;   // memory is kept for the next picture that takes the slot
   return HMGPU_OK;
 }
@@ -419,6 +589,7 @@ int hmgpu_ref_release(hmgpu_ctx* ctx, int slot)
 int hmgpu_ref_download_plane(hmgpu_ctx* ctx, int slot, int frac_x, int frac_y, int16_t* dst)
 {
   if (!ctx || !dst) return HMGPU_E_INVALID;
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_ref_download_plane");
   if (slot < 0 || slot >= ctx->max_refs || !ctx->refs[slot].valid) return hmgpu_fail(ctx, HMGPU_E_STATE, "slot %d holds no reference", slot);
   if (frac_x < 0 || frac_x > 3 || frac_y < 0 || frac_y > 3) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad phase");
   const size_t bytes = ctx->plane_elems * ctx->px_bytes;
@@ -437,6 +608,7 @@ int hmgpu_ref_download_plane(hmgpu_ctx* ctx, int slot, int frac_x, int frac_y, i
 int hmgpu_org_upload(hmgpu_ctx* ctx, const int16_t* luma, int luma_stride)
 {
   if (!ctx || !luma) return HMGPU_E_INVALID;
+  if (ctx->remote) return remote_upload(ctx, HMB_OP_ORG_UPLOAD, 0, luma, luma_stride, NULL, NULL, 0);
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   const size_t ybytes = sizeof(int16_t) * (size_t)ctx->pic_w * ctx->pic_h;
@@ -453,6 +625,7 @@ int hmgpu_org_upload(hmgpu_ctx* ctx, const int16_t* luma, int luma_stride)
 int hmgpu_org_upload_device(hmgpu_ctx* ctx, const void* d_luma, int luma_stride)
 {
   if (!ctx || !d_luma) return HMGPU_E_INVALID;
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_org_upload_device");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   return hmgpu_launch_org(ctx, (const int16_t*)d_luma, luma_stride);
@@ -636,8 +809,8 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
       HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->scan_done[i], cudaEventDisableTiming));
     }
     HMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-    HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_scan, 2 * sizeof(ScanOut)));
-    HMGPU_CUDA(ctx, cudaMallocHost(&ctx->h_scan, 2 * sizeof(ScanOut)));
+    HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&ctx->d_scan, 2 * sizeof(ScanOut)));
+    HMGPU_CUDA(ctx, hmgpu_hmalloc((void**)&ctx->h_scan, 2 * sizeof(ScanOut)));
   }
   ScanOut* d_scan = (ScanOut*)ctx->d_scan;
   ScanOut* h_scan = (ScanOut*)ctx->h_scan;
@@ -652,9 +825,9 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
     if (ob > ctx->d_orgblk_bytes)
     {
       HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if (ctx->d_orgblk) cudaFree(ctx->d_orgblk);
+      if (ctx->d_orgblk) hmgpu_dfree(ctx->d_orgblk);
       ctx->d_orgblk = NULL; ctx->d_orgblk_bytes = 0;
-      HMGPU_CUDA(ctx, cudaMalloc(&ctx->d_orgblk, round_up(ob + ob / 4, 1 << 20)));
+      HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&ctx->d_orgblk, round_up(ob + ob / 4, 1 << 20)));
       ctx->d_orgblk_bytes = round_up(ob + ob / 4, 1 << 20);
     }
     if (is_pinned(org_blocks))
@@ -756,6 +929,9 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
 }
 
 // ---- mailbox server (host side) --------------------------------------------------------------------------
+// The same code drives the server in both deployments: in-process (this process launched me_server_kernel on its own
+// stream) and as the client of a broker daemon (ctx->remote: the daemon launched it, the mailbox is a shared-memory segment
+// both processes map; starting / draining the kernel is one socket round trip, everything else is plain memory traffic).
 static uint32_t line_check(const uint32_t* w)
 {
   uint32_t h = 0x7F4A7C15u;
@@ -763,19 +939,34 @@ static uint32_t line_check(const uint32_t* w)
   return h;
 }
 
-// (re)write all lines: jobs (or no-op lines) of call `ticket` for server generation `gen`
-static void server_write_lines(Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, uint32_t ticket, uint32_t gen)
+// One call = n_lines job lines (ME jobs first, prediction-error jobs after them).  All lines a server CTA may look at are
+// (re)written: CTA b polls line b and, once it has seen the call's ticket there, fetches lines b + srv_ctas, b + 2 srv_ctas ...
+// of the same call -- so the lines a CTA does NOT poll are written first (x86 stores become visible in order).
+static void server_write_lines(const hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, const hmgpu_pred_job* pjobs,
+                               const uint8_t* pfuncs, int n_pred, uint32_t ticket, uint32_t gen)
 {
-  for (int b = 0; b < HMGPU_SERVER_CTAS; b++)
+  const int n_lines = n_jobs + n_pred;
+  const int n_write = n_lines > ctx->srv_ctas ? n_lines : ctx->srv_ctas;
+  for (int b = n_write - 1; b >= 0; b--)
   {
     uint32_t w[16];
     memset(w, 0, sizeof w);
-    if (b < n_jobs) memcpy(w, &jobs[b], sizeof(hmgpu_me_job));
-    w[12] = ticket; w[13] = gen; w[14] = b < n_jobs ? 1u : 0u; w[15] = line_check(w);
+    uint32_t fl = (uint32_t)n_lines << 8;
+    if (b < n_jobs) { memcpy(w, &jobs[b], sizeof(hmgpu_me_job)); fl |= 1u; }
+    else if (b < n_lines) { memcpy(w, &pjobs[b - n_jobs], sizeof(hmgpu_pred_job)); fl |= 3u | ((uint32_t)pfuncs[b - n_jobs] << 16); }
+    w[12] = ticket; w[13] = gen; w[14] = fl; w[15] = line_check(w);
     volatile uint32_t* dst = mb->lines[b];
     for (int i = 0; i < 16; i++) dst[i] = w[i];
   }
   __sync_synchronize();
+}
+
+// wait until the server kernel has left its stream
+static int server_drain(hmgpu_ctx* ctx)
+{
+  if (ctx->remote) return hmgpu_remote_call(ctx, HMB_OP_SERVER_SYNC, NULL, NULL, NULL);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->srv_stream));
+  return HMGPU_OK;
 }
 
 // make the server leave (new generation in every line) and wait for it.  Called before anything that rewrites the
@@ -785,21 +976,45 @@ static int hmgpu_server_stop(hmgpu_ctx* ctx)
   if (!ctx->srv_alive) return HMGPU_OK;
   Mailbox* mb = (Mailbox*)ctx->h_mail;
   ctx->srv_gen++;
-  server_write_lines(mb, NULL, 0, ctx->mail_ticket, ctx->srv_gen);
-  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->srv_stream));
+  server_write_lines(ctx, mb, NULL, 0, NULL, NULL, 0, ctx->mail_ticket, ctx->srv_gen);
+  const int rc = server_drain(ctx);
+  if (rc) return rc;
   ctx->srv_alive = false;
   return HMGPU_OK;
 }
 
-static int server_start(hmgpu_ctx* ctx, Mailbox* mb, int dyn_bytes)
+// the mailbox of an in-process context: mapped pinned memory, allocated on first use
+static int mailbox_ensure(hmgpu_ctx* ctx)
 {
-  const int s_idle_us = ctx->tune.server_idle_us;
+  if (ctx->h_mail) return HMGPU_OK;
+  HMGPU_CUDA(ctx, cudaHostAlloc(&ctx->h_mail, sizeof(Mailbox), cudaHostAllocMapped));
+  memset(ctx->h_mail, 0, sizeof(Mailbox));
+  HMGPU_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_mail, ctx->h_mail, 0));
+  return HMGPU_OK;
+}
+
+// launch generation `gen` of the server kernel of an in-process context (also what the broker daemon runs on behalf of a client)
+static int hmgpu_server_launch(hmgpu_ctx* ctx, uint32_t gen, uint32_t last_ticket, int dyn_bytes)
+{
+  Mailbox* dm = (Mailbox*)ctx->d_mail;
+  if (!dm) return hmgpu_fail(ctx, HMGPU_E_STATE, "no mailbox");
   if (!ctx->srv_stream) HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->srv_stream, cudaStreamNonBlocking));
   // ordered after everything already queued on the context's stream (uploads are synchronous, this is belt and braces)
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return hmgpu_launch_server(ctx, ctx->srv_stream, &dm->lines[0][0], dm->org_blocks, dm->slots, dm->exited, gen, last_ticket,
+                             (unsigned long long)ctx->tune.server_idle_us * 1000ull, ctx->srv_ctas, dyn_bytes);
+}
+
+static int server_start(hmgpu_ctx* ctx, int dyn_bytes)
+{
   ctx->srv_dyn = dyn_bytes;
-  int rc = hmgpu_launch_server(ctx, ctx->srv_stream, &mb->lines[0][0], mb->org_blocks, mb->slots, mb->exited, ctx->srv_gen,
-                               ctx->mail_ticket - 1, (unsigned long long)s_idle_us * 1000ull, HMGPU_SERVER_CTAS, dyn_bytes);
+  int rc;
+  if (ctx->remote)
+  {
+    const int32_t a[6] = { (int32_t)ctx->srv_gen, (int32_t)(ctx->mail_ticket - 1), dyn_bytes, 0, 0, 0 };
+    rc = hmgpu_remote_call(ctx, HMB_OP_SERVER_START, a, NULL, NULL);
+  }
+  else rc = hmgpu_server_launch(ctx, ctx->srv_gen, ctx->mail_ticket - 1, dyn_bytes);
   if (rc) return rc;
   ctx->srv_alive = true;
   ctx->srv_starts++;
@@ -813,21 +1028,28 @@ static inline void cpu_relax()
 #endif
 }
 
-static bool slot_ready(const volatile uint32_t* slot, uint32_t ticket, hmgpu_me_result* out)
+static bool slot_ready(const volatile uint32_t* slot, uint32_t ticket, uint32_t* out6)
 {
   uint32_t w[8];
   for (int k = 0; k < 8; k++) w[k] = slot[k];
   if (w[6] != ticket || w[7] != hmgpu_mail_check(w, ticket)) return false;
-  memcpy(out, w, sizeof(hmgpu_me_result));
+  memcpy(out6, w, 6 * sizeof(uint32_t));
   return true;
 }
 
+// dynamic shared memory a server generation needs: the staged TZ window, the largest full-search window of the call, and (for
+// prediction-error lines) the scratch of the motion-compensation passes
+#define SRV_DYN_MIN (10 * 1024)
+#define SRV_DYN_PRED (28 * 1024)
+
 // one call through the resident server, in two halves so that the caller can work while the device searches:
 // submit = write the lines (start a generation if none is alive); wait = poll the result slots
-static int server_submit(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, bool any_org,
-                         const int16_t* org_blocks, int n_org_elems, int max_win)
+static int server_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, bool any_org, const int16_t* org_blocks, int n_org_elems,
+                         int max_win, const hmgpu_pred_job* pjobs, const uint8_t* pfuncs, int n_pred)
 {
-  const int need_dyn = max_win > 10 * 1024 ? max_win : 10 * 1024;
+  Mailbox* mb = (Mailbox*)ctx->h_mail;
+  int need_dyn = max_win > SRV_DYN_MIN ? max_win : SRV_DYN_MIN;
+  if (n_pred && need_dyn < SRV_DYN_PRED) need_dyn = SRV_DYN_PRED;
   int rc;
   if (ctx->srv_alive && need_dyn > ctx->srv_dyn && (rc = hmgpu_server_stop(ctx))) return rc;
   if (ctx->srv_alive && ((volatile uint32_t*)mb->exited)[0] == ctx->srv_gen)
@@ -838,83 +1060,91 @@ static int server_submit(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, 
   }
   if (any_org) memcpy(mb->org_blocks, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
   const uint32_t ticket = ++ctx->mail_ticket;
-  memcpy(ctx->pend_jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);   // kept for a re-submit if the server must be restarted
-  ctx->pend_n = n_jobs;
-  server_write_lines(mb, jobs, n_jobs, ticket, ctx->srv_gen);
-  if (!ctx->srv_alive && (rc = server_start(ctx, mb, need_dyn > ctx->srv_dyn ? need_dyn : ctx->srv_dyn))) return rc;
+  // kept for a re-submit if the server must be restarted
+  memcpy(ctx->pend_jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
+  if (n_pred) { memcpy(ctx->pend_pred, pjobs, sizeof(hmgpu_pred_job) * (size_t)n_pred); memcpy(ctx->pend_pfunc, pfuncs, (size_t)n_pred); }
+  ctx->pend_n = n_jobs; ctx->pend_np = n_pred;
+  server_write_lines(ctx, mb, jobs, n_jobs, pjobs, pfuncs, n_pred, ticket, ctx->srv_gen);
+  if (!ctx->srv_alive && (rc = server_start(ctx, need_dyn > ctx->srv_dyn ? need_dyn : ctx->srv_dyn))) return rc;
   ctx->srv_calls++;
   return HMGPU_OK;
 }
 
-static int server_wait(hmgpu_ctx* ctx, Mailbox* mb, hmgpu_me_result* results)
+static int server_wait(hmgpu_ctx* ctx, hmgpu_me_result* results, uint32_t* pred_out)
 {
+  Mailbox* mb = (Mailbox*)ctx->h_mail;
   const uint32_t ticket = ctx->mail_ticket;
-  const int n_jobs = ctx->pend_n;
+  const int n_jobs = ctx->pend_n, n_lines = ctx->pend_n + ctx->pend_np;
   int rc;
-  for (int i = 0; i < n_jobs; i++)
+  for (int i = 0; i < n_lines; i++)
   {
     const volatile uint32_t* slot = (const volatile uint32_t*)&mb->slots[i];
+    const int cta = i % ctx->srv_ctas;                     // the server CTA that serves line i
+    uint32_t w6[6];
     unsigned spins = 0;
-    while (!slot_ready(slot, ticket, &results[i]))
+    while (!slot_ready(slot, ticket, w6))
     {
       cpu_relax();
-      if ((++spins & 63u) == 0 && ((volatile uint32_t*)mb->exited)[i] == ctx->srv_gen)
+      if ((++spins & 63u) == 0 && ((volatile uint32_t*)mb->exited)[cta] == ctx->srv_gen)
       {
         // this CTA stopped polling (idle exit racing with the call); anything it published is already visible
-        if (slot_ready(slot, ticket, &results[i])) break;
+        if (slot_ready(slot, ticket, w6)) break;
         ctx->srv_alive = false;
         ctx->srv_gen++;
-        server_write_lines(mb, ctx->pend_jobs, n_jobs, ticket, ctx->srv_gen);
-        if ((rc = server_start(ctx, mb, ctx->srv_dyn))) return rc;
+        server_write_lines(ctx, mb, ctx->pend_jobs, n_jobs, ctx->pend_pred, ctx->pend_pfunc, ctx->pend_np, ticket, ctx->srv_gen);
+        if ((rc = server_start(ctx, ctx->srv_dyn))) return rc;
       }
       if (spins > 4000000u)
       {
         spins = 0;
-        const cudaError_t e = cudaStreamQuery(ctx->srv_stream);
-        if (e != cudaErrorNotReady && e != cudaSuccess)
-          return hmgpu_fail(ctx, HMGPU_E_CUDA, "mailbox server failed: %s", cudaGetErrorString(e));
+        if (ctx->remote) { if ((rc = hmgpu_remote_call(ctx, HMB_OP_SERVER_QUERY, NULL, NULL, NULL))) return rc; }
+        else
+        {
+          const cudaError_t e = cudaStreamQuery(ctx->srv_stream);
+          if (e != cudaErrorNotReady && e != cudaSuccess)
+            return hmgpu_fail(ctx, HMGPU_E_CUDA, "mailbox server failed: %s", cudaGetErrorString(e));
+        }
       }
     }
+    if (i < n_jobs) memcpy(&results[i], w6, sizeof(hmgpu_me_result));
+    else pred_out[i - n_jobs] = w6[0];
   }
-  ctx->pend_n = 0;
+  ctx->pend_n = ctx->pend_np = 0;
   return HMGPU_OK;
-}
-
-static int me_search_server(hmgpu_ctx* ctx, Mailbox* mb, const hmgpu_me_job* jobs, int n_jobs, bool any_org,
-                            const int16_t* org_blocks, int n_org_elems, int max_win, hmgpu_me_result* results)
-{
-  const int rc = server_submit(ctx, mb, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win);
-  return rc ? rc : server_wait(ctx, mb, results);
 }
 
 static bool server_enabled(const hmgpu_ctx* ctx) { return ctx->tune.server && !ctx->tune.trace; }
 
-// Asynchronous pair ("async submit/poll for the mailbox path").  hmgpu_me_submit returns as soon as the jobs are
-// visible to the device; the caller does host work that does not need the vectors (HM: the merge estimation of the PU) and
-// collects them with hmgpu_me_wait.  Batches the resident server cannot take are kept and searched inside hmgpu_me_wait.
-int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems)
+// Asynchronous pair ("async submit/poll for the mailbox path").  hmgpu_pu_submit returns as soon as the jobs are
+// visible to the device; the caller does host work that does not need the results and collects them with hmgpu_pu_wait.
+// Batches the resident server cannot take are kept and run inside the wait.
+static int validate_pred_jobs(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n, bool chroma, int n_dst, bool need_dst);
+
+int hmgpu_pu_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
+                    const hmgpu_pred_job* pred_jobs, const uint8_t* pred_funcs, int n_pred)
 {
   if (!ctx) return HMGPU_E_INVALID;
-  if (ctx->pend_n || ctx->defer_n) return hmgpu_fail(ctx, HMGPU_E_STATE, "hmgpu_me_submit: the previous submit has not been waited for");
-  if (n_jobs == 0) return HMGPU_OK;
-  if (!jobs || n_jobs < 0 || n_jobs > MAIL_JOBS) return hmgpu_fail(ctx, HMGPU_E_INVALID, "hmgpu_me_submit takes 1..%d jobs", MAIL_JOBS);
+  if (ctx->pend_n || ctx->pend_np || ctx->defer_n || ctx->defer_np) return hmgpu_fail(ctx, HMGPU_E_STATE, "submit: the previous submit has not been waited for");
+  if (n_jobs == 0 && n_pred == 0) return HMGPU_OK;
+  if (n_jobs < 0 || n_pred < 0 || n_jobs > MAIL_JOBS || n_pred > HMGPU_MAIL_LINES || (n_jobs && !jobs) || (n_pred && (!pred_jobs || !pred_funcs)))
+    return hmgpu_fail(ctx, HMGPU_E_INVALID, "submit takes up to %d searches and up to %d prediction-error jobs", MAIL_JOBS, HMGPU_MAIL_LINES);
   if (org_blocks && n_org_elems < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "n_org_elems is negative");
-  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  bool any_org, any_full, any_tz, any_frac, any_sel;
-  int max_win;
+  if (!ctx->remote) HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  bool any_org = false, any_full, any_tz, any_frac, any_sel = false;
+  int max_win = 0;
   int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, 0, &any_sel);
   if (rc) return rc;
+  for (int i = 0; i < n_pred; i++)
+    if (pred_funcs[i] != HMGPU_DF_SAD && pred_funcs[i] != HMGPU_DF_SAD_GENERIC && pred_funcs[i] != HMGPU_DF_HADS)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "prediction-error job %d: func %d (only SAD and HADS prediction errors exist in the reference)", i, pred_funcs[i]);
+  if ((rc = validate_pred_jobs(ctx, pred_jobs, n_pred, false, 0, false))) return rc;
   any_org = any_org || any_sel;                            // here: "the side array travels" (key patterns or MV predictors)
-  if (server_enabled(ctx) && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024 && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64))
+  if (server_enabled(ctx) && n_jobs + n_pred <= HMGPU_MAIL_LINES && max_win <= 180 * 1024 && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64))
   {
-    if (!ctx->h_mail)
-    {
-      HMGPU_CUDA(ctx, cudaHostAlloc(&ctx->h_mail, sizeof(Mailbox), cudaHostAllocMapped));
-      memset(ctx->h_mail, 0, sizeof(Mailbox));
-    }
-    return server_submit(ctx, (Mailbox*)ctx->h_mail, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win);
+    if (!ctx->remote && (rc = mailbox_ensure(ctx))) return rc;
+    return server_submit(ctx, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win, pred_jobs, pred_funcs, n_pred);
   }
-  // deferred: the blocking search runs in hmgpu_me_wait (the caller's buffers may be gone by then: copy)
+  // deferred: the blocking calls run in the wait (the caller's buffers may be gone by then: copy)
   if (any_org)
   {
     if ((size_t)n_org_elems > ctx->defer_org_cap)
@@ -927,24 +1157,73 @@ int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const 
     memcpy(ctx->defer_org, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
   }
   memcpy(ctx->pend_jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
-  ctx->defer_n = n_jobs; ctx->defer_org_n = any_org ? n_org_elems : 0;
+  if (n_pred) { memcpy(ctx->pend_pred, pred_jobs, sizeof(hmgpu_pred_job) * (size_t)n_pred); memcpy(ctx->pend_pfunc, pred_funcs, (size_t)n_pred); }
+  ctx->defer_n = n_jobs; ctx->defer_np = n_pred; ctx->defer_org_n = any_org ? n_org_elems : 0;
   return HMGPU_OK;
 }
 
-int hmgpu_me_wait(hmgpu_ctx* ctx, hmgpu_me_result* results)
+int hmgpu_pu_wait(hmgpu_ctx* ctx, hmgpu_me_result* results, uint32_t* pred_out)
 {
   if (!ctx) return HMGPU_E_INVALID;
-  if (ctx->defer_n)
+  if (ctx->defer_n || ctx->defer_np)
   {
-    const int n = ctx->defer_n;
-    ctx->defer_n = 0;
-    hmgpu_me_job jobs[MAIL_JOBS];
-    memcpy(jobs, ctx->pend_jobs, sizeof(hmgpu_me_job) * (size_t)n);
-    return hmgpu_me_search(ctx, jobs, n, ctx->defer_org_n ? ctx->defer_org : NULL, ctx->defer_org_n, results);
+    const int n = ctx->defer_n, np = ctx->defer_np;
+    ctx->defer_n = ctx->defer_np = 0;
+    if ((n && !results) || (np && !pred_out)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL results");
+    int rc = HMGPU_OK;
+    if (n)
+    {
+      hmgpu_me_job jobs[MAIL_JOBS];
+      memcpy(jobs, ctx->pend_jobs, sizeof(hmgpu_me_job) * (size_t)n);
+      rc = hmgpu_me_search(ctx, jobs, n, ctx->defer_org_n ? ctx->defer_org : NULL, ctx->defer_org_n, results);
+    }
+    // prediction-error jobs of one call may mix SAD and HADS: one batched call per function
+    for (int f = 0; f < 3 && rc == HMGPU_OK && np; f++)
+    {
+      const int func = f == 0 ? HMGPU_DF_SAD : (f == 1 ? HMGPU_DF_SAD_GENERIC : HMGPU_DF_HADS);
+      hmgpu_pred_job pj[HMGPU_MAIL_LINES]; int at[HMGPU_MAIL_LINES]; uint32_t o[HMGPU_MAIL_LINES]; int m = 0;
+      for (int i = 0; i < np; i++) if (ctx->pend_pfunc[i] == func) { pj[m] = ctx->pend_pred[i]; at[m++] = i; }
+      if (!m) continue;
+      rc = hmgpu_pred_error(ctx, pj, m, func, o);
+      for (int i = 0; i < m && rc == HMGPU_OK; i++) pred_out[at[i]] = o[i];
+    }
+    return rc;
   }
-  if (!ctx->pend_n) return HMGPU_OK;
-  if (!results) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL results");
-  return server_wait(ctx, (Mailbox*)ctx->h_mail, results);
+  if (!ctx->pend_n && !ctx->pend_np) return HMGPU_OK;
+  if ((ctx->pend_n && !results) || (ctx->pend_np && !pred_out)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL results");
+  return server_wait(ctx, results, pred_out);
+}
+
+int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs != 0 && !jobs) return hmgpu_fail(ctx, HMGPU_E_INVALID, "hmgpu_me_submit takes 1..%d jobs", MAIL_JOBS);
+  return hmgpu_pu_submit(ctx, jobs, n_jobs, org_blocks, n_org_elems, NULL, NULL, 0);
+}
+
+int hmgpu_me_wait(hmgpu_ctx* ctx, hmgpu_me_result* results) { return hmgpu_pu_wait(ctx, results, NULL); }
+
+// a batch through the broker daemon: jobs, key blocks and results travel through the batch area of the shared segment
+static int remote_me_batch(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
+{
+  size_t cap = 0;
+  char* area = (char*)hmgpu_remote_area(ctx, 1, &cap);
+  const size_t ob = round_up(org_blocks ? sizeof(int16_t) * (size_t)n_org_elems : 0, 256);
+  if (ob + 4096 > cap) return hmgpu_fail(ctx, HMGPU_E_NOMEM, "key-pattern blocks (%zu bytes) do not fit the broker's batch area", ob);
+  const size_t per_job = sizeof(hmgpu_me_job) + sizeof(hmgpu_me_result);
+  const int chunk = (int)((cap - ob - 512) / per_job);
+  if (org_blocks && n_org_elems) memcpy(area, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+  for (int first = 0; first < n_jobs; first += chunk)
+  {
+    const int n = n_jobs - first < chunk ? n_jobs - first : chunk;
+    const size_t jb = round_up(sizeof(hmgpu_me_job) * (size_t)n, 256);
+    memcpy(area + ob, jobs + first, sizeof(hmgpu_me_job) * (size_t)n);
+    const int32_t a[6] = { n, org_blocks ? n_org_elems : 0, first, 0, 0, 0 };
+    const int rc = hmgpu_remote_call(ctx, HMB_OP_ME_BATCH, a, NULL, NULL);
+    if (rc) return rc;
+    memcpy(results + first, area + ob + jb, sizeof(hmgpu_me_result) * (size_t)n);
+  }
+  return HMGPU_OK;
 }
 
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
@@ -954,27 +1233,32 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || !results || n_jobs < 0 || n_jobs > (1 << 26)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
   if (org_blocks && n_org_elems < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "n_org_elems is negative");
-  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->pend_n || ctx->pend_np) return hmgpu_fail(ctx, HMGPU_E_STATE, "a submit is outstanding: wait for it first");
+  if (!ctx->remote) HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n_jobs > MAIL_JOBS) { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // a batch wants the whole GPU
-  if (n_jobs >= PIPE_MIN_JOBS && ctx->tune.pipeline) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
+  if (n_jobs >= PIPE_MIN_JOBS && ctx->tune.pipeline && !ctx->remote) return me_search_pipelined(ctx, jobs, n_jobs, org_blocks, n_org_elems, results);
   bool any_org, any_full, any_tz, any_frac, any_sel;
   int max_win;
   int rc = validate_jobs(ctx, jobs, n_jobs, org_blocks ? n_org_elems : 0, &any_org, &any_full, &any_tz, &any_frac, &max_win, 0, &any_sel);
   if (rc) return rc;
   const bool key_blocks = any_org;                         // int16 key patterns present: selects the non-packed kernels
   any_org = any_org || any_sel;                            // below: "the side array travels" (key patterns or MV predictors)
-  if (n_jobs <= MAIL_JOBS && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64) && ctx->tune.fastpath)
+  const bool mail_ok = n_jobs <= MAIL_JOBS && (!any_org || n_org_elems <= MAIL_JOBS * 64 * 64) && ctx->tune.fastpath;
+  if (mail_ok && server_enabled(ctx) && max_win <= 180 * 1024)
   {
-    // ---- low-latency path: mapped pinned mailbox, one fused kernel, host spins on the flags ----
-    if (!ctx->h_mail)
-    {
-      HMGPU_CUDA(ctx, cudaHostAlloc(&ctx->h_mail, sizeof(Mailbox), cudaHostAllocMapped));
-      memset(ctx->h_mail, 0, sizeof(Mailbox));
-    }
+    // ---- low-latency path: the resident server polls the job lines, the host spins on the result slots ----
+    if (!ctx->remote && (rc = mailbox_ensure(ctx))) return rc;
+    rc = server_submit(ctx, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win, NULL, NULL, 0);
+    return rc ? rc : server_wait(ctx, results, NULL);
+  }
+  if (ctx->remote) return remote_me_batch(ctx, jobs, n_jobs, any_org ? org_blocks : NULL, n_org_elems, results);
+  if (mail_ok)
+  {
+    // ---- one fused launch per call (HMGPU_SERVER=0 / tracing): jobs as kernel parameters, results in the mailbox slots ----
+    if ((rc = mailbox_ensure(ctx))) return rc;
     Mailbox* mb = (Mailbox*)ctx->h_mail;
+    Mailbox* dm = (Mailbox*)ctx->d_mail;
     const bool s_trace = ctx->tune.trace != 0;
-    if (server_enabled(ctx) && n_jobs <= HMGPU_SERVER_CTAS && max_win <= 180 * 1024)
-      return me_search_server(ctx, mb, jobs, n_jobs, any_org, org_blocks, n_org_elems, max_win, results);
     const double t0 = s_trace ? now_us() : 0.0;
     HmgpuJobPack pack;
     memcpy(pack.jobs, jobs, sizeof(hmgpu_me_job) * (size_t)n_jobs);
@@ -982,7 +1266,7 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
     const uint32_t ticket = ++ctx->mail_ticket;
     __sync_synchronize();
     const double t1 = s_trace ? now_us() : 0.0;
-    rc = hmgpu_launch_single(ctx, pack, n_jobs, mb->org_blocks, mb->slots, ticket, key_blocks, max_win, s_trace ? mb->trace : NULL);
+    rc = hmgpu_launch_single(ctx, pack, n_jobs, dm->org_blocks, dm->slots, ticket, key_blocks, max_win, s_trace ? dm->trace : NULL);
     if (rc) return rc;
     const double t2 = s_trace ? now_us() : 0.0;
     for (int i = 0; i < n_jobs; i++)
@@ -1055,6 +1339,7 @@ int hmgpu_me_search_device(hmgpu_ctx* ctx, const void* d_jobs, int n_jobs, const
   if (!ctx) return HMGPU_E_INVALID;
   if (n_jobs == 0) return HMGPU_OK;
   if (!d_jobs || !d_results || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad jobs/results/n_jobs");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_me_search_device");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   { const int rcs = hmgpu_server_stop(ctx); if (rcs) return rcs; }   // the server reads the planes through the read-only path
   // jobs are not visible to the host: worst-case full-search window (SR 64, 64x64 PU)
@@ -1118,6 +1403,7 @@ int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_
   if (!ctx) return HMGPU_E_INVALID;
   if (n_items == 0) return HMGPU_OK;
   if (!org || !cur || !items || !out || n_items < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_dist_batch");
   for (int i = 0; i < n_items; i++)
   {
     const hmgpu_dist_item& it = items[i];
@@ -1158,6 +1444,7 @@ int hmgpu_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* jobs, int n_jobs, int16_t*
 {
   if (!ctx) return HMGPU_E_INVALID;
   if (n_jobs == 0) return HMGPU_OK;
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_mc_luma");
   if (!jobs || !dst || n_jobs < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
   for (int i = 0; i < n_jobs; i++)
   {
@@ -1230,6 +1517,19 @@ int hmgpu_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int wi
   if (!jobs || !dst || n_jobs < 0 || n_dst < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
   int rc = validate_pred_jobs(ctx, jobs, n_jobs, with_chroma != 0, n_dst, true);
   if (rc) return rc;
+  if (ctx->remote)
+  {
+    if ((rc = hmgpu_server_stop(ctx))) return rc;
+    size_t cap = 0;
+    char* area = (char*)hmgpu_remote_area(ctx, 1, &cap);
+    const size_t jb = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256);
+    if (jb + sizeof(int16_t) * (size_t)n_dst > cap) return hmgpu_fail(ctx, HMGPU_E_NOMEM, "prediction batch does not fit the broker's batch area");
+    memcpy(area, jobs, sizeof(hmgpu_pred_job) * (size_t)n_jobs);
+    const int32_t a[6] = { n_jobs, with_chroma, n_dst, 0, 0, 0 };
+    if ((rc = hmgpu_remote_call(ctx, HMB_OP_PREDICT, a, NULL, NULL))) return rc;
+    memcpy(dst, area + jb, sizeof(int16_t) * (size_t)n_dst);
+    return HMGPU_OK;
+  }
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t b0 = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256), b1 = round_up(sizeof(int16_t) * (size_t)n_dst, 256);
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1255,6 +1555,18 @@ int hmgpu_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int
     return hmgpu_fail(ctx, HMGPU_E_INVALID, "func %d: only SAD and HADS prediction errors exist in the reference", func);
   int rc = validate_pred_jobs(ctx, jobs, n_jobs, false, 0, false);
   if (rc) return rc;
+  if (ctx->remote)
+  {
+    size_t cap = 0;
+    char* area = (char*)hmgpu_remote_area(ctx, 1, &cap);
+    const size_t jb = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256);
+    if (jb + sizeof(uint32_t) * (size_t)n_jobs > cap) return hmgpu_fail(ctx, HMGPU_E_NOMEM, "prediction batch does not fit the broker's batch area");
+    memcpy(area, jobs, sizeof(hmgpu_pred_job) * (size_t)n_jobs);
+    const int32_t a[6] = { n_jobs, func, 0, 0, 0, 0 };
+    if ((rc = hmgpu_remote_call(ctx, HMB_OP_PRED_ERROR, a, NULL, NULL))) return rc;
+    memcpy(out, area + jb, sizeof(uint32_t) * (size_t)n_jobs);
+    return HMGPU_OK;
+  }
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t b0 = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256), b1 = round_up(sizeof(uint32_t) * (size_t)n_jobs, 256);
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1278,6 +1590,7 @@ int hmgpu_fwd_transform(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, i
   if (n_tus == 0) return HMGPU_OK;
   if (!resi || !coeff || n_tus < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
   if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_fwd_transform");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t elems = (size_t)n_tus * n * n;
   const size_t b0 = round_up(sizeof(int16_t) * elems, 256), b1 = round_up(sizeof(int32_t) * elems, 256);
@@ -1303,6 +1616,7 @@ int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_p
   if (!coeff || !level || !abs_sum || n_tus < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
   if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
   if (qp_rem < 0 || qp_rem > 5 || qp_per < 0 || qp_per > 12) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad qp per/rem");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_quant");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t elems = (size_t)n_tus * n * n;
   const size_t b0 = round_up(sizeof(int32_t) * elems, 256), b3 = round_up(sizeof(uint32_t) * (size_t)n_tus, 256);

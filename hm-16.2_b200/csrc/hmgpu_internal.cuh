@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include "../../include/hmgpu.h"
+#include "broker_proto.h"
 
 #define HMGPU_MARGIN 80          // luma padding, g_uiMaxCUWidth + 16 (TComPicYuv.cpp:87-88)
 #define HMGPU_CMARGIN 40         // chroma padding (4:2:0)
@@ -12,7 +13,8 @@
 #define HMGPU_NUM_SMS 148
 #define HMGPU_MAIL_JOBS 32       // jobs per call of the low-latency path (me_single.cu)
 #define HMGPU_TZ_STREAMS 15      // side streams of the TZ stage (me_tz_thread.cu)
-#define HMGPU_SERVER_CTAS 16     // CTAs of the mailbox server = jobs it takes per call
+#define HMGPU_SERVER_CTAS 16     // most CTAs a mailbox server runs with (hmgpu_ctx::srv_ctas of them)
+#define HMGPU_MAIL_LINES 32      // job lines of the mailbox = jobs a call through the server can carry
 
 // Device view of the reference planes of one context, passed to kernels by value.
 // plane(slot, phase) sample (x, y), x in [-80, W+80): base[slot] + phase*plane_elems + y*pitch + x
@@ -98,10 +100,15 @@ struct hmgpu_ctx
   cudaStream_t copy_stream;              // H2D of the next chunk + its validation scan
   void* d_scan; void* h_scan;            // per-lane verdict of the scan (device / pinned host copy)
   void* d_orgblk; size_t d_orgblk_bytes; // bi-pred key patterns of a pipelined batch
-  void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu)
+  void* h_mail; uint32_t mail_ticket;  // mapped pinned mailbox of the low-latency path (me_single.cu), struct Mailbox
+  void* d_mail;                        // the same memory as the device addresses it
+  bool  mail_external;                 // h_mail lives in a broker shared-memory segment (not freed with the context)
+  struct HmgpuRemote* remote;          // != NULL: client of a broker daemon (remote.cu); this process makes no CUDA call
+  int   srv_ctas;                      // CTAs of this context's server kernel (1..HMGPU_SERVER_CTAS)
   // mailbox server (me_server_kernel): a kernel that stays resident between calls
   hmgpu_me_job pend_jobs[HMGPU_MAIL_JOBS]; int pend_n;   // jobs of a submit that has not been waited for (server path)
-  int defer_n, defer_org_n; int16_t* defer_org; size_t defer_org_cap;   // hmgpu_me_submit batches searched inside hmgpu_me_wait
+  hmgpu_pred_job pend_pred[HMGPU_MAIL_LINES]; uint8_t pend_pfunc[HMGPU_MAIL_LINES]; int pend_np;   // its prediction-error jobs
+  int defer_n, defer_np, defer_org_n; int16_t* defer_org; size_t defer_org_cap;   // submits that run inside the wait
   cudaStream_t srv_stream; bool srv_alive; uint32_t srv_gen; int srv_dyn; uint32_t srv_calls, srv_starts;
   uint64_t launches;
   // optional per-stage device timing (hmgpu_profile_enable): CUDA events on ctx->stream
@@ -121,6 +128,19 @@ struct HmgpuJobPack { hmgpu_me_job jobs[HMGPU_MAIL_JOBS]; };
 // single write.  No system-scope fence is issued (it cost 4 us per call): instead the slot validates itself --
 // the host accepts it only when the ticket matches and the check word matches the six result words.
 struct HmgpuMailSlot { hmgpu_me_result r; uint32_t ticket; uint32_t check; };
+// The mailbox: mapped pinned host memory (or a broker shared-memory segment registered with CUDA) polled by the resident server
+// kernel.  A job line is 64 bytes: words 0..11 the job (hmgpu_me_job, or a hmgpu_pred_job in words 0..4), 12 the ticket of the
+// call, 13 the server generation, 14 flags (bit 0: the line carries a job; bit 1: it is a prediction-error job, func in bits
+// 16..23; bits 8..15: number of lines of the call), 15 the check word over words 0..14.
+struct Mailbox
+{
+  HmgpuMailSlot   slots[HMGPU_MAIL_LINES];
+  uint32_t        lines[HMGPU_MAIL_LINES][16];    // host -> server
+  uint32_t        exited[HMGPU_SERVER_CTAS];      // server -> host: generation of the server CTA that stopped polling
+  unsigned long long trace[8];          // HMGPU_TRACE: globaltimer stamps of the kernel phases
+  int16_t         org_blocks[HMGPU_MAIL_JOBS * 64 * 64];
+};
+
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
@@ -154,12 +174,40 @@ struct HmgpuStage
 };
 
 int hmgpu_fail(hmgpu_ctx* ctx, int code, const char* fmt, ...);
+// device / pinned-host allocations of the library.  In pool mode (the broker daemon) a freed block is kept for the next request
+// of a similar size instead of going back to CUDA: cudaFree / cudaFreeHost synchronise the whole device and would wait for the
+// resident server kernels of every other client.
+cudaError_t hmgpu_dmalloc(void** p, size_t bytes);
+void hmgpu_dfree(void* p);
+cudaError_t hmgpu_hmalloc(void** p, size_t bytes);
+void hmgpu_hfree(void* p);
 int hmgpu_reserve_pinned(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_stage(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_work(hmgpu_ctx* ctx, size_t bytes);
 int hmgpu_reserve_tzlist(hmgpu_ctx* ctx, size_t bytes);
 RefTable hmgpu_ref_table(const hmgpu_ctx* ctx);
 void hmgpu_use_lane(hmgpu_ctx* ctx, int lane);
+
+// ---- client of a broker daemon (remote.cu; no CUDA call is made by a process in this mode) ----------------------------
+// connect to the daemon's socket, create the remote context, map its shared segment; the returned hmgpu_ctx carries the picture
+// geometry, the mailbox (h_mail = the segment's Mailbox), srv_ctas and the tuning values the daemon dictates
+int  hmgpu_remote_create(const char* socket_path, int pic_w, int pic_h, int bit_depth, int max_refs, hmgpu_ctx** out);
+void hmgpu_remote_destroy(hmgpu_ctx* ctx);
+// one round trip on the control socket; a / text / reply may be NULL.  Returns the daemon's rc (its error text lands in ctx->err)
+int  hmgpu_remote_call(hmgpu_ctx* ctx, int op, const int32_t a[6], const char* text, BrokerReply* reply);
+// which = 0: upload area, 1: batch area of the shared segment
+void* hmgpu_remote_area(hmgpu_ctx* ctx, int which, size_t* bytes);
+// ---- used by the daemon (hmgpud.cu) on its in-process contexts ---------------------------------------------------------
+extern "C" {
+void hmgpu_internal_pool_mode(int on);
+// like hmgpu_create, with the mailbox placed at `mail` (host address inside a cudaHostRegister'ed segment, sizeof(Mailbox) bytes)
+int  hmgpu_internal_create_shared(int device, int pic_w, int pic_h, int bit_depth, int max_refs, void* mail, int srv_ctas, hmgpu_ctx** out);
+int  hmgpu_internal_server_launch(hmgpu_ctx* ctx, uint32_t gen, uint32_t last_ticket, int dyn_bytes);
+int  hmgpu_internal_server_sync(hmgpu_ctx* ctx);      // cudaStreamSynchronize of the server stream
+int  hmgpu_internal_server_query(hmgpu_ctx* ctx);
+int  hmgpu_internal_server_kill(hmgpu_ctx* ctx);      // make the server kernel leave whatever the client's state, and wait
+size_t hmgpu_internal_mailbox_bytes(void);
+}
 
 // bits of hmgpu_ctx::attr_done
 enum { HMGPU_ATTR_SINGLE = 1, HMGPU_ATTR_SERVER = 2, HMGPU_ATTR_FULL = 4, HMGPU_ATTR_TZT = 8, HMGPU_ATTR_TZ_CARVE = 16, HMGPU_ATTR_FRAC3 = 32 };

@@ -11,6 +11,7 @@
 #include "me_tz_impl.cuh"
 #include "me_full_impl.cuh"
 #include "me_frac_impl.cuh"
+#include "predict_impl.cuh"
 
 #define SG_THREADS FS_THREADS
 
@@ -275,17 +276,51 @@ me_single_kernel(const __grid_constant__ HmgpuJobPack pack, const int16_t* __res
   sg_stamp(trace, 5);
 }
 
+// fetch line k of the current call (ticket tk, generation gen) into s_line; false when it does not show up within idle_ns
+// (the host then restarts the server and re-submits)
+__device__ __forceinline__ bool srv_fetch_line(const volatile uint32_t* lines, int k, uint32_t tk, uint32_t gen, unsigned long long idle_ns,
+                                               uint32_t* s_line, int* s_flag)
+{
+  const int tid = threadIdx.x;
+  if (tid < 32)
+  {
+    const volatile uint32_t* line = lines + k * 16;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int ok = 0;
+    for (;;)
+    {
+      uint32_t w = tid < 16 ? line[tid] : 0u;
+      uint32_t h = 0x7F4A7C15u;
+#pragma unroll
+      for (int i = 0; i < 15; i++) h = (h ^ __shfl_sync(0xffffffffu, w, i)) * 0x85EBCA6Bu + (h >> 15);
+      const uint32_t chk = __shfl_sync(0xffffffffu, w, 15), t = __shfl_sync(0xffffffffu, w, 12), g = __shfl_sync(0xffffffffu, w, 13);
+      if (h == chk && t == tk && g == gen) { if (tid < 16) s_line[tid] = w; ok = 1; break; }
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (__shfl_sync(0xffffffffu, (int)(now - t0 > idle_ns), 0)) break;
+    }
+    if (tid == 0) *s_flag = ok;
+  }
+  __syncthreads();
+  return *s_flag != 0;
+}
+
 // ---- the mailbox server: a kernel that stays resident between calls --------------------------------------------------
-// CTA b polls line b of the mailbox (64 bytes of mapped pinned host memory: the job, the ticket, the server generation and
-// a check word, fetched with ONE 64-byte read).  A new valid ticket = a new call: the CTA runs the job and publishes slot b.
-// The host writes every line on every call (CTAs without a job get a no-op line), so all CTAs see all tickets and their
-// idle clocks run together.  A CTA leaves when its line names another generation (the host stopped the server: before every
-// picture upload, so the planes are read-only for the life of a server and __ldg stays valid) or when it has been idle for
-// idle_ns -- it then reports exited[b] = generation AFTER its last poll, so the host can tell "will never answer" from
-// "still working" and start a new generation for the pending call.
+// CTA b polls line b of the mailbox (64 bytes of mapped pinned host memory -- or of a broker shared-memory segment -- holding
+// the job, the ticket, the server generation and a check word, fetched with ONE 64-byte read).  A new valid ticket = a new
+// call: the CTA runs the job of its line and then the jobs of lines b + gridDim.x, b + 2 gridDim.x, ... of the same call (a
+// call may carry more lines than the server has CTAs: several encoders share the SMs of one GPU through the broker, so a
+// client's server is kept small), publishing slot k for line k.  A line carries either one xMotionEstimation body or one
+// prediction-error job (merge-candidate SATD / AMVP template SAD, predict_impl.cuh).  The host writes every polled line on
+// every call (CTAs without a job get a no-op line), so all CTAs see all tickets and their idle clocks run together.  A CTA
+// leaves when its line names another generation (the host stopped the server: before every picture upload, so the planes are
+// read-only for the life of a server and __ldg stays valid) or when it has been idle for idle_ns -- it then reports
+// exited[b] = generation AFTER its last poll, so the host can tell "will never answer" from "still working" and start a new
+// generation for the pending call.
 template <typename Px>
 __global__ void __launch_bounds__(SG_THREADS)
-me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org,
+me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org_blocks, RefTable refs, OrgView org, PredPlanes pl,
                  HmgpuMailSlot* slots, volatile uint32_t* exited, uint32_t gen, uint32_t last_ticket, unsigned long long idle_ns,
                  int packed_ok)
 {
@@ -294,12 +329,13 @@ me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org
   __shared__ SgShared sh;
   __shared__ uint32_t s_line[16];
   __shared__ int s_cmd;                                        // 0 keep polling, 1 run the job in s_line, 2 leave
+  __shared__ uint32_t s_sum;
   const int tid = threadIdx.x;
   const volatile uint32_t* line = lines + blockIdx.x * 16;
   unsigned long long t_last = 0;
   if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
-  // A CTA whose line has carried no job for a while polls less often: with several encoder processes on one GPU (MPS) the
-  // 16 x 64-byte reads per poll period of every server add up on PCIe.  CTA 0 (every call has a job 0) always polls flat out.
+  // A CTA whose line has carried no job for a while polls less often: with several encoders on one GPU the 64-byte reads per
+  // poll period of every server CTA add up on PCIe.  CTA 0 (every call has a job 0) always polls flat out.
   int cold = 0;
   for (;;)
   {
@@ -329,21 +365,45 @@ me_server_kernel(const volatile uint32_t* lines, const int16_t* __restrict__ org
       if (tid == 0) s_cmd = cmd;
     }
     __syncthreads();
-    const int cmd = s_cmd;
+    int cmd = s_cmd;
     if (cmd == 2) break;
     if (cmd == 1)
     {
       last_ticket = s_line[12];
+      const int n_lines = (int)((s_line[14] >> 8) & 0xffu);
       cold = (s_line[14] & 1u) ? 0 : cold + 1;
-      if (s_line[14] & 1u)                                     // this CTA has a job in this call
+      for (int k = blockIdx.x; ; )
       {
-        hmgpu_me_job jb;
+        const uint32_t fl = s_line[14];
+        if (fl & 2u)                                             // a prediction-error job
+        {
+          hmgpu_pred_job pj;
 #pragma unroll
-        for (int i = 0; i < 12; i++) ((uint32_t*)&jb)[i] = s_line[i];
-        if (packed_ok && !(jb.flags & HMGPU_F_ORG_BLOCK)) sg_job<uint8_t, true>(jb, org_blocks, refs, org, s_dyn, s_org, sh, NULL);
-        else sg_job<Px, false>(jb, org_blocks, refs, org, s_dyn, s_org, sh, NULL);
-        sg_publish(sh.res, &slots[blockIdx.x], last_ticket);
+          for (int i = 0; i < 5; i++) ((uint32_t*)&pj)[i] = s_line[i];
+          // scratch of the two separable passes: (h + 7) x w intermediates, the list-0 block, the prediction
+          int16_t* s_tmp = (int16_t*)s_dyn;
+          int16_t* s_l0 = s_tmp + (64 + 7) * 64;
+          int16_t* s_out = (int16_t*)s_org;
+          const uint32_t v = pred_error_block<Px, SG_THREADS>(pj, pl, org, ((fl >> 16) & 0xffu) == HMGPU_DF_HADS ? 1 : 0, s_tmp, s_l0, s_out, &s_sum);
+          if (tid == 0) { sh.res.int_x = (int16_t)(v & 0xffffu); sh.res.int_y = (int16_t)(v >> 16); }   // word 0 of the slot
+          __syncthreads();
+          sg_publish(sh.res, &slots[k], last_ticket);
+        }
+        else if (fl & 1u)                                        // an xMotionEstimation body
+        {
+          hmgpu_me_job jb;
+#pragma unroll
+          for (int i = 0; i < 12; i++) ((uint32_t*)&jb)[i] = s_line[i];
+          if (packed_ok && !(jb.flags & HMGPU_F_ORG_BLOCK)) sg_job<uint8_t, true>(jb, org_blocks, refs, org, s_dyn, s_org, sh, NULL);
+          else sg_job<Px, false>(jb, org_blocks, refs, org, s_dyn, s_org, sh, NULL);
+          sg_publish(sh.res, &slots[k], last_ticket);
+        }
+        k += gridDim.x;
+        if (k >= n_lines) break;
+        __syncthreads();                                         // s_line is rewritten
+        if (!srv_fetch_line(lines, k, last_ticket, gen, idle_ns, s_line, &s_cmd)) { cmd = 2; break; }
       }
+      if (cmd == 2) break;
       if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
     }
     __syncthreads();                                           // s_cmd / s_line are rewritten by the next poll
@@ -383,6 +443,7 @@ int hmgpu_launch_server(hmgpu_ctx* ctx, cudaStream_t stream, const uint32_t* d_l
 {
   const RefTable rt = hmgpu_ref_table(ctx);
   OrgView ov; ov.base = ctx->d_org; ov.pitch = ctx->org_pitch;
+  const PredPlanes pl = hmgpu_pred_planes(ctx);
   if (!(ctx->attr_done & HMGPU_ATTR_SERVER))
   {
     HMGPU_CUDA(ctx, cudaFuncSetAttribute(me_server_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
@@ -391,9 +452,9 @@ int hmgpu_launch_server(hmgpu_ctx* ctx, cudaStream_t stream, const uint32_t* d_l
   }
   ctx->launches += 1; ctx->prof_launches[HMGPU_ST_SINGLE] += 1;
   if (ctx->px_bytes == 1)
-    me_server_kernel<uint8_t><<<n_ctas, SG_THREADS, dyn_bytes, stream>>>(d_lines, d_org_blocks, rt, ov, d_slots, d_exited, gen, last_ticket, idle_ns, 1);
+    me_server_kernel<uint8_t><<<n_ctas, SG_THREADS, dyn_bytes, stream>>>(d_lines, d_org_blocks, rt, ov, pl, d_slots, d_exited, gen, last_ticket, idle_ns, 1);
   else
-    me_server_kernel<uint16_t><<<n_ctas, SG_THREADS, dyn_bytes, stream>>>(d_lines, d_org_blocks, rt, ov, d_slots, d_exited, gen, last_ticket, idle_ns, 0);
+    me_server_kernel<uint16_t><<<n_ctas, SG_THREADS, dyn_bytes, stream>>>(d_lines, d_org_blocks, rt, ov, pl, d_slots, d_exited, gen, last_ticket, idle_ns, 0);
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }

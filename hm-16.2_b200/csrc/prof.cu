@@ -122,6 +122,7 @@ extern "C" {
 int hmgpu_profile_enable(hmgpu_ctx* ctx, int on)
 {
   if (!ctx) return HMGPU_E_INVALID;
+  if (ctx->remote) return hmgpu_fail(ctx, HMGPU_E_STATE, "profiling is not available through the broker daemon");
   prof_drain(ctx);
   ctx->prof_on = on != 0;
   return HMGPU_OK;
@@ -138,6 +139,7 @@ const char* hmgpu_profile_stage_name(int stage)
 int hmgpu_profile_read(hmgpu_ctx* ctx, double* ms, uint64_t* launches, int reset)
 {
   if (!ctx) return HMGPU_E_INVALID;
+  if (ctx->remote) return hmgpu_fail(ctx, HMGPU_E_STATE, "profiling is not available through the broker daemon");
   prof_drain(ctx);
   for (int i = 0; i < HMGPU_ST_COUNT; i++)
   {
@@ -153,6 +155,7 @@ int hmgpu_profile_read(hmgpu_ctx* ctx, double* ms, uint64_t* launches, int reset
 int hmgpu_microbench(hmgpu_ctx* ctx, int which, double* gops)
 {
   if (!ctx || !gops) return HMGPU_E_INVALID;
+  if (ctx->remote) return hmgpu_fail(ctx, HMGPU_E_STATE, "the microbenchmark is not available through the broker daemon");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const int blocks = HMGPU_NUM_SMS * 8, threads = 256, iters = 4096;
   int rc = hmgpu_reserve_work(ctx, sizeof(uint32_t) * (size_t)blocks * threads);

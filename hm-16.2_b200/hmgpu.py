@@ -45,7 +45,7 @@ EXPORTS = [
     "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
-    "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
+    "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
@@ -93,6 +93,8 @@ def lib():
     L.hmgpu_me_search_device.argtypes = [vp, vp, ci, vp, vp, ci]
     L.hmgpu_me_submit.argtypes = [vp, vp, ci, vp, ci]
     L.hmgpu_me_wait.argtypes = [vp, vp]
+    L.hmgpu_pu_submit.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci]
+    L.hmgpu_pu_wait.argtypes = [vp, vp, vp]
     L.hmgpu_clip_bounds.argtypes = [ci, ci, ci, ci, vp]
     L.hmgpu_clip_bounds.restype = None
     L.hmgpu_search_range.argtypes = [vp, ci, ci, ci, vp]
@@ -265,6 +267,28 @@ class Context:
         self._check(self.L.hmgpu_me_wait(self.h, res.ctypes.data))
         self._pending = 0
         return res
+
+    def pu_submit(self, jobs, pred_jobs, pred_funcs, org_blocks=None):
+        """searches + prediction-error jobs of one PU in one mailbox round trip; collect with pu_wait()"""
+        jobs = np.ascontiguousarray(jobs, ME_JOB)
+        pred_jobs = np.ascontiguousarray(pred_jobs, PRED_JOB)
+        pred_funcs = np.ascontiguousarray(pred_funcs, np.uint8)
+        assert len(pred_funcs) == len(pred_jobs)
+        if org_blocks is not None:
+            org_blocks = np.ascontiguousarray(org_blocks, np.int16)
+        self._check(self.L.hmgpu_pu_submit(self.h, jobs.ctypes.data if len(jobs) else None, len(jobs),
+                                           org_blocks.ctypes.data if org_blocks is not None else None,
+                                           org_blocks.size if org_blocks is not None else 0,
+                                           pred_jobs.ctypes.data if len(pred_jobs) else None,
+                                           pred_funcs.ctypes.data if len(pred_jobs) else None, len(pred_jobs)))
+        self._pending, self._pending_pred = len(jobs), len(pred_jobs)
+
+    def pu_wait(self):
+        res = np.zeros(self._pending, ME_RESULT)
+        out = np.zeros(self._pending_pred, np.uint32)
+        self._check(self.L.hmgpu_pu_wait(self.h, res.ctypes.data if len(res) else None, out.ctypes.data if len(out) else None))
+        self._pending = self._pending_pred = 0
+        return res, out
 
     def me_search_device(self, d_jobs, n_jobs, d_org_blocks, d_results, flags_any):
         self._check(self.L.hmgpu_me_search_device(self.h, d_jobs, n_jobs, d_org_blocks, d_results, int(flags_any)))

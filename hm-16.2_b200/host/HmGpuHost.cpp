@@ -46,9 +46,10 @@ HmGpuHost::~HmGpuHost()
   if ( m_ctx )
   {
     fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu in %llu GPU calls, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
-                     "%.3f s in motionSearch overall, %.3f s waiting for the one-time CUDA set-up, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
+                     "%.3f s in motionSearch overall, %.3f s waiting for the one-time %s, %llu picture uploads in %.3f s, %llu kernel launches, %llu calls cross-checked\n",
              (unsigned long long)m_calls, (unsigned long long)m_gpuCalls, (unsigned long long)m_cands, m_seconds, m_calls ? m_seconds / (Double)m_calls * 1e6 : 0.0,
              m_seconds > 0 ? (Double)m_cands / m_seconds / 1e6 : 0.0, m_totalSeconds, m_initSeconds,
+             ( getenv( "HMGPU_BROKER" ) && *getenv( "HMGPU_BROKER" ) ) ? "attach (through the broker daemon)" : "CUDA set-up",
              (unsigned long long)m_uploads, m_uploadSeconds,
              (unsigned long long)hmgpu_launch_count( m_ctx ), (unsigned long long)m_checked );
     hmgpu_destroy( m_ctx );

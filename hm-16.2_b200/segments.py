@@ -4,7 +4,7 @@ An intra period that starts with an IDR (--DecodingRefreshType=2) is a closed se
 reference crosses its boundary, so segments are independent encodes (`-fs start -f length`,
 TAppEncTop.cpp:369) and need no exchange step -- no collective, only a final concatenation of the
 Annex-B streams.  Segment k goes to rank k mod N; several segments (encoder processes) share one
-GPU because a single sequential encoder cannot fill it.
+GPU because a single sequential encoder cannot fill it -- through the per-GPU broker daemon (BrokerDaemon).
 """
 import os
 import shutil
@@ -37,9 +37,9 @@ def encoder_cmd(encoder, cfg, yuv, width, height, qp, seg, out_prefix, extra=())
             "-b", "%s_seg%03d.bin" % (out_prefix, seg["segment"]), "-o", "%s_seg%03d.yuv" % (out_prefix, seg["segment"])] + list(extra)
 
 
-def run_rank(encoder, cfg, yuv, width, height, qp, plan, rank, out_prefix, extra=(), device=None, max_parallel=4):
-    """encode this rank's segments, up to max_parallel encoder processes at a time on its GPU"""
-    env = dict(os.environ)
+def run_rank(encoder, cfg, yuv, width, height, qp, plan, rank, out_prefix, extra=(), device=None, max_parallel=4, env=None):
+    """encode this rank's segments, up to max_parallel encoder processes at a time on its GPU (env: e.g. BrokerDaemon.env)"""
+    env = dict(os.environ if env is None else env)
     if device is not None:
         env["HMGPU_DEVICE"] = str(device)
     todo = segments_of_rank(plan, rank)
@@ -58,42 +58,45 @@ def run_rank(encoder, cfg, yuv, width, height, qp, plan, rank, out_prefix, extra
     return done
 
 
-class MpsDaemon:
-    """CUDA MPS for the duration of a `with` block.
+class BrokerDaemon:
+    """The per-GPU broker daemon (hm-16.2_b200/hmgpud, csrc/hmgpud.cu) for the duration of a `with` block.
 
     Several encoder processes on one GPU are the deployment model of this path (a single sequential encoder cannot fill a
-    B200), but without MPS the kernels of different processes time-slice the whole GPU: four 832x480 GPUME encoders took
-    25-40 s each instead of 7 s (profiles/r1l_mps_sharing.log).  Under MPS they run concurrently at single-process speed,
-    resident mailbox servers included.  `ok` is False when the control daemon could not be started (the block still runs)."""
+    B200).  The daemon owns the only CUDA context of the GPU; encoders started with `env` (HMGPU_BROKER=<socket>) attach to it
+    through a shared-memory mailbox instead of creating a context each (2-4 s per process, and kernels of different processes
+    time-slice the GPU unless MPS runs).  Raises when the daemon does not come up: there is no fallback."""
 
-    def __init__(self):
-        self.dir = tempfile.mkdtemp(prefix="hmgpu_mps_")
-        self.env = dict(os.environ, CUDA_MPS_PIPE_DIRECTORY=os.path.join(self.dir, "pipe"),
-                        CUDA_MPS_LOG_DIRECTORY=os.path.join(self.dir, "log"))
-        self.ok = False
+    def __init__(self, device=0, ctas=4, idle_us=2000, socket_path=None):
+        self.device = device
+        self.dir = tempfile.mkdtemp(prefix="hmgpud_")
+        self.socket = socket_path or os.path.join(self.dir, "hmgpud.%d.sock" % device)
+        self.cmd = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "hmgpud"), "--device", str(device),
+                    "--socket", self.socket, "--ctas", str(ctas), "--idle-us", str(idle_us)]
+        self.env = dict(os.environ, HMGPU_BROKER=self.socket)
+        self.proc = None
+        self.startup_s = None
 
     def __enter__(self):
-        os.makedirs(self.env["CUDA_MPS_PIPE_DIRECTORY"], exist_ok=True)
-        os.makedirs(self.env["CUDA_MPS_LOG_DIRECTORY"], exist_ok=True)
-        exe = shutil.which("nvidia-cuda-mps-control")
-        if exe:
-            try:
-                self.ok = subprocess.run([exe, "-d"], env=self.env, timeout=30).returncode == 0
-                time.sleep(0.5)
-                if self.ok:
-                    # the MPS server itself starts with the first client (seconds): do that before anybody is timed
-                    here = os.path.dirname(os.path.abspath(__file__))
-                    subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import hmgpu; hmgpu.Context(64, 64, 8, 1).close()" % here],
-                                   env=self.env, timeout=120, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            except (OSError, subprocess.TimeoutExpired):
-                self.ok = False
+        t0 = time.perf_counter()
+        self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        line = self.proc.stdout.readline()                  # "hmgpud ready: ..." once the context exists and the socket listens
+        if not line.startswith("hmgpud ready"):
+            rest = line + (self.proc.stdout.read() if self.proc.poll() is not None else "")
+            self.__exit__(None, None, None)
+            raise RuntimeError("hmgpud did not start: %s" % rest.strip())
+        self.banner = line.strip()
+        self.startup_s = time.perf_counter() - t0
         return self
 
     def __exit__(self, *exc):
-        if self.ok:
-            try:
-                subprocess.run(["nvidia-cuda-mps-control"], input=b"quit\n", env=self.env, timeout=60)
-            except (OSError, subprocess.TimeoutExpired):
-                pass
+        if self.proc is not None:
+            if self.proc.poll() is None:
+                self.proc.terminate()
+                try:
+                    self.proc.wait(timeout=20)
+                except subprocess.TimeoutExpired:
+                    self.proc.kill()
+            self.proc.stdout.close()
+            self.proc = None
         shutil.rmtree(self.dir, ignore_errors=True)
         return False

@@ -15,6 +15,11 @@
  *   - one context per encoder instance, used from that encoder's single thread; several
  *     contexts / processes may share one GPU.
  *   - there is no CPU fallback: without a CUDA device hmgpu_create() fails.
+ *   - several encoder PROCESSES on one GPU: start one broker daemon per GPU (hm-16.2_b200/hmgpud, csrc/hmgpud.cu) and set
+ *     HMGPU_BROKER=<its socket path> in the encoders' environment.  hmgpu_create() then attaches to the daemon instead of
+ *     creating a CUDA context (the process makes no CUDA call at all); searches, picture uploads and prediction costs work
+ *     as documented below, the test / measurement entry points that hand out device pointers, streams or profiles return
+ *     HMGPU_E_STATE.  Without a reachable daemon hmgpu_create() fails (no private context is created behind the caller's back).
  *   - Pel = int16_t, TCoeff = int32_t, Distortion = uint32_t, MV = 2 x int16_t quarter-pel
  *     (TypeDef.h:692-703, TComMv.h:53-55).
  */
@@ -27,7 +32,8 @@
 extern "C" {
 #endif
 
-#define HMGPU_ABI_VERSION 2   /* 2: hmgpu_me_submit / hmgpu_me_wait, hmgpu_predict / hmgpu_pred_error, job.kind */
+#define HMGPU_ABI_VERSION 3   /* 2: hmgpu_me_submit / hmgpu_me_wait, hmgpu_predict / hmgpu_pred_error, job.kind
+                                 3: hmgpu_pu_submit / hmgpu_pu_wait, hmgpu_set_option, hmgpu_clip_bounds_ctu, broker client mode */
 
 enum
 {
@@ -153,8 +159,9 @@ typedef struct hmgpu_me_result
   uint32_t n_cand;                /* candidates evaluated (integer + 18 sub-pel) */
 } hmgpu_me_result;                /* 24 bytes */
 
-/* host buffers in, host buffers out; blocking.  Up to 16 jobs: the resident mailbox server (no kernel launch); up to 32: one fused
- * launch; larger batches: the batch kernels, from 65 536 jobs on as a two-lane pipeline whose range checks run on the device.
+/* host buffers in, host buffers out; blocking.  Up to 32 jobs: the resident mailbox server (no kernel launch; one fused launch
+ * when the server is switched off); larger batches: the batch kernels, from 65 536 jobs on as a two-lane pipeline whose range
+ * checks run on the device.
  * On an error return the contents of `results` are unspecified (a pipelined batch may have been searched in part). */
 int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
                     const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results);
@@ -165,6 +172,15 @@ int hmgpu_me_search(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs,
  * One submit may be outstanding per context; no search or upload call between a submit and its wait. */
 int hmgpu_me_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems);
 int hmgpu_me_wait(hmgpu_ctx* ctx, hmgpu_me_result* results);
+/* The searches of a PU together with prediction-error costs that do not depend on them, in ONE mailbox round trip: up to 32
+ * searches plus prediction-error jobs (luma MC + SAD / SATD against the source picture, see hmgpu_pred_error), at most 32 job
+ * lines in all.  In HM these are the merge candidates of TEncSearch::xMergeEstimation (TEncSearch.cpp:2987-3040, func
+ * HMGPU_DF_HADS) and the AMVP candidates of xEstimateMvPredAMVP / xGetTemplateCost (:3571-3637, :3771-3811, HMGPU_DF_SAD) of the
+ * same PU.  pred_funcs[i] is the HMGPU_DF_* of pred_jobs[i]; hmgpu_pu_wait fills results[n_jobs] and pred_out[n_pred].
+ * hmgpu_me_submit / hmgpu_me_wait are the n_pred = 0 case. */
+int hmgpu_pu_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
+                    const struct hmgpu_pred_job* pred_jobs, const uint8_t* pred_funcs, int n_pred);
+int hmgpu_pu_wait(hmgpu_ctx* ctx, hmgpu_me_result* results, uint32_t* pred_out);
 /* device-resident variant used for kernel-only timing: d_jobs/d_results are device pointers,
  * asynchronous on hmgpu_stream(); call hmgpu_synchronize() to wait.  The host cannot inspect
  * device-resident jobs: flags_any is the OR of the flags of all jobs (selects the kernels to

@@ -25,7 +25,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(L, n), "libhmgpu.so does not export %s" % n
     assert set(hmgpu.EXPORTS) <= set(names)
-    assert L.hmgpu_abi_version() == 2
+    assert L.hmgpu_abi_version() == 3
 
 
 def test_struct_layouts_match_binding():
