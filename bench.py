@@ -293,6 +293,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_full_search:
             out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak, int_peak)
         if world == 1 and not args.no_encode:
+            out["real_stream"] = real_stream_leg(local_rank)
             out["encode"] = encode_runs(local_rank, args.full)
             out["encode_shared_gpu"] = encode_shared_gpu_leg(local_rank, args.full)
         print(json.dumps(out))
@@ -350,6 +351,68 @@ def full_search_leg(local_rank, steps, sad4_peak, int_peak=None):
                          # the same work as the kernel issues it: 4 pixel-candidates per VABSDIFF4.U8.ACC lane-op (ALU pipe only)
                          "packed": {"achieved": achieved, "peak": sad4_peak, "unit": "G VABSDIFF4 lane-op/s", "frac": achieved / sad4_peak,
                                     "peak_source": "hmgpu_microbench(1) measured in this run"}}}
+
+
+def real_stream_leg(local_rank, frames=3):
+    """ME throughput on the encoder's REAL call stream: the patched HM encoder in capture mode (HMGPU_CAPTURE, CPU search, no
+    GPU) codes `frames` pictures of the 1080p lowdelay-P clip and writes every xMotionEstimation call as the job the binding
+    sends, with the CPU search's answer; the stream is then replayed through libhmgpu, one batch per picture, and every result
+    is compared with the CPU's.  Unlike the synthetic work-list of the headline (every PU shape of every CU, predictors near
+    the true motion) this is exactly what an encode asks for, in its data-dependent mix of shapes and predictors."""
+    ec = _enc()
+    if ec is None:
+        return {"unavailable": "encoder binaries not built (need /root/reference at build time)"}
+    import tempfile
+    import torch
+    import capture
+    import hmgpu
+    import synth
+    tmp = tempfile.mkdtemp(prefix="hmcap_")
+    yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), PIC_W, PIC_H, frames, 8)
+    path = os.path.join(tmp, "stream.bin")
+    t0 = time.perf_counter()
+    capture.capture_encode(os.path.join(ec.CFG_DIR, "encoder_lowdelay_P_main.cfg"), yuv, PIC_W, PIC_H, frames, 32, path)
+    cap_s = time.perf_counter() - t0
+    w, h, bd, events = capture.read_stream(path)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    walls = []
+
+    def timer(fn):
+        t = time.perf_counter()
+        r = fn()
+        walls.append(time.perf_counter() - t)
+        return r
+    with hmgpu.Context(w, h, bd, 16, device=local_rank) as ctx:
+        capture.replay(ctx, events)                           # warm-up pass (allocations, first launches)
+        walls.clear()
+        out = capture.replay(ctx, events, timer)
+        # the largest batch (one whole P picture) device-resident, CUDA events on the library's stream
+        big = max((e for e in events if e[0] == "J"), key=lambda e: len(e[1]))
+        jobs = big[1]
+        stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+        d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(len(jobs), -1).copy()).cuda()
+        d_res = torch.zeros((len(jobs), hmgpu.ME_RESULT.itemsize), dtype=torch.uint8, device="cuda")
+        flags_any = int(np.bitwise_or.reduce(jobs["flags"]))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(4):
+            if rep == 1:
+                e0.record(stream)
+            ctx.me_search_device(d_jobs.data_ptr(), len(jobs), None, d_res.data_ptr(), flags_any)
+        e1.record(stream)
+        ctx.synchronize()
+        dev_ms = e0.elapsed_time(e1) / 3
+        res = d_res.cpu().numpy().view(hmgpu.ME_RESULT).reshape(-1)
+        big_cand = int(res["n_cand"].astype(np.int64).sum())
+        same = all((res[f] == big[2][f]).all() for f in capture.FIELDS)
+    wall = float(sum(walls))
+    return {"workload": "encoder_lowdelay_P_main.cfg 1920x1080 QP32 TZSearch, %d frames: the xMotionEstimation calls of a real CPU HM encode "
+                        "(captured by the binding in capture mode), replayed one batch per picture" % frames,
+            "capture_encode_s": cap_s, "jobs": out["jobs"], "batches": out["batches"], "candidates": out["candidates"],
+            "mismatches_vs_cpu_search": out["mismatches"],
+            "e2e_host_buffers": {"seconds": wall, "gcand_per_s": out["candidates"] / wall / 1e9, "jobs_per_s": out["jobs"] / wall},
+            "largest_batch_device_resident": {"jobs": int(len(jobs)), "candidates": big_cand, "ms": dev_ms,
+                                              "gcand_per_s": big_cand / (dev_ms * 1e-3) / 1e9, "identical_to_cpu_search": bool(same)}}
 
 
 def _enc():
@@ -415,7 +478,7 @@ def encode_segment_leg(rank, world, local_rank, dist, full=False):
     use every host core: each encoder needs a core for its serial part), one encoder process per segment, all processes of a
     GPU attached to that GPU's broker daemon.  No exchange step.  fps = all frames / slowest rank.  Beside it the unmodified CPU
     encoder over the SAME segments with the same number of processes (at N = 8: all host cores).  MD5 compared per segment.
-    Default: 8-frame segments (IntraPeriod 8: one I + one hierarchical-B GOP); --full: 32-frame segments (cfg 4's size)."""
+    Default: 9-frame segments (one I + one hierarchical-B GOP of 8); --full: 32-frame segments (cfg 4's size)."""
     ec = _enc()
     import torch
     if ec is None:
@@ -425,12 +488,12 @@ def encode_segment_leg(rank, world, local_rank, dist, full=False):
     import tempfile
     from concurrent.futures import ThreadPoolExecutor
     w, h = 1920, 1080
-    n = 32 if full else 8
+    n = 32 if full else 9
     cores = os.cpu_count() or 8
     per_gpu = max(1, cores // 8)
     tmp = tempfile.mkdtemp(prefix="hmseg_")
     cfg = os.path.join(ec.CFG_DIR, "encoder_randomaccess_main.cfg")
-    extra = ["--DecodingRefreshType=2", "--IntraPeriod=%d" % n]
+    extra = ["--DecodingRefreshType=2", "--IntraPeriod=%d" % (32 if full else 16)]     # HM wants IntraPeriod > GOP size for IDR periods
     yuvs = [synth.write_yuv(os.path.join(tmp, "seg%d.yuv" % k), w, h, n, 8, seed=1234 + rank * per_gpu + k) for k in range(per_gpu)]
 
     def many(enc, tag, more, env):
@@ -454,8 +517,8 @@ def encode_segment_leg(rank, world, local_rank, dist, full=False):
     out = None
     if rank == 0:
         frames = world * per_gpu * n
-        out = {"workload": "encoder_randomaccess_main.cfg --DecodingRefreshType=2 --IntraPeriod=%d, 1920x1080 QP32, %d closed %d-frame segment(s) "
-                           "per GPU, one encoder process per segment, attached to the GPU's broker daemon" % (n, per_gpu, n),
+        out = {"workload": "encoder_randomaccess_main.cfg --DecodingRefreshType=2, 1920x1080 QP32, %d closed %d-frame segment(s) "
+                           "per GPU, one encoder process per segment, attached to the GPU's broker daemon" % (per_gpu, n),
                "segments": world * per_gpu, "frames": frames, "host_cores": cores, "encoder_processes": world * per_gpu,
                "gpu_fps_total": frames / g_s, "slowest_rank_s": g_s,
                "cpu_fps_total_same_processes": frames / c_s, "cpu_s": c_s, "gpu_over_cpu": c_s / g_s,

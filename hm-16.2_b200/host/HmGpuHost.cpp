@@ -14,6 +14,7 @@
 #include "TLibCommon/TComPicYuv.h"
 #include "TLibCommon/TComPattern.h"
 #include "TLibCommon/TComSlice.h"
+#include "TLibCommon/TComMotionInfo.h"
 
 #include "hmgpu.h"
 
@@ -33,16 +34,31 @@ HmGpuHost& HmGpuHost::instance()
 HmGpuHost::HmGpuHost()
 : m_ctx( NULL ), m_warmThread( NULL ), m_warmCtx( NULL ), m_warmW( 0 ), m_warmH( 0 ), m_warmBitDepth( 0 ), m_picW( 0 ), m_picH( 0 ), m_tick( 0 ), m_orgPic( NULL ), m_orgPoc( -1 ), m_keyBlock( NULL )
 , m_queueing( false ), m_queueLen( 0 ), m_queueDone( false ), m_queueJobs( NULL ), m_queueRes( NULL )
+, m_predJobs( NULL ), m_predLen( 0 ), m_mergeMinArea( 256 ), m_mergeCands( 0 )
+, m_capFile( NULL ), m_capJob( NULL ), m_capRes( NULL ), m_capKeyElems( 0 )
 , m_gpuCalls( 0 ), m_calls( 0 ), m_cands( 0 ), m_checked( 0 ), m_seconds( 0.0 ), m_totalSeconds( 0.0 ), m_initSeconds( 0.0 ), m_uploadSeconds( 0.0 ), m_uploads( 0 )
 {
   for ( Int i = 0; i < NUM_SLOTS; i++ )
   {
     m_slotPic[i] = NULL; m_slotPoc[i] = -1; m_slotUse[i] = 0;
   }
+  const char* cap = getenv( "HMGPU_CAPTURE" );
+  if ( cap && *cap )
+  {
+    m_capFile = fopen( cap, "wb" );
+    if ( !m_capFile ) { fprintf( stderr, "[GPUME] cannot open the capture file %s\n", cap ); exit( 1 ); }
+    m_capJob = new hmgpu_me_job; m_capRes = new hmgpu_me_result;
+  }
 }
 
 HmGpuHost::~HmGpuHost()
 {
+  if ( m_capFile )
+  {
+    fclose( (FILE*)m_capFile );
+    fprintf( stderr, "[GPUME] capture: %llu xMotionEstimation calls written with the CPU search's results, %llu pictures\n", (unsigned long long)m_calls, (unsigned long long)m_uploads );
+    delete m_capJob; delete m_capRes;
+  }
   if ( m_ctx )
   {
     fprintf( stderr, "[GPUME] %llu xMotionEstimation calls on libhmgpu in %llu GPU calls, %llu candidates, %.3f s in hmgpu_me_search (%.1f us/call, %.3f Mcand/s), "
@@ -52,8 +68,10 @@ HmGpuHost::~HmGpuHost()
              ( getenv( "HMGPU_BROKER" ) && *getenv( "HMGPU_BROKER" ) ) ? "attach (through the broker daemon)" : "CUDA set-up",
              (unsigned long long)m_uploads, m_uploadSeconds,
              (unsigned long long)hmgpu_launch_count( m_ctx ), (unsigned long long)m_checked );
+    if ( m_mergeCands ) fprintf( stderr, "[GPUME] %llu merge candidates costed on the device (PUs of at least %d luma samples)\n", (unsigned long long)m_mergeCands, m_mergeMinArea );
     hmgpu_destroy( m_ctx );
   }
+  delete [] m_predJobs;
   delete [] m_keyBlock;
   delete [] m_queueJobs;
   delete [] m_queueRes;
@@ -66,8 +84,19 @@ Void HmGpuHost::xFail( const char* what )
   exit( 1 );
 }
 
+Void HmGpuHost::xCapturePicture( char tag, Int slot, Int poc, TComPicYuv* pic )
+{
+  FILE* f = (FILE*)m_capFile;
+  const int32_t hdr[2] = { slot, poc };
+  fputc( tag, f );
+  fwrite( hdr, sizeof( hdr ), 1, f );
+  const Pel* p = pic->getAddr( COMPONENT_Y );
+  for ( Int y = 0; y < m_picH; y++ ) fwrite( p + (ptrdiff_t)y * pic->getStride( COMPONENT_Y ), sizeof( Pel ), m_picW, f );
+}
+
 Void HmGpuHost::prewarm( Int iPicWidth, Int iPicHeight, Int iBitDepth )
 {
+  if ( m_capFile ) return;
   if ( m_ctx || m_warmThread ) return;
   m_warmW = iPicWidth; m_warmH = iPicHeight; m_warmBitDepth = iBitDepth;
   const char* dev = getenv( "HMGPU_DEVICE" );
@@ -81,6 +110,17 @@ Void HmGpuHost::prewarm( Int iPicWidth, Int iPicHeight, Int iBitDepth )
 Void HmGpuHost::xInit( TComDataCU* pcCU )
 {
   if ( m_ctx ) return;
+  if ( m_capFile )
+  {
+    if ( m_keyBlock ) return;
+    m_picW = pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples();
+    m_picH = pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples();
+    m_keyBlock = new Pel[MAX_CU_SIZE * MAX_CU_SIZE];
+    const int32_t hdr[4] = { 0x50414348 /* "HCAP" */, m_picW, m_picH, g_bitDepth[CHANNEL_TYPE_LUMA] };
+    fputc( 'H', (FILE*)m_capFile );
+    fwrite( hdr, sizeof( hdr ), 1, (FILE*)m_capFile );
+    return;
+  }
   const Double t0 = xNow();
   m_picW = pcCU->getSlice()->getSPS()->getPicWidthInLumaSamples();
   m_picH = pcCU->getSlice()->getSPS()->getPicHeightInLumaSamples();
@@ -119,6 +159,9 @@ Void HmGpuHost::xInit( TComDataCU* pcCU )
   m_keyBlock = new Pel[MAX_CU_SIZE * MAX_CU_SIZE];
   m_queueJobs = new hmgpu_me_job[MAX_QUEUE];
   m_queueRes  = new hmgpu_me_result[MAX_QUEUE];
+  m_predJobs  = new hmgpu_pred_job[MAX_PRED];
+  const char* mma = getenv( "HMGPU_MERGE_MIN_AREA" );
+  if ( mma && *mma ) m_mergeMinArea = atoi( mma );
   m_initSeconds = xNow() - t0;
 }
 
@@ -138,6 +181,8 @@ Int HmGpuHost::xRefSlot( TComPic* pcRefPic )
   }
   const Double t0 = xNow();
   TComPicYuv* rec = pcRefPic->getPicYuvRec();
+  if ( m_capFile ) xCapturePicture( 'R', lru, poc, rec );
+  else
   if ( hmgpu_ref_upload( m_ctx, lru, rec->getAddr( COMPONENT_Y ), rec->getStride( COMPONENT_Y ), NULL, NULL, 0 ) != HMGPU_OK )
   {
     xFail( "hmgpu_ref_upload" );
@@ -153,6 +198,8 @@ Void HmGpuHost::xUploadOrg( TComDataCU* pcCU )
   if ( m_orgPic == pic && m_orgPoc == pic->getPOC() ) return;
   const Double t0 = xNow();
   TComPicYuv* org = pic->getPicYuvOrg();
+  if ( m_capFile ) xCapturePicture( 'O', 0, pic->getPOC(), org );
+  else
   if ( hmgpu_org_upload( m_ctx, org->getAddr( COMPONENT_Y ), org->getStride( COMPONENT_Y ) ) != HMGPU_OK )
   {
     xFail( "hmgpu_org_upload" );
@@ -230,6 +277,15 @@ Void HmGpuHost::motionSearch( TComDataCU* pcCU, TComPic* pcRefPic, TComPattern* 
     keyElems = 6;
   }
 
+  if ( m_capFile )
+  {
+    // the CPU search runs next; checkInteger / checkFractional collect its answers and write the record
+    *m_capJob = j;
+    m_capKeyElems = keyElems;
+    memset( m_capRes, 0, sizeof( *m_capRes ) );
+    m_calls++;
+    return;
+  }
   hmgpu_me_result r;
   if ( m_queueing && !bBi )
   {
@@ -284,17 +340,62 @@ Void HmGpuHost::beginQueue()
   m_queueing  = true;
   m_queueDone = false;
   m_queueLen  = 0;
+  m_predLen   = 0;
+}
+
+Bool HmGpuHost::mergeOnGpu( TComDataCU* pcCU, Int iWidth, Int iHeight )
+{
+  xInit( pcCU );
+  return m_mergeMinArea >= 0 && iWidth * iHeight >= m_mergeMinArea;
+}
+
+Void HmGpuHost::queueMergeCand( TComDataCU* pcCU, UInt uiAbsPartIdx, Int iWidth, Int iHeight, const TComMvField& rcMvField0, const TComMvField& rcMvField1, Bool bSatd )
+{
+  xInit( pcCU );
+  xUploadOrg( pcCU );
+  if ( m_predLen >= MAX_PRED ) xFail( "more merge candidates than MRG_MAX_NUM_CANDS" );
+  hmgpu_pred_job& j = m_predJobs[m_predLen];
+  memset( &j, 0, sizeof( j ) );
+  // PU origin in picture coordinates (as xPredInterBlk addresses it, TComPrediction.cpp:662)
+  TComPicYuv* rec = pcCU->getPic()->getPicYuvRec();
+  const ptrdiff_t off = rec->getAddr( COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + uiAbsPartIdx ) - rec->getAddr( COMPONENT_Y );
+  const Int stride = rec->getStride( COMPONENT_Y );
+  j.pu_y = (int16_t)( off / stride );
+  j.pu_x = (int16_t)( off - (ptrdiff_t)j.pu_y * stride );
+  j.pu_w = (uint8_t)iWidth; j.pu_h = (uint8_t)iHeight;
+  const TComMvField* f[2] = { &rcMvField0, &rcMvField1 };
+  Int refIdx[2] = { f[0]->getRefIdx(), f[1]->getRefIdx() };
+  // TComPrediction::motionCompensation( REF_PIC_LIST_X ) (TComPrediction.cpp:541-549): identical motion in both lists is
+  // predicted from list 0 alone (xCheckIdenticalMotion, :497-512)
+  if ( pcCU->getSlice()->isInterB() && !pcCU->getSlice()->getPPS()->getWPBiPred() && refIdx[0] >= 0 && refIdx[1] >= 0 &&
+       pcCU->getSlice()->getRefPic( REF_PIC_LIST_0, refIdx[0] )->getPOC() == pcCU->getSlice()->getRefPic( REF_PIC_LIST_1, refIdx[1] )->getPOC() &&
+       f[0]->getMv() == f[1]->getMv() )
+  {
+    refIdx[1] = -1;
+  }
+  for ( Int l = 0; l < 2; l++ )
+  {
+    j.ref_slot[l] = -1;
+    if ( refIdx[l] < 0 ) continue;
+    TComMv cMv = f[l]->getMv();
+    pcCU->clipMv( cMv );                                   // xPredInterUni (TComPrediction.cpp:592)
+    j.ref_slot[l] = (int8_t)xRefSlot( pcCU->getSlice()->getRefPic( l ? REF_PIC_LIST_1 : REF_PIC_LIST_0, refIdx[l] ) );
+    j.mv_x[l] = cMv.getHor(); j.mv_y[l] = cMv.getVer();
+  }
+  m_predFuncs[m_predLen] = (UChar)( bSatd ? HMGPU_DF_HADS : HMGPU_DF_SAD );
+  m_predLen++;
+  m_mergeCands++;
 }
 
 Void HmGpuHost::submitQueue()
 {
   m_queueing = false;
-  if ( m_queueLen > 0 )
+  if ( m_queueLen > 0 || m_predLen > 0 )
   {
     const Double t0 = xNow();
-    if ( hmgpu_me_submit( m_ctx, m_queueJobs, m_queueLen, m_queueSide, 6 * m_queueLen ) != HMGPU_OK )
+    if ( hmgpu_pu_submit( m_ctx, m_queueJobs, m_queueLen, m_queueSide, 6 * m_queueLen, m_predJobs, m_predFuncs, m_predLen ) != HMGPU_OK )
     {
-      xFail( "hmgpu_me_submit" );
+      xFail( "hmgpu_pu_submit" );
     }
     m_gpuCalls++;
     const Double dt = xNow() - t0;
@@ -304,12 +405,12 @@ Void HmGpuHost::submitQueue()
 
 Void HmGpuHost::waitQueue()
 {
-  if ( m_queueLen > 0 )
+  if ( m_queueLen > 0 || m_predLen > 0 )
   {
     const Double t0 = xNow();
-    if ( hmgpu_me_wait( m_ctx, m_queueRes ) != HMGPU_OK )
+    if ( hmgpu_pu_wait( m_ctx, m_queueRes, m_predOut ) != HMGPU_OK )
     {
-      xFail( "hmgpu_me_wait" );
+      xFail( "hmgpu_pu_wait" );
     }
     const Double dt = xNow() - t0;
     m_seconds += dt; m_totalSeconds += dt;
@@ -320,6 +421,11 @@ Void HmGpuHost::waitQueue()
 
 Void HmGpuHost::checkInteger( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu )
 {
+  if ( m_capFile )
+  {
+    m_capRes->int_x = rcMvCpu.getHor(); m_capRes->int_y = rcMvCpu.getVer();
+    return;
+  }
   if ( rcOut.mvInt.getHor() != rcMvCpu.getHor() || rcOut.mvInt.getVer() != rcMvCpu.getVer() )
   {
     fprintf( stderr, "[GPUME] MISMATCH at call %llu: integer MV gpu (%d,%d) cpu (%d,%d)\n", (unsigned long long)m_calls,
@@ -330,6 +436,20 @@ Void HmGpuHost::checkInteger( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu
 
 Void HmGpuHost::checkFractional( const HmGpuSearchOut& rcOut, const TComMv& rcHalfCpu, const TComMv& rcQterCpu, Distortion uiCostCpu )
 {
+  if ( m_capFile )
+  {
+    m_capRes->half_x = rcHalfCpu.getHor(); m_capRes->half_y = rcHalfCpu.getVer();
+    m_capRes->qter_x = rcQterCpu.getHor(); m_capRes->qter_y = rcQterCpu.getVer();
+    m_capRes->frac_cost = uiCostCpu;
+    FILE* f = (FILE*)m_capFile;
+    const int32_t nKey = m_capKeyElems;
+    fputc( 'J', f );
+    fwrite( m_capJob, sizeof( *m_capJob ), 1, f );
+    fwrite( m_capRes, sizeof( *m_capRes ), 1, f );
+    fwrite( &nKey, sizeof( nKey ), 1, f );
+    if ( nKey ) fwrite( m_keyBlock, sizeof( Pel ), nKey, f );
+    return;
+  }
   if ( rcOut.mvHalf.getHor() != rcHalfCpu.getHor() || rcOut.mvHalf.getVer() != rcHalfCpu.getVer() ||
        rcOut.mvQter.getHor() != rcQterCpu.getHor() || rcOut.mvQter.getVer() != rcQterCpu.getVer() || rcOut.cost != uiCostCpu )
   {

@@ -14,6 +14,8 @@
 class TComDataCU;
 class TComPic;
 class TComPattern;
+class TComMvField;
+class TComPicYuv;
 struct hmgpu_ctx;
 
 struct HmGpuSearchOut
@@ -52,6 +54,20 @@ public:
   Void flushQueue   () { submitQueue(); waitQueue(); }
   Bool queueing     () const { return m_queueing; }
 
+  /// Merge estimation of a PU (TEncSearch::xMergeEstimation, TEncSearch.cpp:2987-3040) on the device: the prediction error of
+  /// every merge candidate -- motionCompensation + luma SATD / SAD, xGetInterPredictionError (:2952-2972) -- travels as a
+  /// prediction-error job in the same mailbox call as the PU's motion searches (hmgpu_pu_submit).  mergeOnGpu() is the policy:
+  /// small PUs stay on the host, whose work then overlaps the device call (HMGPU_MERGE_MIN_AREA, default 256 luma samples).
+  Bool mergeOnGpu   ( TComDataCU* pcCU, Int iWidth, Int iHeight );
+  Void queueMergeCand( TComDataCU* pcCU, UInt uiAbsPartIdx, Int iWidth, Int iHeight, const TComMvField& rcMvField0, const TComMvField& rcMvField1, Bool bSatd );
+  Distortion mergeCandCost( UInt uiMergeCand ) const { return m_predOut[uiMergeCand]; }
+
+  /// Capture mode (environment HMGPU_CAPTURE=<file>, with GPUME=2): no device is used at all.  Every xMotionEstimation call is
+  /// marshalled into its hmgpu_me_job exactly as for the GPU, the CPU search runs, and job + CPU result are appended to the
+  /// file together with the pictures the jobs refer to (records: 'H' header, 'R' reference upload, 'O' source picture, 'J'
+  /// job).  bench.py / tests replay such a stream through libhmgpu: the encoder's REAL call stream, with the reference's answers.
+  Bool capturing    () const { return m_capFile != NULL; }
+
   /// GPUME=2: compare with what the CPU search just produced; abort on the first mismatch
   Void checkInteger   ( const HmGpuSearchOut& rcOut, const TComMv& rcMvCpu );
   Void checkFractional( const HmGpuSearchOut& rcOut, const TComMv& rcHalfCpu, const TComMv& rcQterCpu, Distortion uiCostCpu );
@@ -86,6 +102,20 @@ private:
   struct hmgpu_me_result* m_queueRes;
   Bool        m_queueUsed[MAX_QUEUE];
   Short       m_queueSide[MAX_QUEUE * 6];   ///< MV predictors of queued selective searches (6 per job)
+  // merge candidates of the current PU whose prediction errors travel with the queue
+  static const Int MAX_PRED = 8;
+  struct hmgpu_pred_job*  m_predJobs;
+  UChar       m_predFuncs[MAX_PRED];
+  UInt        m_predOut[MAX_PRED];
+  Int         m_predLen;
+  Int         m_mergeMinArea;   ///< HMGPU_MERGE_MIN_AREA
+  UInt64      m_mergeCands;     ///< merge candidates costed on the device
+  // capture mode
+  void*       m_capFile;        ///< FILE*
+  struct hmgpu_me_job*    m_capJob;
+  struct hmgpu_me_result* m_capRes;
+  Int         m_capKeyElems;
+  Void        xCapturePicture( char tag, Int slot, Int poc, TComPicYuv* pic );
   // statistics
   UInt64      m_calls, m_cands, m_checked;
   UInt64      m_gpuCalls;       ///< hmgpu_me_search invocations (<= m_calls: queued searches share one)
