@@ -2,6 +2,8 @@
 // interfaces each one replaces).  Host buffers are staged through one pinned buffer and one
 // device buffer per context; everything runs on the context's stream.
 #include "hmgpu_internal.cuh"
+#include <cuda.h>
+#include "me_full_impl.cuh"     // fs_packed_smem_bytes: shared memory of one full-search job
 #include <stdarg.h>
 #include <stdlib.h>
 #include <time.h>
@@ -120,6 +122,7 @@ static void tuning_from_env(HmgpuTuning* t)
   t->tz_p2          = env_int("HMGPU_TZ_P2", 0);
   t->frac_v1        = env_int("HMGPU_FRAC_V1", 0);
   t->frac_overlap   = env_int("HMGPU_FRAC_OVERLAP", 1);
+  t->fs_tma         = env_int("HMGPU_FS_TMA", 1);
   t->pipe_chunk     = env_int("HMGPU_PIPE_CHUNK", 0);
   t->pipeline       = !env_int("HMGPU_NO_PIPELINE", 0);
   t->fastpath       = !env_int("HMGPU_NO_FASTPATH", 0);
@@ -133,7 +136,7 @@ struct TuneName { const char* name; int HmgpuTuning::* field; };
 static const TuneName k_tune_names[] = {
   { "tz_thread", &HmgpuTuning::tz_thread }, { "tz_thread_min", &HmgpuTuning::tz_thread_min }, { "tz_merge", &HmgpuTuning::tz_merge },
   { "tz_carve", &HmgpuTuning::tz_carve }, { "tz_p2", &HmgpuTuning::tz_p2 }, { "frac_v1", &HmgpuTuning::frac_v1 },
-  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipeline", &HmgpuTuning::pipeline },
+  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "fs_tma", &HmgpuTuning::fs_tma }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipeline", &HmgpuTuning::pipeline },
   { "fastpath", &HmgpuTuning::fastpath }, { "server", &HmgpuTuning::server }, { "server_idle_us", &HmgpuTuning::server_idle_us },
   { "trace", &HmgpuTuning::trace }, { "server_stats", &HmgpuTuning::server_stats } };
 
@@ -457,7 +460,6 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   }
   for (int i = 0; i < HMGPU_MAX_REFS; i++)
   {
-    if (ctx->refs[i].planes) hmgpu_dfree(ctx->refs[i].planes);
     if (ctx->refs[i].cb) hmgpu_dfree(ctx->refs[i].cb);
     if (ctx->refs[i].cr) hmgpu_dfree(ctx->refs[i].cr);
   }
@@ -466,6 +468,8 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   for (int i = 0; i < HMGPU_TZ_STREAMS; i++) if (ctx->tz_streams[i]) { cudaStreamSynchronize(ctx->tz_streams[i]); cudaStreamDestroy(ctx->tz_streams[i]); }
   for (int i = 0; i <= HMGPU_TZ_STREAMS; i++) if (ctx->tz_ev[i]) cudaEventDestroy(ctx->tz_ev[i]);
   if (ctx->d_org) hmgpu_dfree(ctx->d_org);
+  if (ctx->planes_all) hmgpu_dfree(ctx->planes_all);
+  free(ctx->h_tmaps);
   if (ctx->d_stage) hmgpu_dfree(ctx->d_stage);
   if (ctx->d_work) hmgpu_dfree(ctx->d_work);
   if (ctx->d_tzlist) hmgpu_dfree(ctx->d_tzlist);
@@ -479,12 +483,15 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
 static int ref_alloc(hmgpu_ctx* ctx, int slot, bool chroma)
 {
   RefSlot& s = ctx->refs[slot];
-  if (!s.planes)
+  if (!ctx->planes_all)
   {
-    const size_t bytes = ctx->plane_elems * 16 * ctx->px_bytes + 512;
-    HMGPU_CUDA(ctx, hmgpu_dmalloc((void**)&s.planes, bytes));
-    HMGPU_CUDA(ctx, cudaMemsetAsync(s.planes, 0, bytes, ctx->stream));
+    // the phase planes of ALL reference slots are one allocation: a slot is then a coordinate of the TMA tensor maps
+    // (me_frac3.cu: x, y, phase plane, slot), which are built once and travel as a kernel parameter
+    ctx->slot_bytes = (ctx->plane_elems * 16 * ctx->px_bytes + 512 + 255) & ~(size_t)255;
+    HMGPU_CUDA(ctx, hmgpu_dmalloc(&ctx->planes_all, ctx->slot_bytes * ctx->max_refs));
+    HMGPU_CUDA(ctx, cudaMemsetAsync(ctx->planes_all, 0, ctx->slot_bytes * ctx->max_refs, ctx->stream));
   }
+  if (!s.planes) s.planes = (char*)ctx->planes_all + (size_t)slot * ctx->slot_bytes;
   if (chroma && !s.cb)
   {
     const size_t bytes = (size_t)ctx->cpitch * ctx->cph * sizeof(int16_t);
@@ -696,10 +703,7 @@ static int validate_jobs(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n, int n_
         const int nx = j.win_r - j.win_l + 1, ny = j.win_b - j.win_t + 1;
         if (nx > 0 && ny > 0)
         {
-          const int rows = ((j.flags & HMGPU_F_FEN) && j.pu_h > 8) ? j.pu_h >> 1 : j.pu_h;
-          const int win_w = 15 + nx - 1 + j.pu_w + 4;
-          const int spitch = ((win_w + 15) >> 4) * 16 + 16;
-          const int bytes = ((rows * j.pu_w + 15) & ~15) + spitch * (ny - 1 + j.pu_h);
+          const int bytes = fs_packed_smem_bytes(j.pu_w, j.pu_h, nx, ny, (j.flags & HMGPU_F_FEN) != 0);
           if (bytes > *max_win_bytes) *max_win_bytes = bytes;
         }
       }
@@ -753,10 +757,7 @@ __host__ __device__ static inline int job_full_window_bytes(const hmgpu_me_job& 
 {
   const int nx = j.win_r - j.win_l + 1, ny = j.win_b - j.win_t + 1;
   if (nx <= 0 || ny <= 0) return 0;
-  const int rows = ((j.flags & HMGPU_F_FEN) && j.pu_h > 8) ? j.pu_h >> 1 : j.pu_h;
-  const int win_w = 15 + nx - 1 + j.pu_w + 4;
-  const int spitch = ((win_w + 15) >> 4) * 16 + 16;
-  return ((rows * j.pu_w + 15) & ~15) + spitch * (ny - 1 + j.pu_h);
+  return fs_packed_smem_bytes(j.pu_w, j.pu_h, nx, ny, (j.flags & HMGPU_F_FEN) != 0);
 }
 
 __global__ void job_scan_kernel(const hmgpu_me_job* __restrict__ jobs, int n, int pic_w, int pic_h, uint32_t valid_slots,

@@ -65,6 +65,7 @@ struct HmgpuTuning
   int tz_carve;         // HMGPU_TZ_CARVE: shared-memory carve-out (percent) of the warp-per-job kernel, < 0: driver default
   int tz_p2;            // HMGPU_TZ_P2: second one-thread-per-job pass for hand-over jobs
   int frac_v1;          // HMGPU_FRAC_V1: generic fractional kernels for 8-bit pictures too
+  int fs_tma;           // HMGPU_FS_TMA: the full-search window is staged by TMA (cp.async.bulk.tensor) instead of per-thread loads
   int frac_overlap;     // HMGPU_FRAC_OVERLAP: 8x8 / 4x4 tile kernels side by side
   int pipe_chunk;       // HMGPU_PIPE_CHUNK: jobs per chunk of the pipelined batch path (0: a quarter of the batch)
   int pipeline;         // !HMGPU_NO_PIPELINE
@@ -88,6 +89,8 @@ struct hmgpu_ctx
   cudaStream_t stream;
   RefSlot refs[HMGPU_MAX_REFS];
   void* d_org; int org_pitch;   // source picture, Px
+  void* planes_all; size_t slot_bytes;   // the phase planes of all reference slots (one allocation), bytes per slot
+  void* h_tmaps;                         // CUtensorMap[16] over planes_all for the full-search window (me_full.cu), built on first use
   // staging (grow on demand)
   void* h_pin; size_t h_pin_bytes;     // pinned host
   void* d_stage; size_t d_stage_bytes; // device

@@ -13,6 +13,7 @@
 // window, builds their byte-shifted operands with one funnel shift each and accumulates with
 // VABSDIFF4.U8.ACC.  >8-bit pictures and int16 key patterns (bi-pred) take a scalar path.
 #pragma once
+#include <cuda.h>
 #include "hmgpu_internal.cuh"
 #include <type_traits>
 
@@ -101,12 +102,53 @@ __device__ __forceinline__ void fs_item_sad(const FsItem& it, uint32_t (&acc)[FS
   }
 }
 
+// ---- TMA staging of the search window ---------------------------------------------------------------------------------------
+// The window of xPatternSearch is a 2-D box out of a pitched plane -- what cp.async.bulk.tensor copies.  One tensor map per row
+// width (a multiple of 16 bytes, 32 .. 256) over the phase planes of all reference slots (x = byte of the padded row, y = padded
+// row, z = phase plane, w = slot; api.cu keeps the slots in one allocation), box = that width x FS_TMA_ROWS rows.  Thread 0 issues
+// ceil(rows / FS_TMA_ROWS) copies against one mbarrier and the CTA stages the PU block meanwhile.  Rules learnt the hard way
+// (profiles/probes/tma_probe.cu): the first coordinate x element size must be a multiple of 16 bytes -- anything else is an
+// "illegal instruction" -- and the copy is ONE warp-level instruction with uniform operands (UTMALDG).
+#define FS_TMA_ROWS 32
+#define FS_TMA_MAPS 15
+struct FsMaps { CUtensorMap m[FS_TMA_MAPS + 1]; };
+
+__device__ __forceinline__ uint32_t fs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fs_tma_box(uint32_t dst, const void* tmap, int x, int y, int z, int slot, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(slot), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "FS_WAIT:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra FS_DONE;\n\t"
+    "bra FS_WAIT;\n\t"
+    "FS_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// shared memory of one job of the packed full search: PU block (visited rows), then the window rows at 128-byte alignment
+// (TMA destination), padded to whole copies of FS_TMA_ROWS rows
+__host__ __device__ static inline int fs_packed_smem_bytes(int pu_w, int pu_h, int nx, int ny, bool fen)
+{
+  const int rows = (fen && pu_h > 8) ? pu_h >> 1 : pu_h;
+  const int win_w = 15 + nx - 1 + pu_w + 4;
+  const int spitch = ((win_w + 15) >> 4) * 16 + 16;
+  const int win_h = ny - 1 + pu_h;
+  return ((rows * pu_w + 127) & ~127) + spitch * ((win_h + FS_TMA_ROWS - 1) / FS_TMA_ROWS * FS_TMA_ROWS) + 128;
+}
+
 // ---- packed 8-bit path -------------------------------------------------------------------------
 // Executed by one CTA of FS_THREADS threads; smem: dynamic shared memory sized by
 // fs_packed_smem_bytes(); thread 0 writes *out.
 __device__ __forceinline__ void full_search_block_packed(const hmgpu_me_job& jb, const RefTable& refs, const OrgView& org,
-                                                         unsigned char* smem, unsigned long long* s_red, hmgpu_me_result* out)
+                                                         unsigned char* smem_raw, unsigned long long* s_red, hmgpu_me_result* out,
+                                                         const FsMaps* maps = NULL, unsigned long long* s_bar = NULL)
 {
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const int W = jb.pu_w, H = jb.pu_h;
   const int sub = ((jb.flags & HMGPU_F_FEN) && H > 8) ? 1 : 0;
   const int rows = H >> sub, rmul = 1 << sub;
@@ -133,7 +175,23 @@ __device__ __forceinline__ void full_search_block_packed(const hmgpu_me_job& jb,
   const int spitch = rw16 * 16 + 16;                      // odd multiple of 16 B keeps rows on different banks
   const int win_h = ny - 1 + H;
   uint32_t* s_org = (uint32_t*)smem;                      // rows * W bytes (visited rows only)
-  unsigned char* s_win = smem + ((rows * W + 15) & ~15);
+  unsigned char* s_win = smem + ((rows * W + 127) & ~127);
+  const bool tma = maps != NULL && spitch <= 256;           // box widths up to 256 bytes have a tensor map
+  if (tma)
+  {
+    if (threadIdx.x == 0)
+    {
+      const uint32_t bar = fs_smem_u32(s_bar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const int n_ops = (win_h + FS_TMA_ROWS - 1) / FS_TMA_ROWS;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(n_ops * FS_TMA_ROWS * spitch)) : "memory");
+      const int x = HMGPU_MARGIN + jb.pu_x + L - mis, y = HMGPU_MARGIN + jb.pu_y + T;   // wbase in padded-plane coordinates
+      for (int op = 0; op < n_ops; op++)
+        fs_tma_box(fs_smem_u32(s_win) + (uint32_t)(op * FS_TMA_ROWS * spitch), &maps->m[(spitch >> 4) - 2], x, y + op * FS_TMA_ROWS, 0, jb.ref_slot, bar);
+    }
+    __syncthreads();                                       // the barrier is initialised for everybody who waits on it
+  }
 
   // stage PU block (visited rows only) and window
   {
@@ -145,6 +203,8 @@ __device__ __forceinline__ void full_search_block_packed(const hmgpu_me_job& jb,
       s_org[i] = __ldg((const uint32_t*)(o + (size_t)(r * rmul) * org.pitch) + k);
     }
     // window: 16 lanes per row (a row is 10..15 chunks of 16 bytes), 16 rows per pass of the CTA, no index division
+    if (tma) fs_mbar_wait(fs_smem_u32(s_bar), 0);
+    else
     {
       const int rr = threadIdx.x >> 4, k = threadIdx.x & 15;
       if (k < rw16)

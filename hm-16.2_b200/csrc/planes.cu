@@ -102,36 +102,48 @@ phase_planes_kernel(Px* __restrict__ planes, size_t plane_elems, int pitch, int 
   const int shift2 = 6 + head;                      // not first, last (:200-205)
   const int off2 = (1 << (shift2 - 1)) + (8192 << 6);
   const int max_val = (1 << bit_depth) - 1;
-  for (int i = tid; i < PP_TY * PP_TX; i += 256)
+  // vertical pass: one thread = FOUR horizontally adjacent samples of all 15 fractional planes, stored as one packed word
+  // (uint8) or two (uint16) per plane -- byte-wide stores made this kernel LSU-bound at 14 % of the HBM rate (round 1)
+  for (int i = tid; i < PP_TY * (PP_TX / 4); i += 256)
   {
-    const int r = i / PP_TX, c = i % PP_TX;
+    const int r = i / (PP_TX / 4), c = (i - r * (PP_TX / 4)) * 4;
     const int x = x0 + c, y = y0 + r;
-    if (x >= pw || y >= ph) continue;
+    if (x >= pw || y >= ph) continue;               // pitch is a multiple of 64: a group of four never straddles the row end
 #pragma unroll
     for (int fx = 0; fx < 4; fx++)
     {
-      int col[8];
+      int col[8][4];
 #pragma unroll
-      for (int k = 0; k < 8; k++) col[k] = s_h[fx][r + k][c];   // rows y-3 .. y+4
+      for (int k = 0; k < 8; k++)
+      {
+        const short4 q = *(const short4*)&s_h[fx][r + k][c];   // rows y-3 .. y+4, 8-byte aligned (c % 4 == 0)
+        col[k][0] = q.x; col[k][1] = q.y; col[k][2] = q.z; col[k][3] = q.w;
+      }
 #pragma unroll
       for (int fy = 0; fy < 4; fy++)
       {
         if (fx == 0 && fy == 0) continue;           // integer plane already in place
-        int v;
-        if (fy == 0)
-        {
-          // filterCopy(isFirst=false, isLast=true) (:127-147)
-          v = (int16_t)((col[3] + 8192 + (1 << (head - 1))) >> head);
-        }
-        else
-        {
-          int sum = 0;
+        int v[4];
 #pragma unroll
-          for (int k = 0; k < 8; k++) sum += col[k] * c_luma_taps[fy][k];
-          v = (int16_t)((sum + off2) >> shift2);
+        for (int e = 0; e < 4; e++)
+        {
+          if (fy == 0)
+          {
+            // filterCopy(isFirst=false, isLast=true) (:127-147)
+            v[e] = (int16_t)((col[3][e] + 8192 + (1 << (head - 1))) >> head);
+          }
+          else
+          {
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += col[k][e] * c_luma_taps[fy][k];
+            v[e] = (int16_t)((sum + off2) >> shift2);
+          }
+          v[e] = min(max_val, max(0, v[e]));
         }
-        v = min(max_val, max(0, v));
-        planes[(size_t)(fy * 4 + fx) * plane_elems + (size_t)y * pitch + x] = (Px)v;
+        Px* out = planes + (size_t)(fy * 4 + fx) * plane_elems + (size_t)y * pitch + x;
+        if (sizeof(Px) == 1) *(uint32_t*)out = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+        else *(uint2*)out = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
       }
     }
   }

@@ -157,6 +157,53 @@ def test_frac_only(bit_depth):
     _run(bit_depth, "frac", 400)
 
 
+def test_full_search_window_by_tma():
+    """xPatternSearch with the window staged by TMA (cp.async.bulk.tensor, me_full_impl.cuh) and by per-thread loads: same
+    bytes, equal to the oracle -- windows clipped at every picture border, every PU shape, search ranges 4 .. 64."""
+    rng = np.random.default_rng(31)
+    fr = _frames(8, 3, noise=True)
+    jobs, _, _ = _random_jobs(rng, 240, 8, "fs", 2)
+    pads = [padded_ref(fr[k]) for k in range(2)]
+    exp = oracle_me(jobs, pads, fr[2], 8)
+    with hmgpu.Context(W, H, 8, 2) as ctx:
+        for k in range(2):
+            ctx.ref_upload(k, fr[k])
+        ctx.org_upload(fr[2])
+        got = ctx.me_search(jobs)
+        assert_results_equal(got, exp, jobs)
+        ctx.set_option("fs_tma", 0)
+        assert ctx.me_search(jobs).tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("noise", [False, True])
+def test_fractional_kernels_agree(noise):
+    """The packed fractional kernels (me_frac2.cu) against the oracle and against the generic kernel (me_frac.cu): all PU shapes
+    incl. 64x64, SAD and SATD, blocks hanging over every picture border, fractional-only jobs next to full searches."""
+    rng = np.random.default_rng(123)
+    fr = _frames(8, 4, noise)
+    org = fr[3]
+    jobs, _, _ = _random_jobs(rng, 3000, 8, "frac", 3)
+    tz, _, _ = _random_jobs(rng, 600, 8, "tz", 3)
+    jobs = np.concatenate([jobs, tz])
+    # integer positions at the clip bounds: the candidate blocks reach the outermost samples the padding holds
+    for i in range(0, 3000, 9):
+        j = jobs[i]
+        j["start_x"] = int([j["win_l"], j["win_r"]][(i // 9) & 1])
+        j["start_y"] = int([j["win_t"], j["win_b"]][(i // 18) & 1])
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    exp = oracle_me(jobs, pads, org, 8)
+    with hmgpu.Context(W, H, 8, 3) as ctx:
+        for k in range(3):
+            ctx.ref_upload(k, fr[k])
+        ctx.org_upload(org)
+        got = ctx.me_search(jobs)
+        assert_results_equal(got, exp, jobs)
+        ctx.set_option("frac_overlap", 0)
+        assert ctx.me_search(jobs).tobytes() == got.tobytes()
+        ctx.set_option("frac_v1", 1)
+        assert ctx.me_search(jobs).tobytes() == got.tobytes()
+
+
 @pytest.mark.parametrize("bit_depth", [8, 10])
 @pytest.mark.parametrize("mode", ["tz", "fs", "frac"])
 def test_bipred_key_pattern_blocks(bit_depth, mode):
