@@ -20,6 +20,7 @@ int hmgpu_launch_full(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, co
 int hmgpu_launch_frac(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, const int16_t* d_org_blocks,
                       hmgpu_me_result* d_results, bool any_frac);
 int hmgpu_launch_frac_packed(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, hmgpu_me_result* d_results, bool any_frac);
+int hmgpu_launch_frac_window(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, hmgpu_me_result* d_results, bool any_frac);
 int hmgpu_launch_single(hmgpu_ctx* ctx, const HmgpuJobPack& pack, int n_jobs, const int16_t* d_org_blocks,
                         HmgpuMailSlot* d_slots, uint32_t ticket, bool any_org_block, int max_win_bytes,
                         unsigned long long* trace);
@@ -122,6 +123,8 @@ static void tuning_from_env(HmgpuTuning* t)
   t->tz_p2          = env_int("HMGPU_TZ_P2", 0);
   t->frac_v1        = env_int("HMGPU_FRAC_V1", 0);
   t->frac_overlap   = env_int("HMGPU_FRAC_OVERLAP", 1);
+  t->frac_win       = env_int("HMGPU_FRAC_WIN", 1);
+  t->frac_win_min   = env_int("HMGPU_FRAC_WIN_MIN", 4096);
   t->fs_tma         = env_int("HMGPU_FS_TMA", 1);
   t->pipe_chunk     = env_int("HMGPU_PIPE_CHUNK", 0);
   t->pipeline       = !env_int("HMGPU_NO_PIPELINE", 0);
@@ -136,7 +139,7 @@ struct TuneName { const char* name; int HmgpuTuning::* field; };
 static const TuneName k_tune_names[] = {
   { "tz_thread", &HmgpuTuning::tz_thread }, { "tz_thread_min", &HmgpuTuning::tz_thread_min }, { "tz_merge", &HmgpuTuning::tz_merge },
   { "tz_carve", &HmgpuTuning::tz_carve }, { "tz_p2", &HmgpuTuning::tz_p2 }, { "frac_v1", &HmgpuTuning::frac_v1 },
-  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "fs_tma", &HmgpuTuning::fs_tma }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipeline", &HmgpuTuning::pipeline },
+  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "frac_win", &HmgpuTuning::frac_win }, { "frac_win_min", &HmgpuTuning::frac_win_min }, { "fs_tma", &HmgpuTuning::fs_tma }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipeline", &HmgpuTuning::pipeline },
   { "fastpath", &HmgpuTuning::fastpath }, { "server", &HmgpuTuning::server }, { "server_idle_us", &HmgpuTuning::server_idle_us },
   { "trace", &HmgpuTuning::trace }, { "server_stats", &HmgpuTuning::server_stats } };
 
@@ -236,7 +239,11 @@ int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
   if (any_full && (rc = hmgpu_launch_full(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_org_block, max_win_bytes))) return rc;
   if (ctx->px_bytes == 1 && !any_org_block && !ctx->tune.frac_v1)
   {
-    if ((rc = hmgpu_launch_frac_packed(ctx, d_jobs, n_jobs, d_results, any_frac))) return rc;
+    if (ctx->tune.frac_win && n_jobs >= ctx->tune.frac_win_min && ctx->planes_all)
+    {
+      if ((rc = hmgpu_launch_frac_window(ctx, d_jobs, n_jobs, d_results, any_frac))) return rc;
+    }
+    else if ((rc = hmgpu_launch_frac_packed(ctx, d_jobs, n_jobs, d_results, any_frac))) return rc;
   }
   else if ((rc = hmgpu_launch_frac(ctx, d_jobs, n_jobs, d_org_blocks, d_results, any_frac))) return rc;
   return HMGPU_OK;
@@ -470,6 +477,7 @@ void hmgpu_destroy(hmgpu_ctx* ctx)
   if (ctx->d_org) hmgpu_dfree(ctx->d_org);
   if (ctx->planes_all) hmgpu_dfree(ctx->planes_all);
   free(ctx->h_tmaps);
+  free(ctx->h_fw_tmap);
   if (ctx->d_stage) hmgpu_dfree(ctx->d_stage);
   if (ctx->d_work) hmgpu_dfree(ctx->d_work);
   if (ctx->d_tzlist) hmgpu_dfree(ctx->d_tzlist);

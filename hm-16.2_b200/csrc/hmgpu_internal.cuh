@@ -67,6 +67,8 @@ struct HmgpuTuning
   int frac_v1;          // HMGPU_FRAC_V1: generic fractional kernels for 8-bit pictures too
   int fs_tma;           // HMGPU_FS_TMA: the full-search window is staged by TMA (cp.async.bulk.tensor) instead of per-thread loads
   int frac_overlap;     // HMGPU_FRAC_OVERLAP: 8x8 / 4x4 tile kernels side by side
+  int frac_win;         // HMGPU_FRAC_WIN: fractional stage of large 8-bit batches by CTU groups with TMA-staged windows (me_fracw.cu)
+  int frac_win_min;     // HMGPU_FRAC_WIN_MIN: batch size from which it is used
   int pipe_chunk;       // HMGPU_PIPE_CHUNK: jobs per chunk of the pipelined batch path (0: a quarter of the batch)
   int pipeline;         // !HMGPU_NO_PIPELINE
   int fastpath;         // !HMGPU_NO_FASTPATH
@@ -91,6 +93,7 @@ struct hmgpu_ctx
   void* d_org; int org_pitch;   // source picture, Px
   void* planes_all; size_t slot_bytes;   // the phase planes of all reference slots (one allocation), bytes per slot
   void* h_tmaps;                         // CUtensorMap[16] over planes_all for the full-search window (me_full.cu), built on first use
+  void* h_fw_tmap;                       // CUtensorMap over planes_all for the windows of the fractional stage (me_fracw.cu)
   // staging (grow on demand)
   void* h_pin; size_t h_pin_bytes;     // pinned host
   void* d_stage; size_t d_stage_bytes; // device
@@ -213,7 +216,7 @@ size_t hmgpu_internal_mailbox_bytes(void);
 }
 
 // bits of hmgpu_ctx::attr_done
-enum { HMGPU_ATTR_SINGLE = 1, HMGPU_ATTR_SERVER = 2, HMGPU_ATTR_FULL = 4, HMGPU_ATTR_TZT = 8, HMGPU_ATTR_TZ_CARVE = 16, HMGPU_ATTR_FRAC3 = 32 };
+enum { HMGPU_ATTR_SINGLE = 1, HMGPU_ATTR_SERVER = 2, HMGPU_ATTR_FULL = 4, HMGPU_ATTR_TZT = 8, HMGPU_ATTR_TZ_CARVE = 16, HMGPU_ATTR_FRAC3 = 32, HMGPU_ATTR_FRACW = 64 };
 
 #define HMGPU_CUDA(ctx, call)                                                              \
   do {                                                                                     \

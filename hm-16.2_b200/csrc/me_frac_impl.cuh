@@ -76,3 +76,77 @@ __device__ __forceinline__ uint32_t tile_dist(const hmgpu_me_job& jb, const int1
   return s;
 }
 
+// ---- packed-byte SATD of one tile (shared by me_frac2.cu and me_fracw.cu) ---------------------------------------------
+// sign patterns of the 8-point Hadamard (Sylvester order): s_kj = (-1)^popc(k & j); +1 -> 0x01, -1 -> 0xff
+__host__ __device__ constexpr uint32_t had_pat4(int k, bool neg)
+{
+  uint32_t w = 0;
+  for (int j = 0; j < 4; j++)
+  {
+    int s = 0;
+    for (int b = 0; b < 3; b++) s ^= ((k >> b) & (j >> b) & 1);
+    const bool minus = (s != 0) != neg;
+    w |= (minus ? 0xffu : 0x01u) << (8 * j);
+  }
+  return w;
+}
+template <int K, bool NEG> struct HadPat
+{
+  static constexpr uint32_t lo = had_pat4(K, NEG);
+  static constexpr uint32_t hi = had_pat4(K, NEG != ((K & 4) != 0));
+};
+
+// out[k] = init[k] + (NEG ? -1 : 1) * sum_j s_kj p_j  for one row of 8 packed pixels (w0 = p0..3, w1 = p4..7)
+template <bool NEG>
+__device__ __forceinline__ void had_row8(uint32_t w0, uint32_t w1, const int* init, int* out)
+{
+  out[0] = hm_dp4a_us(w1, HadPat<0, NEG>::hi, hm_dp4a_us(w0, HadPat<0, NEG>::lo, init[0]));
+  out[1] = hm_dp4a_us(w1, HadPat<1, NEG>::hi, hm_dp4a_us(w0, HadPat<1, NEG>::lo, init[1]));
+  out[2] = hm_dp4a_us(w1, HadPat<2, NEG>::hi, hm_dp4a_us(w0, HadPat<2, NEG>::lo, init[2]));
+  out[3] = hm_dp4a_us(w1, HadPat<3, NEG>::hi, hm_dp4a_us(w0, HadPat<3, NEG>::lo, init[3]));
+  out[4] = hm_dp4a_us(w1, HadPat<4, NEG>::hi, hm_dp4a_us(w0, HadPat<4, NEG>::lo, init[4]));
+  out[5] = hm_dp4a_us(w1, HadPat<5, NEG>::hi, hm_dp4a_us(w0, HadPat<5, NEG>::lo, init[5]));
+  out[6] = hm_dp4a_us(w1, HadPat<6, NEG>::hi, hm_dp4a_us(w0, HadPat<6, NEG>::lo, init[6]));
+  out[7] = hm_dp4a_us(w1, HadPat<7, NEG>::hi, hm_dp4a_us(w0, HadPat<7, NEG>::lo, init[7]));
+}
+template <bool NEG>
+__device__ __forceinline__ void had_row4(uint32_t w0, const int* init, int* out)
+{
+  out[0] = hm_dp4a_us(w0, HadPat<0, NEG>::lo, init[0]);
+  out[1] = hm_dp4a_us(w0, HadPat<1, NEG>::lo, init[1]);
+  out[2] = hm_dp4a_us(w0, HadPat<2, NEG>::lo, init[2]);
+  out[3] = hm_dp4a_us(w0, HadPat<3, NEG>::lo, init[3]);
+}
+
+// vertical 8-point pass over the 8 columns of d[64] + sum of absolute values, rounding (s+2)>>2
+__device__ __forceinline__ uint32_t had_cols8_abs(int* d)
+{
+  uint32_t s = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+  {
+    int* v = d + c;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const int a = v[i * 8], b = v[(i + 4) * 8]; v[i * 8] = a + b; v[(i + 4) * 8] = a - b; }
+#pragma unroll
+    for (int i = 0; i < 8; i += 4)
+#pragma unroll
+      for (int j = i; j < i + 2; j++) { const int a = v[j * 8], b = v[(j + 2) * 8]; v[j * 8] = a + b; v[(j + 2) * 8] = a - b; }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) s += 2u * (uint32_t)max(hm_abs(v[i * 8]), hm_abs(v[(i + 1) * 8]));
+  }
+  return (s + 2) >> 2;
+}
+__device__ __forceinline__ uint32_t had_cols4_abs(int* d)
+{
+  uint32_t s = 0;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+  {
+    int* v = d + c;
+    const int a0 = v[0] + v[8], a1 = v[4] + v[12], a2 = v[0] - v[8], a3 = v[4] - v[12];
+    s += 2u * (uint32_t)max(hm_abs(a0), hm_abs(a1)) + 2u * (uint32_t)max(hm_abs(a2), hm_abs(a3));
+  }
+  return (s + 1) >> 1;
+}
+

@@ -202,6 +202,47 @@ def test_fractional_kernels_agree(noise):
         assert ctx.me_search(jobs).tobytes() == got.tobytes()
         ctx.set_option("frac_v1", 1)
         assert ctx.me_search(jobs).tobytes() == got.tobytes()
+        # the CTU-group kernel with TMA-staged windows (me_fracw.cu; by default only for batches of >= 4096 jobs): random vectors
+        # put most of these jobs on its slow path (footprint outside the group's window), the rest on the fast path
+        ctx.set_option("frac_v1", 0)
+        ctx.set_option("frac_win_min", 1)
+        assert ctx.me_search(jobs).tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("spread", [0, 3, 40])
+def test_fractional_window_kernel(spread):
+    """me_fracw.cu on the jobs of whole pictures (every PU of every CTU x 3 references, fractional-only at integer vectors spread
+    around a global motion): windows staged by TMA, groups larger than one pass (duplicated jobs), picture-border CTUs, SAD-mode
+    and lossless jobs mixed in; against the oracle and against the per-tile kernels (me_frac2.cu)."""
+    rng = np.random.default_rng(5 + spread)
+    fr = _frames(8, 4, True)
+    org = fr[3]
+    jobs = worklist.frame_jobs(W, H, n_refs=3, seed=3 + spread)
+    jobs["flags"] &= ~np.uint8(hmgpu.F_INTEGER)
+    n = len(jobs)
+    mvx = -3 * (jobs["ref_slot"].astype(np.int64) + 1) + rng.integers(-spread, spread + 1, n)
+    mvy = 2 * (jobs["ref_slot"].astype(np.int64) + 1) + rng.integers(-spread, spread + 1, n)
+    jobs["start_x"] = np.clip(mvx, jobs["win_l"], jobs["win_r"])
+    jobs["start_y"] = np.clip(mvy, jobs["win_t"], jobs["win_b"])
+    # SAD instead of SATD, lossless: the slow path of the kernel
+    jobs["flags"][::17] &= ~np.uint8(hmgpu.F_HADME)
+    jobs["flags"][5::29] |= np.uint8(hmgpu.F_LOSSLESS)
+    # one CTU with more jobs than a pass holds
+    first_ctu = jobs[(jobs["pu_x"] < 64) & (jobs["pu_y"] < 64) & (jobs["ref_slot"] == 0)]
+    jobs = np.concatenate([jobs, first_ctu, first_ctu, first_ctu])
+    assert len(jobs) >= 4096
+    with hmgpu.Context(W, H, 8, 3) as ctx:
+        for k in range(3):
+            ctx.ref_upload(k, fr[k])
+        ctx.org_upload(org)
+        got = ctx.me_search(jobs)
+        ctx.set_option("frac_win", 0)
+        ref = ctx.me_search(jobs)
+    bad = np.nonzero(got.view(np.uint8).reshape(len(jobs), -1) != ref.view(np.uint8).reshape(len(jobs), -1))[0]
+    assert bad.size == 0, "first differing job %d: %s vs %s (%s)" % (bad[0], got[bad[0]], ref[bad[0]], jobs[bad[0]])
+    sample = rng.choice(len(jobs), 1500, replace=False)
+    pads = [padded_ref(fr[k]) for k in range(3)]
+    assert_results_equal(got[sample], oracle_me(jobs[sample], pads, org, 8), jobs[sample])
 
 
 @pytest.mark.parametrize("bit_depth", [8, 10])
