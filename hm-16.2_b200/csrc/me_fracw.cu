@@ -40,6 +40,7 @@
 #define FW_T4MAX 3072                  // 4x4 tiles per pass
 #define FW_XOFF 32                     // the window starts this far left of (CTU + mean vector), before the 16-byte alignment
 #define FW_YOFF 16
+#define FW_ORG_PITCH 17                // words per row of the staged source CTU (odd: rows start on different banks)
 
 enum { FWF_FAST = 1, FWF_SATD = 2, FWF_T8 = 4 };
 
@@ -57,14 +58,14 @@ struct __align__(16) FwJob
 struct FwMisc
 {
   unsigned long long bar;
-  int group, sumx, sumy, m, n_slow;
+  int group, sumx, sumy, m, n_slow, next;
   uint32_t warp_tot[FW_THREADS / 32];
 };
 
 struct FwSmem
 {
   unsigned char planes[FW_NBUF][FW_PLANE_BYTES];
-  uint32_t org[64 * 16];
+  uint32_t org[64 * FW_ORG_PITCH];
   uint32_t acc[9][FW_GMAX];
   FwJob job[FW_GMAX];
   uint32_t jidx[FW_GMAX];
@@ -193,70 +194,98 @@ __device__ __forceinline__ uint32_t fw_tile_satd(const unsigned char* win, int x
   return TS == 8 ? had_cols8_abs(d) : had_cols4_abs(d);
 }
 
-// the work items of one list (8x8 or 4x4 tiles) in one phase: item = (tile, group of CPI candidates)
+// one warp-wide batch of work items of one list (8x8 or 4x4 tiles) in one phase: item = (tile, group of CPI candidates), idx = the
+// lane's item (items of one candidate group are consecutive: the lanes of a warp hold consecutive tiles)
 template <int TS, int PHASE>
-__device__ __forceinline__ void fw_run_list(FwSmem& S, const uint16_t* tab, int n_tiles)
+__device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_tiles, int idx, int lane)
 {
   constexpr int CPI = PHASE ? 2 : 3;            // candidates per item
   constexpr int NGRP = PHASE ? 4 : 3;           // items per tile (quarter-pel: candidates 1..8, the centre is reused)
-  const int total = n_tiles * NGRP;
-  const int lane = threadIdx.x & 31;
-  for (int base = (threadIdx.x & ~31); base < total; base += FW_THREADS)
+  const bool valid = idx < n_tiles * NGRP;
+  uint32_t ji = 0xffffu;
+  uint32_t v[CPI];
+#pragma unroll
+  for (int k = 0; k < CPI; k++) v[k] = 0;
+  int grp = 0;
+  if (valid)
   {
-    const int idx = base + lane;
-    const bool valid = idx < total;
-    uint32_t ji = 0xffffu + (uint32_t)lane;     // distinct dummy keys for idle lanes
-    uint32_t v[CPI];
-#pragma unroll
-    for (int k = 0; k < CPI; k++) v[k] = 0;
-    int grp = 0;
-    if (valid)
+    grp = (idx >= n_tiles) + (idx >= 2 * n_tiles) + (NGRP > 3 ? (idx >= 3 * n_tiles) : 0);
+    const uint32_t e = tab[idx - grp * n_tiles];
+    ji = e >> 6;
+    const int t = (int)(e & 63u);
+    const FwJob jb = S.job[ji];
+    const int hx = PHASE ? (int)(S.hsel[ji] & 3) - 1 : 0, hy = PHASE ? (int)(S.hsel[ji] >> 2) - 1 : 0;
+    const int tw = jb.w / TS;
+    const int ty = (t * jb.inv_tw) >> 15, tx = t - ty * tw;
+    const int c = TS == 8 ? (2 * ty) & 7 : ty & 3;
+    uint32_t ow[TS][TS / 4];
     {
-      grp = idx / n_tiles;
-      const uint32_t e = tab[idx - grp * n_tiles];
-      ji = e >> 6;
-      const int t = (int)(e & 63u);
-      const FwJob jb = S.job[ji];
-      const int hx = PHASE ? (int)(S.hsel[ji] & 3) - 1 : 0, hy = PHASE ? (int)(S.hsel[ji] >> 2) - 1 : 0;
-      const int tw = jb.w / TS;
-      const int ty = (t * jb.inv_tw) >> 15, tx = t - ty * tw;
-      const int c = TS == 8 ? (2 * ty) & 7 : ty & 3;
-      uint32_t ow[TS][TS / 4];
-      {
-        const uint32_t* o = S.org + (jb.ry + ty * TS) * 16 + ((jb.rx + tx * TS) >> 2);
+      const uint32_t* o = S.org + (jb.ry + ty * TS) * FW_ORG_PITCH + ((jb.rx + tx * TS) >> 2);
 #pragma unroll
-        for (int r = 0; r < TS; r++)
+      for (int r = 0; r < TS; r++)
 #pragma unroll
-          for (int w = 0; w < TS / 4; w++) ow[r][w] = o[(r ^ c) * 16 + w];
-      }
-      const int x0 = jb.xw + tx * TS, y0 = jb.yw + ty * TS;
-#pragma unroll
-      for (int k = 0; k < CPI; k++)
-      {
-        const int cand = PHASE ? 1 + grp * CPI + k : grp * CPI + k;
-        int qx, qy, slot;
-        if (PHASE == 0)
-        {
-          qx = 2 * c_refine_h[cand][0]; qy = 2 * c_refine_h[cand][1];
-          slot = ((qy & 3) >> 1) * 2 + ((qx & 3) >> 1);
-        }
-        else
-        {
-          qx = 2 * hx + c_refine_q[cand][0]; qy = 2 * hy + c_refine_q[cand][1];
-          slot = fw_slot((qy & 3) * 4 + (qx & 3));
-        }
-        v[k] = fw_tile_satd<TS>(S.planes[slot], x0 + (qx >> 2), y0 + (qy >> 2), ow, c);
-      }
+        for (int w = 0; w < TS / 4; w++) ow[r][w] = o[(r ^ c) * FW_ORG_PITCH + w];
     }
-    // the lanes of a (job, candidate group) add up their tiles: one shared-memory atomic per job and candidate
-    const uint32_t same = __match_any_sync(0xffffffffu, ji | ((uint32_t)grp << 16));
-    const bool head = valid && (lane == __ffs(same) - 1);
+    const int x0 = jb.xw + tx * TS, y0 = jb.yw + ty * TS;
 #pragma unroll
     for (int k = 0; k < CPI; k++)
     {
-      const uint32_t s = __reduce_add_sync(same, v[k]);
-      if (head) atomicAdd(&S.acc[PHASE ? 1 + grp * CPI + k : grp * CPI + k][ji], s);
+      const int cand = PHASE ? 1 + grp * CPI + k : grp * CPI + k;
+      int qx, qy, slot;
+      if (PHASE == 0)
+      {
+        qx = 2 * c_refine_h[cand][0]; qy = 2 * c_refine_h[cand][1];
+        slot = ((qy & 3) >> 1) * 2 + ((qx & 3) >> 1);
+      }
+      else
+      {
+        qx = 2 * hx + c_refine_q[cand][0]; qy = 2 * hy + c_refine_q[cand][1];
+        slot = fw_slot((qy & 3) * 4 + (qx & 3));
+      }
+      v[k] = fw_tile_satd<TS>(S.planes[slot], x0 + (qx >> 2), y0 + (qy >> 2), ow, c);
     }
+  }
+  // The lanes of a (job, candidate group) add up their tiles with a segmented shuffle reduction -- they are consecutive lanes --
+  // and the first lane of the run issues one shared-memory atomic per candidate.  (__reduce_add_sync on the match mask was 29 %
+  // of the kernel's stall samples: REDUX with a partial mask is a loop.)
+  const uint32_t key = ji | ((uint32_t)grp << 16);
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = lane == 0 || prev != key;
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const uint32_t above = heads & ~((2u << lane) - 1u);      // heads at higher lanes (lane 31: 2u << 31 == 0, mask of all lanes)
+  const int run_end = above ? __ffs(above) - 2 : 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+#pragma unroll
+    for (int k = 0; k < CPI; k++)
+    {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, v[k], o);
+      if (lane + o <= run_end) v[k] += t;
+    }
+  }
+  if (head && valid)
+  {
+#pragma unroll
+    for (int k = 0; k < CPI; k++) atomicAdd(&S.acc[PHASE ? 1 + grp * CPI + k : grp * CPI + k][ji], v[k]);
+  }
+}
+
+// all the fast work of one phase: the warps draw batches of 32 items from a shared counter, 8x8 tiles first (the heavier items)
+template <int PHASE>
+__device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
+{
+  constexpr int NGRP = PHASE ? 4 : 3;
+  const int lane = threadIdx.x & 31;
+  const int end8 = (n8 * NGRP + 31) & ~31, end = end8 + n4 * NGRP;
+  for (;;)
+  {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&S.misc.next, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= end) break;
+    if (base < end8) fw_items<8, PHASE>(S, S.t8, n8, base + lane, lane);
+    else fw_items<4, PHASE>(S, S.t4, n4, base - end8 + lane, lane);
   }
 }
 
@@ -329,13 +358,13 @@ fracw_group_kernel(const hmgpu_me_job* __restrict__ jobs, hmgpu_me_result* __res
     for (int i = tid; i < 64 * 16; i += FW_THREADS)
     {
       const int y = ctu_y + (i >> 4), x = ctu_x + (i & 15) * 4;
-      S.org[i] = (y < pic_h && x + 4 <= org.pitch) ? __ldg((const uint32_t*)((const uint8_t*)org.base + (size_t)y * org.pitch + x)) : 0u;
+      S.org[(i >> 4) * FW_ORG_PITCH + (i & 15)] = (y < pic_h && x + 4 <= org.pitch) ? __ldg((const uint32_t*)((const uint8_t*)org.base + (size_t)y * org.pitch + x)) : 0u;
     }
 
     for (int c0 = 0; c0 < n;)
     {
       const int cnt = min(FW_GMAX, n - c0);
-      if (tid == 0) { S.misc.sumx = 0; S.misc.sumy = 0; S.misc.m = cnt; S.misc.n_slow = 0; }
+      if (tid == 0) { S.misc.sumx = 0; S.misc.sumy = 0; S.misc.m = cnt; S.misc.n_slow = 0; S.misc.next = 0; }
       __syncthreads();
       // ---- A: the jobs of the pass, their integer vectors
       {
@@ -441,13 +470,13 @@ fracw_group_kernel(const hmgpu_me_job* __restrict__ jobs, hmgpu_me_result* __res
       }
       // ---- D: half-pel candidates
       fw_mbar_wait(bar, parity); parity ^= 1;
-      fw_run_list<8, 0>(S, S.t8, n8);
-      fw_run_list<4, 0>(S, S.t4, n4);
+      fw_run_phase<0>(S, n8, n4);
       fw_run_slow<0>(S, jobs, refs, org);
       __syncthreads();
       // the windows of the twelve other planes replace them (every thread has left the half-pel pass)
       if (tid == 0)
       {
+        S.misc.next = 0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(12 * FW_PLANE_BYTES)) : "memory");
         for (int p = 0; p < 16; p++)
@@ -476,8 +505,7 @@ fracw_group_kernel(const hmgpu_me_job* __restrict__ jobs, hmgpu_me_result* __res
       __syncthreads();
       // ---- F: quarter-pel candidates
       fw_mbar_wait(bar, parity); parity ^= 1;
-      fw_run_list<8, 1>(S, S.t8, n8);
-      fw_run_list<4, 1>(S, S.t4, n4);
+      fw_run_phase<1>(S, n8, n4);
       fw_run_slow<1>(S, jobs, refs, org);
       __syncthreads();
       // ---- G: quarter-pel winner, result
