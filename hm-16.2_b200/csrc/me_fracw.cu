@@ -89,16 +89,22 @@ __global__ void fracw_bin_kernel(const hmgpu_me_job* __restrict__ jobs, int n_jo
                                  uint32_t* __restrict__ bin_count, int ctus_x, int n_ctus)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_jobs) return;
-  const hmgpu_me_job jb = jobs[j];
-  if (!(jb.flags & HMGPU_F_INTEGER))
+  int bin = -1 - (int)(threadIdx.x & 31);                 // lanes without a job to count: distinct keys
+  if (j < n_jobs)
   {
-    hmgpu_me_result r;
-    r.int_x = jb.start_x; r.int_y = jb.start_y; r.int_sad = 0;
-    r.half_x = r.half_y = r.qter_x = r.qter_y = 0; r.frac_cost = 0; r.n_cand = 0;
-    results[j] = r;
+    const hmgpu_me_job jb = jobs[j];
+    if (!(jb.flags & HMGPU_F_INTEGER))
+    {
+      hmgpu_me_result r;
+      r.int_x = jb.start_x; r.int_y = jb.start_y; r.int_sad = 0;
+      r.half_x = r.half_y = r.qter_x = r.qter_y = 0; r.frac_cost = 0; r.n_cand = 0;
+      results[j] = r;
+    }
+    if (jb.flags & HMGPU_F_FRAC) bin = fw_bin(jb, ctus_x, n_ctus);
   }
-  if (jb.flags & HMGPU_F_FRAC) atomicAdd(&bin_count[fw_bin(jb, ctus_x, n_ctus)], 1u);
+  // neighbouring jobs are the partitions of one CU x the reference pictures: a warp counts into a handful of bins
+  const uint32_t same = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&bin_count[bin], (uint32_t)__popc(same));
 }
 
 // one CTA: exclusive scan of the job counts of the bins and the list of the non-empty bins; totals[0] = jobs, totals[1] = groups
@@ -136,11 +142,19 @@ __global__ void fracw_scatter_kernel(const hmgpu_me_job* __restrict__ jobs, int 
                                      uint32_t* __restrict__ bin_fill, uint32_t* __restrict__ sorted, int ctus_x, int n_ctus)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_jobs) return;
-  const hmgpu_me_job jb = jobs[j];
-  if (!(jb.flags & HMGPU_F_FRAC)) return;
-  const int b = fw_bin(jb, ctus_x, n_ctus);
-  sorted[bin_start[b] + atomicAdd(&bin_fill[b], 1u)] = (uint32_t)j;
+  const int lane = threadIdx.x & 31;
+  int b = -1 - lane;
+  if (j < n_jobs)
+  {
+    const hmgpu_me_job jb = jobs[j];
+    if (jb.flags & HMGPU_F_FRAC) b = fw_bin(jb, ctus_x, n_ctus);
+  }
+  const uint32_t same = __match_any_sync(0xffffffffu, b);
+  const int leader = __ffs(same) - 1;
+  uint32_t pos = 0;
+  if (b >= 0 && lane == leader) pos = bin_start[b] + atomicAdd(&bin_fill[b], (uint32_t)__popc(same));
+  pos = __shfl_sync(0xffffffffu, pos, leader);
+  if (b >= 0) sorted[pos + __popc(same & ((1u << lane) - 1u))] = (uint32_t)j;
 }
 
 // ---- TMA / mbarrier ---------------------------------------------------------------------------------------------------------
@@ -194,22 +208,114 @@ __device__ __forceinline__ uint32_t fw_tile_satd(const unsigned char* win, int x
   return TS == 8 ? had_cols8_abs(d) : had_cols4_abs(d);
 }
 
+// ---- one tile, TWO candidates at once --------------------------------------------------------------------------------------
+// The horizontal pass leaves (H(org) - H(ref B)) * 65536 + (H(org) - H(ref A)) in one register per coefficient: the IDP.4A chain of
+// candidate A simply continues on the shifted result of candidate B, and the row transform of the source tile is computed once
+// for both.  A register then holds the pair as the INTEGER 65536 * hi + lo with lo signed ("carry-save" halves: the raw upper
+// half is hi - (lo < 0)); plain 32-bit additions and subtractions act on both halves at once without interference as long as
+// |lo| < 32768 -- the coefficients of an 8x8 Hadamard transform of 9-bit differences stay below 16 384.  The last butterfly
+// stage adds 0x80008000, which turns both halves into offset-binary values, so that VIMNMX.U16x2 compares them as signed
+// numbers; |a + b| + |a - b| = 2 max(|a|, |b|) = 2 max(max(a, b), -min(a, b)) folds the final stage into two packed maxima, one
+// packed minimum and one subtraction (-v in offset binary is 0x10000 - v per half, i.e. 0x00010000 - x for the pair).
+#define FW_BIAS 0x80008000u
+__device__ __forceinline__ uint32_t fw_pair_absmax(uint32_t ba, uint32_t bb)
+{
+  const uint32_t hi = __vmaxu2(ba, bb), lo = __vminu2(ba, bb);
+  return __vmaxu2(hi, 0x00010000u - lo);        // offset-binary max(|a|, |b|) of both halves
+}
+
+template <int TS>
+__device__ __forceinline__ void fw_tile_satd_pair(const unsigned char* win_a, int xa, int ya, const unsigned char* win_b, int xb, int yb,
+                                                  const uint32_t (&ow)[TS][TS / 4], int c, uint32_t& out_a, uint32_t& out_b)
+{
+  const int sha = (xa & 3) * 8, shb = (xb & 3) * 8;
+  const uint32_t* qa = (const uint32_t*)(win_a + ya * FW_WW + (xa & ~3));
+  const uint32_t* qb = (const uint32_t*)(win_b + yb * FW_WW + (xb & ~3));
+  int x[TS * TS];
+  int zero[TS];
+#pragma unroll
+  for (int k = 0; k < TS; k++) zero[k] = 0;
+#pragma unroll
+  for (int r = 0; r < TS; r++)
+  {
+    const uint32_t* ra = qa + (r ^ c) * (FW_WW / 4);
+    const uint32_t* rb = qb + (r ^ c) * (FW_WW / 4);
+    int h[TS], t[TS];
+    if (TS == 8)
+    {
+      const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], b0 = rb[0], b1 = rb[1], b2 = rb[2];
+      had_row8<false>(ow[r][0], ow[r][1], zero, h);
+      had_row8<true>(__funnelshift_r(b0, b1, shb), __funnelshift_r(b1, b2, shb), h, t);
+#pragma unroll
+      for (int k = 0; k < TS; k++) t[k] = t[k] * 65536 + h[k];
+      had_row8<true>(__funnelshift_r(a0, a1, sha), __funnelshift_r(a1, a2, sha), t, x + r * TS);
+    }
+    else
+    {
+      const uint32_t a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1];
+      had_row4<false>(ow[r][0], zero, h);
+      had_row4<true>(__funnelshift_r(b0, b1, shb), h, t);
+#pragma unroll
+      for (int k = 0; k < TS; k++) t[k] = t[k] * 65536 + h[k];
+      had_row4<true>(__funnelshift_r(a0, a1, sha), t, x + r * TS);
+    }
+  }
+  uint32_t sum = 0;                              // packed: both halves stay below 65 536
+  if (TS == 8)
+  {
+    uint32_t part[4] = { 0, 0, 0, 0 };           // each collects 8 maxima of at most 8 160
+#pragma unroll
+    for (int col = 0; col < 8; col++)
+    {
+      int* v = x + col;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { const int a = v[i * 8], b = v[(i + 4) * 8]; v[i * 8] = a + b; v[(i + 4) * 8] = a - b; }
+      uint32_t m[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 4)
+      {
+        // second stage with the bias folded in, third stage inside the maxima
+        const uint32_t p0 = (uint32_t)(v[i * 8] + v[(i + 2) * 8]) + FW_BIAS, p2 = (uint32_t)(v[i * 8] - v[(i + 2) * 8]) + FW_BIAS;
+        const uint32_t p1 = (uint32_t)(v[(i + 1) * 8] + v[(i + 3) * 8]) + FW_BIAS, p3 = (uint32_t)(v[(i + 1) * 8] - v[(i + 3) * 8]) + FW_BIAS;
+        m[i / 2] = fw_pair_absmax(p0, p1);
+        m[i / 2 + 1] = fw_pair_absmax(p2, p3);
+      }
+      // two offset-binary halves + two more - 0x00010000: the biases leave through the carries (see the file header)
+      part[col & 3] += (m[0] + m[1] + 0xffff0000u) + (m[2] + m[3] + 0xffff0000u);
+    }
+    const uint32_t lo = (part[0] & 0xffffu) + (part[1] & 0xffffu) + (part[2] & 0xffffu) + (part[3] & 0xffffu);
+    const uint32_t hi = (part[0] >> 16) + (part[1] >> 16) + (part[2] >> 16) + (part[3] >> 16);
+    out_a = (2u * lo + 2) >> 2; out_b = (2u * hi + 2) >> 2;
+  }
+  else
+  {
+#pragma unroll
+    for (int col = 0; col < 4; col++)
+    {
+      const int* v = x + col;
+      const uint32_t a0 = (uint32_t)(v[0] + v[8]) + FW_BIAS, a1 = (uint32_t)(v[4] + v[12]) + FW_BIAS;
+      const uint32_t a2 = (uint32_t)(v[0] - v[8]) + FW_BIAS, a3 = (uint32_t)(v[4] - v[12]) + FW_BIAS;
+      sum += fw_pair_absmax(a0, a1) + fw_pair_absmax(a2, a3) + 0xffff0000u;     // 8 maxima of at most 2 040 in all
+    }
+    out_a = (2u * (sum & 0xffffu) + 1) >> 1; out_b = (2u * (sum >> 16) + 1) >> 1;
+  }
+}
+
 // one warp-wide batch of work items of one list (8x8 or 4x4 tiles) in one phase: item = (tile, group of CPI candidates), idx = the
 // lane's item (items of one candidate group are consecutive: the lanes of a warp hold consecutive tiles)
 template <int TS, int PHASE>
 __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_tiles, int idx, int lane)
 {
-  constexpr int CPI = PHASE ? 2 : 3;            // candidates per item
-  constexpr int NGRP = PHASE ? 4 : 3;           // items per tile (quarter-pel: candidates 1..8, the centre is reused)
+  // half-pel: candidate 0 alone (group 0), then the pairs (1,2) (3,4) (5,6) (7,8); quarter-pel: the four pairs (candidate 0 is
+  // the half-pel winner, whose sum is reused)
+  constexpr int NGRP = PHASE ? 4 : 5;
   const bool valid = idx < n_tiles * NGRP;
   uint32_t ji = 0xffffu;
-  uint32_t v[CPI];
-#pragma unroll
-  for (int k = 0; k < CPI; k++) v[k] = 0;
+  uint32_t v[2] = { 0, 0 };
   int grp = 0;
   if (valid)
   {
-    grp = (idx >= n_tiles) + (idx >= 2 * n_tiles) + (NGRP > 3 ? (idx >= 3 * n_tiles) : 0);
+    grp = (idx >= n_tiles) + (idx >= 2 * n_tiles) + (idx >= 3 * n_tiles) + (NGRP > 4 ? (idx >= 4 * n_tiles) : 0);
     const uint32_t e = tab[idx - grp * n_tiles];
     ji = e >> 6;
     const int t = (int)(e & 63u);
@@ -227,22 +333,22 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
         for (int w = 0; w < TS / 4; w++) ow[r][w] = o[(r ^ c) * FW_ORG_PITCH + w];
     }
     const int x0 = jb.xw + tx * TS, y0 = jb.yw + ty * TS;
-#pragma unroll
-    for (int k = 0; k < CPI; k++)
+    if (PHASE == 0 && grp == 0) v[0] = fw_tile_satd<TS>(S.planes[0], x0, y0, ow, c);
+    else
     {
-      const int cand = PHASE ? 1 + grp * CPI + k : grp * CPI + k;
-      int qx, qy, slot;
+      const int ca = PHASE ? 1 + 2 * grp : 2 * grp - 1;
+      int qxa, qya, qxb, qyb, sa, sb;
       if (PHASE == 0)
       {
-        qx = 2 * c_refine_h[cand][0]; qy = 2 * c_refine_h[cand][1];
-        slot = ((qy & 3) >> 1) * 2 + ((qx & 3) >> 1);
+        qxa = 2 * c_refine_h[ca][0]; qya = 2 * c_refine_h[ca][1]; qxb = 2 * c_refine_h[ca + 1][0]; qyb = 2 * c_refine_h[ca + 1][1];
+        sa = ((qya & 3) >> 1) * 2 + ((qxa & 3) >> 1); sb = ((qyb & 3) >> 1) * 2 + ((qxb & 3) >> 1);
       }
       else
       {
-        qx = 2 * hx + c_refine_q[cand][0]; qy = 2 * hy + c_refine_q[cand][1];
-        slot = fw_slot((qy & 3) * 4 + (qx & 3));
+        qxa = 2 * hx + c_refine_q[ca][0]; qya = 2 * hy + c_refine_q[ca][1]; qxb = 2 * hx + c_refine_q[ca + 1][0]; qyb = 2 * hy + c_refine_q[ca + 1][1];
+        sa = fw_slot((qya & 3) * 4 + (qxa & 3)); sb = fw_slot((qyb & 3) * 4 + (qxb & 3));
       }
-      v[k] = fw_tile_satd<TS>(S.planes[slot], x0 + (qx >> 2), y0 + (qy >> 2), ow, c);
+      fw_tile_satd_pair<TS>(S.planes[sa], x0 + (qxa >> 2), y0 + (qya >> 2), S.planes[sb], x0 + (qxb >> 2), y0 + (qyb >> 2), ow, c, v[0], v[1]);
     }
   }
   // The lanes of a (job, candidate group) add up their tiles with a segmented shuffle reduction -- they are consecutive lanes --
@@ -258,7 +364,7 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
   for (int o = 1; o < 32; o <<= 1)
   {
 #pragma unroll
-    for (int k = 0; k < CPI; k++)
+    for (int k = 0; k < 2; k++)
     {
       const uint32_t t = __shfl_down_sync(0xffffffffu, v[k], o);
       if (lane + o <= run_end) v[k] += t;
@@ -266,8 +372,13 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
   }
   if (head && valid)
   {
-#pragma unroll
-    for (int k = 0; k < CPI; k++) atomicAdd(&S.acc[PHASE ? 1 + grp * CPI + k : grp * CPI + k][ji], v[k]);
+    if (PHASE == 0 && grp == 0) atomicAdd(&S.acc[0][ji], v[0]);
+    else
+    {
+      const int ca = PHASE ? 1 + 2 * grp : 2 * grp - 1;
+      atomicAdd(&S.acc[ca][ji], v[0]);
+      atomicAdd(&S.acc[ca + 1][ji], v[1]);
+    }
   }
 }
 
@@ -275,7 +386,7 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
 template <int PHASE>
 __device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
 {
-  constexpr int NGRP = PHASE ? 4 : 3;
+  constexpr int NGRP = PHASE ? 4 : 5;
   const int lane = threadIdx.x & 31;
   const int end8 = (n8 * NGRP + 31) & ~31, end = end8 + n4 * NGRP;
   for (;;)
