@@ -439,8 +439,10 @@ fracw_group_kernel(const hmgpu_me_job* __restrict__ jobs, hmgpu_me_result* __res
                    const uint32_t* __restrict__ group_list, const uint32_t* __restrict__ totals, uint32_t* __restrict__ counter,
                    const __grid_constant__ CUtensorMap tmap, int ctus_x, int n_ctus, int bit_depth)
 {
-  extern __shared__ unsigned char smem_raw[];
-  FwSmem& S = *(FwSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  // no integer round trip on this pointer: the compiler must see a shared-memory address (LDS / ATOMS with 32-bit addresses; through
+  // a cast the whole structure was accessed with generic LD.E and 64-bit address arithmetic, 14 % of the executed instructions)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  FwSmem& S = *reinterpret_cast<FwSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = fw_smem_u32(&S.misc.bar);
   if (tid == 0)
@@ -695,7 +697,7 @@ int hmgpu_launch_frac_window(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_j
   uint32_t* sorted = (uint32_t*)((char*)ctx->d_work + clr_bytes + 2 * bins_al);
   if (!ctx->h_fw_tmap) { rc = fw_build_map(ctx); if (rc) return rc; }
   const CUtensorMap* map = (const CUtensorMap*)(((uintptr_t)ctx->h_fw_tmap + 63) & ~(uintptr_t)63);
-  const size_t smem = sizeof(FwSmem) + 128;
+  const size_t smem = sizeof(FwSmem);
   if (!(ctx->attr_done & HMGPU_ATTR_FRACW))
   {
     HMGPU_CUDA(ctx, cudaFuncSetAttribute(fracw_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
