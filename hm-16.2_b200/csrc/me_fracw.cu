@@ -389,12 +389,14 @@ __device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
   constexpr int NGRP = PHASE ? 4 : 5;
   const int lane = threadIdx.x & 31;
   const int end8 = (n8 * NGRP + 31) & ~31, end = end8 + n4 * NGRP;
+  // the next batch is drawn before the current one is worked on: the round trip of the atomic hides under the arithmetic
+  int next = 0;
+  if (lane == 0) next = atomicAdd(&S.misc.next, 32);
   for (;;)
   {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&S.misc.next, 32);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    const int base = __shfl_sync(0xffffffffu, next, 0);
     if (base >= end) break;
+    if (lane == 0) next = atomicAdd(&S.misc.next, 32);
     if (base < end8) fw_items<8, PHASE>(S, S.t8, n8, base + lane, lane);
     else fw_items<4, PHASE>(S, S.t4, n4, base - end8 + lane, lane);
   }
