@@ -251,14 +251,14 @@ def run_ours(args, rank, world, local_rank):
         ops, byts = work[dom]
         dur = stage_ms[dom] * 1e-3
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic_csv = {"tz": "r1n_ncu_tz_stage.csv", "frac_dist": "r1n_ncu_frac2_dist.csv"}.get(dom)
+        traffic_csv = {"tz": "r1n_ncu_tz_stage.csv", "frac_dist": "r2k_ncu_fracw_group.csv"}.get(dom)
         notes = {
             "tz": "the TZ stage (classify + 14 one-thread-per-job shape kernels + 2 warp-per-job launches) is a chain of dependent "
                   "points per job: bound by latency / instruction issue, not by HBM (DRAM traffic << algorithmic bytes: the planes "
                   "are served by L2); see roofline_int32 and full_search.roofline for the integer-pipe view",
-            "frac_dist": "the fractional stage (8x8-tile and 4x4-tile SATD kernels, half- and quarter-pel phase) is bound by L1 / "
-                         "shared-memory wavefronts and integer issue (ncu: profiles/r1n_ncu_frac2_dist.csv), not by HBM: its 18 "
-                         "candidates per job re-read one small footprint from L2; see roofline_int32"}
+            "frac_dist": "the fractional stage (one CTA per (reference, CTU) group of jobs, windows of the phase planes staged by TMA, "
+                         "me_fracw.cu) is bound by integer issue (ncu: profiles/r2k_ncu_fracw_group.csv: 64 % issue active, ALU pipe "
+                         "54 %), not by HBM: DRAM traffic 0.47 GB per step against 0.60 GB algorithmic; see roofline_int32"}
         # The dominant stage is integer-pipe work out of L1 / shared memory (the north star's "INT32-pipe roofline"; the task's
         # schema only names hbm | tensor, neither of which bounds it), so the headline roofline is the measured INT32 lane-op
         # rate; the same stage in HBM terms is kept as a sub-object.
@@ -276,6 +276,11 @@ def run_ours(args, rank, world, local_rank):
                           "per_stage": {k: {"ms": stage_ms[k], "gops": work[k][0] / (stage_ms[k] * 1e-3) / 1e9,
                                             "frac": work[k][0] / (stage_ms[k] * 1e-3) / 1e9 / int_peak,
                                             "gbs": work[k][1] / (stage_ms[k] * 1e-3) / 1e9} for k in stage_ms if k in work}}
+        me_ops = sum(work[k][0] for k in ("tz", "frac_dist") if k in stage_ms)
+        me_ms = sum(stage_ms[k] for k in ("tz", "frac_dist", "frac_expand", "frac_select") if k in stage_ms)
+        if me_ms > 0:
+            # the whole ME step (integer + fractional search of every job) against the INT32 peak, in algorithmic operations
+            roofline_int32["me_step"] = {"ms": me_ms, "gops": me_ops / (me_ms * 1e-3) / 1e9, "frac": me_ops / (me_ms * 1e-3) / 1e9 / int_peak}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8", "data": "synthetic", "config": workload_config(n_jobs),
