@@ -31,9 +31,12 @@ fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, i
 {
   constexpr int TPB = (N * N >= 256) ? 1 : 256 / (N * N);   // TUs per block
   constexpr int LOG2N = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
+  // rows padded by one word: the lanes of a warp read column x of 32 different rows (j = lane), which with a pitch of N words
+  // is ONE bank for N = 32 (ncu, profiles/r2l_ncu_misc_kernels.csv: L1 97 % busy, 4 % issue active, 1.22 ms per 8 000 TUs)
+  constexpr int P = N + 1;
   __shared__ int s_m[N * N];
-  __shared__ int s_a[TPB][N * N];
-  __shared__ int s_b[TPB][N * N];
+  __shared__ int s_a[TPB][N * P];
+  __shared__ int s_b[TPB][N * P];
   const int tid = threadIdx.x;
   for (int i = tid; i < N * N; i += 256)
     s_m[i] = (use_dst && N == 4) ? c_dst4[i / N][i % N] : dct_coef(N, i / N, i % N);
@@ -41,7 +44,8 @@ fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, i
   for (int i = tid; i < TPB * N * N; i += 256)
   {
     const int t = i / (N * N);
-    if (tu0 + t < n_tus) s_a[t][i % (N * N)] = (int)resi[(size_t)(tu0 + t) * N * N + (i % (N * N))];
+    const int e = i % (N * N);
+    if (tu0 + t < n_tus) s_a[t][(e / N) * P + (e % N)] = (int)resi[(size_t)(tu0 + t) * N * N + e];
   }
   __syncthreads();
   const int shift1 = LOG2N + bit_depth + 6 - 15, shift2 = LOG2N + 6;
@@ -52,8 +56,8 @@ fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, i
     const int t = i / (N * N), e = i % (N * N), k = e / N, j = e % N;
     int acc = 0;
 #pragma unroll
-    for (int x = 0; x < N; x++) acc += s_m[k * N + x] * s_a[t][j * N + x];
-    s_b[t][k * N + j] = (acc + rnd1) >> shift1;
+    for (int x = 0; x < N; x++) acc += s_m[k * N + x] * s_a[t][j * P + x];
+    s_b[t][k * P + j] = (acc + rnd1) >> shift1;
   }
   __syncthreads();
   for (int i = tid; i < TPB * N * N; i += 256)
@@ -62,7 +66,7 @@ fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, i
     if (tu0 + t >= n_tus) continue;
     int acc = 0;
 #pragma unroll
-    for (int x = 0; x < N; x++) acc += s_m[k * N + x] * s_b[t][j * N + x];
+    for (int x = 0; x < N; x++) acc += s_m[k * N + x] * s_b[t][j * P + x];
     coeff[(size_t)(tu0 + t) * N * N + k * N + j] = (acc + rnd2) >> shift2;
   }
 }

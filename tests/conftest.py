@@ -9,3 +9,4 @@ for p in (ROOT, os.path.join(ROOT, "hm-16.2_b200"), os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: whole-encoder runs at BASELINE picture sizes (a minute or two each)")

@@ -58,3 +58,17 @@ def test_lowdelay_p_selective_search():
     # FastSearch=2 (xTZSearchSelective): GPUME=2 cross-checks every call, GPUME=1 exercises the batched path
     _compare("--cfg", "lowdelay_P_main", "--frames", "3", "--gpume", "2", "--", "--FastSearch=2")
     _compare("--cfg", "lowdelay_P_main", "--frames", "3", "--gpume", "1", "--", "--FastSearch=2")
+
+
+@pytest.mark.slow
+def test_lowdelay_p_tz_1080p():
+    # BASELINE cfg 2 at its picture size (1920x1080, TZSearch, 4 references), 8 frames
+    out = _compare("--cfg", "lowdelay_P_main", "--size", "1920x1080", "--frames", "8", "--gpume", "1")
+    assert "xMotionEstimation calls on libhmgpu" in out["gpu"]["gpume"][0]
+
+
+@pytest.mark.slow
+def test_randomaccess_main10_4k():
+    # BASELINE cfg 5 at its picture size: 3840x2160 10-bit, SearchRange 128, closed GOP (uint16 planes of 4160 x 2320 samples)
+    _compare("--cfg", "randomaccess_main10", "--size", "3840x2160", "--frames", "3", "--gpume", "1", "--bit-depth", "10", "--",
+             "--DecodingRefreshType=2", "--IntraPeriod=16", "--SearchRange=128")
