@@ -1447,6 +1447,43 @@ int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_
   return HMGPU_OK;
 }
 
+// ---- intra mode pre-selection (intra.cu) ---------------------------------------------------------
+int hmgpu_intra_costs(hmgpu_ctx* ctx, const hmgpu_intra_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
+                      const int16_t* ref_lines, int n_ref_elems, uint32_t* dist)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !org_blocks || !ref_lines || !dist || n_jobs < 0 || n_org_elems < 0 || n_ref_elems < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_intra_costs");
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const hmgpu_intra_job& j = jobs[i];
+    const int n = j.size;
+    if (n != 4 && n != 8 && n != 16 && n != 32 && n != 64) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: size %d not in {4,8,16,32,64}", i, n);
+    if (j.flags & ~31u) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: unknown flag bits", i);
+    if ((unsigned long long)j.org_offset + (unsigned long long)n * n > (unsigned long long)n_org_elems) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: source block outside org_blocks", i);
+    if ((unsigned long long)j.ref_offset + 2ull * (4 * n + 1) > (unsigned long long)n_ref_elems) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: reference lines outside ref_lines", i);
+  }
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b0 = round_up(sizeof(int16_t) * (size_t)n_org_elems, 256), b1 = round_up(sizeof(int16_t) * (size_t)n_ref_elems, 256);
+  const size_t b2 = round_up(sizeof(hmgpu_intra_job) * (size_t)n_jobs, 256), b3 = round_up(sizeof(uint32_t) * 35 * (size_t)n_jobs, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1 + b2 + b3))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1 + b2 + b3))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+  memcpy(hp + b0, ref_lines, sizeof(int16_t) * (size_t)n_ref_elems);
+  memcpy(hp + b0 + b1, jobs, sizeof(hmgpu_intra_job) * (size_t)n_jobs);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0 + b1 + b2, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_intra_costs(ctx, (const hmgpu_intra_job*)(dp + b0 + b1), n_jobs, (const int16_t*)dp, (const int16_t*)(dp + b0),
+                                     (uint32_t*)(dp + b0 + b1 + b2)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0 + b1 + b2, dp + b0 + b1 + b2, sizeof(uint32_t) * 35 * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(dist, hp + b0 + b1 + b2, sizeof(uint32_t) * 35 * (size_t)n_jobs);
+  return HMGPU_OK;
+}
+
 // ---- motion compensation -----------------------------------------------------------------------
 
 int hmgpu_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* jobs, int n_jobs, int16_t* dst, int n_dst)

@@ -40,13 +40,16 @@ PRED_JOB = np.dtype([
     ("mv_x", "<i2", (2,)), ("mv_y", "<i2", (2,)), ("dst_offset", "<u4")], align=True)
 assert ME_JOB.itemsize == 48 and ME_RESULT.itemsize == 24 and DIST_ITEM.itemsize == 20 and MC_JOB.itemsize == 16
 assert PRED_JOB.itemsize == 20
+INTRA_JOB = np.dtype([("org_offset", "<u4"), ("ref_offset", "<u4"), ("size", "u1"), ("flags", "u1"), ("reserved", "<u2")], align=True)
+assert INTRA_JOB.itemsize == 12
+IF_ABOVE, IF_LEFT, IF_EDGE_FILTERS, IF_SATD, IF_NO_SMOOTH = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "hmgpu_create", "hmgpu_destroy", "hmgpu_last_error", "hmgpu_abi_version", "hmgpu_launch_count",
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
-    "hmgpu_dist_batch", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
+    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
@@ -100,6 +103,7 @@ def lib():
     L.hmgpu_search_range.argtypes = [vp, ci, ci, ci, vp]
     L.hmgpu_search_range.restype = None
     L.hmgpu_dist_batch.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp]
+    L.hmgpu_intra_costs.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp]
     L.hmgpu_mv_bits.argtypes = [ci] * 5
     L.hmgpu_mv_bits.restype = cu
     L.hmgpu_mv_cost.argtypes = [cu] + [ci] * 5
@@ -300,6 +304,16 @@ class Context:
         out = np.zeros(len(items), np.uint32)
         self._check(self.L.hmgpu_dist_batch(self.h, org.ctypes.data, org.size, cur.ctypes.data, cur.size,
                                             items.ctypes.data, len(items), out.ctypes.data))
+        return out
+
+    def intra_costs(self, jobs, org_blocks, ref_lines):
+        """distortion of the 35 luma intra modes of every job (hmgpu_intra_costs): -> uint32 [n_jobs, 35]"""
+        jobs = np.ascontiguousarray(jobs, INTRA_JOB)
+        org_blocks = np.ascontiguousarray(org_blocks, np.int16)
+        ref_lines = np.ascontiguousarray(ref_lines, np.int16)
+        out = np.zeros((len(jobs), 35), np.uint32)
+        self._check(self.L.hmgpu_intra_costs(self.h, jobs.ctypes.data, len(jobs), org_blocks.ctypes.data, org_blocks.size,
+                                             ref_lines.ctypes.data, ref_lines.size, out.ctypes.data))
         return out
 
     def mc_luma(self, jobs, n_dst):

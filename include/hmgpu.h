@@ -220,6 +220,38 @@ typedef struct hmgpu_dist_item
 int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_t* cur, int n_cur,
                      const hmgpu_dist_item* items, int n_items, uint32_t* out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Intra mode pre-selection of luma PUs.  Replaces the first-pass loop of
+ * TEncSearch::estIntraPredQT (TEncSearch.cpp:2352-2395): for every one of the 35 modes
+ * TComPrediction::predIntraAng (TComPrediction.cpp:407-492, blocks without DPCM) followed by
+ * distParam.DistFunc (HADS, or SADS for transquant-bypass CUs).  One job = one PU; the mode bits
+ * (xModeBitsIntra, CABAC state) and the candidate list stay on the host.
+ * The reference samples are what initAdiPatternChType (TComPattern.cpp:225-330) leaves in
+ * m_piYuvExt[COMPONENT_Y][PRED_BUF_UNFILTERED / PRED_BUF_FILTERED], as ONE LINE of 4N+1 samples
+ * each: from the bottom-left neighbour up the left column to the top-left corner (element 2N)
+ * and along the row above to the above-right neighbour -- the order that function walks.
+ * ------------------------------------------------------------------------------------------ */
+enum
+{
+  HMGPU_IF_ABOVE = 1, HMGPU_IF_LEFT = 2,   /* bAbove / bLeft of predIntraAng (DC value and DC edge filter) */
+  HMGPU_IF_EDGE_FILTERS = 4,               /* enableEdgeFilters (:474): off only for RDPCM transquant-bypass CUs */
+  HMGPU_IF_SATD = 8,                       /* bUseHadamard (TEncSearch.cpp:2349): DF_HADS, else DF_SADS */
+  HMGPU_IF_NO_SMOOTH = 16                  /* sps.getDisableIntraReferenceSmoothing(): always the unfiltered samples */
+};
+
+typedef struct hmgpu_intra_job
+{
+  uint32_t org_offset;   /* element offset of the N x N source block (stride N) in org_blocks */
+  uint32_t ref_offset;   /* element offset in ref_lines: 4N+1 unfiltered samples, then 4N+1 filtered samples */
+  uint8_t  size;         /* N = 4, 8, 16, 32 or 64 */
+  uint8_t  flags;        /* HMGPU_IF_* */
+  uint16_t reserved;
+} hmgpu_intra_job;       /* 12 bytes */
+
+/* dist[job * 35 + mode] = the distortion TEncSearch.cpp:2373 adds to uiSad for that mode */
+int hmgpu_intra_costs(hmgpu_ctx* ctx, const hmgpu_intra_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
+                      const int16_t* ref_lines, int n_ref_elems, uint32_t* dist);
+
 /* MV rate cost, TComRdCost::getCost(x,y)/getBits (TComRdCost.h:171-188); host-side scalar */
 uint32_t hmgpu_mv_bits(int pred_x, int pred_y, int scale, int x, int y);
 uint32_t hmgpu_mv_cost(uint32_t ui_cost, int pred_x, int pred_y, int scale, int x, int y);

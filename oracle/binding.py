@@ -102,6 +102,10 @@ def oracle():
     L.hmo_quant.argtypes = [i32p, ci, ci, ci, ci, ci, i32p, i32p]
     L.hmo_me_batch.restype = C.c_double
     L.hmo_me_batch.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, vp]
+    L.hmo_intra_pred.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp]
+    L.hmo_intra_use_filtered.restype = ci
+    L.hmo_intra_use_filtered.argtypes = [ci, ci, ci]
+    L.hmo_intra_costs.argtypes = [vp, vp, vp, ci, ci, ci, u32p]
     _oracle = L
     return L
 
@@ -154,6 +158,9 @@ def ref():
     L.ref_pred_inter_blk.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci]
     L.ref_me_batch.restype = C.c_double
     L.ref_me_batch.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, vp]
+    L.ref_intra_pred.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp]
+    L.ref_intra_use_filtered.restype = ci
+    L.ref_intra_use_filtered.argtypes = [ci, ci, ci]
     _ref = L
     return L
 

@@ -918,3 +918,112 @@ double hmo_me_batch(const hmgpu_me_job* jobs, int n_jobs, const int16_t* const* 
   clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t1);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+
+/* ==== intra mode pre-selection ==========================================================
+ * Restates TComPrediction::predIntraAng for a luma block without DPCM (TComPrediction.cpp:407-492):
+ * xPredIntraPlanar (:746-803), predIntraGetPredValDC (:182-225), xPredIntraAng (:245-405),
+ * xDCPredFiltering (:808-835), and the choice of the filtered / unfiltered reference samples,
+ * TComPrediction::filteringIntraReferenceSamples (TComPattern.cpp:529-554) with m_aucIntraFilter
+ * (TComPrediction.cpp:49-57).  The reference keeps the samples as the first row / first column of a
+ * (2n+1) x (2n+1) buffer and copies them into refAbove / refLeft; here one line m[-2n .. 2n] holds both,
+ * m[0] = top-left corner, m[k] = above sample k-1, m[-k] = left sample k-1 (k >= 1), so that
+ * refAbove[k] = m[k] and refLeft[k] = m[-k]. */
+static const int k_intra_ang[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+static const int k_intra_inv_ang[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
+static const int k_intra_filter_thr[5] = { 10, 7, 1, 0, 10 };   /* 4x4 .. 64x64, luma */
+
+static int hmo_log2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+int hmo_intra_use_filtered(int mode, int n, int no_smooth)
+{
+  if (no_smooth || mode == 1) return 0;                       /* DC_IDX: never smoothed */
+  const int d_hor = abs(mode - 10), d_ver = abs(mode - 26);   /* HOR_IDX 10, VER_IDX 26; planar (0): min(10, 26) = 10 */
+  const int diff = d_hor < d_ver ? d_hor : d_ver;
+  return diff > k_intra_filter_thr[hmo_log2(n) - 2];
+}
+
+void hmo_intra_pred(const int16_t* line, int n, int mode, int bit_depth, int above, int left, int edge_filters, int16_t* dst)
+{
+  const int16_t* m = line + 2 * n;
+  const int lg = hmo_log2(n);
+  if (mode == 0)
+  {
+    /* planar (:746-803): ((n-1-x) L[y] + (x+1) TR + (n-1-y) T[x] + (y+1) BL + n) >> (log2 n + 1), the closed form of the
+     * reference's running sums */
+    const int tr = m[n + 1], bl = m[-(n + 1)];
+    for (int y = 0; y < n; y++)
+      for (int x = 0; x < n; x++)
+        dst[y * n + x] = (int16_t)(((n - 1 - x) * m[-(y + 1)] + (x + 1) * tr + (n - 1 - y) * m[x + 1] + (y + 1) * bl + n) >> (lg + 1));
+    return;
+  }
+  if (mode == 1)
+  {
+    int sum = 0, dc;
+    if (above) for (int i = 0; i < n; i++) sum += m[i + 1];
+    if (left) for (int i = 0; i < n; i++) sum += m[-(i + 1)];
+    if (above && left) dc = (sum + n) / (2 * n);
+    else if (above) dc = (sum + n / 2) / n;
+    else if (left) dc = (sum + n / 2) / n;
+    else dc = m[-1];                                          /* pSrc[-1] (:220) */
+    for (int i = 0; i < n * n; i++) dst[i] = (int16_t)dc;
+    if (above && left && n <= 16)                             /* xDCPredFiltering, luma, MAXIMUM_INTRA_FILTERED_* = 16 */
+    {
+      dst[0] = (int16_t)((m[1] + m[-1] + 2 * dc + 2) >> 2);
+      for (int x = 1; x < n; x++) dst[x] = (int16_t)((m[x + 1] + 3 * dc + 2) >> 2);
+      for (int y = 1; y < n; y++) dst[y * n] = (int16_t)((m[-(y + 1)] + 3 * dc + 2) >> 2);
+    }
+    return;
+  }
+  /* angular (:273-403).  s = +1: vertical modes (main reference = above), -1: horizontal (main = left; the block is
+   * predicted transposed and flipped back) */
+  const int ver = mode >= 18;
+  const int ang_mode = ver ? mode - 26 : -(mode - 10);
+  const int abs_mode = abs(ang_mode), sgn = ang_mode < 0 ? -1 : 1;
+  const int angle = sgn * k_intra_ang[abs_mode], inv = k_intra_inv_ang[abs_mode];
+  const int s = ver ? 1 : -1;
+  const int maxv = (1 << bit_depth) - 1;
+  const int edge = edge_filters && n <= 16;
+  for (int y = 0; y < n; y++)          /* (x, y) in the orientation of the main reference */
+    for (int x = 0; x < n; x++)
+    {
+      int v;
+      if (angle == 0)
+      {
+        v = m[s * (x + 1)];
+        if (edge && x == 0)
+        {
+          v += (m[-s * (y + 1)] - m[0]) >> 1;                 /* refSide[y+1] - refSide[0] (:355) */
+          v = v < 0 ? 0 : (v > maxv ? maxv : v);
+        }
+      }
+      else
+      {
+        const int pos = (y + 1) * angle, di = pos >> 5, df = pos & 31;
+        int k0 = x + di + 1, k1 = k0 + 1, a, b;
+        /* main reference at index k: k >= 0 the line itself, k < 0 the side reference projected with the inverse angle
+         * (:300-305: refMain[k] = refSide[(128 + |k| * invAngle) >> 8]) */
+        a = k0 >= 0 ? m[s * k0] : m[-s * ((128 + (-k0) * inv) >> 8)];
+        if (df)
+        {
+          b = k1 >= 0 ? m[s * k1] : m[-s * ((128 + (-k1) * inv) >> 8)];
+          v = ((32 - df) * a + df * b + 16) >> 5;
+        }
+        else v = a;
+      }
+      if (ver) dst[y * n + x] = (int16_t)v; else dst[x * n + y] = (int16_t)v;
+    }
+}
+
+void hmo_intra_costs(const int16_t* line_unfiltered, const int16_t* line_filtered, const int16_t* org, int n, int bit_depth,
+                     int flags, uint32_t dist[35])
+{
+  int16_t pred[64 * 64];
+  for (int mode = 0; mode < 35; mode++)
+  {
+    const int16_t* line = hmo_intra_use_filtered(mode, n, (flags & 16) != 0) ? line_filtered : line_unfiltered;
+    hmo_intra_pred(line, n, mode, bit_depth, flags & 1, (flags & 2) != 0, (flags & 4) != 0, pred);
+    /* setDistParam(dp, bitDepth, org, stride, pred, stride, w, h, bUseHadamard) (TEncSearch.cpp:2350): DF_HADS or DF_SADS */
+    dist[mode] = (flags & 8) ? hmo_hads(org, n, pred, n, n, n, bit_depth) : hmo_sad(org, n, pred, n, n, n, 0, bit_depth, 0);
+  }
+}

@@ -81,6 +81,16 @@ void hmo_transform_matrix(int n, int32_t* m /* n*n */);
 uint32_t hmo_quant(const int32_t* coef, int n_coef, int qp_per, int qp_rem, int transform_shift,
                    int is_intra_slice, int32_t* level, int32_t* delta_u);
 
+/* ---- intra mode pre-selection: prediction of one luma mode + the 35 distortions of estIntraPredQT's first pass ----
+ * line: the 4n+1 reference samples of the PU in the order initAdiPatternChType walks them (TComPattern.cpp:225-330):
+ * line[0] = bottom-left neighbour ... line[2n-1] = left neighbour of row 0, line[2n] = top-left corner,
+ * line[2n+1] = above sample of column 0 ... line[4n] = above-right.  dst: n x n, stride n. */
+void hmo_intra_pred(const int16_t* line, int n, int mode, int bit_depth, int above, int left, int edge_filters, int16_t* dst);
+int  hmo_intra_use_filtered(int mode, int n, int no_smooth);
+/* flags: HMGPU_IF_* of include/hmgpu.h (1 above, 2 left, 4 edge filters, 8 SATD (else SAD), 16 reference smoothing disabled) */
+void hmo_intra_costs(const int16_t* line_unfiltered, const int16_t* line_filtered, const int16_t* org, int n, int bit_depth,
+                     int flags, uint32_t dist[35]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -469,4 +469,29 @@ void ref_pred_inter_blk(int chroma, const int16_t* ref, int refStride, int mvx, 
   }
 }
 
+// ---- f4: one luma intra prediction exactly as TComPrediction::predIntraAng (TComPrediction.cpp:407-492) performs it for a
+//      block without DPCM.  line = the 4n+1 reference samples from the bottom-left neighbour up to the top-left corner and on
+//      to the above-right neighbour; they are laid out as the first column / first row of the (2n+1) x (2n+1) buffer the
+//      reference predicts from (m_piYuvExt).
+void ref_intra_pred(int bitDepth, const int16_t* line, int n, int mode, int above, int left, int edgeFilters, int16_t* dst)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  const int sw = 2 * n + 1;
+  std::vector<Pel> roi(sw * sw, 0);
+  for (int y = 0; y < 2 * n; y++) roi[(y + 1) * sw] = line[2 * n - 1 - y];     // left column, top to bottom
+  for (int x = 0; x <= 2 * n; x++) roi[x] = line[2 * n + x];                  // top-left corner + top row
+  const Pel* src = &roi[0] + sw + 1;
+  if (mode == PLANAR_IDX) g.search->xPredIntraPlanar(src, sw, (Pel*)dst, n, n, n, CHANNEL_TYPE_LUMA, CHROMA_420);
+  else
+  {
+    g.search->xPredIntraAng(bitDepth, src, sw, (Pel*)dst, n, n, n, CHANNEL_TYPE_LUMA, CHROMA_420, mode, above != 0, left != 0, edgeFilters != 0);
+    if (mode == DC_IDX && above && left) g.search->xDCPredFiltering(src, sw, (Pel*)dst, n, n, n, CHANNEL_TYPE_LUMA);
+  }
+}
+int ref_intra_use_filtered(int mode, int n, int disableSmoothing)
+{
+  ensure_init();
+  return TComPrediction::filteringIntraReferenceSamples(COMPONENT_Y, mode, n, n, CHROMA_420, disableSmoothing != 0) ? 1 : 0;
+}
+
 } // extern "C"

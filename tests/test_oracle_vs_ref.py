@@ -133,3 +133,34 @@ def test_selective_search(bd, noise):
                            s.ui_cost, s.pred_x, s.pred_y, bd, w, h, cu_x, cu_y, s.search_range, has2n, s.i2n_x, s.i2n_y,
                            sel, mv, sad)
         assert (s.mv_x, s.mv_y, s.sad) == (int(mv[0]), int(mv[1]), int(sad[0])), (k, j)
+
+
+def _intra_line(rng, n, bd, kind):
+    """4n+1 reference samples, bottom-left -> top-left -> above-right"""
+    mx = (1 << bd) - 1
+    if kind == 0:
+        return rng.integers(0, mx + 1, 4 * n + 1).astype(np.int16)
+    if kind == 1:   # smooth ramp with noise: the interpolating modes see small differences
+        return np.clip(np.linspace(mx // 4, 3 * mx // 4, 4 * n + 1) + rng.integers(-3, 4, 4 * n + 1), 0, mx).astype(np.int16)
+    return rng.choice(np.array([0, mx], np.int16), 4 * n + 1)    # extremes: the edge filters clip
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_intra_prediction_all_modes(bd):
+    """f4: hmo_intra_pred against the reference's xPredIntraPlanar / xPredIntraAng / xDCPredFiltering for every mode, size,
+    availability and edge-filter combination; the filtered / unfiltered rule against filteringIntraReferenceSamples."""
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(40 + bd)
+    for n in (4, 8, 16, 32, 64):
+        for mode in range(35):
+            for ns in (0, 1):
+                assert O.hmo_intra_use_filtered(mode, n, ns) == R.ref_intra_use_filtered(mode, n, ns), (mode, n, ns)
+        for kind in range(3):
+            line = _intra_line(rng, n, bd, kind)
+            for mode in range(35):
+                for above, left, edge in ((1, 1, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (0, 0, 0)):
+                    a = np.zeros((n, n), np.int16)
+                    b = np.full((n, n), -1, np.int16)
+                    R.ref_intra_pred(bd, B.ptr(line), n, mode, above, left, edge, B.ptr(a))
+                    O.hmo_intra_pred(B.ptr(line), n, mode, bd, above, left, edge, B.ptr(b))
+                    assert np.array_equal(a, b), (n, mode, above, left, edge, kind)
