@@ -178,6 +178,7 @@ int hmgpu_me_wait(hmgpu_ctx* ctx, hmgpu_me_result* results);
  * HMGPU_DF_HADS) and the AMVP candidates of xEstimateMvPredAMVP / xGetTemplateCost (:3571-3637, :3771-3811, HMGPU_DF_SAD) of the
  * same PU.  pred_funcs[i] is the HMGPU_DF_* of pred_jobs[i]; hmgpu_pu_wait fills results[n_jobs] and pred_out[n_pred].
  * hmgpu_me_submit / hmgpu_me_wait are the n_pred = 0 case. */
+struct hmgpu_pred_job;   /* defined with hmgpu_predict below */
 int hmgpu_pu_submit(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
                     const struct hmgpu_pred_job* pred_jobs, const uint8_t* pred_funcs, int n_pred);
 int hmgpu_pu_wait(hmgpu_ctx* ctx, hmgpu_me_result* results, uint32_t* pred_out);
