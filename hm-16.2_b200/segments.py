@@ -48,12 +48,12 @@ def run_rank(encoder, cfg, yuv, width, height, qp, plan, rank, out_prefix, extra
         while todo and len(running) < max_parallel:
             seg = todo.pop(0)
             p = subprocess.Popen(encoder_cmd(encoder, cfg, yuv, width, height, qp, seg, out_prefix, extra),
-                                 stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
             running.append((seg, p))
         seg, p = running.pop(0)
-        _, err = p.communicate()
-        if p.returncode != 0:
-            raise RuntimeError("segment %d failed: %s" % (seg["segment"], err.decode()[-500:]))
+        out, err = p.communicate()
+        if p.returncode != 0:     # HM prints its configuration errors on stdout
+            raise RuntimeError("segment %d failed (rc %d): %s %s" % (seg["segment"], p.returncode, out.decode()[-300:], err.decode()[-300:]))
         done.append(seg["segment"])
     return done
 
