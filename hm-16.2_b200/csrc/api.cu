@@ -1592,6 +1592,64 @@ int hmgpu_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int wi
   return HMGPU_OK;
 }
 
+// f2: motion compensation of every merge candidate + SSE of the skip reconstruction per component: the prediction kernel into
+// device scratch, then the distortion-table kernel over (source block, predicted block) pairs -- nothing leaves the device in
+// between
+int hmgpu_merge_skip_dist(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, const uint32_t* org_offset,
+                          const int16_t* org_blocks, int n_org_elems, int16_t* pred, int n_pred, uint32_t* sse)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !org_offset || !org_blocks || !sse || n_jobs < 0 || n_org_elems < 0 || n_pred < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_merge_skip_dist");
+  int rc = validate_pred_jobs(ctx, jobs, n_jobs, true, n_pred, true);
+  if (rc) return rc;
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const size_t need = (size_t)jobs[i].pu_w * jobs[i].pu_h * 3 / 2;
+    if ((jobs[i].pu_w & 7) || (jobs[i].pu_h & 7)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: a CU is a multiple of 8 samples wide and high", i);
+    if ((size_t)org_offset[i] + need > (size_t)n_org_elems) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: source CU outside org_blocks", i);
+  }
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n_items = (size_t)n_jobs * 3;
+  const size_t b0 = round_up(sizeof(hmgpu_pred_job) * (size_t)n_jobs, 256), b1 = round_up(sizeof(int16_t) * (size_t)n_pred, 256);
+  const size_t b2 = round_up(sizeof(int16_t) * (size_t)n_org_elems, 256), b3 = round_up(sizeof(hmgpu_dist_item) * n_items, 256);
+  const size_t b4 = round_up(sizeof(uint32_t) * n_items, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1 + b2 + b3 + b4))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1 + b2 + b3 + b4))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, jobs, sizeof(hmgpu_pred_job) * (size_t)n_jobs);
+  memcpy(hp + b0 + b1, org_blocks, sizeof(int16_t) * (size_t)n_org_elems);
+  hmgpu_dist_item* items = (hmgpu_dist_item*)(hp + b0 + b1 + b2);
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const int w = jobs[i].pu_w, h = jobs[i].pu_h;
+    uint32_t oo = org_offset[i], po = jobs[i].dst_offset;
+    for (int c = 0; c < 3; c++)
+    {
+      const int cw = c ? w >> 1 : w, ch = c ? h >> 1 : h;
+      hmgpu_dist_item it;
+      it.org_offset = oo; it.cur_offset = po; it.org_stride = cw; it.cur_stride = cw;
+      it.w = (uint8_t)cw; it.h = (uint8_t)ch; it.func = HMGPU_DF_SSE; it.sub_shift = 0;
+      items[i * 3 + c] = it;
+      oo += (uint32_t)(cw * ch); po += (uint32_t)(cw * ch);
+    }
+  }
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp + b0 + b1, hp + b0 + b1, b2 + b3, cudaMemcpyHostToDevice, ctx->stream));
+  HMGPU_CUDA(ctx, cudaMemsetAsync(dp + b0, 0, b1, ctx->stream));
+  if ((rc = hmgpu_launch_predict(ctx, (const hmgpu_pred_job*)dp, n_jobs, 1, (int16_t*)(dp + b0)))) return rc;
+  if ((rc = hmgpu_launch_dist(ctx, (const int16_t*)(dp + b0 + b1), (const int16_t*)(dp + b0), (const hmgpu_dist_item*)(dp + b0 + b1 + b2),
+                              (int)n_items, (uint32_t*)(dp + b0 + b1 + b2 + b3)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0 + b1 + b2 + b3, dp + b0 + b1 + b2 + b3, sizeof(uint32_t) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pred) HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int16_t) * (size_t)n_pred, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(sse, hp + b0 + b1 + b2 + b3, sizeof(uint32_t) * n_items);
+  if (pred) memcpy(pred, hp + b0, sizeof(int16_t) * (size_t)n_pred);
+  return HMGPU_OK;
+}
+
 int hmgpu_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int func, uint32_t* out)
 {
   if (!ctx) return HMGPU_E_INVALID;

@@ -49,7 +49,7 @@ EXPORTS = [
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
-    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_fwd_transform",
+    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
@@ -111,6 +111,7 @@ def lib():
     L.hmgpu_mc_luma.argtypes = [vp, vp, ci, vp, ci]
     L.hmgpu_predict.argtypes = [vp, vp, ci, ci, vp, ci]
     L.hmgpu_pred_error.argtypes = [vp, vp, ci, ci, vp]
+    L.hmgpu_merge_skip_dist.argtypes = [vp, vp, ci, vp, vp, ci, vp, ci, vp]
     L.hmgpu_fwd_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.hmgpu_profile_enable.argtypes = [vp, ci]
@@ -328,6 +329,17 @@ class Context:
         dst = np.zeros(n_dst, np.int16)
         self._check(self.L.hmgpu_predict(self.h, jobs.ctypes.data, len(jobs), int(with_chroma), dst.ctypes.data, n_dst))
         return dst
+
+    def merge_skip_dist(self, jobs, org_offset, org_blocks, n_pred):
+        """MC of every merge candidate (Y, Cb, Cr) + SSE of the skip reconstruction per component: -> (pred int16[n_pred], sse uint32[n, 3])"""
+        jobs = np.ascontiguousarray(jobs, PRED_JOB)
+        org_offset = np.ascontiguousarray(org_offset, np.uint32)
+        org_blocks = np.ascontiguousarray(org_blocks, np.int16)
+        pred = np.zeros(n_pred, np.int16)
+        sse = np.zeros((len(jobs), 3), np.uint32)
+        self._check(self.L.hmgpu_merge_skip_dist(self.h, jobs.ctypes.data, len(jobs), org_offset.ctypes.data, org_blocks.ctypes.data,
+                                                 org_blocks.size, pred.ctypes.data, n_pred, sse.ctypes.data))
+        return pred, sse
 
     def pred_error(self, jobs, func):
         """luma prediction error (DF_SAD / DF_HADS) of every job against the source picture"""

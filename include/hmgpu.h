@@ -298,6 +298,18 @@ int hmgpu_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int wi
  * The double-precision calcRdCost that follows (TComRdCost.cpp:106) stays on the host.  dst_offset is ignored. */
 int hmgpu_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, int func, uint32_t* out);
 
+/* Merge / skip candidate evaluation, the part that needs no CABAC state: for every merge candidate of a CU
+ * (TEncCu::xCheckRDCostMerge2Nx2N, TEncCu.cpp:1406-1528) the motion compensation of the whole CU -- Y, Cb, Cr, uni or bi,
+ * TComPrediction::motionCompensation (TComPrediction.cpp:514-714) -- and the distortion of the SKIP reconstruction
+ * (reco = pred, TEncSearch::encodeResAndCalcRdInterCU, TEncSearch.cpp:4452-4483) against the source CU: getDistPart = xGetSSE*
+ * per component (TComRdCost.cpp:970-1315), BEFORE the chroma weight m_distortionWeight (a double, applied by the host together
+ * with the skip-flag / merge-index bits and calcRdCost).  One call costs all candidates of any number of CUs.
+ *   jobs[i]        candidate i (its dst_offset: where its prediction lands in pred -- w x h luma, then Cb, Cr of w/2 x h/2)
+ *   org_offset[i]  element offset in org_blocks of the source CU of candidate i, in the same layout (Y, Cb, Cr)
+ *   sse[i*3 + c]   distortion of component c;  pred may be NULL when only the distortions are wanted. */
+int hmgpu_merge_skip_dist(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs, const uint32_t* org_offset,
+                          const int16_t* org_blocks, int n_org_elems, int16_t* pred, int n_pred, uint32_t* sse);
+
 /* ------------------------------------------------------------------------------------------
  * Residual costing: forward core transform and scalar quantiser, batched over TUs.
  * hmgpu_fwd_transform replaces TComTrQuant::xT -> xTrMxN -> partialButterfly4/8/16/32 /

@@ -123,3 +123,52 @@ def test_pred_error_matches_oracle(bit_depth):
         blk = np.ascontiguousarray(org[int(j["pu_y"]):int(j["pu_y"]) + h, int(j["pu_x"]):int(j["pu_x"]) + w])
         assert int(got_sad[i]) == O.hmo_sad(B.ptr(blk), w, B.ptr(pred), w, w, h, 0, bit_depth, 0), (i, j)
         assert int(got_had[i]) == O.hmo_hads(B.ptr(blk), w, B.ptr(pred), w, w, h, bit_depth), (i, j)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_merge_skip_dist_matches_oracle(bit_depth):
+    """f2: every merge candidate of a CU -- motion compensation of Y, Cb, Cr (uni / bi) and the SSE of the skip
+    reconstruction per component (xCheckRDCostMerge2Nx2N + the bSkipRes branch of encodeResAndCalcRdInterCU) -- in one call."""
+    O = B.oracle()
+    rng = np.random.default_rng(53)
+    pics = _pictures(bit_depth, 2, 59)
+    src = _pictures(bit_depth, 1, 61)[0]
+    pads = [(_pad(y, M), _pad(cb, CM), _pad(cr, CM)) for (y, cb, cr) in pics]
+    # CUs of 8..64 samples, five merge candidates each (same CU, different motion)
+    cus = [(int(rng.integers(0, (W - s) // 8 + 1)) * 8, int(rng.integers(0, (H - s) // 8 + 1)) * 8, s) for s in (8, 16, 32, 64, 16, 8, 32) for _ in range(3)]
+    jobs = np.zeros(len(cus) * 5, hmgpu.PRED_JOB)
+    org_off = np.zeros(len(jobs), np.uint32)
+    org_blocks, off_o, off_p = [], 0, 0
+    for c, (x, y, s) in enumerate(cus):
+        blk = [src[0][y:y + s, x:x + s], src[1][y // 2:(y + s) // 2, x // 2:(x + s) // 2], src[2][y // 2:(y + s) // 2, x // 2:(x + s) // 2]]
+        org_blocks += [np.ascontiguousarray(b).ravel() for b in blk]
+        for k in range(5):
+            j = jobs[c * 5 + k]
+            j["pu_x"], j["pu_y"], j["pu_w"], j["pu_h"] = x, y, s, s
+            j["ref_slot"] = (-1, -1)
+            for l in ([0, 1] if k % 2 == 0 else [k % 2 - 1 + 1 - (k // 3)]):
+                l = int(l) & 1
+                j["ref_slot"][l] = int(rng.integers(0, 2))
+                j["mv_x"][l] = int(rng.integers(max(-200, (-70 - x) * 4), min(200, (W + 6 - x - s) * 4)))
+                j["mv_y"][l] = int(rng.integers(max(-200, (-70 - y) * 4), min(200, (H + 6 - y - s) * 4)))
+            j["dst_offset"] = off_p
+            org_off[c * 5 + k] = off_o
+            off_p += s * s * 3 // 2
+        off_o += s * s * 3 // 2
+    org_blocks = np.concatenate(org_blocks).astype(np.int16)
+    with hmgpu.Context(W, H, bit_depth, 2) as ctx:
+        for s_, (y_, cb, cr) in enumerate(pics):
+            ctx.ref_upload(s_, y_, cb, cr)
+        pred, sse = ctx.merge_skip_dist(jobs, org_off, org_blocks, off_p)
+        with pytest.raises(hmgpu.HmGpuError):
+            ctx.merge_skip_dist(jobs[:1], np.array([org_blocks.size], np.uint32), org_blocks, off_p)
+    for i, j in enumerate(jobs):
+        s = int(j["pu_w"])
+        po, oo = int(j["dst_offset"]), int(org_off[i])
+        for comp in range(3):
+            cs = s if comp == 0 else s // 2
+            exp = np.ascontiguousarray(_oracle_component(O, pads, j, comp, bit_depth))
+            assert np.array_equal(pred[po:po + cs * cs], exp.ravel()), (i, comp)
+            o = np.ascontiguousarray(org_blocks[oo:oo + cs * cs])
+            assert int(sse[i, comp]) == O.hmo_sse(B.ptr(o), cs, B.ptr(exp), cs, cs, cs, bit_depth), (i, comp, j)
+            po += cs * cs; oo += cs * cs
