@@ -127,6 +127,7 @@ static void tuning_from_env(HmgpuTuning* t)
   t->frac_win_min   = env_int("HMGPU_FRAC_WIN_MIN", 4096);
   t->fs_tma         = env_int("HMGPU_FS_TMA", 1);
   t->pipe_chunk     = env_int("HMGPU_PIPE_CHUNK", 0);
+  t->pipe_edge      = env_int("HMGPU_PIPE_EDGE", 8);
   t->pipeline       = !env_int("HMGPU_NO_PIPELINE", 0);
   t->fastpath       = !env_int("HMGPU_NO_FASTPATH", 0);
   t->server         = env_int("HMGPU_SERVER", 1);
@@ -139,7 +140,7 @@ struct TuneName { const char* name; int HmgpuTuning::* field; };
 static const TuneName k_tune_names[] = {
   { "tz_thread", &HmgpuTuning::tz_thread }, { "tz_thread_min", &HmgpuTuning::tz_thread_min }, { "tz_merge", &HmgpuTuning::tz_merge },
   { "tz_carve", &HmgpuTuning::tz_carve }, { "tz_p2", &HmgpuTuning::tz_p2 }, { "frac_v1", &HmgpuTuning::frac_v1 },
-  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "frac_win", &HmgpuTuning::frac_win }, { "frac_win_min", &HmgpuTuning::frac_win_min }, { "fs_tma", &HmgpuTuning::fs_tma }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipeline", &HmgpuTuning::pipeline },
+  { "frac_overlap", &HmgpuTuning::frac_overlap }, { "frac_win", &HmgpuTuning::frac_win }, { "frac_win_min", &HmgpuTuning::frac_win_min }, { "fs_tma", &HmgpuTuning::fs_tma }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipe_edge", &HmgpuTuning::pipe_edge }, { "pipeline", &HmgpuTuning::pipeline },
   { "fastpath", &HmgpuTuning::fastpath }, { "server", &HmgpuTuning::server }, { "server_idle_us", &HmgpuTuning::server_idle_us },
   { "trace", &HmgpuTuning::trace }, { "server_stats", &HmgpuTuning::server_stats } };
 
@@ -802,12 +803,39 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
                                const int16_t* org_blocks, int n_org_elems, hmgpu_me_result* results)
 {
   const int s_chunk = ctx->tune.pipe_chunk;
-  // a quarter of the batch per chunk: the TZ stage of a chunk is ~17 launches on side streams whose tails overlap best when the
-  // chunk is large (1.18 M jobs, measured end to end: 8 chunks 5.32 ms, 4 chunks 4.72 ms, 2 chunks 4.70 ms)
-  int chunk = s_chunk > 0 ? s_chunk : (n_jobs + 3) / 4;
-  if (s_chunk <= 0) chunk = chunk < 32768 ? 32768 : (chunk > 524288 ? 524288 : chunk);
-  chunk = (chunk + 255) & ~255;
-  const int n_chunks = (n_jobs + chunk - 1) / chunk;
+  // Chunk schedule.  What the pipeline cannot hide is the copy-in of the FIRST chunk and the copy-out of the LAST one, while
+  // the kernels want large chunks (the TZ stage of a chunk is ~17 launches on side streams whose tails overlap best when the
+  // chunk is large, the fractional stage stages one window set per CTU group and chunk).  Default: a short first and last chunk
+  // around two long ones -- 1/8, 3/8, 3/8, 1/8 of the batch (measured end to end on the 1.18 M-job bench batch: equal quarters
+  // 3.86 ms, equal halves 3.77 ms, profiles/r2n_e2e_chunk_sweep.txt).  HMGPU_PIPE_CHUNK=<jobs>: equal chunks of that size.
+  enum { MAX_CHUNKS = 4096 };
+  int n_chunks, chunk;                       // chunk = the longest chunk (sizes the staging buffers)
+  std::vector<int> c_first, c_cnt;
+  if (s_chunk > 0 || n_jobs < 4 * 32768)
+  {
+    chunk = s_chunk > 0 ? s_chunk : 32768;
+    chunk = (chunk + 255) & ~255;
+    if ((n_jobs + chunk - 1) / chunk > MAX_CHUNKS) chunk = ((n_jobs + MAX_CHUNKS - 1) / MAX_CHUNKS + 255) & ~255;
+    for (int f = 0; f < n_jobs; f += chunk) { c_first.push_back(f); c_cnt.push_back(n_jobs - f < chunk ? n_jobs - f : chunk); }
+  }
+  else
+  {
+    const int den = ctx->tune.pipe_edge >= 4 ? ctx->tune.pipe_edge : 8;    // HMGPU_PIPE_EDGE: first / last chunk = 1 / den of the batch
+    const int eighth = ((n_jobs + den - 1) / den + 255) & ~255;
+    int longc = (n_jobs - 2 * eighth + 1) / 2;
+    if (longc > 786432) longc = 786432;      // very large batches: more long chunks instead of longer ones
+    int f = 0;
+    c_first.push_back(f); c_cnt.push_back(eighth); f += eighth;
+    while (n_jobs - f > eighth + longc / 2)
+    {
+      const int c = n_jobs - f - eighth < longc ? n_jobs - f - eighth : longc;
+      c_first.push_back(f); c_cnt.push_back(c); f += c;
+    }
+    c_first.push_back(f); c_cnt.push_back(n_jobs - f);
+    chunk = 0;
+    for (size_t i = 0; i < c_cnt.size(); i++) chunk = c_cnt[i] > chunk ? c_cnt[i] : chunk;
+  }
+  n_chunks = (int)c_first.size();
   if (!ctx->lane_store[1].stream)
   {
     HMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_store[1].stream, cudaStreamNonBlocking));
@@ -865,10 +893,10 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
     rc = hmgpu_reserve_stage(ctx, jb + rb);
     if (rc == HMGPU_OK && !(jobs_pinned && res_pinned)) rc = hmgpu_reserve_pinned(ctx, jb + rb);
   }
-  auto chunk_n = [&](int k) { const int first = k * chunk; return (n_jobs - first < chunk) ? n_jobs - first : chunk; };
+  auto chunk_n = [&](int k) { return c_cnt[k]; };
   // copy stream: jobs of chunk k into its lane's staging buffer (once the lane's previous chunk is done with it), then the scan
   auto prefetch = [&](int k) -> int {
-    const int l = k & 1, first = k * chunk, n = chunk_n(k);
+    const int l = k & 1, first = c_first[k], n = chunk_n(k);
     hmgpu_use_lane(ctx, l);
     char* dp = (char*)ctx->d_stage;
     if (k >= 2) HMGPU_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->lane_done[l], 0));
@@ -894,7 +922,7 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
     hmgpu_use_lane(ctx, k & 1);
     const cudaError_t e = cudaEventSynchronize(ctx->lane_done[k & 1]);
     if (e != cudaSuccess) return hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search, chunk %d: %s", k, cudaGetErrorString(e));
-    if (!res_pinned) memcpy(results + (size_t)k * chunk, (char*)ctx->h_pin + jb, sizeof(hmgpu_me_result) * (size_t)chunk_n(k));
+    if (!res_pinned) memcpy(results + (size_t)c_first[k], (char*)ctx->h_pin + jb, sizeof(hmgpu_me_result) * (size_t)chunk_n(k));
     return HMGPU_OK;
   };
   int next_retire = 0;
@@ -909,7 +937,7 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
     if (so.first_bad != 0xffffffffu)
     {
       rc = hmgpu_fail(ctx, (so.first_bad & 15u) == SCAN_SLOT ? HMGPU_E_STATE : HMGPU_E_INVALID, "job %d: %s",
-                      k * chunk + (int)(so.first_bad >> 4), k_scan_msg[so.first_bad & 15u]);
+                      c_first[k] + (int)(so.first_bad >> 4), k_scan_msg[so.first_bad & 15u]);
       break;
     }
     char* dp = (char*)ctx->d_stage;
@@ -919,7 +947,7 @@ static int me_search_pipelined(hmgpu_ctx* ctx, const hmgpu_me_job* jobs, int n_j
     const bool any_sel = (so.int_kinds & 4u) != 0;
     if ((rc = hmgpu_launch_me(ctx, (const hmgpu_me_job*)dp, n, (any_org || any_sel) ? (const int16_t*)ctx->d_orgblk : NULL, (hmgpu_me_result*)(dp + jb),
                               any_org, (so.int_kinds & 2u) != 0, (so.int_kinds & 1u) != 0, (so.flags_any & HMGPU_F_FRAC) != 0, (int)so.max_win, any_sel))) break;
-    e = cudaMemcpyAsync(res_pinned ? (void*)(results + (size_t)k * chunk) : (void*)(hp + jb), dp + jb, sizeof(hmgpu_me_result) * (size_t)n,
+    e = cudaMemcpyAsync(res_pinned ? (void*)(results + (size_t)c_first[k]) : (void*)(hp + jb), dp + jb, sizeof(hmgpu_me_result) * (size_t)n,
                         cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->lane_done[l], ctx->stream);
     if (e != cudaSuccess) { rc = hmgpu_fail(ctx, HMGPU_E_CUDA, "pipelined search D2H: %s", cudaGetErrorString(e)); break; }

@@ -69,7 +69,8 @@ struct HmgpuTuning
   int frac_overlap;     // HMGPU_FRAC_OVERLAP: 8x8 / 4x4 tile kernels side by side
   int frac_win;         // HMGPU_FRAC_WIN: fractional stage of large 8-bit batches by CTU groups with TMA-staged windows (me_fracw.cu)
   int frac_win_min;     // HMGPU_FRAC_WIN_MIN: batch size from which it is used
-  int pipe_chunk;       // HMGPU_PIPE_CHUNK: jobs per chunk of the pipelined batch path (0: a quarter of the batch)
+  int pipe_chunk;       // HMGPU_PIPE_CHUNK: jobs per chunk of the pipelined batch path (0: short first / last chunk around two long ones)
+  int pipe_edge;        // HMGPU_PIPE_EDGE: the first and the last chunk are 1 / pipe_edge of the batch (default 8)
   int pipeline;         // !HMGPU_NO_PIPELINE
   int fastpath;         // !HMGPU_NO_FASTPATH
   int server;           // HMGPU_SERVER: resident mailbox server for calls of <= HMGPU_SERVER_CTAS jobs
