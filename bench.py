@@ -268,7 +268,9 @@ def run_ours(args, rank, world, local_rank):
         # The dominant stage is integer-pipe work out of L1 / shared memory (the north star's "INT32-pipe roofline"; the task's
         # schema only names hbm | tensor, neither of which bounds it), so the headline roofline is the measured INT32 lane-op
         # rate; the same stage in HBM terms is kept as a sub-object.
-        roofline = {"kernel": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak, "unit": "G int-op/s",
+        kernel_names = {"frac_dist": "fracw_group_kernel (me_fracw.cu)", "tz": "TZ stage: tzt_search_kernel<...> x 14 + tz_search_kernel x 2",
+                        "planes": "phase_planes_kernel"}
+        roofline = {"kernel": kernel_names.get(dom, dom), "stage": dom, "bound": "int32", "achieved": ops / dur / 1e9, "peak": int_peak, "unit": "G int-op/s",
                     "frac": ops / dur / 1e9 / int_peak,
                     "peak_source": "hmgpu_microbench(0): LOP3 + IMAD.IADD lane-ops/s on both integer pipes, measured in this run",
                     "algorithmic_ops_per_step": ops, "launches_per_step": int(prof[dom][1] // args.steps),
