@@ -179,7 +179,7 @@ __device__ __forceinline__ void fw_mbar_wait(uint32_t bar, uint32_t parity)
 // win: the plane's window; (xw, yw): top-left sample of the candidate's tile in window coordinates; ow: source tile, rows already
 // permuted by r -> r ^ c
 template <int TS>
-__device__ __forceinline__ uint32_t fw_tile_satd(const unsigned char* win, int xw, int yw, const uint32_t (&ow)[TS][TS / 4], int c)
+__device__ __forceinline__ uint32_t fw_tile_satd(const unsigned char* win, int xw, int yw, const uint32_t (&ow)[TS][TS / 4], const int (&ro)[TS])
 {
   const int sh = (xw & 3) * 8;
   const uint32_t* q = (const uint32_t*)(win + yw * FW_WW + (xw & ~3));
@@ -190,7 +190,7 @@ __device__ __forceinline__ uint32_t fw_tile_satd(const unsigned char* win, int x
 #pragma unroll
   for (int r = 0; r < TS; r++)
   {
-    const uint32_t* row = q + (r ^ c) * (FW_WW / 4);
+    const uint32_t* row = q + ro[r];
     const uint32_t w0 = row[0], w1 = row[1];
     int h[TS];
     if (TS == 8)
@@ -226,7 +226,7 @@ __device__ __forceinline__ uint32_t fw_pair_absmax(uint32_t ba, uint32_t bb)
 
 template <int TS>
 __device__ __forceinline__ void fw_tile_satd_pair(const unsigned char* win_a, int xa, int ya, const unsigned char* win_b, int xb, int yb,
-                                                  const uint32_t (&ow)[TS][TS / 4], int c, uint32_t& out_a, uint32_t& out_b)
+                                                  const uint32_t (&ow)[TS][TS / 4], const int (&ro)[TS], uint32_t& out_a, uint32_t& out_b)
 {
   const int sha = (xa & 3) * 8, shb = (xb & 3) * 8;
   const uint32_t* qa = (const uint32_t*)(win_a + ya * FW_WW + (xa & ~3));
@@ -238,8 +238,8 @@ __device__ __forceinline__ void fw_tile_satd_pair(const unsigned char* win_a, in
 #pragma unroll
   for (int r = 0; r < TS; r++)
   {
-    const uint32_t* ra = qa + (r ^ c) * (FW_WW / 4);
-    const uint32_t* rb = qb + (r ^ c) * (FW_WW / 4);
+    const uint32_t* ra = qa + ro[r];
+    const uint32_t* rb = qb + ro[r];
     int h[TS], t[TS];
     if (TS == 8)
     {
@@ -303,19 +303,24 @@ __device__ __forceinline__ void fw_tile_satd_pair(const unsigned char* win_a, in
 
 // one warp-wide batch of work items of one list (8x8 or 4x4 tiles) in one phase: item = (tile, group of CPI candidates), idx = the
 // lane's item (items of one candidate group are consecutive: the lanes of a warp hold consecutive tiles)
-template <int TS, int PHASE>
+template <int TS, int PHASE, int NP>
 __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_tiles, int idx, int lane)
 {
-  // half-pel: candidate 0 alone (group 0), then the pairs (1,2) (3,4) (5,6) (7,8); quarter-pel: the four pairs (candidate 0 is
-  // the half-pel winner, whose sum is reused)
-  constexpr int NGRP = PHASE ? 4 : 5;
+  // An item = one tile with NP pairs of candidates (8x8 tiles: one pair; 4x4 tiles: two, so that the per-item work -- table
+  // look-up, tile geometry, source rows, the reduction below -- is paid once per four candidates).  Half-pel: candidate 0 alone
+  // (group 0), then the pairs (1,2) (3,4) (5,6) (7,8); quarter-pel: the four pairs (candidate 0 is the half-pel winner, whose
+  // sum is reused).
+  constexpr int NGRP = PHASE ? 4 / NP : 1 + 4 / NP;
   const bool valid = idx < n_tiles * NGRP;
   uint32_t ji = 0xffffu;
-  uint32_t v[2] = { 0, 0 };
+  uint32_t v[2 * NP];
+#pragma unroll
+  for (int k = 0; k < 2 * NP; k++) v[k] = 0;
   int grp = 0;
   if (valid)
   {
-    grp = (idx >= n_tiles) + (idx >= 2 * n_tiles) + (idx >= 3 * n_tiles) + (NGRP > 4 ? (idx >= 4 * n_tiles) : 0);
+#pragma unroll
+    for (int g = 1; g < NGRP; g++) grp += idx >= g * n_tiles;
     const uint32_t e = tab[idx - grp * n_tiles];
     ji = e >> 6;
     const int t = (int)(e & 63u);
@@ -325,30 +330,39 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
     const int ty = (t * jb.inv_tw) >> 15, tx = t - ty * tw;
     const int c = TS == 8 ? (2 * ty) & 7 : ty & 3;
     uint32_t ow[TS][TS / 4];
+    int ro[TS];                                   // window row offsets (words) in the lane's row order r ^ c
     {
       const uint32_t* o = S.org + (jb.ry + ty * TS) * FW_ORG_PITCH + ((jb.rx + tx * TS) >> 2);
 #pragma unroll
       for (int r = 0; r < TS; r++)
+      {
+        ro[r] = (r ^ c) * (FW_WW / 4);
 #pragma unroll
         for (int w = 0; w < TS / 4; w++) ow[r][w] = o[(r ^ c) * FW_ORG_PITCH + w];
+      }
     }
     const int x0 = jb.xw + tx * TS, y0 = jb.yw + ty * TS;
-    if (PHASE == 0 && grp == 0) v[0] = fw_tile_satd<TS>(S.planes[0], x0, y0, ow, c);
+    if (PHASE == 0 && grp == 0) v[0] = fw_tile_satd<TS>(S.planes[0], x0, y0, ow, ro);
     else
     {
-      const int ca = PHASE ? 1 + 2 * grp : 2 * grp - 1;
-      int qxa, qya, qxb, qyb, sa, sb;
-      if (PHASE == 0)
+#pragma unroll
+      for (int p = 0; p < NP; p++)
       {
-        qxa = 2 * c_refine_h[ca][0]; qya = 2 * c_refine_h[ca][1]; qxb = 2 * c_refine_h[ca + 1][0]; qyb = 2 * c_refine_h[ca + 1][1];
-        sa = ((qya & 3) >> 1) * 2 + ((qxa & 3) >> 1); sb = ((qyb & 3) >> 1) * 2 + ((qxb & 3) >> 1);
+        const int ca = PHASE ? 1 + 2 * (grp * NP + p) : 2 * ((grp - 1) * NP + p) + 1;
+        int qxa, qya, qxb, qyb, sa, sb;
+        if (PHASE == 0)
+        {
+          qxa = 2 * c_refine_h[ca][0]; qya = 2 * c_refine_h[ca][1]; qxb = 2 * c_refine_h[ca + 1][0]; qyb = 2 * c_refine_h[ca + 1][1];
+          sa = ((qya & 3) >> 1) * 2 + ((qxa & 3) >> 1); sb = ((qyb & 3) >> 1) * 2 + ((qxb & 3) >> 1);
+        }
+        else
+        {
+          qxa = 2 * hx + c_refine_q[ca][0]; qya = 2 * hy + c_refine_q[ca][1]; qxb = 2 * hx + c_refine_q[ca + 1][0]; qyb = 2 * hy + c_refine_q[ca + 1][1];
+          sa = fw_slot((qya & 3) * 4 + (qxa & 3)); sb = fw_slot((qyb & 3) * 4 + (qxb & 3));
+        }
+        fw_tile_satd_pair<TS>(S.planes[sa], x0 + (qxa >> 2), y0 + (qya >> 2), S.planes[sb], x0 + (qxb >> 2), y0 + (qyb >> 2), ow, ro,
+                              v[2 * p], v[2 * p + 1]);
       }
-      else
-      {
-        qxa = 2 * hx + c_refine_q[ca][0]; qya = 2 * hy + c_refine_q[ca][1]; qxb = 2 * hx + c_refine_q[ca + 1][0]; qyb = 2 * hy + c_refine_q[ca + 1][1];
-        sa = fw_slot((qya & 3) * 4 + (qxa & 3)); sb = fw_slot((qyb & 3) * 4 + (qxb & 3));
-      }
-      fw_tile_satd_pair<TS>(S.planes[sa], x0 + (qxa >> 2), y0 + (qya >> 2), S.planes[sb], x0 + (qxb >> 2), y0 + (qyb >> 2), ow, c, v[0], v[1]);
     }
   }
   // The lanes of a (job, candidate group) add up their tiles with a segmented shuffle reduction -- they are consecutive lanes --
@@ -358,16 +372,19 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
   const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
   const bool head = lane == 0 || prev != key;
   const uint32_t heads = __ballot_sync(0xffffffffu, head);
-  const uint32_t above = heads & ~((2u << lane) - 1u);      // heads at higher lanes (lane 31: 2u << 31 == 0, mask of all lanes)
-  const int run_end = above ? __ffs(above) - 2 : 31;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
+  if (heads != 0xffffffffu)                                 // (every lane its own job: nothing to add up)
   {
+    const uint32_t above = heads & ~((2u << lane) - 1u);    // heads at higher lanes (lane 31: 2u << 31 == 0, mask of all lanes)
+    const int run_end = above ? __ffs(above) - 2 : 31;
 #pragma unroll
-    for (int k = 0; k < 2; k++)
+    for (int o = 1; o < 32; o <<= 1)
     {
-      const uint32_t t = __shfl_down_sync(0xffffffffu, v[k], o);
-      if (lane + o <= run_end) v[k] += t;
+#pragma unroll
+      for (int k = 0; k < 2 * NP; k++)
+      {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, v[k], o);
+        if (lane + o <= run_end) v[k] += t;
+      }
     }
   }
   if (head && valid)
@@ -375,9 +392,13 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
     if (PHASE == 0 && grp == 0) atomicAdd(&S.acc[0][ji], v[0]);
     else
     {
-      const int ca = PHASE ? 1 + 2 * grp : 2 * grp - 1;
-      atomicAdd(&S.acc[ca][ji], v[0]);
-      atomicAdd(&S.acc[ca + 1][ji], v[1]);
+#pragma unroll
+      for (int p = 0; p < NP; p++)
+      {
+        const int ca = PHASE ? 1 + 2 * (grp * NP + p) : 2 * ((grp - 1) * NP + p) + 1;
+        atomicAdd(&S.acc[ca][ji], v[2 * p]);
+        atomicAdd(&S.acc[ca + 1][ji], v[2 * p + 1]);
+      }
     }
   }
 }
@@ -386,9 +407,9 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
 template <int PHASE>
 __device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
 {
-  constexpr int NGRP = PHASE ? 4 : 5;
+  constexpr int NGRP8 = PHASE ? 4 : 5, NGRP4 = PHASE ? 2 : 3;
   const int lane = threadIdx.x & 31;
-  const int end8 = (n8 * NGRP + 31) & ~31, end = end8 + n4 * NGRP;
+  const int end8 = (n8 * NGRP8 + 31) & ~31, end = end8 + n4 * NGRP4;
   // the next batch is drawn before the current one is worked on: the round trip of the atomic hides under the arithmetic
   int next = 0;
   if (lane == 0) next = atomicAdd(&S.misc.next, 32);
@@ -397,8 +418,8 @@ __device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
     const int base = __shfl_sync(0xffffffffu, next, 0);
     if (base >= end) break;
     if (lane == 0) next = atomicAdd(&S.misc.next, 32);
-    if (base < end8) fw_items<8, PHASE>(S, S.t8, n8, base + lane, lane);
-    else fw_items<4, PHASE>(S, S.t4, n4, base - end8 + lane, lane);
+    if (base < end8) fw_items<8, PHASE, 1>(S, S.t8, n8, base + lane, lane);
+    else fw_items<4, PHASE, 2>(S, S.t4, n4, base - end8 + lane, lane);
   }
 }
 
