@@ -407,7 +407,7 @@ __device__ __forceinline__ void fw_items(FwSmem& S, const uint16_t* tab, int n_t
 template <int PHASE>
 __device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
 {
-  constexpr int NGRP8 = PHASE ? 4 : 5, NGRP4 = PHASE ? 2 : 3;
+  constexpr int NGRP8 = PHASE ? 2 : 3, NGRP4 = PHASE ? 2 : 3;
   const int lane = threadIdx.x & 31;
   const int end8 = (n8 * NGRP8 + 31) & ~31, end = end8 + n4 * NGRP4;
   // the next batch is drawn before the current one is worked on: the round trip of the atomic hides under the arithmetic
@@ -418,7 +418,7 @@ __device__ __forceinline__ void fw_run_phase(FwSmem& S, int n8, int n4)
     const int base = __shfl_sync(0xffffffffu, next, 0);
     if (base >= end) break;
     if (lane == 0) next = atomicAdd(&S.misc.next, 32);
-    if (base < end8) fw_items<8, PHASE, 1>(S, S.t8, n8, base + lane, lane);
+    if (base < end8) fw_items<8, PHASE, 2>(S, S.t8, n8, base + lane, lane);
     else fw_items<4, PHASE, 2>(S, S.t4, n4, base - end8 + lane, lane);
   }
 }
