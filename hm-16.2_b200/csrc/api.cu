@@ -1475,6 +1475,76 @@ int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_
   return HMGPU_OK;
 }
 
+// ---- SAO statistics (sao.cu) ----------------------------------------------------------------------
+int hmgpu_sao_stats(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, const int16_t* org, int org_stride, int width, int height,
+                    int ctu_w, int ctu_h, const uint8_t* ctu_flags, const int32_t skip_r[5], const int32_t skip_b[5], int64_t* stats)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (!rec || !org || !skip_r || !skip_b || !stats) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_sao_stats");
+  if (width < 1 || height < 1 || width > 16384 || height > 16384 || rec_stride < width || org_stride < width)
+    return hmgpu_fail(ctx, HMGPU_E_INVALID, "component of %d x %d samples with strides %d / %d", width, height, rec_stride, org_stride);
+  if (ctu_w < 8 || ctu_h < 8 || ctu_w > 64 || ctu_h > 64) return hmgpu_fail(ctx, HMGPU_E_INVALID, "CTU of %d x %d samples", ctu_w, ctu_h);
+  for (int t = 0; t < 5; t++)
+    if (skip_r[t] < 0 || skip_b[t] < 0 || skip_r[t] >= ctu_w || skip_b[t] >= ctu_h) return hmgpu_fail(ctx, HMGPU_E_INVALID, "skip lines of type %d outside the CTU", t);
+  const int ctus_x = (width + ctu_w - 1) / ctu_w, n_ctus = ctus_x * ((height + ctu_h - 1) / ctu_h);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t rb = round_up(sizeof(int16_t) * (size_t)width * height, 256), fb = round_up((size_t)n_ctus, 256);
+  const size_t sb = round_up(sizeof(int64_t) * 5 * 64 * (size_t)n_ctus, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, 2 * rb + fb + sb))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, 2 * rb + fb + sb))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  for (int y = 0; y < height; y++)               // tight rows on the device
+  {
+    memcpy(hp + sizeof(int16_t) * (size_t)y * width, rec + (size_t)y * rec_stride, sizeof(int16_t) * (size_t)width);
+    memcpy(hp + rb + sizeof(int16_t) * (size_t)y * width, org + (size_t)y * org_stride, sizeof(int16_t) * (size_t)width);
+  }
+  if (ctu_flags) memcpy(hp + 2 * rb, ctu_flags, (size_t)n_ctus);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, 2 * rb + fb, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_sao_stats(ctx, (const int16_t*)dp, width, (const int16_t*)(dp + rb), width, width, height, ctu_w, ctu_h,
+                                   ctu_flags ? (const uint8_t*)(dp + 2 * rb) : NULL, skip_r, skip_b, (long long*)(dp + 2 * rb + fb)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + 2 * rb + fb, dp + 2 * rb + fb, sizeof(int64_t) * 5 * 64 * (size_t)n_ctus, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(stats, hp + 2 * rb + fb, sizeof(int64_t) * 5 * 64 * (size_t)n_ctus);
+  return HMGPU_OK;
+}
+
+int hmgpu_sao_apply(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, int width, int height, int ctu_w, int ctu_h,
+                    const uint8_t* ctu_flags, const int8_t* types, const int32_t* offsets, int16_t* out)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (!rec || !types || !offsets || !out) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_sao_apply");
+  if (width < 1 || height < 1 || width > 16384 || height > 16384 || rec_stride < width)
+    return hmgpu_fail(ctx, HMGPU_E_INVALID, "component of %d x %d samples with stride %d", width, height, rec_stride);
+  if (ctu_w < 8 || ctu_h < 8 || ctu_w > 64 || ctu_h > 64) return hmgpu_fail(ctx, HMGPU_E_INVALID, "CTU of %d x %d samples", ctu_w, ctu_h);
+  const int ctus_x = (width + ctu_w - 1) / ctu_w, n_ctus = ctus_x * ((height + ctu_h - 1) / ctu_h);
+  for (int c = 0; c < n_ctus; c++)
+    if (types[c] < -1 || types[c] > 4) return hmgpu_fail(ctx, HMGPU_E_INVALID, "CTU %d: SAO type %d", c, types[c]);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t rb = round_up(sizeof(int16_t) * (size_t)width * height, 256), fb = round_up((size_t)n_ctus, 256);
+  const size_t ob = round_up(sizeof(int32_t) * 32 * (size_t)n_ctus, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, 2 * rb + 2 * fb + ob))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, 2 * rb + 2 * fb + ob))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  for (int y = 0; y < height; y++) memcpy(hp + sizeof(int16_t) * (size_t)y * width, rec + (size_t)y * rec_stride, sizeof(int16_t) * (size_t)width);
+  if (ctu_flags) memcpy(hp + rb, ctu_flags, (size_t)n_ctus);
+  memcpy(hp + rb + fb, types, (size_t)n_ctus);
+  memcpy(hp + rb + 2 * fb, offsets, sizeof(int32_t) * 32 * (size_t)n_ctus);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, rb + 2 * fb + ob, cudaMemcpyHostToDevice, ctx->stream));
+  int16_t* d_out = (int16_t*)(dp + rb + 2 * fb + ob);
+  if ((rc = hmgpu_launch_sao_apply(ctx, (const int16_t*)dp, width, width, height, ctu_w, ctu_h, ctu_flags ? (const uint8_t*)(dp + rb) : NULL,
+                                   (const int8_t*)(dp + rb + fb), (const int32_t*)(dp + rb + 2 * fb), d_out))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + rb + 2 * fb + ob, d_out, sizeof(int16_t) * (size_t)width * height, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out, hp + rb + 2 * fb + ob, sizeof(int16_t) * (size_t)width * height);
+  return HMGPU_OK;
+}
+
 // ---- intra mode pre-selection (intra.cu) ---------------------------------------------------------
 int hmgpu_intra_costs(hmgpu_ctx* ctx, const hmgpu_intra_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
                       const int16_t* ref_lines, int n_ref_elems, uint32_t* dist)

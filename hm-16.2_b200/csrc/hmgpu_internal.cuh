@@ -236,6 +236,10 @@ int hmgpu_launch_me(hmgpu_ctx* ctx, const hmgpu_me_job* d_jobs, int n_jobs, cons
 int hmgpu_launch_dist(hmgpu_ctx* ctx, const int16_t* d_org, const int16_t* d_cur,
                       const hmgpu_dist_item* d_items, int n_items, uint32_t* d_out);
 int hmgpu_launch_intra_costs(hmgpu_ctx* ctx, const hmgpu_intra_job* d_jobs, int n_jobs, const int16_t* d_org, const int16_t* d_lines, uint32_t* d_dist);
+int hmgpu_launch_sao_stats(hmgpu_ctx* ctx, const int16_t* d_rec, int rec_stride, const int16_t* d_org, int org_stride, int width, int height,
+                           int ctu_w, int ctu_h, const uint8_t* d_flags, const int32_t* skip_r, const int32_t* skip_b, long long* d_stats);
+int hmgpu_launch_sao_apply(hmgpu_ctx* ctx, const int16_t* d_src, int stride, int width, int height, int ctu_w, int ctu_h, const uint8_t* d_flags,
+                           const int8_t* d_types, const int32_t* d_offsets, int16_t* d_dst);
 int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst);
 int hmgpu_launch_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int with_chroma, int16_t* d_dst);
 int hmgpu_launch_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int func, uint32_t* d_out);

@@ -49,7 +49,7 @@ EXPORTS = [
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
-    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform",
+    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
@@ -104,6 +104,8 @@ def lib():
     L.hmgpu_search_range.restype = None
     L.hmgpu_dist_batch.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp]
     L.hmgpu_intra_costs.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp]
+    L.hmgpu_sao_stats.argtypes = [vp, vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp]
+    L.hmgpu_sao_apply.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp]
     L.hmgpu_mv_bits.argtypes = [ci] * 5
     L.hmgpu_mv_bits.restype = cu
     L.hmgpu_mv_cost.argtypes = [cu] + [ci] * 5
@@ -305,6 +307,32 @@ class Context:
         out = np.zeros(len(items), np.uint32)
         self._check(self.L.hmgpu_dist_batch(self.h, org.ctypes.data, org.size, cur.ctypes.data, cur.size,
                                             items.ctypes.data, len(items), out.ctypes.data))
+        return out
+
+    def sao_stats(self, rec, org, ctu_w, ctu_h, skip_r, skip_b, ctu_flags=None):
+        """SAO statistics of one picture component (hmgpu_sao_stats): -> int64 [n_ctus, 5 types, 2 (diff, count), 32 classes]"""
+        rec = np.ascontiguousarray(rec, np.int16)
+        org = np.ascontiguousarray(org, np.int16)
+        h, w = rec.shape
+        n_ctus = ((w + ctu_w - 1) // ctu_w) * ((h + ctu_h - 1) // ctu_h)
+        skip_r = np.ascontiguousarray(skip_r, np.int32)
+        skip_b = np.ascontiguousarray(skip_b, np.int32)
+        flags = None if ctu_flags is None else np.ascontiguousarray(ctu_flags, np.uint8)
+        out = np.zeros((n_ctus, 5, 2, 32), np.int64)
+        self._check(self.L.hmgpu_sao_stats(self.h, rec.ctypes.data, w, org.ctypes.data, w, w, h, ctu_w, ctu_h,
+                                           None if flags is None else flags.ctypes.data, skip_r.ctypes.data, skip_b.ctypes.data, out.ctypes.data))
+        return out
+
+    def sao_apply(self, rec, ctu_w, ctu_h, types, offsets, ctu_flags=None):
+        """SAO applied to one picture component (hmgpu_sao_apply): -> int16 picture"""
+        rec = np.ascontiguousarray(rec, np.int16)
+        h, w = rec.shape
+        types = np.ascontiguousarray(types, np.int8)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        flags = None if ctu_flags is None else np.ascontiguousarray(ctu_flags, np.uint8)
+        out = np.zeros_like(rec)
+        self._check(self.L.hmgpu_sao_apply(self.h, rec.ctypes.data, w, w, h, ctu_w, ctu_h, None if flags is None else flags.ctypes.data,
+                                           types.ctypes.data, offsets.ctypes.data, out.ctypes.data))
         return out
 
     def intra_costs(self, jobs, org_blocks, ref_lines):

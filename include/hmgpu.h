@@ -222,6 +222,36 @@ int hmgpu_dist_batch(hmgpu_ctx* ctx, const int16_t* org, int n_org, const int16_
                      const hmgpu_dist_item* items, int n_items, uint32_t* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * SAO statistics of one picture component (first half).  Replaces
+ * TEncSampleAdaptiveOffset::getStatistics -> getBlkStats (TEncSampleAdaptiveOffset.cpp:312-363, 910-1340)
+ * without the pre-deblock sample mode (SAOLcuBoundary 0): per CTU and SAO type (EO_0, EO_90, EO_135, EO_45, BO)
+ * the sum of (source - reconstruction) and the sample count per class.  deriveModeNewRDO / deriveModeMergeRDO
+ * (rate-distortion with CABAC estimates) stay on the host.
+ *   rec / org       the deblocked reconstruction and the source of the component, width x height samples
+ *   ctu_w / ctu_h   CTU size in samples of this component (64 for luma, 32 for 4:2:0 chroma)
+ *   ctu_flags       per CTU, or NULL for a picture of one slice and one tile: bit 0 left, bit 2 above, bit 4 above-left
+ *                   neighbour available (TComPicSym::deriveLoopFilterBoundaryAvailibility); right / below / above-right
+ *                   follow from the picture geometry, as getStatistics sets them
+ *   skip_r / skip_b m_skipLinesR / m_skipLinesB of the component, per SAO type
+ *   stats           [n_ctus][5 types][2: diff, count][32 classes]; EO classes are edgeType + 2 (0..4)
+ * ------------------------------------------------------------------------------------------ */
+int hmgpu_sao_stats(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, const int16_t* org, int org_stride, int width, int height,
+                    int ctu_w, int ctu_h, const uint8_t* ctu_flags, const int32_t skip_r[5], const int32_t skip_b[5], int64_t* stats);
+
+/* SAO applied to one picture component: TComSampleAdaptiveOffset::offsetCTU -> offsetBlock
+ * (TComSampleAdaptiveOffset.cpp:309-620) for every CTU.
+ *   rec        the deblocked reconstruction (the reference's m_tempPicYuv copy), width x height samples
+ *   types      per CTU: SAO type 0..4 (EO_0, EO_90, EO_135, EO_45, BO) of the component's SAOOffset after
+ *              reconstructBlkSAOParams, or -1 for SAO_MODE_OFF
+ *   offsets    per CTU 32 values, SAOOffset::offset: the EO offsets of the classes edgeType + 2 (0..4), the BO offsets of
+ *              the 32 bands
+ *   ctu_flags  per CTU all eight availabilities of deriveLoopFilterBoundaryAvailibility -- bit 0 left, 1 right, 2 above,
+ *              3 below, 4 above-left, 5 above-right, 6 below-left, 7 below-right -- or NULL for one slice and one tile
+ *   out        width x height samples, stride = width */
+int hmgpu_sao_apply(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, int width, int height, int ctu_w, int ctu_h,
+                    const uint8_t* ctu_flags, const int8_t* types, const int32_t* offsets, int16_t* out);
+
+/* ---------------------------------------------------------------------------------------------
  * Intra mode pre-selection of luma PUs.  Replaces the first-pass loop of
  * TEncSearch::estIntraPredQT (TEncSearch.cpp:2352-2395): for every one of the 35 modes
  * TComPrediction::predIntraAng (TComPrediction.cpp:407-492, blocks without DPCM) followed by

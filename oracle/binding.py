@@ -19,6 +19,7 @@ OUT = os.path.join(HERE, "_ref")
 i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 vp = C.c_void_p
 ci = C.c_int
 cu = C.c_uint
@@ -106,6 +107,8 @@ def oracle():
     L.hmo_intra_use_filtered.restype = ci
     L.hmo_intra_use_filtered.argtypes = [ci, ci, ci]
     L.hmo_intra_costs.argtypes = [vp, vp, vp, ci, ci, ci, u32p]
+    L.hmo_sao_blk_stats.argtypes = [vp, ci, vp, ci, ci, ci, ci, i32p, i32p, ci, i64p, i64p]
+    L.hmo_sao_offset_block.argtypes = [ci, i32p, vp, ci, vp, ci, ci, ci, ci, ci]
     _oracle = L
     return L
 
@@ -161,6 +164,8 @@ def ref():
     L.ref_intra_pred.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp]
     L.ref_intra_use_filtered.restype = ci
     L.ref_intra_use_filtered.argtypes = [ci, ci, ci]
+    L.ref_sao_blk_stats.argtypes = [vp, ci, vp, ci, ci, ci, ci, i32p, i32p, ci, i64p, i64p]
+    L.ref_sao_offset_block.argtypes = [ci, i32p, vp, ci, vp, ci, ci, ci, ci, ci]
     _ref = L
     return L
 

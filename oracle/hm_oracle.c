@@ -1027,3 +1027,108 @@ void hmo_intra_costs(const int16_t* line_unfiltered, const int16_t* line_filtere
     dist[mode] = (flags & 8) ? hmo_hads(org, n, pred, n, n, n, bit_depth) : hmo_sad(org, n, pred, n, n, n, 0, bit_depth, 0);
   }
 }
+
+
+/* ==== SAO statistics ===================================================================
+ * Restates TEncSampleAdaptiveOffset::getBlkStats (TEncSampleAdaptiveOffset.cpp:910-1340) with
+ * isCalculatePreDeblockSamples = false.  The reference walks each line with running sign buffers; the class of a sample
+ * only depends on the sample and its two neighbours along the direction of the type,
+ *   edgeType = sgn(c - a) + sgn(c - b),
+ * so the statistics are restated per sample, with the region of each type written out: which samples of the block are
+ * visited depends on the availability of the neighbouring blocks and on the lines skipped next to the right / bottom
+ * boundary (not yet deblocked when the statistics are gathered per CTU). */
+static int hmo_sgn(int v) { return (v > 0) - (v < 0); }
+
+void hmo_sao_blk_stats(const int16_t* src, int src_stride, const int16_t* org, int org_stride, int w, int h, int flags,
+                       const int32_t skip_r[5], const int32_t skip_b[5], int bit_depth, int64_t diff[5][32], int64_t count[5][32])
+{
+  const int L = flags & 1, R = (flags >> 1) & 1, A = (flags >> 2) & 1, B = (flags >> 3) & 1, AL = (flags >> 4) & 1, AR = (flags >> 5) & 1;
+  memset(diff, 0, sizeof(int64_t) * 5 * 32);
+  memset(count, 0, sizeof(int64_t) * 5 * 32);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int16_t* p = src + (ptrdiff_t)y * src_stride + x;
+      const int c = p[0], d = org[(ptrdiff_t)y * org_stride + x] - c;
+      /* EO_0 (:947-1004): left and right neighbour */
+      if (y < (B ? h - skip_b[0] : h) && x >= (L ? 0 : 1) && x < (R ? w - skip_r[0] : w - 1))
+      {
+        const int e = 2 + hmo_sgn(c - p[-1]) + hmo_sgn(c - p[1]);
+        diff[0][e] += d; count[0][e]++;
+      }
+      /* EO_90 (:1005-1091): above and below */
+      if (y >= (A ? 0 : 1) && y < (B ? h - skip_b[1] : h - 1) && x < (R ? w - skip_r[1] : w))
+      {
+        const int e = 2 + hmo_sgn(c - p[-src_stride]) + hmo_sgn(c - p[src_stride]);
+        diff[1][e] += d; count[1][e]++;
+      }
+      /* EO_135 (:1092-1190): above-left and below-right; the first line has its own range (:1129-1141) */
+      {
+        const int sx = L ? 0 : 1, ex = R ? w - skip_r[2] : w - 1, ey = B ? h - skip_b[2] : h - 1;
+        const int in = y == 0 ? (x >= (AL ? 0 : 1) && x < (A ? ex : 1)) : (y < ey && x >= sx && x < ex);
+        if (in)
+        {
+          const int e = 2 + hmo_sgn(c - p[-src_stride - 1]) + hmo_sgn(c - p[src_stride + 1]);
+          diff[2][e] += d; count[2][e]++;
+        }
+      }
+      /* EO_45 (:1191-1292): above-right and below-left; first line :1226-1245 */
+      {
+        const int sx = L ? 0 : 1, ex = R ? w - skip_r[3] : w - 1, ey = B ? h - skip_b[3] : h - 1;
+        const int in = y == 0 ? (x >= (A ? sx : ex) && x < ((!R && AR) ? w : ex)) : (y < ey && x >= sx && x < ex);
+        if (in)
+        {
+          const int e = 2 + hmo_sgn(c - p[-src_stride + 1]) + hmo_sgn(c - p[src_stride - 1]);
+          diff[3][e] += d; count[3][e]++;
+        }
+      }
+      /* BO (:1293-1340): band of the sample */
+      if (y < (B ? h - skip_b[4] : h) && x < (R ? w - skip_r[4] : w))
+      {
+        const int b = c >> (bit_depth - 5);
+        diff[4][b] += d; count[4][b]++;
+      }
+    }
+}
+
+
+/* TComSampleAdaptiveOffset::offsetBlock (TComSampleAdaptiveOffset.cpp:309-545), restated per sample like the statistics:
+ * the region of each type (first and last line of the diagonal types on their own, :407-415, :441-449, :468-476, :496-504). */
+void hmo_sao_offset_block(int type, const int32_t* offset, const int16_t* src, int src_stride, int16_t* res, int res_stride,
+                          int w, int h, int flags, int bit_depth)
+{
+  const int L = flags & 1, R = (flags >> 1) & 1, A = (flags >> 2) & 1, B = (flags >> 3) & 1;
+  const int AL = (flags >> 4) & 1, AR = (flags >> 5) & 1, BL = (flags >> 6) & 1, BR = (flags >> 7) & 1;
+  const int maxv = (1 << bit_depth) - 1;
+  const int sx = L ? 0 : 1, ex = R ? w : w - 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+    {
+      const int16_t* p = src + (ptrdiff_t)y * src_stride + x;
+      const int c = p[0];
+      int in = 0, cls = 0;
+      switch (type)
+      {
+        case 0: in = x >= sx && x < ex; if (in) cls = 2 + hmo_sgn(c - p[-1]) + hmo_sgn(c - p[1]); break;
+        case 1: in = y >= (A ? 0 : 1) && y < (B ? h : h - 1); if (in) cls = 2 + hmo_sgn(c - p[-src_stride]) + hmo_sgn(c - p[src_stride]); break;
+        case 2:
+          if (y == 0) in = x >= (AL ? 0 : 1) && x < (A ? ex : 1);
+          else if (y == h - 1) in = x >= (B ? sx : w - 1) && x < (BR ? w : w - 1);
+          else in = x >= sx && x < ex;
+          if (in) cls = 2 + hmo_sgn(c - p[-src_stride - 1]) + hmo_sgn(c - p[src_stride + 1]);
+          break;
+        case 3:
+          if (y == 0) in = x >= (A ? sx : w - 1) && x < (AR ? w : w - 1);
+          else if (y == h - 1) in = x >= (BL ? 0 : 1) && x < (B ? ex : 1);
+          else in = x >= sx && x < ex;
+          if (in) cls = 2 + hmo_sgn(c - p[-src_stride + 1]) + hmo_sgn(c - p[src_stride - 1]);
+          break;
+        default: in = 1; cls = c >> (bit_depth - 5); break;
+      }
+      if (in)
+      {
+        const int v = c + offset[cls];
+        res[(ptrdiff_t)y * res_stride + x] = (int16_t)(v < 0 ? 0 : (v > maxv ? maxv : v));
+      }
+    }
+}

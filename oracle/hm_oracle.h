@@ -91,6 +91,19 @@ int  hmo_intra_use_filtered(int mode, int n, int no_smooth);
 void hmo_intra_costs(const int16_t* line_unfiltered, const int16_t* line_filtered, const int16_t* org, int n, int bit_depth,
                      int flags, uint32_t dist[35]);
 
+/* ---- SAO statistics (first half): one block of one component, TEncSampleAdaptiveOffset::getBlkStats without the
+ * pre-deblock sample mode.  flags: 1 left, 2 right, 4 above, 8 below, 16 above-left, 32 above-right available.
+ * diff / count: [type 0..4 = EO_0, EO_90, EO_135, EO_45, BO][class]; EO classes are edgeType + 2 (0..4), BO classes the 32 bands. */
+void hmo_sao_blk_stats(const int16_t* src, int src_stride, const int16_t* org, int org_stride, int w, int h, int flags,
+                       const int32_t skip_r[5], const int32_t skip_b[5], int bit_depth, int64_t diff[5][32], int64_t count[5][32]);
+
+/* SAO applied to one block: TComSampleAdaptiveOffset::offsetBlock (TComSampleAdaptiveOffset.cpp:309-545).
+ * flags: 1 left, 2 right, 4 above, 8 below, 16 above-left, 32 above-right, 64 below-left, 128 below-right available.
+ * type 0..4 as above; offset[32]: EO offsets of the classes edgeType + 2 (0..4), BO offsets of the 32 bands.
+ * res receives the visited samples only (the reference leaves the others as they are). */
+void hmo_sao_offset_block(int type, const int32_t* offset, const int16_t* src, int src_stride, int16_t* res, int res_stride,
+                          int w, int h, int flags, int bit_depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,7 @@
 #include "TLibCommon/TComPrediction.h"
 #include "TLibEncoder/TEncCfg.h"
 #include "TLibEncoder/TEncSearch.h"
+#include "TLibEncoder/TEncSampleAdaptiveOffset.h"
 #undef private
 #undef protected
 
@@ -492,6 +493,45 @@ int ref_intra_use_filtered(int mode, int n, int disableSmoothing)
 {
   ensure_init();
   return TComPrediction::filteringIntraReferenceSamples(COMPONENT_Y, mode, n, n, CHROMA_420, disableSmoothing != 0) ? 1 : 0;
+}
+
+// ---- f3 (first half): the real TEncSampleAdaptiveOffset::getBlkStats on one block of one component, without the pre-deblock
+//      sample mode.  flags: 1 left, 2 right, 4 above, 8 below, 16 above-left, 32 above-right available.
+void ref_sao_blk_stats(const int16_t* src, int srcStride, const int16_t* org, int orgStride, int w, int h, int flags,
+                       const int32_t* skipR, const int32_t* skipB, int bitDepth, int64_t* diff /* [5][32] */, int64_t* count)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  static TEncSampleAdaptiveOffset* sao = NULL;
+  if (!sao) { sao = new TEncSampleAdaptiveOffset; sao->m_maxCUWidth = 64; sao->m_maxCUHeight = 64; }
+  for (int t = 0; t < NUM_SAO_NEW_TYPES; t++)
+  {
+    sao->m_skipLinesR[COMPONENT_Y][t] = skipR[t];
+    sao->m_skipLinesB[COMPONENT_Y][t] = skipB[t];
+  }
+  SAOStatData st[NUM_SAO_NEW_TYPES];
+  sao->getBlkStats(COMPONENT_Y, st, (Pel*)src, (Pel*)org, srcStride, orgStride, w, h,
+                   (flags & 1) != 0, (flags & 2) != 0, (flags & 4) != 0, (flags & 8) != 0, (flags & 16) != 0, (flags & 32) != 0,
+                   false, false
+#if SAO_ENCODE_ALLOW_USE_PREDEBLOCK
+                   , false
+#endif
+                   );
+  for (int t = 0; t < NUM_SAO_NEW_TYPES; t++)
+    for (int c = 0; c < 32; c++) { diff[t * 32 + c] = st[t].diff[c]; count[t * 32 + c] = st[t].count[c]; }
+}
+
+// f3: the real TComSampleAdaptiveOffset::offsetBlock.  flags as ref_sao_blk_stats plus 64 below-left, 128 below-right.
+void ref_sao_offset_block(int type, const int32_t* offset, const int16_t* src, int srcStride, int16_t* res, int resStride,
+                          int w, int h, int flags, int bitDepth)
+{
+  ensure_init(); set_bitdepth(bitDepth);
+  static TEncSampleAdaptiveOffset* sao = NULL;
+  if (!sao) { sao = new TEncSampleAdaptiveOffset; sao->m_maxCUWidth = 64; sao->m_maxCUHeight = 64; }
+  Int off[MAX_NUM_SAO_CLASSES];
+  for (int i = 0; i < MAX_NUM_SAO_CLASSES; i++) off[i] = offset[i];
+  sao->offsetBlock(COMPONENT_Y, type, off, (Pel*)src, (Pel*)res, srcStride, resStride, w, h,
+                   (flags & 1) != 0, (flags & 2) != 0, (flags & 4) != 0, (flags & 8) != 0, (flags & 16) != 0, (flags & 32) != 0,
+                   (flags & 64) != 0, (flags & 128) != 0);
 }
 
 } // extern "C"

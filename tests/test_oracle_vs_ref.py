@@ -164,3 +164,59 @@ def test_intra_prediction_all_modes(bd):
                     R.ref_intra_pred(bd, B.ptr(line), n, mode, above, left, edge, B.ptr(a))
                     O.hmo_intra_pred(B.ptr(line), n, mode, bd, above, left, edge, B.ptr(b))
                     assert np.array_equal(a, b), (n, mode, above, left, edge, kind)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_sao_block_statistics(bd):
+    """f3 (first half): hmo_sao_blk_stats against the reference's TEncSampleAdaptiveOffset::getBlkStats for every combination
+    of neighbour availability, the skip-line sets HM uses, whole and partial CTUs, luma and chroma block sizes."""
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(90 + bd)
+    mx = (1 << bd) - 1
+    skips = [([5, 5, 5, 5, 5], [4, 4, 4, 4, 4]), ([3, 3, 3, 3, 3], [2, 2, 2, 2, 2]), ([5, 5, 5, 5, 4], [3, 3, 3, 3, 4]), ([0, 0, 0, 0, 0], [0, 0, 0, 0, 0])]
+    for it in range(160):
+        w, h = [(64, 64), (32, 32), (64, 56), (32, 28), (16, 16), (48, 64), (8, 8)][it % 7]
+        pic = rng.integers(0, mx + 1, (h + 8, w + 8)).astype(np.int16)
+        if it % 3 == 0:     # smooth content: many flat / monotone neighbourhoods (edge classes 0 ties)
+            pic = (pic // 64 * 64 + rng.integers(0, 3, pic.shape)).astype(np.int16)
+        org = np.clip(pic + rng.integers(-6, 7, pic.shape), 0, mx).astype(np.int16)
+        flags = int(rng.integers(0, 64)) if it >= 8 else [0, 63, 1, 2, 4, 8, 16, 32][it]
+        sr, sb = skips[it % 4]
+        sr, sb = np.array(sr, np.int32), np.array(sb, np.int32)
+        st = w + 8
+        d0, c0 = np.zeros((5, 32), np.int64), np.zeros((5, 32), np.int64)
+        d1, c1 = np.zeros((5, 32), np.int64), np.zeros((5, 32), np.int64)
+        R.ref_sao_blk_stats(B.ptr(pic, 4 * st + 4), st, B.ptr(org, 4 * st + 4), st, w, h, flags, sr, sb, bd, d0, c0)
+        O.hmo_sao_blk_stats(B.ptr(pic, 4 * st + 4), st, B.ptr(org, 4 * st + 4), st, w, h, flags, sr, sb, bd, d1, c1)
+        assert np.array_equal(c0, c1), (it, w, h, flags, np.argwhere(c0 != c1)[:4])
+        assert np.array_equal(d0, d1), (it, w, h, flags)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_sao_offset_block(bd):
+    """f3: hmo_sao_offset_block against the reference's TComSampleAdaptiveOffset::offsetBlock, all five types, every availability
+    combination (first / last line rules of the diagonal types), offsets that clip at both ends of the sample range."""
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(120 + bd)
+    mx = (1 << bd) - 1
+    for it in range(300):
+        w, h = [(64, 64), (32, 32), (64, 56), (32, 28), (16, 16), (8, 8)][it % 6]
+        pic = rng.integers(0, mx + 1, (h + 8, w + 8)).astype(np.int16)
+        if it % 3 == 0:
+            pic = (pic // 64 * 64 + rng.integers(0, 3, pic.shape)).astype(np.int16)
+        if it % 5 == 0:
+            pic = rng.choice(np.array([0, 1, mx - 1, mx], np.int16), pic.shape)
+        typ = it % 5
+        off = np.zeros(32, np.int32)
+        if typ < 4:
+            off[:5] = [int(rng.integers(0, 8)), int(rng.integers(0, 8)), 0, -int(rng.integers(0, 8)), -int(rng.integers(0, 8))]
+        else:
+            b0 = int(rng.integers(0, 29))
+            off[b0:b0 + 4] = rng.integers(-7, 8, 4)
+        flags = int(rng.integers(0, 256)) if it >= 10 else [0, 255, 1, 2, 4, 8, 16, 32, 64, 128][it]
+        st = w + 8
+        a = np.full_like(pic, -5)
+        b = np.full_like(pic, -5)
+        R.ref_sao_offset_block(typ, off, B.ptr(pic, 4 * st + 4), st, B.ptr(a, 4 * st + 4), st, w, h, flags, bd)
+        O.hmo_sao_offset_block(typ, off, B.ptr(pic, 4 * st + 4), st, B.ptr(b, 4 * st + 4), st, w, h, flags, bd)
+        assert np.array_equal(a, b), (it, typ, w, h, flags, np.argwhere(a != b)[:4])
