@@ -263,8 +263,8 @@ def run_ours(args, rank, world, local_rank):
                   "points per job: bound by latency / instruction issue, not by HBM (DRAM traffic << algorithmic bytes: the planes "
                   "are served by L2); see roofline_int32 and full_search.roofline for the integer-pipe view",
             "frac_dist": "the fractional stage (one CTA per (reference, CTU) group of jobs, windows of the phase planes staged by TMA, "
-                         "me_fracw.cu) is bound by integer issue (ncu: profiles/r2k_ncu_fracw_group.csv: 64 % issue active, ALU pipe "
-                         "54 %), not by HBM: DRAM traffic 0.47 GB per step against 0.60 GB algorithmic; see roofline_int32"}
+                         "me_fracw.cu) is bound by integer issue (ncu: profiles/r2k_ncu_fracw_group.csv: 62 % issue active, ALU pipe "
+                         "52 %, FMA-heavy pipe 47 %), not by HBM: DRAM traffic 0.47 GB per step against 0.60 GB algorithmic; see roofline_int32"}
         # The dominant stage is integer-pipe work out of L1 / shared memory (the north star's "INT32-pipe roofline"; the task's
         # schema only names hbm | tensor, neither of which bounds it), so the headline roofline is the measured INT32 lane-op
         # rate; the same stage in HBM terms is kept as a sub-object.
