@@ -149,6 +149,143 @@ phase_planes_kernel(Px* __restrict__ planes, size_t plane_elems, int pitch, int 
   }
 }
 
+// ---- 8-bit pictures: the same two passes on packed operands ---------------------------------------------------------------
+// The horizontal pass reads the source tile as packed bytes: the eight taps of an output are two IDP.4A (unsigned pixels x
+// signed taps, the taps of a phase as two constant words), the byte alignment of the four outputs of a thread comes from funnel
+// shifts of three aligned words.  The vertical pass reads the 14-bit intermediates as PAIRS of vertically adjacent rows in one
+// word (the horizontal pass stores them that way): an even output row is four IDP.2A, the odd row below it five (its first and
+// last tap stand alone in their pair), instead of eight IMAD each.  Same integers, same rounding: ncu had shown the kernel
+// bound by instruction issue (76 % issue active, profiles/r2l_ncu_misc_kernels.csv), not by the 41 MB it writes.
+__host__ __device__ constexpr uint32_t pp_pack4(int a, int b, int c, int d)
+{
+  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+__host__ __device__ constexpr int pp_tap(int f, int k)
+{
+  return f == 1 ? (k == 0 ? -1 : k == 1 ? 4 : k == 2 ? -10 : k == 3 ? 58 : k == 4 ? 17 : k == 5 ? -5 : k == 6 ? 1 : 0)
+       : f == 2 ? (k == 0 ? -1 : k == 1 ? 4 : k == 2 ? -11 : k == 3 ? 40 : k == 4 ? 40 : k == 5 ? -11 : k == 6 ? 4 : -1)
+       : f == 3 ? (k == 0 ? 0 : k == 1 ? 1 : k == 2 ? -5 : k == 3 ? 17 : k == 4 ? 58 : k == 5 ? -10 : k == 6 ? 4 : -1)
+       : (k == 3 ? 64 : 0);
+}
+// taps k0..k0+1 of phase F as the two low bytes of a word (IDP.2A.LO multiplies them with the low / high half of its first operand)
+template <int F, int K0> struct PpTap2 { static constexpr uint32_t w = pp_pack4(K0 < 0 ? 0 : pp_tap(F, K0), K0 + 1 > 7 ? 0 : pp_tap(F, K0 + 1), 0, 0); };
+template <int F> struct PpTap4 { static constexpr uint32_t lo = pp_pack4(pp_tap(F, 0), pp_tap(F, 1), pp_tap(F, 2), pp_tap(F, 3)),
+                                                           hi = pp_pack4(pp_tap(F, 4), pp_tap(F, 5), pp_tap(F, 6), pp_tap(F, 7)); };
+
+__device__ __forceinline__ int pp_dp2a(uint32_t pair, uint32_t taps, int acc)
+{
+  int r;
+  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(pair), "r"(taps), "r"(acc));
+  return r;
+}
+
+#define PP8_SWW ((PP_TX + 12) / 4)   // source tile words per row: columns -4 .. +7 around the tile (aligned words)
+
+template <int FY>
+__device__ __forceinline__ void pp8_vertical(const uint32_t (&p)[5][4], int off2, int shift2, int (&even)[4], int (&odd)[4])
+{
+#pragma unroll
+  for (int e = 0; e < 4; e++)
+  {
+    int a = off2, b = off2;
+    a = pp_dp2a(p[0][e], PpTap2<FY, 0>::w, a); a = pp_dp2a(p[1][e], PpTap2<FY, 2>::w, a);
+    a = pp_dp2a(p[2][e], PpTap2<FY, 4>::w, a); a = pp_dp2a(p[3][e], PpTap2<FY, 6>::w, a);
+    b = pp_dp2a(p[0][e], PpTap2<FY, -1>::w, b); b = pp_dp2a(p[1][e], PpTap2<FY, 1>::w, b); b = pp_dp2a(p[2][e], PpTap2<FY, 3>::w, b);
+    b = pp_dp2a(p[3][e], PpTap2<FY, 5>::w, b); b = pp_dp2a(p[4][e], PpTap2<FY, 7>::w, b);
+    even[e] = min(255, max(0, a >> shift2));
+    odd[e] = min(255, max(0, b >> shift2));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+phase_planes8_kernel(uint8_t* __restrict__ planes, size_t plane_elems, int pitch, int pw, int ph)
+{
+  __shared__ uint32_t s_src[PP_SH][PP8_SWW];                // packed bytes, word 0 = columns x0-4 .. x0-1
+  __shared__ __align__(16) uint32_t s_hp[4][(PP_SH + 1) / 2][PP_TX];      // [phase][row pair][column] = (row 2j | row 2j+1 << 16); read as uint4
+  const int x0 = blockIdx.x * PP_TX, y0 = blockIdx.y * PP_TY;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < PP_SH * PP8_SWW; i += 256)
+  {
+    const int r = i / PP8_SWW, wq = i - r * PP8_SWW;
+    const int sy = min(ph - 1, max(0, y0 + r - 3));
+    const int sx = x0 - 4 + wq * 4;
+    const uint8_t* row = planes + (size_t)sy * pitch;
+    uint32_t v;
+    if (sx >= 0 && sx + 3 < pw) v = *(const uint32_t*)(row + sx);     // pitch and x0 are multiples of 4: aligned
+    else
+    {
+      v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) v |= (uint32_t)row[min(pw - 1, max(0, sx + b))] << (8 * b);
+    }
+    s_src[r][wq] = v;
+  }
+  __syncthreads();
+  // horizontal pass (8-bit: headRoom 6, shift 0, offset -8192): four adjacent outputs of one row per thread
+  int16_t* s_h16 = (int16_t*)s_hp;
+  for (int i = tid; i < PP_SH * (PP_TX / 4); i += 256)
+  {
+    const int r = i / (PP_TX / 4), c = (i - r * (PP_TX / 4)) * 4;
+    const uint32_t w0 = s_src[r][c / 4], w1 = s_src[r][c / 4 + 1], w2 = s_src[r][c / 4 + 2];
+    // output column c + j reads bytes (c + j - 3) .. (c + j + 4) = byte 1 + j of w0 onwards
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+      const uint32_t lo = j < 3 ? __funnelshift_r(w0, w1, 8 * (j + 1)) : w1;
+      const uint32_t hi = j < 3 ? __funnelshift_r(w1, w2, 8 * (j + 1)) : w2;
+      int16_t* dst = s_h16 + ((size_t)(r >> 1) * PP_TX + c + j) * 2 + (r & 1);
+      const size_t ph_stride = (size_t)((PP_SH + 1) / 2) * PP_TX * 2;
+      dst[0] = (int16_t)((int)((lo >> 24) << 6) - 8192);                        // phase 0: filterCopy, sample (c + j) << 6
+      dst[ph_stride] = (int16_t)(hm_dp4a_us(hi, PpTap4<1>::hi, hm_dp4a_us(lo, PpTap4<1>::lo, -8192)));
+      dst[2 * ph_stride] = (int16_t)(hm_dp4a_us(hi, PpTap4<2>::hi, hm_dp4a_us(lo, PpTap4<2>::lo, -8192)));
+      dst[3 * ph_stride] = (int16_t)(hm_dp4a_us(hi, PpTap4<3>::hi, hm_dp4a_us(lo, PpTap4<3>::lo, -8192)));
+    }
+  }
+  __syncthreads();
+  // vertical pass (shift 12, offset 2048 + 8192 * 64): four adjacent columns of TWO rows (even, odd) per thread
+  const int shift2 = 12, off2 = (1 << 11) + (8192 << 6);
+  for (int i = tid; i < (PP_TY / 2) * (PP_TX / 4); i += 256)
+  {
+    const int rp = i / (PP_TX / 4), c = (i - rp * (PP_TX / 4)) * 4;
+    const int x = x0 + c, y = y0 + 2 * rp;
+    if (x >= pw || y >= ph) continue;
+    const bool odd_row = y + 1 < ph;
+#pragma unroll
+    for (int fx = 0; fx < 4; fx++)
+    {
+      uint32_t p[5][4];                             // row pairs rp .. rp + 4 (rows y-3 .. y+6)
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+      {
+        const uint4 q = *(const uint4*)&s_hp[fx][rp + k][c];
+        p[k][0] = q.x; p[k][1] = q.y; p[k][2] = q.z; p[k][3] = q.w;
+      }
+#pragma unroll
+      for (int fy = 0; fy < 4; fy++)
+      {
+        if (fx == 0 && fy == 0) continue;           // integer plane already in place
+        int ev[4], od[4];
+        if (fy == 0)
+        {
+          // filterCopy(isFirst=false, isLast=true): rows y and y+1 are the high half of pair rp+1 and the low half of pair rp+2
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+          {
+            ev[e] = min(255, max(0, ((int)(int16_t)(p[1][e] >> 16) + 8192 + 32) >> 6));
+            od[e] = min(255, max(0, ((int)(int16_t)(p[2][e] & 0xffffu) + 8192 + 32) >> 6));
+          }
+        }
+        else if (fy == 1) pp8_vertical<1>(p, off2, shift2, ev, od);
+        else if (fy == 2) pp8_vertical<2>(p, off2, shift2, ev, od);
+        else pp8_vertical<3>(p, off2, shift2, ev, od);
+        uint8_t* out = planes + (size_t)(fy * 4 + fx) * plane_elems + (size_t)y * pitch + x;
+        *(uint32_t*)out = (uint32_t)ev[0] | ((uint32_t)ev[1] << 8) | ((uint32_t)ev[2] << 16) | ((uint32_t)ev[3] << 24);
+        if (odd_row) *(uint32_t*)(out + pitch) = (uint32_t)od[0] | ((uint32_t)od[1] << 8) | ((uint32_t)od[2] << 16) | ((uint32_t)od[3] << 24);
+      }
+    }
+  }
+}
+
 template <typename Px>
 static int launch_planes_t(hmgpu_ctx* ctx, int slot, const int16_t* d_src, int src_stride)
 {
@@ -157,7 +294,10 @@ static int launch_planes_t(hmgpu_ctx* ctx, int slot, const int16_t* d_src, int s
   HmgpuStage st(ctx, HMGPU_ST_PLANES, 2);
   pad_convert_kernel<Px><<<g, b, 0, ctx->stream>>>(d_src, src_stride, ctx->pic_w, ctx->pic_h, planes, ctx->pitch, ctx->pw, ctx->ph);
   dim3 g2((ctx->pw + PP_TX - 1) / PP_TX, (ctx->ph + PP_TY - 1) / PP_TY);
-  phase_planes_kernel<Px><<<g2, 256, 0, ctx->stream>>>(planes, ctx->plane_elems, ctx->pitch, ctx->pw, ctx->ph, ctx->bit_depth);
+  if (sizeof(Px) == 1 && ctx->bit_depth == 8)
+    phase_planes8_kernel<<<g2, 256, 0, ctx->stream>>>((uint8_t*)planes, ctx->plane_elems, ctx->pitch, ctx->pw, ctx->ph);
+  else
+    phase_planes_kernel<Px><<<g2, 256, 0, ctx->stream>>>(planes, ctx->plane_elems, ctx->pitch, ctx->pw, ctx->ph, ctx->bit_depth);
   HMGPU_CUDA(ctx, cudaGetLastError());
   return HMGPU_OK;
 }
