@@ -91,15 +91,32 @@ __global__ void quant_kernel(const int32_t* __restrict__ coeff, size_t total, in
                              uint32_t* __restrict__ abs_sum)
 {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = coeff[i];
-  const long long t = (long long)hm_abs(c) * scale;
-  const int q = (int)((t + add) >> qbits);
-  if (delta_u) delta_u[i] = (int)((t - ((long long)q << qbits)) >> (qbits - 8));
-  int v = c < 0 ? -q : q;
-  v = min(32767, max(-32768, v));
-  level[i] = v;
-  if (q) atomicAdd(&abs_sum[i / nn], (uint32_t)q);
+  const int lane = threadIdx.x & 31;
+  uint32_t q = 0;
+  if (i < total)
+  {
+    const int c = coeff[i];
+    const long long t = (long long)hm_abs(c) * scale;
+    q = (uint32_t)((t + add) >> qbits);
+    if (delta_u) delta_u[i] = (int)((t - ((long long)q << qbits)) >> (qbits - 8));
+    int v = c < 0 ? -(int)q : (int)q;
+    v = min(32767, max(-32768, v));
+    level[i] = v;
+  }
+  // uiAcSum of the TU: the lanes of a warp belong to one TU (nn >= 32: a multiple of 32 coefficients per TU, blocks of 256
+  // threads start on a TU boundary) or to two (4x4 TUs: the halves of the warp), so the warp adds up before the atomic -- one
+  // atomic per nonzero coefficient made this kernel 421 us per 7.7 M coefficients at 4 % issue active (profiles/r2s_ncu_misc_kernels.csv)
+  if (nn >= 32)
+  {
+    const uint32_t s = __reduce_add_sync(0xffffffffu, q);
+    if (lane == 0 && s) atomicAdd(&abs_sum[i / nn], s);
+  }
+  else
+  {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((lane & 15) == 0 && q) atomicAdd(&abs_sum[i / nn], q);
+  }
 }
 
 int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int qp_per, int qp_rem,

@@ -67,4 +67,31 @@ it["org_offset"] = rng.integers(0, (1 << 20) - 64 * 16, m)
 it["cur_offset"] = rng.integers(0, (1 << 20) - 64 * 16, m)
 it["func"] = np.arange(m) % 4
 timed("dist_batch 50000 x 16x16", lambda: ctx.dist_batch(org, cur, it), 1)
+# f4: intra mode pre-selection, 8 000 PUs of 8x8 / 16x16 / 32x32
+ni = 8000
+ij = np.zeros(ni, hmgpu.INTRA_JOB)
+oo = lo = 0
+for i in range(ni):
+    nn = (8, 16, 32)[i % 3]
+    ij[i] = (oo, lo, nn, hmgpu.IF_ABOVE | hmgpu.IF_LEFT | hmgpu.IF_EDGE_FILTERS | hmgpu.IF_SATD, 0)
+    oo += nn * nn; lo += 2 * (4 * nn + 1)
+iorg = rng.integers(0, 256, oo).astype(np.int16)
+ilin = rng.integers(0, 256, lo).astype(np.int16)
+timed("intra_costs 8000 PUs x 35", lambda: ctx.intra_costs(ij, iorg, ilin), 1)
+# f3: SAO statistics and application of the 1080p luma component
+rec = frames[0]
+orgp = np.clip(frames[0] + rng.integers(-4, 5, frames[0].shape), 0, 255).astype(np.int16)
+sk_r, sk_b = np.full(5, 5, np.int32), np.full(5, 4, np.int32)
+timed("sao_stats 1080p luma", lambda: ctx.sao_stats(rec, orgp, 64, 64, sk_r, sk_b), 1)
+n_ctu = ((W + 63) // 64) * ((H + 63) // 64)
+stype = (np.arange(n_ctu) % 6 - 1).astype(np.int8)
+soff = np.zeros((n_ctu, 32), np.int32); soff[:, :5] = (3, 1, 0, -1, -3); soff[:, 12:16] = (2, 1, -1, -2)
+timed("sao_apply 1080p luma", lambda: ctx.sao_apply(rec, 64, 64, stype, soff), 1)
+# f2: merge candidates of 4 000 CUs of 16x16, five each
+nm = 20000
+mj = pj[:nm].copy()
+mj["pu_x"] &= ~7; mj["pu_y"] &= ~7
+moff = (np.arange(nm) // 5 * 384).astype(np.uint32)
+morg = rng.integers(0, 256, nm // 5 * 384).astype(np.int16)
+timed("merge_skip_dist 20000 cands", lambda: ctx.merge_skip_dist(mj, moff, morg, nm * 384), 1)
 ctx.close()
