@@ -109,6 +109,7 @@ def oracle():
     L.hmo_intra_costs.argtypes = [vp, vp, vp, ci, ci, ci, u32p]
     L.hmo_sao_blk_stats.argtypes = [vp, ci, vp, ci, ci, ci, ci, i32p, i32p, ci, i64p, i64p]
     L.hmo_sao_offset_block.argtypes = [ci, i32p, vp, ci, vp, ci, ci, ci, ci, ci]
+    L.hmo_deblock_picture.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci, ci, ci, ci]
     _oracle = L
     return L
 

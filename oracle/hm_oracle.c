@@ -1132,3 +1132,111 @@ void hmo_sao_offset_block(int type, const int32_t* offset, const int16_t* src, i
       }
     }
 }
+
+
+/* ==== deblocking filter ===============================================================
+ * Restates the edge filtering of TComLoopFilter: xEdgeFilterLuma (TComLoopFilter.cpp:530-660), xEdgeFilterChroma (:663-790),
+ * xPelFilterLuma (:804-860), xPelFilterChroma (:872-890), xUseStrongFiltering (:902-912), xCalcDP / xCalcDQ (:914-922), with the
+ * tables sm_tcTable / sm_betaTable (:59-67) and the 4:2:0 chroma QP mapping g_aucChromaScale (TComRom.cpp:499-506).  The
+ * reference walks the CU quadtree; the filtering itself only depends on per-unit data (boundary strength, QP, no-filter flag),
+ * so it is restated over the picture's grid of 4x4 units.  Pinned to pictures decoded by the instrumented reference decoder
+ * (oracle/dbk_dump.inc, tests/golden/make_deblock_golden.py). */
+static const uint8_t k_dbk_tc[54] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,5,5,6,6,7,8,9,10,11,13,14,16,18,20,22,24 };
+static const uint8_t k_dbk_beta[52] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,42,44,46,48,50,52,54,56,58,60,62,64 };
+static const uint8_t k_chroma_scale_420[58] = { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,29,30,31,32,33,33,34,34,35,35,36,36,37,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51 };
+
+static int dbk_clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* one 4-sample segment of a luma edge; p points at sample q0 of line 0, off = step across the edge, step = step along it */
+static void dbk_luma_segment(int16_t* p, int off, int step, int bs, int qp_p, int qp_q, int nf_p, int nf_q, int beta_off2, int tc_off2, int bit_depth)
+{
+  const int qp = (qp_p + qp_q + 1) >> 1, scale = 1 << (bit_depth - 8), maxv = (1 << bit_depth) - 1;
+  const int tc = k_dbk_tc[dbk_clip3(0, 53, qp + 2 * (bs - 1) + (tc_off2 << 1))] * scale;     /* DEFAULT_INTRA_TC_OFFSET 2 */
+  const int beta = k_dbk_beta[dbk_clip3(0, 51, qp + (beta_off2 << 1))] * scale;
+  const int side_thr = (beta + (beta >> 1)) >> 3, thr_cut = tc * 10;
+  int16_t* l0 = p; int16_t* l3 = p + 3 * step;
+  const int dp0 = abs(l0[-3 * off] - 2 * l0[-2 * off] + l0[-off]), dq0 = abs(l0[0] - 2 * l0[off] + l0[2 * off]);
+  const int dp3 = abs(l3[-3 * off] - 2 * l3[-2 * off] + l3[-off]), dq3 = abs(l3[0] - 2 * l3[off] + l3[2 * off]);
+  const int d0 = dp0 + dq0, d3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3, d = d0 + d3;
+  if (d >= beta) return;
+  const int filt_p = dp < side_thr, filt_q = dq < side_thr;
+  const int s0 = (abs(l0[-4 * off] - l0[-off]) + abs(l0[3 * off] - l0[0]) < (beta >> 3)) && (2 * d0 < (beta >> 2)) && (abs(l0[-off] - l0[0]) < ((tc * 5 + 1) >> 1));
+  const int s3 = (abs(l3[-4 * off] - l3[-off]) + abs(l3[3 * off] - l3[0]) < (beta >> 3)) && (2 * d3 < (beta >> 2)) && (abs(l3[-off] - l3[0]) < ((tc * 5 + 1) >> 1));
+  const int sw = s0 && s3;
+  for (int i = 0; i < 4; i++)
+  {
+    int16_t* s = p + i * step;
+    const int m0 = s[-4 * off], m1 = s[-3 * off], m2 = s[-2 * off], m3 = s[-off], m4 = s[0], m5 = s[off], m6 = s[2 * off], m7 = s[3 * off];
+    int n1 = m1, n2 = m2, n3 = m3, n4 = m4, n5 = m5, n6 = m6;
+    if (sw)
+    {
+      n3 = dbk_clip3(m3 - 2 * tc, m3 + 2 * tc, (m1 + 2 * m2 + 2 * m3 + 2 * m4 + m5 + 4) >> 3);
+      n4 = dbk_clip3(m4 - 2 * tc, m4 + 2 * tc, (m2 + 2 * m3 + 2 * m4 + 2 * m5 + m6 + 4) >> 3);
+      n2 = dbk_clip3(m2 - 2 * tc, m2 + 2 * tc, (m1 + m2 + m3 + m4 + 2) >> 2);
+      n5 = dbk_clip3(m5 - 2 * tc, m5 + 2 * tc, (m3 + m4 + m5 + m6 + 2) >> 2);
+      n1 = dbk_clip3(m1 - 2 * tc, m1 + 2 * tc, (2 * m0 + 3 * m1 + m2 + m3 + m4 + 4) >> 3);
+      n6 = dbk_clip3(m6 - 2 * tc, m6 + 2 * tc, (m3 + m4 + m5 + 3 * m6 + 2 * m7 + 4) >> 3);
+    }
+    else
+    {
+      int delta = (9 * (m4 - m3) - 3 * (m5 - m2) + 8) >> 4;
+      if (abs(delta) < thr_cut)
+      {
+        const int tc2 = tc >> 1;
+        delta = dbk_clip3(-tc, tc, delta);
+        n3 = dbk_clip3(0, maxv, m3 + delta);
+        n4 = dbk_clip3(0, maxv, m4 - delta);
+        if (filt_p) n2 = dbk_clip3(0, maxv, m2 + dbk_clip3(-tc2, tc2, ((((m1 + m3 + 1) >> 1) - m2 + delta) >> 1)));
+        if (filt_q) n5 = dbk_clip3(0, maxv, m5 + dbk_clip3(-tc2, tc2, ((((m6 + m4 + 1) >> 1) - m5 - delta) >> 1)));
+      }
+    }
+    if (!nf_p) { s[-off] = (int16_t)n3; s[-2 * off] = (int16_t)n2; s[-3 * off] = (int16_t)n1; }
+    if (!nf_q) { s[0] = (int16_t)n4; s[off] = (int16_t)n5; s[2 * off] = (int16_t)n6; }
+  }
+}
+
+void hmo_deblock_picture(int16_t* y, int16_t* cb, int16_t* cr, int w, int h, int bit_depth_luma, int bit_depth_chroma,
+                         const uint8_t* bs_ver, const uint8_t* bs_hor, const int8_t* qp, const uint8_t* nofilter,
+                         int beta_offset_div2, int tc_offset_div2, int cb_qp_offset, int cr_qp_offset)
+{
+  const int uw = (w + 3) >> 2, uh = (h + 3) >> 2, cw = w >> 1;
+  for (int dir = 0; dir < 2; dir++)            /* all vertical edges of the picture, then all horizontal edges (:128-157) */
+  {
+    const uint8_t* bs = dir ? bs_hor : bs_ver;
+    for (int uy = 0; uy < uh; uy++)
+      for (int ux = 0; ux < uw; ux++)
+      {
+        /* edges lie on the 8-sample grid (xDeblockCU steps iEdge by DEBLOCK_SMALLEST_BLOCK / 4 = 2 units, :251-266); the
+         * reference's own BS array holds the "internal edge" flag of 4x4 transform units at odd positions, never filtered */
+        const int b = ((dir ? uy : ux) & 1) ? 0 : bs[uy * uw + ux];
+        if (!b) continue;
+        const int q = uy * uw + ux, pn = dir ? q - uw : q - 1;      /* the unit across the edge: left / above */
+        /* luma: one 4-sample segment per unit */
+        dbk_luma_segment(y + (size_t)(uy * 4) * w + ux * 4, dir ? w : 1, dir ? 1 : w, b, qp[pn], qp[q], nofilter[pn], nofilter[q],
+                         beta_offset_div2, tc_offset_div2, bit_depth_luma);
+        /* chroma (4:2:0): edges on the 8-sample chroma grid = 16 luma samples, intra boundaries only (bs > 1, :737);
+         * a 4x4 luma unit covers 2 chroma samples of the edge */
+        if (b > 1 && ((dir ? uy : ux) & 3) == 0)
+        {
+          for (int c = 0; c < 2; c++)
+          {
+            int16_t* pl = c ? cr : cb;
+            int iqp = ((qp[pn] + qp[q] + 1) >> 1) + (c ? cr_qp_offset : cb_qp_offset);
+            if (iqp >= 58) iqp -= 6; else if (iqp >= 0) iqp = k_chroma_scale_420[iqp];
+            const int tc = k_dbk_tc[dbk_clip3(0, 53, iqp + 2 * (b - 1) + (tc_offset_div2 << 1))] * (1 << (bit_depth_chroma - 8));
+            const int maxv = (1 << bit_depth_chroma) - 1;
+            const int off = dir ? cw : 1, step = dir ? 1 : cw;
+            int16_t* p0 = pl + (size_t)(uy * 2) * cw + ux * 2;
+            for (int i = 0; i < 2; i++)
+            {
+              int16_t* s = p0 + i * step;
+              const int m2 = s[-2 * off], m3 = s[-off], m4 = s[0], m5 = s[off];
+              const int delta = dbk_clip3(-tc, tc, ((((m4 - m3) << 2) + m2 - m5 + 4) >> 3));
+              if (!nofilter[pn]) s[-off] = (int16_t)dbk_clip3(0, maxv, m3 + delta);
+              if (!nofilter[q]) s[0] = (int16_t)dbk_clip3(0, maxv, m4 - delta);
+            }
+          }
+        }
+      }
+  }
+}

@@ -104,6 +104,14 @@ void hmo_sao_blk_stats(const int16_t* src, int src_stride, const int16_t* org, i
 void hmo_sao_offset_block(int type, const int32_t* offset, const int16_t* src, int src_stride, int16_t* res, int res_stride,
                           int w, int h, int flags, int bit_depth);
 
+/* ---- deblocking filter of one picture (second half): the edge filtering of TComLoopFilter::loopFilterPic
+ * (TComLoopFilter.cpp:128-157: every vertical edge of the picture, then every horizontal edge) given what xDeblockCU derived
+ * per 4x4 luma unit: bs_ver / bs_hor = boundary strength of the unit's LEFT / TOP edge (0 off the 8-sample grid), qp,
+ * nofilter (IPCM with pcm_loop_filter_disabled or lossless).  Planes are filtered in place; 4:2:0. */
+void hmo_deblock_picture(int16_t* y, int16_t* cb, int16_t* cr, int w, int h, int bit_depth_luma, int bit_depth_chroma,
+                         const uint8_t* bs_ver, const uint8_t* bs_hor, const int8_t* qp, const uint8_t* nofilter,
+                         int beta_offset_div2, int tc_offset_div2, int cb_qp_offset, int cr_qp_offset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,3 +116,27 @@ def test_selective_search(bd):
     got = oracle_me(jobs, pads, fr[3], bd, side)
     assert np.array_equal(got["int_x"], rows[:, 0]) and np.array_equal(got["int_y"], rows[:, 1])
     assert np.array_equal(got["int_sad"].astype(np.int64), rows[:, 2])
+
+
+def _deblock_pictures():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deblock_golden.npz"))
+    for i in range(int(z["n_pictures"][0])):
+        yield i, {k[len("p%d_" % i):]: z[k] for k in z.files if k.startswith("p%d_" % i)}
+
+
+def test_deblock_oracle_matches_reference_decoder_pictures():
+    """f3, second half: hmo_deblock_picture on the pictures the instrumented reference decoder dumped (before / after
+    TComLoopFilter::loopFilterPic with the boundary strengths, QPs and no-filter flags it used; tests/golden/make_deblock_golden.py):
+    intra, P and B pictures, 8 and 10 bit, deblocking and chroma QP offsets, picture sizes that are not multiples of the CTU."""
+    O = B.oracle()
+    n = 0
+    for i, p in _deblock_pictures():
+        w, h, bdl, bdc, beta, tc, cbo, cro, poc = [int(v) for v in p["params"]]
+        y, cb, cr = p["pre_y"].copy(), p["pre_cb"].copy(), p["pre_cr"].copy()
+        O.hmo_deblock_picture(y.ctypes.data, cb.ctypes.data, cr.ctypes.data, w, h, bdl, bdc,
+                              np.ascontiguousarray(p["bs_ver"]).ctypes.data, np.ascontiguousarray(p["bs_hor"]).ctypes.data,
+                              np.ascontiguousarray(p["qp"]).ctypes.data, np.ascontiguousarray(p["nofilter"]).ctypes.data, beta, tc, cbo, cro)
+        assert np.array_equal(y, p["post_y"]) and np.array_equal(cb, p["post_cb"]) and np.array_equal(cr, p["post_cr"]), (i, poc)
+        assert (p["pre_y"] != p["post_y"]).any(), "picture %d: the reference filtered nothing" % i
+        n += 1
+    assert n >= 9
