@@ -249,7 +249,7 @@ def run_ours(args, rank, world, local_rank):
         stage_ms = {k: v[0] / args.steps for k, v in prof.items() if v[1]}
         # roofline = the dominant KERNEL: the stage with the longest average launch (the fractional stage is ONE launch of
         # fracw_group_kernel; the TZ stage is 17 launches on side streams, none longer than half of it -- the launch list
-        # profiles/r2m_ncu_launches_bench.csv shows both).  The longest STAGE is named next to it (roofline.longest_stage) and every
+        # profiles/r2t_ncu_launches_bench.csv shows both).  The longest STAGE is named next to it (roofline.longest_stage) and every
         # stage has its own entry in roofline_int32.per_stage.
         per_launch = {k: stage_ms[k] / max(1.0, prof[k][1] / args.steps) for k in stage_ms if k in work}
         dom = max(per_launch, key=lambda k: per_launch[k])

@@ -1545,6 +1545,46 @@ int hmgpu_sao_apply(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, int widt
   return HMGPU_OK;
 }
 
+// ---- deblocking (deblock.cu) -----------------------------------------------------------------------
+int hmgpu_deblock(hmgpu_ctx* ctx, int16_t* y, int16_t* cb, int16_t* cr, int width, int height,
+                  const uint8_t* bs_ver, const uint8_t* bs_hor, const int8_t* qp, const uint8_t* nofilter,
+                  int beta_offset_div2, int tc_offset_div2, int cb_qp_offset, int cr_qp_offset)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (!y || !cb || !cr || !bs_ver || !bs_hor || !qp || !nofilter) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_deblock");
+  if (width < 8 || height < 8 || width > 16384 || height > 16384 || (width & 1) || (height & 1))
+    return hmgpu_fail(ctx, HMGPU_E_INVALID, "picture of %d x %d samples", width, height);
+  if (beta_offset_div2 < -6 || beta_offset_div2 > 6 || tc_offset_div2 < -6 || tc_offset_div2 > 6 || cb_qp_offset < -12 || cb_qp_offset > 12 ||
+      cr_qp_offset < -12 || cr_qp_offset > 12) return hmgpu_fail(ctx, HMGPU_E_INVALID, "deblocking / chroma QP offsets out of the ranges of the syntax");
+  const size_t nu = (size_t)((width + 3) >> 2) * ((height + 3) >> 2);
+  for (size_t i = 0; i < nu; i++)
+    if (bs_ver[i] > 2 || bs_hor[i] > 2 || qp[i] < -48 || qp[i] > 51) return hmgpu_fail(ctx, HMGPU_E_INVALID, "unit %zu: boundary strength or QP out of range", i);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t yb = round_up(sizeof(int16_t) * (size_t)width * height, 256), cbb = round_up(sizeof(int16_t) * (size_t)(width >> 1) * (height >> 1), 256);
+  const size_t ub = round_up(nu, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, yb + 2 * cbb + 4 * ub))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, yb + 2 * cbb + 4 * ub))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, y, sizeof(int16_t) * (size_t)width * height);
+  memcpy(hp + yb, cb, sizeof(int16_t) * (size_t)(width >> 1) * (height >> 1));
+  memcpy(hp + yb + cbb, cr, sizeof(int16_t) * (size_t)(width >> 1) * (height >> 1));
+  memcpy(hp + yb + 2 * cbb, bs_ver, nu); memcpy(hp + yb + 2 * cbb + ub, bs_hor, nu);
+  memcpy(hp + yb + 2 * cbb + 2 * ub, qp, nu); memcpy(hp + yb + 2 * cbb + 3 * ub, nofilter, nu);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, yb + 2 * cbb + 4 * ub, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_deblock(ctx, (int16_t*)dp, (int16_t*)(dp + yb), (int16_t*)(dp + yb + cbb), width, height, ctx->bit_depth, ctx->bit_depth,
+                                 (const uint8_t*)(dp + yb + 2 * cbb), (const uint8_t*)(dp + yb + 2 * cbb + ub), (const int8_t*)(dp + yb + 2 * cbb + 2 * ub),
+                                 (const uint8_t*)(dp + yb + 2 * cbb + 3 * ub), beta_offset_div2, tc_offset_div2, cb_qp_offset, cr_qp_offset))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp, dp, yb + 2 * cbb, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(y, hp, sizeof(int16_t) * (size_t)width * height);
+  memcpy(cb, hp + yb, sizeof(int16_t) * (size_t)(width >> 1) * (height >> 1));
+  memcpy(cr, hp + yb + cbb, sizeof(int16_t) * (size_t)(width >> 1) * (height >> 1));
+  return HMGPU_OK;
+}
+
 // ---- intra mode pre-selection (intra.cu) ---------------------------------------------------------
 int hmgpu_intra_costs(hmgpu_ctx* ctx, const hmgpu_intra_job* jobs, int n_jobs, const int16_t* org_blocks, int n_org_elems,
                       const int16_t* ref_lines, int n_ref_elems, uint32_t* dist)

@@ -240,6 +240,9 @@ int hmgpu_launch_sao_stats(hmgpu_ctx* ctx, const int16_t* d_rec, int rec_stride,
                            int ctu_w, int ctu_h, const uint8_t* d_flags, const int32_t* skip_r, const int32_t* skip_b, long long* d_stats);
 int hmgpu_launch_sao_apply(hmgpu_ctx* ctx, const int16_t* d_src, int stride, int width, int height, int ctu_w, int ctu_h, const uint8_t* d_flags,
                            const int8_t* d_types, const int32_t* d_offsets, int16_t* d_dst);
+int hmgpu_launch_deblock(hmgpu_ctx* ctx, int16_t* d_y, int16_t* d_cb, int16_t* d_cr, int w, int h, int bd_luma, int bd_chroma,
+                         const uint8_t* d_bs_ver, const uint8_t* d_bs_hor, const int8_t* d_qp, const uint8_t* d_nf,
+                         int beta_off2, int tc_off2, int cb_off, int cr_off);
 int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst);
 int hmgpu_launch_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int with_chroma, int16_t* d_dst);
 int hmgpu_launch_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int func, uint32_t* d_out);

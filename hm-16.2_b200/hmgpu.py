@@ -49,7 +49,7 @@ EXPORTS = [
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
-    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform",
+    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_deblock", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
@@ -106,6 +106,7 @@ def lib():
     L.hmgpu_intra_costs.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp]
     L.hmgpu_sao_stats.argtypes = [vp, vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp]
     L.hmgpu_sao_apply.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp]
+    L.hmgpu_deblock.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, ci, ci, ci, ci]
     L.hmgpu_mv_bits.argtypes = [ci] * 5
     L.hmgpu_mv_bits.restype = cu
     L.hmgpu_mv_cost.argtypes = [cu] + [ci] * 5
@@ -334,6 +335,16 @@ class Context:
         self._check(self.L.hmgpu_sao_apply(self.h, rec.ctypes.data, w, w, h, ctu_w, ctu_h, None if flags is None else flags.ctypes.data,
                                            types.ctypes.data, offsets.ctypes.data, out.ctypes.data))
         return out
+
+    def deblock(self, y, cb, cr, bs_ver, bs_hor, qp, nofilter, beta_offset_div2=0, tc_offset_div2=0, cb_qp_offset=0, cr_qp_offset=0):
+        """deblocking of one picture (hmgpu_deblock): -> filtered copies (y, cb, cr)"""
+        y, cb, cr = [np.array(a, np.int16, order="C", copy=True) for a in (y, cb, cr)]
+        h, w = y.shape
+        bs_ver, bs_hor, nofilter = [np.ascontiguousarray(a, np.uint8) for a in (bs_ver, bs_hor, nofilter)]
+        qp = np.ascontiguousarray(qp, np.int8)
+        self._check(self.L.hmgpu_deblock(self.h, y.ctypes.data, cb.ctypes.data, cr.ctypes.data, w, h, bs_ver.ctypes.data, bs_hor.ctypes.data,
+                                         qp.ctypes.data, nofilter.ctypes.data, beta_offset_div2, tc_offset_div2, cb_qp_offset, cr_qp_offset))
+        return y, cb, cr
 
     def intra_costs(self, jobs, org_blocks, ref_lines):
         """distortion of the 35 luma intra modes of every job (hmgpu_intra_costs): -> uint32 [n_jobs, 35]"""

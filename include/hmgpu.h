@@ -251,6 +251,19 @@ int hmgpu_sao_stats(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, const in
 int hmgpu_sao_apply(hmgpu_ctx* ctx, const int16_t* rec, int rec_stride, int width, int height, int ctu_w, int ctu_h,
                     const uint8_t* ctu_flags, const int8_t* types, const int32_t* offsets, int16_t* out);
 
+/* Deblocking of one picture: the edge filtering of TComLoopFilter::loopFilterPic (TComLoopFilter.cpp:128-157,
+ * xEdgeFilterLuma :530-660, xEdgeFilterChroma :663-790; 4:2:0) -- every vertical edge, then every horizontal edge -- given per
+ * 4x4 luma unit of the picture (raster, ceil(w/4) per row) what xDeblockCU derives and what stays on the host:
+ *   bs_ver / bs_hor  boundary strength of the unit's left / top edge as in m_aapucBS (only units on the 8-sample grid are
+ *                    looked at; xGetBoundaryStrengthSingle, :398-528, needs the CU data of both sides)
+ *   qp               TComDataCU::getQP of the unit;   nofilter: IPCM with pcm_loop_filter_disabled, or lossless (:636-645)
+ *   beta / tc offsets: slice_beta_offset_div2 / slice_tc_offset_div2; cb / cr: pps_cb_qp_offset / pps_cr_qp_offset
+ * y / cb / cr: the reconstruction before deblocking, tight rows (w, w/2, w/2 samples); filtered in place.
+ * Bit depths: the context's for luma and chroma. */
+int hmgpu_deblock(hmgpu_ctx* ctx, int16_t* y, int16_t* cb, int16_t* cr, int width, int height,
+                  const uint8_t* bs_ver, const uint8_t* bs_hor, const int8_t* qp, const uint8_t* nofilter,
+                  int beta_offset_div2, int tc_offset_div2, int cb_qp_offset, int cr_qp_offset);
+
 /* ---------------------------------------------------------------------------------------------
  * Intra mode pre-selection of luma PUs.  Replaces the first-pass loop of
  * TEncSearch::estIntraPredQT (TEncSearch.cpp:2352-2395): for every one of the 35 modes

@@ -14,6 +14,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "hm-16.2_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dbkdump  # noqa: E402
 import synth  # noqa: E402
 
