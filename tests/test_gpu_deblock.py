@@ -60,6 +60,6 @@ def test_deblock_random_maps_match_oracle(bit_depth):
             if it == 0:
                 with pytest.raises(hmgpu.HmGpuError):
                     ctx.deblock(y, cb, cr, bs_ver + 3, bs_hor, qp, nf)
-        assert (ey != y).any()
+        assert it == 3 or (ey != y).any()             # (pure noise, case 3: every edge fails the activity test, nothing is filtered)
         assert np.array_equal(gy, ey), (it, np.argwhere(gy != ey)[:4])
         assert np.array_equal(gcb, ecb) and np.array_equal(gcr, ecr), it

@@ -220,3 +220,32 @@ def test_sao_offset_block(bd):
         R.ref_sao_offset_block(typ, off, B.ptr(pic, 4 * st + 4), st, B.ptr(a, 4 * st + 4), st, w, h, flags, bd)
         O.hmo_sao_offset_block(typ, off, B.ptr(pic, 4 * st + 4), st, B.ptr(b, 4 * st + 4), st, w, h, flags, bd)
         assert np.array_equal(a, b), (it, typ, w, h, flags, np.argwhere(a != b)[:4])
+
+
+def test_deblock_against_instrumented_decoder_live():
+    """f3, second half: a fresh encode (content and QP not among the golden pictures) decoded by the instrumented reference decoder
+    (oracle/_ref/TAppDecoderDbk, oracle/Makefile target `dbk`); hmo_deblock_picture reproduces every picture it deblocks."""
+    import os
+    import subprocess
+    import tempfile
+    import dbkdump
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    enc = os.path.join(root, "oracle", "_ref", "TAppEncoderRef")
+    dec = os.path.join(root, "oracle", "_ref", "TAppDecoderDbk")
+    cfg = os.path.join(root, "oracle", "_ref", "cfg", "encoder_lowdelay_main.cfg")
+    if not (os.path.exists(enc) and os.path.exists(dec) and os.path.exists(cfg)):
+        pytest.skip("instrumented decoder not built (make -C oracle dbk, needs /root/reference)")
+    O = B.oracle()
+    with tempfile.TemporaryDirectory(prefix="hmdbk_") as tmp:
+        yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), 208, 120, 4, 8, seed=4242)
+        bits, dump = os.path.join(tmp, "s.bin"), os.path.join(tmp, "s.dump")
+        subprocess.run([enc, "-c", cfg, "-i", yuv, "-wdt", "208", "-hgt", "120", "-fr", "30", "-f", "4", "-q", "29", "-b", bits], check=True, capture_output=True)
+        subprocess.run([dec, "-b", bits], check=True, capture_output=True, env=dict(os.environ, HM_DBK_DUMP=dump))
+        pics = dbkdump.read(dump)
+    assert len(pics) == 4
+    for p in pics:
+        y, cb, cr = [a.copy() for a in p["pre"]]
+        O.hmo_deblock_picture(y.ctypes.data, cb.ctypes.data, cr.ctypes.data, p["w"], p["h"], p["bd_luma"], p["bd_chroma"], p["bs_ver"].ctypes.data,
+                              p["bs_hor"].ctypes.data, p["qp"].ctypes.data, p["nofilter"].ctypes.data, p["beta_offset_div2"], p["tc_offset_div2"],
+                              p["cb_qp_offset"], p["cr_qp_offset"])
+        assert np.array_equal(y, p["post"][0]) and np.array_equal(cb, p["post"][1]) and np.array_equal(cr, p["post"][2]), p["poc"]
