@@ -1850,6 +1850,30 @@ int hmgpu_fwd_transform(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, i
   return HMGPU_OK;
 }
 
+int hmgpu_inv_transform(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int use_dst, int16_t* resi)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_tus == 0) return HMGPU_OK;
+  if (!resi || !coeff || n_tus < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_inv_transform");
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t elems = (size_t)n_tus * n * n;
+  const size_t b0 = round_up(sizeof(int32_t) * elems, 256), b1 = round_up(sizeof(int16_t) * elems, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, b0 + b1))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, b0 + b1))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, coeff, sizeof(int32_t) * elems);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_inv_transform(ctx, (const int32_t*)dp, n_tus, n, use_dst, (int16_t*)(dp + b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int16_t) * elems, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(resi, hp + b0, sizeof(int16_t) * elems);
+  return HMGPU_OK;
+}
+
 int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_per, int qp_rem,
                 int is_intra_slice, int32_t* level, int32_t* delta_u, uint32_t* abs_sum)
 {

@@ -246,6 +246,7 @@ int hmgpu_launch_deblock(hmgpu_ctx* ctx, int16_t* d_y, int16_t* d_cb, int16_t* d
 int hmgpu_launch_mc_luma(hmgpu_ctx* ctx, const hmgpu_mc_job* d_jobs, int n_jobs, int16_t* d_dst);
 int hmgpu_launch_predict(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int with_chroma, int16_t* d_dst);
 int hmgpu_launch_pred_error(hmgpu_ctx* ctx, const hmgpu_pred_job* d_jobs, int n_jobs, int func, uint32_t* d_out);
+int hmgpu_launch_inv_transform(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int use_dst, int16_t* d_resi);
 int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff);
 int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int qp_per, int qp_rem,
                        int is_intra, int32_t* d_level, int32_t* d_delta, uint32_t* d_abs_sum);

@@ -71,6 +71,65 @@ fwd_transform_kernel(const int16_t* __restrict__ resi, int n_tus, int use_dst, i
   }
 }
 
+// Inverse core transform: TComTrQuant::xIT -> xITrMxN -> partialButterflyInverse4/8/16/32 / fastInverseDst (TComTrQuant.cpp:894-960,
+// 437-810), square TUs.  The partial butterflies factor the transposed integer matrix product exactly, so the kernel evaluates it
+// directly: stage 1 (shift 7) clipped to the 16-bit transform dynamic range, stage 2 (shift 20 - bitDepth) clipped to the Pel range.
+template <int N>
+__global__ void __launch_bounds__(256)
+inv_transform_kernel(const int32_t* __restrict__ coeff, int n_tus, int use_dst, int bit_depth, int16_t* __restrict__ resi)
+{
+  constexpr int TPB = (N * N >= 256) ? 1 : 256 / (N * N);   // TUs per block
+  constexpr int P = N + 1;
+  __shared__ int s_m[N * P];                                  // M[i][k], rows padded: stage loops read column k of 32 rows
+  __shared__ int s_a[TPB][N * P];
+  __shared__ int s_b[TPB][N * P];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N * N; i += 256)
+    s_m[(i / N) * P + (i % N)] = (use_dst && N == 4) ? c_dst4[i / N][i % N] : dct_coef(N, i / N, i % N);
+  const int tu0 = blockIdx.x * TPB;
+  for (int i = tid; i < TPB * N * N; i += 256)
+  {
+    const int t = i / (N * N), e = i % (N * N);
+    if (tu0 + t < n_tus) s_a[t][(e / N) * P + (e % N)] = coeff[(size_t)(tu0 + t) * N * N + e];
+  }
+  __syncthreads();
+  const int shift2 = 20 - bit_depth;
+  // stage 1: b[j][k] = clip((sum_i M[i][k] * a[i][j] + 64) >> 7)
+  for (int i = tid; i < TPB * N * N; i += 256)
+  {
+    const int t = i / (N * N), e = i % (N * N), j = e / N, k = e % N;
+    int acc = 0;
+#pragma unroll
+    for (int x = 0; x < N; x++) acc += s_m[x * P + k] * s_a[t][x * P + j];
+    s_b[t][j * P + k] = min(32767, max(-32768, (acc + 64) >> 7));
+  }
+  __syncthreads();
+  for (int i = tid; i < TPB * N * N; i += 256)
+  {
+    const int t = i / (N * N), e = i % (N * N), j = e / N, k = e % N;
+    if (tu0 + t >= n_tus) continue;
+    int acc = 0;
+#pragma unroll
+    for (int x = 0; x < N; x++) acc += s_m[x * P + k] * s_b[t][x * P + j];
+    resi[(size_t)(tu0 + t) * N * N + j * N + k] = (int16_t)min(32767, max(-32768, (acc + (1 << (shift2 - 1))) >> shift2));
+  }
+}
+
+int hmgpu_launch_inv_transform(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int use_dst, int16_t* d_resi)
+{
+  HmgpuStage st(ctx, HMGPU_ST_TRANSFORM, 1);
+  switch (n)
+  {
+    case 4:  inv_transform_kernel<4><<<(n_tus + 15) / 16, 256, 0, ctx->stream>>>(d_coeff, n_tus, use_dst, ctx->bit_depth, d_resi); break;
+    case 8:  inv_transform_kernel<8><<<(n_tus + 3) / 4, 256, 0, ctx->stream>>>(d_coeff, n_tus, 0, ctx->bit_depth, d_resi); break;
+    case 16: inv_transform_kernel<16><<<n_tus, 256, 0, ctx->stream>>>(d_coeff, n_tus, 0, ctx->bit_depth, d_resi); break;
+    case 32: inv_transform_kernel<32><<<n_tus, 256, 0, ctx->stream>>>(d_coeff, n_tus, 0, ctx->bit_depth, d_resi); break;
+    default: return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  }
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}
+
 int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff)
 {
   HmgpuStage st(ctx, HMGPU_ST_TRANSFORM, 1);

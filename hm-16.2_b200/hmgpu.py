@@ -49,7 +49,7 @@ EXPORTS = [
     "hmgpu_stream", "hmgpu_synchronize", "hmgpu_set_option", "hmgpu_clip_bounds_ctu", "hmgpu_host_alloc", "hmgpu_host_free", "hmgpu_struct_sizes", "hmgpu_ref_upload", "hmgpu_ref_release",
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
-    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_deblock", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform",
+    "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_deblock", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform", "hmgpu_inv_transform",
     "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
@@ -116,6 +116,7 @@ def lib():
     L.hmgpu_pred_error.argtypes = [vp, vp, ci, ci, vp]
     L.hmgpu_merge_skip_dist.argtypes = [vp, vp, ci, vp, vp, ci, vp, ci, vp]
     L.hmgpu_fwd_transform.argtypes = [vp, vp, ci, ci, ci, vp]
+    L.hmgpu_inv_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.hmgpu_profile_enable.argtypes = [vp, ci]
     L.hmgpu_profile_stage_name.argtypes = [ci]
@@ -391,6 +392,12 @@ class Context:
         resi = np.ascontiguousarray(resi, np.int16).reshape(-1, n, n)
         out = np.zeros(resi.shape, np.int32)
         self._check(self.L.hmgpu_fwd_transform(self.h, resi.ctypes.data, resi.shape[0], n, int(use_dst), out.ctypes.data))
+        return out
+
+    def inv_transform(self, coeff, n, use_dst=False):
+        coeff = np.ascontiguousarray(coeff, np.int32).reshape(-1, n, n)
+        out = np.zeros(coeff.shape, np.int16)
+        self._check(self.L.hmgpu_inv_transform(self.h, coeff.ctypes.data, coeff.shape[0], n, int(use_dst), out.ctypes.data))
         return out
 
     def quant(self, coeff, n, qp_per, qp_rem, is_intra):

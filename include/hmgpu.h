@@ -363,6 +363,10 @@ int hmgpu_merge_skip_dist(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs
  * ------------------------------------------------------------------------------------------ */
 int hmgpu_fwd_transform(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, int use_dst,
                         int32_t* coeff);
+/* hmgpu_inv_transform replaces TComTrQuant::xIT -> xITrMxN -> partialButterflyInverse4/8/16/32 / fastInverseDst
+ * (TComTrQuant.cpp:1830-1850, 894-960, 437-810): n_tus blocks of n x n TCoeff in, n x n residual Pel out (the reconstruction
+ * side of the residual-costing loop; dequantisation and RDOQ stay on the host). */
+int hmgpu_inv_transform(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int use_dst, int16_t* resi);
 int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_per, int qp_rem,
                 int is_intra_slice, int32_t* level, int32_t* delta_u, uint32_t* abs_sum);
 

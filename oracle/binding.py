@@ -99,6 +99,7 @@ def oracle():
     L.hmo_motion_estimation.argtypes = [C.POINTER(SearchT), ci, ci, C.POINTER(cu), i32p, C.POINTER(cu)]
     L.hmo_fwd_transform.argtypes = [ci, i32p, i32p, ci, ci, ci]
     L.hmo_transform_matrix.argtypes = [ci, i32p]
+    L.hmo_inv_transform.argtypes = [ci, i32p, i32p, ci, ci]
     L.hmo_quant.restype = cu
     L.hmo_quant.argtypes = [i32p, ci, ci, ci, ci, ci, i32p, i32p]
     L.hmo_me_batch.restype = C.c_double
@@ -157,6 +158,7 @@ def ref():
     L.ref_frac_search.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, cu, ci, ci, ci, ci, ci, i32p, i32p, u32p]
     L.ref_fwd_transform.argtypes = [ci, i32p, i32p, ci, ci, ci]
     L.ref_partial_butterfly.argtypes = [ci, i32p, i32p, ci, ci]
+    L.ref_inv_transform.argtypes = [ci, i32p, i32p, ci, ci]
     L.ref_quant_scale.restype = ci
     L.ref_quant_scale.argtypes = [ci]
     L.ref_pred_inter_blk.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci]

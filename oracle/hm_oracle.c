@@ -836,6 +836,34 @@ void hmo_fwd_transform(int bit_depth, const int32_t* block, int32_t* coeff, int 
   free(tmp);
 }
 
+/* one stage of the inverse transform: partialButterflyInverse4/8/16/32 / fastInverseDst (TComTrQuant.cpp:437-810) factor
+ * dst[j][k] = clip((sum_i M[i][k] * src[i][j] + rnd) >> shift): the transposed matrix applied to column j, result stored
+ * transposed, clipped to [lo, hi] */
+static void inv_stage(const int32_t* src, int32_t* dst, int n, int shift, int use_dst, int32_t lo, int32_t hi)
+{
+  const int32_t rnd = shift > 0 ? (1 << (shift - 1)) : 0;
+  for (int j = 0; j < n; j++)
+    for (int k = 0; k < n; k++)
+    {
+      int32_t acc = 0;
+      for (int i = 0; i < n; i++)
+        acc += (use_dst ? kDst4[i][k] : dct_coef(n, i, k)) * src[i * n + j];
+      acc = (acc + rnd) >> shift;
+      dst[j * n + k] = acc < lo ? lo : (acc > hi ? hi : acc);
+    }
+}
+
+/* xITrMxN (TComTrQuant.cpp:894-960): first stage shift 7 with the clip to the 16-bit transform dynamic range, second stage
+ * shift 20 - bitDepth with the clip to the Pel range */
+void hmo_inv_transform(int bit_depth, const int32_t* coeff, int32_t* block, int n, int use_dst)
+{
+  const int dst = use_dst && n == 4;
+  int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (size_t)n * (size_t)n);
+  inv_stage(coeff, tmp, n, 7, dst, -32768, 32767);
+  inv_stage(tmp, block, n, 20 - bit_depth, dst, -32768, 32767);
+  free(tmp);
+}
+
 /* Scalar (non-RDOQ) quantiser, flat scaling: TComTrQuant::xQuant else-branch
  * (TComTrQuant.cpp:1120-1199) without the sign-hiding post-pass.
  * qbits = 14 + per + transformShift; add = (I ? 171 : 85) << (qbits-9). Returns absSum. */

@@ -78,6 +78,8 @@ void hmo_motion_estimation(hmo_search_t* s, int full_search, int bi, uint32_t* i
 /* ---- forward transform + scalar quantiser (a17, a18) ---- */
 void hmo_fwd_transform(int bit_depth, const int32_t* block, int32_t* coeff, int w, int h, int use_dst);
 void hmo_transform_matrix(int n, int32_t* m /* n*n */);
+/* xITrMxN (TComTrQuant.cpp:894-960), square blocks: coefficients -> residual (TCoeff, clipped to the Pel range) */
+void hmo_inv_transform(int bit_depth, const int32_t* coeff, int32_t* block, int n, int use_dst);
 uint32_t hmo_quant(const int32_t* coef, int n_coef, int qp_per, int qp_rem, int transform_shift,
                    int is_intra_slice, int32_t* level, int32_t* delta_u);
 

@@ -57,6 +57,7 @@ extern Void partialButterfly16(TCoeff *src, TCoeff *dst, Int shift, Int line);
 extern Void partialButterfly32(TCoeff *src, TCoeff *dst, Int shift, Int line);
 extern Void fastForwardDst(TCoeff *block, TCoeff *coeff, Int shift);
 extern Void xTrMxN(Int bitDepth, TCoeff *block, TCoeff *coeff, Int iWidth, Int iHeight, Bool useDST, const Int maxTrDynamicRange);
+extern Void xITrMxN(Int bitDepth, TCoeff *coeff, TCoeff *block, Int iWidth, Int iHeight, Bool useDST, const Int maxTrDynamicRange);
 
 namespace {
 
@@ -418,6 +419,12 @@ void ref_fwd_transform(int bitDepth, const int32_t* block, int32_t* coeff, int w
   ensure_init();
   std::vector<TCoeff> tmp(block, block + w * h);
   xTrMxN(bitDepth, &tmp[0], (TCoeff*)coeff, w, h, useDST != 0, 15);
+}
+void ref_inv_transform(int bitDepth, const int32_t* coeff, int32_t* block, int n, int useDST)
+{
+  ensure_init();
+  std::vector<TCoeff> tmp(coeff, coeff + n * n);
+  xITrMxN(bitDepth, &tmp[0], (TCoeff*)block, n, n, useDST != 0, 15);
 }
 void ref_partial_butterfly(int n, const int32_t* src, int32_t* dst, int shift, int line)
 {

@@ -325,6 +325,29 @@ def test_fwd_transform_and_quant(bit_depth):
 
 
 @pytest.mark.parametrize("bit_depth", [8, 10])
+def test_inverse_transform(bit_depth):
+    """hmgpu_inv_transform (xITrMxN) against the oracle: quantised-looking coefficients, full-range noise, the clip extremes; and the
+    round trip forward -> inverse of a residual stays within the transform's rounding"""
+    rng = np.random.default_rng(19)
+    O = B.oracle()
+    with hmgpu.Context(W, H, bit_depth, 1) as ctx:
+        for n in (4, 8, 16, 32):
+            for use_dst in ((False, True) if n == 4 else (False,)):
+                c = rng.integers(-32768, 32768, (41, n, n)).astype(np.int32)
+                c[0] = 32767; c[1] = -32768
+                c[2:12] = 0
+                c[2:12, : max(1, n // 4), : max(1, n // 4)] = rng.integers(-3000, 3000, (10, max(1, n // 4), max(1, n // 4)))
+                got = ctx.inv_transform(c, n, use_dst)
+                exp = np.zeros(c.shape, np.int32)
+                for t in range(len(c)):
+                    O.hmo_inv_transform(bit_depth, np.ascontiguousarray(c[t]), exp[t], n, int(use_dst))
+                assert np.array_equal(got.astype(np.int32), exp), (n, use_dst)
+                resi = rng.integers(-(1 << bit_depth) + 1, 1 << bit_depth, (8, n, n)).astype(np.int16)
+                back = ctx.inv_transform(ctx.fwd_transform(resi, n, use_dst), n, use_dst)
+                assert np.abs(back.astype(np.int32) - resi).max() <= 4, (n, use_dst)    # the integer transform pair is not exactly orthogonal
+
+
+@pytest.mark.parametrize("bit_depth", [8, 10])
 def test_mc_luma_matches_oracle(bit_depth):
     rng = np.random.default_rng(17)
     O = B.oracle()

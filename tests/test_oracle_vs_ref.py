@@ -249,3 +249,24 @@ def test_deblock_against_instrumented_decoder_live():
                               p["bs_hor"].ctypes.data, p["qp"].ctypes.data, p["nofilter"].ctypes.data, p["beta_offset_div2"], p["tc_offset_div2"],
                               p["cb_qp_offset"], p["cr_qp_offset"])
         assert np.array_equal(y, p["post"][0]) and np.array_equal(cb, p["post"][1]) and np.array_equal(cr, p["post"][2]), p["poc"]
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_inverse_transform(bd):
+    """hmo_inv_transform against the reference's xITrMxN (partialButterflyInverse4/8/16/32, fastInverseDst): coefficients as the forward
+    transform + quantiser leave them, and extreme ones that hit both clips"""
+    O, R = B.oracle(), B.ref()
+    rng = np.random.default_rng(500 + bd)
+    for n in (4, 8, 16, 32):
+        for it in range(40):
+            if it % 3 == 0:
+                c = rng.integers(-32768, 32768, (n, n)).astype(np.int32)
+            elif it % 3 == 1:
+                c = np.zeros((n, n), np.int32); c[: max(1, n // 4), : max(1, n // 4)] = rng.integers(-2000, 2000, (max(1, n // 4), max(1, n // 4)))
+            else:
+                c = rng.choice(np.array([-32768, 32767, 0], np.int32), (n, n))
+            for dst in ((0, 1) if n == 4 else (0,)):
+                a = np.zeros((n, n), np.int32); b = np.zeros((n, n), np.int32)
+                R.ref_inv_transform(bd, c.copy(), a, n, dst)
+                O.hmo_inv_transform(bd, c, b, n, dst)
+                assert np.array_equal(a, b), (n, it, dst)
