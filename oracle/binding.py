@@ -111,8 +111,29 @@ def oracle():
     L.hmo_sao_blk_stats.argtypes = [vp, ci, vp, ci, ci, ci, ci, i32p, i32p, ci, i64p, i64p]
     L.hmo_sao_offset_block.argtypes = [ci, i32p, vp, ci, vp, ci, ci, ci, ci, ci]
     L.hmo_deblock_picture.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci, ci, ci, ci]
+    L.hmo_rdoq.restype = ci
+    L.hmo_rdoq.argtypes = [vp, vp, i32p, i32p]
+    L.hmo_scan_order.argtypes = [ci, ci, vp, vp]
     _oracle = L
     return L
+
+
+# hmo_rdoq_bits / hmo_rdoq_tu of oracle/hm_oracle.h
+RDOQ_BITS = np.dtype([("sig_group", np.int32, (2, 2)), ("sig", np.int32, (44, 2)), ("last_x", np.int32, (2, 10)),
+                      ("last_y", np.int32, (2, 10)), ("greater_one", np.int32, (24, 2)), ("level_abs", np.int32, (6, 2))])
+RDOQ_TU = np.dtype([("log2_size", np.int32), ("channel", np.int32), ("scan", np.int32), ("sign_hide", np.int32), ("qbits", np.int32),
+                    ("qp_per", np.int32), ("qp_rem", np.int32), ("go_rice_init", np.int32), ("cbf_bits", np.int32, 2),
+                    ("bit_depth", np.int32), ("pad", np.int32), ("err_scale", np.float64), ("lambda", np.float64)], align=True)
+
+
+def rdoq(tu, bits, coef):
+    """hmo_rdoq on one TU: tu = RDOQ_TU record, bits = RDOQ_BITS record, coef = int32 raster -> (levels, abs_sum)"""
+    coef = np.ascontiguousarray(coef, np.int32).ravel()
+    level = np.zeros_like(coef)
+    tu = np.ascontiguousarray(tu)
+    bits = np.ascontiguousarray(bits)
+    s = oracle().hmo_rdoq(tu.ctypes.data, bits.ctypes.data, coef, level)
+    return level, int(s)
 
 
 def have_ref():

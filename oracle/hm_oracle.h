@@ -114,6 +114,35 @@ void hmo_deblock_picture(int16_t* y, int16_t* cb, int16_t* cr, int w, int h, int
                          const uint8_t* bs_ver, const uint8_t* bs_hor, const int8_t* qp, const uint8_t* nofilter,
                          int beta_offset_div2, int tc_offset_div2, int cb_qp_offset, int cr_qp_offset);
 
+/* ---- rate-distortion optimised quantisation (f1; oracle/hm_rdoq.c) ---- */
+/* the CABAC bit estimates RDOQ reads: estBitsSbacStruct (TComTrQuant.h:59-73) without its cbf tables (the two cbf values that
+ * apply to a TU travel in hmo_rdoq_tu); 15-bit fixed point */
+typedef struct hmo_rdoq_bits {
+  int32_t sig_group[2][2];       /* significantCoeffGroupBits */
+  int32_t sig[44][2];            /* significantBits: 28 luma contexts, then 16 chroma */
+  int32_t last_x[2][10];         /* lastXBits[channel][group] */
+  int32_t last_y[2][10];
+  int32_t greater_one[24][2];    /* m_greaterOneBits */
+  int32_t level_abs[6][2];       /* m_levelAbsBits */
+} hmo_rdoq_bits;
+typedef struct hmo_rdoq_tu {
+  int32_t log2_size;             /* 2..5 */
+  int32_t channel;               /* 0 luma, 1 chroma */
+  int32_t scan;                  /* 0 diagonal, 1 horizontal, 2 vertical */
+  int32_t sign_hide;
+  int32_t qbits;                 /* QUANT_SHIFT + per + transform shift */
+  int32_t qp_per, qp_rem;
+  int32_t go_rice_init;
+  int32_t cbf_bits[2];           /* bits of cbf = 0 / cbf = 1 in the context the TU's (root) cbf is coded in */
+  int32_t bit_depth;
+  double  err_scale;             /* getErrScaleCoeffNoScalingList */
+  double  lambda;                /* m_dLambda */
+} hmo_rdoq_tu;
+/* coef, level: raster, pitch = width; returns uiAbsSum */
+int hmo_rdoq(const hmo_rdoq_tu* tu, const hmo_rdoq_bits* bits, const int32_t* coef, int32_t* level);
+/* scan[k] = raster position of the k-th coefficient (SCAN_GROUPED_4x4), scan_cg[i] = raster index of the i-th coefficient group */
+void hmo_scan_order(int log2_size, int scan_type, uint16_t* scan, uint16_t* scan_cg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,3 +140,65 @@ def test_deblock_oracle_matches_reference_decoder_pictures():
         assert (p["pre_y"] != p["post_y"]).any(), "picture %d: the reference filtered nothing" % i
         n += 1
     assert n >= 9
+
+
+def rdoq_golden_calls():
+    """tests/golden/rdoq_golden.npz -> the dumped calls of the reference's xRateDistOptQuant (tests/golden/make_rdoq_golden.py)"""
+    import rdoqdump
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rdoq_golden.npz"))
+    calls = []
+    for i in range(len(z["abs_sum"])):
+        c = {k: int(v) for k, v in zip(rdoqdump.HDR, z["hdr"][i])}
+        c["err_scale"], c["lambda"] = float(z["scale_lambda"][i, 0]), float(z["scale_lambda"][i, 1])
+        c["bits"] = z["bits"][z["bits_index"][i]]
+        a, b = int(z["offset"][i]), int(z["offset"][i + 1])
+        c["coef"], c["level"], c["abs_sum"] = z["coef"][a:b], z["level"][a:b], int(z["abs_sum"][i])
+        calls.append(c)
+    return calls
+
+
+def test_rdoq_oracle_matches_reference_encoder_calls():
+    """f1: hmo_rdoq on the calls of TComTrQuant::xRateDistOptQuant the instrumented reference encoder dumped: 4x4 .. 32x32 TUs, luma
+    and chroma, the three scans, inter (root cbf) and intra TUs, transform skip, sign-bit hiding on and off, 8 and 10 bit, P / B /
+    intra slices -- levels and uiAbsSum identical for every call (the decisions compare sums of doubles: this also pins the order
+    of the floating-point operations)."""
+    import rdoqdump
+    calls = rdoq_golden_calls()
+    assert len(calls) >= 1000
+    seen = set()
+    hidden = 0
+    for i, c in enumerate(calls):
+        assert rdoqdump.supported(c)
+        tu, bits = rdoqdump.to_tu_and_bits(c, B.RDOQ_TU, B.RDOQ_BITS)
+        level, abs_sum = B.rdoq(tu, bits, c["coef"])
+        assert abs_sum == c["abs_sum"] and np.array_equal(level, c["level"]), (i, {k: c[k] for k in rdoqdump.HDR})
+        seen.add((c["log2"], c["channel"], c["scan"], c["sign_hide"], c["bit_depth"], c["root_cbf"], c["tskip"]))
+        hidden += int(c["sign_hide"] and np.abs(c["level"]).sum() != c["abs_sum"])
+    assert {s[0] for s in seen} == {2, 3, 4, 5} and {s[1] for s in seen} == {0, 1} and {s[2] for s in seen} == {0, 1, 2}
+    assert {s[3] for s in seen} == {0, 1} and {s[4] for s in seen} == {8, 10} and {s[5] for s in seen} == {0, 1} and {s[6] for s in seen} == {0, 1}
+    assert hidden > 20          # calls in which the sign-hiding pass changed a level
+
+
+def test_scan_orders():
+    """hmo_scan_order: every scan is a permutation, groups of 16 stay inside one 4x4 block, and the three 4x4 orders are the
+    textbook ones (TComRom.cpp:53-137)"""
+    O = B.oracle()
+    for log2 in (2, 3, 4, 5):
+        n = 1 << log2
+        for st in (0, 1, 2):
+            scan = np.zeros(n * n, np.uint16)
+            cg = np.zeros(max(1, n * n // 16), np.uint16)
+            O.hmo_scan_order(log2, st, scan.ctypes.data, cg.ctypes.data)
+            assert sorted(scan.tolist()) == list(range(n * n)) and sorted(cg.tolist()) == list(range(n * n // 16))
+            for g in range(n * n // 16):
+                blk = scan[16 * g:16 * g + 16]
+                assert len({(int(p) // n // 4, int(p) % n // 4) for p in blk}) == 1
+                assert (int(blk[0]) // n // 4) * (n // 4) + int(blk[0]) % n // 4 == int(cg[g])
+    scan = np.zeros(16, np.uint16)
+    cg = np.zeros(1, np.uint16)
+    O.hmo_scan_order(2, 0, scan.ctypes.data, cg.ctypes.data)
+    assert scan.tolist() == [0, 4, 1, 8, 5, 2, 12, 9, 6, 3, 13, 10, 7, 14, 11, 15]
+    O.hmo_scan_order(2, 1, scan.ctypes.data, cg.ctypes.data)
+    assert scan.tolist() == list(range(16))
+    O.hmo_scan_order(2, 2, scan.ctypes.data, cg.ctypes.data)
+    assert scan.tolist() == [0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15]

@@ -270,3 +270,32 @@ def test_inverse_transform(bd):
                 R.ref_inv_transform(bd, c.copy(), a, n, dst)
                 O.hmo_inv_transform(bd, c, b, n, dst)
                 assert np.array_equal(a, b), (n, it, dst)
+
+
+def test_rdoq_against_instrumented_encoder_live():
+    """f1: a fresh encode (content, size and QP not among the golden calls) by the instrumented reference encoder
+    (oracle/_ref/TAppEncoderRdoq, oracle/Makefile target `rdoq`); hmo_rdoq reproduces every sampled call of xRateDistOptQuant."""
+    import os
+    import subprocess
+    import tempfile
+    import rdoqdump
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    enc = os.path.join(root, "oracle", "_ref", "TAppEncoderRdoq")
+    cfg = os.path.join(root, "oracle", "_ref", "cfg", "encoder_lowdelay_main.cfg")
+    if not (os.path.exists(enc) and os.path.exists(cfg)):
+        pytest.skip("instrumented encoder not built (make -C oracle rdoq, needs /root/reference)")
+    with tempfile.TemporaryDirectory(prefix="hmrdoq_") as tmp:
+        yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), 208, 120, 3, 8, seed=991)
+        dump = os.path.join(tmp, "s.dump")
+        subprocess.run([enc, "-c", cfg, "-i", yuv, "-wdt", "208", "-hgt", "120", "-fr", "30", "-f", "3", "-q", "26", "-b", os.path.join(tmp, "s.bin")],
+                       check=True, capture_output=True, env=dict(os.environ, HM_RDOQ_DUMP=dump, HM_RDOQ_EVERY="11"))
+        calls = rdoqdump.read(dump)
+    assert len(calls) > 5000
+    coded = 0
+    for i, c in enumerate(calls):
+        assert rdoqdump.supported(c)
+        tu, bits = rdoqdump.to_tu_and_bits(c, B.RDOQ_TU, B.RDOQ_BITS)
+        level, abs_sum = B.rdoq(tu, bits, c["coef"])
+        assert abs_sum == c["abs_sum"] and np.array_equal(level, c["level"]), (i, {k: c[k] for k in rdoqdump.HDR})
+        coded += int(abs_sum > 0)
+    assert coded > 1000
