@@ -1903,4 +1903,59 @@ int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_p
   return HMGPU_OK;
 }
 
+// ---- rate-distortion optimised quantisation (rdoq.cu) ----------------------------------------------------------------------
+int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmgpu_rdoq_bits* bits, int n_bits,
+               const int32_t* coef, int n_coef, int32_t* level, int32_t* abs_sum)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !bits || !coef || !level || !abs_sum || n_jobs < 0 || n_bits <= 0 || n_coef < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_rdoq");
+  int n_class[4] = { 0, 0, 0, 0 };
+  for (int i = 0; i < n_jobs; i++)
+  {
+    const hmgpu_rdoq_job& j = jobs[i];
+    if (j.log2_size < 2 || j.log2_size > 5) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: log2 size %d not in 2..5", i, j.log2_size);
+    if ((unsigned)j.channel > 1u || (unsigned)j.scan > 2u || (j.flags & ~HMGPU_RDOQ_SIGN_HIDE)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: bad channel / scan / flags", i);
+    if (j.qbits < 9 || j.qbits > 30 || (unsigned)j.qp_rem > 5u || (unsigned)j.qp_per > 12u) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: bad qbits / qp per / rem", i);
+    if ((unsigned)j.go_rice_init > 4u || j.bit_depth < 8 || j.bit_depth > 16) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: bad Rice parameter / bit depth", i);
+    if ((unsigned)j.bits_index >= (unsigned)n_bits) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: bits_index %d outside bits", i, j.bits_index);
+    if (!(j.lambda > 0.0) || !(j.err_scale > 0.0)) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: lambda / err_scale not positive", i);
+    if ((unsigned long long)j.coef_offset + (1ull << (2 * j.log2_size)) > (unsigned long long)n_coef) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: coefficients outside coef", i);
+    n_class[j.log2_size - 2]++;
+  }
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  static uint16_t s_scan[4336];
+  static bool s_scan_done = false;                       // (written with the same values by whoever comes first)
+  if (!s_scan_done) { hmgpu_rdoq_scan_table(s_scan); s_scan_done = true; }
+  // staging: [coef | jobs | bits | scan table | index list] in, [level | abs_sum] out
+  const size_t b_coef = round_up(sizeof(int32_t) * (size_t)n_coef, 256), b_jobs = round_up(sizeof(hmgpu_rdoq_job) * (size_t)n_jobs, 256);
+  const size_t b_bits = round_up(sizeof(hmgpu_rdoq_bits) * (size_t)n_bits, 256), b_scan = round_up(sizeof s_scan, 256);
+  const size_t b_list = round_up(sizeof(int) * (size_t)n_jobs, 256);
+  const size_t in_bytes = b_coef + b_jobs + b_bits + b_scan + b_list, out_bytes = b_coef + b_list;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, in_bytes + out_bytes))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, in_bytes + out_bytes))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, coef, sizeof(int32_t) * (size_t)n_coef);
+  memcpy(hp + b_coef, jobs, sizeof(hmgpu_rdoq_job) * (size_t)n_jobs);
+  memcpy(hp + b_coef + b_jobs, bits, sizeof(hmgpu_rdoq_bits) * (size_t)n_bits);
+  memcpy(hp + b_coef + b_jobs + b_bits, s_scan, sizeof s_scan);
+  int* list = (int*)(hp + b_coef + b_jobs + b_bits + b_scan);
+  int at[4] = { 0, n_class[0], n_class[0] + n_class[1], n_class[0] + n_class[1] + n_class[2] };
+  for (int i = 0; i < n_jobs; i++) list[at[jobs[i].log2_size - 2]++] = i;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // coefficients no job covers come back as zero levels
+  HMGPU_CUDA(ctx, cudaMemsetAsync(dp + in_bytes, 0, out_bytes, ctx->stream));
+  if ((rc = hmgpu_launch_rdoq(ctx, (const hmgpu_rdoq_job*)(dp + b_coef), (const int*)(dp + b_coef + b_jobs + b_bits + b_scan), n_class,
+                              (const hmgpu_rdoq_bits*)(dp + b_coef + b_jobs), (const uint16_t*)(dp + b_coef + b_jobs + b_bits),
+                              (const int32_t*)dp, (int32_t*)(dp + in_bytes), (int32_t*)(dp + in_bytes + b_coef)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(level, hp + in_bytes, sizeof(int32_t) * (size_t)n_coef);
+  memcpy(abs_sum, hp + in_bytes + b_coef, sizeof(int32_t) * (size_t)n_jobs);
+  return HMGPU_OK;
+}
+
 } // extern "C"

@@ -217,7 +217,8 @@ size_t hmgpu_internal_mailbox_bytes(void);
 }
 
 // bits of hmgpu_ctx::attr_done
-enum { HMGPU_ATTR_SINGLE = 1, HMGPU_ATTR_SERVER = 2, HMGPU_ATTR_FULL = 4, HMGPU_ATTR_TZT = 8, HMGPU_ATTR_TZ_CARVE = 16, HMGPU_ATTR_FRAC3 = 32, HMGPU_ATTR_FRACW = 64 };
+enum { HMGPU_ATTR_SINGLE = 1, HMGPU_ATTR_SERVER = 2, HMGPU_ATTR_FULL = 4, HMGPU_ATTR_TZT = 8, HMGPU_ATTR_TZ_CARVE = 16, HMGPU_ATTR_FRAC3 = 32, HMGPU_ATTR_FRACW = 64,
+       HMGPU_ATTR_RDOQ2 = 128, HMGPU_ATTR_RDOQ3 = 256, HMGPU_ATTR_RDOQ4 = 512, HMGPU_ATTR_RDOQ5 = 1024 };
 
 #define HMGPU_CUDA(ctx, call)                                                              \
   do {                                                                                     \
@@ -250,6 +251,9 @@ int hmgpu_launch_inv_transform(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus
 int hmgpu_launch_fwd_transform(hmgpu_ctx* ctx, const int16_t* d_resi, int n_tus, int n, int use_dst, int32_t* d_coeff);
 int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n, int qp_per, int qp_rem,
                        int is_intra, int32_t* d_level, int32_t* d_delta, uint32_t* d_abs_sum);
+int hmgpu_launch_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* d_jobs, const int* d_list, const int n_class[4], const hmgpu_rdoq_bits* d_bits,
+                      const uint16_t* d_scan, const int32_t* d_coef, int32_t* d_level, int32_t* d_abs_sum);
+void hmgpu_rdoq_scan_table(uint16_t* tab);      // 4335 words, layout in rdoq_impl.cuh
 
 // ---------------------------------------------------------------------------------------
 // device helpers shared by the search kernels

@@ -1,0 +1,456 @@
+// rdoq_impl.cuh -- rate-distortion optimised quantisation of one TU, the per-TU body of rdoq.cu.
+//
+// Replaces TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1974-2520) with xGetCodedLevel (:2660), xGetICRate (:2725),
+// xGetRateLast (:2815), getSigCtxInc (:2548), calcPatternSigCtx (:2521), getSigCoeffGroupCtxInc (:2872) for square TUs of
+// 4:2:0 pictures without scaling lists, extended precision or Golomb-Rice adaptation (every BASELINE cfg).
+//
+// The reference walks the coefficients of a TU once, backwards, with the state of the level coder (context set, greater-1 /
+// greater-2 counters, Rice parameter) carried from coefficient to coefficient, and sums IEEE doubles in that order; the order
+// of the additions is part of the result.  What does NOT depend on that state is split off and done by all lanes of the TU's
+// lane group: the scaled magnitudes, the cost of quantising to zero, the distortion of the two candidate levels, the position
+// of the first non-zero magnitude, the signs, the sign-bit hiding of the coefficient groups (independent of one another) and the
+// stores.  The group's leader runs the state machine on those precomputed terms:
+//
+//   phase A  rq_prepass      every lane   q, cost of level 0, distortion of levels max and max-1 per scan position; last position
+//   phase B  rq_decide       leader       level decisions, coefficient-group zero-out, last-position search      (sequential)
+//   phase C  rq_finish       every lane   signs, zeros above the chosen last position, partial absolute sum
+//   phase D  rq_hide_signs   every lane   sign-bit hiding, one coefficient group per lane at a time
+//
+// The functions are __host__ __device__ so that tests/rdoq_emul.cpp can run the same lines lane by lane on the CPU where there is
+// no GPU (test infrastructure; the product launches them from rdoq.cu only).  Every double operation that the reference performs
+// as a separate multiplication / addition is written with RQ_MUL / RQ_ADD / RQ_SUB (__dmul_rn / __dadd_rn on the device: never
+// contracted into a fused multiply-add).
+#pragma once
+#include <stdint.h>
+#include "../../include/hmgpu.h"
+
+#if defined(__CUDACC__)
+#define RQ_HD __host__ __device__ __forceinline__
+#else
+#define RQ_HD static inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define RQ_MUL(a, b) __dmul_rn((a), (b))
+#define RQ_ADD(a, b) __dadd_rn((a), (b))
+#define RQ_SUB(a, b) __dadd_rn((a), -(b))
+#define RQ_LD(p) __ldg(p)
+#else
+#define RQ_MUL(a, b) ((a) * (b))
+#define RQ_ADD(a, b) ((a) + (b))
+#define RQ_SUB(a, b) ((a) - (b))
+#define RQ_LD(p) (*(p))
+#endif
+
+#define RQ_SIGN_BITS   32768      // one bypass bin, 15-bit fixed point (xGetIEPRate)
+#define RQ_MAX_LEVEL   32767      // entropyCodingMaximum of a 15-bit dynamic range
+#define RQ_DBL_MAX     1.7976931348623157e308
+
+// ---- scan tables (TComRom.cpp:53-220: SCAN_GROUPED_4x4 per TU size and scan type, SCAN_UNGROUPED over the groups) -------------
+// one table for all (scan type t = 0 diagonal / 1 horizontal / 2 vertical, size class s = log2 - 2):
+//   positions of the coefficients:        tab[t * 1360 + {0, 16, 80, 336}[s] + k]           k < 4^log2
+//   raster index of the k-th group:       tab[4080 + t * 85 + {0, 1, 5, 21}[s] + k]         k < 4^(log2 - 2)
+#define RQ_SCAN_WORDS 4335
+RQ_HD int rq_scan_base(int t, int s) { return t * 1360 + (s == 0 ? 0 : s == 1 ? 16 : s == 2 ? 80 : 336); }
+RQ_HD int rq_cg_base(int t, int s) { return 4080 + t * 85 + (s == 0 ? 0 : s == 1 ? 1 : s == 2 ? 5 : 21); }
+
+// (host side: the table is built once and travels with every call)
+// k-th sample of a w x w block in scan order -> (x, y)
+static inline void rq_scan_xy(int type, int w, int k, int* x, int* y)
+{
+  if (type == 1) { *y = k / w; *x = k % w; return; }
+  if (type == 2) { *x = k / w; *y = k % w; return; }
+  // up-right diagonal: walk the anti-diagonals, each from its lower-left end
+  int d = 0, first = 0;
+  for (;; d++)
+  {
+    const int lo = d < w ? 0 : d - w + 1, hi = d < w ? d : w - 1, len = hi - lo + 1;     // x runs lo..hi on diagonal d
+    if (k < first + len) { *x = lo + (k - first); *y = d - *x; return; }
+    first += len;
+  }
+}
+static inline void rq_build_scan_table(uint16_t* tab)
+{
+  for (int t = 0; t < 3; t++)
+    for (int s = 0; s < 4; s++)
+    {
+      const int n = 4 << s, g = n >> 2;
+      uint16_t* sc = tab + rq_scan_base(t, s);
+      uint16_t* cg = tab + rq_cg_base(t, s);
+      for (int i = 0; i < g * g; i++)
+      {
+        int gx, gy;
+        rq_scan_xy(t, g, i, &gx, &gy);
+        cg[i] = (uint16_t)(gy * g + gx);
+        for (int k = 0; k < 16; k++)
+        {
+          int x, y;
+          rq_scan_xy(t, 4, k, &x, &y);
+          sc[16 * i + k] = (uint16_t)((4 * gy + y) * n + 4 * gx + x);
+        }
+      }
+    }
+}
+
+// ---- the workspace of one TU (shared memory on the device) -------------------------------------------------------------------
+// indexed by scan position except lv (raster).  44 bytes per coefficient.
+struct RqWork
+{
+  double*  cz;     // cost of level 0
+  double*  cc;     // A: distortion of level max            B: cost of the chosen level (pdCostCoeff)
+  double*  cs;     // A: distortion of level max - 1        B: cost of its significance flag (pdCostSig)
+  int32_t* qv;     // A: scaled magnitude (lLevelDouble)    B: deltaU
+  int32_t* ru;     // rateIncUp
+  int32_t* rd;     // rateIncDown
+  int32_t* sd;     // sigRateDelta
+  int32_t* lv;     // levels, raster
+};
+#define RQ_WORK_BYTES_PER_COEF 44
+RQ_HD RqWork rq_carve(void* base, int n_coef)
+{
+  RqWork w;
+  w.cz = (double*)base; w.cc = w.cz + n_coef; w.cs = w.cc + n_coef;
+  w.qv = (int32_t*)(w.cs + n_coef); w.ru = w.qv + n_coef; w.rd = w.ru + n_coef; w.sd = w.rd + n_coef; w.lv = w.sd + n_coef;
+  return w;
+}
+
+RQ_HD int rq_quant_scale(int rem) { return rem == 0 ? 26214 : rem == 1 ? 23302 : rem == 2 ? 20560 : rem == 3 ? 18396 : rem == 4 ? 16384 : 14564; }   // g_quantScales
+RQ_HD int rq_inv_quant_scale(int rem) { return rem == 0 ? 40 : rem == 1 ? 45 : rem == 2 ? 51 : rem == 3 ? 57 : rem == 4 ? 64 : 72; }                    // g_invQuantScales
+RQ_HD int rq_abs(int v) { return v < 0 ? -v : v; }
+
+// ---- phase A: lane `lane` of `lanes` -----------------------------------------------------------------------------------------
+// returns the highest scan position this lane saw with a non-zero rounded magnitude (-1: none)
+RQ_HD int rq_prepass(const hmgpu_rdoq_job& j, const uint16_t* scan, const int32_t* coef, RqWork w, int lane, int lanes)
+{
+  const int n_coef = 1 << (2 * j.log2_size), qbits = j.qbits, qscale = rq_quant_scale(j.qp_rem);
+  const long long cap = 0x7fffffffLL - (1LL << (qbits - 1));
+  const double es = j.err_scale;
+  int last = -1;
+  for (int sp = lane; sp < n_coef; sp += lanes)
+  {
+    const int pos = scan[sp];
+    const long long wide = (long long)rq_abs(RQ_LD(coef + pos)) * qscale;
+    const int q = (int)(wide < cap ? wide : cap);
+    int max_lvl = (q + (1 << (qbits - 1))) >> qbits;
+    if (max_lvl > RQ_MAX_LEVEL) max_lvl = RQ_MAX_LEVEL;
+    const double e0 = (double)q;
+    w.cz[sp] = RQ_MUL(RQ_MUL(e0, e0), es);
+    w.qv[sp] = q;
+    if (max_lvl > 0)
+    {
+      last = sp;                                                   // sp ascends: the lane's highest
+      const double e1 = (double)(q - (int)((unsigned)max_lvl << qbits));
+      w.cc[sp] = RQ_MUL(RQ_MUL(e1, e1), es);
+      if (max_lvl > 1)
+      {
+        const double e2 = (double)(q - (int)((unsigned)(max_lvl - 1) << qbits));
+        w.cs[sp] = RQ_MUL(RQ_MUL(e2, e2), es);
+      }
+    }
+    w.lv[sp] = 0;                                                  // (every raster entry once: sp runs over all of them)
+  }
+  return last;
+}
+
+// ---- rates -----------------------------------------------------------------------------------------------------------------
+struct RqCoder { int ctx_set, c1, c2, c1_idx, c2_idx, rice; };
+
+// bits of coding the absolute level lvl after its significance flag (xGetICRate; 8 greater-1 flags and 1 greater-2 flag per group,
+// Rice prefix of at most 3 before the escape, no limited prefix length)
+RQ_HD int rq_level_rate(const hmgpu_rdoq_bits* eb, int lvl, int ctx_one, int ctx_abs, const RqCoder& c)
+{
+  if (lvl <= 0) return 0;
+  const bool g1 = c.c1_idx < 8, g2 = g1 && c.c2_idx < 1;
+  const int base = g1 ? (g2 ? 3 : 2) : 1;
+  int rate = RQ_SIGN_BITS;
+  if (lvl >= base)
+  {
+    unsigned sym = (unsigned)(lvl - base);
+    const int rice = c.rice;
+    if (sym < (3u << rice)) rate += (int)((sym >> rice) + 1 + rice) << 15;
+    else
+    {
+      sym -= 3u << rice;
+      int len = rice;
+      while (sym >= (1u << len)) { sym -= 1u << len; len++; }
+      rate += (3 + len + 1 - rice + len) << 15;
+    }
+    if (g1)
+    {
+      rate += RQ_LD(&eb->greater_one[ctx_one][1]);
+      if (g2) rate += RQ_LD(&eb->level_abs[ctx_abs][1]);
+    }
+  }
+  else if (lvl == 1) rate += RQ_LD(&eb->greater_one[ctx_one][0]);
+  else rate += RQ_LD(&eb->greater_one[ctx_one][1]) + RQ_LD(&eb->level_abs[ctx_abs][0]);       // lvl == 2 below a base of 3
+  return rate;
+}
+
+RQ_HD int rq_last_group(int v) { return v < 4 ? v : v < 6 ? 4 : v < 8 ? 5 : v < 12 ? 6 : v < 16 ? 7 : v < 24 ? 8 : 9; }          // g_uiGroupIdx
+
+// lambda x bits of (x, y) as the last significant position (xGetRateLast)
+RQ_HD double rq_last_cost(const hmgpu_rdoq_bits* eb, double lambda, int ch, int x, int y)
+{
+  const int cx = rq_last_group(x), cy = rq_last_group(y);
+  double bits = (double)(RQ_LD(&eb->last_x[ch][cx]) + RQ_LD(&eb->last_y[ch][cy]));
+  if (cx > 3) bits = RQ_ADD(bits, 32768.0 * ((cx - 2) >> 1));
+  if (cy > 3) bits = RQ_ADD(bits, 32768.0 * ((cy - 2) >> 1));
+  return RQ_MUL(lambda, bits);
+}
+
+// significant_coeff_flag context of raster position pos (getSigCtxInc), with the chroma table offset
+RQ_HD int rq_sig_ctx(int pattern, int first_ctx, int pos, int log2, int ch)
+{
+  const int y = pos >> log2, x = pos - (y << log2);
+  const int table = ch ? 28 : 0;
+  if (pos == 0) return table;
+  if (log2 == 2)
+  {
+    const unsigned long long map = 0x8877886654325410ULL;          // ctxIndMap4x4, a nibble per position
+    return table + first_ctx + (int)((map >> (4 * pos)) & 15);
+  }
+  const int xs = x & 3, ys = y & 3;
+  int cnt;
+  if (pattern == 0) cnt = xs + ys >= 3 ? 0 : (xs + ys >= 1 ? 1 : 2);
+  else if (pattern == 1) cnt = ys >= 2 ? 0 : (ys >= 1 ? 1 : 2);
+  else if (pattern == 2) cnt = xs >= 2 ? 0 : (xs >= 1 ? 1 : 2);
+  else cnt = 2;
+  return table + first_ctx + ((ch == 0 && ((x | y) >> 2)) ? 3 : 0) + cnt;
+}
+
+// ---- phase B: the leader -----------------------------------------------------------------------------------------------------
+// last_pos = highest scan position with a non-zero rounded magnitude (>= 0).  Returns iBestLastIdxP1: the levels of the scan
+// positions below it stand (in w.lv, magnitudes), everything from it upwards is zero.
+RQ_HD int rq_decide(const hmgpu_rdoq_job& j, const hmgpu_rdoq_bits* eb, const uint16_t* scan, const uint16_t* scan_cg, RqWork w, int last_pos)
+{
+  const int log2 = j.log2_size, n_coef = 1 << (2 * log2), g = 1 << (log2 - 2), n_cg = g * g;
+  const int ch = j.channel, qbits = j.qbits, rice0 = j.go_rice_init;
+  const double lambda = j.lambda;
+  const int set0 = ch ? 4 : 0;
+  const int first_ctx = log2 == 2 ? 0 : log2 == 3 ? 9 + ((ch == 0 && j.scan != 0) ? 6 : 0) : (ch == 0 ? 21 : 12);
+  const int last_cg = last_pos >> 4;
+  unsigned long long cg_mask = 0;                                  // coefficient groups marked significant, bit = raster index
+  double cg_cost[64];                                              // cost of the group flag as decided (pdCostCoeffGroupSig)
+
+  // everything above the last position costs its level-0 distortion, summed from the top as the reference does
+  double base = 0.0;
+  for (int sp = n_coef - 1; sp > last_pos; sp--) base = RQ_ADD(base, w.cz[sp]);
+  double uncoded = base;
+
+  RqCoder lc;
+  lc.ctx_set = set0 + ((ch == 0 && last_cg > 0) ? 2 : 0); lc.c1 = 1; lc.c2 = 0; lc.c1_idx = 0; lc.c2_idx = 0; lc.rice = rice0;
+
+  for (int cg = last_cg; cg >= 0; cg--)
+  {
+    const int blk = scan_cg[cg], gy = blk >> (log2 - 2), gx = blk - (gy << (log2 - 2));
+    const int right = gx < g - 1 ? (int)((cg_mask >> (blk + 1)) & 1) : 0;
+    const int below = gy < g - 1 ? (int)((cg_mask >> (blk + g)) & 1) : 0;
+    const int pattern = n_cg > 1 ? right + 2 * below : 0;
+    double s_sig = 0.0, s_sig_first = 0.0, s_coded = 0.0, s_uncoded = 0.0;
+    int nz_above_first = 0, any = 0;
+    for (int k = (cg == last_cg ? (last_pos & 15) : 15); k >= 0; k--)
+    {
+      const int sp = cg * 16 + k, pos = scan[sp];
+      const int q = w.qv[sp];
+      int max_lvl = (q + (1 << (qbits - 1))) >> qbits;
+      if (max_lvl > RQ_MAX_LEVEL) max_lvl = RQ_MAX_LEVEL;
+      const double c_zero = w.cz[sp];
+      uncoded = RQ_ADD(uncoded, c_zero);
+      const int ctx_one = 4 * lc.ctx_set + lc.c1, ctx_abs = lc.ctx_set + lc.c2;
+      const bool is_last = sp == last_pos;
+      int sig0 = 0, sig1 = 0;
+      if (!is_last)
+      {
+        const int ctx_sig = rq_sig_ctx(pattern, first_ctx, pos, log2, ch);
+        sig0 = RQ_LD(&eb->sig[ctx_sig][0]); sig1 = RQ_LD(&eb->sig[ctx_sig][1]);
+      }
+      // xGetCodedLevel: level 0 competes only below 3 and not at the last position; then max, then max - 1 (strict <)
+      int best = 0;
+      double c_best = RQ_DBL_MAX, c_sig_best = 0.0;
+      if (!is_last && max_lvl < 3)
+      {
+        c_sig_best = RQ_MUL(lambda, (double)sig0);
+        c_best = RQ_ADD(c_zero, c_sig_best);
+      }
+      if (max_lvl > 0)
+      {
+        const double c_sig_one = is_last ? 0.0 : RQ_MUL(lambda, (double)sig1);
+        double c = RQ_ADD(RQ_ADD(w.cc[sp], RQ_MUL(lambda, (double)rq_level_rate(eb, max_lvl, ctx_one, ctx_abs, lc))), c_sig_one);
+        if (c < c_best) { best = max_lvl; c_best = c; c_sig_best = c_sig_one; }
+        if (max_lvl > 1)
+        {
+          c = RQ_ADD(RQ_ADD(w.cs[sp], RQ_MUL(lambda, (double)rq_level_rate(eb, max_lvl - 1, ctx_one, ctx_abs, lc))), c_sig_one);
+          if (c < c_best) { best = max_lvl - 1; c_best = c; c_sig_best = c_sig_one; }
+        }
+      }
+      w.cc[sp] = c_best;
+      w.cs[sp] = c_sig_best;
+      w.sd[sp] = sig1 - sig0;
+      w.qv[sp] = (q - (int)((unsigned)best << qbits)) >> (qbits - 8);
+      if (best > 0)
+      {
+        const int now = rq_level_rate(eb, best, ctx_one, ctx_abs, lc);
+        w.ru[sp] = rq_level_rate(eb, best + 1, ctx_one, ctx_abs, lc) - now;
+        w.rd[sp] = rq_level_rate(eb, best - 1, ctx_one, ctx_abs, lc) - now;
+      }
+      else { w.ru[sp] = RQ_LD(&eb->greater_one[ctx_one][0]); w.rd[sp] = 0; }
+      w.lv[pos] = best;
+      base = RQ_ADD(base, c_best);
+
+      // the level coder after this coefficient
+      const int base_lvl = lc.c1_idx < 8 ? (lc.c2_idx < 1 ? 3 : 2) : 1;
+      if (best >= base_lvl && best > (3 << lc.rice) && lc.rice < 4) lc.rice++;
+      if (best >= 1) lc.c1_idx++;
+      if (best > 1) { lc.c1 = 0; if (lc.c2 < 2) lc.c2++; lc.c2_idx++; }
+      else if (best == 1 && lc.c1 > 0 && lc.c1 < 3) lc.c1++;
+      if (k == 0 && sp > 0)
+      {
+        lc.ctx_set = set0 + ((ch == 0 && cg > 1) ? 2 : 0) + (lc.c1 == 0);
+        lc.c1 = 1; lc.c2 = 0; lc.c1_idx = 0; lc.c2_idx = 0; lc.rice = rice0;
+      }
+
+      s_sig = RQ_ADD(s_sig, c_sig_best);
+      if (k == 0) s_sig_first = c_sig_best;
+      if (best)
+      {
+        any = 1;
+        s_coded = RQ_ADD(s_coded, RQ_SUB(c_best, c_sig_best));
+        s_uncoded = RQ_ADD(s_uncoded, c_zero);
+        if (k != 0) nz_above_first++;
+      }
+    }
+    cg_cost[cg] = 0.0;
+    if (any) cg_mask |= 1ULL << blk;
+    if (cg == 0) { cg_mask |= 1ULL; continue; }                    // the flag of the DC group is inferred
+    const int ctx_grp = (right | below) != 0;                      // (the neighbours were decided before this group)
+    if (!any)
+    {
+      const double flag0 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][0]));
+      base = RQ_ADD(base, RQ_SUB(flag0, s_sig));
+      cg_cost[cg] = flag0;
+    }
+    else if (cg < last_cg)                                         // (the group of the last position is settled with that position)
+    {
+      if (nz_above_first == 0) { base = RQ_SUB(base, s_sig_first); s_sig = RQ_SUB(s_sig, s_sig_first); }
+      const double flag0 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][0]));
+      const double flag1 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][1]));
+      double zeroed = RQ_ADD(base, flag0);
+      base = RQ_ADD(base, flag1);
+      cg_cost[cg] = flag1;
+      zeroed = RQ_ADD(zeroed, s_uncoded);
+      zeroed = RQ_SUB(zeroed, s_coded);
+      zeroed = RQ_SUB(zeroed, s_sig);
+      if (zeroed < base)
+      {
+        cg_mask &= ~(1ULL << blk);
+        base = zeroed;
+        cg_cost[cg] = flag0;
+        for (int k = 15; k >= 0; k--)
+        {
+          const int sp = cg * 16 + k, pos = scan[sp];
+          if (w.lv[pos]) { w.lv[pos] = 0; w.cc[sp] = w.cz[sp]; w.cs[sp] = 0.0; }
+        }
+      }
+    }
+  }
+
+  // where to put the last significant position, or nothing coded at all
+  double best_cost = RQ_ADD(uncoded, RQ_MUL(lambda, (double)j.cbf_bits[0]));
+  base = RQ_ADD(base, RQ_MUL(lambda, (double)j.cbf_bits[1]));
+  int best_end = 0;
+  bool stop = false;
+  for (int cg = last_cg; cg >= 0 && !stop; cg--)
+  {
+    base = RQ_SUB(base, cg_cost[cg]);
+    if (!((cg_mask >> scan_cg[cg]) & 1)) continue;
+    for (int k = (cg == last_cg ? (last_pos & 15) : 15); k >= 0; k--)
+    {
+      const int sp = cg * 16 + k, pos = scan[sp];
+      const int l = w.lv[pos];
+      if (l)
+      {
+        const int y = pos >> log2, x = pos - (y << log2);
+        const double c_last = j.scan == 2 ? rq_last_cost(eb, lambda, ch, y, x) : rq_last_cost(eb, lambda, ch, x, y);
+        const double total = RQ_SUB(RQ_ADD(base, c_last), w.cs[sp]);
+        if (total < best_cost) { best_end = sp + 1; best_cost = total; }
+        if (l > 1) { stop = true; break; }
+        base = RQ_SUB(base, w.cc[sp]);
+        base = RQ_ADD(base, w.cz[sp]);
+      }
+      else base = RQ_SUB(base, w.cs[sp]);
+    }
+  }
+  return best_end;
+}
+
+// ---- phase C: signs below best_end, zeros from it up to last_pos; returns the lane's part of uiAbsSum ----------------------------
+RQ_HD int rq_finish(const hmgpu_rdoq_job& j, const uint16_t* scan, const int32_t* coef, RqWork w, int best_end, int last_pos, int lane, int lanes)
+{
+  int sum = 0;
+  for (int sp = lane; sp <= last_pos; sp += lanes)
+  {
+    const int pos = scan[sp];
+    if (sp < best_end)
+    {
+      const int l = w.lv[pos];
+      sum += l;
+      if (RQ_LD(coef + pos) < 0) w.lv[pos] = -l;
+    }
+    else w.lv[pos] = 0;
+  }
+  (void)j;
+  return sum;
+}
+
+// ---- phase D: sign-bit hiding (TComTrQuant.cpp:2380-2517), coefficient groups cg = lane, lane + lanes, ... ------------------------
+// The parity of the sum of a group's levels must tell the sign of its first non-zero coefficient when its first and last non-zero
+// are at least 4 scan positions apart; where it does not, the cheapest +-1 change in the group is applied.  Groups are independent
+// but for one rule: in the first non-empty group from the top (`top_cg`) candidates above its last non-zero are not considered.
+RQ_HD void rq_hide_signs(const hmgpu_rdoq_job& j, const uint16_t* scan, const int32_t* coef, RqWork w, int best_end, int lane, int lanes)
+{
+  const int top_cg = (best_end - 1) >> 4;
+  const double inv = (double)rq_inv_quant_scale(j.qp_rem);
+  // (Int64)(invQuant^2 * 2^(2 per) / lambda / 16 / 2^(2 (bitDepth - 8)) + 0.5), the reference's order of operations
+  const double f = (RQ_MUL(RQ_MUL(inv, inv), (double)(1 << (2 * j.qp_per))) / j.lambda) / 16.0 / (double)(1 << (2 * (j.bit_depth - 8)));
+  const long long rd_factor = (long long)RQ_ADD(f, 0.5);
+  for (int cg = lane; cg <= top_cg; cg += lanes)
+  {
+    const uint16_t* s = scan + cg * 16;
+    int first_nz = 16, last_nz = -1, sum = 0;
+    for (int k = 0; k < 16; k++)
+    {
+      const int l = w.lv[s[k]];
+      if (l) { if (first_nz == 16) first_nz = k; last_nz = k; }
+    }
+    if (last_nz - first_nz < 4) continue;
+    for (int k = first_nz; k <= last_nz; k++) sum += w.lv[s[k]];
+    const int sign = w.lv[s[first_nz]] > 0 ? 0 : 1;
+    if (sign == (sum & 1)) continue;
+    const bool top = cg == top_cg;
+    long long min_cost = INT64_MAX;
+    int min_pos = -1, final_change = 0;
+    for (int k = top ? last_nz : 15; k >= 0; k--)
+    {
+      const int sp = cg * 16 + k, pos = s[k], l = w.lv[pos];
+      long long cur;
+      int change;
+      if (l != 0)
+      {
+        const bool one = l == 1 || l == -1;
+        const long long up = rd_factor * (long long)(-w.qv[sp]) + w.ru[sp];
+        long long down = rd_factor * (long long)w.qv[sp] + w.rd[sp] - (one ? w.sd[sp] : 0);
+        if (top && last_nz == k && one) down -= 4 << 15;
+        if (up < down) { cur = up; change = 1; }
+        else { change = -1; cur = (k == first_nz && one) ? INT64_MAX : down; }
+      }
+      else
+      {
+        cur = rd_factor * (long long)(-rq_abs(w.qv[sp])) + (1 << 15) + w.ru[sp] + w.sd[sp];
+        change = 1;
+        if (k < first_nz && (RQ_LD(coef + pos) >= 0 ? 0 : 1) != sign) cur = INT64_MAX;
+      }
+      if (cur < min_cost) { min_cost = cur; final_change = change; min_pos = pos; }
+    }
+    if (w.lv[min_pos] == RQ_MAX_LEVEL || w.lv[min_pos] == -RQ_MAX_LEVEL - 1) final_change = -1;
+    if (RQ_LD(coef + min_pos) >= 0) w.lv[min_pos] += final_change; else w.lv[min_pos] -= final_change;
+  }
+}

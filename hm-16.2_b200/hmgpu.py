@@ -42,6 +42,14 @@ assert ME_JOB.itemsize == 48 and ME_RESULT.itemsize == 24 and DIST_ITEM.itemsize
 assert PRED_JOB.itemsize == 20
 INTRA_JOB = np.dtype([("org_offset", "<u4"), ("ref_offset", "<u4"), ("size", "u1"), ("flags", "u1"), ("reserved", "<u2")], align=True)
 assert INTRA_JOB.itemsize == 12
+# hmgpu_rdoq_bits / hmgpu_rdoq_job of include/hmgpu.h
+RDOQ_BITS = np.dtype([("sig_group", "<i4", (2, 2)), ("sig", "<i4", (44, 2)), ("last_x", "<i4", (2, 10)), ("last_y", "<i4", (2, 10)),
+                      ("greater_one", "<i4", (24, 2)), ("level_abs", "<i4", (6, 2))])
+RDOQ_JOB = np.dtype([("log2_size", "<i4"), ("channel", "<i4"), ("scan", "<i4"), ("flags", "<u4"), ("qbits", "<i4"), ("qp_per", "<i4"),
+                     ("qp_rem", "<i4"), ("go_rice_init", "<i4"), ("cbf_bits", "<i4", (2,)), ("bit_depth", "<i4"), ("bits_index", "<i4"),
+                     ("coef_offset", "<u4"), ("reserved", "<u4"), ("err_scale", "<f8"), ("lambda", "<f8")], align=True)
+assert RDOQ_BITS.itemsize == 768 and RDOQ_JOB.itemsize == 72
+RDOQ_SIGN_HIDE = 1
 IF_ABOVE, IF_LEFT, IF_EDGE_FILTERS, IF_SATD, IF_NO_SMOOTH = 1, 2, 4, 8, 16
 
 EXPORTS = [
@@ -50,7 +58,7 @@ EXPORTS = [
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_deblock", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform", "hmgpu_inv_transform",
-    "hmgpu_quant", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
+    "hmgpu_quant", "hmgpu_rdoq", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
 _lib = None
@@ -118,6 +126,7 @@ def lib():
     L.hmgpu_fwd_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_inv_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.hmgpu_rdoq.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp, vp]
     L.hmgpu_profile_enable.argtypes = [vp, ci]
     L.hmgpu_profile_stage_name.argtypes = [ci]
     L.hmgpu_profile_stage_name.restype = C.c_char_p
@@ -408,3 +417,14 @@ class Context:
         self._check(self.L.hmgpu_quant(self.h, coeff.ctypes.data, coeff.shape[0], n, qp_per, qp_rem, int(is_intra),
                                        level.ctypes.data, delta.ctypes.data, abs_sum.ctypes.data))
         return level, delta, abs_sum
+
+    def rdoq(self, jobs, bits, coef):
+        """rate-distortion optimised quantisation of every TU of `jobs` (hmgpu_rdoq): -> (levels laid out like coef, uiAbsSum per TU)"""
+        jobs = np.ascontiguousarray(jobs, RDOQ_JOB).ravel()
+        bits = np.ascontiguousarray(bits, RDOQ_BITS).ravel()
+        coef = np.ascontiguousarray(coef, np.int32).ravel()
+        level = np.zeros_like(coef)
+        abs_sum = np.zeros(len(jobs), np.int32)
+        self._check(self.L.hmgpu_rdoq(self.h, jobs.ctypes.data, len(jobs), bits.ctypes.data, len(bits), coef.ctypes.data, coef.size,
+                                      level.ctypes.data, abs_sum.ctypes.data))
+        return level, abs_sum

@@ -370,6 +370,47 @@ int hmgpu_inv_transform(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, 
 int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_per, int qp_rem,
                 int is_intra_slice, int32_t* level, int32_t* delta_u, uint32_t* abs_sum);
 
+/* ------------------------------------------------------------------------------------------
+ * Rate-distortion optimised quantisation, batched over TUs.
+ * hmgpu_rdoq replaces TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1974-2520; called from TComTrQuant::xQuant :1074-1118 when
+ * RDOQ = 1) with xGetCodedLevel (:2660), xGetICRate (:2725), xGetRateLast (:2815), getSigCtxInc (:2548): the level decision per
+ * coefficient, the zero-out of coefficient groups, the choice of the last significant position and sign-bit hiding, for square
+ * TUs of 4:2:0 pictures without scaling lists / extended precision / Golomb-Rice adaptation.  The CABAC bit estimates stay the
+ * host's (TEncSbac::estBit fills estBitsSbacStruct, TComTrQuant.h:59-73, from the coder's state of the moment): the caller
+ * passes the tables RDOQ reads, one set per distinct coder state, and every TU names its set.  Costs are IEEE doubles summed in
+ * the reference's order; levels and uiAbsSum are bit-identical.
+ *   jobs[i]          TU i (coef_offset: where its n x n coefficients / levels start in coef / level, raster, pitch n)
+ *   bits[k]          set k of bit estimates, 15-bit fixed point
+ *   abs_sum[i]       uiAbsSum of TU i (sum of the magnitudes before sign-bit hiding, as the reference returns it)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmgpu_rdoq_bits {
+  int32_t sig_group[2][2];       /* significantCoeffGroupBits */
+  int32_t sig[44][2];            /* significantBits: 28 luma contexts, then 16 chroma (getSignificanceMapContextOffset) */
+  int32_t last_x[2][10];         /* lastXBits[channel type][group] */
+  int32_t last_y[2][10];
+  int32_t greater_one[24][2];    /* m_greaterOneBits */
+  int32_t level_abs[6][2];       /* m_levelAbsBits */
+} hmgpu_rdoq_bits;
+#define HMGPU_RDOQ_SIGN_HIDE 1u  /* flags: cu.getSlice()->getPPS()->getSignHideFlag() (and no transquant bypass) */
+typedef struct hmgpu_rdoq_job {
+  int32_t  log2_size;            /* 2..5 */
+  int32_t  channel;              /* 0 luma, 1 chroma */
+  int32_t  scan;                 /* 0 diagonal, 1 horizontal, 2 vertical (getTUEntropyCodingParameters) */
+  uint32_t flags;
+  int32_t  qbits;                /* QUANT_SHIFT + per + transform shift */
+  int32_t  qp_per, qp_rem;
+  int32_t  go_rice_init;         /* 0 without persistent Rice adaptation */
+  int32_t  cbf_bits[2];          /* blockCbpBits / blockRootCbpBits of cbf = 0 / 1 in the context this TU's flag is coded in */
+  int32_t  bit_depth;
+  int32_t  bits_index;           /* which set of `bits` */
+  uint32_t coef_offset;
+  uint32_t reserved;
+  double   err_scale;            /* getErrScaleCoeffNoScalingList (TComTrQuant.cpp:2043, set at :2954) */
+  double   lambda;               /* m_dLambda of the component */
+} hmgpu_rdoq_job;
+int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmgpu_rdoq_bits* bits, int n_bits,
+               const int32_t* coef, int n_coef, int32_t* level, int32_t* abs_sum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,101 @@
+"""f1 without a GPU: the __host__ __device__ body of the RDOQ kernel (hm-16.2_b200/csrc/rdoq_impl.cuh), run lane by lane by
+tests/rdoq_emul.cpp in the phase order of rdoq.cu, against the calls of the reference's xRateDistOptQuant dumped by the
+instrumented reference encoder (tests/golden/rdoq_golden.npz) and against the oracle on random TUs.  This checks the kernel's
+LOGIC where there is no GPU; the kernel itself is checked by tests/test_gpu_rdoq.py.  Also: the scan tables of the kernel
+against the oracle's (which follow TComRom.cpp's ScanGenerator)."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import hmgpu
+import rdoqdump
+from oracle import binding as B
+from test_golden import rdoq_golden_calls
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LANES = {2: 1, 3: 2, 4: 8, 5: 32}          # lanes per TU of rdoq.cu's launch classes
+
+
+@pytest.fixture(scope="module")
+def emul():
+    tmp = tempfile.mkdtemp(prefix="rdoq_emul_")
+    so = os.path.join(tmp, "librdoq_emul.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, os.path.join(HERE, "rdoq_emul.cpp")])
+    L = C.CDLL(so)
+    L.rdoq_emul.restype = C.c_int
+    L.rdoq_emul.argtypes = [C.c_void_p] * 4 + [C.c_int]
+    L.rdoq_emul_scan_table.argtypes = [C.c_void_p]
+    return L
+
+
+def run_emul(L, job, bits, coef, lanes):
+    coef = np.ascontiguousarray(coef, np.int32)
+    level = np.full_like(coef, 12345)
+    job = np.ascontiguousarray(job)
+    bits = np.ascontiguousarray(bits)
+    s = L.rdoq_emul(job.ctypes.data, bits.ctypes.data, coef.ctypes.data, level.ctypes.data, lanes)
+    return level, s
+
+
+def test_scan_tables_match_oracle(emul):
+    tab = np.zeros(4335, np.uint16)
+    emul.rdoq_emul_scan_table(tab.ctypes.data)
+    scan_at, cg_at = [0, 16, 80, 336], [0, 1, 5, 21]
+    for t in range(3):
+        for s in range(4):
+            n = 16 << (2 * s)
+            scan = np.zeros(n, np.uint16)
+            scan_cg = np.zeros(max(n // 16, 1), np.uint16)
+            B.oracle().hmo_scan_order(s + 2, t, scan.ctypes.data, scan_cg.ctypes.data)
+            assert np.array_equal(tab[t * 1360 + scan_at[s]:t * 1360 + scan_at[s] + n], scan), (t, s)
+            assert np.array_equal(tab[4080 + t * 85 + cg_at[s]:4080 + t * 85 + cg_at[s] + n // 16], scan_cg), (t, s)
+
+
+def test_kernel_body_on_the_reference_encoders_calls(emul):
+    calls = rdoq_golden_calls()
+    assert len(calls) >= 1000
+    for i, c in enumerate(calls):
+        job, bits = rdoqdump.to_tu_and_bits(c, hmgpu.RDOQ_JOB, hmgpu.RDOQ_BITS)
+        for lanes in {LANES[c["log2"]], 1, 32}:
+            level, s = run_emul(emul, job, bits, c["coef"], lanes)
+            assert s == c["abs_sum"] and np.array_equal(level, c["level"]), (i, lanes, {k: c[k] for k in rdoqdump.HDR})
+
+
+def random_tus(rng, n, calls):
+    """random TUs in the statistics RDOQ sees (Laplacian coefficients decaying with frequency, now and then dense or huge),
+    with the bit estimates / lambda / scale of a dumped call of the same size and channel"""
+    out = []
+    for k in range(n):
+        c = calls[int(rng.integers(len(calls)))]
+        nn = c["w"]
+        yy, xx = np.mgrid[0:nn, 0:nn]
+        mode = k % 4
+        scale = [400.0, 3000.0, 60.0, 20000.0][mode] / (1.0 + (xx + yy) * [0.8, 0.15, 1.5, 0.02][mode])
+        coef = np.round(rng.laplace(0.0, 1.0, (nn, nn)) * scale).astype(np.int64)
+        if mode == 3:
+            coef[rng.integers(nn), rng.integers(nn)] = int(rng.choice([32767, -32768]))
+        coef = np.clip(coef, -32768, 32767).astype(np.int32).ravel()
+        d = dict(c)
+        d["coef"] = coef
+        d["sign_hide"] = int(rng.integers(2))
+        d["scan"] = int(rng.integers(3)) if nn <= 8 else 0
+        out.append(d)
+    return out
+
+
+def test_kernel_body_on_random_tus_against_oracle(emul):
+    rng = np.random.default_rng(2024)
+    calls = rdoq_golden_calls()
+    changed = 0
+    for i, c in enumerate(random_tus(rng, 1500, calls)):
+        tu, obits = rdoqdump.to_tu_and_bits(c, B.RDOQ_TU, B.RDOQ_BITS)
+        want, want_sum = B.rdoq(tu, obits, c["coef"])
+        job, bits = rdoqdump.to_tu_and_bits(c, hmgpu.RDOQ_JOB, hmgpu.RDOQ_BITS)
+        level, s = run_emul(emul, job, bits, c["coef"], LANES[c["log2"]])
+        assert s == want_sum and np.array_equal(level, want), (i, {k: c[k] for k in rdoqdump.HDR})
+        changed += int(np.abs(want).sum() != want_sum)
+    assert changed > 50
