@@ -126,6 +126,7 @@ static void tuning_from_env(HmgpuTuning* t)
   t->frac_win       = env_int("HMGPU_FRAC_WIN", 1);
   t->frac_win_min   = env_int("HMGPU_FRAC_WIN_MIN", 4096);
   t->fs_tma         = env_int("HMGPU_FS_TMA", 1);
+  t->rdoq_tu        = env_int("HMGPU_RDOQ_TU", 1);
   t->pipe_chunk     = env_int("HMGPU_PIPE_CHUNK", 0);
   t->pipe_edge      = env_int("HMGPU_PIPE_EDGE", 8);
   t->pipeline       = !env_int("HMGPU_NO_PIPELINE", 0);
@@ -142,7 +143,7 @@ static const TuneName k_tune_names[] = {
   { "tz_carve", &HmgpuTuning::tz_carve }, { "tz_p2", &HmgpuTuning::tz_p2 }, { "frac_v1", &HmgpuTuning::frac_v1 },
   { "frac_overlap", &HmgpuTuning::frac_overlap }, { "frac_win", &HmgpuTuning::frac_win }, { "frac_win_min", &HmgpuTuning::frac_win_min }, { "fs_tma", &HmgpuTuning::fs_tma }, { "pipe_chunk", &HmgpuTuning::pipe_chunk }, { "pipe_edge", &HmgpuTuning::pipe_edge }, { "pipeline", &HmgpuTuning::pipeline },
   { "fastpath", &HmgpuTuning::fastpath }, { "server", &HmgpuTuning::server }, { "server_idle_us", &HmgpuTuning::server_idle_us },
-  { "trace", &HmgpuTuning::trace }, { "server_stats", &HmgpuTuning::server_stats } };
+  { "trace", &HmgpuTuning::trace }, { "server_stats", &HmgpuTuning::server_stats }, { "rdoq_tu", &HmgpuTuning::rdoq_tu } };
 
 // true when p is page-locked host memory known to CUDA (hmgpu_host_alloc or the caller's own cudaHostAlloc)
 static bool is_pinned(const void* p)

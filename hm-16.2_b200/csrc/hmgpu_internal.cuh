@@ -77,6 +77,7 @@ struct HmgpuTuning
   int server_idle_us;   // HMGPU_SERVER_IDLE_US
   int trace;            // HMGPU_TRACE
   int server_stats;     // HMGPU_SERVER_STATS
+  int rdoq_tu;          // HMGPU_RDOQ_TU: RDOQ with one thread per TU (rdoq_tu_kernel) instead of one lane group per TU
 };
 
 struct hmgpu_ctx

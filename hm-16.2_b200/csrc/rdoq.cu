@@ -92,10 +92,76 @@ static int launch_class(hmgpu_ctx* ctx, uint32_t attr_bit, const hmgpu_rdoq_job*
   return HMGPU_OK;
 }
 
-// d_list: the job indices sorted by TU size, n_class[s] of size class s = log2 - 2, one class after the other
+// ---- one thread per TU (rdoq_impl.cuh, second half) ---------------------------------------------------------------------------
+// Warp i of the launch takes 32 TUs of one size class -- the classes follow one another in the warp numbering, largest TUs first,
+// so the long chains start first and the short ones fill the machine around them -- and one launch covers all four sizes.  The
+// workspace of a warp (24 bytes per coefficient and lane, [scan position][lane]) lives in global memory: resident warps x 768 KB
+// for 32x32 TUs, written and read once in full lines.
+#define RDOQ_TU_WARPS 2         // warps per CTA
+struct RdoqTuPlan
+{
+  int first_warp[5];            // warps [first_warp[c], first_warp[c + 1]) work on size class 3 - c (32x32 first)
+  int first_item[4];            // where the items of that class start in the list
+  int n_item[4];
+  unsigned long long slot_bytes;
+};
+
+__global__ void __launch_bounds__(RDOQ_TU_WARPS * 32)
+rdoq_tu_kernel(const hmgpu_rdoq_job* __restrict__ jobs, const int* __restrict__ list, RdoqTuPlan plan, const hmgpu_rdoq_bits* __restrict__ bits,
+               const uint16_t* __restrict__ scan_tab, const int32_t* __restrict__ coef_all, int32_t* __restrict__ level_all, int32_t* __restrict__ abs_sum,
+               unsigned char* __restrict__ work)
+{
+  const int lane = threadIdx.x & 31, slot = blockIdx.x * RDOQ_TU_WARPS + (threadIdx.x >> 5);
+  for (int wi = slot; wi < plan.first_warp[4]; wi += gridDim.x * RDOQ_TU_WARPS)
+  {
+    const int c = wi < plan.first_warp[1] ? 0 : wi < plan.first_warp[2] ? 1 : wi < plan.first_warp[3] ? 2 : 3;
+    const int log2 = 5 - c, at = (wi - plan.first_warp[c]) * 32 + lane;
+    const bool has_tu = at < plan.n_item[c];
+    const int ji = has_tu ? list[plan.first_item[c] + at] : 0;
+    hmgpu_rdoq_job j;
+    if (has_tu) j = jobs[ji];
+    else { memset(&j, 0, sizeof j); j.qbits = 14; j.err_scale = 1.0; j.lambda = 1.0; }
+    const uint16_t* scan = scan_tab + rq_scan_base(j.scan, log2 - 2);
+    const uint16_t* scan_cg = scan_tab + rq_cg_base(j.scan, log2 - 2);
+    Rq2Work w = rq2_carve(work + (size_t)slot * plan.slot_bytes, 1 << (2 * log2), lane);
+    const int sum = rq2_tu(j, has_tu, log2, bits + j.bits_index, scan, scan_cg, coef_all + j.coef_offset, level_all + j.coef_offset, w);
+    if (has_tu) abs_sum[ji] = sum;
+    __syncwarp();
+  }
+}
+
+static int launch_tu(hmgpu_ctx* ctx, const hmgpu_rdoq_job* d_jobs, const int* d_list, const int n_class[4], const hmgpu_rdoq_bits* d_bits,
+                     const uint16_t* d_scan, const int32_t* d_coef, int32_t* d_level, int32_t* d_abs_sum)
+{
+  RdoqTuPlan plan;
+  int item = n_class[0] + n_class[1] + n_class[2] + n_class[3], warp = 0, largest = -1;
+  for (int c = 0; c < 4; c++)                                      // class 3 - c
+  {
+    const int n = n_class[3 - c];
+    item -= n;
+    plan.first_warp[c] = warp; plan.first_item[c] = item; plan.n_item[c] = n;
+    warp += (n + 31) / 32;
+    if (n > 0 && largest < 0) largest = 3 - c;
+  }
+  plan.first_warp[4] = warp;
+  if (warp == 0) return HMGPU_OK;
+  plan.slot_bytes = (unsigned long long)RQ2_BYTES_PER_COEF * 32 * (16u << (2 * largest));
+  int grid = (warp + RDOQ_TU_WARPS - 1) / RDOQ_TU_WARPS;
+  if (grid > 148 * 4) grid = 148 * 4;                              // at most 1184 warps' worth of workspace (0.9 GB for 32x32 TUs)
+  int rc;
+  if ((rc = hmgpu_reserve_work(ctx, (size_t)grid * RDOQ_TU_WARPS * plan.slot_bytes))) return rc;
+  HmgpuStage st(ctx, HMGPU_ST_QUANT, 1);
+  rdoq_tu_kernel<<<grid, RDOQ_TU_WARPS * 32, 0, ctx->stream>>>(d_jobs, d_list, plan, d_bits, d_scan, d_coef, d_level, d_abs_sum, (unsigned char*)ctx->d_work);
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}
+
+// d_list: the job indices sorted by TU size, n_class[s] of size class s = log2 - 2, one class after the other.
+// d_level must be zero where no level is written (rdoq_tu_kernel stores the non-zero levels only).
 int hmgpu_launch_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* d_jobs, const int* d_list, const int n_class[4], const hmgpu_rdoq_bits* d_bits,
                       const uint16_t* d_scan, const int32_t* d_coef, int32_t* d_level, int32_t* d_abs_sum)
 {
+  if (ctx->tune.rdoq_tu) return launch_tu(ctx, d_jobs, d_list, n_class, d_bits, d_scan, d_coef, d_level, d_abs_sum);
   const int launches = (n_class[0] > 0) + (n_class[1] > 0) + (n_class[2] > 0) + (n_class[3] > 0);
   HmgpuStage st(ctx, HMGPU_ST_QUANT, launches);
   int rc;

@@ -454,3 +454,358 @@ RQ_HD void rq_hide_signs(const hmgpu_rdoq_job& j, const uint16_t* scan, const in
     if (RQ_LD(coef + min_pos) >= 0) w.lv[min_pos] += final_change; else w.lv[min_pos] -= final_change;
   }
 }
+
+// =================================================================================================================================
+// One THREAD per TU (rdoq.cu, rdoq_tu_kernel): the 32 lanes of a warp carry 32 TUs of the same size through the reference's loop
+// in LOCKSTEP -- every lane is at the same scan position at the same time, so the workspace of the warp, laid out
+// [scan position][lane] in global memory, is read and written in full 128-byte lines -- and each lane runs the state machine of its
+// own TU.  Where the lane-group kernel above keeps one lane of 32 busy during the sequential phase, this one keeps all of them.
+//
+// Per coefficient the workspace holds 24 bytes: the scaled magnitude with the coefficient's sign in bit 31 (qw), the decision
+// (st: level, the level coder's state at that moment, the group's pattern), the cost of the decided level (cc) and of its
+// significance flag (cs).  Everything else the reference stores per coefficient (cost of level 0, deltaU, rateIncUp / Down,
+// sigRateDelta) is a function of those and is recomputed where it is needed: the same operations on the same operands, so the
+// same bits.
+//
+// The loops have warp-uniform bounds (RQ_WARP_MAX over the lanes) and lane predicates inside.  On the host (tests/rdoq_emul.cpp)
+// one lane runs alone; rq_ghost_top >= 0 stands for a neighbouring lane that is longer in every respect, so that the predicates
+// are exercised too.
+// =================================================================================================================================
+#if defined(__CUDA_ARCH__)
+#define RQ_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))
+#define RQ_WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#define RQ2_STRIDE 32
+#else
+static int rq_ghost_top = -1;
+#define RQ_WARP_MAX(v) ((v) > rq_ghost_top ? (v) : rq_ghost_top)
+#define RQ_WARP_ANY(p) ((p) || rq_ghost_top >= 0)
+#define RQ2_STRIDE 1
+#endif
+#define RQ2_BYTES_PER_COEF 24
+#define RQ2_ZEROED (1u << 15)
+
+struct Rq2Work { int32_t* qw; uint32_t* st; double* cc; double* cs; };      // this lane's element sp: [sp * RQ2_STRIDE]
+// slot = the workspace of one warp (32 TUs of n_coef coefficients), lane = this thread's place in it
+RQ_HD Rq2Work rq2_carve(void* slot, int n_coef, int lane)
+{
+  Rq2Work w;
+  const size_t n = (size_t)n_coef * RQ2_STRIDE;
+  w.cc = (double*)slot + lane; w.cs = w.cc + n;
+  w.qw = (int32_t*)((double*)slot + 2 * n) + lane; w.st = (uint32_t*)(w.qw - lane + n) + lane;
+  return w;
+}
+
+// st: bits 0..14 level, 15 zeroed afterwards (group zero-out), 16..18 context set, 19..20 c1, 21..22 c2, 23 greater-1 flags left,
+// 24 greater-2 flag left, 25..27 Rice parameter, 28..29 pattern of the group, 30 the last position
+RQ_HD uint32_t rq2_pack(int best, const RqCoder& c, int pattern, bool is_last)
+{
+  return (uint32_t)best | ((uint32_t)c.ctx_set << 16) | ((uint32_t)c.c1 << 19) | ((uint32_t)c.c2 << 21) | ((uint32_t)(c.c1_idx < 8) << 23)
+       | ((uint32_t)(c.c2_idx < 1) << 24) | ((uint32_t)c.rice << 25) | ((uint32_t)pattern << 28) | ((uint32_t)is_last << 30);
+}
+RQ_HD int rq2_level(uint32_t st) { return (st & RQ2_ZEROED) ? 0 : (int)(st & 0x7fffu); }
+RQ_HD double rq2_cost_zero(int q, double es) { const double e0 = (double)q; return RQ_MUL(RQ_MUL(e0, e0), es); }
+RQ_HD int rq2_first_ctx(const hmgpu_rdoq_job& j, int log2)
+{
+  return log2 == 2 ? 0 : log2 == 3 ? 9 + ((j.channel == 0 && j.scan != 0) ? 6 : 0) : (j.channel == 0 ? 21 : 12);
+}
+
+// what the reference noted down beside a decision for sign-bit hiding: deltaU, rateIncUp, rateIncDown, sigRateDelta
+RQ_HD void rq2_side(const hmgpu_rdoq_job& j, const hmgpu_rdoq_bits* eb, uint32_t st, int q, int pos, int log2, int* d_u, int* r_up, int* r_down, int* sig_delta)
+{
+  const int best = (int)(st & 0x7fffu);
+  RqCoder c;
+  c.ctx_set = (st >> 16) & 7; c.c1 = (st >> 19) & 3; c.c2 = (st >> 21) & 3;
+  c.c1_idx = ((st >> 23) & 1) ? 0 : 8; c.c2_idx = ((st >> 24) & 1) ? 0 : 1; c.rice = (st >> 25) & 7;
+  const int ctx_one = 4 * c.ctx_set + c.c1, ctx_abs = c.ctx_set + c.c2;
+  *d_u = (q - (int)((unsigned)best << j.qbits)) >> (j.qbits - 8);
+  if (best > 0)
+  {
+    const int now = rq_level_rate(eb, best, ctx_one, ctx_abs, c);
+    *r_up = rq_level_rate(eb, best + 1, ctx_one, ctx_abs, c) - now;
+    *r_down = rq_level_rate(eb, best - 1, ctx_one, ctx_abs, c) - now;
+  }
+  else { *r_up = RQ_LD(&eb->greater_one[ctx_one][0]); *r_down = 0; }
+  if ((st >> 30) & 1) *sig_delta = 0;
+  else
+  {
+    const int ctx_sig = rq_sig_ctx((st >> 28) & 3, rq2_first_ctx(j, log2), pos, log2, j.channel);
+    *sig_delta = RQ_LD(&eb->sig[ctx_sig][1]) - RQ_LD(&eb->sig[ctx_sig][0]);
+  }
+}
+
+// The whole of xRateDistOptQuant for this lane's TU.  has_tu: the lane carries a TU (the last warp of a size class may not be
+// full); log2: the size class, the same for every lane of the warp.  Levels that come out zero are NOT stored: the caller's level
+// buffer starts out as zeros.  Returns uiAbsSum.
+RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdoq_bits* eb, const uint16_t* scan, const uint16_t* scan_cg,
+                 const int32_t* coef, int32_t* level, Rq2Work w)
+{
+  const int n_coef = 1 << (2 * log2), g = 1 << (log2 - 2), n_cg = g * g;
+  const int qbits = j.qbits, half = 1 << (qbits - 1), ch = j.channel;
+  const double lambda = j.lambda, es = j.err_scale;
+
+  // A: scaled magnitudes, the highest position whose rounded magnitude is not zero
+  int last_pos = -1;
+  if (has_tu)
+  {
+    const int qscale = rq_quant_scale(j.qp_rem);
+    const long long cap = 0x7fffffffLL - (1LL << (qbits - 1));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+    for (int sp = 0; sp < n_coef; sp++)
+    {
+      const int c = RQ_LD(coef + RQ_LD(scan + sp));
+      const long long wide = (long long)rq_abs(c) * qscale;
+      const int q = (int)(wide < cap ? wide : cap);
+      if (((q + half) >> qbits) > 0) last_pos = sp;
+      w.qw[(size_t)sp * RQ2_STRIDE] = (int32_t)((uint32_t)q | (c < 0 ? 0x80000000u : 0u));
+    }
+  }
+  const bool live = last_pos >= 0;
+  if (!RQ_WARP_ANY(live)) return 0;
+
+  // B: level decisions and group zero-out, from the top of the scan down
+  const int last_cg = last_pos >> 4;                               // (-1 for a lane that is not live)
+  const int rice0 = j.go_rice_init, set0 = ch ? 4 : 0, first_ctx = rq2_first_ctx(j, log2);
+  unsigned long long cg_mask = 0;
+  double cg_cost[64];
+  double base = 0.0, uncoded = 0.0;
+  RqCoder lc;
+  lc.ctx_set = set0 + ((ch == 0 && last_cg > 0) ? 2 : 0); lc.c1 = 1; lc.c2 = 0; lc.c1_idx = 0; lc.c2_idx = 0; lc.rice = rice0;
+  int q_next = live ? w.qw[(size_t)(n_coef - 1) * RQ2_STRIDE] : 0;
+  for (int cg = n_cg - 1; cg >= 0; cg--)
+  {
+    const bool in = live && cg <= last_cg;
+    int blk = 0, right = 0, below = 0, pattern = 0;
+    if (in)
+    {
+      blk = RQ_LD(scan_cg + cg);
+      const int gy = blk >> (log2 - 2), gx = blk - (gy << (log2 - 2));
+      right = gx < g - 1 ? (int)((cg_mask >> (blk + 1)) & 1) : 0;
+      below = gy < g - 1 ? (int)((cg_mask >> (blk + g)) & 1) : 0;
+      pattern = n_cg > 1 ? right + 2 * below : 0;
+    }
+    double s_sig = 0.0, s_sig_first = 0.0, s_coded = 0.0, s_uncoded = 0.0;
+    int nz_above_first = 0, any = 0;
+    for (int k = 15; k >= 0; k--)
+    {
+      const int sp = cg * 16 + k;
+      if (!live) continue;
+      const int q = q_next & 0x7fffffff;
+      if (sp > 0) q_next = w.qw[(size_t)(sp - 1) * RQ2_STRIDE];     // (one position ahead: the load is off the critical path)
+      const double c_zero = rq2_cost_zero(q, es);
+      uncoded = RQ_ADD(uncoded, c_zero);
+      if (sp > last_pos) { base = uncoded; continue; }             // above the last position only the cost of level 0 adds up
+      const int pos = RQ_LD(scan + sp);
+      int max_lvl = (q + half) >> qbits;
+      if (max_lvl > RQ_MAX_LEVEL) max_lvl = RQ_MAX_LEVEL;
+      const int ctx_one = 4 * lc.ctx_set + lc.c1, ctx_abs = lc.ctx_set + lc.c2;
+      const bool is_last = sp == last_pos;
+      int sig0 = 0, sig1 = 0;
+      if (!is_last)
+      {
+        const int ctx_sig = rq_sig_ctx(pattern, first_ctx, pos, log2, ch);
+        sig0 = RQ_LD(&eb->sig[ctx_sig][0]); sig1 = RQ_LD(&eb->sig[ctx_sig][1]);
+      }
+      int best = 0;
+      double c_best = RQ_DBL_MAX, c_sig_best = 0.0;
+      if (!is_last && max_lvl < 3)
+      {
+        c_sig_best = RQ_MUL(lambda, (double)sig0);
+        c_best = RQ_ADD(c_zero, c_sig_best);
+      }
+      if (max_lvl > 0)
+      {
+        const double c_sig_one = is_last ? 0.0 : RQ_MUL(lambda, (double)sig1);
+        const double e1 = (double)(q - (int)((unsigned)max_lvl << qbits));
+        double c = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e1, e1), es), RQ_MUL(lambda, (double)rq_level_rate(eb, max_lvl, ctx_one, ctx_abs, lc))), c_sig_one);
+        if (c < c_best) { best = max_lvl; c_best = c; c_sig_best = c_sig_one; }
+        if (max_lvl > 1)
+        {
+          const double e2 = (double)(q - (int)((unsigned)(max_lvl - 1) << qbits));
+          c = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e2, e2), es), RQ_MUL(lambda, (double)rq_level_rate(eb, max_lvl - 1, ctx_one, ctx_abs, lc))), c_sig_one);
+          if (c < c_best) { best = max_lvl - 1; c_best = c; c_sig_best = c_sig_one; }
+        }
+      }
+      w.cc[(size_t)sp * RQ2_STRIDE] = c_best;
+      w.cs[(size_t)sp * RQ2_STRIDE] = c_sig_best;
+      w.st[(size_t)sp * RQ2_STRIDE] = rq2_pack(best, lc, pattern, is_last);
+      base = RQ_ADD(base, c_best);
+
+      // the level coder after this coefficient
+      const int base_lvl = lc.c1_idx < 8 ? (lc.c2_idx < 1 ? 3 : 2) : 1;
+      if (best >= base_lvl && best > (3 << lc.rice) && lc.rice < 4) lc.rice++;
+      if (best >= 1) lc.c1_idx++;
+      if (best > 1) { lc.c1 = 0; if (lc.c2 < 2) lc.c2++; lc.c2_idx++; }
+      else if (best == 1 && lc.c1 > 0 && lc.c1 < 3) lc.c1++;
+      if (k == 0 && sp > 0)
+      {
+        lc.ctx_set = set0 + ((ch == 0 && cg > 1) ? 2 : 0) + (lc.c1 == 0);
+        lc.c1 = 1; lc.c2 = 0; lc.c1_idx = 0; lc.c2_idx = 0; lc.rice = rice0;
+      }
+
+      s_sig = RQ_ADD(s_sig, c_sig_best);
+      if (k == 0) s_sig_first = c_sig_best;
+      if (best)
+      {
+        any = 1;
+        s_coded = RQ_ADD(s_coded, RQ_SUB(c_best, c_sig_best));
+        s_uncoded = RQ_ADD(s_uncoded, c_zero);
+        if (k != 0) nz_above_first++;
+      }
+    }
+    if (!in) continue;
+    cg_cost[cg] = 0.0;
+    if (any) cg_mask |= 1ULL << blk;
+    if (cg == 0) { cg_mask |= 1ULL; continue; }                    // the flag of the DC group is inferred
+    const int ctx_grp = (right | below) != 0;
+    if (!any)
+    {
+      const double flag0 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][0]));
+      base = RQ_ADD(base, RQ_SUB(flag0, s_sig));
+      cg_cost[cg] = flag0;
+    }
+    else if (cg < last_cg)                                         // (the group of the last position is settled with that position)
+    {
+      if (nz_above_first == 0) { base = RQ_SUB(base, s_sig_first); s_sig = RQ_SUB(s_sig, s_sig_first); }
+      const double flag0 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][0]));
+      const double flag1 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][1]));
+      double zeroed = RQ_ADD(base, flag0);
+      base = RQ_ADD(base, flag1);
+      cg_cost[cg] = flag1;
+      zeroed = RQ_ADD(zeroed, s_uncoded);
+      zeroed = RQ_SUB(zeroed, s_coded);
+      zeroed = RQ_SUB(zeroed, s_sig);
+      if (zeroed < base)
+      {
+        cg_mask &= ~(1ULL << blk);
+        base = zeroed;
+        cg_cost[cg] = flag0;
+        for (int k = 15; k >= 0; k--)
+        {
+          const size_t at = (size_t)(cg * 16 + k) * RQ2_STRIDE;
+          const uint32_t st = w.st[at];
+          if (st & 0x7fffu) { w.st[at] = st | RQ2_ZEROED; w.cc[at] = rq2_cost_zero(w.qw[at] & 0x7fffffff, es); w.cs[at] = 0.0; }
+        }
+      }
+    }
+  }
+
+  // where to put the last significant position, or nothing coded at all
+  int best_end = 0;
+  {
+    double best_cost = RQ_ADD(uncoded, RQ_MUL(lambda, (double)j.cbf_bits[0]));
+    base = RQ_ADD(base, RQ_MUL(lambda, (double)j.cbf_bits[1]));
+    bool stop = !live;
+    for (int cg = RQ_WARP_MAX(last_cg); cg >= 0; cg--)
+    {
+      if (!RQ_WARP_ANY(!stop)) break;
+      bool act = !stop && cg <= last_cg;
+      if (act) { base = RQ_SUB(base, cg_cost[cg]); act = ((cg_mask >> RQ_LD(scan_cg + cg)) & 1) != 0; }
+      if (!RQ_WARP_ANY(act)) continue;
+      for (int k = 15; k >= 0; k--)
+      {
+        const int sp = cg * 16 + k;
+        if (!act || sp > last_pos) continue;
+        const size_t at = (size_t)sp * RQ2_STRIDE;
+        const int l = rq2_level(w.st[at]);
+        if (l)
+        {
+          const int pos = RQ_LD(scan + sp), y = pos >> log2, x = pos - (y << log2);
+          const double c_last = j.scan == 2 ? rq_last_cost(eb, lambda, ch, y, x) : rq_last_cost(eb, lambda, ch, x, y);
+          const double total = RQ_SUB(RQ_ADD(base, c_last), w.cs[at]);
+          if (total < best_cost) { best_end = sp + 1; best_cost = total; }
+          if (l > 1) { stop = true; act = false; continue; }
+          base = RQ_SUB(base, w.cc[at]);
+          base = RQ_ADD(base, rq2_cost_zero(w.qw[at] & 0x7fffffff, es));
+        }
+        else base = RQ_SUB(base, w.cs[at]);
+      }
+    }
+  }
+
+  // C: uiAbsSum (before sign-bit hiding, as the reference returns it)
+  int sum = 0;
+  {
+    const int top_end = RQ_WARP_MAX(best_end);
+    for (int sp = 0; sp < top_end; sp++)
+      if (sp < best_end) sum += rq2_level(w.st[(size_t)sp * RQ2_STRIDE]);
+  }
+
+  // D: sign-bit hiding group by group (TComTrQuant.cpp:2380-2517), then the signed levels of the group go out
+  const bool hide = (j.flags & HMGPU_RDOQ_SIGN_HIDE) && sum >= 2;
+  const int top_cg = (best_end - 1) >> 4;                          // (-1: nothing coded)
+  long long rd_factor = 0;
+  if (hide)
+  {
+    const double inv = (double)rq_inv_quant_scale(j.qp_rem);
+    const double f = (RQ_MUL(RQ_MUL(inv, inv), (double)(1 << (2 * j.qp_per))) / lambda) / 16.0 / (double)(1 << (2 * (j.bit_depth - 8)));
+    rd_factor = (long long)RQ_ADD(f, 0.5);
+  }
+  const int top_top_cg = RQ_WARP_MAX(top_cg);
+  for (int cg = 0; cg <= top_top_cg; cg++)
+  {
+    if (cg > top_cg) continue;
+    const uint16_t* s = scan + cg * 16;
+    const size_t at0 = (size_t)cg * 16 * RQ2_STRIDE;
+    const int in_end = best_end - cg * 16;                         // positions k < in_end of this group are coded
+    int chg_k = -1, chg = 0;
+    if (hide)
+    {
+      int first_nz = 16, last_nz = -1, gsum = 0;
+      for (int k = 0; k < 16; k++)
+      {
+        const int l = k < in_end ? rq2_level(w.st[at0 + (size_t)k * RQ2_STRIDE]) : 0;
+        if (l) { if (first_nz == 16) first_nz = k; last_nz = k; gsum += l; }
+      }
+      if (last_nz - first_nz >= 4)
+      {
+        const int sign = (w.qw[at0 + (size_t)first_nz * RQ2_STRIDE] < 0) ? 1 : 0;
+        if (sign != (gsum & 1))
+        {
+          const bool top = cg == top_cg;
+          long long min_cost = INT64_MAX;
+          for (int k = top ? last_nz : 15; k >= 0; k--)
+          {
+            const size_t at = at0 + (size_t)k * RQ2_STRIDE;
+            const uint32_t st = w.st[at];
+            const int qword = w.qw[at], l = rq2_level(st);
+            int d_u, r_up, r_down, sig_delta;
+            rq2_side(j, eb, st & ~RQ2_ZEROED, qword & 0x7fffffff, RQ_LD(s + k), log2, &d_u, &r_up, &r_down, &sig_delta);
+            long long cur;
+            int change;
+            if (l != 0)
+            {
+              const bool one = l == 1;
+              const long long up = rd_factor * (long long)(-d_u) + r_up;
+              long long down = rd_factor * (long long)d_u + r_down - (one ? sig_delta : 0);
+              if (top && last_nz == k && one) down -= 4 << 15;
+              if (up < down) { cur = up; change = 1; }
+              else { change = -1; cur = (k == first_nz && one) ? INT64_MAX : down; }
+            }
+            else
+            {
+              cur = rd_factor * (long long)(-rq_abs(d_u)) + (1 << 15) + r_up + sig_delta;
+              change = 1;
+              if (k < first_nz && ((qword < 0) ? 1 : 0) != sign) cur = INT64_MAX;
+            }
+            if (cur < min_cost) { min_cost = cur; chg = change; chg_k = k; }
+          }
+          if (chg_k >= 0)
+          {
+            const size_t at = at0 + (size_t)chg_k * RQ2_STRIDE;
+            if (rq2_level(w.st[at]) == RQ_MAX_LEVEL && w.qw[at] >= 0) chg = -1;
+          }
+        }
+      }
+    }
+    for (int k = 0; k < 16 && k < in_end; k++)
+    {
+      const size_t at = at0 + (size_t)k * RQ2_STRIDE;
+      int l = rq2_level(w.st[at]);
+      if (k == chg_k) l += chg;
+      if (l) level[RQ_LD(s + k)] = w.qw[at] < 0 ? -l : l;
+    }
+  }
+  return sum;
+}

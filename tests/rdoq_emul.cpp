@@ -36,3 +36,22 @@ extern "C" int rdoq_emul(const hmgpu_rdoq_job* job, const hmgpu_rdoq_bits* bits,
 }
 
 extern "C" void rdoq_emul_scan_table(uint16_t* tab) { rq_build_scan_table(tab); }
+
+// the one-thread-per-TU body (rq2_tu); ghost != 0: as if a neighbouring lane of the warp carried a TU that keeps every lockstep
+// loop running to its end, so the lane's predicates decide alone
+extern "C" int rdoq_emul_tu(const hmgpu_rdoq_job* job, const hmgpu_rdoq_bits* bits, const int32_t* coef, int32_t* level, int ghost)
+{
+  static uint16_t tab[RQ_SCAN_WORDS];
+  static bool built = false;
+  if (!built) { rq_build_scan_table(tab); built = true; }
+  const hmgpu_rdoq_job& j = *job;
+  const int n_coef = 1 << (2 * j.log2_size);
+  std::vector<double> store((size_t)n_coef * RQ2_BYTES_PER_COEF / 8);
+  memset(store.data(), 0xA5, store.size() * 8);
+  Rq2Work w = rq2_carve(store.data(), n_coef, 0);
+  memset(level, 0, sizeof(int32_t) * n_coef);                      // (the kernel's level buffer starts out as zeros)
+  rq_ghost_top = ghost ? n_coef - 1 : -1;
+  const int sum = rq2_tu(j, true, j.log2_size, bits, tab + rq_scan_base(j.scan, j.log2_size - 2), tab + rq_cg_base(j.scan, j.log2_size - 2), coef, level, w);
+  rq_ghost_top = -1;
+  return sum;
+}

@@ -46,9 +46,9 @@ def test_rdoq_matches_the_reference_encoders_calls():
     calls = rdoq_golden_calls()
     assert len(calls) >= 1000 and {c["log2"] for c in calls} == {2, 3, 4, 5}
     with hmgpu.Context(64, 64, 8, 1) as ctx:
-        n0 = ctx.launch_count()
+        n0 = ctx.launches
         jobs, bits, coef = check(ctx, calls, [c["level"] for c in calls], np.array([c["abs_sum"] for c in calls]))
-        assert ctx.launch_count() - n0 == 4                     # one launch per TU size
+        assert ctx.launches - n0 == 4                     # one launch per TU size
         assert len(bits) > 10
         # one TU at a time, and each size class alone (ragged batches: the last warp / lane group is partly empty)
         for n in (1, 3, 33):

@@ -29,6 +29,8 @@ def emul():
     L.rdoq_emul.restype = C.c_int
     L.rdoq_emul.argtypes = [C.c_void_p] * 4 + [C.c_int]
     L.rdoq_emul_scan_table.argtypes = [C.c_void_p]
+    L.rdoq_emul_tu.restype = C.c_int
+    L.rdoq_emul_tu.argtypes = [C.c_void_p] * 4 + [C.c_int]
     return L
 
 
@@ -38,6 +40,11 @@ def run_emul(L, job, bits, coef, lanes):
     job = np.ascontiguousarray(job)
     bits = np.ascontiguousarray(bits)
     s = L.rdoq_emul(job.ctypes.data, bits.ctypes.data, coef.ctypes.data, level.ctypes.data, lanes)
+    # the one-thread-per-TU body must say the same, alone in its warp and beside a longer neighbour
+    for ghost in (0, 1):
+        level2 = np.full_like(coef, 54321)
+        s2 = L.rdoq_emul_tu(job.ctypes.data, bits.ctypes.data, coef.ctypes.data, level2.ctypes.data, ghost)
+        assert s2 == s and np.array_equal(level2, level), ("thread-per-TU body differs from the lane-group body", ghost, s2, s)
     return level, s
 
 
