@@ -474,8 +474,12 @@ RQ_HD void rq_hide_signs(const hmgpu_rdoq_job& j, const uint16_t* scan, const in
 #if defined(__CUDA_ARCH__)
 #define RQ_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))
 #define RQ_WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#define RQ_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#define RQ_UNROLL _Pragma("unroll")
 #define RQ2_STRIDE 32
 #else
+#define RQ_PREFETCH(p) ((void)(p))
+#define RQ_UNROLL
 static int rq_ghost_top = -1;
 #define RQ_WARP_MAX(v) ((v) > rq_ghost_top ? (v) : rq_ghost_top)
 #define RQ_WARP_ANY(p) ((p) || rq_ghost_top >= 0)
@@ -550,7 +554,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
     const int qscale = rq_quant_scale(j.qp_rem);
     const long long cap = 0x7fffffffLL - (1LL << (qbits - 1));
 #if defined(__CUDA_ARCH__)
-#pragma unroll 4
+#pragma unroll 8
 #endif
     for (int sp = 0; sp < n_coef; sp++)
     {
@@ -570,6 +574,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
   unsigned long long cg_mask = 0;
   double cg_cost[64];
   double base = 0.0, uncoded = 0.0;
+  int sum_all = 0;                                                 // sum of the levels as they stand (zeroed groups taken out again)
   RqCoder lc;
   lc.ctx_set = set0 + ((ch == 0 && last_cg > 0) ? 2 : 0); lc.c1 = 1; lc.c2 = 0; lc.c1_idx = 0; lc.c2_idx = 0; lc.rice = rice0;
   int q_next = live ? w.qw[(size_t)(n_coef - 1) * RQ2_STRIDE] : 0;
@@ -586,7 +591,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
       pattern = n_cg > 1 ? right + 2 * below : 0;
     }
     double s_sig = 0.0, s_sig_first = 0.0, s_coded = 0.0, s_uncoded = 0.0;
-    int nz_above_first = 0, any = 0;
+    int nz_above_first = 0, any = 0, grp_sum = 0;
     for (int k = 15; k >= 0; k--)
     {
       const int sp = cg * 16 + k;
@@ -649,12 +654,14 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
       if (best)
       {
         any = 1;
+        grp_sum += best;
         s_coded = RQ_ADD(s_coded, RQ_SUB(c_best, c_sig_best));
         s_uncoded = RQ_ADD(s_uncoded, c_zero);
         if (k != 0) nz_above_first++;
       }
     }
     if (!in) continue;
+    sum_all += grp_sum;
     cg_cost[cg] = 0.0;
     if (any) cg_mask |= 1ULL << blk;
     if (cg == 0) { cg_mask |= 1ULL; continue; }                    // the flag of the DC group is inferred
@@ -681,6 +688,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
         cg_mask &= ~(1ULL << blk);
         base = zeroed;
         cg_cost[cg] = flag0;
+        sum_all -= grp_sum;
         for (int k = 15; k >= 0; k--)
         {
           const size_t at = (size_t)(cg * 16 + k) * RQ2_STRIDE;
@@ -691,45 +699,54 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
     }
   }
 
-  // where to put the last significant position, or nothing coded at all
-  int best_end = 0;
+  // where to put the last significant position, or nothing coded at all.  The walk goes down from the last position until the
+  // first level above 1; the decisions of a group are fetched at once (the loads do not depend on the running cost).
+  // uiAbsSum (before sign-bit hiding, as the reference returns it) = the levels as they stand minus those the walk passed before it
+  // found its best position: every one of them was a 1.
+  int best_end = 0, sum = 0;
   {
     double best_cost = RQ_ADD(uncoded, RQ_MUL(lambda, (double)j.cbf_bits[0]));
     base = RQ_ADD(base, RQ_MUL(lambda, (double)j.cbf_bits[1]));
     bool stop = !live;
+    int walked = 0, above_best = 0;
     for (int cg = RQ_WARP_MAX(last_cg); cg >= 0; cg--)
     {
       if (!RQ_WARP_ANY(!stop)) break;
       bool act = !stop && cg <= last_cg;
       if (act) { base = RQ_SUB(base, cg_cost[cg]); act = ((cg_mask >> RQ_LD(scan_cg + cg)) & 1) != 0; }
       if (!RQ_WARP_ANY(act)) continue;
+      const size_t at0 = (size_t)cg * 16 * RQ2_STRIDE;
+      uint32_t stv[16];
+      double csv[16];
+      RQ_UNROLL
+      for (int k = 0; k < 16; k++)
+        if (act) { stv[k] = w.st[at0 + (size_t)k * RQ2_STRIDE]; csv[k] = w.cs[at0 + (size_t)k * RQ2_STRIDE]; }
+        else { stv[k] = 0; csv[k] = 0.0; }
+      RQ_UNROLL
+      for (int k = 0; k < 16; k++)
+        if (rq2_level(stv[k])) { RQ_PREFETCH(&w.cc[at0 + (size_t)k * RQ2_STRIDE]); RQ_PREFETCH(&w.qw[at0 + (size_t)k * RQ2_STRIDE]); }
+      RQ_UNROLL
       for (int k = 15; k >= 0; k--)
       {
         const int sp = cg * 16 + k;
         if (!act || sp > last_pos) continue;
         const size_t at = (size_t)sp * RQ2_STRIDE;
-        const int l = rq2_level(w.st[at]);
+        const int l = rq2_level(stv[k]);
         if (l)
         {
           const int pos = RQ_LD(scan + sp), y = pos >> log2, x = pos - (y << log2);
           const double c_last = j.scan == 2 ? rq_last_cost(eb, lambda, ch, y, x) : rq_last_cost(eb, lambda, ch, x, y);
-          const double total = RQ_SUB(RQ_ADD(base, c_last), w.cs[at]);
-          if (total < best_cost) { best_end = sp + 1; best_cost = total; }
+          const double total = RQ_SUB(RQ_ADD(base, c_last), csv[k]);
+          if (total < best_cost) { best_end = sp + 1; best_cost = total; above_best = walked; }
           if (l > 1) { stop = true; act = false; continue; }
+          walked += l;
           base = RQ_SUB(base, w.cc[at]);
           base = RQ_ADD(base, rq2_cost_zero(w.qw[at] & 0x7fffffff, es));
         }
-        else base = RQ_SUB(base, w.cs[at]);
+        else base = RQ_SUB(base, csv[k]);
       }
     }
-  }
-
-  // C: uiAbsSum (before sign-bit hiding, as the reference returns it)
-  int sum = 0;
-  {
-    const int top_end = RQ_WARP_MAX(best_end);
-    for (int sp = 0; sp < top_end; sp++)
-      if (sp < best_end) sum += rq2_level(w.st[(size_t)sp * RQ2_STRIDE]);
+    if (best_end) sum = sum_all - above_best;
   }
 
   // D: sign-bit hiding group by group (TComTrQuant.cpp:2380-2517), then the signed levels of the group go out
@@ -749,62 +766,63 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
     const uint16_t* s = scan + cg * 16;
     const size_t at0 = (size_t)cg * 16 * RQ2_STRIDE;
     const int in_end = best_end - cg * 16;                         // positions k < in_end of this group are coded
+    int lv[16], qwv[16];
+    RQ_UNROLL
+    for (int k = 0; k < 16; k++) { lv[k] = rq2_level(w.st[at0 + (size_t)k * RQ2_STRIDE]); qwv[k] = w.qw[at0 + (size_t)k * RQ2_STRIDE]; }
+    if (cg < top_cg)                                               // the next group's lines, while this one is worked on
+    {
+      RQ_UNROLL
+      for (int k = 0; k < 16; k++) { RQ_PREFETCH(&w.st[at0 + (size_t)(16 + k) * RQ2_STRIDE]); RQ_PREFETCH(&w.qw[at0 + (size_t)(16 + k) * RQ2_STRIDE]); }
+    }
+    RQ_UNROLL
+    for (int k = 0; k < 16; k++) if (k >= in_end) lv[k] = 0;
     int chg_k = -1, chg = 0;
     if (hide)
     {
-      int first_nz = 16, last_nz = -1, gsum = 0;
+      int first_nz = 16, last_nz = -1, gsum = 0, sign = 0;
+      RQ_UNROLL
       for (int k = 0; k < 16; k++)
+        if (lv[k]) { if (first_nz == 16) { first_nz = k; sign = qwv[k] < 0 ? 1 : 0; } last_nz = k; gsum += lv[k]; }
+      if (last_nz - first_nz >= 4 && sign != (gsum & 1))
       {
-        const int l = k < in_end ? rq2_level(w.st[at0 + (size_t)k * RQ2_STRIDE]) : 0;
-        if (l) { if (first_nz == 16) first_nz = k; last_nz = k; gsum += l; }
-      }
-      if (last_nz - first_nz >= 4)
-      {
-        const int sign = (w.qw[at0 + (size_t)first_nz * RQ2_STRIDE] < 0) ? 1 : 0;
-        if (sign != (gsum & 1))
+        const bool top = cg == top_cg;
+        long long min_cost = INT64_MAX;
+        bool chg_at_max = false;
+        for (int k = top ? last_nz : 15; k >= 0; k--)             // (the group's lines are in L1 now)
         {
-          const bool top = cg == top_cg;
-          long long min_cost = INT64_MAX;
-          for (int k = top ? last_nz : 15; k >= 0; k--)
+          const size_t at = at0 + (size_t)k * RQ2_STRIDE;
+          const uint32_t st = w.st[at];
+          const int qword = w.qw[at], l = k < in_end ? rq2_level(st) : 0;
+          int d_u, r_up, r_down, sig_delta;
+          rq2_side(j, eb, st & ~RQ2_ZEROED, qword & 0x7fffffff, RQ_LD(s + k), log2, &d_u, &r_up, &r_down, &sig_delta);
+          long long cur;
+          int change;
+          if (l != 0)
           {
-            const size_t at = at0 + (size_t)k * RQ2_STRIDE;
-            const uint32_t st = w.st[at];
-            const int qword = w.qw[at], l = rq2_level(st);
-            int d_u, r_up, r_down, sig_delta;
-            rq2_side(j, eb, st & ~RQ2_ZEROED, qword & 0x7fffffff, RQ_LD(s + k), log2, &d_u, &r_up, &r_down, &sig_delta);
-            long long cur;
-            int change;
-            if (l != 0)
-            {
-              const bool one = l == 1;
-              const long long up = rd_factor * (long long)(-d_u) + r_up;
-              long long down = rd_factor * (long long)d_u + r_down - (one ? sig_delta : 0);
-              if (top && last_nz == k && one) down -= 4 << 15;
-              if (up < down) { cur = up; change = 1; }
-              else { change = -1; cur = (k == first_nz && one) ? INT64_MAX : down; }
-            }
-            else
-            {
-              cur = rd_factor * (long long)(-rq_abs(d_u)) + (1 << 15) + r_up + sig_delta;
-              change = 1;
-              if (k < first_nz && ((qword < 0) ? 1 : 0) != sign) cur = INT64_MAX;
-            }
-            if (cur < min_cost) { min_cost = cur; chg = change; chg_k = k; }
+            const bool one = l == 1;
+            const long long up = rd_factor * (long long)(-d_u) + r_up;
+            long long down = rd_factor * (long long)d_u + r_down - (one ? sig_delta : 0);
+            if (top && last_nz == k && one) down -= 4 << 15;
+            if (up < down) { cur = up; change = 1; }
+            else { change = -1; cur = (k == first_nz && one) ? INT64_MAX : down; }
           }
-          if (chg_k >= 0)
+          else
           {
-            const size_t at = at0 + (size_t)chg_k * RQ2_STRIDE;
-            if (rq2_level(w.st[at]) == RQ_MAX_LEVEL && w.qw[at] >= 0) chg = -1;
+            cur = rd_factor * (long long)(-rq_abs(d_u)) + (1 << 15) + r_up + sig_delta;
+            change = 1;
+            if (k < first_nz && ((qword < 0) ? 1 : 0) != sign) cur = INT64_MAX;
           }
+          if (cur < min_cost) { min_cost = cur; chg = change; chg_k = k; chg_at_max = l == RQ_MAX_LEVEL && qword >= 0; }
         }
+        if (chg_at_max) chg = -1;
       }
     }
-    for (int k = 0; k < 16 && k < in_end; k++)
+    RQ_UNROLL
+    for (int k = 0; k < 16; k++)
     {
-      const size_t at = at0 + (size_t)k * RQ2_STRIDE;
-      int l = rq2_level(w.st[at]);
+      int l = lv[k];
       if (k == chg_k) l += chg;
-      if (l) level[RQ_LD(s + k)] = w.qw[at] < 0 ? -l : l;
+      if (l) level[RQ_LD(s + k)] = qwv[k] < 0 ? -l : l;
     }
   }
   return sum;

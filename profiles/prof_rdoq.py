@@ -31,27 +31,39 @@ jobs["coef_offset"] = (jobs["coef_offset"].astype(np.int64) + np.repeat(np.arang
 sizes = {lg: int((jobs["log2_size"] == lg).sum()) for lg in (2, 3, 4, 5)}
 print("batch: %d TUs (%s), %d coefficients, %d sets of bit estimates" % (len(jobs), sizes, coef.size, len(bits)))
 
+modes = [int(m) for m in os.environ.get("RDOQ_MODES", "1,0").split(",")]
 with hmgpu.Context(64, 64, 8, 1) as ctx:
-    level, abs_sum = ctx.rdoq(jobs, bits, coef)                         # warm-up + check
-    assert np.array_equal(level.reshape(rep, n1), np.tile(want, (rep, 1))), "levels differ from the reference encoder's"
-    ctx.profile_enable(True)
-    ctx.profile_read(True)
-    t0 = time.perf_counter()
-    for _ in range(reps_timed):
-        ctx.rdoq(jobs, bits, coef)
-    wall = (time.perf_counter() - t0) / reps_timed
-    st = ctx.profile_read(True)
-    dev_ms = st["quant"][0] / reps_timed
-    print("device: %.3f ms per batch (%d launches)  -> %.2f M TU/s, %.1f M coef/s" % (dev_ms, st["quant"][1] // reps_timed, len(jobs) / dev_ms / 1e3, coef.size / dev_ms / 1e3))
-    print("C-ABI call with host buffers: %.3f ms per batch -> %.2f M TU/s, %.1f M coef/s" % (wall * 1e3, len(jobs) / wall / 1e6, coef.size / wall / 1e6))
-    # per size class alone
-    for lg in (5, 4, 3, 2):
-        sel = jobs["log2_size"] == lg
+    for mode in modes:
+        ctx.set_option("rdoq_tu", mode)
+        print("--- %s" % ("one thread per TU (rdoq_tu_kernel, one launch)" if mode else "one lane group per TU (rdoq_kernel<log2, lanes>, one launch per size)"))
+        level, abs_sum = ctx.rdoq(jobs, bits, coef)                         # warm-up + check
+        assert np.array_equal(level.reshape(rep, n1), np.tile(want, (rep, 1))), "levels differ from the reference encoder's"
+        ctx.profile_enable(True)
         ctx.profile_read(True)
-        ctx.rdoq(jobs[sel], bits, coef)
-        ms = ctx.profile_read(True)["quant"][0]
-        print("  %2dx%-2d: %6d TUs  %.3f ms  (%.3f us per TU across the machine)" % (1 << lg, 1 << lg, int(sel.sum()), ms, ms * 1e3 / max(int(sel.sum()), 1)))
+        t0 = time.perf_counter()
+        for _ in range(reps_timed):
+            ctx.rdoq(jobs, bits, coef)
+        wall = (time.perf_counter() - t0) / reps_timed
+        st = ctx.profile_read(True)
+        dev_ms = st["quant"][0] / reps_timed
+        print("device: %.3f ms per batch (%d launches)  -> %.2f M TU/s, %.1f M coef/s" % (dev_ms, st["quant"][1] // reps_timed, len(jobs) / dev_ms / 1e3, coef.size / dev_ms / 1e3))
+        print("C-ABI call with host buffers: %.3f ms per batch -> %.2f M TU/s, %.1f M coef/s" % (wall * 1e3, len(jobs) / wall / 1e6, coef.size / wall / 1e6))
+        # each size class alone, and the un-repeated calls (a small batch: the latency of the longest chain)
+        for lg in (5, 4, 3, 2):
+            sel = jobs["log2_size"] == lg
+            ctx.rdoq(jobs[sel], bits, coef)
+            ctx.profile_read(True)
+            ctx.rdoq(jobs[sel], bits, coef)
+            ms = ctx.profile_read(True)["quant"][0]
+            print("  %2dx%-2d: %6d TUs  %.3f ms  (%.3f us per TU across the machine)" % (1 << lg, 1 << lg, int(sel.sum()), ms, ms * 1e3 / max(int(sel.sum()), 1)))
+        ctx.rdoq(jobs1, bits, coef1)
+        ctx.profile_read(True)
+        ctx.rdoq(jobs1, bits, coef1)
+        print("  the %d calls once: %.3f ms" % (len(jobs1), ctx.profile_read(True)["quant"][0]))
+        ctx.profile_enable(False)
 
+if os.environ.get("RDOQ_NO_CPU"):
+    sys.exit(0)
 try:
     from oracle import binding as B
     prepared = [(rdoqdump.to_tu_and_bits(c, B.RDOQ_TU, B.RDOQ_BITS), c["coef"]) for c in calls]

@@ -42,13 +42,19 @@ def check(ctx, calls, want_level, want_sum):
     return jobs, bits, coef
 
 
-def test_rdoq_matches_the_reference_encoders_calls():
+# both mappings of the kernel: one thread per TU (32 TUs of a size per warp, one launch; the default) and one lane group per TU
+MAPPINGS = pytest.mark.parametrize("per_thread", [1, 0])
+
+
+@MAPPINGS
+def test_rdoq_matches_the_reference_encoders_calls(per_thread):
     calls = rdoq_golden_calls()
     assert len(calls) >= 1000 and {c["log2"] for c in calls} == {2, 3, 4, 5}
     with hmgpu.Context(64, 64, 8, 1) as ctx:
+        ctx.set_option("rdoq_tu", per_thread)
         n0 = ctx.launches
         jobs, bits, coef = check(ctx, calls, [c["level"] for c in calls], np.array([c["abs_sum"] for c in calls]))
-        assert ctx.launches - n0 == 4                     # one launch per TU size
+        assert ctx.launches - n0 == (1 if per_thread else 4)          # one launch for all sizes / one per TU size
         assert len(bits) > 10
         # one TU at a time, and each size class alone (ragged batches: the last warp / lane group is partly empty)
         for n in (1, 3, 33):
@@ -64,7 +70,8 @@ def test_rdoq_matches_the_reference_encoders_calls():
                 ctx.rdoq(broken, bits, coef)
 
 
-def test_rdoq_matches_oracle_on_random_tus():
+@MAPPINGS
+def test_rdoq_matches_oracle_on_random_tus(per_thread):
     rng = np.random.default_rng(99)
     calls = random_tus(rng, 3000, rdoq_golden_calls())
     want_level, want_sum = [], []
@@ -73,10 +80,15 @@ def test_rdoq_matches_oracle_on_random_tus():
         lv, s = B.rdoq(tu, obits, c["coef"])
         want_level.append(lv); want_sum.append(s)
     with hmgpu.Context(64, 64, 8, 1) as ctx:
+        ctx.set_option("rdoq_tu", per_thread)
         check(ctx, calls, want_level, np.array(want_sum))
+        # the same TUs in another order: other neighbours in every warp, the same levels
+        order = rng.permutation(len(calls))
+        check(ctx, [calls[i] for i in order], [want_level[i] for i in order], np.array(want_sum)[order])
 
 
-def test_rdoq_all_zero_and_uncovered_coefficients():
+@MAPPINGS
+def test_rdoq_all_zero_and_uncovered_coefficients(per_thread):
     """TUs that quantise to nothing return zero levels and uiAbsSum 0; coefficients no job covers come back as zeros"""
     calls = [dict(c) for c in rdoq_golden_calls()[:40]]
     for c in calls:
@@ -84,5 +96,6 @@ def test_rdoq_all_zero_and_uncovered_coefficients():
     jobs, bits, coef = batch_of(calls)
     coef = np.concatenate([coef, np.full(100, 7777, np.int32)])
     with hmgpu.Context(64, 64, 8, 1) as ctx:
+        ctx.set_option("rdoq_tu", per_thread)
         level, abs_sum = ctx.rdoq(jobs, bits, coef)
     assert not level.any() and not abs_sum.any()
