@@ -513,6 +513,60 @@ RQ_HD int rq2_first_ctx(const hmgpu_rdoq_job& j, int log2)
   return log2 == 2 ? 0 : log2 == 3 ? 9 + ((j.channel == 0 && j.scan != 0) ? 6 : 0) : (j.channel == 0 ? 21 : 12);
 }
 
+// ---- the rates without branches: the lanes of a warp carry different TUs, so every branch of the per-coefficient step that two
+// lanes take differently is walked twice.  The bit estimates of the level coder's contexts are loaded once per coefficient and the
+// rate of a level is arithmetic on them (same sums as rq_level_rate, the escape length in closed form).
+#if defined(__CUDA_ARCH__)
+#define RQ_CLZ(v) __clz((int)(v))
+#else
+#define RQ_CLZ(v) __builtin_clz((unsigned)(v))
+#endif
+struct RqRateCtx { int go0, go1, la0, la1, base_lvl, rice; bool g1, g2; };
+RQ_HD RqRateCtx rq_rate_ctx(const hmgpu_rdoq_bits* eb, const RqCoder& c)
+{
+  RqRateCtx r;
+  const int ctx_one = 4 * c.ctx_set + c.c1;
+  r.g1 = c.c1_idx < 8; r.g2 = r.g1 && c.c2_idx < 1;
+  r.base_lvl = r.g1 ? (r.g2 ? 3 : 2) : 1; r.rice = c.rice;
+  r.go0 = RQ_LD(&eb->greater_one[ctx_one][0]); r.go1 = RQ_LD(&eb->greater_one[ctx_one][1]);
+  const int ctx_abs = r.g2 ? c.ctx_set + c.c2 : 0;               // (only read while no greater-2 flag was coded in the group: c2 = 0)
+  r.la0 = RQ_LD(&eb->level_abs[ctx_abs][0]); r.la1 = RQ_LD(&eb->level_abs[ctx_abs][1]);
+  return r;
+}
+RQ_HD int rq_rate_alu(int lvl, const RqRateCtx& r)
+{
+  const unsigned sym = (unsigned)(lvl - r.base_lvl), thr = 3u << r.rice;
+  const int prefix = (int)((sym >> r.rice) + 1 + r.rice);
+  const int len = 31 - RQ_CLZ((sym - thr + (1u << r.rice)) | 1u);  // Exp-Golomb of order rice: 2^len <= sym - thr + 2^rice
+  const int escape = 3 + len + 1 - r.rice + len;
+  const int at_base = ((sym < thr ? prefix : escape) << 15) + (r.g1 ? r.go1 : 0) + (r.g2 ? r.la1 : 0);
+  const int below = lvl == 1 ? r.go0 : r.go1 + r.la0;
+  return lvl > 0 ? RQ_SIGN_BITS + (lvl >= r.base_lvl ? at_base : below) : 0;
+}
+
+// getSigCtxInc with the group's part taken out of the per-coefficient step: grp_off = table + first_ctx (+ 3 in a luma group other
+// than the DC group); the count of the neighbouring groups' pattern comes from a table of 64 two-bit entries [pattern][ys][xs]
+constexpr unsigned long long rq_cnt_lut(int half)
+{
+  unsigned long long v = 0;
+  for (int i = 0; i < 32; i++)
+  {
+    const int idx = half * 32 + i, p = idx >> 4, ys = (idx >> 2) & 3, xs = idx & 3;
+    const int c = p == 0 ? (xs + ys >= 3 ? 0 : (xs + ys >= 1 ? 1 : 2)) : p == 1 ? (ys >= 2 ? 0 : (ys >= 1 ? 1 : 2)) : p == 2 ? (xs >= 2 ? 0 : (xs >= 1 ? 1 : 2)) : 2;
+    v |= (unsigned long long)c << (2 * i);
+  }
+  return v;
+}
+constexpr unsigned long long RQ_CNT_LUT0 = rq_cnt_lut(0), RQ_CNT_LUT1 = rq_cnt_lut(1);
+RQ_HD int rq_sig_ctx_lut(int pattern, int table, int first_ctx, int grp_off, int pos, int log2)
+{
+  const int idx = pattern * 16 + ((pos >> log2) & 3) * 4 + (pos & 3);
+  const int cnt = (int)(((idx & 32 ? RQ_CNT_LUT1 : RQ_CNT_LUT0) >> (2 * (idx & 31))) & 3);
+  const int in4 = table + first_ctx + (int)((0x8877886654325410ULL >> (4 * (pos & 15))) & 15);      // ctxIndMap4x4
+  return pos == 0 ? table : (log2 == 2 ? in4 : grp_off + cnt);
+}
+RQ_HD int rq_sig_grp_off(int table, int first_ctx, int ch, int blk) { return table + first_ctx + ((ch == 0 && blk != 0) ? 3 : 0); }
+
 // what the reference noted down beside a decision for sign-bit hiding: deltaU, rateIncUp, rateIncDown, sigRateDelta
 RQ_HD void rq2_side(const hmgpu_rdoq_job& j, const hmgpu_rdoq_bits* eb, uint32_t st, int q, int pos, int log2, int* d_u, int* r_up, int* r_down, int* sig_delta)
 {
@@ -520,21 +574,15 @@ RQ_HD void rq2_side(const hmgpu_rdoq_job& j, const hmgpu_rdoq_bits* eb, uint32_t
   RqCoder c;
   c.ctx_set = (st >> 16) & 7; c.c1 = (st >> 19) & 3; c.c2 = (st >> 21) & 3;
   c.c1_idx = ((st >> 23) & 1) ? 0 : 8; c.c2_idx = ((st >> 24) & 1) ? 0 : 1; c.rice = (st >> 25) & 7;
-  const int ctx_one = 4 * c.ctx_set + c.c1, ctx_abs = c.ctx_set + c.c2;
+  const RqRateCtx r = rq_rate_ctx(eb, c);
   *d_u = (q - (int)((unsigned)best << j.qbits)) >> (j.qbits - 8);
-  if (best > 0)
-  {
-    const int now = rq_level_rate(eb, best, ctx_one, ctx_abs, c);
-    *r_up = rq_level_rate(eb, best + 1, ctx_one, ctx_abs, c) - now;
-    *r_down = rq_level_rate(eb, best - 1, ctx_one, ctx_abs, c) - now;
-  }
-  else { *r_up = RQ_LD(&eb->greater_one[ctx_one][0]); *r_down = 0; }
-  if ((st >> 30) & 1) *sig_delta = 0;
-  else
-  {
-    const int ctx_sig = rq_sig_ctx((st >> 28) & 3, rq2_first_ctx(j, log2), pos, log2, j.channel);
-    *sig_delta = RQ_LD(&eb->sig[ctx_sig][1]) - RQ_LD(&eb->sig[ctx_sig][0]);
-  }
+  const int now = rq_rate_alu(best, r);
+  *r_up = best > 0 ? rq_rate_alu(best + 1, r) - now : r.go0;
+  *r_down = best > 0 ? rq_rate_alu(best - 1, r) - now : 0;
+  const int table = j.channel ? 28 : 0, first_ctx = rq2_first_ctx(j, log2);
+  const int not_dc = (pos >> (log2 + 2)) | ((pos & ((1 << log2) - 1)) >> 2);     // the group is not the DC group
+  const int ctx_sig = rq_sig_ctx_lut((st >> 28) & 3, table, first_ctx, rq_sig_grp_off(table, first_ctx, j.channel, not_dc), pos, log2);
+  *sig_delta = ((st >> 30) & 1) ? 0 : RQ_LD(&eb->sig[ctx_sig][1]) - RQ_LD(&eb->sig[ctx_sig][0]);
 }
 
 // The whole of xRateDistOptQuant for this lane's TU.  has_tu: the lane carries a TU (the last warp of a size class may not be
@@ -570,7 +618,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
 
   // B: level decisions and group zero-out, from the top of the scan down
   const int last_cg = last_pos >> 4;                               // (-1 for a lane that is not live)
-  const int rice0 = j.go_rice_init, set0 = ch ? 4 : 0, first_ctx = rq2_first_ctx(j, log2);
+  const int rice0 = j.go_rice_init, set0 = ch ? 4 : 0, first_ctx = rq2_first_ctx(j, log2), table = ch ? 28 : 0;
   unsigned long long cg_mask = 0;
   double cg_cost[64];
   double base = 0.0, uncoded = 0.0;
@@ -581,7 +629,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
   for (int cg = n_cg - 1; cg >= 0; cg--)
   {
     const bool in = live && cg <= last_cg;
-    int blk = 0, right = 0, below = 0, pattern = 0;
+    int blk = 0, right = 0, below = 0, pattern = 0, grp_off = 0;
     if (in)
     {
       blk = RQ_LD(scan_cg + cg);
@@ -589,6 +637,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
       right = gx < g - 1 ? (int)((cg_mask >> (blk + 1)) & 1) : 0;
       below = gy < g - 1 ? (int)((cg_mask >> (blk + g)) & 1) : 0;
       pattern = n_cg > 1 ? right + 2 * below : 0;
+      grp_off = rq_sig_grp_off(table, first_ctx, ch, blk);
     }
     double s_sig = 0.0, s_sig_first = 0.0, s_coded = 0.0, s_uncoded = 0.0;
     int nz_above_first = 0, any = 0, grp_sum = 0;
@@ -604,34 +653,21 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
       const int pos = RQ_LD(scan + sp);
       int max_lvl = (q + half) >> qbits;
       if (max_lvl > RQ_MAX_LEVEL) max_lvl = RQ_MAX_LEVEL;
-      const int ctx_one = 4 * lc.ctx_set + lc.c1, ctx_abs = lc.ctx_set + lc.c2;
       const bool is_last = sp == last_pos;
-      int sig0 = 0, sig1 = 0;
-      if (!is_last)
-      {
-        const int ctx_sig = rq_sig_ctx(pattern, first_ctx, pos, log2, ch);
-        sig0 = RQ_LD(&eb->sig[ctx_sig][0]); sig1 = RQ_LD(&eb->sig[ctx_sig][1]);
-      }
+      // the bit estimates this coefficient can meet (independent loads), then both candidate levels side by side
+      const RqRateCtx r = rq_rate_ctx(eb, lc);
+      const int ctx_sig = rq_sig_ctx_lut(pattern, table, first_ctx, grp_off, pos, log2);
+      const int sig0 = is_last ? 0 : RQ_LD(&eb->sig[ctx_sig][0]), sig1 = is_last ? 0 : RQ_LD(&eb->sig[ctx_sig][1]);
+      const double c_sig_zero = RQ_MUL(lambda, (double)sig0), c_sig_one = RQ_MUL(lambda, (double)sig1);    // (0.0 at the last position)
+      const double e1 = (double)(q - (int)((unsigned)max_lvl << qbits)), e2 = (double)(q - (int)((unsigned)(max_lvl - 1) << qbits));
+      const double c1 = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e1, e1), es), RQ_MUL(lambda, (double)rq_rate_alu(max_lvl, r))), c_sig_one);
+      const double c2 = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e2, e2), es), RQ_MUL(lambda, (double)rq_rate_alu(max_lvl - 1, r))), c_sig_one);
+      // xGetCodedLevel: level 0 competes only below 3 and not at the last position; then max, then max - 1 (strict <)
       int best = 0;
       double c_best = RQ_DBL_MAX, c_sig_best = 0.0;
-      if (!is_last && max_lvl < 3)
-      {
-        c_sig_best = RQ_MUL(lambda, (double)sig0);
-        c_best = RQ_ADD(c_zero, c_sig_best);
-      }
-      if (max_lvl > 0)
-      {
-        const double c_sig_one = is_last ? 0.0 : RQ_MUL(lambda, (double)sig1);
-        const double e1 = (double)(q - (int)((unsigned)max_lvl << qbits));
-        double c = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e1, e1), es), RQ_MUL(lambda, (double)rq_level_rate(eb, max_lvl, ctx_one, ctx_abs, lc))), c_sig_one);
-        if (c < c_best) { best = max_lvl; c_best = c; c_sig_best = c_sig_one; }
-        if (max_lvl > 1)
-        {
-          const double e2 = (double)(q - (int)((unsigned)(max_lvl - 1) << qbits));
-          c = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e2, e2), es), RQ_MUL(lambda, (double)rq_level_rate(eb, max_lvl - 1, ctx_one, ctx_abs, lc))), c_sig_one);
-          if (c < c_best) { best = max_lvl - 1; c_best = c; c_sig_best = c_sig_one; }
-        }
-      }
+      if (!is_last && max_lvl < 3) { c_sig_best = c_sig_zero; c_best = RQ_ADD(c_zero, c_sig_zero); }
+      if (max_lvl > 0 && c1 < c_best) { best = max_lvl; c_best = c1; c_sig_best = c_sig_one; }
+      if (max_lvl > 1 && c2 < c_best) { best = max_lvl - 1; c_best = c2; c_sig_best = c_sig_one; }
       w.cc[(size_t)sp * RQ2_STRIDE] = c_best;
       w.cs[(size_t)sp * RQ2_STRIDE] = c_sig_best;
       w.st[(size_t)sp * RQ2_STRIDE] = rq2_pack(best, lc, pattern, is_last);
