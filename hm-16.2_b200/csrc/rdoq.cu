@@ -111,6 +111,7 @@ rdoq_tu_kernel(const hmgpu_rdoq_job* __restrict__ jobs, const int* __restrict__ 
                const uint16_t* __restrict__ scan_tab, const int32_t* __restrict__ coef_all, int32_t* __restrict__ level_all, int32_t* __restrict__ abs_sum,
                unsigned char* __restrict__ work)
 {
+  __shared__ int32_t s_bits[RDOQ_TU_WARPS][RQ2_BITS_WORDS * 32];    // 24 KB per warp
   const int lane = threadIdx.x & 31, slot = blockIdx.x * RDOQ_TU_WARPS + (threadIdx.x >> 5);
   for (int wi = slot; wi < plan.first_warp[4]; wi += gridDim.x * RDOQ_TU_WARPS)
   {
@@ -124,7 +125,20 @@ rdoq_tu_kernel(const hmgpu_rdoq_job* __restrict__ jobs, const int* __restrict__ 
     const uint16_t* scan = scan_tab + rq_scan_base(j.scan, log2 - 2);
     const uint16_t* scan_cg = scan_tab + rq_cg_base(j.scan, log2 - 2);
     Rq2Work w = rq2_carve(work + (size_t)slot * plan.slot_bytes, 1 << (2 * log2), lane);
-    const int sum = rq2_tu(j, has_tu, log2, bits + j.bits_index, scan, scan_cg, coef_all + j.coef_offset, level_all + j.coef_offset, w);
+    // the lane's set of bit estimates into shared memory, [word][lane]
+    int32_t* my_bits = s_bits[threadIdx.x >> 5] + lane;
+    {
+      const int4* src = (const int4*)(bits + j.bits_index);
+#pragma unroll 8
+      for (int i = 0; i < RQ2_BITS_WORDS / 4; i++)
+      {
+        const int4 v = __ldg(src + i);
+        my_bits[(4 * i) * 32] = v.x; my_bits[(4 * i + 1) * 32] = v.y; my_bits[(4 * i + 2) * 32] = v.z; my_bits[(4 * i + 3) * 32] = v.w;
+      }
+    }
+    __syncwarp();
+    Rq2Bits eb; eb.p = my_bits;
+    const int sum = rq2_tu(j, has_tu, log2, eb, scan, scan_cg, coef_all + j.coef_offset, level_all + j.coef_offset, w);
     if (has_tu) abs_sum[ji] = sum;
     __syncwarp();
   }

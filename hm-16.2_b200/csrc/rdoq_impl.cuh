@@ -22,6 +22,7 @@
 // contracted into a fused multiply-add).
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 #include "../../include/hmgpu.h"
 
 #if defined(__CUDACC__)
@@ -488,6 +489,31 @@ static int rq_ghost_top = -1;
 #define RQ2_BYTES_PER_COEF 24
 #define RQ2_ZEROED (1u << 15)
 
+// The bit estimates as this half reads them: the 192 words of hmgpu_rdoq_bits, word i of the lane's set at p[i * RQ2_EB_STRIDE].
+// On the device the warp keeps the 32 sets of its TUs in shared memory as [word][lane]: whatever word a lane asks for, it sits in
+// the lane's own bank.
+#if defined(__CUDA_ARCH__)
+#define RQ2_EB_STRIDE 32
+#else
+#define RQ2_EB_STRIDE 1
+#endif
+struct Rq2Bits { const int32_t* p; };
+#define RQ2_EB(eb, i) ((eb).p[(i) * RQ2_EB_STRIDE])
+enum { RQ2_SIG_GROUP = 0, RQ2_SIG = 4, RQ2_LAST_X = 92, RQ2_LAST_Y = 112, RQ2_GREATER_ONE = 132, RQ2_LEVEL_ABS = 180, RQ2_BITS_WORDS = 192 };
+static_assert(sizeof(hmgpu_rdoq_bits) == 4 * RQ2_BITS_WORDS && offsetof(hmgpu_rdoq_bits, sig) == 4 * RQ2_SIG && offsetof(hmgpu_rdoq_bits, last_x) == 4 * RQ2_LAST_X
+              && offsetof(hmgpu_rdoq_bits, last_y) == 4 * RQ2_LAST_Y && offsetof(hmgpu_rdoq_bits, greater_one) == 4 * RQ2_GREATER_ONE
+              && offsetof(hmgpu_rdoq_bits, level_abs) == 4 * RQ2_LEVEL_ABS, "layout of hmgpu_rdoq_bits");
+
+// lambda x bits of (x, y) as the last significant position (xGetRateLast; rq_last_cost on this half's bit estimates)
+RQ_HD double rq2_last_cost(Rq2Bits eb, double lambda, int ch, int x, int y)
+{
+  const int cx = rq_last_group(x), cy = rq_last_group(y);
+  double bits = (double)(RQ2_EB(eb, RQ2_LAST_X + 10 * ch + cx) + RQ2_EB(eb, RQ2_LAST_Y + 10 * ch + cy));
+  if (cx > 3) bits = RQ_ADD(bits, 32768.0 * ((cx - 2) >> 1));
+  if (cy > 3) bits = RQ_ADD(bits, 32768.0 * ((cy - 2) >> 1));
+  return RQ_MUL(lambda, bits);
+}
+
 struct Rq2Work { int32_t* qw; uint32_t* st; double* cc; double* cs; };      // this lane's element sp: [sp * RQ2_STRIDE]
 // slot = the workspace of one warp (32 TUs of n_coef coefficients), lane = this thread's place in it
 RQ_HD Rq2Work rq2_carve(void* slot, int n_coef, int lane)
@@ -522,15 +548,15 @@ RQ_HD int rq2_first_ctx(const hmgpu_rdoq_job& j, int log2)
 #define RQ_CLZ(v) __builtin_clz((unsigned)(v))
 #endif
 struct RqRateCtx { int go0, go1, la0, la1, base_lvl, rice; bool g1, g2; };
-RQ_HD RqRateCtx rq_rate_ctx(const hmgpu_rdoq_bits* eb, const RqCoder& c)
+RQ_HD RqRateCtx rq_rate_ctx(Rq2Bits eb, const RqCoder& c)
 {
   RqRateCtx r;
   const int ctx_one = 4 * c.ctx_set + c.c1;
   r.g1 = c.c1_idx < 8; r.g2 = r.g1 && c.c2_idx < 1;
   r.base_lvl = r.g1 ? (r.g2 ? 3 : 2) : 1; r.rice = c.rice;
-  r.go0 = RQ_LD(&eb->greater_one[ctx_one][0]); r.go1 = RQ_LD(&eb->greater_one[ctx_one][1]);
+  r.go0 = RQ2_EB(eb, RQ2_GREATER_ONE + 2 * ctx_one); r.go1 = RQ2_EB(eb, RQ2_GREATER_ONE + 2 * ctx_one + 1);
   const int ctx_abs = r.g2 ? c.ctx_set + c.c2 : 0;               // (only read while no greater-2 flag was coded in the group: c2 = 0)
-  r.la0 = RQ_LD(&eb->level_abs[ctx_abs][0]); r.la1 = RQ_LD(&eb->level_abs[ctx_abs][1]);
+  r.la0 = RQ2_EB(eb, RQ2_LEVEL_ABS + 2 * ctx_abs); r.la1 = RQ2_EB(eb, RQ2_LEVEL_ABS + 2 * ctx_abs + 1);
   return r;
 }
 RQ_HD int rq_rate_alu(int lvl, const RqRateCtx& r)
@@ -568,7 +594,7 @@ RQ_HD int rq_sig_ctx_lut(int pattern, int table, int first_ctx, int grp_off, int
 RQ_HD int rq_sig_grp_off(int table, int first_ctx, int ch, int blk) { return table + first_ctx + ((ch == 0 && blk != 0) ? 3 : 0); }
 
 // what the reference noted down beside a decision for sign-bit hiding: deltaU, rateIncUp, rateIncDown, sigRateDelta
-RQ_HD void rq2_side(const hmgpu_rdoq_job& j, const hmgpu_rdoq_bits* eb, uint32_t st, int q, int pos, int log2, int* d_u, int* r_up, int* r_down, int* sig_delta)
+RQ_HD void rq2_side(const hmgpu_rdoq_job& j, Rq2Bits eb, uint32_t st, int q, int pos, int log2, int* d_u, int* r_up, int* r_down, int* sig_delta)
 {
   const int best = (int)(st & 0x7fffu);
   RqCoder c;
@@ -582,13 +608,13 @@ RQ_HD void rq2_side(const hmgpu_rdoq_job& j, const hmgpu_rdoq_bits* eb, uint32_t
   const int table = j.channel ? 28 : 0, first_ctx = rq2_first_ctx(j, log2);
   const int not_dc = (pos >> (log2 + 2)) | ((pos & ((1 << log2) - 1)) >> 2);     // the group is not the DC group
   const int ctx_sig = rq_sig_ctx_lut((st >> 28) & 3, table, first_ctx, rq_sig_grp_off(table, first_ctx, j.channel, not_dc), pos, log2);
-  *sig_delta = ((st >> 30) & 1) ? 0 : RQ_LD(&eb->sig[ctx_sig][1]) - RQ_LD(&eb->sig[ctx_sig][0]);
+  *sig_delta = ((st >> 30) & 1) ? 0 : RQ2_EB(eb, RQ2_SIG + 2 * ctx_sig + 1) - RQ2_EB(eb, RQ2_SIG + 2 * ctx_sig);
 }
 
 // The whole of xRateDistOptQuant for this lane's TU.  has_tu: the lane carries a TU (the last warp of a size class may not be
 // full); log2: the size class, the same for every lane of the warp.  Levels that come out zero are NOT stored: the caller's level
 // buffer starts out as zeros.  Returns uiAbsSum.
-RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdoq_bits* eb, const uint16_t* scan, const uint16_t* scan_cg,
+RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, Rq2Bits eb, const uint16_t* scan, const uint16_t* scan_cg,
                  const int32_t* coef, int32_t* level, Rq2Work w)
 {
   const int n_coef = 1 << (2 * log2), g = 1 << (log2 - 2), n_cg = g * g;
@@ -602,7 +628,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
     const int qscale = rq_quant_scale(j.qp_rem);
     const long long cap = 0x7fffffffLL - (1LL << (qbits - 1));
 #if defined(__CUDA_ARCH__)
-#pragma unroll 8
+#pragma unroll 16
 #endif
     for (int sp = 0; sp < n_coef; sp++)
     {
@@ -647,6 +673,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
       if (!live) continue;
       const int q = q_next & 0x7fffffff;
       if (sp > 0) q_next = w.qw[(size_t)(sp - 1) * RQ2_STRIDE];     // (one position ahead: the load is off the critical path)
+      if (sp >= 12) RQ_PREFETCH(&w.qw[(size_t)(sp - 12) * RQ2_STRIDE]);
       const double c_zero = rq2_cost_zero(q, es);
       uncoded = RQ_ADD(uncoded, c_zero);
       if (sp > last_pos) { base = uncoded; continue; }             // above the last position only the cost of level 0 adds up
@@ -657,7 +684,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
       // the bit estimates this coefficient can meet (independent loads), then both candidate levels side by side
       const RqRateCtx r = rq_rate_ctx(eb, lc);
       const int ctx_sig = rq_sig_ctx_lut(pattern, table, first_ctx, grp_off, pos, log2);
-      const int sig0 = is_last ? 0 : RQ_LD(&eb->sig[ctx_sig][0]), sig1 = is_last ? 0 : RQ_LD(&eb->sig[ctx_sig][1]);
+      const int sig0 = is_last ? 0 : RQ2_EB(eb, RQ2_SIG + 2 * ctx_sig), sig1 = is_last ? 0 : RQ2_EB(eb, RQ2_SIG + 2 * ctx_sig + 1);
       const double c_sig_zero = RQ_MUL(lambda, (double)sig0), c_sig_one = RQ_MUL(lambda, (double)sig1);    // (0.0 at the last position)
       const double e1 = (double)(q - (int)((unsigned)max_lvl << qbits)), e2 = (double)(q - (int)((unsigned)(max_lvl - 1) << qbits));
       const double c1 = RQ_ADD(RQ_ADD(RQ_MUL(RQ_MUL(e1, e1), es), RQ_MUL(lambda, (double)rq_rate_alu(max_lvl, r))), c_sig_one);
@@ -704,15 +731,15 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
     const int ctx_grp = (right | below) != 0;
     if (!any)
     {
-      const double flag0 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][0]));
+      const double flag0 = RQ_MUL(lambda, (double)RQ2_EB(eb, RQ2_SIG_GROUP + 2 * ctx_grp));
       base = RQ_ADD(base, RQ_SUB(flag0, s_sig));
       cg_cost[cg] = flag0;
     }
     else if (cg < last_cg)                                         // (the group of the last position is settled with that position)
     {
       if (nz_above_first == 0) { base = RQ_SUB(base, s_sig_first); s_sig = RQ_SUB(s_sig, s_sig_first); }
-      const double flag0 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][0]));
-      const double flag1 = RQ_MUL(lambda, (double)RQ_LD(&eb->sig_group[ctx_grp][1]));
+      const double flag0 = RQ_MUL(lambda, (double)RQ2_EB(eb, RQ2_SIG_GROUP + 2 * ctx_grp));
+      const double flag1 = RQ_MUL(lambda, (double)RQ2_EB(eb, RQ2_SIG_GROUP + 2 * ctx_grp + 1));
       double zeroed = RQ_ADD(base, flag0);
       base = RQ_ADD(base, flag1);
       cg_cost[cg] = flag1;
@@ -771,7 +798,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, const hmgpu_rdo
         if (l)
         {
           const int pos = RQ_LD(scan + sp), y = pos >> log2, x = pos - (y << log2);
-          const double c_last = j.scan == 2 ? rq_last_cost(eb, lambda, ch, y, x) : rq_last_cost(eb, lambda, ch, x, y);
+          const double c_last = j.scan == 2 ? rq2_last_cost(eb, lambda, ch, y, x) : rq2_last_cost(eb, lambda, ch, x, y);
           const double total = RQ_SUB(RQ_ADD(base, c_last), csv[k]);
           if (total < best_cost) { best_end = sp + 1; best_cost = total; above_best = walked; }
           if (l > 1) { stop = true; act = false; continue; }

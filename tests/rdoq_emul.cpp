@@ -51,7 +51,8 @@ extern "C" int rdoq_emul_tu(const hmgpu_rdoq_job* job, const hmgpu_rdoq_bits* bi
   Rq2Work w = rq2_carve(store.data(), n_coef, 0);
   memset(level, 0, sizeof(int32_t) * n_coef);                      // (the kernel's level buffer starts out as zeros)
   rq_ghost_top = ghost ? n_coef - 1 : -1;
-  const int sum = rq2_tu(j, true, j.log2_size, bits, tab + rq_scan_base(j.scan, j.log2_size - 2), tab + rq_cg_base(j.scan, j.log2_size - 2), coef, level, w);
+  Rq2Bits eb; eb.p = (const int32_t*)bits;
+  const int sum = rq2_tu(j, true, j.log2_size, eb, tab + rq_scan_base(j.scan, j.log2_size - 2), tab + rq_cg_base(j.scan, j.log2_size - 2), coef, level, w);
   rq_ghost_top = -1;
   return sum;
 }
