@@ -308,6 +308,8 @@ def run_ours(args, rank, world, local_rank):
             out["encode_segments"] = seg
         if world == 1 and not args.no_full_search:
             out["full_search"] = full_search_leg(local_rank, max(2, args.steps // 2), sad4_peak, int_peak)
+        if world == 1 and not args.no_rdoq:
+            out["rdoq"] = rdoq_leg(local_rank, max(2, args.steps))
         if world == 1 and not args.no_encode:
             out["real_stream"] = real_stream_leg(local_rank)
             out["encode"] = encode_runs(local_rank, args.full)
@@ -367,6 +369,69 @@ def full_search_leg(local_rank, steps, sad4_peak, int_peak=None):
                          # the same work as the kernel issues it: 4 pixel-candidates per VABSDIFF4.U8.ACC lane-op (ALU pipe only)
                          "packed": {"achieved": achieved, "peak": sad4_peak, "unit": "G VABSDIFF4 lane-op/s", "frac": achieved / sad4_peak,
                                     "peak_source": "hmgpu_microbench(1) measured in this run"}}}
+
+
+def rdoq_leg(local_rank, steps, rep=64):
+    """SURVEY 8 f1: rate-distortion optimised quantisation (TComTrQuant::xRateDistOptQuant) of a batch of TUs through hmgpu_rdoq.
+    The batch is the reference encoder's own calls (tests/golden/rdoq_golden.npz: 1067 TUs of every size, luma + chroma, 686 coder
+    states) `rep` times over; the levels are compared with the ones the reference returned before anything is timed.  Device time =
+    the stage timers around the launch (CUDA events on the context's stream); e2e = the blocking C-ABI call with page-locked host
+    buffers, copies inside.  cpu_baseline: the oracle's restatement (oracle/hm_rdoq.c, pinned to the same calls) on one host core."""
+    import hmgpu
+    import rdoq_batch
+    jobs, bits, coef, want, want_sum = rdoq_batch.golden_batch(rep)
+    n_coef = int(coef.size)
+    with hmgpu.Context(64, 64, 8, 1, device=local_rank) as ctx:
+        h_coef, h_level = ctx.host_array(coef.shape, np.int32), ctx.host_array(coef.shape, np.int32)
+        h_coef[:] = coef
+        for _ in range(2):
+            level, abs_sum = ctx.rdoq(jobs, bits, h_coef, out=h_level)
+        identical = bool(np.array_equal(level, want) and np.array_equal(abs_sum, want_sum))
+        ctx.profile_enable(True)
+        ctx.profile_read(True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.rdoq(jobs, bits, h_coef, out=h_level)
+        wall = (time.perf_counter() - t0) / steps
+        ms, launches = ctx.profile_read(True)["quant"]
+        ctx.profile_enable(False)
+    ms /= steps
+    out = {"workload": "the reference encoder's %d xRateDistOptQuant calls x %d: %d TUs (4x4 %d, 8x8 %d, 16x16 %d, 32x32 %d), %d coefficients, %d sets of bit estimates"
+                       % (len(jobs) // rep, rep, len(jobs), *[int((jobs["log2_size"] == lg).sum()) for lg in (2, 3, 4, 5)], n_coef, len(bits)),
+           "levels_identical_to_reference": identical, "kernel": "rdoq_tu_kernel (rdoq.cu): one thread per TU, one launch", "launches_per_batch": launches // steps,
+           "ms_per_batch": ms, "mtu_per_s": len(jobs) / ms / 1e3, "mcoef_per_s": n_coef / ms / 1e3,
+           "e2e": {"ms_per_batch": wall * 1e3, "mcoef_per_s": n_coef / wall / 1e6, "h2d_bytes": int(coef.nbytes + jobs.nbytes + bits.nbytes),
+                   "d2h_bytes": int(coef.nbytes + 4 * len(jobs)), "timing": "wall clock around the blocking C-ABI call, page-locked host buffers"},
+           # 4 bytes in + 4 bytes out per coefficient are compulsory; what bounds the kernel is the chain of a TU (one level
+           # decision after the other: the level coder's state and the running cost pass from coefficient to coefficient)
+           "roofline": {"bound": "latency", "hbm": {"achieved": 8.0 * n_coef / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_batch": 8 * n_coef},
+                        "ns_per_chain_step": ms * 1e6 / 1024.0,
+                        "note": "the batch cannot finish before its longest chain: 1024 dependent steps of a 32x32 TU; "
+                                "throughput grows with the batch until every scheduler holds several warps (DESIGN.md, RDOQ)"}}
+    try:
+        from oracle import binding as B
+        tus = np.zeros(len(jobs) // rep, B.RDOQ_TU)
+        for f in ("log2_size", "channel", "scan", "qbits", "qp_per", "qp_rem", "go_rice_init", "cbf_bits", "bit_depth", "err_scale", "lambda"):
+            tus[f] = jobs[f][:len(tus)]
+        tus["sign_hide"] = jobs["flags"][:len(tus)]
+        obits = np.zeros(len(bits), B.RDOQ_BITS)
+        for f in obits.dtype.names:
+            obits[f] = bits[f]
+        n1 = n_coef // rep
+        t0, loops, bad = time.perf_counter(), 0, 0
+        while time.perf_counter() - t0 < 3.0:
+            for i in range(len(tus)):
+                a = int(jobs["coef_offset"][i])
+                k = int(jobs["bits_index"][i])
+                lv, sm = B.rdoq(tus[i:i + 1], obits[k:k + 1], coef[a:a + (1 << (2 * int(tus["log2_size"][i])))])
+                bad += int(sm != want_sum[i])
+            loops += 1
+        cpu = (time.perf_counter() - t0) / loops
+        out["cpu_baseline"] = {"value": n1 / cpu / 1e6, "unit": "Mcoef/s", "cores": 1, "kind": "port", "mismatches": bad,
+                               "sample": "the %d calls once per pass, %d passes, oracle/hm_rdoq.c through ctypes" % (len(tus), loops)}
+    except Exception as e:                                          # (the oracle is the checker: its timing is a reported extra)
+        out["cpu_baseline"] = {"unavailable": repr(e)}
+    return out
 
 
 def real_stream_leg(local_rank, frames=3):
@@ -678,6 +743,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the whole-encoder CPU vs GPUME runs")
     ap.add_argument("--no-full-search", action="store_true", help="skip the full-search (BASELINE configs[0]) leg")
+    ap.add_argument("--no-rdoq", action="store_true", help="skip the RDOQ (SURVEY 8 f1) leg")
     ap.add_argument("--full", action="store_true", help="encode legs at BASELINE size (cfg 2: 32 frames at QP 27/32/37; cfg 4: 32-frame "
                                                         "1080p segments) -- tens of minutes; logs of such runs are under profiles/")
     args = ap.parse_args()

@@ -5,6 +5,7 @@
   hmgpu.py     ctypes binding (tests, bench)
   worklist.py  HM-shaped ME job lists (CTU quadtree x partitions x references)
   synth.py     deterministic synthetic 4:2:0 video
+  rdoq_batch.py  batches of TUs for hmgpu_rdoq out of the reference encoder's dumped calls
   host/        the C++ host side that plugs into HM behind the GPUME cfg switch
 
 The directory name is not a Python identifier; import the modules with this directory on
@@ -20,5 +21,6 @@ if _here not in sys.path:
 import hmgpu  # noqa: E402
 import synth  # noqa: E402
 import worklist  # noqa: E402
+import rdoq_batch  # noqa: E402
 
-__all__ = ["hmgpu", "synth", "worklist"]
+__all__ = ["hmgpu", "synth", "worklist", "rdoq_batch"]

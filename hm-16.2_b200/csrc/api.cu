@@ -1939,22 +1939,31 @@ int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmg
   if ((rc = hmgpu_reserve_pinned(ctx, in_bytes + out_bytes))) return rc;
   if ((rc = hmgpu_reserve_stage(ctx, in_bytes + out_bytes))) return rc;
   char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
-  memcpy(hp, coef, sizeof(int32_t) * (size_t)n_coef);
+  // page-locked caller buffers (hmgpu_host_alloc) are copied directly; pageable ones go through the pinned staging buffer
+  const bool coef_pinned = is_pinned(coef), level_pinned = is_pinned(level);
+  if (coef_pinned) HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, coef, sizeof(int32_t) * (size_t)n_coef, cudaMemcpyHostToDevice, ctx->stream));
+  else memcpy(hp, coef, sizeof(int32_t) * (size_t)n_coef);
   memcpy(hp + b_coef, jobs, sizeof(hmgpu_rdoq_job) * (size_t)n_jobs);
   memcpy(hp + b_coef + b_jobs, bits, sizeof(hmgpu_rdoq_bits) * (size_t)n_bits);
   memcpy(hp + b_coef + b_jobs + b_bits, s_scan, sizeof s_scan);
   int* list = (int*)(hp + b_coef + b_jobs + b_bits + b_scan);
   int at[4] = { 0, n_class[0], n_class[0] + n_class[1], n_class[0] + n_class[1] + n_class[2] };
   for (int i = 0; i < n_jobs; i++) list[at[jobs[i].log2_size - 2]++] = i;
-  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (coef_pinned) HMGPU_CUDA(ctx, cudaMemcpyAsync(dp + b_coef, hp + b_coef, in_bytes - b_coef, cudaMemcpyHostToDevice, ctx->stream));
+  else HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   // coefficients no job covers come back as zero levels
   HMGPU_CUDA(ctx, cudaMemsetAsync(dp + in_bytes, 0, out_bytes, ctx->stream));
   if ((rc = hmgpu_launch_rdoq(ctx, (const hmgpu_rdoq_job*)(dp + b_coef), (const int*)(dp + b_coef + b_jobs + b_bits + b_scan), n_class,
                               (const hmgpu_rdoq_bits*)(dp + b_coef + b_jobs), (const uint16_t*)(dp + b_coef + b_jobs + b_bits),
                               (const int32_t*)dp, (int32_t*)(dp + in_bytes), (int32_t*)(dp + in_bytes + b_coef)))) return rc;
-  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (level_pinned)
+  {
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(level, dp + in_bytes, sizeof(int32_t) * (size_t)n_coef, cudaMemcpyDeviceToHost, ctx->stream));
+    HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + in_bytes + b_coef, dp + in_bytes + b_coef, b_list, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  else HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(level, hp + in_bytes, sizeof(int32_t) * (size_t)n_coef);
+  if (!level_pinned) memcpy(level, hp + in_bytes, sizeof(int32_t) * (size_t)n_coef);
   memcpy(abs_sum, hp + in_bytes + b_coef, sizeof(int32_t) * (size_t)n_jobs);
   return HMGPU_OK;
 }

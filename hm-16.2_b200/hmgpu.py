@@ -418,12 +418,14 @@ class Context:
                                        level.ctypes.data, delta.ctypes.data, abs_sum.ctypes.data))
         return level, delta, abs_sum
 
-    def rdoq(self, jobs, bits, coef):
-        """rate-distortion optimised quantisation of every TU of `jobs` (hmgpu_rdoq): -> (levels laid out like coef, uiAbsSum per TU)"""
+    def rdoq(self, jobs, bits, coef, out=None):
+        """rate-distortion optimised quantisation of every TU of `jobs` (hmgpu_rdoq): -> (levels laid out like coef, uiAbsSum per TU).
+        coef / out from host_array() (page-locked) are copied without the staging pass"""
         jobs = np.ascontiguousarray(jobs, RDOQ_JOB).ravel()
         bits = np.ascontiguousarray(bits, RDOQ_BITS).ravel()
         coef = np.ascontiguousarray(coef, np.int32).ravel()
-        level = np.zeros_like(coef)
+        level = np.zeros_like(coef) if out is None else out
+        assert level.dtype == np.int32 and level.size == coef.size and level.flags.c_contiguous
         abs_sum = np.zeros(len(jobs), np.int32)
         self._check(self.L.hmgpu_rdoq(self.h, jobs.ctypes.data, len(jobs), bits.ctypes.data, len(bits), coef.ctypes.data, coef.size,
                                       level.ctypes.data, abs_sum.ctypes.data))
