@@ -487,7 +487,6 @@ static int rq_ghost_top = -1;
 #define RQ2_STRIDE 1
 #endif
 #define RQ2_BYTES_PER_COEF 24
-#define RQ2_ZEROED (1u << 15)
 
 // The bit estimates as this half reads them: the 192 words of hmgpu_rdoq_bits, word i of the lane's set at p[i * RQ2_EB_STRIDE].
 // On the device the warp keeps the 32 sets of its TUs in shared memory as [word][lane]: whatever word a lane asks for, it sits in
@@ -525,14 +524,14 @@ RQ_HD Rq2Work rq2_carve(void* slot, int n_coef, int lane)
   return w;
 }
 
-// st: bits 0..14 level, 15 zeroed afterwards (group zero-out), 16..18 context set, 19..20 c1, 21..22 c2, 23 greater-1 flags left,
+// st: bits 0..14 level (as decided: a group zeroed afterwards is known by its bit in cg_mask), 16..18 context set, 19..20 c1, 21..22 c2, 23 greater-1 flags left,
 // 24 greater-2 flag left, 25..27 Rice parameter, 28..29 pattern of the group, 30 the last position
 RQ_HD uint32_t rq2_pack(int best, const RqCoder& c, int pattern, bool is_last)
 {
   return (uint32_t)best | ((uint32_t)c.ctx_set << 16) | ((uint32_t)c.c1 << 19) | ((uint32_t)c.c2 << 21) | ((uint32_t)(c.c1_idx < 8) << 23)
        | ((uint32_t)(c.c2_idx < 1) << 24) | ((uint32_t)c.rice << 25) | ((uint32_t)pattern << 28) | ((uint32_t)is_last << 30);
 }
-RQ_HD int rq2_level(uint32_t st) { return (st & RQ2_ZEROED) ? 0 : (int)(st & 0x7fffu); }
+RQ_HD int rq2_level(uint32_t st) { return (int)(st & 0x7fffu); }
 RQ_HD double rq2_cost_zero(int q, double es) { const double e0 = (double)q; return RQ_MUL(RQ_MUL(e0, e0), es); }
 RQ_HD int rq2_first_ctx(const hmgpu_rdoq_job& j, int log2)
 {
@@ -751,13 +750,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, Rq2Bits eb, con
         cg_mask &= ~(1ULL << blk);
         base = zeroed;
         cg_cost[cg] = flag0;
-        sum_all -= grp_sum;
-        for (int k = 15; k >= 0; k--)
-        {
-          const size_t at = (size_t)(cg * 16 + k) * RQ2_STRIDE;
-          const uint32_t st = w.st[at];
-          if (st & 0x7fffu) { w.st[at] = st | RQ2_ZEROED; w.cc[at] = rq2_cost_zero(w.qw[at] & 0x7fffffff, es); w.cs[at] = 0.0; }
-        }
+        sum_all -= grp_sum;                                        // (nothing reads the decisions of a group that is not in cg_mask)
       }
     }
   }
@@ -825,7 +818,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, Rq2Bits eb, con
   const int top_top_cg = RQ_WARP_MAX(top_cg);
   for (int cg = 0; cg <= top_top_cg; cg++)
   {
-    if (cg > top_cg) continue;
+    if (cg > top_cg || !((cg_mask >> RQ_LD(scan_cg + cg)) & 1)) continue;        // zeroed or empty groups: every level is zero
     const uint16_t* s = scan + cg * 16;
     const size_t at0 = (size_t)cg * 16 * RQ2_STRIDE;
     const int in_end = best_end - cg * 16;                         // positions k < in_end of this group are coded
@@ -857,7 +850,7 @@ RQ_HD int rq2_tu(const hmgpu_rdoq_job& j, bool has_tu, int log2, Rq2Bits eb, con
           const uint32_t st = w.st[at];
           const int qword = w.qw[at], l = k < in_end ? rq2_level(st) : 0;
           int d_u, r_up, r_down, sig_delta;
-          rq2_side(j, eb, st & ~RQ2_ZEROED, qword & 0x7fffffff, RQ_LD(s + k), log2, &d_u, &r_up, &r_down, &sig_delta);
+          rq2_side(j, eb, st, qword & 0x7fffffff, RQ_LD(s + k), log2, &d_u, &r_up, &r_down, &sig_delta);
           long long cur;
           int change;
           if (l != 0)
