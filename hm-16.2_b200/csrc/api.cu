@@ -1905,14 +1905,8 @@ int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_p
 }
 
 // ---- rate-distortion optimised quantisation (rdoq.cu) ----------------------------------------------------------------------
-int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmgpu_rdoq_bits* bits, int n_bits,
-               const int32_t* coef, int n_coef, int32_t* level, int32_t* abs_sum)
+static int rdoq_check_jobs(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, int n_bits, long long n_coef, int n_class[4])
 {
-  if (!ctx) return HMGPU_E_INVALID;
-  if (n_jobs == 0) return HMGPU_OK;
-  if (!jobs || !bits || !coef || !level || !abs_sum || n_jobs < 0 || n_bits <= 0 || n_coef < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
-  HMGPU_NOT_REMOTE(ctx, "hmgpu_rdoq");
-  int n_class[4] = { 0, 0, 0, 0 };
   for (int i = 0; i < n_jobs; i++)
   {
     const hmgpu_rdoq_job& j = jobs[i];
@@ -1925,13 +1919,30 @@ int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmg
     if ((unsigned long long)j.coef_offset + (1ull << (2 * j.log2_size)) > (unsigned long long)n_coef) return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: coefficients outside coef", i);
     n_class[j.log2_size - 2]++;
   }
-  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  return HMGPU_OK;
+}
+static const uint16_t* rdoq_scan_host()
+{
   static uint16_t s_scan[4336];
   static bool s_scan_done = false;                       // (written with the same values by whoever comes first)
   if (!s_scan_done) { hmgpu_rdoq_scan_table(s_scan); s_scan_done = true; }
+  return s_scan;
+}
+
+int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmgpu_rdoq_bits* bits, int n_bits,
+               const int32_t* coef, int n_coef, int32_t* level, int32_t* abs_sum)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_jobs == 0) return HMGPU_OK;
+  if (!jobs || !bits || !coef || !level || !abs_sum || n_jobs < 0 || n_bits <= 0 || n_coef < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_rdoq");
+  int n_class[4] = { 0, 0, 0, 0 };
+  { const int rcv = rdoq_check_jobs(ctx, jobs, n_jobs, n_bits, n_coef, n_class); if (rcv) return rcv; }
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint16_t* s_scan = rdoq_scan_host();
   // staging: [coef | jobs | bits | scan table | index list] in, [level | abs_sum] out
   const size_t b_coef = round_up(sizeof(int32_t) * (size_t)n_coef, 256), b_jobs = round_up(sizeof(hmgpu_rdoq_job) * (size_t)n_jobs, 256);
-  const size_t b_bits = round_up(sizeof(hmgpu_rdoq_bits) * (size_t)n_bits, 256), b_scan = round_up(sizeof s_scan, 256);
+  const size_t b_bits = round_up(sizeof(hmgpu_rdoq_bits) * (size_t)n_bits, 256), b_scan = round_up(sizeof(uint16_t) * 4336, 256);
   const size_t b_list = round_up(sizeof(int) * (size_t)n_jobs, 256);
   const size_t in_bytes = b_coef + b_jobs + b_bits + b_scan + b_list, out_bytes = b_coef + b_list;
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1945,7 +1956,7 @@ int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmg
   else memcpy(hp, coef, sizeof(int32_t) * (size_t)n_coef);
   memcpy(hp + b_coef, jobs, sizeof(hmgpu_rdoq_job) * (size_t)n_jobs);
   memcpy(hp + b_coef + b_jobs, bits, sizeof(hmgpu_rdoq_bits) * (size_t)n_bits);
-  memcpy(hp + b_coef + b_jobs + b_bits, s_scan, sizeof s_scan);
+  memcpy(hp + b_coef + b_jobs + b_bits, s_scan, sizeof(uint16_t) * 4336);
   int* list = (int*)(hp + b_coef + b_jobs + b_bits + b_scan);
   int at[4] = { 0, n_class[0], n_class[0] + n_class[1], n_class[0] + n_class[1] + n_class[2] };
   for (int i = 0; i < n_jobs; i++) list[at[jobs[i].log2_size - 2]++] = i;
@@ -1965,6 +1976,101 @@ int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmg
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (!level_pinned) memcpy(level, hp + in_bytes, sizeof(int32_t) * (size_t)n_coef);
   memcpy(abs_sum, hp + in_bytes + b_coef, sizeof(int32_t) * (size_t)n_jobs);
+  return HMGPU_OK;
+}
+
+// ---- dequantiser (transform.cu) and the residual-costing loop of a batch of TUs without leaving the device -----------------------
+int hmgpu_dequant(hmgpu_ctx* ctx, const int32_t* level, int n_tus, int n, int qp_per, int qp_rem, int32_t* coef)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_tus == 0) return HMGPU_OK;
+  if (!level || !coef || n_tus < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  if (qp_rem < 0 || qp_rem > 5 || qp_per < 0 || qp_per > 12) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad qp per/rem");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_dequant");
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t elems = (size_t)n_tus * n * n, b0 = round_up(sizeof(int32_t) * elems, 256);
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, 2 * b0))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, 2 * b0))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, level, sizeof(int32_t) * elems);
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, b0, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = hmgpu_launch_dequant(ctx, (const int32_t*)dp, n_tus, n, NULL, qp_per, qp_rem, (int32_t*)(dp + b0)))) return rc;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(hp + b0, dp + b0, sizeof(int32_t) * elems, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(coef, hp + b0, sizeof(int32_t) * elems);
+  return HMGPU_OK;
+}
+
+int hmgpu_residual_tus(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, int use_dst, const hmgpu_rdoq_job* jobs,
+                       const hmgpu_rdoq_bits* bits, int n_bits, int32_t* level, int32_t* abs_sum, int16_t* rec_resi, uint32_t* dist)
+{
+  if (!ctx) return HMGPU_E_INVALID;
+  if (n_tus == 0) return HMGPU_OK;
+  if (!resi || !jobs || !bits || !level || !abs_sum || !rec_resi || !dist || n_tus < 0 || n_bits <= 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
+  if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
+  if (use_dst && n != 4) return hmgpu_fail(ctx, HMGPU_E_INVALID, "the DST exists for 4x4 TUs only");
+  HMGPU_NOT_REMOTE(ctx, "hmgpu_residual_tus");
+  const int nn = n * n, log2n = n == 4 ? 2 : n == 8 ? 3 : n == 16 ? 4 : 5;
+  const size_t elems = (size_t)n_tus * nn;
+  if (elems > 0x7fffffffu) return hmgpu_fail(ctx, HMGPU_E_INVALID, "%d TUs of %d x %d: more than 2^31 coefficients in one call", n_tus, n, n);
+  int n_class[4] = { 0, 0, 0, 0 };
+  { const int rcv = rdoq_check_jobs(ctx, jobs, n_tus, n_bits, (long long)elems, n_class); if (rcv) return rcv; }
+  for (int i = 0; i < n_tus; i++)
+    if (jobs[i].log2_size != log2n || jobs[i].coef_offset != (uint32_t)((size_t)i * nn) || jobs[i].bit_depth != ctx->bit_depth)
+      return hmgpu_fail(ctx, HMGPU_E_INVALID, "job %d: log2_size / coef_offset / bit_depth do not describe TU %d of %d x %d in a %d-bit context", i, i, n, n, ctx->bit_depth);
+  HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint16_t* s_scan = rdoq_scan_host();
+  // staging, in:  [resi | jobs | bits | scan table | index list | distortion items]
+  //          work:[coefficients | dequantised coefficients]     out: [levels | abs_sum | reconstructed residual + one zero block | distortions]
+  const size_t b_resi = round_up(sizeof(int16_t) * elems, 256), b_jobs = round_up(sizeof(hmgpu_rdoq_job) * (size_t)n_tus, 256);
+  const size_t b_bits = round_up(sizeof(hmgpu_rdoq_bits) * (size_t)n_bits, 256), b_scan = round_up(sizeof(uint16_t) * 4336, 256);
+  const size_t b_list = round_up(sizeof(int) * (size_t)n_tus, 256), b_items = round_up(sizeof(hmgpu_dist_item) * 2 * (size_t)n_tus, 256);
+  const size_t b_c32 = round_up(sizeof(int32_t) * elems, 256), b_rec = round_up(sizeof(int16_t) * (elems + nn), 256), b_dist = round_up(sizeof(uint32_t) * 2 * (size_t)n_tus, 256);
+  const size_t in_bytes = b_resi + b_jobs + b_bits + b_scan + b_list + b_items, work_bytes = 2 * b_c32, out_bytes = b_c32 + b_list + b_rec + b_dist;
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
+  if ((rc = hmgpu_reserve_pinned(ctx, in_bytes + out_bytes))) return rc;
+  if ((rc = hmgpu_reserve_stage(ctx, in_bytes + work_bytes + out_bytes))) return rc;
+  char* hp = (char*)ctx->h_pin; char* dp = (char*)ctx->d_stage;
+  memcpy(hp, resi, sizeof(int16_t) * elems);
+  size_t at = b_resi;
+  memcpy(hp + at, jobs, sizeof(hmgpu_rdoq_job) * (size_t)n_tus); const size_t o_jobs = at; at += b_jobs;
+  memcpy(hp + at, bits, sizeof(hmgpu_rdoq_bits) * (size_t)n_bits); const size_t o_bits = at; at += b_bits;
+  memcpy(hp + at, s_scan, sizeof(uint16_t) * 4336); const size_t o_scan = at; at += b_scan;
+  int* list = (int*)(hp + at); const size_t o_list = at; at += b_list;
+  for (int i = 0; i < n_tus; i++) list[i] = i;
+  hmgpu_dist_item* items = (hmgpu_dist_item*)(hp + at); const size_t o_items = at; at += b_items;
+  for (int i = 0; i < n_tus; i++)
+  {
+    // the residual against its reconstruction, and against nothing coded (a block of zeros behind the reconstructions)
+    hmgpu_dist_item a = { (uint32_t)((size_t)i * nn), (uint32_t)((size_t)i * nn), n, n, (uint8_t)n, (uint8_t)n, HMGPU_DF_SSE, 0 };
+    hmgpu_dist_item z = { (uint32_t)((size_t)i * nn), (uint32_t)elems, n, n, (uint8_t)n, (uint8_t)n, HMGPU_DF_SSE, 0 };
+    items[2 * i] = a; items[2 * i + 1] = z;
+  }
+  const size_t o_coef = in_bytes, o_deq = in_bytes + b_c32, o_level = in_bytes + work_bytes, o_sum = o_level + b_c32, o_rec = o_sum + b_list, o_dist = o_rec + b_rec;
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  HMGPU_CUDA(ctx, cudaMemsetAsync(dp + o_level, 0, b_c32 + b_list, ctx->stream));          // (the RDOQ kernel stores the non-zero levels only)
+  HMGPU_CUDA(ctx, cudaMemsetAsync(dp + o_rec + sizeof(int16_t) * elems, 0, sizeof(int16_t) * nn, ctx->stream));
+  const int16_t* d_resi = (const int16_t*)dp;
+  // transformNxN: xT, then the RDOQ branch of xQuant
+  if ((rc = hmgpu_launch_fwd_transform(ctx, d_resi, n_tus, n, use_dst, (int32_t*)(dp + o_coef)))) return rc;
+  if ((rc = hmgpu_launch_rdoq(ctx, (const hmgpu_rdoq_job*)(dp + o_jobs), (const int*)(dp + o_list), n_class, (const hmgpu_rdoq_bits*)(dp + o_bits),
+                              (const uint16_t*)(dp + o_scan), (const int32_t*)(dp + o_coef), (int32_t*)(dp + o_level), (int32_t*)(dp + o_sum)))) return rc;
+  // invTransformNxN: xDeQuant, then xIT (all-zero TUs come out as zero residuals, as the reference leaves them)
+  if ((rc = hmgpu_launch_dequant(ctx, (const int32_t*)(dp + o_level), n_tus, n, (const hmgpu_rdoq_job*)(dp + o_jobs), 0, 0, (int32_t*)(dp + o_deq)))) return rc;
+  if ((rc = hmgpu_launch_inv_transform(ctx, (const int32_t*)(dp + o_deq), n_tus, n, use_dst, (int16_t*)(dp + o_rec)))) return rc;
+  // the two distortions xEstimateResidualQT compares
+  if ((rc = hmgpu_launch_dist(ctx, d_resi, (const int16_t*)(dp + o_rec), (const hmgpu_dist_item*)(dp + o_items), 2 * n_tus, (uint32_t*)(dp + o_dist)))) return rc;
+  char* ho = hp + in_bytes;                                         // the pinned copy of the out region
+  HMGPU_CUDA(ctx, cudaMemcpyAsync(ho, dp + o_level, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(level, ho, sizeof(int32_t) * elems);
+  memcpy(abs_sum, ho + (o_sum - o_level), sizeof(int32_t) * (size_t)n_tus);
+  memcpy(rec_resi, ho + (o_rec - o_level), sizeof(int16_t) * elems);
+  memcpy(dist, ho + (o_dist - o_level), sizeof(uint32_t) * 2 * (size_t)n_tus);
   return HMGPU_OK;
 }
 

@@ -254,6 +254,7 @@ int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n,
                        int is_intra, int32_t* d_level, int32_t* d_delta, uint32_t* d_abs_sum);
 int hmgpu_launch_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* d_jobs, const int* d_list, const int n_class[4], const hmgpu_rdoq_bits* d_bits,
                       const uint16_t* d_scan, const int32_t* d_coef, int32_t* d_level, int32_t* d_abs_sum);
+int hmgpu_launch_dequant(hmgpu_ctx* ctx, const int32_t* d_level, int n_tus, int n, const hmgpu_rdoq_job* d_jobs, int qp_per, int qp_rem, int32_t* d_coef);
 void hmgpu_rdoq_scan_table(uint16_t* tab);      // 4335 words, layout in rdoq_impl.cuh
 
 // ---------------------------------------------------------------------------------------

@@ -196,6 +196,37 @@ int hmgpu_launch_quant(hmgpu_ctx* ctx, const int32_t* d_coeff, int n_tus, int n,
   return HMGPU_OK;
 }
 
+// xDeQuant (TComTrQuant.cpp:1203-1313), the branch without scaling lists (:1276-1311): level x g_invQuantScales[rem], rounded and
+// shifted right by IQUANT_SHIFT - (transform shift + per) -- or left when that is not positive -- between the clip of the input
+// to what the 32-bit intermediate carries and the clip of the output to the 16-bit transform range.  One thread per coefficient;
+// the QP of a TU comes from its RDOQ job (hmgpu_residual_tus) or is the same for the whole call (hmgpu_dequant).
+__global__ void dequant_kernel(const int32_t* __restrict__ level, size_t total, int nn, int transform_shift, const hmgpu_rdoq_job* __restrict__ jobs,
+                               int qp_per, int qp_rem, int32_t* __restrict__ coef)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (jobs) { const hmgpu_rdoq_job* j = jobs + i / nn; qp_per = j->qp_per; qp_rem = j->qp_rem; }
+  const int scale = qp_rem == 0 ? 40 : qp_rem == 1 ? 45 : qp_rem == 2 ? 51 : qp_rem == 3 ? 57 : qp_rem == 4 ? 64 : 72;     // g_invQuantScales
+  const int right_shift = 6 - (transform_shift + qp_per);
+  const int target = min(16, 32 + right_shift - 7);
+  const int q = min((1 << (target - 1)) - 1, max(-(1 << (target - 1)), level[i]));
+  int v;
+  if (right_shift > 0) v = (q * scale + (1 << (right_shift - 1))) >> right_shift;
+  else v = (int)((unsigned)(q * scale) << -right_shift);
+  coef[i] = min(32767, max(-32768, v));
+}
+
+int hmgpu_launch_dequant(hmgpu_ctx* ctx, const int32_t* d_level, int n_tus, int n, const hmgpu_rdoq_job* d_jobs, int qp_per, int qp_rem, int32_t* d_coef)
+{
+  int log2n = 0;
+  while ((1 << log2n) < n) log2n++;
+  const size_t total = (size_t)n_tus * n * n;
+  HmgpuStage st(ctx, HMGPU_ST_QUANT, 1);
+  dequant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_level, total, n * n, 15 - ctx->bit_depth - log2n, d_jobs, qp_per, qp_rem, d_coef);
+  HMGPU_CUDA(ctx, cudaGetLastError());
+  return HMGPU_OK;
+}
+
 template <typename Px>
 __global__ void mc_luma_kernel(const hmgpu_mc_job* __restrict__ jobs, RefTable refs, int16_t* __restrict__ dst)
 {

@@ -58,7 +58,7 @@ EXPORTS = [
     "hmgpu_ref_download_plane", "hmgpu_ref_upload_device", "hmgpu_org_upload", "hmgpu_org_upload_device",
     "hmgpu_me_search", "hmgpu_me_submit", "hmgpu_me_wait", "hmgpu_pu_submit", "hmgpu_pu_wait", "hmgpu_me_search_device", "hmgpu_clip_bounds", "hmgpu_search_range",
     "hmgpu_dist_batch", "hmgpu_intra_costs", "hmgpu_sao_stats", "hmgpu_sao_apply", "hmgpu_deblock", "hmgpu_mv_bits", "hmgpu_mv_cost", "hmgpu_mc_luma", "hmgpu_predict", "hmgpu_pred_error", "hmgpu_merge_skip_dist", "hmgpu_fwd_transform", "hmgpu_inv_transform",
-    "hmgpu_quant", "hmgpu_rdoq", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
+    "hmgpu_quant", "hmgpu_rdoq", "hmgpu_dequant", "hmgpu_residual_tus", "hmgpu_profile_enable", "hmgpu_profile_stage_count", "hmgpu_profile_stage_name",
     "hmgpu_profile_read", "hmgpu_microbench"]
 
 _lib = None
@@ -127,6 +127,8 @@ def lib():
     L.hmgpu_inv_transform.argtypes = [vp, vp, ci, ci, ci, vp]
     L.hmgpu_quant.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.hmgpu_rdoq.argtypes = [vp, vp, ci, vp, ci, vp, ci, vp, vp]
+    L.hmgpu_dequant.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.hmgpu_residual_tus.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci, vp, vp, vp, vp]
     L.hmgpu_profile_enable.argtypes = [vp, ci]
     L.hmgpu_profile_stage_name.argtypes = [ci]
     L.hmgpu_profile_stage_name.restype = C.c_char_p
@@ -430,3 +432,25 @@ class Context:
         self._check(self.L.hmgpu_rdoq(self.h, jobs.ctypes.data, len(jobs), bits.ctypes.data, len(bits), coef.ctypes.data, coef.size,
                                       level.ctypes.data, abs_sum.ctypes.data))
         return level, abs_sum
+
+    def dequant(self, level, n, qp_per, qp_rem):
+        """hmgpu_dequant: [n_tus, n, n] levels -> transform coefficients (xDeQuant, flat quantiser)"""
+        level = np.ascontiguousarray(level, np.int32).reshape(-1, n, n)
+        coef = np.zeros_like(level)
+        self._check(self.L.hmgpu_dequant(self.h, level.ctypes.data, level.shape[0], n, qp_per, qp_rem, coef.ctypes.data))
+        return coef
+
+    def residual_tus(self, resi, n, jobs, bits, use_dst=False):
+        """hmgpu_residual_tus: transform + RDOQ + dequantisation + inverse transform + distortions of [n_tus, n, n] residual blocks
+        -> (levels, uiAbsSum, reconstructed residuals, distortions [n_tus, 2] = (coded, nothing coded))"""
+        resi = np.ascontiguousarray(resi, np.int16).reshape(-1, n, n)
+        jobs = np.ascontiguousarray(jobs, RDOQ_JOB).ravel()
+        bits = np.ascontiguousarray(bits, RDOQ_BITS).ravel()
+        assert len(jobs) == resi.shape[0]
+        level = np.zeros(resi.shape, np.int32)
+        abs_sum = np.zeros(len(jobs), np.int32)
+        rec = np.zeros(resi.shape, np.int16)
+        dist = np.zeros((len(jobs), 2), np.uint32)
+        self._check(self.L.hmgpu_residual_tus(self.h, resi.ctypes.data, resi.shape[0], n, int(use_dst), jobs.ctypes.data, bits.ctypes.data, len(bits),
+                                              level.ctypes.data, abs_sum.ctypes.data, rec.ctypes.data, dist.ctypes.data))
+        return level, abs_sum, rec, dist

@@ -411,6 +411,27 @@ typedef struct hmgpu_rdoq_job {
 int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmgpu_rdoq_bits* bits, int n_bits,
                const int32_t* coef, int n_coef, int32_t* level, int32_t* abs_sum);
 
+/* hmgpu_dequant replaces TComTrQuant::xDeQuant (TComTrQuant.cpp:1203-1313; called from invTransformNxN :1495) for square TUs with
+ * the flat quantiser (no scaling lists), no transform skip, no extended precision: n_tus blocks of n x n levels in, n x n
+ * transform coefficients out, one QP (per, rem) for the call.  Bit depth: the context's. */
+int hmgpu_dequant(hmgpu_ctx* ctx, const int32_t* level, int n_tus, int n, int qp_per, int qp_rem, int32_t* coef);
+
+/* ------------------------------------------------------------------------------------------
+ * The residual-costing loop for a batch of TUs of one size, without leaving the device.
+ * hmgpu_residual_tus does for every TU what TEncSearch::xEstimateResidualQT (TEncSearch.cpp:4680-5310) asks of TComTrQuant per
+ * component: transformNxN (TComTrQuant.cpp:1341-1432: xT :1805, then the RDOQ branch of xQuant :1074-1118), invTransformNxN
+ * (:1435-1530: xDeQuant :1203, xIT :1830) and the two distortions it then compares (getDistPart with DF_SSE, TComRdCost.cpp:
+ * 970-1315): the residual against its reconstruction and against nothing coded.  The bits of the coefficients (CABAC estimate),
+ * the chroma distortion weight and calcRdCost stay the host's.
+ *   resi        n_tus blocks of n x n residual Pel, contiguous
+ *   jobs[i]     the quantiser of TU i as for hmgpu_rdoq; log2_size must say n, coef_offset must be i * n * n, bit_depth the context's
+ *   level       n_tus x n x n levels;  abs_sum[i] = uiAbsSum of TU i
+ *   rec_resi    n_tus blocks of the reconstructed residual (zeros where nothing was coded)
+ *   dist[2i]    SSE(resi, rec_resi) of TU i;  dist[2i + 1] = SSE(resi, 0)
+ * ------------------------------------------------------------------------------------------ */
+int hmgpu_residual_tus(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, int use_dst, const hmgpu_rdoq_job* jobs,
+                       const hmgpu_rdoq_bits* bits, int n_bits, int32_t* level, int32_t* abs_sum, int16_t* rec_resi, uint32_t* dist);
+
 #ifdef __cplusplus
 }
 #endif

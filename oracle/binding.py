@@ -114,6 +114,7 @@ def oracle():
     L.hmo_rdoq.restype = ci
     L.hmo_rdoq.argtypes = [vp, vp, i32p, i32p]
     L.hmo_scan_order.argtypes = [ci, ci, vp, vp]
+    L.hmo_dequant.argtypes = [i32p, ci, ci, ci, ci, ci, i32p]
     _oracle = L
     return L
 
@@ -215,3 +216,11 @@ def me_batch(lib_fn, jobs, refs_padded, org, bit_depth, org_blocks=None, margin=
 def ptr(a, off=0):
     """address of element `off` of a contiguous int16/int32 numpy array"""
     return a.ctypes.data + off * a.itemsize
+
+
+def dequant(level, log2_size, qp_per, qp_rem, bit_depth):
+    """hmo_dequant on one TU: levels (int32 raster) -> transform coefficients"""
+    level = np.ascontiguousarray(level, np.int32).ravel()
+    coef = np.zeros_like(level)
+    oracle().hmo_dequant(level, level.size, log2_size, qp_per, qp_rem, bit_depth, coef)
+    return coef

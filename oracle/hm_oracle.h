@@ -83,6 +83,10 @@ void hmo_inv_transform(int bit_depth, const int32_t* coeff, int32_t* block, int 
 uint32_t hmo_quant(const int32_t* coef, int n_coef, int qp_per, int qp_rem, int transform_shift,
                    int is_intra_slice, int32_t* level, int32_t* delta_u);
 
+/* xDeQuant (TComTrQuant.cpp:1203-1313), flat quantiser (no scaling lists), no transform skip / extended precision:
+   levels -> transform coefficients of a square TU of 2^log2_size samples a side, clipped to the 16-bit transform range */
+void hmo_dequant(const int32_t* level, int n_coef, int log2_size, int qp_per, int qp_rem, int bit_depth, int32_t* coef);
+
 /* ---- intra mode pre-selection: prediction of one luma mode + the 35 distortions of estIntraPredQT's first pass ----
  * line: the 4n+1 reference samples of the PU in the order initAdiPatternChType walks them (TComPattern.cpp:225-330):
  * line[0] = bottom-left neighbour ... line[2n-1] = left neighbour of row 0, line[2n] = top-left corner,

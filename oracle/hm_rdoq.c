@@ -374,3 +374,28 @@ int hmo_rdoq(const hmo_rdoq_tu* tu, const hmo_rdoq_bits* eb, const int32_t* coef
   }
   return abs_sum;
 }
+
+
+/* ---- xDeQuant (TComTrQuant.cpp:1203-1313), the branch without scaling lists (:1276-1311) ------------------------------------
+   rightShift = IQUANT_SHIFT - (transform shift + per) with transform shift = 15 - bitDepth - log2 (getTransformShift,
+   TComTrQuant.h); the level is clipped to the input range the 32-bit intermediate can carry (:1284-1286), multiplied by
+   g_invQuantScales[rem], rounded and shifted right -- or shifted left when rightShift <= 0 -- and clipped to [-32768, 32767].
+   Intermediate_Int is a 32-bit int in this build (TypeDef.h:696). */
+void hmo_dequant(const int32_t* level, int n_coef, int log2_size, int qp_per, int qp_rem, int bit_depth, int32_t* coef)
+{
+  static const int inv_scale[6] = { 40, 45, 51, 57, 64, 72 };              /* g_invQuantScales (TComRom.cpp) */
+  const int transform_shift = 15 - bit_depth - log2_size;
+  const int right_shift = 6 - (transform_shift + qp_per);                 /* IQUANT_SHIFT = 6 */
+  const int scale = inv_scale[qp_rem], scale_bits = 6 + 1;
+  int target = 32 + right_shift - scale_bits;
+  if (target > 16) target = 16;
+  const int32_t in_min = -(1 << (target - 1)), in_max = (1 << (target - 1)) - 1;
+  for (int i = 0; i < n_coef; i++)
+  {
+    int32_t q = level[i] < in_min ? in_min : level[i] > in_max ? in_max : level[i];
+    int32_t v;
+    if (right_shift > 0) v = (q * scale + (1 << (right_shift - 1))) >> right_shift;
+    else v = (int32_t)((uint32_t)(q * scale) << -right_shift);
+    coef[i] = v < -32768 ? -32768 : v > 32767 ? 32767 : v;
+  }
+}

@@ -70,3 +70,31 @@ def supported(c):
     """the configurations hmo_rdoq / hmgpu_rdoq restate (every call of the BASELINE cfgs)"""
     return (c["w"] == c["h"] and not c["scaling_lists"] and not c["ext_precision"] and not c["go_rice_adapt"]
             and c["max_dyn_range"] == 15 and not c["adapt_qp_select"])
+
+
+# ---- xDeQuant dumps (oracle/rdoq_dump.inc, hm_deq_after) ----------------------------------------------------------------------
+DEQ_HDR = ("w", "h", "log2", "channel", "per", "rem", "bit_depth", "max_dyn_range", "scaling_lists", "tskip", "ext_precision", "spare")
+
+
+def read_dequant(path):
+    """-> list of calls of TComTrQuant::xDeQuant: header fields by name, 'level' (what it was given), 'coef' (what it produced)"""
+    data = open(path, "rb").read()
+    pos, calls = 0, []
+    while pos < len(data):
+        if data[pos:pos + 1] != b"D":
+            raise ValueError("bad record tag at %d" % pos)
+        pos += 1
+        c = {k: int(v) for k, v in zip(DEQ_HDR, np.frombuffer(data, np.int32, 12, pos))}
+        pos += 48
+        n = c["w"] * c["h"]
+        c["level"] = np.frombuffer(data, np.int32, n, pos).copy()
+        pos += 4 * n
+        c["coef"] = np.frombuffer(data, np.int32, n, pos).copy()
+        pos += 4 * n
+        calls.append(c)
+    return calls
+
+
+def dequant_supported(c):
+    """what hmo_dequant / hmgpu_dequant restate: square TUs, flat quantiser, no transform skip, no extended precision"""
+    return c["w"] == c["h"] and not c["scaling_lists"] and not c["tskip"] and not c["ext_precision"] and c["max_dyn_range"] == 15

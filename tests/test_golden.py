@@ -202,3 +202,29 @@ def test_scan_orders():
     assert scan.tolist() == list(range(16))
     O.hmo_scan_order(2, 2, scan.ctypes.data, cg.ctypes.data)
     assert scan.tolist() == [0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15]
+
+
+def dequant_golden_calls():
+    """tests/golden/dequant_golden.npz -> the dumped calls of the reference's xDeQuant (tests/golden/make_dequant_golden.py)"""
+    import rdoqdump
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dequant_golden.npz"))
+    calls = []
+    for i in range(len(z["hdr"])):
+        c = {k: int(v) for k, v in zip(rdoqdump.DEQ_HDR, z["hdr"][i])}
+        a, b = int(z["offset"][i]), int(z["offset"][i + 1])
+        c["level"], c["coef"] = z["level"][a:b], z["coef"][a:b]
+        calls.append(c)
+    return calls
+
+
+def test_dequant_oracle_matches_reference_encoder_calls():
+    """hmo_dequant against what the instrumented reference encoder's xDeQuant produced: every TU size, 8 and 10 bit, QPs on both
+    sides of the point where the right shift turns into a left shift"""
+    from oracle import binding as B
+    calls = dequant_golden_calls()
+    shifts = set()
+    for i, c in enumerate(calls):
+        got = B.dequant(c["level"], c["log2"], c["per"], c["rem"], c["bit_depth"])
+        assert np.array_equal(got, c["coef"]), (i, {k: c[k] for k in ("w", "per", "rem", "bit_depth")})
+        shifts.add(6 - (15 - c["bit_depth"] - c["log2"] + c["per"]))
+    assert len(calls) >= 300 and min(shifts) < 0 < max(shifts)
