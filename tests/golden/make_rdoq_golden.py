@@ -38,7 +38,7 @@ def dump_case(cfg, w, h, frames, qp, bd, extra, every, tmp, tag):
     yuv = synth.write_yuv(os.path.join(tmp, tag + ".yuv"), w, h, frames, bd, seed=31 + len(tag))
     dump = os.path.join(tmp, tag + ".dump")
     cmd = [ENC, "-c", os.path.join(CFG, cfg), "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-f", str(frames), "-q", str(qp),
-           "-b", os.path.join(tmp, tag + ".bin")]
+           "-b", os.path.join(tmp, tag + ".bin"), "-o", os.path.join(tmp, tag + ".rec.yuv")]
     if bd != 8:
         cmd += ["--InputBitDepth=%d" % bd]
     subprocess.run(cmd + extra, check=True, capture_output=True, env=dict(os.environ, HM_RDOQ_DUMP=dump, HM_RDOQ_EVERY=str(every)))

@@ -106,3 +106,21 @@ def test_kernel_body_on_random_tus_against_oracle(emul):
         assert s == want_sum and np.array_equal(level, want), (i, {k: c[k] for k in rdoqdump.HDR})
         changed += int(np.abs(want).sum() != want_sum)
     assert changed > 50
+
+
+def test_golden_batch_is_the_dumped_calls():
+    """hm-16.2_b200/rdoq_batch.py (bench.py's rdoq leg, smoke()) builds the same jobs / coefficients / levels as the dump reader"""
+    import rdoq_batch
+    from test_gpu_rdoq import batch_of
+    calls = rdoq_golden_calls()
+    jobs1, bits1, coef1 = batch_of(calls)
+    jobs, bits, coef, level, abs_sum = rdoq_batch.golden_batch(2)
+    n, n1 = len(jobs1), coef1.size
+    assert len(jobs) == 2 * n and coef.size == 2 * n1 and np.array_equal(coef[:n1], coef1) and np.array_equal(coef[n1:], coef1)
+    for f in jobs1.dtype.names:
+        if f not in ("bits_index", "coef_offset"):
+            assert np.array_equal(jobs[f][:n], jobs1[f]) and np.array_equal(jobs[f][n:], jobs1[f]), f
+    assert np.array_equal(jobs["coef_offset"][:n], jobs1["coef_offset"]) and np.array_equal(jobs["coef_offset"][n:].astype(np.int64), jobs1["coef_offset"].astype(np.int64) + n1)
+    for i in range(n):
+        assert bits[jobs["bits_index"][i]].tobytes() == bits1[jobs1["bits_index"][i]].tobytes(), i
+    assert np.array_equal(level[:n1], np.concatenate([c["level"] for c in calls])) and np.array_equal(abs_sum[:n], [c["abs_sum"] for c in calls])
