@@ -359,13 +359,13 @@ int hmgpu_merge_skip_dist(hmgpu_ctx* ctx, const hmgpu_pred_job* jobs, int n_jobs
  * fastForwardDst (TComTrQuant.cpp:1805-1827, 836-885, 387-758).  Input: n_tus residual
  * blocks of n x n Pel, each contiguous row-major; output n x n TCoeff each.
  * hmgpu_quant replaces the scalar branch of TComTrQuant::xQuant (TComTrQuant.cpp:1120-1199,
- * flat scaling list, no sign hiding); RDOQ stays on the host.
+ * flat scaling list, no sign hiding); the RDOQ branch is hmgpu_rdoq below.
  * ------------------------------------------------------------------------------------------ */
 int hmgpu_fwd_transform(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, int use_dst,
                         int32_t* coeff);
 /* hmgpu_inv_transform replaces TComTrQuant::xIT -> xITrMxN -> partialButterflyInverse4/8/16/32 / fastInverseDst
  * (TComTrQuant.cpp:1830-1850, 894-960, 437-810): n_tus blocks of n x n TCoeff in, n x n residual Pel out (the reconstruction
- * side of the residual-costing loop; dequantisation and RDOQ stay on the host). */
+ * side of the residual-costing loop; hmgpu_dequant and hmgpu_residual_tus below complete it). */
 int hmgpu_inv_transform(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int use_dst, int16_t* resi);
 int hmgpu_quant(hmgpu_ctx* ctx, const int32_t* coeff, int n_tus, int n, int qp_per, int qp_rem,
                 int is_intra_slice, int32_t* level, int32_t* delta_u, uint32_t* abs_sum);
@@ -413,7 +413,8 @@ int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmg
 
 /* hmgpu_dequant replaces TComTrQuant::xDeQuant (TComTrQuant.cpp:1203-1313; called from invTransformNxN :1495) for square TUs with
  * the flat quantiser (no scaling lists), no transform skip, no extended precision: n_tus blocks of n x n levels in, n x n
- * transform coefficients out, one QP (per, rem) for the call.  Bit depth: the context's. */
+ * transform coefficients out, one QP (per, rem) for the call.  Bit depth: the context's.  (Transform-skipped TUs are dequantised
+ * by the same arithmetic while extended precision is off.) */
 int hmgpu_dequant(hmgpu_ctx* ctx, const int32_t* level, int n_tus, int n, int qp_per, int qp_rem, int32_t* coef);
 
 /* ------------------------------------------------------------------------------------------

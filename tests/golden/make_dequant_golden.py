@@ -32,7 +32,7 @@ CASES = [
     ("encoder_randomaccess_main10.cfg", 176, 144, 2, 45, 10, 3),
     ("encoder_intra_main.cfg", 136, 72, 1, 51, 8, 1),
 ]
-PER_CLASS = 4          # calls kept per (case, size, channel, per, rem)
+PER_CLASS = 4          # calls kept per (case, size, channel, per, rem, transform skip)
 
 
 def dump_case(cfg, w, h, frames, qp, bd, every, tmp, tag):
@@ -53,7 +53,7 @@ def main():
             calls = [c for c in dump_case(cfg, w, h, frames, qp, bd, every, tmp, "case%d" % i) if rdoqdump.dequant_supported(c)]
             groups = collections.defaultdict(list)
             for c in calls:
-                groups[(c["log2"], c["channel"], c["per"], c["rem"])].append(c)
+                groups[(c["log2"], c["channel"], c["per"], c["rem"], c["tskip"])].append(c)
             sel = []
             for key in sorted(groups):       # the busiest calls of every class first
                 sel += sorted(groups[key], key=lambda c: -int(np.abs(c["level"]).sum()))[:PER_CLASS]

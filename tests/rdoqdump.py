@@ -96,5 +96,6 @@ def read_dequant(path):
 
 
 def dequant_supported(c):
-    """what hmo_dequant / hmgpu_dequant restate: square TUs, flat quantiser, no transform skip, no extended precision"""
-    return c["w"] == c["h"] and not c["scaling_lists"] and not c["tskip"] and not c["ext_precision"] and c["max_dyn_range"] == 15
+    """what hmo_dequant / hmgpu_dequant restate: square TUs, flat quantiser, no extended precision (transform-skipped TUs are
+    dequantised by the same arithmetic as long as extended precision is off)"""
+    return c["w"] == c["h"] and not c["scaling_lists"] and not c["ext_precision"] and c["max_dyn_range"] == 15

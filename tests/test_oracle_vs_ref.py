@@ -274,7 +274,8 @@ def test_inverse_transform(bd):
 
 def test_rdoq_against_instrumented_encoder_live():
     """f1: a fresh encode (content, size and QP not among the golden calls) by the instrumented reference encoder
-    (oracle/_ref/TAppEncoderRdoq, oracle/Makefile target `rdoq`); hmo_rdoq reproduces every sampled call of xRateDistOptQuant."""
+    (oracle/_ref/TAppEncoderRdoq, oracle/Makefile target `rdoq`); hmo_rdoq reproduces every sampled call of xRateDistOptQuant and
+    hmo_dequant every sampled call of xDeQuant."""
     import os
     import subprocess
     import tempfile
@@ -287,9 +288,12 @@ def test_rdoq_against_instrumented_encoder_live():
     with tempfile.TemporaryDirectory(prefix="hmrdoq_") as tmp:
         yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), 208, 120, 3, 8, seed=991)
         dump = os.path.join(tmp, "s.dump")
-        subprocess.run([enc, "-c", cfg, "-i", yuv, "-wdt", "208", "-hgt", "120", "-fr", "30", "-f", "3", "-q", "26", "-b", os.path.join(tmp, "s.bin")],
-                       check=True, capture_output=True, env=dict(os.environ, HM_RDOQ_DUMP=dump, HM_RDOQ_EVERY="11"))
+        deq_dump = os.path.join(tmp, "d.dump")
+        subprocess.run([enc, "-c", cfg, "-i", yuv, "-wdt", "208", "-hgt", "120", "-fr", "30", "-f", "3", "-q", "26", "-b", os.path.join(tmp, "s.bin"),
+                        "-o", os.path.join(tmp, "rec.yuv")],
+                       check=True, capture_output=True, env=dict(os.environ, HM_RDOQ_DUMP=dump, HM_RDOQ_EVERY="11", HM_DEQ_DUMP=deq_dump, HM_DEQ_EVERY="7"))
         calls = rdoqdump.read(dump)
+        deq_calls = rdoqdump.read_dequant(deq_dump)
     assert len(calls) > 5000
     coded = 0
     for i, c in enumerate(calls):
@@ -299,3 +303,8 @@ def test_rdoq_against_instrumented_encoder_live():
         assert abs_sum == c["abs_sum"] and np.array_equal(level, c["level"]), (i, {k: c[k] for k in rdoqdump.HDR})
         coded += int(abs_sum > 0)
     assert coded > 1000
+    # the same encode's calls of xDeQuant (hook hm_deq_after) against hmo_dequant
+    assert len(deq_calls) > 1000
+    for i, c in enumerate(deq_calls):
+        assert rdoqdump.dequant_supported(c)
+        assert np.array_equal(B.dequant(c["level"], c["log2"], c["per"], c["rem"], c["bit_depth"]), c["coef"]), (i, {k: c[k] for k in rdoqdump.DEQ_HDR})
