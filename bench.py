@@ -417,21 +417,45 @@ def rdoq_leg(local_rank, steps, rep=64):
         obits = np.zeros(len(bits), B.RDOQ_BITS)
         for f in obits.dtype.names:
             obits[f] = bits[f]
-        n1 = n_coef // rep
+        n1, m = n_coef // rep, len(tus)
         t0, loops, bad = time.perf_counter(), 0, 0
         while time.perf_counter() - t0 < 3.0:
-            for i in range(len(tus)):
-                a = int(jobs["coef_offset"][i])
-                k = int(jobs["bits_index"][i])
-                lv, sm = B.rdoq(tus[i:i + 1], obits[k:k + 1], coef[a:a + (1 << (2 * int(tus["log2_size"][i])))])
-                bad += int(sm != want_sum[i])
+            lv, total = B.rdoq_batch(tus, jobs["bits_index"][:m], jobs["coef_offset"][:m], obits, coef[:n1])
+            bad += int(not np.array_equal(lv, want[:n1])) + int(total != int(want_sum[:m].sum()))
             loops += 1
         cpu = (time.perf_counter() - t0) / loops
         out["cpu_baseline"] = {"value": n1 / cpu / 1e6, "unit": "Mcoef/s", "cores": 1, "kind": "port", "mismatches": bad,
-                               "sample": "the %d calls once per pass, %d passes, oracle/hm_rdoq.c through ctypes" % (len(tus), loops)}
+                               "sample": "the %d calls once per pass, %d passes, oracle/hm_rdoq.c (hmo_rdoq_batch: one C call per pass)" % (m, loops)}
     except Exception as e:                                          # (the oracle is the checker: its timing is a reported extra)
         out["cpu_baseline"] = {"unavailable": repr(e)}
+    out["cpu_reference_encoder"] = rdoq_reference_speed()
     return out
+
+
+def rdoq_reference_speed():
+    """the reference's own xRateDistOptQuant on this host: a short encode by the instrumented reference encoder
+    (oracle/_ref/TAppEncoderRdoq, HM_RDOQ_TIME: seconds between the two hooks around the call, summed over the encode).  Its mix of
+    TUs is the encode's own (many TUs quantise to nothing and return early), not the bench batch: a second reported baseline."""
+    import synth
+    import tempfile
+    enc = os.path.join(ROOT, "oracle", "_ref", "TAppEncoderRdoq")
+    cfg = os.path.join(ROOT, "oracle", "_ref", "cfg", "encoder_lowdelay_P_main.cfg")
+    if not (os.path.exists(enc) and os.path.exists(cfg)):
+        return {"unavailable": "oracle/_ref/TAppEncoderRdoq not built"}
+    try:
+        with tempfile.TemporaryDirectory(prefix="hmrdoq_") as tmp:
+            yuv = synth.write_yuv(os.path.join(tmp, "in.yuv"), 416, 240, 3, 8, seed=5)
+            tf = os.path.join(tmp, "time.txt")
+            t0 = time.perf_counter()
+            subprocess.run([enc, "-c", cfg, "-i", yuv, "-wdt", "416", "-hgt", "240", "-fr", "30", "-f", "3", "-q", "32", "-b", os.path.join(tmp, "s.bin"),
+                            "-o", os.path.join(tmp, "rec.yuv")], check=True, capture_output=True, env=dict(os.environ, HM_RDOQ_TIME=tf), timeout=120)
+            wall = time.perf_counter() - t0
+            calls, coefs, secs = open(tf).read().split()
+        return {"value": int(coefs) / float(secs) / 1e6, "unit": "Mcoef/s", "cores": 1, "kind": "reference", "calls": int(calls), "coefficients": int(coefs),
+                "seconds_in_rdoq": float(secs), "encode_s": wall,
+                "sample": "encoder_lowdelay_P_main.cfg 416x240 3 frames QP32: every xRateDistOptQuant call of the encode, timed inside the reference encoder"}
+    except Exception as e:
+        return {"unavailable": repr(e)}
 
 
 def real_stream_leg(local_rank, frames=3):

@@ -115,6 +115,8 @@ def oracle():
     L.hmo_rdoq.argtypes = [vp, vp, i32p, i32p]
     L.hmo_scan_order.argtypes = [ci, ci, vp, vp]
     L.hmo_dequant.argtypes = [i32p, ci, ci, ci, ci, ci, i32p]
+    L.hmo_rdoq_batch.restype = C.c_longlong
+    L.hmo_rdoq_batch.argtypes = [vp, i32p, vp, ci, vp, i32p, i32p]
     _oracle = L
     return L
 
@@ -224,3 +226,15 @@ def dequant(level, log2_size, qp_per, qp_rem, bit_depth):
     coef = np.zeros_like(level)
     oracle().hmo_dequant(level, level.size, log2_size, qp_per, qp_rem, bit_depth, coef)
     return coef
+
+
+def rdoq_batch(tus, bits_index, coef_offset, bits, coef):
+    """hmo_rdoq_batch: every TU of `tus` (RDOQ_TU records) in one C call -> (levels laid out like coef, sum of the uiAbsSum values)"""
+    tus = np.ascontiguousarray(tus, RDOQ_TU)
+    bits = np.ascontiguousarray(bits, RDOQ_BITS)
+    bits_index = np.ascontiguousarray(bits_index, np.int32)
+    coef_offset = np.ascontiguousarray(coef_offset, np.uint32)
+    coef = np.ascontiguousarray(coef, np.int32)
+    level = np.zeros_like(coef)
+    total = oracle().hmo_rdoq_batch(tus.ctypes.data, bits_index, coef_offset.ctypes.data, len(tus), bits.ctypes.data, coef, level)
+    return level, int(total)

@@ -144,6 +144,8 @@ typedef struct hmo_rdoq_tu {
 } hmo_rdoq_tu;
 /* coef, level: raster, pitch = width; returns uiAbsSum */
 int hmo_rdoq(const hmo_rdoq_tu* tu, const hmo_rdoq_bits* bits, const int32_t* coef, int32_t* level);
+long long hmo_rdoq_batch(const hmo_rdoq_tu* tus, const int32_t* bits_index, const uint32_t* coef_offset, int n_tus,
+                         const hmo_rdoq_bits* bits, const int32_t* coef, int32_t* level);
 /* scan[k] = raster position of the k-th coefficient (SCAN_GROUPED_4x4), scan_cg[i] = raster index of the i-th coefficient group */
 void hmo_scan_order(int log2_size, int scan_type, uint16_t* scan, uint16_t* scan_cg);
 

@@ -399,3 +399,15 @@ void hmo_dequant(const int32_t* level, int n_coef, int log2_size, int qp_per, in
     coef[i] = v < -32768 ? -32768 : v > 32767 ? 32767 : v;
   }
 }
+
+
+/* many TUs in one call: TU i reads coef + coef_offset[i], writes level + coef_offset[i] and uses bits[bits_index[i]]; returns the
+   sum of the uiAbsSum values.  (bench.py's cpu_baseline of the rdoq leg: the restatement timed without the binding's per-call cost) */
+long long hmo_rdoq_batch(const hmo_rdoq_tu* tus, const int32_t* bits_index, const uint32_t* coef_offset, int n_tus,
+                         const hmo_rdoq_bits* bits, const int32_t* coef, int32_t* level)
+{
+  long long total = 0;
+  for (int i = 0; i < n_tus; i++)
+    total += hmo_rdoq(&tus[i], &bits[bits_index[i]], coef + coef_offset[i], level + coef_offset[i]);
+  return total;
+}
