@@ -1936,6 +1936,7 @@ int hmgpu_rdoq(hmgpu_ctx* ctx, const hmgpu_rdoq_job* jobs, int n_jobs, const hmg
   if (n_jobs == 0) return HMGPU_OK;
   if (!jobs || !bits || !coef || !level || !abs_sum || n_jobs < 0 || n_bits <= 0 || n_coef < 0) return hmgpu_fail(ctx, HMGPU_E_INVALID, "NULL argument");
   HMGPU_NOT_REMOTE(ctx, "hmgpu_rdoq");
+  if (ctx->pend_n || ctx->pend_np || ctx->defer_n || ctx->defer_np) return hmgpu_fail(ctx, HMGPU_E_STATE, "a submitted search is outstanding: wait for it first");
   int n_class[4] = { 0, 0, 0, 0 };
   { const int rcv = rdoq_check_jobs(ctx, jobs, n_jobs, n_bits, n_coef, n_class); if (rcv) return rcv; }
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1988,6 +1989,7 @@ int hmgpu_dequant(hmgpu_ctx* ctx, const int32_t* level, int n_tus, int n, int qp
   if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
   if (qp_rem < 0 || qp_rem > 5 || qp_per < 0 || qp_per > 12) return hmgpu_fail(ctx, HMGPU_E_INVALID, "bad qp per/rem");
   HMGPU_NOT_REMOTE(ctx, "hmgpu_dequant");
+  if (ctx->pend_n || ctx->pend_np || ctx->defer_n || ctx->defer_np) return hmgpu_fail(ctx, HMGPU_E_STATE, "a submitted search is outstanding: wait for it first");
   HMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t elems = (size_t)n_tus * n * n, b0 = round_up(sizeof(int32_t) * elems, 256);
   HMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2013,6 +2015,7 @@ int hmgpu_residual_tus(hmgpu_ctx* ctx, const int16_t* resi, int n_tus, int n, in
   if (n != 4 && n != 8 && n != 16 && n != 32) return hmgpu_fail(ctx, HMGPU_E_INVALID, "transform size %d not in {4,8,16,32}", n);
   if (use_dst && n != 4) return hmgpu_fail(ctx, HMGPU_E_INVALID, "the DST exists for 4x4 TUs only");
   HMGPU_NOT_REMOTE(ctx, "hmgpu_residual_tus");
+  if (ctx->pend_n || ctx->pend_np || ctx->defer_n || ctx->defer_np) return hmgpu_fail(ctx, HMGPU_E_STATE, "a submitted search is outstanding: wait for it first");
   const int nn = n * n, log2n = n == 4 ? 2 : n == 8 ? 3 : n == 16 ? 4 : 5;
   const size_t elems = (size_t)n_tus * nn;
   if (elems > 0x7fffffffu) return hmgpu_fail(ctx, HMGPU_E_INVALID, "%d TUs of %d x %d: more than 2^31 coefficients in one call", n_tus, n, n);
