@@ -481,10 +481,13 @@ RQ_HD void rq_hide_signs(const hmgpu_rdoq_job& j, const uint16_t* scan, const in
 #else
 #define RQ_PREFETCH(p) ((void)(p))
 #define RQ_UNROLL
+#ifndef RQ_WARP_MAX      // (tests/rdoq_emul_warp.cpp brings its own: 32 host threads as the lanes of a warp, the device's strides)
 static int rq_ghost_top = -1;
 #define RQ_WARP_MAX(v) ((v) > rq_ghost_top ? (v) : rq_ghost_top)
 #define RQ_WARP_ANY(p) ((p) || rq_ghost_top >= 0)
 #define RQ2_STRIDE 1
+#define RQ2_EB_STRIDE 1
+#endif
 #endif
 #define RQ2_BYTES_PER_COEF 24
 
@@ -493,8 +496,6 @@ static int rq_ghost_top = -1;
 // the lane's own bank.
 #if defined(__CUDA_ARCH__)
 #define RQ2_EB_STRIDE 32
-#else
-#define RQ2_EB_STRIDE 1
 #endif
 struct Rq2Bits { const int32_t* p; };
 #define RQ2_EB(eb, i) ((eb).p[(i) * RQ2_EB_STRIDE])

@@ -124,3 +124,40 @@ def test_golden_batch_is_the_dumped_calls():
     for i in range(n):
         assert bits[jobs["bits_index"][i]].tobytes() == bits1[jobs1["bits_index"][i]].tobytes(), i
     assert np.array_equal(level[:n1], np.concatenate([c["level"] for c in calls])) and np.array_equal(abs_sum[:n], [c["abs_sum"] for c in calls])
+
+
+def test_a_warp_of_different_tus_in_lockstep():
+    """rdoq_tu_kernel's warp on the CPU (tests/rdoq_emul_warp.cpp): 32 threads = 32 lanes, real collectives, the device's strides.
+    The reference encoder's calls of one size, shuffled, 32 at a time (the last warp not full) -- and every TU comes out as the
+    reference returned it, whatever its neighbours were."""
+    from test_gpu_rdoq import batch_of
+    tmp = tempfile.mkdtemp(prefix="rdoq_warp_")
+    so = os.path.join(tmp, "librdoq_emul_warp.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-std=c++17", "-o", so, os.path.join(HERE, "rdoq_emul_warp.cpp")])
+    L = C.CDLL(so)
+    L.rdoq_emul_warp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    calls = rdoq_golden_calls()
+    jobs, bits, coef = batch_of(calls)
+    want = np.concatenate([c["level"] for c in calls])
+    want_sum = np.array([c["abs_sum"] for c in calls], np.int32)
+    level = np.zeros_like(coef)                       # (the kernel's level buffer starts out as zeros; only non-zero levels are stored)
+    abs_sum = np.full(len(jobs), -1, np.int32)
+    rng = np.random.default_rng(7)
+    warps = 0
+    for lg in (5, 4, 3, 2):
+        idx = rng.permutation(np.flatnonzero(jobs["log2_size"] == lg))
+        if lg == 2:
+            idx = idx[:200]                           # (enough of the smallest size: a warp of threads costs more than its 32 TUs)
+        for a in range(0, len(idx), 32):
+            sel = idx[a:a + 32]
+            wj = np.ascontiguousarray(jobs[sel])
+            ws = np.zeros(32, np.int32)
+            L.rdoq_emul_warp(wj.ctypes.data, len(sel), lg, bits.ctypes.data, coef.ctypes.data, level.ctypes.data, ws.ctypes.data)
+            abs_sum[sel] = ws[:len(sel)]
+            warps += 1
+        done = idx
+        assert np.array_equal(abs_sum[done], want_sum[done]), lg
+        for i in done:
+            o, n = int(jobs["coef_offset"][i]), 1 << (2 * lg)
+            assert np.array_equal(level[o:o + n], want[o:o + n]), (lg, int(i))
+    assert warps >= 20
